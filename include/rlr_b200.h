@@ -1,0 +1,290 @@
+/*
+ * rlr_b200.h -- C ABI of the B200-native retrieval hot path for rust-local-rag.
+ *
+ * This is the whole drop-in boundary.  The reference (CrashCartCapital/rust-local-rag)
+ * has no FFI/plugin interface for this path: the boundary is three methods of
+ * `RagEngine` (src/rag_engine.rs:470 `search`, :717 `search_with_diversity`, :415
+ * `get_embedding_candidates`).  A `-sys` crate binds the symbols below and
+ * `rag_engine.rs` keeps its method signatures; INTEGRATION.md shows the binding.
+ * Each entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - every function returns an `int` status (RLR_OK == 0); the message of the last
+ *     failure on the calling thread is `rlr_last_error()`.  Nothing unwinds or aborts
+ *     across the boundary; CUDA failures become RLR_ERR_CUDA.
+ *   - plain pointers and sizes only.  Host buffers are borrowed for the call; output
+ *     buffers are caller-allocated with the stated capacity.  The library owns all
+ *     device memory.
+ *   - rows are dense `uint32_t` positions into the caller's `row -> chunk_id` table
+ *     (the library never sees chunk ids, text or metadata).
+ *   - threading mirrors the reference's RwLock (src/mcp_server.rs:89,377 read lock;
+ *     src/worker.rs:397-437 write lock): every `rlr_search*` / `rlr_mmr*` /
+ *     `rlr_embedding_candidates` call is re-entrant on one store handle and may run
+ *     concurrently from several host threads; `rlr_store_*` mutators and
+ *     `rlr_store_destroy` require exclusivity.
+ *   - there is NO CPU fallback: without a usable sm_100 device every compute entry
+ *     point fails with RLR_ERR_NO_DEVICE.
+ *   - arithmetic: scores are bit-identical to the reference's f32 arithmetic
+ *     (strict left-to-right sums, separate multiply and add roundings -- see
+ *     DESIGN.md); exact-score ties are ordered "lower row first".
+ */
+#ifndef RLR_B200_H
+#define RLR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLR_ABI_VERSION 1
+
+/* status codes */
+#define RLR_OK                 0
+#define RLR_ERR_INVALID_ARG    1
+#define RLR_ERR_NO_DEVICE      2  /* no CUDA device / not sm_100 / extension unusable   */
+#define RLR_ERR_CUDA           3  /* a CUDA runtime/driver call or kernel failed         */
+#define RLR_ERR_OOM            4
+#define RLR_ERR_DIM_MISMATCH   5  /* deliberate deviation from :1778 (zip truncates)     */
+#define RLR_ERR_UNSUPPORTED    6
+#define RLR_ERR_NONFINITE      7  /* NaN/Inf in a query or in uploaded rows              */
+
+/* limits */
+#define RLR_MAX_TOP_K          100   /* src/mcp_server.rs:364 MAX_TOP_K                   */
+#define RLR_MAX_M              1024  /* max candidates one scan can return (>= 3*pool=900)*/
+#define RLR_MAX_DIM            4096
+
+typedef struct rlr_store rlr_store; /* opaque: one embedding model's chunk store on one GPU */
+
+/* QueryWeights (src/rag_engine.rs:1846-1863): four Option<f32>.  Bit i of `has`
+ * set means field i is Some(..): 0 embedding, 1 lexical, 2 reranker, 3 initial. */
+typedef struct rlr_query_weights {
+    float    embedding;
+    float    lexical;
+    float    reranker;
+    float    initial;
+    uint32_t has;
+} rlr_query_weights;
+
+/* ResolvedWeights (src/rag_engine.rs:1877-1896) */
+typedef struct rlr_resolved_weights {
+    float embedding;
+    float lexical;
+    float reranker;
+    float initial;
+} rlr_resolved_weights;
+
+typedef struct rlr_store_info {
+    uint64_t n_rows;        /* rows in this store (this shard)                           */
+    uint64_t row_base;      /* global row index of local row 0 (multi-GPU shards)        */
+    uint32_t dim;
+    uint32_t pitch;         /* floats per stored row (dim rounded up to 32, zero padded) */
+    int32_t  device;        /* CUDA ordinal                                              */
+    uint32_t flags;
+    uint64_t bytes_device;  /* device bytes held by the store                            */
+} rlr_store_info;
+
+typedef struct rlr_device_info {
+    int32_t  device;
+    int32_t  sm_count;
+    int32_t  cc_major, cc_minor;
+    uint64_t total_mem;
+    char     name[128];
+} rlr_device_info;
+
+/* per-call stage timings, from CUDA events recorded on the call's own stream */
+typedef struct rlr_timings {
+    float scan_ms;          /* fused scan + per-CTA top-M kernel                          */
+    float merge_ms;         /* cross-CTA merge + finalize                                 */
+    float mmr_ms;           /* pairwise-similarity + greedy selection kernels             */
+    float total_ms;         /* first launch to last launch on the device                  */
+    uint32_t launches;      /* kernels launched by the call                               */
+} rlr_timings;
+
+/* store flags */
+#define RLR_STORE_KEEP_F16      0x1u  /* also keep an f16 copy of the rows (config 5)      */
+#define RLR_STORE_CHECK_FINITE  0x2u  /* scan uploaded rows for NaN/Inf on the device      */
+
+/* search flags */
+#define RLR_QUERY_PRENORMALIZED 0x1u  /* skip the normalize(&mut q) of :494                */
+#define RLR_WANT_TIMINGS        0x2u  /* record CUDA events; read with rlr_last_timings    */
+
+/* synthetic fill kinds (bench / parity inputs) */
+#define RLR_SYNTH_IID           0
+#define RLR_SYNTH_CLUSTERED     1
+
+/* ---- library ----------------------------------------------------------------- */
+
+int         rlr_abi_version(void);
+const char *rlr_last_error(void);                 /* thread-local, never NULL             */
+int         rlr_device_count(int *out_count);
+int         rlr_device_query(int device, rlr_device_info *out);
+
+/* ---- host-side scalar helpers (bit-exact mirrors, for glue and tests) ---------- */
+
+/* normalize, src/rag_engine.rs:1763-1771 (in place). */
+int rlr_normalize(float *v, size_t n);
+
+/* ResolvedWeights::from_query_weights, src/rag_engine.rs:1869-1896, defaults
+ * :1801-1804, env cache RAG_*_WEIGHT :1806-1841 (read once per process). */
+int rlr_resolve_weights(const rlr_query_weights *overrides /* nullable */,
+                        rlr_resolved_weights *out);
+
+/* ---- chunk store ------------------------------------------------------------- */
+
+/*
+ * Create a device-resident store from host rows.  Replaces the embedding half of
+ * `HashMap<String, DocumentChunk>` (src/rag_engine.rs:105) after `apply_loaded_state`
+ * (:1655-1696).  `rows` is n_rows x dim f32, row stride `host_pitch` floats (0 =>
+ * dim), ALREADY normalised by the host exactly as :1678-1680 does (so device rows
+ * are bit-identical to what the reference would scan).  rows may be NULL to create
+ * an uninitialised store that is then filled by rlr_store_upload / rlr_store_fill_synthetic.
+ * row_base: global index of row 0 when this store is one shard of a row-sharded corpus.
+ */
+int rlr_store_create(int device, uint32_t dim, uint64_t n_rows, const float *rows,
+                     uint64_t host_pitch, uint64_t row_base, uint32_t flags,
+                     rlr_store **out);
+int rlr_store_destroy(rlr_store *s);
+int rlr_store_info_get(const rlr_store *s, rlr_store_info *out);
+
+/* overwrite rows [row0, row0+n) from host memory (normalised by the caller). */
+int rlr_store_upload(rlr_store *s, uint64_t row0, uint64_t n, const float *rows,
+                     uint64_t host_pitch);
+
+/* copy rows[i] (local indices) back to host: out is n x dim, stride dim. */
+int rlr_store_read_rows(const rlr_store *s, const uint32_t *rows, uint64_t n, float *out);
+
+/* Fill local rows [0,n_rows) with synthetic unit vectors for GLOBAL rows
+ * row_base.. (bit-reproducible on the CPU; normalised on the device with the
+ * reference's sequential arithmetic). */
+int rlr_store_fill_synthetic(rlr_store *s, int kind, uint64_t seed, uint64_t centroid_seed,
+                             uint32_t n_clusters, float sigma);
+
+/* ---- the hot path ------------------------------------------------------------ */
+
+/*
+ * rlr_search_topm -- RagEngine::search up to the candidate cut, reranker absent:
+ * src/rag_engine.rs:476-565 (+ the fallback ordering :667-698).
+ *   query      dim f32 as returned by the embedding service; normalised here (:494)
+ *              unless RLR_QUERY_PRENORMALIZED
+ *   w          resolved weights (embedding, lexical used)
+ *   lex_rows / lex_scores / n_lex
+ *              what LexicalIndex::score(query, 5*top_k) returned (:505-506): unique
+ *              local rows with raw BM25 scores; normalised by max (:511-530) here
+ *   m          number of candidates wanted, 1..RLR_MAX_M.  search(top_k) semantics:
+ *              m = top_k for the reranker-absent result, m = 3*top_k to feed a host
+ *              reranker (:544)
+ * Outputs (capacity m each; any may be NULL except out_rows/out_n): rows in
+ * (combined desc, row asc) order with combined (= initial_score), embedding_score,
+ * lexical_score.  *out_n = min(m, n_rows).  Empty store => RLR_OK, *out_n = 0 (:476).
+ */
+int rlr_search_topm(rlr_store *s, const float *query, uint32_t dim, uint32_t flags,
+                    const rlr_resolved_weights *w,
+                    const uint32_t *lex_rows, const float *lex_scores, uint32_t n_lex,
+                    uint32_t m,
+                    uint32_t *out_rows, float *out_combined, float *out_emb, float *out_lex,
+                    uint32_t *out_n);
+
+/*
+ * rlr_mmr -- RagEngine::mmr_diversify, src/rag_engine.rs:767-839, on rows resident
+ * in the store (replaces the embedding lookup :742-753 as well).
+ *   cand_rows  p local rows in `search` order;  relevance: their result.score (:794;
+ *              caller-supplied so that a host reranker can sit in between)
+ *   top_k      selections wanted (the first candidate is always selected, :782-785)
+ *   lambda     diversity_factor, used as given (clamp is the caller's, :725)
+ * out_sel_pos (capacity min(p, max(top_k,1))): positions into cand_rows, selection
+ * order.  p <= RLR_MAX_M.
+ */
+int rlr_mmr(rlr_store *s, const uint32_t *cand_rows, const float *relevance, uint32_t p,
+            uint32_t top_k, float lambda, uint32_t flags,
+            uint32_t *out_sel_pos, uint32_t *out_n);
+
+/*
+ * rlr_search_mmr -- RagEngine::search_with_diversity with no reranker,
+ * src/rag_engine.rs:717-759: lambda clamped to [0,1]; lambda == 0 => search(top_k);
+ * else pool = max(3*top_k, top_k+10), search(pool), MMR to top_k.  One launch
+ * sequence, one host<->device round trip.  This is the benchmarked entry point.
+ * Outputs have capacity max(top_k, 1).
+ */
+int rlr_search_mmr(rlr_store *s, const float *query, uint32_t dim, uint32_t flags,
+                   uint32_t top_k, float diversity_factor,
+                   const rlr_resolved_weights *w,
+                   const uint32_t *lex_rows, const float *lex_scores, uint32_t n_lex,
+                   uint32_t *out_rows, float *out_score, float *out_emb, float *out_lex,
+                   uint32_t *out_n);
+
+/*
+ * rlr_embedding_candidates -- RagEngine::get_embedding_candidates,
+ * src/rag_engine.rs:415-461 (ann_index == None): top `count` by raw dot product.
+ */
+int rlr_embedding_candidates(rlr_store *s, const float *query, uint32_t dim, uint32_t flags,
+                             uint32_t count, uint32_t *out_rows, float *out_score,
+                             uint32_t *out_n);
+
+/* stage timings of the calling thread's most recent call made with RLR_WANT_TIMINGS */
+int rlr_last_timings(rlr_timings *out);
+
+/* ---- device-level building blocks (multi-GPU composition, bench `value`) -------
+ *
+ * Same kernels, but inputs/outputs stay in device memory and work is enqueued on a
+ * caller-supplied CUDA stream (`cudaStream_t` passed as void*; device pointers as
+ * void*).  No host synchronisation.  Used by the one-process-per-GPU path to place
+ * the NCCL all-gather between the local top-M and the merge + MMR, and by bench.py
+ * to time the path with inputs already resident in HBM.
+ */
+typedef struct rlr_ctx rlr_ctx; /* per-caller workspace bound to one store */
+
+int rlr_ctx_create(rlr_store *s, rlr_ctx **out);
+int rlr_ctx_destroy(rlr_ctx *c);
+
+/* Candidate record exchanged between GPUs: 16 bytes. */
+typedef struct rlr_cand {
+    uint64_t key;       /* (ordered(combined) << 32) | ~global_row : larger == ranks earlier */
+    float    emb;       /* embedding_score                                                   */
+    float    lex;       /* lexical_score                                                     */
+} rlr_cand;
+
+/* scan + local top-m: d_query = dim normalised f32 on the device; d_lex_* sorted by
+ * row (may be NULL); writes m records (rank order, padded with key 0) to d_out and
+ * the valid count to d_out_n.  Rows in the keys are GLOBAL (row_base + local). */
+int rlr_topm_async(rlr_ctx *c, const void *d_query, float w_embed, float w_lex,
+                   const void *d_lex_rows, const void *d_lex_norm, uint32_t n_lex,
+                   uint32_t m, void *d_out /* rlr_cand[m] */, void *d_out_n /* u32 */,
+                   void *stream);
+
+/* merge n_lists lists of m records each (e.g. the all-gathered per-GPU lists) into
+ * the best m, same record format. */
+int rlr_merge_async(rlr_ctx *c, const void *d_lists, uint32_t n_lists, uint32_t m,
+                    void *d_out, void *d_out_n, void *stream);
+
+/* gather the embeddings of the records that this store owns into d_out
+ * (m x pitch f32, zero rows for records owned by another shard). */
+int rlr_gather_async(rlr_ctx *c, const void *d_cands, const void *d_n, uint32_t m,
+                     void *d_out, void *stream);
+
+/* MMR over a dense candidate matrix in device memory (p x pitch f32) with relevance
+ * = combined score decoded from d_cands.  Writes selected positions / count. */
+int rlr_mmr_async(rlr_ctx *c, const void *d_emb, uint32_t pitch, uint32_t dim,
+                  const void *d_cands, const void *d_n, uint32_t p_cap,
+                  uint32_t top_k, float lambda,
+                  void *d_sel_pos /* u32[top_k] */, void *d_sel_n /* u32 */, void *stream);
+
+/* fused single-GPU search_with_diversity on the device: results stay in HBM.
+ * d_result: rlr_cand[max(top_k,1)] in selection order, d_result_n: u32. */
+int rlr_search_mmr_async(rlr_ctx *c, const void *d_query, uint32_t top_k, float diversity_factor,
+                         float w_embed, float w_lex,
+                         void *d_result, void *d_result_n, void *stream);
+
+/* launches enqueued by this ctx since creation (bench `gpu_launches`) */
+int rlr_ctx_launch_count(const rlr_ctx *c, uint64_t *out);
+
+/* Time the scan kernel alone: `iters` back-to-back launches on `stream`, CUDA
+ * events around them on that stream; returns mean ms per launch (roofline). */
+int rlr_time_scan(rlr_ctx *c, const void *d_query, uint32_t m, uint32_t iters,
+                  void *stream, float *out_ms_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLR_B200_H */

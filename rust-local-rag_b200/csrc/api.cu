@@ -1,0 +1,934 @@
+// api.cu -- the C ABI of include/rlr_b200.h: store management, host<->device plumbing
+// and launch sequencing around the sm_100a kernels.  No compute happens on the host
+// except the O(dim) query normalisation and O(n_lex) lexical normalisation that the
+// reference also does once per query (/root/reference/src/rag_engine.rs:494,511-530).
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+#define RLR_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+thread_local std::string g_err;
+thread_local rlr_timings g_timings = {0, 0, 0, 0, 0};
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                             \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            cudaGetLastError();                                                                  \
+            return fail(e__ == cudaErrorMemoryAllocation ? RLR_ERR_OOM : RLR_ERR_CUDA,           \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                        \
+    } while (0)
+
+constexpr uint32_t kLexCap = 8192;
+
+struct DeviceState {
+    bool checked = false;
+    bool ok = false;
+    int sm_count = 0;
+    int smem_optin = 0;
+    std::string why;
+};
+std::mutex g_dev_mu;
+DeviceState g_dev[64];
+
+// A device is usable iff it exists and is compute capability 10.x (the fatbin holds
+// sm_100a SASS only).  There is no fallback.
+int ensure_device(int device)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(RLR_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= count || device >= 64)
+        return fail(RLR_ERR_INVALID_ARG, "device %d out of range (have %d)", device, count);
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    DeviceState &d = g_dev[device];
+    if (!d.checked) {
+        d.checked = true;
+        cudaDeviceProp prop;
+        e = cudaGetDeviceProperties(&prop, device);
+        if (e != cudaSuccess) {
+            d.why = cudaGetErrorString(e);
+        } else if (prop.major != 10) {
+            char b[160];
+            snprintf(b, sizeof b, "device %d (%s) is sm_%d%d; kernels are built for sm_100a only", device, prop.name,
+                     prop.major, prop.minor);
+            d.why = b;
+        } else {
+            d.sm_count = prop.multiProcessorCount;
+            e = cudaSetDevice(device);
+            if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+            if (e == cudaSuccess) e = rlr::scan_configure();
+            if (e == cudaSuccess) e = rlr::mmr_configure();
+            if (e != cudaSuccess) d.why = cudaGetErrorString(e);
+            else d.ok = true;
+        }
+    }
+    if (!d.ok) return fail(RLR_ERR_NO_DEVICE, "%s", d.why.c_str());
+    CU_TRY(cudaSetDevice(device));
+    return RLR_OK;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode()
+{
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+        else
+            cudaGetLastError();
+    });
+    return fn;
+}
+
+} // namespace
+
+struct rlr_store {
+    int device = 0;
+    uint32_t dim = 0, pitch = 0, flags = 0;
+    uint64_t n_rows = 0, row_base = 0;
+    float *d_rows = nullptr;
+    CUtensorMap tmap;
+    int sm_count = 0, smem_optin = 0;
+    std::mutex mu;
+    std::vector<rlr_ctx *> free_ctx;
+};
+
+struct rlr_ctx {
+    rlr_store *s = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float *d_query = nullptr;
+    uint32_t *d_lex_rows = nullptr;
+    float *d_lex_norm = nullptr;
+    rlr_cand *d_lists = nullptr;
+    uint32_t *d_counts = nullptr;
+    rlr_cand *d_tmp = nullptr;
+    rlr_cand *d_pool = nullptr;
+    uint32_t *d_pool_n = nullptr;
+    float *d_tri = nullptr;
+    uint32_t *d_sel_pos = nullptr;
+    uint32_t *d_sel_n = nullptr;
+    rlr_cand *d_result = nullptr;
+    uint32_t *d_rows_in = nullptr;
+    float *d_rel_in = nullptr;
+    uint32_t *d_p_in = nullptr;
+    // pinned host staging
+    float *h_query = nullptr;
+    uint32_t *h_lex_rows = nullptr;
+    float *h_lex_norm = nullptr;
+    rlr_cand *h_result = nullptr;   // RLR_MAX_M records
+    uint32_t *h_u32 = nullptr;      // RLR_MAX_M + 8 words
+    float *h_rel = nullptr;
+    uint64_t launches = 0;
+    uint32_t n_lists_cap = 0;
+};
+
+namespace {
+
+void ctx_free(rlr_ctx *c)
+{
+    if (!c) return;
+    cudaFree(c->d_query); cudaFree(c->d_lex_rows); cudaFree(c->d_lex_norm); cudaFree(c->d_lists);
+    cudaFree(c->d_counts); cudaFree(c->d_tmp); cudaFree(c->d_pool); cudaFree(c->d_pool_n); cudaFree(c->d_tri);
+    cudaFree(c->d_sel_pos); cudaFree(c->d_sel_n); cudaFree(c->d_result); cudaFree(c->d_rows_in);
+    cudaFree(c->d_rel_in); cudaFree(c->d_p_in);
+    cudaFreeHost(c->h_query); cudaFreeHost(c->h_lex_rows); cudaFreeHost(c->h_lex_norm);
+    cudaFreeHost(c->h_result); cudaFreeHost(c->h_u32); cudaFreeHost(c->h_rel);
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    cudaGetLastError();
+    delete c;
+}
+
+int ctx_new(rlr_store *s, rlr_ctx **out)
+{
+    rlr_ctx *c = new rlr_ctx();
+    c->s = s;
+    c->n_lists_cap = static_cast<uint32_t>(std::max(s->sm_count, 64));
+#define CTX_TRY(expr)                                                                                    \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            cudaGetLastError();                                                                          \
+            ctx_free(c);                                                                                 \
+            return fail(e__ == cudaErrorMemoryAllocation ? RLR_ERR_OOM : RLR_ERR_CUDA, "%s failed: %s", #expr, \
+                        cudaGetErrorString(e__));                                                        \
+        }                                                                                                \
+    } while (0)
+    CTX_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &e : c->ev) CTX_TRY(cudaEventCreate(&e));
+    CTX_TRY(cudaMalloc(&c->d_query, rlr::kQueryCap * sizeof(float)));
+    CTX_TRY(cudaMemset(c->d_query, 0, rlr::kQueryCap * sizeof(float)));
+    CTX_TRY(cudaMalloc(&c->d_lex_rows, kLexCap * sizeof(uint32_t)));
+    CTX_TRY(cudaMalloc(&c->d_lex_norm, kLexCap * sizeof(float)));
+    CTX_TRY(cudaMalloc(&c->d_lists, static_cast<size_t>(c->n_lists_cap) * RLR_MAX_M * sizeof(rlr_cand)));
+    CTX_TRY(cudaMalloc(&c->d_counts, c->n_lists_cap * sizeof(uint32_t)));
+    CTX_TRY(cudaMalloc(&c->d_tmp, (static_cast<size_t>(c->n_lists_cap) + 3) * RLR_MAX_M * sizeof(rlr_cand)));
+    CTX_TRY(cudaMalloc(&c->d_pool, RLR_MAX_M * sizeof(rlr_cand)));
+    CTX_TRY(cudaMalloc(&c->d_pool_n, sizeof(uint32_t)));
+    CTX_TRY(cudaMalloc(&c->d_tri, static_cast<size_t>(RLR_MAX_M) * (RLR_MAX_M - 1) / 2 * sizeof(float)));
+    CTX_TRY(cudaMalloc(&c->d_sel_pos, RLR_MAX_M * sizeof(uint32_t)));
+    CTX_TRY(cudaMalloc(&c->d_sel_n, sizeof(uint32_t)));
+    CTX_TRY(cudaMalloc(&c->d_result, RLR_MAX_M * sizeof(rlr_cand)));
+    CTX_TRY(cudaMalloc(&c->d_rows_in, RLR_MAX_M * sizeof(uint32_t)));
+    CTX_TRY(cudaMalloc(&c->d_rel_in, RLR_MAX_M * sizeof(float)));
+    CTX_TRY(cudaMalloc(&c->d_p_in, sizeof(uint32_t)));
+    CTX_TRY(cudaMallocHost(&c->h_query, rlr::kQueryCap * sizeof(float)));
+    memset(c->h_query, 0, rlr::kQueryCap * sizeof(float));
+    CTX_TRY(cudaMallocHost(&c->h_lex_rows, kLexCap * sizeof(uint32_t)));
+    CTX_TRY(cudaMallocHost(&c->h_lex_norm, kLexCap * sizeof(float)));
+    CTX_TRY(cudaMallocHost(&c->h_result, RLR_MAX_M * sizeof(rlr_cand)));
+    CTX_TRY(cudaMallocHost(&c->h_u32, (RLR_MAX_M + 8) * sizeof(uint32_t)));
+    CTX_TRY(cudaMallocHost(&c->h_rel, RLR_MAX_M * sizeof(float)));
+#undef CTX_TRY
+    *out = c;
+    return RLR_OK;
+}
+
+// RAII lease of a pooled ctx so that concurrent searches on one store are re-entrant.
+struct CtxLease {
+    rlr_store *s;
+    rlr_ctx *c = nullptr;
+    explicit CtxLease(rlr_store *st) : s(st) {}
+    int acquire()
+    {
+        {
+            std::lock_guard<std::mutex> lk(s->mu);
+            if (!s->free_ctx.empty()) { c = s->free_ctx.back(); s->free_ctx.pop_back(); }
+        }
+        if (c) return RLR_OK;
+        return ctx_new(s, &c);
+    }
+    ~CtxLease()
+    {
+        if (c) { std::lock_guard<std::mutex> lk(s->mu); s->free_ctx.push_back(c); }
+    }
+};
+
+void host_normalize(float *v, size_t n)
+{
+    // src/rag_engine.rs:1763-1771; volatile keeps gcc/nvcc-host from re-associating
+    volatile float norm_sq = 0.0f;
+    for (size_t i = 0; i < n; ++i) { volatile float p = v[i] * v[i]; norm_sq = norm_sq + p; }
+    if (norm_sq > 1e-20f) {
+        const float norm = sqrtf(norm_sq);
+        for (size_t i = 0; i < n; ++i) v[i] = v[i] / norm;
+    }
+}
+
+// Stage the query in pinned memory, normalise (:494), upload.  Everything beyond dim
+// stays zero so that the kernel's padded chunks contribute exact zeros.
+int stage_query(rlr_ctx *c, const float *query, uint32_t dim, uint32_t flags, cudaStream_t st)
+{
+    rlr_store *s = c->s;
+    if (!query) return fail(RLR_ERR_INVALID_ARG, "query is NULL");
+    if (dim != s->dim)
+        return fail(RLR_ERR_DIM_MISMATCH, "query has %u dims, store has %u (the reference would silently truncate, "
+                    "src/rag_engine.rs:1778; this library refuses)", dim, s->dim);
+    memcpy(c->h_query, query, dim * sizeof(float));
+    for (uint32_t i = 0; i < dim; ++i)
+        if (!std::isfinite(c->h_query[i])) return fail(RLR_ERR_NONFINITE, "query[%u] is not finite", i);
+    if (!(flags & RLR_QUERY_PRENORMALIZED)) host_normalize(c->h_query, dim);
+    const size_t n = s->pitch + rlr::kChunkFloats * rlr::kScanChunks;
+    CU_TRY(cudaMemcpyAsync(c->d_query, c->h_query, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    return RLR_OK;
+}
+
+// :505-530: lexical map -> (sorted local rows, score / max_lexical).
+int stage_lex(rlr_ctx *c, const uint32_t *lex_rows, const float *lex_scores, uint32_t n_lex, uint32_t *out_n,
+              cudaStream_t st)
+{
+    rlr_store *s = c->s;
+    *out_n = 0;
+    if (n_lex == 0) return RLR_OK;
+    if (!lex_rows || !lex_scores) return fail(RLR_ERR_INVALID_ARG, "n_lex > 0 but lex_rows/lex_scores is NULL");
+    if (n_lex > kLexCap) return fail(RLR_ERR_UNSUPPORTED, "n_lex %u exceeds %u", n_lex, kLexCap);
+    float max_lexical = 0.0f; // fold(0.0_f32, f32::max).max(f32::EPSILON)
+    for (uint32_t i = 0; i < n_lex; ++i) max_lexical = fmaxf(max_lexical, lex_scores[i]);
+    max_lexical = fmaxf(max_lexical, 1.1920929e-07f);
+    std::vector<std::pair<uint32_t, uint32_t>> order; // (row, original index); later duplicates win (HashMap collect)
+    order.reserve(n_lex);
+    for (uint32_t i = 0; i < n_lex; ++i) {
+        const uint64_t g = lex_rows[i];
+        if (g < s->row_base || g - s->row_base >= s->n_rows) continue; // `if let Some(chunk)`, :525
+        order.emplace_back(static_cast<uint32_t>(g - s->row_base), i);
+    }
+    std::stable_sort(order.begin(), order.end(),
+                     [](const std::pair<uint32_t, uint32_t> &a, const std::pair<uint32_t, uint32_t> &b) { return a.first < b.first; });
+    uint32_t n = 0;
+    for (size_t i = 0; i < order.size(); ++i) {
+        if (i + 1 < order.size() && order[i + 1].first == order[i].first) continue;
+        c->h_lex_rows[n] = order[i].first;
+        c->h_lex_norm[n] = lex_scores[order[i].second] / max_lexical; // :527-530
+        ++n;
+    }
+    if (n) {
+        CU_TRY(cudaMemcpyAsync(c->d_lex_rows, c->h_lex_rows, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(c->d_lex_norm, c->h_lex_norm, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    *out_n = n;
+    return RLR_OK;
+}
+
+// scan + merge on `st`: best m records of this store -> d_out / d_out_n
+int enqueue_topm(rlr_ctx *c, const float *d_query, float w_e, float w_l, const uint32_t *d_lex_rows,
+                 const float *d_lex_norm, uint32_t n_lex, uint32_t m, rlr_cand *d_out, uint32_t *d_out_n,
+                 cudaStream_t st, cudaEvent_t ev_after_scan)
+{
+    rlr_store *s = c->s;
+    rlr::ScanArgs a;
+    memset(&a, 0, sizeof a);
+    rlr::scan_plan(s->sm_count, s->smem_optin, static_cast<uint32_t>(s->n_rows), s->pitch, &a);
+    a.tmap = &s->tmap;
+    a.d_query = d_query;
+    a.n_rows = static_cast<uint32_t>(s->n_rows);
+    a.row_base = static_cast<uint32_t>(s->row_base);
+    a.pitch = s->pitch;
+    a.w_embed = w_e; a.w_lex = w_l;
+    a.d_lex_rows = d_lex_rows; a.d_lex_norm = d_lex_norm; a.n_lex = n_lex;
+    a.m = m;
+    a.d_lists = c->d_lists; a.d_counts = c->d_counts;
+    CU_TRY(rlr::scan_launch(a, st));
+    ++c->launches;
+    if (ev_after_scan) CU_TRY(cudaEventRecord(ev_after_scan, st));
+    uint32_t l = 0;
+    CU_TRY(rlr::merge_launch(c->d_lists, static_cast<uint32_t>(a.grid), m, c->d_tmp, d_out, d_out_n, st, &l));
+    c->launches += l;
+    return RLR_OK;
+}
+
+void unpack(const rlr_cand *h, uint32_t n, uint32_t *rows, float *score, float *emb, float *lex)
+{
+    for (uint32_t i = 0; i < n; ++i) {
+        if (rows) rows[i] = rlr::key_row(h[i].key);
+        if (score) {
+            const uint32_t b = rlr::bits_from_ord(static_cast<uint32_t>(h[i].key >> 32));
+            memcpy(&score[i], &b, 4);
+        }
+        if (emb) emb[i] = h[i].emb;
+        if (lex) lex[i] = h[i].lex;
+    }
+}
+
+int check_store(const rlr_store *s)
+{
+    if (!s) return fail(RLR_ERR_INVALID_ARG, "store is NULL");
+    return RLR_OK;
+}
+
+float parse_env_weight(const char *name, float dflt)
+{
+    // parse_weight, src/rag_engine.rs:1813-1819: str::parse::<f32>() then finite && in [0,1]
+    const char *v = getenv(name);
+    if (!v || !*v) return dflt;
+    if (isspace(static_cast<unsigned char>(v[0]))) return dflt;       // Rust does not trim
+    if (strchr(v, 'x') || strchr(v, 'X')) return dflt;                // no hex floats in Rust
+    char *end = nullptr;
+    const float w = strtof(v, &end);
+    if (end == v || *end != '\0') return dflt;
+    if (!std::isfinite(w) || w < 0.0f || w > 1.0f) return dflt;
+    return w;
+}
+
+float resolve_one(bool has, float w, float dflt)
+{
+    // resolve_weight, src/rag_engine.rs:1869-1873
+    if (has && std::isfinite(w) && w >= 0.0f && w <= 1.0f) return w;
+    return dflt;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------
+// library
+// ---------------------------------------------------------------------------------
+RLR_EXPORT int rlr_abi_version(void) { return RLR_ABI_VERSION; }
+RLR_EXPORT const char *rlr_last_error(void) { return g_err.c_str(); }
+
+RLR_EXPORT int rlr_device_count(int *out_count)
+{
+    if (!out_count) return fail(RLR_ERR_INVALID_ARG, "out_count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *out_count = 0;
+        return fail(RLR_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *out_count = n;
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_device_query(int device, rlr_device_info *out)
+{
+    if (!out) return fail(RLR_ERR_INVALID_ARG, "out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(RLR_ERR_NO_DEVICE, "no CUDA device available");
+    }
+    if (device < 0 || device >= n) return fail(RLR_ERR_INVALID_ARG, "device %d out of range", device);
+    cudaDeviceProp p;
+    CU_TRY(cudaGetDeviceProperties(&p, device));
+    memset(out, 0, sizeof *out);
+    out->device = device;
+    out->sm_count = p.multiProcessorCount;
+    out->cc_major = p.major; out->cc_minor = p.minor;
+    out->total_mem = p.totalGlobalMem;
+    strncpy(out->name, p.name, sizeof(out->name) - 1);
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_normalize(float *v, size_t n)
+{
+    if (!v && n) return fail(RLR_ERR_INVALID_ARG, "v is NULL");
+    host_normalize(v, n);
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_resolve_weights(const rlr_query_weights *o, rlr_resolved_weights *out)
+{
+    if (!out) return fail(RLR_ERR_INVALID_ARG, "out is NULL");
+    // OnceLock caches, src/rag_engine.rs:1806-1841 (defaults :1801-1804)
+    static float d_e, d_l, d_r, d_i;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        d_e = parse_env_weight("RAG_EMBEDDING_WEIGHT", 0.7f);
+        d_l = parse_env_weight("RAG_LEXICAL_WEIGHT", 0.3f);
+        d_r = parse_env_weight("RAG_RERANKER_WEIGHT", 0.7f);
+        d_i = parse_env_weight("RAG_INITIAL_SCORE_WEIGHT", 0.3f);
+    });
+    out->embedding = resolve_one(o && (o->has & 1u), o ? o->embedding : 0.f, d_e);
+    out->lexical = resolve_one(o && (o->has & 2u), o ? o->lexical : 0.f, d_l);
+    out->reranker = resolve_one(o && (o->has & 4u), o ? o->reranker : 0.f, d_r);
+    out->initial = resolve_one(o && (o->has & 8u), o ? o->initial : 0.f, d_i);
+    return RLR_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// store
+// ---------------------------------------------------------------------------------
+RLR_EXPORT int rlr_store_create(int device, uint32_t dim, uint64_t n_rows, const float *rows, uint64_t host_pitch,
+                                uint64_t row_base, uint32_t flags, rlr_store **out)
+{
+    if (!out) return fail(RLR_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    if (dim == 0 || dim > RLR_MAX_DIM) return fail(RLR_ERR_INVALID_ARG, "dim %u not in 1..%d", dim, RLR_MAX_DIM);
+    if (n_rows >= (1ull << 31)) return fail(RLR_ERR_UNSUPPORTED, "n_rows %llu >= 2^31 per store", (unsigned long long)n_rows);
+    if (row_base + n_rows >= (1ull << 32)) return fail(RLR_ERR_UNSUPPORTED, "global rows must fit 32 bits");
+    if (flags & RLR_STORE_KEEP_F16) return fail(RLR_ERR_UNSUPPORTED, "f16 store copy is not built yet");
+    if (host_pitch == 0) host_pitch = dim;
+    if (host_pitch < dim) return fail(RLR_ERR_INVALID_ARG, "host_pitch %llu < dim %u", (unsigned long long)host_pitch, dim);
+    int rc = ensure_device(device);
+    if (rc) return rc;
+
+    rlr_store *s = new rlr_store();
+    s->device = device;
+    s->dim = dim;
+    s->pitch = (dim + 31u) & ~31u;
+    s->n_rows = n_rows;
+    s->row_base = row_base;
+    s->flags = flags;
+    {
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        s->sm_count = g_dev[device].sm_count;
+        s->smem_optin = g_dev[device].smem_optin;
+    }
+    memset(&s->tmap, 0, sizeof s->tmap);
+    if (n_rows) {
+        const size_t bytes = static_cast<size_t>(n_rows) * s->pitch * sizeof(float);
+        cudaError_t e = cudaMalloc(&s->d_rows, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            delete s;
+            return fail(RLR_ERR_OOM, "cudaMalloc of %zu bytes for the store failed: %s", bytes, cudaGetErrorString(e));
+        }
+        PFN_encodeTiled enc = get_encode();
+        if (!enc) { cudaFree(s->d_rows); delete s; return fail(RLR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found"); }
+        const cuuint64_t gdim[2] = {s->pitch, n_rows};
+        const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(s->pitch) * sizeof(float)};
+        const cuuint32_t box[2] = {rlr::kChunkFloats, rlr::kScanRows};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&s->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, s->d_rows, gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            cudaFree(s->d_rows);
+            delete s;
+            return fail(RLR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+        }
+    }
+    *out = s;
+    if (rows && n_rows) {
+        rc = rlr_store_upload(s, 0, n_rows, rows, host_pitch);
+        if (rc) { std::string keep = g_err; rlr_store_destroy(s); *out = nullptr; g_err = keep; return rc; }
+    }
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_store_destroy(rlr_store *s)
+{
+    if (!s) return RLR_OK;
+    cudaSetDevice(s->device);
+    for (rlr_ctx *c : s->free_ctx) ctx_free(c);
+    cudaFree(s->d_rows);
+    cudaGetLastError();
+    delete s;
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_store_info_get(const rlr_store *s, rlr_store_info *out)
+{
+    if (int rc = check_store(s)) return rc;
+    if (!out) return fail(RLR_ERR_INVALID_ARG, "out is NULL");
+    out->n_rows = s->n_rows; out->row_base = s->row_base; out->dim = s->dim; out->pitch = s->pitch;
+    out->device = s->device; out->flags = s->flags;
+    out->bytes_device = s->n_rows * s->pitch * sizeof(float);
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_store_upload(rlr_store *s, uint64_t row0, uint64_t n, const float *rows, uint64_t host_pitch)
+{
+    if (int rc = check_store(s)) return rc;
+    if (!rows && n) return fail(RLR_ERR_INVALID_ARG, "rows is NULL");
+    if (row0 + n > s->n_rows) return fail(RLR_ERR_INVALID_ARG, "rows [%llu,%llu) outside the store", (unsigned long long)row0, (unsigned long long)(row0 + n));
+    if (host_pitch == 0) host_pitch = s->dim;
+    if (host_pitch < s->dim) return fail(RLR_ERR_INVALID_ARG, "host_pitch < dim");
+    if (n == 0) return RLR_OK;
+    CU_TRY(cudaSetDevice(s->device));
+    float *dst = s->d_rows + row0 * s->pitch;
+    if (s->pitch != s->dim) CU_TRY(cudaMemset(dst, 0, n * s->pitch * sizeof(float)));
+    // cudaMemcpy2D is limited to 2^31-ish heights on some drivers: go in slabs
+    const uint64_t slab = 1u << 20;
+    for (uint64_t r = 0; r < n; r += slab) {
+        const uint64_t cnt = std::min(slab, n - r);
+        CU_TRY(cudaMemcpy2D(dst + r * s->pitch, s->pitch * sizeof(float), rows + r * host_pitch, host_pitch * sizeof(float),
+                            s->dim * sizeof(float), cnt, cudaMemcpyHostToDevice));
+    }
+    if (s->flags & RLR_STORE_CHECK_FINITE) {
+        uint32_t *d_flag = nullptr, h_flag = 0;
+        CU_TRY(cudaMalloc(&d_flag, sizeof(uint32_t)));
+        cudaMemset(d_flag, 0, sizeof(uint32_t));
+        cudaError_t e = rlr::finite_check_launch(dst, n * s->pitch, d_flag, 0);
+        if (e == cudaSuccess) e = cudaMemcpy(&h_flag, d_flag, sizeof h_flag, cudaMemcpyDeviceToHost);
+        cudaFree(d_flag);
+        CU_TRY(e);
+        if (h_flag) return fail(RLR_ERR_NONFINITE, "uploaded rows contain NaN/Inf");
+    }
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_store_read_rows(const rlr_store *s, const uint32_t *rows, uint64_t n, float *out)
+{
+    if (int rc = check_store(s)) return rc;
+    if ((!rows || !out) && n) return fail(RLR_ERR_INVALID_ARG, "rows/out is NULL");
+    CU_TRY(cudaSetDevice(s->device));
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t g = rows[i];
+        if (g < s->row_base || g - s->row_base >= s->n_rows) return fail(RLR_ERR_INVALID_ARG, "row %llu not in this store", (unsigned long long)g);
+        CU_TRY(cudaMemcpy(out + i * s->dim, s->d_rows + (g - s->row_base) * s->pitch, s->dim * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_store_fill_synthetic(rlr_store *s, int kind, uint64_t seed, uint64_t centroid_seed,
+                                        uint32_t n_clusters, float sigma)
+{
+    if (int rc = check_store(s)) return rc;
+    if (kind != RLR_SYNTH_IID && kind != RLR_SYNTH_CLUSTERED) return fail(RLR_ERR_INVALID_ARG, "unknown synthetic kind %d", kind);
+    if (kind == RLR_SYNTH_CLUSTERED && n_clusters == 0) return fail(RLR_ERR_INVALID_ARG, "n_clusters must be > 0");
+    CU_TRY(cudaSetDevice(s->device));
+    CU_TRY(rlr::synth_launch(s->d_rows, s->pitch, s->dim, s->row_base, static_cast<uint32_t>(s->n_rows), kind, seed,
+                             centroid_seed, n_clusters, sigma, 0));
+    CU_TRY(cudaDeviceSynchronize());
+    return RLR_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// hot path, host-facing
+// ---------------------------------------------------------------------------------
+namespace {
+
+void timings_from_events(rlr_ctx *c, bool has_mmr)
+{
+    rlr_timings t = {0, 0, 0, 0, 0};
+    cudaEventElapsedTime(&t.scan_ms, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&t.merge_ms, c->ev[1], c->ev[2]);
+    if (has_mmr) cudaEventElapsedTime(&t.mmr_ms, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&t.total_ms, c->ev[0], has_mmr ? c->ev[3] : c->ev[2]);
+    cudaGetLastError();
+    g_timings = t;
+}
+
+} // namespace
+
+RLR_EXPORT int rlr_search_topm(rlr_store *s, const float *query, uint32_t dim, uint32_t flags,
+                               const rlr_resolved_weights *w, const uint32_t *lex_rows, const float *lex_scores,
+                               uint32_t n_lex, uint32_t m, uint32_t *out_rows, float *out_combined, float *out_emb,
+                               float *out_lex, uint32_t *out_n)
+{
+    if (int rc = check_store(s)) return rc;
+    if (!out_rows || !out_n) return fail(RLR_ERR_INVALID_ARG, "out_rows/out_n is NULL");
+    if (!w) return fail(RLR_ERR_INVALID_ARG, "weights is NULL");
+    if (m == 0 || m > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "m %u not in 1..%d", m, RLR_MAX_M);
+    *out_n = 0;
+    if (int rc = ensure_device(s->device)) return rc;
+    if (s->n_rows == 0) return RLR_OK; // :476-478
+    CtxLease lease(s);
+    if (int rc = lease.acquire()) return rc;
+    rlr_ctx *c = lease.c;
+    cudaStream_t st = c->stream;
+    const uint64_t launches0 = c->launches;
+    if (int rc = stage_query(c, query, dim, flags, st)) return rc;
+    uint32_t nl = 0;
+    if (int rc = stage_lex(c, lex_rows, lex_scores, n_lex, &nl, st)) return rc;
+    const uint32_t m_eff = static_cast<uint32_t>(std::min<uint64_t>(m, s->n_rows));
+    const bool timed = flags & RLR_WANT_TIMINGS;
+    if (timed) CU_TRY(cudaEventRecord(c->ev[0], st));
+    if (int rc = enqueue_topm(c, c->d_query, w->embedding, w->lexical, c->d_lex_rows, c->d_lex_norm, nl, m_eff,
+                              c->d_pool, c->d_pool_n, st, timed ? c->ev[1] : nullptr))
+        return rc;
+    if (timed) CU_TRY(cudaEventRecord(c->ev[2], st));
+    CU_TRY(cudaMemcpyAsync(c->h_result, c->d_pool, m_eff * sizeof(rlr_cand), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(c->h_u32, c->d_pool_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    const uint32_t n = std::min(c->h_u32[0], m_eff);
+    unpack(c->h_result, n, out_rows, out_combined, out_emb, out_lex);
+    *out_n = n;
+    if (timed) { timings_from_events(c, false); g_timings.launches = static_cast<uint32_t>(c->launches - launches0); }
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_embedding_candidates(rlr_store *s, const float *query, uint32_t dim, uint32_t flags, uint32_t count,
+                                        uint32_t *out_rows, float *out_score, uint32_t *out_n)
+{
+    // :438-447 raw dot, sort desc, take(count): w_embed = 1 makes combined == emb exactly
+    if (!out_n) return fail(RLR_ERR_INVALID_ARG, "out_n is NULL");
+    *out_n = 0;
+    if (count == 0) return RLR_OK;
+    const rlr_resolved_weights w = {1.0f, 0.0f, 0.0f, 0.0f};
+    return rlr_search_topm(s, query, dim, flags, &w, nullptr, nullptr, 0, count, out_rows, nullptr, out_score, nullptr, out_n);
+}
+
+RLR_EXPORT int rlr_mmr(rlr_store *s, const uint32_t *cand_rows, const float *relevance, uint32_t p, uint32_t top_k,
+                       float lambda, uint32_t flags, uint32_t *out_sel_pos, uint32_t *out_n)
+{
+    if (int rc = check_store(s)) return rc;
+    if (!out_sel_pos || !out_n) return fail(RLR_ERR_INVALID_ARG, "out_sel_pos/out_n is NULL");
+    *out_n = 0;
+    if (p == 0) return RLR_OK; // :773-775
+    if (!cand_rows || !relevance) return fail(RLR_ERR_INVALID_ARG, "cand_rows/relevance is NULL");
+    if (p > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "p %u exceeds %d", p, RLR_MAX_M);
+    if (int rc = ensure_device(s->device)) return rc;
+    for (uint32_t i = 0; i < p; ++i) {
+        const uint64_t g = cand_rows[i];
+        if (g < s->row_base || g - s->row_base >= s->n_rows) return fail(RLR_ERR_INVALID_ARG, "cand_rows[%u]=%llu not in this store", i, (unsigned long long)g);
+    }
+    CtxLease lease(s);
+    if (int rc = lease.acquire()) return rc;
+    rlr_ctx *c = lease.c;
+    cudaStream_t st = c->stream;
+    const uint64_t launches0 = c->launches;
+    memcpy(c->h_u32, cand_rows, p * sizeof(uint32_t));
+    c->h_u32[RLR_MAX_M] = p;
+    memcpy(c->h_rel, relevance, p * sizeof(float));
+    CU_TRY(cudaMemcpyAsync(c->d_rows_in, c->h_u32, p * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(c->d_p_in, c->h_u32 + RLR_MAX_M, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(c->d_rel_in, c->h_rel, p * sizeof(float), cudaMemcpyHostToDevice, st));
+    const bool timed = flags & RLR_WANT_TIMINGS;
+    if (timed) CU_TRY(cudaEventRecord(c->ev[2], st));
+    rlr::MmrArgs a;
+    memset(&a, 0, sizeof a);
+    a.d_emb = s->d_rows; a.pitch = s->pitch; a.dim = s->dim;
+    a.d_cands = nullptr; a.d_n = c->d_p_in; a.d_rows = c->d_rows_in; a.d_rel = c->d_rel_in;
+    a.row_base = static_cast<uint32_t>(s->row_base); a.use_rows = 1;
+    a.p_cap = p; a.top_k = top_k; a.lambda = lambda;
+    a.d_tri = c->d_tri; a.d_sel_pos = c->d_sel_pos; a.d_sel_n = c->d_sel_n; a.d_result = nullptr;
+    a.max_smem_optin = s->smem_optin;
+    uint32_t l = 0;
+    CU_TRY(rlr::mmr_launch(a, st, &l));
+    c->launches += l;
+    if (timed) CU_TRY(cudaEventRecord(c->ev[3], st));
+    const uint32_t cap = std::min<uint32_t>(p, std::max<uint32_t>(top_k, 1));
+    CU_TRY(cudaMemcpyAsync(c->h_u32, c->d_sel_pos, cap * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(c->h_u32 + RLR_MAX_M, c->d_sel_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    const uint32_t n = std::min(c->h_u32[RLR_MAX_M], cap);
+    memcpy(out_sel_pos, c->h_u32, n * sizeof(uint32_t));
+    *out_n = n;
+    if (timed) {
+        rlr_timings t = {0, 0, 0, 0, 0};
+        cudaEventElapsedTime(&t.mmr_ms, c->ev[2], c->ev[3]);
+        t.total_ms = t.mmr_ms;
+        t.launches = static_cast<uint32_t>(c->launches - launches0);
+        g_timings = t;
+    }
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_search_mmr(rlr_store *s, const float *query, uint32_t dim, uint32_t flags, uint32_t top_k,
+                              float diversity_factor, const rlr_resolved_weights *w, const uint32_t *lex_rows,
+                              const float *lex_scores, uint32_t n_lex, uint32_t *out_rows, float *out_score,
+                              float *out_emb, float *out_lex, uint32_t *out_n)
+{
+    if (int rc = check_store(s)) return rc;
+    if (!out_rows || !out_n) return fail(RLR_ERR_INVALID_ARG, "out_rows/out_n is NULL");
+    if (!w) return fail(RLR_ERR_INVALID_ARG, "weights is NULL");
+    // :725 f32::clamp (NaN stays NaN)
+    float lambda = diversity_factor;
+    if (lambda < 0.0f) lambda = 0.0f;
+    if (lambda > 1.0f) lambda = 1.0f;
+    if (lambda == 0.0f) { // :728-730 -> search(top_k), top_k.max(1) at :490
+        const uint32_t m = std::max<uint32_t>(top_k, 1);
+        return rlr_search_topm(s, query, dim, flags, w, lex_rows, lex_scores, n_lex, m, out_rows, out_score, out_emb,
+                               out_lex, out_n);
+    }
+    *out_n = 0;
+    const uint64_t pool = std::max<uint64_t>(3ull * top_k, static_cast<uint64_t>(top_k) + 10); // :734
+    if (pool > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "candidate pool %llu exceeds %d (top_k %u)", (unsigned long long)pool, RLR_MAX_M, top_k);
+    if (int rc = ensure_device(s->device)) return rc;
+    if (s->n_rows == 0) return RLR_OK;
+    CtxLease lease(s);
+    if (int rc = lease.acquire()) return rc;
+    rlr_ctx *c = lease.c;
+    cudaStream_t st = c->stream;
+    const uint64_t launches0 = c->launches;
+    if (int rc = stage_query(c, query, dim, flags, st)) return rc;
+    uint32_t nl = 0;
+    if (int rc = stage_lex(c, lex_rows, lex_scores, n_lex, &nl, st)) return rc;
+    const uint32_t p = static_cast<uint32_t>(std::min<uint64_t>(pool, s->n_rows));
+    const bool timed = flags & RLR_WANT_TIMINGS;
+    if (timed) CU_TRY(cudaEventRecord(c->ev[0], st));
+    if (int rc = enqueue_topm(c, c->d_query, w->embedding, w->lexical, c->d_lex_rows, c->d_lex_norm, nl, p, c->d_pool,
+                              c->d_pool_n, st, timed ? c->ev[1] : nullptr))
+        return rc;
+    if (timed) CU_TRY(cudaEventRecord(c->ev[2], st));
+    rlr::MmrArgs a;
+    memset(&a, 0, sizeof a);
+    a.d_emb = s->d_rows; a.pitch = s->pitch; a.dim = s->dim;
+    a.d_cands = c->d_pool; a.d_n = c->d_pool_n; a.d_rows = nullptr; a.d_rel = nullptr;
+    a.row_base = static_cast<uint32_t>(s->row_base); a.use_rows = 1;
+    a.p_cap = p; a.top_k = top_k; a.lambda = lambda;
+    a.d_tri = c->d_tri; a.d_sel_pos = c->d_sel_pos; a.d_sel_n = c->d_sel_n; a.d_result = c->d_result;
+    a.max_smem_optin = s->smem_optin;
+    uint32_t l = 0;
+    CU_TRY(rlr::mmr_launch(a, st, &l));
+    c->launches += l;
+    if (timed) CU_TRY(cudaEventRecord(c->ev[3], st));
+    const uint32_t cap = std::min<uint32_t>(p, std::max<uint32_t>(top_k, 1));
+    CU_TRY(cudaMemcpyAsync(c->h_result, c->d_result, cap * sizeof(rlr_cand), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(c->h_u32, c->d_sel_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    const uint32_t n = std::min(c->h_u32[0], cap);
+    unpack(c->h_result, n, out_rows, out_score, out_emb, out_lex);
+    *out_n = n;
+    if (timed) { timings_from_events(c, true); g_timings.launches = static_cast<uint32_t>(c->launches - launches0); }
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_last_timings(rlr_timings *out)
+{
+    if (!out) return fail(RLR_ERR_INVALID_ARG, "out is NULL");
+    *out = g_timings;
+    return RLR_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// device-level building blocks
+// ---------------------------------------------------------------------------------
+RLR_EXPORT int rlr_ctx_create(rlr_store *s, rlr_ctx **out)
+{
+    if (int rc = check_store(s)) return rc;
+    if (!out) return fail(RLR_ERR_INVALID_ARG, "out is NULL");
+    if (int rc = ensure_device(s->device)) return rc;
+    return ctx_new(s, out);
+}
+
+RLR_EXPORT int rlr_ctx_destroy(rlr_ctx *c)
+{
+    if (!c) return RLR_OK;
+    cudaSetDevice(c->s->device);
+    ctx_free(c);
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_ctx_launch_count(const rlr_ctx *c, uint64_t *out)
+{
+    if (!c || !out) return fail(RLR_ERR_INVALID_ARG, "ctx/out is NULL");
+    *out = c->launches;
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_topm_async(rlr_ctx *c, const void *d_query, float w_embed, float w_lex, const void *d_lex_rows,
+                              const void *d_lex_norm, uint32_t n_lex, uint32_t m, void *d_out, void *d_out_n,
+                              void *stream)
+{
+    if (!c || !d_query || !d_out || !d_out_n) return fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    if (m == 0 || m > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "m %u not in 1..%d", m, RLR_MAX_M);
+    rlr_store *s = c->s;
+    CU_TRY(cudaSetDevice(s->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (s->n_rows == 0) {
+        CU_TRY(cudaMemsetAsync(d_out, 0, m * sizeof(rlr_cand), st));
+        CU_TRY(cudaMemsetAsync(d_out_n, 0, sizeof(uint32_t), st));
+        return RLR_OK;
+    }
+    // lists shorter than m are zero-key padded by the kernels, so m need not be clamped
+    const uint32_t m_eff = m;
+    return enqueue_topm(c, static_cast<const float *>(d_query), w_embed, w_lex, static_cast<const uint32_t *>(d_lex_rows),
+                        static_cast<const float *>(d_lex_norm), n_lex, m_eff, static_cast<rlr_cand *>(d_out),
+                        static_cast<uint32_t *>(d_out_n), st, nullptr);
+}
+
+RLR_EXPORT int rlr_merge_async(rlr_ctx *c, const void *d_lists, uint32_t n_lists, uint32_t m, void *d_out,
+                               void *d_out_n, void *stream)
+{
+    if (!c || !d_lists || !d_out || !d_out_n) return fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    if (m == 0 || m > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "m %u not in 1..%d", m, RLR_MAX_M);
+    if (n_lists == 0 || n_lists > c->n_lists_cap) return fail(RLR_ERR_UNSUPPORTED, "n_lists %u not in 1..%u", n_lists, c->n_lists_cap);
+    CU_TRY(cudaSetDevice(c->s->device));
+    uint32_t l = 0;
+    CU_TRY(rlr::merge_launch(static_cast<const rlr_cand *>(d_lists), n_lists, m, c->d_tmp, static_cast<rlr_cand *>(d_out),
+                             static_cast<uint32_t *>(d_out_n), static_cast<cudaStream_t>(stream), &l));
+    c->launches += l;
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_gather_async(rlr_ctx *c, const void *d_cands, const void *d_n, uint32_t m, void *d_out, void *stream)
+{
+    if (!c || !d_cands || !d_n || !d_out) return fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    rlr_store *s = c->s;
+    CU_TRY(cudaSetDevice(s->device));
+    CU_TRY(rlr::gather_launch(s->d_rows, s->pitch, static_cast<uint32_t>(s->n_rows), static_cast<uint32_t>(s->row_base),
+                              static_cast<const rlr_cand *>(d_cands), static_cast<const uint32_t *>(d_n), m,
+                              static_cast<float *>(d_out), static_cast<cudaStream_t>(stream)));
+    ++c->launches;
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_mmr_async(rlr_ctx *c, const void *d_emb, uint32_t pitch, uint32_t dim, const void *d_cands,
+                             const void *d_n, uint32_t p_cap, uint32_t top_k, float lambda, void *d_sel_pos,
+                             void *d_sel_n, void *stream)
+{
+    if (!c || !d_emb || !d_cands || !d_n || !d_sel_pos || !d_sel_n) return fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    if (p_cap == 0 || p_cap > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "p_cap %u not in 1..%d", p_cap, RLR_MAX_M);
+    if (pitch % 4) return fail(RLR_ERR_INVALID_ARG, "pitch must be a multiple of 4 floats");
+    CU_TRY(cudaSetDevice(c->s->device));
+    rlr::MmrArgs a;
+    memset(&a, 0, sizeof a);
+    a.d_emb = static_cast<const float *>(d_emb); a.pitch = pitch; a.dim = dim;
+    a.d_cands = static_cast<const rlr_cand *>(d_cands); a.d_n = static_cast<const uint32_t *>(d_n);
+    a.use_rows = 0; a.p_cap = p_cap; a.top_k = top_k; a.lambda = lambda;
+    a.d_tri = c->d_tri; a.d_sel_pos = static_cast<uint32_t *>(d_sel_pos); a.d_sel_n = static_cast<uint32_t *>(d_sel_n);
+    a.d_result = c->d_result;
+    a.max_smem_optin = c->s->smem_optin;
+    uint32_t l = 0;
+    CU_TRY(rlr::mmr_launch(a, static_cast<cudaStream_t>(stream), &l));
+    c->launches += l;
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_search_mmr_async(rlr_ctx *c, const void *d_query, uint32_t top_k, float diversity_factor,
+                                    float w_embed, float w_lex, void *d_result, void *d_result_n, void *stream)
+{
+    if (!c || !d_query || !d_result || !d_result_n) return fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    rlr_store *s = c->s;
+    CU_TRY(cudaSetDevice(s->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float lambda = diversity_factor;
+    if (lambda < 0.0f) lambda = 0.0f;
+    if (lambda > 1.0f) lambda = 1.0f;
+    if (s->n_rows == 0) { CU_TRY(cudaMemsetAsync(d_result_n, 0, sizeof(uint32_t), st)); return RLR_OK; }
+    if (lambda == 0.0f) {
+        const uint32_t m = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint32_t>(top_k, 1), s->n_rows));
+        if (m > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "top_k too large");
+        return enqueue_topm(c, static_cast<const float *>(d_query), w_embed, w_lex, nullptr, nullptr, 0, m,
+                            static_cast<rlr_cand *>(d_result), static_cast<uint32_t *>(d_result_n), st, nullptr);
+    }
+    const uint64_t pool = std::max<uint64_t>(3ull * top_k, static_cast<uint64_t>(top_k) + 10);
+    if (pool > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "candidate pool %llu exceeds %d", (unsigned long long)pool, RLR_MAX_M);
+    const uint32_t p = static_cast<uint32_t>(std::min<uint64_t>(pool, s->n_rows));
+    if (int rc = enqueue_topm(c, static_cast<const float *>(d_query), w_embed, w_lex, nullptr, nullptr, 0, p, c->d_pool,
+                              c->d_pool_n, st, nullptr))
+        return rc;
+    rlr::MmrArgs a;
+    memset(&a, 0, sizeof a);
+    a.d_emb = s->d_rows; a.pitch = s->pitch; a.dim = s->dim;
+    a.d_cands = c->d_pool; a.d_n = c->d_pool_n;
+    a.row_base = static_cast<uint32_t>(s->row_base); a.use_rows = 1;
+    a.p_cap = p; a.top_k = top_k; a.lambda = lambda;
+    a.d_tri = c->d_tri; a.d_sel_pos = c->d_sel_pos; a.d_sel_n = static_cast<uint32_t *>(d_result_n);
+    a.d_result = static_cast<rlr_cand *>(d_result);
+    a.max_smem_optin = s->smem_optin;
+    uint32_t l = 0;
+    CU_TRY(rlr::mmr_launch(a, st, &l));
+    c->launches += l;
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_time_scan(rlr_ctx *c, const void *d_query, uint32_t m, uint32_t iters, void *stream,
+                             float *out_ms_per_launch)
+{
+    if (!c || !d_query || !out_ms_per_launch || iters == 0) return fail(RLR_ERR_INVALID_ARG, "bad argument");
+    if (m == 0 || m > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "m %u not in 1..%d", m, RLR_MAX_M);
+    rlr_store *s = c->s;
+    if (s->n_rows == 0) return fail(RLR_ERR_INVALID_ARG, "empty store");
+    CU_TRY(cudaSetDevice(s->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rlr::ScanArgs a;
+    memset(&a, 0, sizeof a);
+    rlr::scan_plan(s->sm_count, s->smem_optin, static_cast<uint32_t>(s->n_rows), s->pitch, &a);
+    a.tmap = &s->tmap; a.d_query = static_cast<const float *>(d_query);
+    a.n_rows = static_cast<uint32_t>(s->n_rows); a.row_base = static_cast<uint32_t>(s->row_base); a.pitch = s->pitch;
+    a.w_embed = 0.7f; a.w_lex = 0.3f; a.m = m; a.d_lists = c->d_lists; a.d_counts = c->d_counts;
+    CU_TRY(rlr::scan_launch(a, st)); // warm
+    CU_TRY(cudaEventRecord(c->ev[0], st));
+    for (uint32_t i = 0; i < iters; ++i) CU_TRY(rlr::scan_launch(a, st));
+    CU_TRY(cudaEventRecord(c->ev[1], st));
+    CU_TRY(cudaEventSynchronize(c->ev[1]));
+    c->launches += iters + 1;
+    float ms = 0;
+    CU_TRY(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+    *out_ms_per_launch = ms / iters;
+    return RLR_OK;
+}

@@ -1,0 +1,90 @@
+// kernels.cuh -- host-side launch interface of the sm_100a kernels (internal).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rlr_b200.h"
+
+namespace rlr {
+
+constexpr int kScanRows = 128;        // rows per tile == consumer threads per CTA
+constexpr int kScanChunks = 2;        // 128-byte column chunks per pipeline stage
+constexpr int kScanThreads = kScanRows + 32;
+constexpr int kTopBuf = 2048;         // per-CTA candidate buffer (entries)
+constexpr int kChunkFloats = 32;      // 128 B : the TMA SWIZZLE_128B span
+constexpr int kQueryCap = RLR_MAX_DIM + kChunkFloats * kScanChunks; // floats, zero padded
+
+struct ScanArgs {
+    const CUtensorMap *tmap;   // host pointer; copied into the kernel's param space
+    const float *d_query;      // kQueryCap floats, zero beyond dim
+    uint32_t n_rows;
+    uint32_t row_base;
+    uint32_t pitch;            // floats, multiple of 32
+    float w_embed, w_lex;
+    const uint32_t *d_lex_rows; // sorted ascending, local rows (may be null)
+    const float *d_lex_norm;    // lexical_score per entry (already / max_lexical)
+    uint32_t n_lex;
+    uint32_t m;                // 1..RLR_MAX_M
+    rlr_cand *d_lists;         // grid x m records
+    uint32_t *d_counts;        // grid
+    int grid;                  // CTAs to launch (<= SM count)
+    int smem_bytes;            // dynamic shared memory to request
+    int n_stages;
+};
+
+// Pick grid / stages / smem for a store on a device.
+void scan_plan(int sm_count, int max_smem_optin, uint32_t n_rows, uint32_t pitch, ScanArgs *a);
+cudaError_t scan_configure(); // one-time cudaFuncSetAttribute
+cudaError_t scan_launch(const ScanArgs &a, cudaStream_t stream);
+
+// Merge n_lists lists of m records (zero-key padded) into the best m.  Uses d_tmp
+// (capacity >= merge_tmp_records(n_lists, m) records) for intermediate levels.
+size_t merge_tmp_records(uint32_t n_lists, uint32_t m);
+cudaError_t merge_launch(const rlr_cand *d_lists, uint32_t n_lists, uint32_t m, rlr_cand *d_tmp,
+                         rlr_cand *d_out, uint32_t *d_out_n, cudaStream_t stream, uint32_t *launches);
+
+// MMR: pairwise similarities (upper triangle) + greedy selection.
+//   d_emb/pitch : matrix the candidate embeddings live in
+//   d_cands     : p_cap candidate records (rank order); row index of candidate i is
+//                 (key_row(cand.key) - row_base) when use_rows != 0, else i
+//   d_rel       : optional explicit relevance (else decoded from the keys)
+struct MmrArgs {
+    const float *d_emb;
+    uint32_t pitch, dim;
+    const rlr_cand *d_cands;
+    const uint32_t *d_n;       // number of valid candidates (device)
+    const uint32_t *d_rows;    // optional explicit local rows (overrides keys)
+    const float *d_rel;        // optional explicit relevance
+    uint32_t row_base;
+    int use_rows;
+    uint32_t p_cap;            // launch bound for p
+    uint32_t top_k;
+    float lambda;
+    float *d_tri;              // p_cap*(p_cap-1)/2 floats
+    uint32_t *d_sel_pos;       // top_k (>=1)
+    uint32_t *d_sel_n;
+    rlr_cand *d_result;        // optional: selected records in selection order
+    int max_smem_optin;
+};
+cudaError_t mmr_configure();
+cudaError_t mmr_launch(const MmrArgs &a, cudaStream_t stream, uint32_t *launches);
+
+// gather rows owned by this shard into a dense p x pitch matrix (zeros otherwise)
+cudaError_t gather_launch(const float *d_store, uint32_t pitch, uint32_t n_rows, uint32_t row_base,
+                          const rlr_cand *d_cands, const uint32_t *d_n, uint32_t p_cap, float *d_out,
+                          cudaStream_t stream);
+cudaError_t gather_rows_launch(const float *d_store, uint32_t pitch, const uint32_t *d_rows, uint32_t n,
+                               float *d_out, uint32_t out_pitch, cudaStream_t stream);
+
+// synthetic rows + finite check
+cudaError_t synth_launch(float *d_rows, uint32_t pitch, uint32_t dim, uint64_t row_base, uint32_t n_rows,
+                         int kind, uint64_t seed, uint64_t centroid_seed, uint32_t n_clusters, float sigma,
+                         cudaStream_t stream);
+cudaError_t finite_check_launch(const float *d_rows, uint64_t n_floats, uint32_t *d_flag, cudaStream_t stream);
+
+// copy a selected subset of records into SoA output arrays (host-facing results)
+cudaError_t unpack_launch(const rlr_cand *d_cands, const uint32_t *d_n, uint32_t cap, uint32_t *d_rows,
+                          float *d_score, float *d_emb, float *d_lex, cudaStream_t stream);
+
+} // namespace rlr

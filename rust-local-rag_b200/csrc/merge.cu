@@ -1,0 +1,125 @@
+// merge.cu -- reduce several rank-ordered candidate lists to the best m.
+//
+// Completes the "stable sort desc + take(initial_k)" of RagEngine::search
+// (/root/reference/src/rag_engine.rs:543-548) across the per-CTA lists of scan_topm.cu
+// and, on the multi-GPU path, across the all-gathered per-GPU lists.
+// Keys are unique (they embed the global row), so the merge is order-exact.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace rlr {
+
+namespace {
+
+constexpr int kMergeThreads = 1024;
+constexpr uint32_t kMergeCap = 4096; // entries sorted per block
+
+__global__ void __launch_bounds__(kMergeThreads, 1)
+merge_kernel(const rlr_cand *__restrict__ in, uint32_t n_lists, uint32_t m, uint32_t lists_per_block,
+             rlr_cand *__restrict__ out, uint32_t *__restrict__ out_n)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *src = reinterpret_cast<uint32_t *>(smem_raw + kMergeCap * 8);
+
+    const uint32_t t = threadIdx.x;
+    const uint32_t l0 = blockIdx.x * lists_per_block;
+    uint32_t l1 = l0 + lists_per_block;
+    if (l1 > n_lists) l1 = n_lists;
+    const uint32_t n_in = (l1 - l0) * m;
+    const rlr_cand *base = in + static_cast<size_t>(l0) * m;
+
+    uint32_t n2 = 1;
+    while (n2 < n_in) n2 <<= 1;
+    for (uint32_t i = t; i < n2; i += kMergeThreads) {
+        keys[i] = i < n_in ? base[i].key : 0ull;
+        src[i] = i;
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= n2; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = t; i < (n2 >> 1); i += kMergeThreads) {
+                const uint32_t lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                const uint32_t hi = lo | j;
+                const uint64_t a = keys[lo], b = keys[hi];
+                const bool desc = (lo & k) == 0;
+                if ((a < b) == desc) {
+                    keys[lo] = b; keys[hi] = a;
+                    const uint32_t sa = src[lo], sb = src[hi];
+                    src[lo] = sb; src[hi] = sa;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    rlr_cand *o = out + static_cast<size_t>(blockIdx.x) * m;
+    for (uint32_t i = t; i < m; i += kMergeThreads) {
+        rlr_cand c;
+        c.key = i < n2 ? keys[i] : 0ull;
+        if (c.key != 0ull) {
+            const rlr_cand s = base[src[i]];
+            c.emb = s.emb; c.lex = s.lex;
+        } else {
+            c.emb = 0.0f; c.lex = 0.0f;
+        }
+        o[i] = c;
+    }
+    if (out_n != nullptr && gridDim.x == 1) {
+        // number of valid records among the first m (keys are sorted, zeros last)
+        __shared__ uint32_t s_n;
+        if (t == 0) s_n = 0;
+        __syncthreads();
+        uint32_t local = 0;
+        for (uint32_t i = t; i < m && i < n2; i += kMergeThreads) local += keys[i] != 0ull;
+        if (local) atomicAdd(&s_n, local);
+        __syncthreads();
+        if (t == 0) *out_n = s_n;
+    }
+}
+
+inline uint32_t lists_per_block(uint32_t m)
+{
+    uint32_t l = kMergeCap / m;
+    return l < 2 ? 2 : l;
+}
+
+} // namespace
+
+size_t merge_tmp_records(uint32_t n_lists, uint32_t m)
+{
+    const uint32_t lpb = lists_per_block(m);
+    const size_t nb = (n_lists + lpb - 1) / lpb;
+    return 2 * nb * m + m;
+}
+
+cudaError_t merge_launch(const rlr_cand *d_lists, uint32_t n_lists, uint32_t m, rlr_cand *d_tmp, rlr_cand *d_out,
+                         uint32_t *d_out_n, cudaStream_t stream, uint32_t *launches)
+{
+    static bool configured = false;
+    const int smem = kMergeCap * 12;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const uint32_t lpb = lists_per_block(m);
+    const rlr_cand *cur = d_lists;
+    uint32_t n = n_lists;
+    const size_t half = ((n_lists + lpb - 1) / lpb) * static_cast<size_t>(m);
+    int ping = 0;
+    for (;;) {
+        const uint32_t nb = (n + lpb - 1) / lpb;
+        rlr_cand *dst = nb == 1 ? d_out : d_tmp + (ping ? half : 0);
+        merge_kernel<<<nb, kMergeThreads, smem, stream>>>(cur, n, m, lpb, dst, nb == 1 ? d_out_n : nullptr);
+        if (launches) ++*launches;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (nb == 1) break;
+        cur = dst;
+        n = nb;
+        ping ^= 1;
+    }
+    return cudaSuccess;
+}
+
+} // namespace rlr

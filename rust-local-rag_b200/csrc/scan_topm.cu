@@ -1,0 +1,281 @@
+// scan_topm.cu -- kernels (1)+(2): exhaustive exact-order cosine scan fused with a
+// per-CTA top-M, for sm_100a.
+//
+// Replaces the hot loop + sort + cut of RagEngine::search,
+// /root/reference/src/rag_engine.rs:524-548 (dot_product per chunk :526, blend :531-532,
+// stable sort desc :543, take(initial_k) :546), without ever writing an N-length score
+// array to HBM.
+//
+// Design (HBM-bound):
+//   * the store is a row-major f32 matrix with 128-byte-aligned rows.  A persistent CTA
+//     per SM streams tiles of 128 rows through a ring of shared-memory stages with TMA
+//     (cp.async.bulk.tensor.2d, SWIZZLE_128B, L2 evict-first), one producer lane.
+//   * each of the 128 consumer threads owns ONE row of the tile and accumulates
+//     q[i]*row[i] strictly left to right with separate mul/add roundings, i.e. the
+//     reference's exact f32 result.  The 128B swizzle makes the per-thread row walk
+//     (LDS.128 at row*128 + (chunk ^ (row&7))*16) bank-conflict free; q is a broadcast
+//     read.  The FP32 pipe needs ~0.25 of its issue slots for this, so the sequential
+//     order costs nothing against the HBM roofline.
+//   * scores are blended (w_e*e + w_l*lex) and encoded as rank keys; a warp ballot +
+//     one shared atomic appends the keys that beat the CTA's running M-th best to a
+//     2048-entry buffer that is pruned with a bitonic sort when it fills.
+//   * each CTA writes its best M records; merge.cu reduces the <=148 lists.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace rlr {
+
+namespace {
+
+constexpr int R = kScanRows;
+constexpr int CH = kScanChunks;
+constexpr uint32_t kBoxBytes = R * 128;            // one TMA box: 128 rows x 128 B
+constexpr uint32_t kStageBytes = CH * kBoxBytes;
+
+struct SmemLayout {
+    uint32_t stages_off, q_off, keys_off, embs_off, bars_off, misc_off, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int n_stages, uint32_t q_floats)
+{
+    SmemLayout L;
+    uint32_t o = 0;
+    L.stages_off = o; o += n_stages * kStageBytes;
+    L.q_off = o;      o += q_floats * 4;
+    L.keys_off = o;   o += kTopBuf * 8;
+    L.embs_off = o;   o += kTopBuf * 4;
+    L.bars_off = o;   o += n_stages * 16;
+    L.misc_off = o;   o += 32;
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ float lex_lookup(const uint32_t *__restrict__ rows, const float *__restrict__ vals,
+                                            uint32_t n, uint32_t row)
+{
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        uint32_t r = __ldg(rows + mid);
+        if (r < row) lo = mid + 1; else hi = mid;
+    }
+    if (lo < n && __ldg(rows + lo) == row) return __ldg(vals + lo);
+    return 0.0f;
+}
+
+// Bitonic sort (descending) of n = 2^k entries (key, emb payload) in shared memory by
+// the R consumer threads.
+__device__ void bitonic_desc(uint64_t *keys, float *embs, uint32_t n, uint32_t t)
+{
+    for (uint32_t k = 2; k <= n; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = t; i < (n >> 1); i += R) {
+                uint32_t lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                uint32_t hi = lo | j;
+                uint64_t a = keys[lo], b = keys[hi];
+                bool desc = (lo & k) == 0;
+                if ((a < b) == desc) {
+                    keys[lo] = b; keys[hi] = a;
+                    float ea = embs[lo], eb = embs[hi];
+                    embs[lo] = eb; embs[hi] = ea;
+                }
+            }
+            named_bar_sync(1, R);
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t next_pow2(uint32_t x)
+{
+    return x <= 1 ? 1u : 1u << (32 - __clz(x - 1));
+}
+
+__global__ void __launch_bounds__(kScanThreads, 1)
+scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ g_query,
+                 uint32_t n_rows, uint32_t row_base, uint32_t n_chunks, float w_embed, float w_lex,
+                 const uint32_t *__restrict__ lex_rows, const float *__restrict__ lex_norm, uint32_t n_lex,
+                 uint32_t m, int n_stages, rlr_cand *__restrict__ g_lists, uint32_t *__restrict__ g_counts)
+{
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B atoms are 1024 B: align the carve-up by hand.
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+    uint8_t *smem = smem_raw + pad;
+
+    const uint32_t KB = (n_chunks + CH - 1) / CH;      // pipeline stages consumed per tile
+    const uint32_t q_floats = KB * CH * kChunkFloats;
+    const SmemLayout L = smem_layout(n_stages, q_floats);
+
+    float *q_s = reinterpret_cast<float *>(smem + L.q_off);
+    uint64_t *keys = reinterpret_cast<uint64_t *>(smem + L.keys_off);
+    float *embs = reinterpret_cast<float *>(smem + L.embs_off);
+    volatile uint32_t *s_count = reinterpret_cast<volatile uint32_t *>(smem + L.misc_off);
+    volatile uint64_t *s_tau = reinterpret_cast<volatile uint64_t *>(smem + L.misc_off + 8);
+    const uint32_t stages_addr = smem_u32(smem + L.stages_off);
+    const uint32_t full_bar = smem_u32(smem + L.bars_off);
+    const uint32_t empty_bar = full_bar + n_stages * 8;
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t warp = tid >> 5, lane = tid & 31;
+    const uint32_t n_tiles = (n_rows + R - 1) / R;
+
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s) {
+            mbar_init(full_bar + s * 8, 1);
+            mbar_init(empty_bar + s * 8, R / 32);
+        }
+        *s_count = 0;
+        *s_tau = 0;
+        fence_mbar_init();
+    }
+    for (uint32_t i = tid; i < q_floats; i += kScanThreads) q_s[i] = g_query[i];
+    __syncthreads();
+
+    if (warp == R / 32) {
+        // ------------------------------ TMA producer ------------------------------
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap);
+            const uint64_t pol = policy_evict_first();
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (uint32_t kb = 0; kb < KB; ++kb) {
+                    mbar_wait(empty_bar + stage * 8, phase ^ 1);
+                    mbar_arrive_expect_tx(full_bar + stage * 8, kStageBytes);
+#pragma unroll
+                    for (int c = 0; c < CH; ++c)
+                        tma_load_2d(stages_addr + stage * kStageBytes + c * kBoxBytes, &tmap,
+                                    static_cast<int32_t>((kb * CH + c) * kChunkFloats),
+                                    static_cast<int32_t>(tile * R), full_bar + stage * 8, pol);
+                    if (++stage == static_cast<uint32_t>(n_stages)) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+
+    // --------------------------------- consumers ---------------------------------
+    const uint32_t t = tid;                       // row of the tile owned by this thread
+    const uint32_t xr = (t & 7u) << 4;            // SWIZZLE_128B: 16B-chunk index ^= row & 7
+    const uint8_t *stage0 = smem + L.stages_off + t * 128;
+    const float4 *q4 = reinterpret_cast<const float4 *>(q_s);
+    uint32_t stage = 0, phase = 0;
+    uint64_t tau = 0;                             // key of the CTA's current M-th best
+
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        float acc = 0.0f;
+        for (uint32_t kb = 0; kb < KB; ++kb) {
+            mbar_wait(full_bar + stage * 8, phase);
+            const uint8_t *sp = stage0 + stage * kStageBytes;
+            const float4 *qp = q4 + kb * (CH * 8);
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 v = *reinterpret_cast<const float4 *>(sp + c * kBoxBytes + ((j << 4) ^ xr));
+                    const float4 w = qp[c * 8 + j];
+                    acc = add_rn(acc, mul_rn(w.x, v.x));
+                    acc = add_rn(acc, mul_rn(w.y, v.y));
+                    acc = add_rn(acc, mul_rn(w.z, v.z));
+                    acc = add_rn(acc, mul_rn(w.w, v.w));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar + stage * 8);
+            if (++stage == static_cast<uint32_t>(n_stages)) { stage = 0; phase ^= 1; }
+        }
+
+        // ---- blend (:531-532) and offer to the CTA's top-M ----
+        const uint32_t row_local = tile * R + t;
+        float lexv = 0.0f;
+        if (n_lex) lexv = lex_lookup(lex_rows, lex_norm, n_lex, row_local);
+        const float combined = add_rn(mul_rn(w_embed, acc), mul_rn(w_lex, lexv));
+        const uint64_t key = make_key(combined, row_base + row_local);
+        const bool pass = (row_local < n_rows) && (key > tau);
+        const uint32_t mask = __ballot_sync(0xffffffffu, pass);
+        if (mask) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(const_cast<uint32_t *>(s_count), __popc(mask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) {
+                const uint32_t idx = base + __popc(mask & ((1u << lane) - 1u));
+                keys[idx] = key;
+                embs[idx] = acc;
+            }
+        }
+        named_bar_sync(1, R);
+        const uint32_t cnt = *s_count;
+        named_bar_sync(1, R);
+        if (cnt > kTopBuf - R) {
+            // prune: keep the best m, raise the threshold
+            for (uint32_t i = cnt + t; i < kTopBuf; i += R) keys[i] = 0;
+            named_bar_sync(1, R);
+            bitonic_desc(keys, embs, kTopBuf, t);
+            if (t == 0) {
+                *s_count = cnt < m ? cnt : m;
+                *s_tau = cnt >= m ? keys[m - 1] : 0;
+            }
+            named_bar_sync(1, R);
+            tau = *s_tau;
+        }
+    }
+
+    // ---- final: sort what is left, write the CTA's best m records ----
+    named_bar_sync(1, R);
+    const uint32_t cnt = *s_count;
+    const uint32_t n2 = next_pow2(cnt);
+    for (uint32_t i = cnt + t; i < n2; i += R) keys[i] = 0;
+    named_bar_sync(1, R);
+    bitonic_desc(keys, embs, n2, t);
+    const uint32_t keep = cnt < m ? cnt : m;
+    rlr_cand *out = g_lists + static_cast<size_t>(blockIdx.x) * m;
+    for (uint32_t i = t; i < m; i += R) {
+        rlr_cand c;
+        if (i < keep) {
+            c.key = keys[i];
+            c.emb = embs[i];
+            c.lex = n_lex ? lex_lookup(lex_rows, lex_norm, n_lex, key_row(c.key) - row_base) : 0.0f;
+        } else {
+            c.key = 0; c.emb = 0.0f; c.lex = 0.0f;
+        }
+        out[i] = c;
+    }
+    if (t == 0) g_counts[blockIdx.x] = keep;
+}
+
+} // namespace
+
+void scan_plan(int sm_count, int max_smem_optin, uint32_t n_rows, uint32_t pitch, ScanArgs *a)
+{
+    const uint32_t n_chunks = pitch / kChunkFloats;
+    const uint32_t KB = (n_chunks + CH - 1) / CH;
+    const uint32_t q_floats = KB * CH * kChunkFloats;
+    const uint32_t n_tiles = (n_rows + R - 1) / R;
+    int grid = sm_count;
+    if (static_cast<uint32_t>(grid) > n_tiles) grid = static_cast<int>(n_tiles);
+    if (grid < 1) grid = 1;
+    // as many stages as fit (1 KB slack for the manual 1024 B alignment)
+    int stages = 8;
+    while (stages > 2 && smem_layout(stages, q_floats).total + 1024 > static_cast<uint32_t>(max_smem_optin)) --stages;
+    a->grid = grid;
+    a->n_stages = stages;
+    a->smem_bytes = static_cast<int>(smem_layout(stages, q_floats).total + 1024);
+}
+
+cudaError_t scan_configure()
+{
+    int dev = 0, optin = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(scan_topm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+}
+
+cudaError_t scan_launch(const ScanArgs &a, cudaStream_t stream)
+{
+    scan_topm_kernel<<<a.grid, kScanThreads, a.smem_bytes, stream>>>(
+        *a.tmap, a.d_query, a.n_rows, a.row_base, a.pitch / kChunkFloats, a.w_embed, a.w_lex, a.d_lex_rows,
+        a.d_lex_norm, a.n_lex, a.m, a.n_stages, a.d_lists, a.d_counts);
+    return cudaGetLastError();
+}
+
+} // namespace rlr

@@ -1,0 +1,104 @@
+// synth.cu -- synthetic unit-norm embedding rows generated on the device, plus the
+// non-finite check for uploaded rows.
+//
+// Inputs for the benchmark configurations of BASELINE.json: the values
+// come from a counter-based hash (bit-reproducible by oracle/rlr_oracle.c:orc_synth_rows)
+// and every row is normalised with the reference's own arithmetic,
+// /root/reference/src/rag_engine.rs:1763-1771 (sequential sum of squares, sqrt, true
+// division per element), so a device-generated store is bit-identical to one the host
+// would have normalised and uploaded.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace rlr {
+
+namespace {
+
+constexpr int kRowsPerBlock = 128;
+
+__device__ __forceinline__ float synth_value(int kind, uint64_t seed, uint64_t centroid_seed, uint32_t n_clusters,
+                                             float sigma, uint64_t row, uint32_t dim, uint32_t c)
+{
+    float u = hash_uniform(seed, row * dim + c);
+    if (kind == RLR_SYNTH_CLUSTERED) {
+        const uint64_t cl = row % n_clusters;
+        const float ce = hash_uniform(centroid_seed, cl * dim + c);
+        u = add_rn(ce, mul_rn(sigma, u));
+    }
+    return u;
+}
+
+// One thread per row (sequential arithmetic), 32-column tiles transposed through shared
+// memory so that the global stores are 128-byte coalesced.
+__global__ void __launch_bounds__(kRowsPerBlock)
+synth_kernel(float *__restrict__ out, uint32_t pitch, uint32_t dim, uint64_t row_base, uint32_t n_rows, int kind,
+             uint64_t seed, uint64_t centroid_seed, uint32_t n_clusters, float sigma)
+{
+    __shared__ float tile[kRowsPerBlock][33];
+    const uint32_t t = threadIdx.x;
+    const uint32_t r_local = blockIdx.x * kRowsPerBlock + t;
+    const uint64_t row = row_base + r_local;
+    const bool valid = r_local < n_rows;
+
+    float norm_sq = 0.0f;
+    if (valid)
+        for (uint32_t c = 0; c < dim; ++c) {
+            const float x = synth_value(kind, seed, centroid_seed, n_clusters, sigma, row, dim, c);
+            norm_sq = add_rn(norm_sq, mul_rn(x, x));
+        }
+    const bool scale = norm_sq > 1e-20f;
+    const float norm = __fsqrt_rn(norm_sq); // IEEE round-to-nearest
+
+    const uint32_t warp = t >> 5, lane = t & 31;
+    for (uint32_t c0 = 0; c0 < pitch; c0 += 32) {
+        if (valid)
+            for (uint32_t j = 0; j < 32; ++j) {
+                const uint32_t c = c0 + j;
+                float x = 0.0f;
+                if (c < dim) {
+                    x = synth_value(kind, seed, centroid_seed, n_clusters, sigma, row, dim, c);
+                    if (scale) x = __fdiv_rn(x, norm);
+                }
+                tile[t][j] = x;
+            }
+        __syncwarp();
+        // warp w writes its own 32 rows: lane = column
+        for (uint32_t r = 0; r < 32; ++r) {
+            const uint32_t rl = blockIdx.x * kRowsPerBlock + warp * 32 + r;
+            if (rl < n_rows) out[static_cast<size_t>(rl) * pitch + c0 + lane] = tile[warp * 32 + r][lane];
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void finite_check_kernel(const float4 *__restrict__ v, uint64_t n4, uint32_t *flag)
+{
+    bool bad = false;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const float4 x = __ldg(v + i);
+        bad |= !is_finite_f32(x.x) | !is_finite_f32(x.y) | !is_finite_f32(x.z) | !is_finite_f32(x.w);
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+
+} // namespace
+
+cudaError_t synth_launch(float *d_rows, uint32_t pitch, uint32_t dim, uint64_t row_base, uint32_t n_rows, int kind,
+                         uint64_t seed, uint64_t centroid_seed, uint32_t n_clusters, float sigma, cudaStream_t stream)
+{
+    if (n_rows == 0) return cudaSuccess;
+    const uint32_t blocks = (n_rows + kRowsPerBlock - 1) / kRowsPerBlock;
+    synth_kernel<<<blocks, kRowsPerBlock, 0, stream>>>(d_rows, pitch, dim, row_base, n_rows, kind, seed, centroid_seed,
+                                                       n_clusters ? n_clusters : 1, sigma);
+    return cudaGetLastError();
+}
+
+cudaError_t finite_check_launch(const float *d_rows, uint64_t n_floats, uint32_t *d_flag, cudaStream_t stream)
+{
+    if (n_floats == 0) return cudaSuccess;
+    finite_check_kernel<<<148 * 8, 256, 0, stream>>>(reinterpret_cast<const float4 *>(d_rows), n_floats / 4, d_flag);
+    return cudaGetLastError();
+}
+
+} // namespace rlr

@@ -1,0 +1,388 @@
+"""Host-side mirror of the reference's `RagEngine` for the retrieval path, above the C ABI.
+
+Same method names, argument meaning and error behaviour as
+/root/reference/src/rag_engine.rs: `search` (:470), `search_with_diversity` (:717),
+`get_embedding_candidates` (:415), `QueryWeights` (:1846), `SearchResult` (:72-100), and the
+API clamps of src/mcp_server.rs:81-110 (`search_documents`).  Everything numeric happens in
+librlr_b200.so on the GPU; this file only keeps the `row -> chunk` table, resolves weights
+and formats results.  There is no CPU fallback: without the CUDA library / a B200 every
+search raises RlrError.
+
+The embedding service (Ollama HTTP, src/embeddings.rs) and the reranker are out of scope;
+`query` is therefore either an embedding vector or a string handed to a caller-supplied
+`embedder` callable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import binding as B
+
+MAX_TOP_K = 100  # src/mcp_server.rs:364
+
+
+@dataclass
+class QueryWeights:
+    """src/rag_engine.rs:1846-1863 -- all fields Option<f32>."""
+    embedding: Optional[float] = None
+    lexical: Optional[float] = None
+    reranker: Optional[float] = None
+    initial: Optional[float] = None
+
+    def to_c(self) -> B.QueryWeightsC:
+        c = B.QueryWeightsC()
+        has = 0
+        for bit, name in enumerate(("embedding", "lexical", "reranker", "initial")):
+            v = getattr(self, name)
+            if v is not None:
+                setattr(c, name, float(v))
+                has |= 1 << bit
+        c.has = has
+        return c
+
+
+@dataclass
+class ResolvedWeights:
+    embedding: float
+    lexical: float
+    reranker: float
+    initial: float
+
+
+def resolve_weights(weights: Optional[QueryWeights]) -> ResolvedWeights:
+    """ResolvedWeights::from_query_weights, src/rag_engine.rs:1888-1896."""
+    lib = B.load()
+    out = B.ResolvedWeightsC()
+    B.check(lib.rlr_resolve_weights(C.byref(weights.to_c()) if weights is not None else None, C.byref(out)))
+    return ResolvedWeights(out.embedding, out.lexical, out.reranker, out.initial)
+
+
+@dataclass
+class DocumentChunk:
+    """src/rag_engine.rs:46-59 minus the embedding (which lives on the device)."""
+    id: str
+    document_name: str = ""
+    text: str = ""
+    chunk_index: int = 0
+    page_number: int = 0
+    section: Optional[str] = None
+    metadata: dict = field(default_factory=dict)
+
+
+@dataclass
+class SearchResult:
+    """src/rag_engine.rs:72-100."""
+    text: str
+    score: float
+    document: str
+    chunk_id: str
+    chunk_index: int
+    page_number: int
+    section: Optional[str]
+    embedding_score: Optional[float] = None
+    lexical_score: Optional[float] = None
+    initial_score: Optional[float] = None
+    reranker_score: Optional[float] = None
+    yes_logprob: Optional[float] = None
+    no_logprob: Optional[float] = None
+    row: int = -1  # position in the device store (not in the reference struct)
+
+    def to_json(self) -> dict:
+        d = {"text": self.text, "score": self.score, "document": self.document, "chunk_id": self.chunk_id,
+             "chunk_index": self.chunk_index, "page_number": self.page_number, "section": self.section}
+        for k in ("embedding_score", "lexical_score", "initial_score", "reranker_score", "yes_logprob", "no_logprob"):
+            v = getattr(self, k)
+            if v is not None:  # skip_serializing_if = "Option::is_none"
+                d[k] = v
+        return d
+
+
+def sanitize_model_name(model_name: str) -> str:
+    """src/rag_engine.rs:1435-1462."""
+    trimmed = model_name.strip()
+    if not trimmed:
+        return "default"
+    s = "".join(c if (c.isascii() and c.isalnum()) or c in "-_." else "_" for c in trimmed)
+    if not s or all(c in "_." for c in s):
+        return "default"
+    return s
+
+
+def get_index_path(data_dir: str, model_name: str) -> str:
+    """src/rag_engine.rs:1465-1468."""
+    return os.path.join(data_dir, f"chunks_{sanitize_model_name(model_name)}.json")
+
+
+class DeviceStore:
+    """Owns one rlr_store handle."""
+
+    def __init__(self, handle, lib):
+        self._h = handle
+        self._lib = lib
+
+    @classmethod
+    def from_rows(cls, rows: np.ndarray, device: int = 0, row_base: int = 0, flags: int = 0) -> "DeviceStore":
+        lib = B.load()
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        if rows.ndim != 2:
+            raise ValueError("rows must be (n, dim)")
+        n, dim = rows.shape
+        h = C.c_void_p()
+        B.check(lib.rlr_store_create(device, dim, n, B.ptr(rows) if n else None, dim, row_base, flags, C.byref(h)))
+        return cls(h, lib)
+
+    @classmethod
+    def empty(cls, n_rows: int, dim: int, device: int = 0, row_base: int = 0, flags: int = 0) -> "DeviceStore":
+        lib = B.load()
+        h = C.c_void_p()
+        B.check(lib.rlr_store_create(device, dim, n_rows, None, dim, row_base, flags, C.byref(h)))
+        return cls(h, lib)
+
+    @classmethod
+    def synthetic(cls, n_rows: int, dim: int, kind: int = B.RLR_SYNTH_IID, seed: int = 0x5EED0001,
+                  centroid_seed: int = 0x5EED00C0, n_clusters: int = 4096, sigma: float = 0.65,
+                  device: int = 0, row_base: int = 0) -> "DeviceStore":
+        s = cls.empty(n_rows, dim, device=device, row_base=row_base)
+        B.check(s._lib.rlr_store_fill_synthetic(s._h, kind, seed, centroid_seed, n_clusters, sigma))
+        return s
+
+    @property
+    def handle(self):
+        return self._h
+
+    def info(self) -> B.StoreInfoC:
+        out = B.StoreInfoC()
+        B.check(self._lib.rlr_store_info_get(self._h, C.byref(out)))
+        return out
+
+    def read_rows(self, rows: Sequence[int]) -> np.ndarray:
+        r = np.ascontiguousarray(rows, dtype=np.uint32)
+        out = np.empty((len(r), self.info().dim), dtype=np.float32)
+        B.check(self._lib.rlr_store_read_rows(self._h, B.ptr(r), len(r), B.ptr(out)))
+        return out
+
+    def upload(self, row0: int, rows: np.ndarray) -> None:
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        B.check(self._lib.rlr_store_upload(self._h, row0, rows.shape[0], B.ptr(rows), rows.shape[1]))
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.rlr_store_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- raw hot-path calls (numpy in / numpy out) ----
+    def search_topm(self, query: np.ndarray, m: int, w: ResolvedWeights, lex_rows=None, lex_scores=None,
+                    flags: int = 0):
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        rows = np.empty(m, np.uint32); comb = np.empty(m, np.float32)
+        emb = np.empty(m, np.float32); lex = np.empty(m, np.float32)
+        n = C.c_uint32(0)
+        wc = B.ResolvedWeightsC(w.embedding, w.lexical, w.reranker, w.initial)
+        lr = np.ascontiguousarray(lex_rows, dtype=np.uint32) if lex_rows is not None and len(lex_rows) else None
+        ls = np.ascontiguousarray(lex_scores, dtype=np.float32) if lr is not None else None
+        B.check(self._lib.rlr_search_topm(self._h, B.ptr(q), q.shape[0], flags, C.byref(wc), B.ptr(lr), B.ptr(ls),
+                                          0 if lr is None else len(lr), m, B.ptr(rows), B.ptr(comb), B.ptr(emb),
+                                          B.ptr(lex), C.byref(n)))
+        k = n.value
+        return rows[:k], comb[:k], emb[:k], lex[:k]
+
+    def mmr(self, cand_rows, relevance, top_k: int, lam: float, flags: int = 0) -> np.ndarray:
+        r = np.ascontiguousarray(cand_rows, dtype=np.uint32)
+        rel = np.ascontiguousarray(relevance, dtype=np.float32)
+        out = np.empty(max(len(r), 1), np.uint32)
+        n = C.c_uint32(0)
+        B.check(self._lib.rlr_mmr(self._h, B.ptr(r) if len(r) else None, B.ptr(rel) if len(r) else None, len(r),
+                                  top_k, lam, flags, B.ptr(out), C.byref(n)))
+        return out[:n.value]
+
+    def search_mmr(self, query: np.ndarray, top_k: int, diversity: float, w: ResolvedWeights, lex_rows=None,
+                   lex_scores=None, flags: int = 0):
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        cap = max(top_k, 1)
+        rows = np.empty(cap, np.uint32); score = np.empty(cap, np.float32)
+        emb = np.empty(cap, np.float32); lex = np.empty(cap, np.float32)
+        n = C.c_uint32(0)
+        wc = B.ResolvedWeightsC(w.embedding, w.lexical, w.reranker, w.initial)
+        lr = np.ascontiguousarray(lex_rows, dtype=np.uint32) if lex_rows is not None and len(lex_rows) else None
+        ls = np.ascontiguousarray(lex_scores, dtype=np.float32) if lr is not None else None
+        B.check(self._lib.rlr_search_mmr(self._h, B.ptr(q), q.shape[0], flags, top_k, diversity, C.byref(wc),
+                                         B.ptr(lr), B.ptr(ls), 0 if lr is None else len(lr), B.ptr(rows),
+                                         B.ptr(score), B.ptr(emb), B.ptr(lex), C.byref(n)))
+        k = n.value
+        return rows[:k], score[:k], emb[:k], lex[:k]
+
+    def embedding_candidates(self, query: np.ndarray, count: int, flags: int = 0):
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        rows = np.empty(max(count, 1), np.uint32); score = np.empty(max(count, 1), np.float32)
+        n = C.c_uint32(0)
+        B.check(self._lib.rlr_embedding_candidates(self._h, B.ptr(q), q.shape[0], flags, count, B.ptr(rows),
+                                                   B.ptr(score), C.byref(n)))
+        return rows[:n.value], score[:n.value]
+
+    def last_timings(self) -> B.TimingsC:
+        t = B.TimingsC()
+        B.check(self._lib.rlr_last_timings(C.byref(t)))
+        return t
+
+
+Query = Union[str, Sequence[float], np.ndarray]
+LexicalFn = Callable[[str, int], List[Tuple[str, float]]]
+
+
+class RagEngine:
+    """The retrieval half of the reference's RagEngine (src/rag_engine.rs:104-113): chunk
+    metadata on the host, embeddings on the device."""
+
+    def __init__(self, chunks: List[DocumentChunk], store: DeviceStore, model: str = "nomic-embed-text",
+                 embedder: Optional[Callable[[str], Sequence[float]]] = None,
+                 lexical: Optional[LexicalFn] = None):
+        self.chunks = chunks                     # row -> chunk (the `row -> chunk_id` table)
+        self.row_of = {c.id: i for i, c in enumerate(chunks)}
+        self.store = store
+        self.model = model
+        self.embedder = embedder
+        self.lexical = lexical                   # LexicalIndex::score stand-in (host, out of scope)
+        self.needs_reindex = False
+        self.document_hashes = {}
+
+    # ---- construction ----
+    @classmethod
+    def load_from_disk(cls, data_dir: str, model: str = "nomic-embed-text", device: int = 0, **kw) -> "RagEngine":
+        """load_from_disk + apply_loaded_state, src/rag_engine.rs:1520-1696, for the
+        model-specific file `chunks_{sanitized}.json` (:1465-1468)."""
+        return cls.from_chunks_json(get_index_path(data_dir, model), model=model, device=device, **kw)
+
+    @classmethod
+    def from_chunks_json(cls, path: str, model: str = "nomic-embed-text", device: int = 0, **kw) -> "RagEngine":
+        with open(path, "r", encoding="utf-8") as f:
+            state = json.load(f)
+        version = int(state["version"])
+        chunks_map = state.get("chunks", {})
+        if version < 2:                          # :1664-1673 outdated index: wipe, mark for reindex
+            eng = cls([], DeviceStore.from_rows(np.zeros((0, 1), np.float32), device=device), model=model, **kw)
+            eng.needs_reindex = True
+            return eng
+        # HashMap iteration order is arbitrary in the reference; rows here follow file order.
+        metas: List[DocumentChunk] = []
+        dim = None
+        embs = []
+        for cid, ch in chunks_map.items():
+            e = np.asarray(ch["embedding"], dtype=np.float32)
+            if dim is None:
+                dim = e.shape[0]
+            elif e.shape[0] != dim:
+                raise ValueError(f"chunk {cid}: embedding has {e.shape[0]} dims, expected {dim}")
+            embs.append(e)
+            metas.append(DocumentChunk(id=ch.get("id", cid), document_name=ch.get("document_name", ""),
+                                       text=ch.get("text", ""), chunk_index=int(ch.get("chunk_index", 0)),
+                                       page_number=int(ch.get("page_number", 0)), section=ch.get("section"),
+                                       metadata=ch.get("metadata") or {}))
+        rows = np.stack(embs) if embs else np.zeros((0, 1), np.float32)
+        lib = B.load()
+        for i in range(rows.shape[0]):           # :1678-1680 re-normalise every embedding at load
+            B.check(lib.rlr_normalize(rows[i].ctypes.data_as(C.POINTER(C.c_float)), rows.shape[1]))
+        eng = cls(metas, DeviceStore.from_rows(rows, device=device), model=model, **kw)
+        eng.needs_reindex = bool(state.get("needs_reindex", False))
+        eng.document_hashes = dict(state.get("document_hashes", {}))
+        if not eng.document_hashes and metas:    # :1686-1691
+            eng.needs_reindex = True
+        return eng
+
+    @classmethod
+    def from_rows(cls, rows: np.ndarray, chunk_ids: Optional[Sequence[str]] = None, normalize: bool = True,
+                  device: int = 0, **kw) -> "RagEngine":
+        rows = np.array(rows, dtype=np.float32, order="C")
+        if normalize:                            # :359 normalise at insert
+            lib = B.load()
+            for i in range(rows.shape[0]):
+                B.check(lib.rlr_normalize(rows[i].ctypes.data_as(C.POINTER(C.c_float)), rows.shape[1]))
+        ids = list(chunk_ids) if chunk_ids is not None else [f"chunk-{i}" for i in range(rows.shape[0])]
+        metas = [DocumentChunk(id=i) for i in ids]
+        return cls(metas, DeviceStore.from_rows(rows, device=device), **kw)
+
+    # ---- helpers ----
+    def _embed(self, query: Query) -> np.ndarray:
+        if isinstance(query, str):
+            if self.embedder is None:
+                raise B.RlrError(B.RLR_ERR_INVALID_ARG, "string query but no embedder configured "
+                                 "(EmbeddingService is out of scope; pass an embedding)")
+            return np.asarray(self.embedder(query), dtype=np.float32)
+        return np.asarray(query, dtype=np.float32)
+
+    def _lex(self, query: Query, top_k: int):
+        if self.lexical is None or not isinstance(query, str):
+            return None, None
+        pairs = self.lexical(query, top_k * 5)   # :505 lexical_index.score(query, top_k*5)
+        rows, scores = [], []
+        for cid, sc in pairs:
+            r = self.row_of.get(cid)
+            if r is not None:
+                rows.append(r); scores.append(sc)
+        return (np.asarray(rows, np.uint32), np.asarray(scores, np.float32)) if rows else (None, None)
+
+    def _result(self, row: int, score: float, emb: float, lex: float) -> SearchResult:
+        ch = self.chunks[row]
+        # fallback-fill fields, :680-695 (no reranker => reranker fields None)
+        return SearchResult(text=ch.text, score=float(score), document=ch.document_name, chunk_id=ch.id,
+                            chunk_index=ch.chunk_index, page_number=ch.page_number, section=ch.section,
+                            embedding_score=float(emb), lexical_score=float(lex), initial_score=float(score),
+                            row=int(row))
+
+    # ---- the reference's public methods ----
+    def search(self, query: Query, top_k: int, weights: Optional[QueryWeights] = None) -> List[SearchResult]:
+        """RagEngine::search, :470-701 (reranker absent)."""
+        if not self.chunks:                      # :476-478
+            return []
+        w = resolve_weights(weights)             # :481
+        top_k = max(int(top_k), 1)               # :490
+        q = self._embed(query)
+        lr, ls = self._lex(query, top_k)
+        rows, comb, emb, lex = self.store.search_topm(q, top_k, w, lr, ls)
+        return [self._result(r, c, e, l) for r, c, e, l in zip(rows, comb, emb, lex)]
+
+    def search_with_diversity(self, query: Query, top_k: int, diversity_factor: float,
+                              weights: Optional[QueryWeights] = None) -> List[SearchResult]:
+        """RagEngine::search_with_diversity, :717-759 (one fused device call)."""
+        if not self.chunks:
+            return []
+        w = resolve_weights(weights)
+        q = self._embed(query)
+        lam = min(max(float(diversity_factor), 0.0), 1.0) if diversity_factor == diversity_factor else diversity_factor
+        pool = max(int(top_k), 1) if lam == 0.0 else max(3 * int(top_k), int(top_k) + 10)
+        lr, ls = self._lex(query, pool)
+        rows, score, emb, lex = self.store.search_mmr(q, int(top_k), float(diversity_factor), w, lr, ls)
+        return [self._result(r, c, e, l) for r, c, e, l in zip(rows, score, emb, lex)]
+
+    def get_embedding_candidates(self, query: Query, count: int):
+        """RagEngine::get_embedding_candidates, :415-461 -> (chunk_id, document, text, page, section, initial_score)."""
+        if not self.chunks:
+            return []
+        q = self._embed(query)
+        rows, score = self.store.embedding_candidates(q, int(count))
+        out = []
+        for r, s in zip(rows, score):
+            ch = self.chunks[int(r)]
+            out.append({"chunk_id": ch.id, "document": ch.document_name, "text": ch.text,
+                        "page_number": ch.page_number, "section": ch.section, "initial_score": float(s)})
+        return out
+
+
+def search_documents(engine: RagEngine, query: Query, top_k: Optional[int] = None,
+                     diversity_factor: Optional[float] = None, weights: Optional[QueryWeights] = None):
+    """MCP tool `search_documents`, src/mcp_server.rs:81-110: parameter defaults and clamps."""
+    k = min(5 if top_k is None else int(top_k), MAX_TOP_K)          # :85
+    lam = 0.3 if diversity_factor is None else float(diversity_factor)
+    lam = min(max(lam, 0.0), 1.0)                                    # :86
+    return engine.search_with_diversity(query, k, lam, weights)

@@ -1,0 +1,299 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle
+on the same seeded inputs.  Bar: bit-exact scores (f32 arithmetic identical to the
+reference), identical row lists (ties: lower row first), identical MMR selections."""
+import ctypes as C
+import math
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from rust_local_rag_b200 import engine
+    return engine
+
+
+def W(e=0.7, l=0.3):
+    from rust_local_rag_b200.engine import ResolvedWeights
+    return ResolvedWeights(F32(e), F32(l), F32(0.7), F32(0.3))
+
+
+def same(a, b):
+    return np.asarray(a).tobytes() == np.asarray(b).tobytes()
+
+
+# ------------------------------------------------------------------ synthetic generator
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("dim", [3, 100, 768])
+def test_device_synth_bit_identical_to_cpu(eng, orc, kind, dim):
+    n, base = 1000, 12345
+    s = eng.DeviceStore.synthetic(n, dim, kind=kind, seed=0xABCDEF, centroid_seed=77, n_clusters=17, sigma=0.65,
+                                  row_base=base)
+    got = s.read_rows(np.arange(base, base + n))
+    ref = orc.synth_rows(n, dim, kind=kind, seed=0xABCDEF, centroid_seed=77, n_clusters=17, sigma=0.65, row0=base)
+    assert same(got, ref)
+    s.close()
+
+
+# ------------------------------------------------------------------ scan + top-m
+@pytest.mark.parametrize("n,dim,m", [
+    (1, 3, 1), (7, 3, 5), (127, 32, 127), (128, 33, 10), (129, 100, 129), (1000, 384, 45),
+    (4097, 768, 300), (20000, 768, 900), (5000, 1024, 1024), (300, 2000, 64), (60000, 64, 1000),
+])
+def test_search_topm_parity(eng, orc, n, dim, m):
+    rng = np.random.default_rng(n * 31 + dim)
+    rows = orc.normalize_rows(rng.standard_normal((n, dim)).astype(F32))
+    q = rng.standard_normal(dim).astype(F32)
+    s = eng.DeviceStore.from_rows(rows)
+    for (we, wl) in ((0.7, 0.3), (1.0, 0.0)):
+        r, c, e, l = s.search_topm(q, m, W(we, wl))
+        R, Cc, E, L = orc.search(rows, q, m, w_embed=we, w_lex=wl, full_sort=n <= 5000, threads=4)
+        assert same(r, R), (n, dim, m)
+        assert same(c, Cc) and same(e, E) and same(l, L)
+    s.close()
+
+
+def test_ties_lower_row_first_and_duplicates(eng, orc):
+    rng = np.random.default_rng(5)
+    base = orc.normalize_rows(rng.standard_normal((50, 768)).astype(F32))
+    rows = np.tile(base, (200, 1))                      # every row appears 200 times: massive exact ties
+    q = rng.standard_normal(768).astype(F32)
+    s = eng.DeviceStore.from_rows(rows)
+    r, c, e, l = s.search_topm(q, 900, W())
+    R, Cc, E, L = orc.search(rows, q, 900, full_sort=True)
+    assert same(r, R) and same(c, Cc) and same(e, E)
+    # all rows identical: every score ties, result must be rows 0..m-1
+    rows2 = np.tile(base[:1], (70000, 1))
+    s2 = eng.DeviceStore.from_rows(rows2)
+    r2, c2, _, _ = s2.search_topm(q, 300, W())
+    assert (r2 == np.arange(300)).all() and len(set(c2.tolist())) == 1
+    s.close(); s2.close()
+
+
+def test_lexical_blend_parity(eng, orc):
+    rng = np.random.default_rng(8)
+    n, dim = 30000, 768
+    rows = orc.normalize_rows(rng.standard_normal((n, dim)).astype(F32))
+    q = rng.standard_normal(dim).astype(F32)
+    s = eng.DeviceStore.from_rows(rows)
+    lex_rows = rng.choice(n, 1500, replace=False).astype(np.uint32)
+    lex_scores = (rng.random(1500) * 9).astype(F32)
+    for m in (15, 300, 900):
+        got = s.search_topm(q, m, W(), lex_rows, lex_scores)
+        ref = orc.search(rows, q, m, lex_rows=lex_rows, lex_scores=lex_scores, full_sort=False, threads=4)
+        for a, b in zip(got, ref):
+            assert same(a, b), m
+    assert (got[3] > 0).any()                           # lexical rows do make it into the list
+    # out-of-range lexical rows are ignored like a missed HashMap lookup (:525)
+    got = s.search_topm(q, 50, W(), np.array([5, n + 7], np.uint32), np.array([1.0, 50.0], F32))
+    ref = orc.search(rows, q, 50, lex_rows=np.array([5, n + 7], np.uint32), lex_scores=np.array([1.0, 50.0], F32))
+    for a, b in zip(got, ref):
+        assert same(a, b)
+    s.close()
+
+
+def test_unnormalised_and_zero_rows(eng, orc):
+    rng = np.random.default_rng(9)
+    rows = (rng.standard_normal((2000, 96)) * 3).astype(F32)    # store is used as given
+    rows[17] = 0                                                 # zero row scores exactly 0.0 (:1765)
+    q = rng.standard_normal(96).astype(F32)
+    s = eng.DeviceStore.from_rows(rows)
+    got = s.search_topm(q, 2000, W())
+    ref = orc.search(rows, q, 2000, full_sort=True)
+    for a, b in zip(got, ref):
+        assert same(a, b)
+    s.close()
+
+
+def test_embedding_candidates_parity(eng, orc):
+    rng = np.random.default_rng(10)
+    rows = orc.normalize_rows(rng.standard_normal((9000, 384)).astype(F32))
+    q = rng.standard_normal(384).astype(F32)
+    s = eng.DeviceStore.from_rows(rows)
+    r, sc = s.embedding_candidates(q, 30)
+    R, S = orc.embedding_candidates(rows, q, 30)
+    assert same(r, R) and same(sc, S)
+    s.close()
+
+
+# ------------------------------------------------------------------ MMR
+def _mmr_gpu(eng, cands, top_k, lam):
+    if not cands:
+        return []
+    dim = max(len(c[2]) for c in cands)
+    emb = np.zeros((len(cands), dim), F32)
+    for i, c in enumerate(cands):
+        emb[i, :len(c[2])] = c[2]
+    s = eng.DeviceStore.from_rows(emb)                  # rows are NOT normalised, like the reference's tests
+    pos = s.mmr(np.arange(len(cands)), np.array([c[1] for c in cands], F32), top_k, lam)
+    s.close()
+    return [cands[p][0] for p in pos]
+
+
+def test_reference_mmr_kats_on_gpu(eng):
+    """/root/reference/src/rag_engine.rs:2877-3038, through rlr_mmr."""
+    g = lambda c, k, lam: _mmr_gpu(eng, c, k, lam)
+    assert g([("chunk1", 0.9, [1, 0, 0])], 5, 0.3) == ["chunk1"]
+    assert len(g([("chunk1", 0.9, [1, 0, 0]), ("chunk2", 0.8, [0, 1, 0])], 10, 0.3)) == 2
+    assert g([("chunk1", 0.9, [1, 0.1, 0]), ("chunk2", 0.8, [1, 0.2, 0]), ("chunk3", 0.7, [1, 0.3, 0])], 3, 0.0) == \
+        ["chunk1", "chunk2", "chunk3"]
+    assert g([("chunk1", 0.9, [1, 0, 0]), ("chunk2", 0.85, [0.99, 0.1, 0]), ("chunk3", 0.7, [0, 1, 0])], 2, 0.9) == \
+        ["chunk1", "chunk3"]
+    r = g([("chunk1", 0.9, [1, 0, 0]), ("chunk_nan", math.nan, [0, 1, 0]), ("chunk3", 0.7, [0, 0, 1])], 3, 0.3)
+    assert len(r) == 2 and "chunk_nan" not in r
+    r = g([("chunk1", 0.9, [1, 0, 0]), ("chunk_inf", math.inf, [0, 1, 0]), ("chunk3", 0.7, [0, 0, 1])], 3, 0.3)
+    assert len(r) == 2 and "chunk_inf" not in r
+    assert g([("a", 0.9, [1, 0, 0, 0]), ("b", 0.8, [0, 1, 0, 0]), ("c", 0.7, [0, 0, 1, 0]), ("d", 0.6, [0, 0, 0, 1])],
+             4, 0.3) == ["a", "b", "c", "d"]
+    c = [("selected", 0.9, [1, 0, 0]), ("similar", 0.8, [1, 0, 0]), ("diverse", 0.6, [0, 1, 0])]
+    assert g(c, 2, 0.5) == ["selected", "diverse"]
+    assert g(c, 3, 0.5) == ["selected", "diverse", "similar"]
+    assert g([("a", 0.9, [1, 0]), ("b", 0.8, [0, 1])], 0, 0.3) == ["a"]          # top_k = 0 -> first only
+    t = [(f"t{i}", 0.5, [1.0 if j == i else 0.0 for j in range(5)]) for i in range(5)]
+    assert g(t, 5, 0.0) == ["t0", "t4", "t3", "t2", "t1"]                         # swap_remove tie order
+
+
+@pytest.mark.parametrize("p,dim,k,lam", [(15, 768, 5, 0.3), (300, 768, 100, 0.7), (300, 1024, 100, 0.3),
+                                         (45, 384, 45, 1.0), (333, 96, 50, 0.5), (1024, 64, 100, 0.7),
+                                         (2, 768, 5, 0.9), (300, 768, 100, float("nan"))])
+def test_mmr_parity_clustered(eng, orc, p, dim, k, lam):
+    rng = np.random.default_rng(p + dim)
+    cent = rng.standard_normal((8, dim)).astype(F32)
+    rows = orc.normalize_rows(cent[rng.integers(0, 8, p)] + 0.5 * rng.standard_normal((p, dim)).astype(F32))
+    rel = np.sort(rng.random(p).astype(F32))[::-1].copy()
+    rel[p // 2] = rel[p // 2 - 1]                         # an exact relevance tie
+    s = eng.DeviceStore.from_rows(rows)
+    got = s.mmr(np.arange(p), rel, k, lam)
+    ref = orc.mmr(rows, rel, k, lam, threads=4)
+    assert same(got, ref), (got, ref)
+    s.close()
+
+
+def test_mmr_nonfinite_inputs(eng, orc):
+    rng = np.random.default_rng(3)
+    rows = orc.normalize_rows(rng.standard_normal((40, 32)).astype(F32))
+    rel = np.sort(rng.random(40).astype(F32))[::-1].copy()
+    rel[3] = np.nan; rel[7] = np.inf; rel[9] = -np.inf
+    s = eng.DeviceStore.from_rows(rows)
+    got = s.mmr(np.arange(40), rel, 40, 0.4)
+    ref = orc.mmr(rows, rel, 40, 0.4)
+    assert same(got, ref) and len(got) == 37
+    rel[:] = np.nan                                       # nothing valid after the first pick
+    assert same(s.mmr(np.arange(40), rel, 10, 0.4), orc.mmr(rows, rel, 10, 0.4))
+    s.close()
+
+
+# ------------------------------------------------------------------ fused search_with_diversity
+@pytest.mark.parametrize("kind", [0, 1])
+def test_config1_search_documents_10k(eng, orc, kind):
+    """BASELINE config 1: top_k=5 diversity=0.3 over 10k synthetic 768-d chunks."""
+    n, dim = 10000, 768
+    rows = orc.synth_rows(n, dim, kind=kind, n_clusters=64)
+    s = eng.DeviceStore.from_rows(rows)
+    for qi in range(6):
+        q = orc.synth_rows(1, dim, kind=kind, seed=0x5EED0002, n_clusters=64, row0=qi)[0] * F32(3.0)
+        for (k, lam) in ((5, 0.3), (5, 0.0), (100, 0.7), (0, 0.3), (1, 1.0)):
+            got = s.search_mmr(q, k, lam, W())
+            ref = orc.search_with_diversity(rows, q, k, lam, full_sort=True)
+            for a, b in zip(got, ref):
+                assert same(a, b), (kind, qi, k, lam)
+    s.close()
+
+
+def test_config2_1m_x_768_top100_mmr(eng, orc):
+    """BASELINE config 2: single-query top_k=100 diversity=0.7 MMR over 1M x 768 f32 chunks."""
+    n, dim = 1_000_000, 768
+    s = eng.DeviceStore.synthetic(n, dim, kind=1, n_clusters=4096)
+    rows = orc.synth_rows(n, dim, kind=1, n_clusters=4096)         # bit-identical twin on the host
+    assert same(s.read_rows([0, 1, n // 2, n - 1]), rows[[0, 1, n // 2, n - 1]])
+    for qi in range(3):
+        q = orc.synth_rows(1, dim, kind=1, seed=0x5EED0002, n_clusters=4096, row0=qi * 17)[0]
+        got = s.search_mmr(q, 100, 0.7, W())
+        ref = orc.search_with_diversity(rows, q, 100, 0.7, full_sort=False, threads=orc.max_threads())
+        for a, b in zip(got, ref):
+            assert same(a, b), qi
+        assert len(got[0]) == 100 and len(set(got[0].tolist())) == 100
+        top = s.search_topm(q, 900, W())
+        topr = orc.search(rows, q, 900, full_sort=False, threads=orc.max_threads())
+        assert same(top[0], topr[0]) and same(top[1], topr[1])
+    s.close()
+
+
+# ------------------------------------------------------------------ size-independent properties
+def test_properties_full_size(eng):
+    n, dim = 1_000_000, 768
+    s = eng.DeviceStore.synthetic(n, dim, kind=0)
+    q = np.random.default_rng(1).standard_normal(dim).astype(F32)
+    r900, c900, e900, _ = s.search_topm(q, 900, W())
+    r300, c300, _, _ = s.search_topm(q, 300, W())
+    assert same(r900[:300], r300) and same(c900[:300], c300)            # prefix property
+    assert (np.diff(c900.astype(np.float64)) <= 0).all()                # sorted descending
+    assert len(set(r900.tolist())) == 900
+    again = s.search_topm(q, 900, W())
+    assert same(again[0], r900) and same(again[1], c900)                # idempotent
+    # the scores are the exact sequential dot of the stored rows
+    from oracle import orc as O
+    back = s.read_rows(r900[:20])
+    qn = O.normalize(q)
+    assert same(e900[:20], np.array([O.dot(qn, b) for b in back], F32))
+    # querying with a stored row returns that row first with score w_e * ~1
+    probe = s.read_rows([123456])[0]
+    r, c, e, _ = s.search_topm(probe, 5, W(1.0, 0.0))
+    assert r[0] == 123456 and abs(e[0] - 1.0) < 1e-5
+    # MMR with lambda -> 0+ keeps relevance order; selection is a subset of the pool
+    sel = s.search_mmr(q, 100, 1e-9, W())
+    assert same(sel[0], r300[:100])
+    sel7 = s.search_mmr(q, 100, 0.7, W())
+    assert set(sel7[0].tolist()) <= set(r300.tolist()) and sel7[0][0] == r300[0]
+    s.close()
+
+
+# ------------------------------------------------------------------ errors, empties, re-entrancy
+def test_errors_and_empty(eng, rlr):
+    s = eng.DeviceStore.from_rows(np.eye(8, dtype=F32))
+    with pytest.raises(rlr.RlrError) as ei:
+        s.search_topm(np.ones(7, F32), 3, W())
+    assert ei.value.code == rlr.RLR_ERR_DIM_MISMATCH
+    bad = np.ones(8, F32); bad[2] = np.nan
+    with pytest.raises(rlr.RlrError) as ei:
+        s.search_topm(bad, 3, W())
+    assert ei.value.code == rlr.RLR_ERR_NONFINITE
+    with pytest.raises(rlr.RlrError) as ei:
+        s.search_topm(np.ones(8, F32), 5000, W())
+    assert ei.value.code == rlr.RLR_ERR_UNSUPPORTED
+    r, c, e, l = s.search_topm(np.ones(8, F32), 100, W())               # m > n_rows
+    assert len(r) == 8
+    s.close()
+    empty = eng.DeviceStore.from_rows(np.zeros((0, 16), F32))
+    assert len(empty.search_topm(np.ones(16, F32), 5, W())[0]) == 0      # :476-478 Ok(vec![])
+    assert len(empty.search_mmr(np.ones(16, F32), 5, 0.3, W())[0]) == 0
+    empty.close()
+
+
+def test_concurrent_searches_one_store(eng, orc):
+    """Searches hold only the read lock in the reference (src/mcp_server.rs:89): re-entrant."""
+    rng = np.random.default_rng(4)
+    rows = orc.normalize_rows(rng.standard_normal((50000, 256)).astype(F32))
+    qs = rng.standard_normal((8, 256)).astype(F32)
+    s = eng.DeviceStore.from_rows(rows)
+    refs = [orc.search_with_diversity(rows, q, 20, 0.5, threads=2) for q in qs]
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(5):
+                got = s.search_mmr(qs[i], 20, 0.5, W())
+                if not (same(got[0], refs[i][0]) and same(got[1], refs[i][1])):
+                    errs.append(i)
+        except Exception as ex:  # pragma: no cover
+            errs.append(repr(ex))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert not errs
+    s.close()
