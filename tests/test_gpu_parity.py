@@ -103,10 +103,11 @@ def test_unnormalised_and_zero_rows(eng, orc):
     rows[17] = 0                                                 # zero row scores exactly 0.0 (:1765)
     q = rng.standard_normal(96).astype(F32)
     s = eng.DeviceStore.from_rows(rows)
-    got = s.search_topm(q, 2000, W())
-    ref = orc.search(rows, q, 2000, full_sort=True)
+    got = s.search_topm(q, 1024, W())
+    ref = orc.search(rows, q, 1024, full_sort=True)
     for a, b in zip(got, ref):
         assert same(a, b)
+    assert 17 in got[0].tolist() and got[2][got[0].tolist().index(17)] == 0.0
     s.close()
 
 
