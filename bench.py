@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- queries/s of `search_with_diversity(top_k=100)` over 10M x 768 f32 chunks.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A step is one query (one pass of the hot path over the whole corpus).  The corpus is the
+BASELINE.json metric's: 10,000,000 x 768 synthetic unit vectors (clustered, seeded), rows
+sharded contiguously over the N ranks (strong scaling: total work fixed).  `value` times the
+path with queries already resident in HBM; `e2e` times the public host-buffer API (C-ABI
+`rlr_search_mmr` at N=1, the sharded searcher at N>1) with the H2D copy of the query and the
+D2H read of the result inside the timed region.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED_STORE, SEED_QUERY, SEED_CENTROID = 0x5EED0001, 0x5EED0002, 0x5EED00C0
+N_CLUSTERS, SIGMA = 4096, 0.65
+N_QUERIES = 64
+METRIC = "search_with_diversity queries/sec (top_k=100 MMR, 10Mx768 f32 chunks)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--top-k", type=int, default=100)
+    ap.add_argument("--diversity", type=float, default=0.7)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, world):
+    return {
+        "workload": f"single-query top_k={a.top_k} diversity={a.diversity} MMR over {a.rows}x{a.dim} f32 chunks "
+                    f"(BASELINE configs[2]), rows sharded contiguously over {world} GPU(s)",
+        "rows": a.rows, "dim": a.dim, "top_k": a.top_k, "diversity": a.diversity,
+        "pool": max(3 * a.top_k, a.top_k + 10), "weights": [0.7, 0.3],
+        "distribution": f"clustered: normalize(centroid[row % {N_CLUSTERS}] + {SIGMA}*U[-1,1)), splitmix64 counter hash, "
+                        f"seeds store={SEED_STORE:#x} query={SEED_QUERY:#x} centroid={SEED_CENTROID:#x}",
+        "queries": N_QUERIES,
+        "l2": "inputs larger than L2 (store shard >= 3.8 GB vs 126 MB L2)",
+        "parallelism": f"rows/{world}",
+    }
+
+
+# ----------------------------------------------------------------------------------------
+# clocks: sampled with NVML during the timed regions
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        if self._t is not None:
+            self._stop.set()
+            self._t.join()
+            self._t = None
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the CPU oracle (the reference is Rust; no toolchain here)
+# ----------------------------------------------------------------------------------------
+def cpu_reference(a, steps, warmup, budget_s):
+    """Times oracle.search_with_diversity (bit-faithful restatement of the reference's
+    single-process search, all host threads) on the bench workload.  Returns dict."""
+    from oracle import orc
+    threads = orc.max_threads()
+    rows_n = a.rows
+    t0 = time.perf_counter()
+    rows = orc.synth_rows(rows_n, a.dim, kind=1, seed=SEED_STORE, centroid_seed=SEED_CENTROID,
+                          n_clusters=N_CLUSTERS, sigma=SIGMA, threads=threads)
+    gen_s = time.perf_counter() - t0
+    qs = orc.synth_rows(N_QUERIES, a.dim, kind=1, seed=SEED_QUERY, centroid_seed=SEED_CENTROID,
+                        n_clusters=N_CLUSTERS, sigma=SIGMA, threads=1)
+    # probe one query to size the sample
+    t0 = time.perf_counter()
+    orc.search_with_diversity(rows, qs[0], a.top_k, a.diversity, threads=threads)
+    probe = time.perf_counter() - t0
+    sample_rows = rows_n
+    if probe * (steps + warmup) > budget_s:
+        sample_rows = max(100_000, int(rows_n * budget_s / (probe * (steps + warmup))))
+        rows = rows[:sample_rows]
+    for i in range(warmup):
+        orc.search_with_diversity(rows, qs[i % N_QUERIES], a.top_k, a.diversity, threads=threads)
+    lat = []
+    for i in range(steps):
+        t0 = time.perf_counter()
+        orc.search_with_diversity(rows, qs[(warmup + i) % N_QUERIES], a.top_k, a.diversity, threads=threads)
+        lat.append(time.perf_counter() - t0)
+    total = sum(lat)
+    sample = (f"{steps} queries, each the full path (scan + top-{max(3 * a.top_k, a.top_k + 10)} + literal O(k^2 P D) MMR) "
+              f"over {sample_rows} of {rows_n} rows x {a.dim}, {threads} OpenMP threads; host rows generated in {gen_s:.1f}s")
+    if sample_rows != rows_n:
+        sample += f"; ROWS SUBSAMPLED x{rows_n / sample_rows:.1f} to bound run time: value is for the subsample"
+    return {"value": steps / total, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample,
+            "ms_per_step": 1e3 * total / steps, "p50_ms": 1e3 * statistics.median(lat), "sample_rows": sample_rows}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference(a, a.steps, a.warmup, budget_s=200.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "queries/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, a.gpus),
+        "p50_latency_ms": r["p50_ms"],
+        "cpu_baseline": {"value": r["value"], "unit": "queries/s", "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference arm = CPU oracle (C restatement of rag_engine.rs search/MMR arithmetic, OpenMP over rows); "
+                "the Rust reference cannot be built here (no cargo/rustc) and additionally clones every chunk and "
+                "sorts N fat tuples per query, so this is a lower bound on its time",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+# own arm
+# ----------------------------------------------------------------------------------------
+def run_b200(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import rust_local_rag_b200  # noqa: F401
+    from rust_local_rag_b200 import binding as B, engine
+    from rust_local_rag_b200 import dist as rdist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {a.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    lib = B.load()
+
+    plan = rdist.ShardPlan(a.rows, world, rank)
+    store = engine.DeviceStore.synthetic(plan.n_local, a.dim, kind=B.RLR_SYNTH_CLUSTERED, seed=SEED_STORE,
+                                         centroid_seed=SEED_CENTROID, n_clusters=N_CLUSTERS, sigma=SIGMA,
+                                         device=local_rank, row_base=plan.row0)
+    info = store.info()
+    pitch = info.pitch
+    # queries: same generator, different noise seed (clustered around the same centroids)
+    qstore = engine.DeviceStore.synthetic(N_QUERIES, a.dim, kind=B.RLR_SYNTH_CLUSTERED, seed=SEED_QUERY,
+                                          centroid_seed=SEED_CENTROID, n_clusters=N_CLUSTERS, sigma=SIGMA,
+                                          device=local_rank)
+    q_host = qstore.read_rows(np.arange(N_QUERIES))
+    qstore.close()
+    qcap = B.RLR_MAX_DIM + 64
+    q_pinned = torch.zeros((N_QUERIES, qcap), dtype=torch.float32).pin_memory()
+    q_pinned[:, :a.dim] = torch.from_numpy(q_host)
+    q_dev = q_pinned.to(dev)
+
+    backend = rdist.CudaBackend(store, dev)
+    p_cap = max(3 * a.top_k, a.top_k + 10, 1)
+    bufs = rdist.Buffers(world, p_cap, pitch, dev)
+    w_e, w_l = float(np.float32(0.7)), float(np.float32(0.3))
+    result_host = torch.zeros((p_cap, 2), dtype=torch.int64).pin_memory()
+    n_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+    q_stage = torch.zeros(qcap, dtype=torch.float32, device=dev)
+
+    def step_device(i):
+        q = q_dev[i % N_QUERIES]
+        if world == 1:
+            backend.search_mmr(q, a.top_k, a.diversity, w_e, w_l, bufs.result, bufs.sel_n)
+            return bufs.result, bufs.sel_n
+        return rdist.sharded_search(backend, group, bufs, q, a.top_k, a.diversity, w_e, w_l)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier(group=group)
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        return float(t.item())
+
+    clocks = ClockSampler(local_rank)
+
+    # ---- value: queries resident in HBM, device-timed ----
+    for i in range(a.warmup):
+        step_device(i)
+    sync_all()
+    l0 = backend.launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.start()
+    ev0.record()
+    for i in range(a.steps):
+        step_device(a.warmup + i)
+    ev1.record()
+    sync_all()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = backend.launches() - l0
+    value = a.steps / (dev_ms * 1e-3)
+
+    # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region ----
+    wts = engine.ResolvedWeights(np.float32(0.7), np.float32(0.3), np.float32(0.7), np.float32(0.3))
+    scan_ms_samples, stage_samples = [], []
+
+    def step_e2e(i, timed):
+        qi = i % N_QUERIES
+        if world == 1:
+            out = store.search_mmr(q_host[qi], a.top_k, a.diversity, wts, flags=B.RLR_WANT_TIMINGS if timed else 0)
+            if timed:
+                t = store.last_timings()
+                scan_ms_samples.append(t.scan_ms)
+                stage_samples.append((t.scan_ms, t.merge_ms, t.mmr_ms, t.total_ms))
+            return out
+        q_stage.copy_(q_pinned[qi], non_blocking=True)
+        res, n = rdist.sharded_search(backend, group, bufs, q_stage, a.top_k, a.diversity, w_e, w_l)
+        if rank == 0:
+            result_host.copy_(res[:p_cap], non_blocking=True)
+            n_host.copy_(n, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return None
+
+    for i in range(a.warmup):
+        step_e2e(i, False)
+    sync_all()
+    lat = []
+    t_start = time.perf_counter()
+    for i in range(a.steps):
+        t0 = time.perf_counter()
+        step_e2e(a.warmup + i, True)
+        lat.append(time.perf_counter() - t0)
+    sync_all()
+    e2e_s = max_over_ranks(time.perf_counter() - t_start)
+    clocks.stop()
+    e2e_value = a.steps / e2e_s
+    h2d = (pitch + 64) * 4 if world == 1 else qcap * 4
+    d2h = max(a.top_k, 1) * 16 + 4 if world == 1 else p_cap * 16 + 4
+
+    # ---- roofline: the scan kernel (dominant) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy)") if "hbm_gbs" in peaks \
+        else (6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)")
+    iso_ms = C.c_float(0)
+    B.check(lib.rlr_time_scan(backend.ctx, C.c_void_p(q_dev[0].data_ptr()), p_cap, 20,
+                              C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), C.byref(iso_ms)))
+    algo_bytes = plan.n_local * a.dim * 4
+    if scan_ms_samples:
+        scan_ms = statistics.mean(scan_ms_samples)
+        how = "CUDA events around the scan kernel inside every timed e2e call (mean)"
+    else:
+        scan_ms = iso_ms.value
+        how = "20 back-to-back launches after the timed region, CUDA events on the launch stream"
+    achieved = algo_bytes / (scan_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "scan_topm_kernel", "bytes_per_launch": algo_bytes,
+                "ms_per_launch": scan_ms, "isolated_ms_per_launch": iso_ms.value,
+                "isolated_GBps": algo_bytes / (iso_ms.value * 1e-3) / 1e9, "peak_source": peak_src, "how": how,
+                "frac_of_nominal_8TBps": achieved / 8000.0}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        r = cpu_reference(a, steps=6, warmup=1, budget_s=60.0)
+        cpu = {"value": r["value"], "unit": "queries/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+               "p50_ms": r["p50_ms"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, world),
+            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "p50_latency_ms": 1e3 * statistics.median(lat), "p99_latency_ms": 1e3 * sorted(lat)[int(0.99 * (len(lat) - 1))],
+                    "api": "rlr_search_mmr (C ABI, host buffers)" if world == 1 else
+                           "rust_local_rag_b200.dist.sharded_search (pinned query H2D, result D2H on rank 0)"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": clocks.summary(),
+        }
+        if stage_samples:
+            m = [statistics.mean(x[j] for x in stage_samples) for j in range(4)]
+            line["stage_ms"] = {"scan": m[0], "merge": m[1], "mmr": m[2], "device_total": m[3]}
+        print(json.dumps(line), flush=True)
+    backend.close()
+    store.close()
+    if world > 1:
+        dist.barrier(group=group)
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

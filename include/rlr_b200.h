@@ -264,11 +264,18 @@ int rlr_gather_async(rlr_ctx *c, const void *d_cands, const void *d_n, uint32_t 
                      void *d_out, void *stream);
 
 /* MMR over a dense candidate matrix in device memory (p x pitch f32) with relevance
- * = combined score decoded from d_cands.  Writes selected positions / count. */
+ * = combined score decoded from d_cands.  Writes selected positions / count and, when
+ * d_result != NULL, the selected records in selection order. */
 int rlr_mmr_async(rlr_ctx *c, const void *d_emb, uint32_t pitch, uint32_t dim,
                   const void *d_cands, const void *d_n, uint32_t p_cap,
                   uint32_t top_k, float lambda,
-                  void *d_sel_pos /* u32[top_k] */, void *d_sel_n /* u32 */, void *stream);
+                  void *d_sel_pos /* u32[top_k] */, void *d_sel_n /* u32 */,
+                  void *d_result /* rlr_cand[top_k], nullable */, void *stream);
+
+/* MMR over candidates that are rows of THIS store (keys carry global rows): no gather. */
+int rlr_mmr_store_async(rlr_ctx *c, const void *d_cands, const void *d_n, uint32_t p_cap,
+                        uint32_t top_k, float lambda, void *d_sel_pos, void *d_sel_n,
+                        void *d_result /* nullable */, void *stream);
 
 /* fused single-GPU search_with_diversity on the device: results stay in HBM.
  * d_result: rlr_cand[max(top_k,1)] in selection order, d_result_n: u32. */

@@ -90,7 +90,8 @@ PROTOTYPES = {
     "rlr_topm_async": (_int, [_vp, _vp, _f32, _f32, _vp, _vp, _u32, _u32, _vp, _vp, _vp]),
     "rlr_merge_async": (_int, [_vp, _vp, _u32, _u32, _vp, _vp, _vp]),
     "rlr_gather_async": (_int, [_vp, _vp, _vp, _u32, _vp, _vp]),
-    "rlr_mmr_async": (_int, [_vp, _vp, _u32, _u32, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp]),
+    "rlr_mmr_async": (_int, [_vp, _vp, _u32, _u32, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp, _vp]),
+    "rlr_mmr_store_async": (_int, [_vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp, _vp]),
     "rlr_search_mmr_async": (_int, [_vp, _vp, _u32, _f32, _f32, _f32, _vp, _vp, _vp]),
     "rlr_ctx_launch_count": (_int, [_vp, C.POINTER(_u64)]),
     "rlr_time_scan": (_int, [_vp, _vp, _u32, _u32, _vp, _pf]),

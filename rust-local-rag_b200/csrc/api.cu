@@ -848,7 +848,7 @@ RLR_EXPORT int rlr_gather_async(rlr_ctx *c, const void *d_cands, const void *d_n
 
 RLR_EXPORT int rlr_mmr_async(rlr_ctx *c, const void *d_emb, uint32_t pitch, uint32_t dim, const void *d_cands,
                              const void *d_n, uint32_t p_cap, uint32_t top_k, float lambda, void *d_sel_pos,
-                             void *d_sel_n, void *stream)
+                             void *d_sel_n, void *d_result, void *stream)
 {
     if (!c || !d_emb || !d_cands || !d_n || !d_sel_pos || !d_sel_n) return fail(RLR_ERR_INVALID_ARG, "NULL argument");
     if (p_cap == 0 || p_cap > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "p_cap %u not in 1..%d", p_cap, RLR_MAX_M);
@@ -860,8 +860,30 @@ RLR_EXPORT int rlr_mmr_async(rlr_ctx *c, const void *d_emb, uint32_t pitch, uint
     a.d_cands = static_cast<const rlr_cand *>(d_cands); a.d_n = static_cast<const uint32_t *>(d_n);
     a.use_rows = 0; a.p_cap = p_cap; a.top_k = top_k; a.lambda = lambda;
     a.d_tri = c->d_tri; a.d_sel_pos = static_cast<uint32_t *>(d_sel_pos); a.d_sel_n = static_cast<uint32_t *>(d_sel_n);
-    a.d_result = c->d_result;
+    a.d_result = static_cast<rlr_cand *>(d_result);
     a.max_smem_optin = c->s->smem_optin;
+    uint32_t l = 0;
+    CU_TRY(rlr::mmr_launch(a, static_cast<cudaStream_t>(stream), &l));
+    c->launches += l;
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_mmr_store_async(rlr_ctx *c, const void *d_cands, const void *d_n, uint32_t p_cap, uint32_t top_k,
+                                   float lambda, void *d_sel_pos, void *d_sel_n, void *d_result, void *stream)
+{
+    if (!c || !d_cands || !d_n || !d_sel_pos || !d_sel_n) return fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    if (p_cap == 0 || p_cap > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "p_cap %u not in 1..%d", p_cap, RLR_MAX_M);
+    rlr_store *s = c->s;
+    CU_TRY(cudaSetDevice(s->device));
+    rlr::MmrArgs a;
+    memset(&a, 0, sizeof a);
+    a.d_emb = s->d_rows; a.pitch = s->pitch; a.dim = s->dim;
+    a.d_cands = static_cast<const rlr_cand *>(d_cands); a.d_n = static_cast<const uint32_t *>(d_n);
+    a.row_base = static_cast<uint32_t>(s->row_base); a.use_rows = 1;
+    a.p_cap = p_cap; a.top_k = top_k; a.lambda = lambda;
+    a.d_tri = c->d_tri; a.d_sel_pos = static_cast<uint32_t *>(d_sel_pos); a.d_sel_n = static_cast<uint32_t *>(d_sel_n);
+    a.d_result = static_cast<rlr_cand *>(d_result);
+    a.max_smem_optin = s->smem_optin;
     uint32_t l = 0;
     CU_TRY(rlr::mmr_launch(a, static_cast<cudaStream_t>(stream), &l));
     c->launches += l;

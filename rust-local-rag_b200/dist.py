@@ -1,0 +1,198 @@
+"""Row-sharded search across the GPUs of one NVSwitch box: one process per GPU,
+`torch.distributed` (NCCL over NVLink) for the plumbing.  SURVEY.md 8(e).
+
+Per query, on every rank g of G:
+  1. local fused scan + top-P over the rank's contiguous row block   (rlr_topm_async)
+  2. ONE all-gather of the fixed-size per-rank lists (P x 16 B)      (NCCL)
+  3. merge of the G lists to the global pool of P                    (rlr_merge_async)
+  4. gather of the pool rows this rank owns into a P x pitch matrix  (rlr_gather_async)
+  5. reduce-to-rank-0 of that matrix as int32 bit patterns: every row is non-zero on
+     exactly one rank, and integer x + 0 == x, so the transport is bit-exact (NCCL)
+  6. MMR on rank 0                                                   (rlr_mmr_async)
+Nothing here computes on the host; the steps are enqueued on the current CUDA stream.
+
+The choreography takes a `backend` object so that tests/test_dist_gloo.py can drive the
+same collective sequence on CPU tensors over gloo with a test-only stand-in backend; the
+product backend is `CudaBackend` and needs the CUDA library and a B200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+CAND_WORDS = 2  # one rlr_cand == two int64 words: key, (emb f32 | lex f32 << 32)
+
+
+@dataclass(frozen=True)
+class ShardPlan:
+    """Contiguous row blocks [g*N/G, (g+1)*N/G) (global row = row0 + local)."""
+    n_total: int
+    world: int
+    rank: int
+
+    @staticmethod
+    def bounds(n_total: int, world: int, rank: int):
+        lo = (n_total * rank) // world
+        hi = (n_total * (rank + 1)) // world
+        return lo, hi
+
+    @property
+    def row0(self) -> int:
+        return self.bounds(self.n_total, self.world, self.rank)[0]
+
+    @property
+    def n_local(self) -> int:
+        lo, hi = self.bounds(self.n_total, self.world, self.rank)
+        return hi - lo
+
+    def owner(self, row: int) -> int:
+        for g in range(self.world):
+            lo, hi = self.bounds(self.n_total, self.world, g)
+            if lo <= row < hi:
+                return g
+        raise ValueError(row)
+
+
+def pool_size(top_k: int, lam: float) -> int:
+    """m handed to `search` by search_with_diversity: src/rag_engine.rs:728-734 (+ :490)."""
+    if lam == 0.0:
+        return max(int(top_k), 1)
+    return max(3 * int(top_k), int(top_k) + 10)
+
+
+def clamp_lambda(lam: float) -> float:
+    """f32::clamp(0.0, 1.0), src/rag_engine.rs:725 (NaN stays NaN)."""
+    if lam != lam:
+        return lam
+    return min(max(lam, 0.0), 1.0)
+
+
+class Buffers:
+    """Per-searcher device buffers (fixed shapes so that the collectives are fixed-size)."""
+
+    def __init__(self, world: int, p_cap: int, pitch: int, device):
+        i64, i32, f32 = torch.int64, torch.int32, torch.float32
+        self.local = torch.zeros((p_cap, CAND_WORDS), dtype=i64, device=device)
+        self.local_n = torch.zeros(1, dtype=i32, device=device)
+        self.gathered = torch.zeros((world, p_cap, CAND_WORDS), dtype=i64, device=device)
+        self.pool = torch.zeros((p_cap, CAND_WORDS), dtype=i64, device=device)
+        self.pool_n = torch.zeros(1, dtype=i32, device=device)
+        self.emb = torch.zeros((p_cap, pitch), dtype=f32, device=device)
+        self.sel_pos = torch.zeros(p_cap, dtype=i32, device=device)
+        self.sel_n = torch.zeros(1, dtype=i32, device=device)
+        self.result = torch.zeros((p_cap, CAND_WORDS), dtype=i64, device=device)
+        self.p_cap = p_cap
+
+
+def sharded_search(backend, group, bufs: Buffers, query, top_k: int, diversity_factor: float,
+                   w_embed: float, w_lex: float):
+    """search_with_diversity (src/rag_engine.rs:717-759, no reranker) over a row-sharded
+    corpus.  Returns (result, result_n) device tensors; they are meaningful on rank 0
+    (for diversity_factor == 0 on every rank)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    lam = clamp_lambda(float(diversity_factor))
+    m = pool_size(top_k, lam)
+    if m > bufs.p_cap:
+        raise ValueError(f"pool {m} exceeds buffer capacity {bufs.p_cap}")
+    local = bufs.local[:m]
+    gathered = bufs.gathered[:, :m]
+    backend.topm(query, w_embed, w_lex, m, local, bufs.local_n)
+    if world > 1:
+        g_flat = gathered if gathered.is_contiguous() else None
+        if g_flat is not None and dist.get_backend(group) == "nccl":
+            dist.all_gather_into_tensor(g_flat.view(world * m, CAND_WORDS), local, group=group)
+            lists = g_flat
+        else:
+            parts = [torch.empty_like(local) for _ in range(world)]
+            dist.all_gather(parts, local.contiguous(), group=group)
+            lists = torch.stack(parts)
+        backend.merge(lists, world, m, bufs.pool[:m], bufs.pool_n)
+        pool, pool_n = bufs.pool[:m], bufs.pool_n
+    else:
+        pool, pool_n = local, bufs.local_n
+    if lam == 0.0:
+        return pool, pool_n
+    emb = bufs.emb[:m]
+    if world > 1:
+        backend.gather(pool, pool_n, m, emb)
+        dist.reduce(emb.view(torch.int32), dst=dist.get_global_rank(group, 0) if group is not None else 0,
+                    op=dist.ReduceOp.SUM, group=group)
+        if rank != 0:
+            return bufs.result, bufs.sel_n
+        backend.mmr_matrix(emb, pool, pool_n, m, top_k, lam, bufs.sel_pos, bufs.sel_n, bufs.result)
+    else:
+        backend.mmr_store(pool, pool_n, m, top_k, lam, bufs.sel_pos, bufs.sel_n, bufs.result)
+    return bufs.result, bufs.sel_n
+
+
+class CudaBackend:
+    """The product backend: every step is a kernel launch from librlr_b200.so on the
+    current torch CUDA stream.  No fallback."""
+
+    def __init__(self, store, device: Optional[torch.device] = None):
+        from . import binding as B
+        self.B = B
+        self.lib = B.load()
+        self.store = store
+        info = store.info()
+        self.pitch, self.dim = info.pitch, info.dim
+        self.device = device if device is not None else torch.device("cuda", info.device)
+        self.ctx = C.c_void_p()
+        B.check(self.lib.rlr_ctx_create(store.handle, C.byref(self.ctx)))
+
+    def close(self):
+        if self.ctx:
+            self.lib.rlr_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    @staticmethod
+    def _p(t: torch.Tensor):
+        return C.c_void_p(t.data_ptr())
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def launches(self) -> int:
+        n = C.c_uint64(0)
+        self.B.check(self.lib.rlr_ctx_launch_count(self.ctx, C.byref(n)))
+        return n.value
+
+    def topm(self, query, w_embed, w_lex, m, out, out_n):
+        self.B.check(self.lib.rlr_topm_async(self.ctx, self._p(query), w_embed, w_lex, None, None, 0, m,
+                                             self._p(out), self._p(out_n), self._stream()))
+
+    def merge(self, lists, n_lists, m, out, out_n):
+        self.B.check(self.lib.rlr_merge_async(self.ctx, self._p(lists), n_lists, m, self._p(out), self._p(out_n),
+                                              self._stream()))
+
+    def gather(self, pool, pool_n, m, emb):
+        self.B.check(self.lib.rlr_gather_async(self.ctx, self._p(pool), self._p(pool_n), m, self._p(emb),
+                                               self._stream()))
+
+    def mmr_matrix(self, emb, pool, pool_n, p_cap, top_k, lam, sel_pos, sel_n, result):
+        self.B.check(self.lib.rlr_mmr_async(self.ctx, self._p(emb), emb.stride(0), self.dim, self._p(pool),
+                                            self._p(pool_n), p_cap, top_k, lam, self._p(sel_pos), self._p(sel_n),
+                                            self._p(result), self._stream()))
+
+    def mmr_store(self, pool, pool_n, p_cap, top_k, lam, sel_pos, sel_n, result):
+        # single GPU: candidates are read straight from the store (no gather)
+        self.B.check(self.lib.rlr_mmr_store_async(self.ctx, self._p(pool), self._p(pool_n), p_cap, top_k, lam,
+                                                  self._p(sel_pos), self._p(sel_n), self._p(result), self._stream()))
+
+    def search_mmr(self, query, top_k, diversity_factor, w_embed, w_lex, result, result_n):
+        """fused single-GPU path (rlr_search_mmr_async)."""
+        self.B.check(self.lib.rlr_search_mmr_async(self.ctx, self._p(query), top_k, diversity_factor, w_embed, w_lex,
+                                                   self._p(result), self._p(result_n), self._stream()))
+
+
+def decode_result(result: torch.Tensor, n: int):
+    """(rows, score, emb, lex) numpy arrays from rlr_cand records held as int64 pairs."""
+    import numpy as np
+    from . import binding as B
+    a = result[:n].cpu().numpy().reshape(-1).view(B.CAND_DTYPE)
+    return B.key_row(a["key"]), B.key_score(a["key"]), a["emb"].copy(), a["lex"].copy()
