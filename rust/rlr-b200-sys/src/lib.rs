@@ -1,0 +1,61 @@
+//! Raw bindings to `include/rlr_b200.h`.  NOT COMPILED HERE (no Rust toolchain in the image).
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+pub const RLR_OK: c_int = 0;
+pub const RLR_ERR_INVALID_ARG: c_int = 1;
+pub const RLR_ERR_NO_DEVICE: c_int = 2;
+pub const RLR_ERR_CUDA: c_int = 3;
+pub const RLR_ERR_OOM: c_int = 4;
+pub const RLR_ERR_DIM_MISMATCH: c_int = 5;
+pub const RLR_ERR_UNSUPPORTED: c_int = 6;
+pub const RLR_ERR_NONFINITE: c_int = 7;
+pub const RLR_MAX_M: u32 = 1024;
+pub const RLR_QUERY_PRENORMALIZED: u32 = 0x1;
+pub const RLR_WANT_TIMINGS: u32 = 0x2;
+
+#[repr(C)] pub struct rlr_store { _p: [u8; 0] }
+#[repr(C)] pub struct rlr_ctx { _p: [u8; 0] }
+
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct rlr_query_weights { pub embedding: f32, pub lexical: f32, pub reranker: f32, pub initial: f32, pub has: u32 }
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct rlr_resolved_weights { pub embedding: f32, pub lexical: f32, pub reranker: f32, pub initial: f32 }
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct rlr_store_info { pub n_rows: u64, pub row_base: u64, pub dim: u32, pub pitch: u32, pub device: i32, pub flags: u32, pub bytes_device: u64 }
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct rlr_device_info { pub device: i32, pub sm_count: i32, pub cc_major: i32, pub cc_minor: i32, pub total_mem: u64, pub name: [c_char; 128] }
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct rlr_timings { pub scan_ms: f32, pub merge_ms: f32, pub mmr_ms: f32, pub total_ms: f32, pub launches: u32 }
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct rlr_cand { pub key: u64, pub emb: f32, pub lex: f32 }
+
+extern "C" {
+    pub fn rlr_abi_version() -> c_int;
+    pub fn rlr_last_error() -> *const c_char;
+    pub fn rlr_device_count(out_count: *mut c_int) -> c_int;
+    pub fn rlr_device_query(device: c_int, out: *mut rlr_device_info) -> c_int;
+    pub fn rlr_normalize(v: *mut f32, n: usize) -> c_int;
+    pub fn rlr_resolve_weights(overrides: *const rlr_query_weights, out: *mut rlr_resolved_weights) -> c_int;
+    pub fn rlr_store_create(device: c_int, dim: u32, n_rows: u64, rows: *const f32, host_pitch: u64, row_base: u64, flags: u32, out: *mut *mut rlr_store) -> c_int;
+    pub fn rlr_store_destroy(s: *mut rlr_store) -> c_int;
+    pub fn rlr_store_info_get(s: *const rlr_store, out: *mut rlr_store_info) -> c_int;
+    pub fn rlr_store_upload(s: *mut rlr_store, row0: u64, n: u64, rows: *const f32, host_pitch: u64) -> c_int;
+    pub fn rlr_store_read_rows(s: *const rlr_store, rows: *const u32, n: u64, out: *mut f32) -> c_int;
+    pub fn rlr_store_fill_synthetic(s: *mut rlr_store, kind: c_int, seed: u64, centroid_seed: u64, n_clusters: u32, sigma: f32) -> c_int;
+    pub fn rlr_search_topm(s: *mut rlr_store, query: *const f32, dim: u32, flags: u32, w: *const rlr_resolved_weights, lex_rows: *const u32, lex_scores: *const f32, n_lex: u32, m: u32, out_rows: *mut u32, out_combined: *mut f32, out_emb: *mut f32, out_lex: *mut f32, out_n: *mut u32) -> c_int;
+    pub fn rlr_mmr(s: *mut rlr_store, cand_rows: *const u32, relevance: *const f32, p: u32, top_k: u32, lambda: f32, flags: u32, out_sel_pos: *mut u32, out_n: *mut u32) -> c_int;
+    pub fn rlr_search_mmr(s: *mut rlr_store, query: *const f32, dim: u32, flags: u32, top_k: u32, diversity_factor: f32, w: *const rlr_resolved_weights, lex_rows: *const u32, lex_scores: *const f32, n_lex: u32, out_rows: *mut u32, out_score: *mut f32, out_emb: *mut f32, out_lex: *mut f32, out_n: *mut u32) -> c_int;
+    pub fn rlr_embedding_candidates(s: *mut rlr_store, query: *const f32, dim: u32, flags: u32, count: u32, out_rows: *mut u32, out_score: *mut f32, out_n: *mut u32) -> c_int;
+    pub fn rlr_last_timings(out: *mut rlr_timings) -> c_int;
+    pub fn rlr_ctx_create(s: *mut rlr_store, out: *mut *mut rlr_ctx) -> c_int;
+    pub fn rlr_ctx_destroy(c: *mut rlr_ctx) -> c_int;
+    pub fn rlr_topm_async(c: *mut rlr_ctx, d_query: *const c_void, w_embed: f32, w_lex: f32, d_lex_rows: *const c_void, d_lex_norm: *const c_void, n_lex: u32, m: u32, d_out: *mut c_void, d_out_n: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn rlr_merge_async(c: *mut rlr_ctx, d_lists: *const c_void, n_lists: u32, m: u32, d_out: *mut c_void, d_out_n: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn rlr_gather_async(c: *mut rlr_ctx, d_cands: *const c_void, d_n: *const c_void, m: u32, d_out: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn rlr_mmr_async(c: *mut rlr_ctx, d_emb: *const c_void, pitch: u32, dim: u32, d_cands: *const c_void, d_n: *const c_void, p_cap: u32, top_k: u32, lambda: f32, d_sel_pos: *mut c_void, d_sel_n: *mut c_void, d_result: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn rlr_mmr_store_async(c: *mut rlr_ctx, d_cands: *const c_void, d_n: *const c_void, p_cap: u32, top_k: u32, lambda: f32, d_sel_pos: *mut c_void, d_sel_n: *mut c_void, d_result: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn rlr_search_mmr_async(c: *mut rlr_ctx, d_query: *const c_void, top_k: u32, diversity_factor: f32, w_embed: f32, w_lex: f32, d_result: *mut c_void, d_result_n: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn rlr_ctx_launch_count(c: *const rlr_ctx, out: *mut u64) -> c_int;
+    pub fn rlr_time_scan(c: *mut rlr_ctx, d_query: *const c_void, m: u32, iters: u32, stream: *mut c_void, out_ms_per_launch: *mut f32) -> c_int;
+}

@@ -1,0 +1,32 @@
+"""The Rust -sys crate cannot be compiled here (no cargo/rustc).  The least we can do is keep
+its extern block textually in sync with include/rlr_b200.h: same symbol set, same arity."""
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_decls():
+    text = open(os.path.join(ROOT, "include", "rlr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(rlr_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return out
+
+
+def _rust_decls():
+    text = open(os.path.join(ROOT, "rust", "rlr-b200-sys", "src", "lib.rs")).read()
+    out = {}
+    for m in re.finditer(r"pub fn (rlr_[a-z0-9_]+)\(([^)]*)\)", text):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if not args else args.count(":")
+    return out
+
+
+def test_rust_extern_block_matches_header():
+    h, r = _header_decls(), _rust_decls()
+    assert set(h) == set(r), (sorted(set(h) - set(r)), sorted(set(r) - set(h)))
+    for name in h:
+        assert h[name] == r[name], (name, h[name], r[name])
