@@ -141,6 +141,7 @@ struct rlr_ctx {
     float *d_lex_norm = nullptr;
     rlr_cand *d_lists = nullptr;
     uint32_t *d_counts = nullptr;
+    uint32_t *d_ticket = nullptr;
     rlr_cand *d_tmp = nullptr;
     rlr_cand *d_pool = nullptr;
     uint32_t *d_pool_n = nullptr;
@@ -168,7 +169,7 @@ void ctx_free(rlr_ctx *c)
 {
     if (!c) return;
     cudaFree(c->d_query); cudaFree(c->d_lex_rows); cudaFree(c->d_lex_norm); cudaFree(c->d_lists);
-    cudaFree(c->d_counts); cudaFree(c->d_tmp); cudaFree(c->d_pool); cudaFree(c->d_pool_n); cudaFree(c->d_tri);
+    cudaFree(c->d_counts); cudaFree(c->d_ticket); cudaFree(c->d_tmp); cudaFree(c->d_pool); cudaFree(c->d_pool_n); cudaFree(c->d_tri);
     cudaFree(c->d_sel_pos); cudaFree(c->d_sel_n); cudaFree(c->d_result); cudaFree(c->d_rows_in);
     cudaFree(c->d_rel_in); cudaFree(c->d_p_in);
     cudaFreeHost(c->h_query); cudaFreeHost(c->h_lex_rows); cudaFreeHost(c->h_lex_norm);
@@ -202,6 +203,8 @@ int ctx_new(rlr_store *s, rlr_ctx **out)
     CTX_TRY(cudaMalloc(&c->d_lex_norm, kLexCap * sizeof(float)));
     CTX_TRY(cudaMalloc(&c->d_lists, static_cast<size_t>(c->n_lists_cap) * RLR_MAX_M * sizeof(rlr_cand)));
     CTX_TRY(cudaMalloc(&c->d_counts, c->n_lists_cap * sizeof(uint32_t)));
+    CTX_TRY(cudaMalloc(&c->d_ticket, sizeof(uint32_t)));
+    CTX_TRY(cudaMemset(c->d_ticket, 0, sizeof(uint32_t)));
     CTX_TRY(cudaMalloc(&c->d_tmp, (static_cast<size_t>(c->n_lists_cap) + 3) * RLR_MAX_M * sizeof(rlr_cand)));
     CTX_TRY(cudaMalloc(&c->d_pool, RLR_MAX_M * sizeof(rlr_cand)));
     CTX_TRY(cudaMalloc(&c->d_pool_n, sizeof(uint32_t)));
@@ -327,12 +330,10 @@ int enqueue_topm(rlr_ctx *c, const float *d_query, float w_e, float w_l, const u
     a.d_lex_rows = d_lex_rows; a.d_lex_norm = d_lex_norm; a.n_lex = n_lex;
     a.m = m;
     a.d_lists = c->d_lists; a.d_counts = c->d_counts;
+    a.d_ticket = c->d_ticket; a.d_out = d_out; a.d_out_n = d_out_n; // cross-CTA merge happens in the scan's last CTA
     CU_TRY(rlr::scan_launch(a, st));
     ++c->launches;
     if (ev_after_scan) CU_TRY(cudaEventRecord(ev_after_scan, st));
-    uint32_t l = 0;
-    CU_TRY(rlr::merge_launch(c->d_lists, static_cast<uint32_t>(a.grid), m, c->d_tmp, d_out, d_out_n, st, &l));
-    c->launches += l;
     return RLR_OK;
 }
 
@@ -943,6 +944,7 @@ RLR_EXPORT int rlr_time_scan(rlr_ctx *c, const void *d_query, uint32_t m, uint32
     a.tmap = &s->tmap; a.d_query = static_cast<const float *>(d_query);
     a.n_rows = static_cast<uint32_t>(s->n_rows); a.row_base = static_cast<uint32_t>(s->row_base); a.pitch = s->pitch;
     a.w_embed = 0.7f; a.w_lex = 0.3f; a.m = m; a.d_lists = c->d_lists; a.d_counts = c->d_counts;
+    a.d_ticket = c->d_ticket; a.d_out = c->d_pool; a.d_out_n = c->d_pool_n;
     CU_TRY(rlr::scan_launch(a, st)); // warm
     CU_TRY(cudaEventRecord(c->ev[0], st));
     for (uint32_t i = 0; i < iters; ++i) CU_TRY(rlr::scan_launch(a, st));

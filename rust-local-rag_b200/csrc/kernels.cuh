@@ -28,6 +28,9 @@ struct ScanArgs {
     uint32_t m;                // 1..RLR_MAX_M
     rlr_cand *d_lists;         // grid x m records
     uint32_t *d_counts;        // grid
+    uint32_t *d_ticket;        // zero-initialised; the last CTA to finish merges and resets it
+    rlr_cand *d_out;           // best m records over all CTAs (null: skip the in-kernel merge)
+    uint32_t *d_out_n;
     int grid;                  // CTAs to launch (<= SM count)
     int smem_bytes;            // dynamic shared memory to request
     int n_stages;

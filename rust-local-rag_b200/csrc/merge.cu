@@ -77,6 +77,51 @@ merge_kernel(const rlr_cand *__restrict__ in, uint32_t n_lists, uint32_t m, uint
     }
 }
 
+// Few long sorted lists (the all-gathered per-GPU lists): rank by counting.  An element's
+// global rank is its position in its own list plus, for every other list, the number of
+// keys greater than it (binary search in shared memory).  Keys are unique, so ranks are a
+// permutation and every record is written straight to its final slot: no sorting passes.
+constexpr uint32_t kRankCap = 16384;   // keys held in shared memory (128 KB)
+
+__global__ void __launch_bounds__(kMergeThreads, 1)
+merge_rank_kernel(const rlr_cand *__restrict__ in, uint32_t n_lists, uint32_t m, rlr_cand *__restrict__ out,
+                  uint32_t *__restrict__ out_n)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw);
+    __shared__ uint32_t s_total;
+    const uint32_t t = threadIdx.x;
+    const uint32_t n = n_lists * m;
+    if (t == 0) s_total = 0;
+    for (uint32_t i = t; i < n; i += kMergeThreads) keys[i] = in[i].key;
+    __syncthreads();
+    // valid records per list (zero keys pad the tail)
+    if (t < n_lists) {
+        const uint64_t *l = keys + t * m;
+        uint32_t lo = 0, hi = m;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (l[mid] != 0ull) lo = mid + 1; else hi = mid; }
+        atomicAdd(&s_total, lo);
+    }
+    for (uint32_t e = t; e < n; e += kMergeThreads) {
+        const uint64_t x = keys[e];
+        if (x == 0ull) continue;
+        const uint32_t j = e / m;
+        uint32_t rank = e - j * m;
+        for (uint32_t i = 0; i < n_lists && rank < m; ++i) {
+            if (i == j) continue;
+            const uint64_t *l = keys + i * m;
+            uint32_t lo = 0, hi = m;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (l[mid] > x) lo = mid + 1; else hi = mid; }
+            rank += lo;
+        }
+        if (rank < m) out[rank] = in[e];
+    }
+    __syncthreads();
+    const uint32_t total = s_total < m ? s_total : m;
+    for (uint32_t i = total + t; i < m; i += kMergeThreads) { rlr_cand z; z.key = 0; z.emb = 0.0f; z.lex = 0.0f; out[i] = z; }
+    if (t == 0 && out_n != nullptr) *out_n = total;
+}
+
 inline uint32_t lists_per_block(uint32_t m)
 {
     uint32_t l = kMergeCap / m;
@@ -95,12 +140,18 @@ size_t merge_tmp_records(uint32_t n_lists, uint32_t m)
 cudaError_t merge_launch(const rlr_cand *d_lists, uint32_t n_lists, uint32_t m, rlr_cand *d_tmp, rlr_cand *d_out,
                          uint32_t *d_out_n, cudaStream_t stream, uint32_t *launches)
 {
-    static bool configured = false;
     const int smem = kMergeCap * 12;
-    if (!configured) {
+    {
+        // per-device function attributes (cheap; a process may drive several devices)
         cudaError_t e = cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(merge_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRankCap * 8);
         if (e != cudaSuccess) return e;
-        configured = true;
+    }
+    if (static_cast<uint64_t>(n_lists) * m <= kRankCap) {
+        merge_rank_kernel<<<1, kMergeThreads, n_lists * m * 8, stream>>>(d_lists, n_lists, m, d_out, d_out_n);
+        if (launches) ++*launches;
+        return cudaGetLastError();
     }
     const uint32_t lpb = lists_per_block(m);
     const rlr_cand *cur = d_lists;

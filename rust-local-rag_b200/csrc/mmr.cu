@@ -8,9 +8,9 @@
 // order-free, the same result is obtained from
 //   (a) ONE pass that computes every pairwise dot exactly (strict left-to-right f32 sum,
 //       separate mul/add roundings == dot_product :1776-1779), spread over all SMs; then
-//   (b) a single-CTA greedy loop that keeps the similarity triangle in shared memory,
-//       a running max_sim per candidate in a register, and does a warp-level argmax
-//       (redux.sync) + one block barrier per selection.
+//   (b) a greedy loop run by ONE warp: the similarity triangle sits in shared memory, each
+//       lane keeps its candidates' relevance / running max_sim / position in registers,
+//       and every selection is a warp-level argmax (redux.sync) -- no block barrier.
 // swap_remove bookkeeping (:783,:825) is reproduced with a per-candidate "position in
 // `remaining`" so that exact MMR-score ties resolve to the lowest CURRENT position,
 // exactly what the strict '>' scan at :812 does.
@@ -22,7 +22,7 @@ namespace rlr {
 namespace {
 
 constexpr int T = 16;             // pair tile edge
-constexpr int KC = 64;            // floats per staged chunk
+constexpr int KC = 768;           // floats of every row staged per pass (whole row for dim <= 768)
 constexpr int PADW = KC + 4;      // +16 B: conflict-free LDS.128 across 8 rows
 
 __device__ __forceinline__ uint32_t cand_row(const rlr_cand *cands, const uint32_t *rows, uint32_t row_base,
@@ -33,6 +33,11 @@ __device__ __forceinline__ uint32_t cand_row(const rlr_cand *cands, const uint32
     return i;
 }
 
+// All P(P-1)/2 pairwise dots, one 16x16 pair tile per CTA.  The 32 candidate rows of a tile
+// are staged into shared memory in ONE shot with cp.async (LDGSTS, 16 B each, L2 only): a
+// single DRAM round trip instead of one per column chunk; then every thread runs its own
+// strictly sequential mul/add chain over the row pair.  Row stride +16 B keeps the LDS.128
+// of eight different rows on eight different bank groups.
 __global__ void __launch_bounds__(T * T)
 mmr_pairwise_kernel(const float *__restrict__ emb, uint32_t pitch, const rlr_cand *__restrict__ cands,
                     const uint32_t *__restrict__ rows, const uint32_t *__restrict__ d_n, uint32_t row_base,
@@ -43,8 +48,7 @@ mmr_pairwise_kernel(const float *__restrict__ emb, uint32_t pitch, const rlr_can
     const uint32_t p = *d_n;
     if (bi * T >= p || bj * T >= p) return;
 
-    __shared__ __align__(16) float A[T][PADW];
-    __shared__ __align__(16) float B[T][PADW];
+    extern __shared__ __align__(16) float pw_smem[];     // [2*T][KC + 4]
     __shared__ const float *rowptr[2 * T];
 
     const uint32_t tid = threadIdx.x;
@@ -56,28 +60,30 @@ mmr_pairwise_kernel(const float *__restrict__ emb, uint32_t pitch, const rlr_can
     __syncthreads();
 
     const uint32_t ti = tid >> 4, tj = tid & 15;
-    // two float4 per thread per chunk: (row, col4) = (idx / 16, idx % 16), idx = tid, tid + 256
-    const uint32_t r0 = tid >> 4, c0 = tid & 15;
-    const float *p0 = rowptr[r0];
-    const float *p1 = rowptr[r0 + T];
-
+    const float *a_row = pw_smem + ti * PADW;
+    const float *b_row = pw_smem + (T + tj) * PADW;
     float acc = 0.0f;
-    float4 v0, v1;
-    auto fetch = [&](uint32_t base) {
-        const uint32_t col = base + c0 * 4;
-        v0 = (p0 != nullptr && col < pitch) ? __ldg(reinterpret_cast<const float4 *>(p0 + col)) : make_float4(0, 0, 0, 0);
-        v1 = (p1 != nullptr && col < pitch) ? __ldg(reinterpret_cast<const float4 *>(p1 + col)) : make_float4(0, 0, 0, 0);
-    };
-    fetch(0);
     for (uint32_t base = 0; base < pitch; base += KC) {
-        *reinterpret_cast<float4 *>(&A[r0][c0 * 4]) = v0;
-        *reinterpret_cast<float4 *>(&B[r0][c0 * 4]) = v1;
+        const uint32_t ncols = (pitch - base) < KC ? (pitch - base) : KC;   // multiple of 32
+        const uint32_t n4 = ncols >> 2;
+        for (uint32_t idx = tid; idx < 2 * T * n4; idx += T * T) {
+            const uint32_t r = idx / n4, c4 = idx - r * n4;
+            float *dst = pw_smem + r * PADW + c4 * 4;
+            const float *src = rowptr[r];
+            if (src != nullptr) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src + base + c4 * 4)
+                             : "memory");
+            } else {
+                *reinterpret_cast<float4 *>(dst) = make_float4(0, 0, 0, 0);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        if (base + KC < pitch) fetch(base + KC);
-#pragma unroll
-        for (int d = 0; d < KC; d += 4) {
-            const float4 a = *reinterpret_cast<const float4 *>(&A[ti][d]);
-            const float4 b = *reinterpret_cast<const float4 *>(&B[tj][d]);
+#pragma unroll 8
+        for (uint32_t d = 0; d < ncols; d += 4) {
+            const float4 a = *reinterpret_cast<const float4 *>(a_row + d);
+            const float4 b = *reinterpret_cast<const float4 *>(b_row + d);
             acc = add_rn(acc, mul_rn(a.x, b.x));
             acc = add_rn(acc, mul_rn(a.y, b.y));
             acc = add_rn(acc, mul_rn(a.z, b.z));
@@ -98,82 +104,102 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t key)
     return (static_cast<uint64_t>(mh) << 32) | ml;
 }
 
-__global__ void __launch_bounds__(1024, 1)
+// Greedy selection loop, run by ONE warp: candidate i lives in lane (i & 31), slot (i >> 5),
+// with its relevance, running max_sim and current position in `remaining` in registers.
+// Per selection: CPL shared-memory reads of the similarity triangle, CPL fmax/mul/sub, a
+// local argmax, two redux.sync + ballot + shfl for the warp argmax -- no block barrier.
+// The other warps of the CTA only help to stage the triangle into shared memory.
+constexpr int kGreedyThreads = 256;
+
+template <int CPL>
+__global__ void __launch_bounds__(kGreedyThreads, 1)
 mmr_greedy_kernel(const float *__restrict__ tri_g, const rlr_cand *__restrict__ cands,
                   const float *__restrict__ rel_opt, const uint32_t *__restrict__ d_n, uint32_t top_k,
                   float lambda, int tri_in_smem, uint32_t *__restrict__ sel_pos, uint32_t *__restrict__ sel_n,
                   rlr_cand *__restrict__ result)
 {
-    extern __shared__ float tri_s[];
-    __shared__ uint64_t part_key[2][32];
-    __shared__ uint32_t part_idx[2][32];
-    __shared__ uint32_t s_sel[RLR_MAX_M];
-
+    extern __shared__ __align__(16) float tri_s[];
     const uint32_t p = *d_n;
-    const uint32_t i = threadIdx.x;
-    const uint32_t warp = i >> 5;
-    const uint32_t n_warps = blockDim.x >> 5;
+    const uint32_t tid = threadIdx.x;
     if (p == 0) {
-        if (i == 0) *sel_n = 0;
+        if (tid == 0) *sel_n = 0;
         return;
     }
     const float *tri = tri_g;
     if (tri_in_smem) {
         const uint32_t n_tri = p * (p - 1) / 2;
-        for (uint32_t x = i; x < n_tri; x += blockDim.x) tri_s[x] = tri_g[x];
+        const uint32_t n4 = n_tri >> 2;
+        const float4 *g4 = reinterpret_cast<const float4 *>(tri_g);
+        float4 *s4 = reinterpret_cast<float4 *>(tri_s);
+        for (uint32_t x = tid; x < n4; x += kGreedyThreads) s4[x] = g4[x];
+        for (uint32_t x = (n4 << 2) + tid; x < n_tri; x += kGreedyThreads) tri_s[x] = tri_g[x];
         tri = tri_s;
-    }
-    float rel = 0.0f;
-    if (i < p) rel = rel_opt != nullptr ? rel_opt[i] : key_score(cands[i].key);
-    const bool rel_ok = is_finite_f32(rel);                 // :794-797
-    bool alive = (i < p) && (i != 0);
-    uint32_t pos = i;
-    if (i == p - 1 && i != 0) pos = 0;                      // swap_remove(0), :783
-    uint32_t n_rem = p - 1, n_sel = 1, last = 0;
-    if (i == 0) s_sel[0] = 0;
-    const float one_minus = sub_rn(1.0f, lambda);           // (1.0 - diversity_factor), :808
-    float max_sim = 0.0f;                                   // fold(0.0_f32, max), :804
-    uint32_t buf = 0;
-    __syncthreads();
-
-    while (n_sel < top_k && n_rem > 0) {                    // :788
-        uint64_t key = 0;
-        if (alive) {
-            const uint32_t a = i < last ? i : last, b = i < last ? last : i;
-            const float sim = tri[b * (b - 1) / 2 + a];
-            if (is_finite_f32(sim)) max_sim = fmaxf(max_sim, sim);   // :803-804
-            if (rel_ok) {
-                const float mmr = sub_rn(mul_rn(one_minus, rel), mul_rn(lambda, max_sim)); // :808-809
-                if (is_finite_f32(mmr))                                                    // :812
-                    key = (static_cast<uint64_t>(ord_f32(mmr)) << 32) | (0xffffffffu - pos);
-            }
-        }
-        const uint64_t wk = warp_max_u64(key);
-        if (wk != 0) {
-            if (key == wk) { part_key[buf][warp] = wk; part_idx[buf][warp] = i; }
-        } else if ((i & 31) == 0) {
-            part_key[buf][warp] = 0;
-        }
         __syncthreads();
+    }
+    if (tid >= 32) return;
+    const uint32_t lane = tid;
+
+    float rel[CPL], max_sim[CPL];
+    uint32_t pos[CPL];
+    uint32_t alive = 0, rel_ok = 0;                        // bit s: slot s
+#pragma unroll
+    for (int s = 0; s < CPL; ++s) {
+        const uint32_t i = lane + 32u * s;
+        rel[s] = 0.0f;
+        max_sim[s] = 0.0f;                                 // fold(0.0_f32, max), :804
+        pos[s] = i;
+        if (i < p) {
+            rel[s] = rel_opt != nullptr ? rel_opt[i] : key_score(cands[i].key);
+            if (i != 0) alive |= 1u << s;
+            if (is_finite_f32(rel[s])) rel_ok |= 1u << s;  // :794-797
+            if (i == p - 1 && i != 0) pos[s] = 0;          // swap_remove(0), :783
+        }
+    }
+    uint32_t n_rem = p - 1, n_sel = 1, last = 0;
+    if (lane == 0) {
+        sel_pos[0] = 0;
+        if (result != nullptr) result[0] = cands[0];
+    }
+    const float one_minus = sub_rn(1.0f, lambda);          // (1.0 - diversity_factor), :808
+
+    while (n_sel < top_k && n_rem > 0) {                   // :788
         uint64_t best = 0;
         uint32_t best_i = 0;
-        for (uint32_t w = 0; w < n_warps; ++w) {
-            const uint64_t k = part_key[buf][w];
-            if (k > best) { best = k; best_i = part_idx[buf][w]; }
+#pragma unroll
+        for (int s = 0; s < CPL; ++s) {
+            if (alive & (1u << s)) {
+                const uint32_t i = lane + 32u * s;
+                const uint32_t a = i < last ? i : last, b = i < last ? last : i;
+                const float sim = tri[b * (b - 1) / 2 + a];
+                if (is_finite_f32(sim)) max_sim[s] = fmaxf(max_sim[s], sim);          // :803-804
+                if (rel_ok & (1u << s)) {
+                    const float mmr = sub_rn(mul_rn(one_minus, rel[s]), mul_rn(lambda, max_sim[s])); // :808-809
+                    if (is_finite_f32(mmr)) {                                          // :812
+                        const uint64_t key = (static_cast<uint64_t>(ord_f32(mmr)) << 32) | (0xffffffffu - pos[s]);
+                        if (key > best) { best = key; best_i = i; }
+                    }
+                }
+            }
         }
-        if (best == 0) break;                                // :819-822
-        const uint32_t b_pos = 0xffffffffu - static_cast<uint32_t>(best);
-        if (i == best_i) alive = false;                      // swap_remove(best_idx), :825
-        else if (alive && pos == n_rem - 1) pos = b_pos;
-        if (i == 0) s_sel[n_sel] = best_i;
-        ++n_sel; --n_rem; last = best_i; buf ^= 1;
+        const uint64_t wk = warp_max_u64(best);
+        if (wk == 0) break;                                // :819-822
+        const uint32_t owner = __ffs(__ballot_sync(0xffffffffu, best == wk)) - 1;
+        best_i = __shfl_sync(0xffffffffu, best_i, owner);
+        const uint32_t b_pos = 0xffffffffu - static_cast<uint32_t>(wk);
+        // swap_remove(best_idx), :825: winner leaves, the last element moves into its slot
+#pragma unroll
+        for (int s = 0; s < CPL; ++s) {
+            const uint32_t i = lane + 32u * s;
+            if (i == best_i) alive &= ~(1u << s);
+            else if ((alive & (1u << s)) && pos[s] == n_rem - 1) pos[s] = b_pos;
+        }
+        if (lane == 0) {
+            sel_pos[n_sel] = best_i;
+            if (result != nullptr) result[n_sel] = cands[best_i];
+        }
+        ++n_sel; --n_rem; last = best_i;
     }
-    __syncthreads();
-    if (i == 0) *sel_n = n_sel;
-    for (uint32_t x = i; x < n_sel; x += blockDim.x) {
-        sel_pos[x] = s_sel[x];
-        if (result != nullptr) result[x] = cands[s_sel[x]];
-    }
+    if (lane == 0) *sel_n = n_sel;
 }
 
 __global__ void gather_kernel(const float *__restrict__ store, uint32_t pitch, uint32_t n_rows, uint32_t row_base,
@@ -211,7 +237,14 @@ cudaError_t mmr_configure()
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(mmr_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16 * 1024);
+    e = cudaFuncSetAttribute(mmr_pairwise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             2 * T * PADW * static_cast<int>(sizeof(float)));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(mmr_greedy_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 4 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(mmr_greedy_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 4 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(mmr_greedy_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 4 * 1024);
 }
 
 cudaError_t mmr_launch(const MmrArgs &a, cudaStream_t stream, uint32_t *launches)
@@ -219,19 +252,23 @@ cudaError_t mmr_launch(const MmrArgs &a, cudaStream_t stream, uint32_t *launches
     if (a.p_cap == 0) return cudaErrorInvalidValue;
     const uint32_t nb = (a.p_cap + T - 1) / T;
     if (a.p_cap > 1) {
-        mmr_pairwise_kernel<<<dim3(nb, nb), T * T, 0, stream>>>(a.d_emb, a.pitch, a.d_cands, a.d_rows, a.d_n,
-                                                               a.row_base, a.use_rows, a.d_tri);
+        mmr_pairwise_kernel<<<dim3(nb, nb), T * T, 2 * T * PADW * sizeof(float), stream>>>(
+            a.d_emb, a.pitch, a.d_cands, a.d_rows, a.d_n, a.row_base, a.use_rows, a.d_tri);
         if (launches) ++*launches;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     const size_t tri_bytes = static_cast<size_t>(a.p_cap) * (a.p_cap - 1) / 2 * sizeof(float);
-    const size_t smem_cap = static_cast<size_t>(a.max_smem_optin) - 16 * 1024; // static arrays live there too
+    const size_t smem_cap = static_cast<size_t>(a.max_smem_optin) - 4 * 1024;
     const int in_smem = tri_bytes <= smem_cap;
-    const uint32_t threads = ((a.p_cap + 31) / 32) * 32;
-    mmr_greedy_kernel<<<1, threads, in_smem ? tri_bytes : 0, stream>>>(a.d_tri, a.d_cands, a.d_rel, a.d_n, a.top_k,
-                                                                      a.lambda, in_smem, a.d_sel_pos, a.d_sel_n,
-                                                                      a.d_result);
+    const size_t smem = in_smem ? tri_bytes + 16 : 0;
+#define RLR_GREEDY(CPL)                                                                                               \
+    mmr_greedy_kernel<CPL><<<1, kGreedyThreads, smem, stream>>>(a.d_tri, a.d_cands, a.d_rel, a.d_n, a.top_k, a.lambda, \
+                                                                in_smem, a.d_sel_pos, a.d_sel_n, a.d_result)
+    if (a.p_cap <= 320) RLR_GREEDY(10);
+    else if (a.p_cap <= 512) RLR_GREEDY(16);
+    else RLR_GREEDY(32);
+#undef RLR_GREEDY
     if (launches) ++*launches;
     return cudaGetLastError();
 }

@@ -19,7 +19,8 @@
 //   * scores are blended (w_e*e + w_l*lex) and encoded as rank keys; a warp ballot +
 //     one shared atomic appends the keys that beat the CTA's running M-th best to a
 //     2048-entry buffer that is pruned with a bitonic sort when it fills.
-//   * each CTA writes its best M records; merge.cu reduces the <=148 lists.
+//   * each CTA writes its best M records; the LAST CTA to finish (atomic ticket) merges
+//     the <=148 lists in place (final_merge), so one launch yields the global top-M.
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -89,11 +90,177 @@ __device__ __forceinline__ uint32_t next_pow2(uint32_t x)
     return x <= 1 ? 1u : 1u << (32 - __clz(x - 1));
 }
 
+// Records written by OTHER CTAs of the same launch are read with ld.global.cg (L2, never
+// the non-coherent path); the writers fence before taking their ticket.
+__device__ __forceinline__ uint64_t ld_key(const rlr_cand *p)
+{
+    return __ldcg(reinterpret_cast<const unsigned long long *>(p));
+}
+__device__ __forceinline__ rlr_cand ld_cand(const rlr_cand *p)
+{
+    const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(p));
+    rlr_cand r;
+    r.key = (static_cast<uint64_t>(v.y) << 32) | v.x;
+    r.emb = __uint_as_float(v.z);
+    r.lex = __uint_as_float(v.w);
+    return r;
+}
+
+// number of keys >= T in a descending list of `cnt` records
+__device__ __forceinline__ uint32_t count_ge(const rlr_cand *list, uint32_t lo, uint32_t cnt, uint64_t T)
+{
+    uint32_t hi = cnt;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (ld_key(list + mid) >= T) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Reduce the L per-CTA lists (each sorted descending, `counts[j]` valid records) to the
+// global best m, by the R consumer threads of the last CTA.  Keys are unique.
+//   1. sample: the first c records of every list, sorted in shared memory; its m-th key
+//      T_A is a lower bound of the global m-th key;
+//   2. verify: any record outside the sample with key > T_A ("extra") is added and the
+//      buffer re-sorted -- for evenly spread data there are none;
+//   3. if the extras do not fit (adversarially skewed lists): exact bisection on the key
+//      value for the global m-th key, then gather exactly m records.
+__device__ void final_merge(uint64_t *keys, float *embs, volatile uint32_t *s_cnt, volatile uint32_t *s_aux,
+                            const rlr_cand *lists, const uint32_t *counts, uint32_t Ln,
+                            uint32_t m, uint32_t row_base, const uint32_t *__restrict__ lex_rows,
+                            const float *__restrict__ lex_norm, uint32_t n_lex, rlr_cand *__restrict__ out,
+                            uint32_t *__restrict__ out_n, uint32_t t)
+{
+    // total valid records
+    if (t == 0) { *s_cnt = 0; *s_aux = 0; }
+    named_bar_sync(1, R);
+    {
+        uint32_t local = 0;
+        for (uint32_t j = t; j < Ln; j += R) local += __ldcg(counts + j);
+        if (local) atomicAdd(const_cast<uint32_t *>(s_cnt), local);
+    }
+    named_bar_sync(1, R);
+    const uint32_t total = *s_cnt;
+    const uint32_t m_out = total < m ? total : m;
+    named_bar_sync(1, R);
+
+    uint32_t c = 1024u / Ln;
+    if (c > m) c = m;
+    {
+        const uint32_t want = (2u * m < Ln * m) ? 2u * m : Ln * m;
+        if (c * Ln < want) { c = kTopBuf / Ln; if (c > m) c = m; }
+        if (c == 0) c = 1;
+    }
+    const uint32_t nA = Ln * c;
+    uint32_t n2 = next_pow2(nA);
+    for (uint32_t i = t; i < n2; i += R) {
+        uint64_t k = 0; float e = 0.0f;
+        if (i < nA) {
+            const uint32_t j = i / c, p = i - j * c;
+            if (p < __ldcg(counts + j)) { const rlr_cand r = ld_cand(lists + static_cast<size_t>(j) * m + p); k = r.key; e = r.emb; }
+        }
+        keys[i] = k; embs[i] = e;
+    }
+    named_bar_sync(1, R);
+    bitonic_desc(keys, embs, n2, t);
+
+    uint32_t n_final = n2;                       // sorted entries currently in keys[]
+    if (m_out > 0) {
+        const uint64_t TA = (m_out <= nA) ? keys[m_out - 1] : 0ull;   // 0 => sample holds < m_out valid records
+        const uint32_t base = (TA != 0ull) ? m_out : nA;
+        named_bar_sync(1, R);
+        // count extras: records at positions >= c with key > TA
+        if (t == 0) { *s_cnt = 0; *s_aux = 0; }
+        named_bar_sync(1, R);
+        uint32_t my_extra = 0;
+        for (uint32_t j = t; j < Ln; j += R) {
+            const uint32_t cj = __ldcg(counts + j);
+            if (cj > c) my_extra += count_ge(lists + static_cast<size_t>(j) * m, c, cj, TA + 1) - c;
+        }
+        if (my_extra) atomicAdd(const_cast<uint32_t *>(s_cnt), my_extra);
+        named_bar_sync(1, R);
+        const uint32_t n_extra = *s_cnt;
+        named_bar_sync(1, R);
+        if (n_extra != 0 && base + n_extra <= kTopBuf) {
+            // append extras after the kept prefix, re-sort
+            for (uint32_t j = t; j < Ln; j += R) {
+                const uint32_t cj = __ldcg(counts + j);
+                if (cj <= c) continue;
+                const rlr_cand *lj = lists + static_cast<size_t>(j) * m;
+                const uint32_t e_end = count_ge(lj, c, cj, TA + 1);
+                if (e_end > c) {
+                    const uint32_t slot = atomicAdd(const_cast<uint32_t *>(s_aux), e_end - c);
+                    for (uint32_t p = c; p < e_end; ++p) { const rlr_cand r = ld_cand(lj + p); keys[base + slot + p - c] = r.key; embs[base + slot + p - c] = r.emb; }
+                }
+            }
+            n2 = next_pow2(base + n_extra);
+            named_bar_sync(1, R);
+            for (uint32_t i = base + n_extra + t; i < n2; i += R) keys[i] = 0;
+            named_bar_sync(1, R);
+            bitonic_desc(keys, embs, n2, t);
+            n_final = n2;
+        } else if (n_extra != 0) {
+            // exact bisection for T* = the m_out-th largest key overall
+            if (t == 0) *s_aux = 0;
+            named_bar_sync(1, R);
+            {
+                uint32_t hmax = 0;
+                for (uint32_t j = t; j < Ln; j += R)
+                    if (__ldcg(counts + j)) { const uint32_t h = static_cast<uint32_t>(ld_key(lists + static_cast<size_t>(j) * m) >> 32); hmax = h > hmax ? h : hmax; }
+                atomicMax(const_cast<uint32_t *>(s_aux), hmax);
+            }
+            named_bar_sync(1, R);
+            uint64_t lo = 1, hi = (static_cast<uint64_t>(*s_aux) << 32) | 0xffffffffull;
+            while (lo < hi) {
+                const uint64_t mid = lo + ((hi - lo + 1) >> 1);
+                named_bar_sync(1, R);
+                if (t == 0) *s_cnt = 0;
+                named_bar_sync(1, R);
+                uint32_t cnt = 0;
+                for (uint32_t j = t; j < Ln; j += R) cnt += count_ge(lists + static_cast<size_t>(j) * m, 0, __ldcg(counts + j), mid);
+                if (cnt) atomicAdd(const_cast<uint32_t *>(s_cnt), cnt);
+                named_bar_sync(1, R);
+                if (*s_cnt >= m_out) lo = mid; else hi = mid - 1;
+            }
+            named_bar_sync(1, R);
+            if (t == 0) *s_cnt = 0;
+            named_bar_sync(1, R);
+            for (uint32_t j = t; j < Ln; j += R) {
+                const rlr_cand *lj = lists + static_cast<size_t>(j) * m;
+                const uint32_t e_end = count_ge(lj, 0, __ldcg(counts + j), lo);
+                if (e_end) {
+                    const uint32_t slot = atomicAdd(const_cast<uint32_t *>(s_cnt), e_end);
+                    for (uint32_t p = 0; p < e_end; ++p) { const rlr_cand r = ld_cand(lj + p); keys[slot + p] = r.key; embs[slot + p] = r.emb; }
+                }
+            }
+            n2 = next_pow2(m_out);
+            named_bar_sync(1, R);
+            for (uint32_t i = m_out + t; i < n2; i += R) keys[i] = 0;
+            named_bar_sync(1, R);
+            bitonic_desc(keys, embs, n2, t);
+            n_final = n2;
+        }
+    }
+    for (uint32_t i = t; i < m; i += R) {
+        rlr_cand r;
+        if (i < m_out && i < n_final) {
+            r.key = keys[i];
+            r.emb = embs[i];
+            r.lex = n_lex ? lex_lookup(lex_rows, lex_norm, n_lex, key_row(r.key) - row_base) : 0.0f;
+        } else {
+            r.key = 0; r.emb = 0.0f; r.lex = 0.0f;
+        }
+        out[i] = r;
+    }
+    if (t == 0) *out_n = m_out;
+}
+
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ g_query,
                  uint32_t n_rows, uint32_t row_base, uint32_t n_chunks, float w_embed, float w_lex,
                  const uint32_t *__restrict__ lex_rows, const float *__restrict__ lex_norm, uint32_t n_lex,
-                 uint32_t m, int n_stages, rlr_cand *__restrict__ g_lists, uint32_t *__restrict__ g_counts)
+                 uint32_t m, int n_stages, rlr_cand *g_lists, uint32_t *g_counts, uint32_t *g_ticket,
+                 rlr_cand *g_out, uint32_t *g_out_n)
 {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B atoms are 1024 B: align the carve-up by hand.
@@ -239,6 +406,22 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
         out[i] = c;
     }
     if (t == 0) g_counts[blockIdx.x] = keep;
+    if (g_out == nullptr) return;
+
+    // ---- cross-CTA merge, done by whichever CTA finishes last (no second launch) ----
+    volatile uint32_t *s_flag = reinterpret_cast<volatile uint32_t *>(smem + L.misc_off + 16);
+    __threadfence();
+    named_bar_sync(1, R);
+    if (t == 0) {
+        const uint32_t ticket = atomicAdd(g_ticket, 1u);
+        *s_flag = (ticket == gridDim.x - 1) ? 1u : 0u;
+    }
+    named_bar_sync(1, R);
+    if (*s_flag == 0) return;
+    __threadfence();
+    if (t == 0) *g_ticket = 0; // stream-ordered launches reuse the ticket
+    final_merge(keys, embs, s_count, s_flag, g_lists, g_counts, gridDim.x, m, row_base, lex_rows, lex_norm, n_lex,
+                g_out, g_out_n, t);
 }
 
 } // namespace
@@ -274,7 +457,7 @@ cudaError_t scan_launch(const ScanArgs &a, cudaStream_t stream)
 {
     scan_topm_kernel<<<a.grid, kScanThreads, a.smem_bytes, stream>>>(
         *a.tmap, a.d_query, a.n_rows, a.row_base, a.pitch / kChunkFloats, a.w_embed, a.w_lex, a.d_lex_rows,
-        a.d_lex_norm, a.n_lex, a.m, a.n_stages, a.d_lists, a.d_counts);
+        a.d_lex_norm, a.n_lex, a.m, a.n_stages, a.d_lists, a.d_counts, a.d_ticket, a.d_out, a.d_out_n);
     return cudaGetLastError();
 }
 

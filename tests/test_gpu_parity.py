@@ -298,3 +298,66 @@ def test_concurrent_searches_one_store(eng, orc):
     [t.start() for t in th]; [t.join() for t in th]
     assert not errs
     s.close()
+
+
+# ------------------------------------------------------------------ in-kernel cross-CTA merge, adversarial layouts
+@pytest.mark.parametrize("n,m", [(2000, 300), (70000, 300), (70000, 900), (70000, 1024), (200000, 15), (19000, 1000),
+                                 (148 * 128 * 3, 700)])
+def test_merge_paths_on_sorted_and_skewed_data(eng, orc, n, m):
+    """Scores that decrease with the row index put the whole top-m into a few CTAs' lists, which
+    defeats the sampled merge and forces the 'extras' and the bisection paths of final_merge."""
+    dim = 64
+    rng = np.random.default_rng(n + m)
+    q = orc.normalize(rng.standard_normal(dim).astype(F32))
+    noise = rng.standard_normal((n, dim)).astype(F32)
+    scale = (np.arange(n, dtype=F32) / F32(n))[:, None]
+    rows = orc.normalize_rows(q[None, :] + scale * noise)            # row 0 == q, similarity decays with the row index
+    s = eng.DeviceStore.from_rows(rows)
+    got = s.search_topm(q, m, W(1.0, 0.0))
+    ref = orc.search(rows, q, m, w_embed=1.0, w_lex=0.0, full_sort=False, threads=4)
+    for a, b in zip(got, ref):
+        assert same(a, b)
+    # reversed: the best rows are the LAST ones (last tiles, other CTAs)
+    rows_r = rows[::-1].copy()
+    s2 = eng.DeviceStore.from_rows(rows_r)
+    got = s2.search_topm(q, m, W())
+    ref = orc.search(rows_r, q, m, full_sort=False, threads=4)
+    for a, b in zip(got, ref):
+        assert same(a, b)
+    s.close(); s2.close()
+
+
+# ------------------------------------------------------------------ rlr_merge_async (the multi-GPU exchange merge)
+@pytest.mark.parametrize("n_lists,m,fill", [(2, 300, 1.0), (8, 300, 1.0), (8, 1024, 1.0), (3, 15, 0.5), (8, 300, 0.1),
+                                            (1, 100, 1.0), (64, 1024, 0.7), (40, 900, 1.0)])
+def test_merge_async_matches_numpy(eng, rlr, n_lists, m, fill):
+    import torch
+    rng = np.random.default_rng(n_lists * 1000 + m)
+    s = eng.DeviceStore.from_rows(np.eye(4, dtype=F32))
+    lib = rlr.load()
+    ctx = C.c_void_p()
+    rlr.check(lib.rlr_ctx_create(s.handle, C.byref(ctx)))
+    rec = np.zeros((n_lists, m), rlr.CAND_DTYPE)
+    all_keys = rng.choice(np.arange(1, 1 << 40, dtype=np.uint64), size=n_lists * m, replace=False) << np.uint64(20)
+    all_keys = all_keys.reshape(n_lists, m)
+    for j in range(n_lists):
+        cnt = int(round(m * fill)) if j % 2 == 0 else m
+        k = np.sort(all_keys[j, :cnt])[::-1]
+        rec["key"][j, :cnt] = k
+        rec["emb"][j, :cnt] = (k % np.uint64(1000)).astype(F32)
+        rec["lex"][j, :cnt] = (k % np.uint64(7)).astype(F32)
+    d_in = torch.from_numpy(rec.view(np.int64).reshape(n_lists, m, 2)).cuda()
+    d_out = torch.zeros((m, 2), dtype=torch.int64, device="cuda")
+    d_n = torch.zeros(1, dtype=torch.int32, device="cuda")
+    rlr.check(lib.rlr_merge_async(ctx, C.c_void_p(d_in.data_ptr()), n_lists, m, C.c_void_p(d_out.data_ptr()),
+                                  C.c_void_p(d_n.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy().reshape(-1).view(rlr.CAND_DTYPE)
+    flat = rec.reshape(-1)
+    flat = flat[flat["key"] != 0]
+    ref = flat[np.argsort(flat["key"])[::-1]][:m]
+    assert int(d_n.item()) == len(ref)
+    assert got[:len(ref)].tobytes() == ref.tobytes()
+    assert (got["key"][len(ref):] == 0).all()
+    lib.rlr_ctx_destroy(ctx)
+    s.close()
