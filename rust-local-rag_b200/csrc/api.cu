@@ -142,6 +142,7 @@ struct rlr_ctx {
     rlr_cand *d_lists = nullptr;
     uint32_t *d_counts = nullptr;
     uint32_t *d_ticket = nullptr;
+    uint32_t *d_pub = nullptr;
     rlr_cand *d_tmp = nullptr;
     rlr_cand *d_pool = nullptr;
     uint32_t *d_pool_n = nullptr;
@@ -169,7 +170,7 @@ void ctx_free(rlr_ctx *c)
 {
     if (!c) return;
     cudaFree(c->d_query); cudaFree(c->d_lex_rows); cudaFree(c->d_lex_norm); cudaFree(c->d_lists);
-    cudaFree(c->d_counts); cudaFree(c->d_ticket); cudaFree(c->d_tmp); cudaFree(c->d_pool); cudaFree(c->d_pool_n); cudaFree(c->d_tri);
+    cudaFree(c->d_counts); cudaFree(c->d_ticket); cudaFree(c->d_pub); cudaFree(c->d_tmp); cudaFree(c->d_pool); cudaFree(c->d_pool_n); cudaFree(c->d_tri);
     cudaFree(c->d_sel_pos); cudaFree(c->d_sel_n); cudaFree(c->d_result); cudaFree(c->d_rows_in);
     cudaFree(c->d_rel_in); cudaFree(c->d_p_in);
     cudaFreeHost(c->h_query); cudaFreeHost(c->h_lex_rows); cudaFreeHost(c->h_lex_norm);
@@ -203,8 +204,10 @@ int ctx_new(rlr_store *s, rlr_ctx **out)
     CTX_TRY(cudaMalloc(&c->d_lex_norm, kLexCap * sizeof(float)));
     CTX_TRY(cudaMalloc(&c->d_lists, static_cast<size_t>(c->n_lists_cap) * RLR_MAX_M * sizeof(rlr_cand)));
     CTX_TRY(cudaMalloc(&c->d_counts, c->n_lists_cap * sizeof(uint32_t)));
-    CTX_TRY(cudaMalloc(&c->d_ticket, sizeof(uint32_t)));
-    CTX_TRY(cudaMemset(c->d_ticket, 0, sizeof(uint32_t)));
+    CTX_TRY(cudaMalloc(&c->d_ticket, 2 * sizeof(uint32_t)));
+    CTX_TRY(cudaMemset(c->d_ticket, 0, 2 * sizeof(uint32_t)));
+    CTX_TRY(cudaMalloc(&c->d_pub, c->n_lists_cap * sizeof(uint32_t)));
+    CTX_TRY(cudaMemset(c->d_pub, 0, c->n_lists_cap * sizeof(uint32_t)));
     CTX_TRY(cudaMalloc(&c->d_tmp, (static_cast<size_t>(c->n_lists_cap) + 3) * RLR_MAX_M * sizeof(rlr_cand)));
     CTX_TRY(cudaMalloc(&c->d_pool, RLR_MAX_M * sizeof(rlr_cand)));
     CTX_TRY(cudaMalloc(&c->d_pool_n, sizeof(uint32_t)));
@@ -330,7 +333,7 @@ int enqueue_topm(rlr_ctx *c, const float *d_query, float w_e, float w_l, const u
     a.d_lex_rows = d_lex_rows; a.d_lex_norm = d_lex_norm; a.n_lex = n_lex;
     a.m = m;
     a.d_lists = c->d_lists; a.d_counts = c->d_counts;
-    a.d_ticket = c->d_ticket; a.d_out = d_out; a.d_out_n = d_out_n; // cross-CTA merge happens in the scan's last CTA
+    a.d_ticket = c->d_ticket; a.d_pub = c->d_pub; a.d_out = d_out; a.d_out_n = d_out_n; // cross-CTA merge happens in the scan's last CTA
     CU_TRY(rlr::scan_launch(a, st));
     ++c->launches;
     if (ev_after_scan) CU_TRY(cudaEventRecord(ev_after_scan, st));
@@ -944,7 +947,7 @@ RLR_EXPORT int rlr_time_scan(rlr_ctx *c, const void *d_query, uint32_t m, uint32
     a.tmap = &s->tmap; a.d_query = static_cast<const float *>(d_query);
     a.n_rows = static_cast<uint32_t>(s->n_rows); a.row_base = static_cast<uint32_t>(s->row_base); a.pitch = s->pitch;
     a.w_embed = 0.7f; a.w_lex = 0.3f; a.m = m; a.d_lists = c->d_lists; a.d_counts = c->d_counts;
-    a.d_ticket = c->d_ticket; a.d_out = c->d_pool; a.d_out_n = c->d_pool_n;
+    a.d_ticket = c->d_ticket; a.d_pub = c->d_pub; a.d_out = c->d_pool; a.d_out_n = c->d_pool_n;
     CU_TRY(rlr::scan_launch(a, st)); // warm
     CU_TRY(cudaEventRecord(c->ev[0], st));
     for (uint32_t i = 0; i < iters; ++i) CU_TRY(rlr::scan_launch(a, st));
@@ -954,5 +957,33 @@ RLR_EXPORT int rlr_time_scan(rlr_ctx *c, const void *d_query, uint32_t m, uint32
     float ms = 0;
     CU_TRY(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
     *out_ms_per_launch = ms / iters;
+    if (getenv("RLR_DEBUG_TRACE")) {
+        // dev-only: one more launch with phase timestamps, printed to stderr
+        const int g = a.grid;
+        unsigned long long *d_tr = nullptr;
+        std::vector<unsigned long long> h(5 * g + 16, 0);
+        CU_TRY(cudaMalloc(&d_tr, h.size() * 8));
+        CU_TRY(cudaMemset(d_tr, 0, h.size() * 8));
+        a.d_trace = d_tr;
+        CU_TRY(rlr::scan_launch(a, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        CU_TRY(cudaMemcpy(h.data(), d_tr, h.size() * 8, cudaMemcpyDeviceToHost));
+        cudaFree(d_tr);
+        unsigned long long t0 = ~0ull, loop_max = 0, list_max = 0, loop_min = ~0ull;
+        for (int i = 0; i < g; ++i) { t0 = std::min(t0, h[i]); loop_max = std::max(loop_max, h[g + i]); loop_min = std::min(loop_min, h[g + i]); list_max = std::max(list_max, h[2 * g + i]); }
+        unsigned long long cnt_sum = 0, cnt2_sum = 0, cnt_max = 0, tiles_min = ~0ull, tiles_max = 0;
+        for (int i = 0; i < g; ++i) {
+            const unsigned long long w = h[3 * g + i], cn = (w >> 24) & 0xffffffu, tl = w >> 48;
+            cnt_sum += cn; cnt2_sum += w & 0xffffffu; cnt_max = std::max(cnt_max, cn);
+            tiles_min = std::min(tiles_min, tl); tiles_max = std::max(tiles_max, tl);
+        }
+        fprintf(stderr, "[trace m=%u] tiles per CTA min/max %llu/%llu\n", m, tiles_min, tiles_max);
+        const unsigned long long *tr = h.data() + 4 * g;
+        fprintf(stderr, "[trace m=%u] loop_end first/last %.1f/%.1f us, lists written by %.1f us; buffer entries avg %.0f max %llu, after global-bound compaction avg %.1f\n",
+                m, (loop_min - t0) / 1e3, (loop_max - t0) / 1e3, (list_max - t0) / 1e3, double(cnt_sum) / g, cnt_max, double(cnt2_sum) / g);
+        fprintf(stderr, "[trace m=%u] merge: start %.1f, sample loaded +%.1f, sorted +%.1f, extras counted +%.1f, ready +%.1f, done +%.1f us (total valid %llu, extras %llu, c %llu, n2 %llu)\n",
+                m, (tr[0] - t0) / 1e3, (tr[1] - tr[0]) / 1e3, (tr[2] - tr[1]) / 1e3, (tr[3] - tr[2]) / 1e3, (tr[4] - tr[3]) / 1e3, (tr[7] - tr[4]) / 1e3,
+                tr[8] >> 32, tr[8] & 0xffffffffu, tr[9] >> 32, tr[9] & 0xffffffffu);
+    }
     return RLR_OK;
 }

@@ -138,6 +138,16 @@ __device__ __forceinline__ float4 lds128(uint32_t addr)
     return v;
 }
 
+// warp-wide max of a u64 with two redux.sync (keys compare as unsigned integers)
+__device__ __forceinline__ uint64_t warp_max_u64(uint64_t key)
+{
+    const uint32_t hi = static_cast<uint32_t>(key >> 32);
+    const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+    const uint32_t lo = (hi == mh) ? static_cast<uint32_t>(key) : 0u;
+    const uint32_t ml = __reduce_max_sync(0xffffffffu, lo);
+    return (static_cast<uint64_t>(mh) << 32) | ml;
+}
+
 // ---------------------------------------------------------------------------------
 // splitmix64-based counter hash for synthetic embeddings; the CPU
 // twin lives in oracle/rlr_oracle.c and must produce the same bits.

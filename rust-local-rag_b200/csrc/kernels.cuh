@@ -10,7 +10,7 @@ namespace rlr {
 
 constexpr int kScanRows = 128;        // rows per tile == consumer threads per CTA
 constexpr int kScanChunks = 2;        // 128-byte column chunks per pipeline stage
-constexpr int kScanThreads = kScanRows + 32;
+constexpr int kScanThreads = kScanRows + 64;   // 4 consumer warps + TMA producer warp + threshold warp
 constexpr int kTopBuf = 2048;         // per-CTA candidate buffer (entries)
 constexpr int kChunkFloats = 32;      // 128 B : the TMA SWIZZLE_128B span
 constexpr int kQueryCap = RLR_MAX_DIM + kChunkFloats * kScanChunks; // floats, zero padded
@@ -28,12 +28,16 @@ struct ScanArgs {
     uint32_t m;                // 1..RLR_MAX_M
     rlr_cand *d_lists;         // grid x m records
     uint32_t *d_counts;        // grid
-    uint32_t *d_ticket;        // zero-initialised; the last CTA to finish merges and resets it
+    uint32_t *d_ticket;        // 2 words, zero-initialised: [0] finish ticket, [1] dynamic tile counter;
+                               // the last CTA to finish merges and resets both
+    uint32_t *d_pub;           // grid words, zero-initialised: per-CTA published r-th best score
     rlr_cand *d_out;           // best m records over all CTAs (null: skip the in-kernel merge)
     uint32_t *d_out_n;
     int grid;                  // CTAs to launch (<= SM count)
     int smem_bytes;            // dynamic shared memory to request
     int n_stages;
+    uint32_t buf_cap;          // 0: derive from m
+    unsigned long long *d_trace; // dev-only: phase timestamps (5*grid + 16 words) or null
 };
 
 // Pick grid / stages / smem for a store on a device.

@@ -95,15 +95,6 @@ mmr_pairwise_kernel(const float *__restrict__ emb, uint32_t pitch, const rlr_can
     if (i < j && j < p) tri[static_cast<size_t>(j) * (j - 1) / 2 + i] = acc;
 }
 
-__device__ __forceinline__ uint64_t warp_max_u64(uint64_t key)
-{
-    const uint32_t hi = static_cast<uint32_t>(key >> 32);
-    const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
-    const uint32_t lo = (hi == mh) ? static_cast<uint32_t>(key) : 0u;
-    const uint32_t ml = __reduce_max_sync(0xffffffffu, lo);
-    return (static_cast<uint64_t>(mh) << 32) | ml;
-}
-
 // Greedy selection loop, run by ONE warp: candidate i lives in lane (i & 31), slot (i >> 5),
 // with its relevance, running max_sim and current position in `remaining` in registers.
 // Per selection: CPL shared-memory reads of the similarity triangle, CPL fmax/mul/sub, a
@@ -111,34 +102,15 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t key)
 // The other warps of the CTA only help to stage the triangle into shared memory.
 constexpr int kGreedyThreads = 256;
 
+// The selection loop proper.  `tri` is either the shared-memory copy (LDS) or the global
+// triangle; the body is branch-free per slot (dead / out-of-range slots compute on a
+// clamped index and are masked out of the argmax) so that the CPL loads issue back to back.
 template <int CPL>
-__global__ void __launch_bounds__(kGreedyThreads, 1)
-mmr_greedy_kernel(const float *__restrict__ tri_g, const rlr_cand *__restrict__ cands,
-                  const float *__restrict__ rel_opt, const uint32_t *__restrict__ d_n, uint32_t top_k,
-                  float lambda, int tri_in_smem, uint32_t *__restrict__ sel_pos, uint32_t *__restrict__ sel_n,
-                  rlr_cand *__restrict__ result)
+__device__ __forceinline__ void greedy_loop(const float *tri, const rlr_cand *__restrict__ cands,
+                                            const float *__restrict__ rel_opt, uint32_t p, uint32_t top_k, float lambda,
+                                            uint32_t *__restrict__ sel_pos, uint32_t *__restrict__ sel_n,
+                                            rlr_cand *__restrict__ result, uint32_t lane)
 {
-    extern __shared__ __align__(16) float tri_s[];
-    const uint32_t p = *d_n;
-    const uint32_t tid = threadIdx.x;
-    if (p == 0) {
-        if (tid == 0) *sel_n = 0;
-        return;
-    }
-    const float *tri = tri_g;
-    if (tri_in_smem) {
-        const uint32_t n_tri = p * (p - 1) / 2;
-        const uint32_t n4 = n_tri >> 2;
-        const float4 *g4 = reinterpret_cast<const float4 *>(tri_g);
-        float4 *s4 = reinterpret_cast<float4 *>(tri_s);
-        for (uint32_t x = tid; x < n4; x += kGreedyThreads) s4[x] = g4[x];
-        for (uint32_t x = (n4 << 2) + tid; x < n_tri; x += kGreedyThreads) tri_s[x] = tri_g[x];
-        tri = tri_s;
-        __syncthreads();
-    }
-    if (tid >= 32) return;
-    const uint32_t lane = tid;
-
     float rel[CPL], max_sim[CPL];
     uint32_t pos[CPL];
     uint32_t alive = 0, rel_ok = 0;                        // bit s: slot s
@@ -161,37 +133,44 @@ mmr_greedy_kernel(const float *__restrict__ tri_g, const rlr_cand *__restrict__ 
         if (result != nullptr) result[0] = cands[0];
     }
     const float one_minus = sub_rn(1.0f, lambda);          // (1.0 - diversity_factor), :808
+    const uint32_t i_max = p - 1;
 
     while (n_sel < top_k && n_rem > 0) {                   // :788
-        uint64_t best = 0;
-        uint32_t best_i = 0;
+        float sim[CPL];
+        const uint32_t tl = last * (last - 1) / 2;         // row offset of `last` in the triangle (last > i)
 #pragma unroll
         for (int s = 0; s < CPL; ++s) {
-            if (alive & (1u << s)) {
-                const uint32_t i = lane + 32u * s;
-                const uint32_t a = i < last ? i : last, b = i < last ? last : i;
-                const float sim = tri[b * (b - 1) / 2 + a];
-                if (is_finite_f32(sim)) max_sim[s] = fmaxf(max_sim[s], sim);          // :803-804
-                if (rel_ok & (1u << s)) {
-                    const float mmr = sub_rn(mul_rn(one_minus, rel[s]), mul_rn(lambda, max_sim[s])); // :808-809
-                    if (is_finite_f32(mmr)) {                                          // :812
-                        const uint64_t key = (static_cast<uint64_t>(ord_f32(mmr)) << 32) | (0xffffffffu - pos[s]);
-                        if (key > best) { best = key; best_i = i; }
-                    }
-                }
-            }
+            uint32_t i = lane + 32u * s;
+            i = i > i_max ? i_max : i;                     // clamp: masked out below
+            const uint32_t idx = i < last ? tl + i : (i == last ? 0u : i * (i - 1) / 2 + last);
+            sim[s] = tri[idx];
         }
-        const uint64_t wk = warp_max_u64(best);
-        if (wk == 0) break;                                // :819-822
-        const uint32_t owner = __ffs(__ballot_sync(0xffffffffu, best == wk)) - 1;
+        uint32_t best_hi = 0, best_lo = 0, best_i = 0;
+        const uint32_t live = alive & rel_ok;
+#pragma unroll
+        for (int s = 0; s < CPL; ++s) {
+            // dead slots keep updating a max_sim nobody reads; alive slots follow :803-804
+            if (is_finite_f32(sim[s]) && (alive & (1u << s))) max_sim[s] = fmaxf(max_sim[s], sim[s]);
+            const float mmr = sub_rn(mul_rn(one_minus, rel[s]), mul_rn(lambda, max_sim[s])); // :808-809
+            const bool ok = ((live >> s) & 1u) && is_finite_f32(mmr);                        // :794, :812
+            const uint32_t hi = ok ? ord_f32(mmr) : 0u;
+            const uint32_t lo = 0xffffffffu - pos[s];
+            const bool better = (hi > best_hi) || (hi == best_hi && hi != 0u && lo > best_lo);
+            if (better) { best_hi = hi; best_lo = lo; best_i = lane + 32u * s; }
+        }
+        const uint32_t mh = __reduce_max_sync(0xffffffffu, best_hi);
+        if (mh == 0) break;                                // :819-822 (no finite candidate left)
+        const uint32_t ml = __reduce_max_sync(0xffffffffu, best_hi == mh ? best_lo : 0u);
+        const uint32_t owner = __ffs(__ballot_sync(0xffffffffu, best_hi == mh && best_lo == ml)) - 1;
         best_i = __shfl_sync(0xffffffffu, best_i, owner);
-        const uint32_t b_pos = 0xffffffffu - static_cast<uint32_t>(wk);
+        const uint32_t b_pos = 0xffffffffu - ml;
         // swap_remove(best_idx), :825: winner leaves, the last element moves into its slot
 #pragma unroll
         for (int s = 0; s < CPL; ++s) {
             const uint32_t i = lane + 32u * s;
+            const bool is_alive = (alive >> s) & 1u;
+            if (is_alive && i != best_i && pos[s] == n_rem - 1) pos[s] = b_pos;
             if (i == best_i) alive &= ~(1u << s);
-            else if ((alive & (1u << s)) && pos[s] == n_rem - 1) pos[s] = b_pos;
         }
         if (lane == 0) {
             sel_pos[n_sel] = best_i;
@@ -200,6 +179,36 @@ mmr_greedy_kernel(const float *__restrict__ tri_g, const rlr_cand *__restrict__ 
         ++n_sel; --n_rem; last = best_i;
     }
     if (lane == 0) *sel_n = n_sel;
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(kGreedyThreads, 1)
+mmr_greedy_kernel(const float *__restrict__ tri_g, const rlr_cand *__restrict__ cands,
+                  const float *__restrict__ rel_opt, const uint32_t *__restrict__ d_n, uint32_t top_k,
+                  float lambda, int tri_in_smem, uint32_t *__restrict__ sel_pos, uint32_t *__restrict__ sel_n,
+                  rlr_cand *__restrict__ result)
+{
+    extern __shared__ __align__(16) float tri_s[];
+    const uint32_t p = *d_n;
+    const uint32_t tid = threadIdx.x;
+    if (p == 0) {
+        if (tid == 0) *sel_n = 0;
+        return;
+    }
+    if (tri_in_smem) {
+        const uint32_t n_tri = p * (p - 1) / 2;
+        const uint32_t n4 = n_tri >> 2;
+        const float4 *g4 = reinterpret_cast<const float4 *>(tri_g);
+        float4 *s4 = reinterpret_cast<float4 *>(tri_s);
+        for (uint32_t x = tid; x < n4; x += kGreedyThreads) s4[x] = g4[x];
+        for (uint32_t x = (n4 << 2) + tid; x < n_tri; x += kGreedyThreads) tri_s[x] = tri_g[x];
+        __syncthreads();
+        if (tid >= 32) return;
+        greedy_loop<CPL>(tri_s, cands, rel_opt, p, top_k, lambda, sel_pos, sel_n, result, tid);
+    } else {
+        if (tid >= 32) return;
+        greedy_loop<CPL>(tri_g, cands, rel_opt, p, top_k, lambda, sel_pos, sel_n, result, tid);
+    }
 }
 
 __global__ void gather_kernel(const float *__restrict__ store, uint32_t pitch, uint32_t n_rows, uint32_t row_base,

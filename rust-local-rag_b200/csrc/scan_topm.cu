@@ -21,8 +21,11 @@
 //     2048-entry buffer that is pruned with a bitonic sort when it fills.
 //   * each CTA writes its best M records; the LAST CTA to finish (atomic ticket) merges
 //     the <=148 lists in place (final_merge), so one launch yields the global top-M.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
+#include "sort_regs.cuh"
 
 namespace rlr {
 
@@ -45,7 +48,7 @@ __host__ __device__ inline SmemLayout smem_layout(int n_stages, uint32_t q_float
     L.keys_off = o;   o += kTopBuf * 8;
     L.embs_off = o;   o += kTopBuf * 4;
     L.bars_off = o;   o += n_stages * 16;
-    L.misc_off = o;   o += 32;
+    L.misc_off = o;   o += 128;
     L.total = o;
     return L;
 }
@@ -61,28 +64,6 @@ __device__ __forceinline__ float lex_lookup(const uint32_t *__restrict__ rows, c
     }
     if (lo < n && __ldg(rows + lo) == row) return __ldg(vals + lo);
     return 0.0f;
-}
-
-// Bitonic sort (descending) of n = 2^k entries (key, emb payload) in shared memory by
-// the R consumer threads.
-__device__ void bitonic_desc(uint64_t *keys, float *embs, uint32_t n, uint32_t t)
-{
-    for (uint32_t k = 2; k <= n; k <<= 1) {
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = t; i < (n >> 1); i += R) {
-                uint32_t lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-                uint32_t hi = lo | j;
-                uint64_t a = keys[lo], b = keys[hi];
-                bool desc = (lo & k) == 0;
-                if ((a < b) == desc) {
-                    keys[lo] = b; keys[hi] = a;
-                    float ea = embs[lo], eb = embs[hi];
-                    embs[lo] = eb; embs[hi] = ea;
-                }
-            }
-            named_bar_sync(1, R);
-        }
-    }
 }
 
 __device__ __forceinline__ uint32_t next_pow2(uint32_t x)
@@ -106,6 +87,13 @@ __device__ __forceinline__ rlr_cand ld_cand(const rlr_cand *p)
     return r;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // number of keys >= T in a descending list of `cnt` records
 __device__ __forceinline__ uint32_t count_ge(const rlr_cand *list, uint32_t lo, uint32_t cnt, uint64_t T)
 {
@@ -117,6 +105,21 @@ __device__ __forceinline__ uint32_t count_ge(const rlr_cand *list, uint32_t lo, 
     return lo;
 }
 
+// end (exclusive) of the run of records at positions >= c whose key is > TA.  The first four
+// positions are probed with independent loads (one L2 round trip covers the common case).
+__device__ __forceinline__ uint32_t extras_end(const rlr_cand *list, uint32_t c, uint32_t cnt, uint64_t TA)
+{
+    if (cnt <= c) return c;
+    uint64_t k[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) k[i] = (c + i < cnt) ? ld_key(list + c + i) : 0ull;
+    uint32_t n = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) n += (n == static_cast<uint32_t>(i) && k[i] > TA) ? 1u : 0u;
+    if (n < 4 || c + 4 >= cnt) return c + n;
+    return count_ge(list, c + 4, cnt, TA + 1);
+}
+
 // Reduce the L per-CTA lists (each sorted descending, `counts[j]` valid records) to the
 // global best m, by the R consumer threads of the last CTA.  Keys are unique.
 //   1. sample: the first c records of every list, sorted in shared memory; its m-th key
@@ -125,18 +128,18 @@ __device__ __forceinline__ uint32_t count_ge(const rlr_cand *list, uint32_t lo, 
 //      buffer re-sorted -- for evenly spread data there are none;
 //   3. if the extras do not fit (adversarially skewed lists): exact bisection on the key
 //      value for the global m-th key, then gather exactly m records.
-__device__ void final_merge(uint64_t *keys, float *embs, volatile uint32_t *s_cnt, volatile uint32_t *s_aux,
-                            const rlr_cand *lists, const uint32_t *counts, uint32_t Ln,
+__device__ void final_merge(uint64_t *keys, float *embs, uint32_t *s_counts, volatile uint32_t *s_cnt,
+                            volatile uint32_t *s_aux, const rlr_cand *lists, const uint32_t *counts, uint32_t Ln,
                             uint32_t m, uint32_t row_base, const uint32_t *__restrict__ lex_rows,
                             const float *__restrict__ lex_norm, uint32_t n_lex, rlr_cand *__restrict__ out,
-                            uint32_t *__restrict__ out_n, uint32_t t)
+                            uint32_t *__restrict__ out_n, uint32_t t, unsigned long long *tr)
 {
-    // total valid records
+    // counts -> shared memory (one batched L2 round trip), total valid records
     if (t == 0) { *s_cnt = 0; *s_aux = 0; }
     named_bar_sync(1, R);
     {
         uint32_t local = 0;
-        for (uint32_t j = t; j < Ln; j += R) local += __ldcg(counts + j);
+        for (uint32_t j = t; j < Ln; j += R) { const uint32_t cj = __ldcg(counts + j); s_counts[j] = cj; local += cj; }
         if (local) atomicAdd(const_cast<uint32_t *>(s_cnt), local);
     }
     named_bar_sync(1, R);
@@ -144,25 +147,27 @@ __device__ void final_merge(uint64_t *keys, float *embs, volatile uint32_t *s_cn
     const uint32_t m_out = total < m ? total : m;
     named_bar_sync(1, R);
 
-    uint32_t c = 1024u / Ln;
-    if (c > m) c = m;
-    {
-        const uint32_t want = (2u * m < Ln * m) ? 2u * m : Ln * m;
-        if (c * Ln < want) { c = kTopBuf / Ln; if (c > m) c = m; }
-        if (c == 0) c = 1;
-    }
+    // sample depth: the least c whose sample can hold m records, grown while it does not
+    // change the padded (power-of-two) sort size
+    uint32_t c = (m + Ln - 1) / Ln;
+    while (c < m && Ln * (c + 1) <= next_pow2(Ln * c)) ++c;
+    if (Ln * c > static_cast<uint32_t>(kTopBuf)) c = kTopBuf / Ln;
+    if (c == 0) c = 1;
     const uint32_t nA = Ln * c;
     uint32_t n2 = next_pow2(nA);
+#pragma unroll 4
     for (uint32_t i = t; i < n2; i += R) {
-        uint64_t k = 0; float e = 0.0f;
-        if (i < nA) {
-            const uint32_t j = i / c, p = i - j * c;
-            if (p < __ldcg(counts + j)) { const rlr_cand r = ld_cand(lists + static_cast<size_t>(j) * m + p); k = r.key; e = r.emb; }
-        }
-        keys[i] = k; embs[i] = e;
+        const uint32_t j = i / c, p = i - j * c;
+        const bool valid = (i < nA) && (p < s_counts[j < Ln ? j : 0]);
+        rlr_cand r;
+        r.key = 0; r.emb = 0.0f;
+        if (valid) r = ld_cand(lists + static_cast<size_t>(j) * m + p);
+        keys[i] = r.key; embs[i] = r.emb;
     }
     named_bar_sync(1, R);
+    if (tr != nullptr && t == 0) tr[1] = globaltimer_ns();
     bitonic_desc(keys, embs, n2, t);
+    if (tr != nullptr && t == 0) tr[2] = globaltimer_ns();
 
     uint32_t n_final = n2;                       // sorted entries currently in keys[]
     if (m_out > 0) {
@@ -173,21 +178,19 @@ __device__ void final_merge(uint64_t *keys, float *embs, volatile uint32_t *s_cn
         if (t == 0) { *s_cnt = 0; *s_aux = 0; }
         named_bar_sync(1, R);
         uint32_t my_extra = 0;
-        for (uint32_t j = t; j < Ln; j += R) {
-            const uint32_t cj = __ldcg(counts + j);
-            if (cj > c) my_extra += count_ge(lists + static_cast<size_t>(j) * m, c, cj, TA + 1) - c;
-        }
+        for (uint32_t j = t; j < Ln; j += R) my_extra += extras_end(lists + static_cast<size_t>(j) * m, c, s_counts[j], TA) - c;
         if (my_extra) atomicAdd(const_cast<uint32_t *>(s_cnt), my_extra);
         named_bar_sync(1, R);
         const uint32_t n_extra = *s_cnt;
         named_bar_sync(1, R);
+        if (tr != nullptr && t == 0) { tr[3] = globaltimer_ns(); tr[8] = (static_cast<unsigned long long>(total) << 32) | n_extra; tr[9] = (static_cast<unsigned long long>(c) << 32) | n2; }
         if (n_extra != 0 && base + n_extra <= kTopBuf) {
             // append extras after the kept prefix, re-sort
             for (uint32_t j = t; j < Ln; j += R) {
-                const uint32_t cj = __ldcg(counts + j);
+                const uint32_t cj = s_counts[j];
                 if (cj <= c) continue;
                 const rlr_cand *lj = lists + static_cast<size_t>(j) * m;
-                const uint32_t e_end = count_ge(lj, c, cj, TA + 1);
+                const uint32_t e_end = extras_end(lj, c, cj, TA);
                 if (e_end > c) {
                     const uint32_t slot = atomicAdd(const_cast<uint32_t *>(s_aux), e_end - c);
                     for (uint32_t p = c; p < e_end; ++p) { const rlr_cand r = ld_cand(lj + p); keys[base + slot + p - c] = r.key; embs[base + slot + p - c] = r.emb; }
@@ -241,6 +244,7 @@ __device__ void final_merge(uint64_t *keys, float *embs, volatile uint32_t *s_cn
             n_final = n2;
         }
     }
+    if (tr != nullptr && t == 0) tr[4] = globaltimer_ns();
     for (uint32_t i = t; i < m; i += R) {
         rlr_cand r;
         if (i < m_out && i < n_final) {
@@ -255,12 +259,44 @@ __device__ void final_merge(uint64_t *keys, float *embs, volatile uint32_t *s_cn
     if (t == 0) *out_n = m_out;
 }
 
+constexpr int kTopR = 8;   // a CTA publishes its r-th best score, r = ceil(m / grid) <= kTopR
+
+// warp 0: fold the keys appended since the last call (keys[from, to)) into the CTA's sorted
+// top-r and publish the r-th best score.  r rounds of "largest key below the previous one".
+__device__ __forceinline__ void top_r_update_warp(const uint64_t *keys, uint32_t from, uint32_t to,
+                                                  volatile uint64_t *top, volatile uint32_t *n_top, uint32_t r,
+                                                  uint32_t lane, uint32_t *pub_slot)
+{
+    const uint32_t n_old = *n_top;
+    const uint64_t mine_old = lane < n_old ? top[lane] : 0ull;
+    __syncwarp();
+    uint64_t bound = ~0ull, best = 0;
+    uint32_t n = 0;
+    for (uint32_t round = 0; round < r; ++round) {
+        best = mine_old < bound ? mine_old : 0ull;
+        for (uint32_t i = from + lane; i < to; i += 32) {
+            const uint64_t k = keys[i];
+            if (k < bound && k > best) best = k;
+        }
+        best = warp_max_u64(best);
+        if (best == 0ull) break;
+        if (lane == 0) top[round] = best;
+        bound = best;
+        ++n;
+    }
+    if (lane == 0) {
+        *n_top = n;
+        if (n >= r) *reinterpret_cast<volatile uint32_t *>(pub_slot) = static_cast<uint32_t>(best >> 32);
+    }
+}
+
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ g_query,
                  uint32_t n_rows, uint32_t row_base, uint32_t n_chunks, float w_embed, float w_lex,
                  const uint32_t *__restrict__ lex_rows, const float *__restrict__ lex_norm, uint32_t n_lex,
-                 uint32_t m, int n_stages, rlr_cand *g_lists, uint32_t *g_counts, uint32_t *g_ticket,
-                 rlr_cand *g_out, uint32_t *g_out_n)
+                 uint32_t m, uint32_t buf_cap, uint32_t r_pub, int n_stages, rlr_cand *g_lists, uint32_t *g_counts,
+                 uint32_t *g_pub, uint32_t *g_ticket, uint32_t *g_tile_ctr, rlr_cand *g_out, uint32_t *g_out_n,
+                 unsigned long long *g_trace /* dev-only phase timestamps, may be null */)
 {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B atoms are 1024 B: align the carve-up by hand.
@@ -277,6 +313,14 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
     float *embs = reinterpret_cast<float *>(smem + L.embs_off);
     volatile uint32_t *s_count = reinterpret_cast<volatile uint32_t *>(smem + L.misc_off);
     volatile uint64_t *s_tau = reinterpret_cast<volatile uint64_t *>(smem + L.misc_off + 8);
+    volatile uint32_t *s_flag = reinterpret_cast<volatile uint32_t *>(smem + L.misc_off + 16);
+    volatile uint32_t *s_tau_g = reinterpret_cast<volatile uint32_t *>(smem + L.misc_off + 20);
+    volatile uint32_t *s_done = reinterpret_cast<volatile uint32_t *>(smem + L.misc_off + 24);
+    volatile uint32_t *s_ntop = reinterpret_cast<volatile uint32_t *>(smem + L.misc_off + 28);
+    volatile uint64_t *s_top = reinterpret_cast<volatile uint64_t *>(smem + L.misc_off + 32);   // [kTopR]
+    // tile-id mailbox, one slot per pipeline stage (<= 8): the slot belongs to whoever owns the
+    // stage, so the producer can run any number of tiles ahead without overwriting an unread id
+    volatile uint32_t *s_tile = reinterpret_cast<volatile uint32_t *>(smem + L.misc_off + 96);
     const uint32_t stages_addr = smem_u32(smem + L.stages_off);
     const uint32_t full_bar = smem_u32(smem + L.bars_off);
     const uint32_t empty_bar = full_bar + n_stages * 8;
@@ -292,10 +336,15 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
         }
         *s_count = 0;
         *s_tau = 0;
+        *s_flag = 0;
+        *s_tau_g = 0;
+        *s_done = 0;
+        *s_ntop = 0;
         fence_mbar_init();
     }
     for (uint32_t i = tid; i < q_floats; i += kScanThreads) q_s[i] = g_query[i];
     __syncthreads();
+    if (g_trace != nullptr && tid == 0) g_trace[blockIdx.x] = globaltimer_ns();
 
     if (warp == R / 32) {
         // ------------------------------ TMA producer ------------------------------
@@ -303,9 +352,19 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
             tma_prefetch_desc(&tmap);
             const uint64_t pol = policy_evict_first();
             uint32_t stage = 0, phase = 0;
-            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            // Tiles are handed out dynamically (first one static, then a global counter): SMs
+            // do not get equal shares of HBM bandwidth, and with a static split the slow ones
+            // finish ~40 % later than the fast ones.  Tile ids still ascend within a CTA.
+            uint32_t tile = blockIdx.x;
+            for (;;) {
+                const bool has = tile < n_tiles;
+                uint32_t next_tile = 0xffffffffu;
+                if (has) next_tile = atomicAdd(g_tile_ctr, 1u) + gridDim.x;   // consumed a whole tile later
+                mbar_wait(empty_bar + stage * 8, phase ^ 1);
+                s_tile[stage] = has ? tile : 0xffffffffu;                    // published by the arrive below
+                if (!has) { mbar_arrive(full_bar + stage * 8); break; }
                 for (uint32_t kb = 0; kb < KB; ++kb) {
-                    mbar_wait(empty_bar + stage * 8, phase ^ 1);
+                    if (kb != 0) mbar_wait(empty_bar + stage * 8, phase ^ 1);
                     mbar_arrive_expect_tx(full_bar + stage * 8, kStageBytes);
 #pragma unroll
                     for (int c = 0; c < CH; ++c)
@@ -314,7 +373,25 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
                                     static_cast<int32_t>(tile * R), full_bar + stage * 8, pol);
                     if (++stage == static_cast<uint32_t>(n_stages)) { stage = 0; phase ^= 1; }
                 }
+                tile = next_tile;
             }
+        }
+        return;
+    }
+    if (warp == R / 32 + 1) {
+        // ---------------- threshold warp: global lower bound of the m-th best score ----------------
+        // Every CTA publishes the score of its r-th best row so far, r = ceil(m / grid).  All
+        // CTAs then hold >= r rows at or above min_j pub[j], i.e. >= m rows in total, so the
+        // global m-th best score is >= that minimum at any moment: rows strictly below it can
+        // be dropped without ever entering a buffer.  Stale reads only make the bound looser.
+        if (r_pub == 0) return;
+        const volatile uint32_t *pub = g_pub;
+        while (*s_done == 0) {
+            uint32_t v = 0xffffffffu;
+            for (uint32_t j = lane; j < gridDim.x; j += 32) { const uint32_t u = pub[j]; v = u < v ? u : v; }
+            v = __reduce_min_sync(0xffffffffu, v);
+            if (lane == 0 && v > *s_tau_g) *s_tau_g = v;
+            __nanosleep(400);
         }
         return;
     }
@@ -326,11 +403,16 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
     const float4 *q4 = reinterpret_cast<const float4 *>(q_s);
     uint32_t stage = 0, phase = 0;
     uint64_t tau = 0;                             // key of the CTA's current M-th best
+    uint32_t prev_cnt = 0, n_my_tiles = 0;
 
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (;;) {
+        mbar_wait(full_bar + stage * 8, phase);   // first stage of the next tile (or the end marker)
+        const uint32_t tile = s_tile[stage];
+        if (tile == 0xffffffffu) break;
+        ++n_my_tiles;
         float acc = 0.0f;
         for (uint32_t kb = 0; kb < KB; ++kb) {
-            mbar_wait(full_bar + stage * 8, phase);
+            if (kb != 0) mbar_wait(full_bar + stage * 8, phase);
             const uint8_t *sp = stage0 + stage * kStageBytes;
             const float4 *qp = q4 + kb * (CH * 8);
 #pragma unroll
@@ -356,7 +438,8 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
         if (n_lex) lexv = lex_lookup(lex_rows, lex_norm, n_lex, row_local);
         const float combined = add_rn(mul_rn(w_embed, acc), mul_rn(w_lex, lexv));
         const uint64_t key = make_key(combined, row_base + row_local);
-        const bool pass = (row_local < n_rows) && (key > tau);
+        const uint32_t tau_g = *s_tau_g;          // ordered score bits; 0 while unknown
+        const bool pass = (row_local < n_rows) && (key > tau) && (static_cast<uint32_t>(key >> 32) >= tau_g);
         const uint32_t mask = __ballot_sync(0xffffffffu, pass);
         if (mask) {
             uint32_t base = 0;
@@ -369,47 +452,94 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
             }
         }
         named_bar_sync(1, R);
-        const uint32_t cnt = *s_count;
+        uint32_t cnt = *s_count;
+        if (warp == 0 && r_pub != 0 && cnt > prev_cnt)
+            top_r_update_warp(keys, prev_cnt, cnt, s_top, s_ntop, r_pub, lane, g_pub + blockIdx.x);
         named_bar_sync(1, R);
-        if (cnt > kTopBuf - R) {
-            // prune: keep the best m, raise the threshold
-            for (uint32_t i = cnt + t; i < kTopBuf; i += R) keys[i] = 0;
+        if (cnt > buf_cap - R) {
+            // prune: keep the best m, raise the threshold.  buf_cap (a power of two <= kTopBuf)
+            // is sized so that one prune costs about as much HBM time as the TMA ring holds.
+            for (uint32_t i = cnt + t; i < buf_cap; i += R) keys[i] = 0;
             named_bar_sync(1, R);
-            bitonic_desc(keys, embs, kTopBuf, t);
+            bitonic_desc(keys, embs, buf_cap, t);
             if (t == 0) {
-                *s_count = cnt < m ? cnt : m;
+                const uint32_t kept = cnt < m ? cnt : m;
+                *s_count = kept;
                 *s_tau = cnt >= m ? keys[m - 1] : 0;
+                if (r_pub != 0) {                 // the sorted prefix IS the top-r now
+                    const uint32_t nt = kept < r_pub ? kept : r_pub;
+                    for (uint32_t i = 0; i < nt; ++i) s_top[i] = keys[i];
+                    *s_ntop = nt;
+                    if (nt >= r_pub)
+                        *reinterpret_cast<volatile uint32_t *>(g_pub + blockIdx.x) = static_cast<uint32_t>(keys[r_pub - 1] >> 32);
+                }
             }
             named_bar_sync(1, R);
             tau = *s_tau;
+            cnt = *s_count;
+            named_bar_sync(1, R);             // reads done before the next tile's appends bump s_count
         }
+        prev_cnt = cnt;
     }
 
-    // ---- final: sort what is left, write the CTA's best m records ----
+    // ---- final: drop what the freshest global bound excludes, sort the rest, write the list ----
+    if (g_trace != nullptr && t == 0) g_trace[gridDim.x + blockIdx.x] = globaltimer_ns();
+    if (t == 0) { *s_done = 1; *s_flag = 0xffffffffu; }
     named_bar_sync(1, R);
     const uint32_t cnt = *s_count;
-    const uint32_t n2 = next_pow2(cnt);
-    for (uint32_t i = cnt + t; i < n2; i += R) keys[i] = 0;
+    if (r_pub != 0) {
+        const volatile uint32_t *pub = g_pub;
+        uint32_t v = 0xffffffffu;
+        for (uint32_t j = t; j < gridDim.x; j += R) { const uint32_t u = pub[j]; v = u < v ? u : v; }
+        v = __reduce_min_sync(0xffffffffu, v);
+        if (lane == 0) atomicMin(const_cast<uint32_t *>(s_flag), v);
+    }
+    named_bar_sync(1, R);                     // everyone has read cnt; the atomicMin results are in
+    uint32_t tau_fin = *s_tau_g;
+    if (r_pub != 0 && *s_flag > tau_fin) tau_fin = *s_flag;
+    if (t == 0) *s_count = 0;
     named_bar_sync(1, R);
-    bitonic_desc(keys, embs, n2, t);
-    const uint32_t keep = cnt < m ? cnt : m;
-    rlr_cand *out = g_lists + static_cast<size_t>(blockIdx.x) * m;
-    for (uint32_t i = t; i < m; i += R) {
-        rlr_cand c;
-        if (i < keep) {
-            c.key = keys[i];
-            c.emb = embs[i];
-            c.lex = n_lex ? lex_lookup(lex_rows, lex_norm, n_lex, key_row(c.key) - row_base) : 0.0f;
-        } else {
-            c.key = 0; c.emb = 0.0f; c.lex = 0.0f;
+    // the TMA ring is idle now (every issued load was consumed): reuse it as the compaction target
+    uint64_t *keys2 = reinterpret_cast<uint64_t *>(smem + L.stages_off);
+    float *embs2 = reinterpret_cast<float *>(smem + L.stages_off + kTopBuf * 8);
+    for (uint32_t i0 = 0; i0 < cnt; i0 += R) {
+        const uint32_t i = i0 + t;
+        const uint64_t k = i < cnt ? keys[i] : 0ull;
+        const bool keep_it = (i < cnt) && (static_cast<uint32_t>(k >> 32) >= tau_fin);
+        const uint32_t mk = __ballot_sync(0xffffffffu, keep_it);
+        if (mk) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(const_cast<uint32_t *>(s_count), __popc(mk));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep_it) {
+                const uint32_t idx = base + __popc(mk & ((1u << lane) - 1u));
+                keys2[idx] = k;
+                embs2[idx] = embs[i];
+            }
         }
+    }
+    named_bar_sync(1, R);
+    const uint32_t cnt2 = *s_count;
+    const uint32_t n2 = next_pow2(cnt2);
+    for (uint32_t i = cnt2 + t; i < n2; i += R) keys2[i] = 0;
+    named_bar_sync(1, R);
+    bitonic_desc(keys2, embs2, n2, t);
+    const uint32_t keep = cnt2 < m ? cnt2 : m;
+    rlr_cand *out = g_lists + static_cast<size_t>(blockIdx.x) * m;
+    for (uint32_t i = t; i < keep; i += R) {       // records beyond `keep` are never read
+        rlr_cand c;
+        c.key = keys2[i];
+        c.emb = embs2[i];
+        c.lex = n_lex ? lex_lookup(lex_rows, lex_norm, n_lex, key_row(c.key) - row_base) : 0.0f;
         out[i] = c;
     }
     if (t == 0) g_counts[blockIdx.x] = keep;
-    if (g_out == nullptr) return;
+    if (g_trace != nullptr && t == 0) {
+        g_trace[2 * gridDim.x + blockIdx.x] = globaltimer_ns();
+        g_trace[3 * gridDim.x + blockIdx.x] = (static_cast<unsigned long long>(n_my_tiles) << 48) | (static_cast<unsigned long long>(cnt) << 24) | cnt2;
+    }
 
     // ---- cross-CTA merge, done by whichever CTA finishes last (no second launch) ----
-    volatile uint32_t *s_flag = reinterpret_cast<volatile uint32_t *>(smem + L.misc_off + 16);
     __threadfence();
     named_bar_sync(1, R);
     if (t == 0) {
@@ -417,11 +547,18 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
         *s_flag = (ticket == gridDim.x - 1) ? 1u : 0u;
     }
     named_bar_sync(1, R);
-    if (*s_flag == 0) return;
+    const uint32_t is_last = *s_flag;
+    named_bar_sync(1, R);                     // s_flag is reused below: everyone reads it first
+    if (is_last == 0) return;
     __threadfence();
-    if (t == 0) *g_ticket = 0; // stream-ordered launches reuse the ticket
-    final_merge(keys, embs, s_count, s_flag, g_lists, g_counts, gridDim.x, m, row_base, lex_rows, lex_norm, n_lex,
-                g_out, g_out_n, t);
+    if (t == 0) { *g_ticket = 0; *g_tile_ctr = 0; } // stream-ordered launches reuse the ticket, the tile counter ...
+    for (uint32_t j = t; j < gridDim.x; j += R) g_pub[j] = 0;   // ... and the published bounds
+    if (g_out == nullptr) return;
+    unsigned long long *tr = g_trace != nullptr ? g_trace + 4 * gridDim.x : nullptr;
+    if (tr != nullptr && t == 0) tr[0] = globaltimer_ns();
+    final_merge(keys, embs, reinterpret_cast<uint32_t *>(smem + L.stages_off + kTopBuf * 12), s_count, s_flag, g_lists,
+                g_counts, gridDim.x, m, row_base, lex_rows, lex_norm, n_lex, g_out, g_out_n, t, tr);
+    if (tr != nullptr && t == 0) tr[7] = globaltimer_ns();
 }
 
 } // namespace
@@ -440,6 +577,7 @@ void scan_plan(int sm_count, int max_smem_optin, uint32_t n_rows, uint32_t pitch
     while (stages > 2 && smem_layout(stages, q_floats).total + 1024 > static_cast<uint32_t>(max_smem_optin)) --stages;
     a->grid = grid;
     a->n_stages = stages;
+    a->buf_cap = 0;
     a->smem_bytes = static_cast<int>(smem_layout(stages, q_floats).total + 1024);
 }
 
@@ -453,11 +591,30 @@ cudaError_t scan_configure()
     return cudaFuncSetAttribute(scan_topm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
 }
 
+// candidate-buffer capacity for a given m: room for m kept + a few tiles of new entries
+static uint32_t pick_buf_cap(uint32_t m)
+{
+    uint32_t want = 2 * m > m + 2 * R ? 2 * m : m + 2 * R;
+    uint32_t cap = 512;
+    while (cap < want) cap <<= 1;
+    if (cap > static_cast<uint32_t>(kTopBuf)) cap = kTopBuf;
+    if (const char *e = getenv("RLR_DEBUG_BUFCAP")) {       // tuning knob (power of two, >= m + R)
+        const uint32_t v = static_cast<uint32_t>(atoi(e));
+        if (v >= m + R && v <= static_cast<uint32_t>(kTopBuf) && (v & (v - 1)) == 0) cap = v;
+    }
+    return cap;
+}
+
 cudaError_t scan_launch(const ScanArgs &a, cudaStream_t stream)
 {
+    const uint32_t buf_cap = a.buf_cap ? a.buf_cap : pick_buf_cap(a.m);
+    const bool no_merge = getenv("RLR_DEBUG_NOMERGE") != nullptr;   // tuning knob: time the scan without final_merge
+    uint32_t r_pub = (a.m + a.grid - 1) / a.grid;                    // r-th best published per CTA (0 = off)
+    if (r_pub > static_cast<uint32_t>(kTopR) || a.d_pub == nullptr || getenv("RLR_DEBUG_NOGLOBALTAU")) r_pub = 0;
     scan_topm_kernel<<<a.grid, kScanThreads, a.smem_bytes, stream>>>(
         *a.tmap, a.d_query, a.n_rows, a.row_base, a.pitch / kChunkFloats, a.w_embed, a.w_lex, a.d_lex_rows,
-        a.d_lex_norm, a.n_lex, a.m, a.n_stages, a.d_lists, a.d_counts, a.d_ticket, a.d_out, a.d_out_n);
+        a.d_lex_norm, a.n_lex, a.m, buf_cap, r_pub, a.n_stages, a.d_lists, a.d_counts, a.d_pub, a.d_ticket,
+        a.d_ticket + 1, no_merge ? nullptr : a.d_out, a.d_out_n, a.d_trace);
     return cudaGetLastError();
 }
 
