@@ -95,100 +95,124 @@ mmr_pairwise_kernel(const float *__restrict__ emb, uint32_t pitch, const rlr_can
     if (i < j && j < p) tri[static_cast<size_t>(j) * (j - 1) / 2 + i] = acc;
 }
 
-// Greedy selection loop, run by ONE warp: candidate i lives in lane (i & 31), slot (i >> 5),
-// with its relevance, running max_sim and current position in `remaining` in registers.
-// Per selection: CPL shared-memory reads of the similarity triangle, CPL fmax/mul/sub, a
-// local argmax, two redux.sync + ballot + shfl for the warp argmax -- no block barrier.
-// The other warps of the CTA only help to stage the triangle into shared memory.
+// Greedy selection loop, run by FOUR warps (one per SM sub-partition): candidate i lives in
+// thread (i % 128), slot (i / 128), with its relevance term, running max_sim and current
+// position in `remaining` in registers.  Per selection: CPT shared-memory reads of the
+// similarity triangle, CPT fmax/mul/sub, a local argmax, two redux.sync + ballot + shfl for the
+// warp argmax, then ONE named barrier to exchange the four warp winners through a
+// double-buffered shared slot.  The remaining warps of the CTA only help to stage the triangle.
 constexpr int kGreedyThreads = 256;
+constexpr int kLoopThreads = 128;
 
-// The selection loop proper.  `tri` is either the shared-memory copy (LDS) or the global
-// triangle; the body is branch-free per slot (dead / out-of-range slots compute on a
-// clamped index and are masked out of the argmax) so that the CPL loads issue back to back.
-template <int CPL>
+template <int CPT>
 __device__ __forceinline__ void greedy_loop(const float *tri, const rlr_cand *__restrict__ cands,
                                             const float *__restrict__ rel_opt, uint32_t p, uint32_t top_k, float lambda,
                                             uint32_t *__restrict__ sel_pos, uint32_t *__restrict__ sel_n,
-                                            rlr_cand *__restrict__ result, uint32_t lane)
+                                            rlr_cand *__restrict__ result, uint32_t tid, uint64_t (*s_best)[4],
+                                            uint32_t (*s_besti)[4])
 {
-    float rel[CPL], max_sim[CPL];
-    uint32_t pos[CPL];
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    float rel_term[CPT], max_sim[CPT];
+    uint32_t pos[CPT], tri_row[CPT];
     uint32_t alive = 0, rel_ok = 0;                        // bit s: slot s
+    const float one_minus = sub_rn(1.0f, lambda);          // (1.0 - diversity_factor), :808
+    const uint32_t i_max = p - 1;
 #pragma unroll
-    for (int s = 0; s < CPL; ++s) {
-        const uint32_t i = lane + 32u * s;
-        rel[s] = 0.0f;
+    for (int s = 0; s < CPT; ++s) {
+        const uint32_t i = tid + kLoopThreads * s;
+        const uint32_t ic = i > i_max ? i_max : i;         // out-of-range slots are never alive
+        float rel = 0.0f;
         max_sim[s] = 0.0f;                                 // fold(0.0_f32, max), :804
         pos[s] = i;
         if (i < p) {
-            rel[s] = rel_opt != nullptr ? rel_opt[i] : key_score(cands[i].key);
+            rel = rel_opt != nullptr ? rel_opt[i] : key_score(cands[i].key);
             if (i != 0) alive |= 1u << s;
-            if (is_finite_f32(rel[s])) rel_ok |= 1u << s;  // :794-797
+            if (is_finite_f32(rel)) rel_ok |= 1u << s;     // :794-797
             if (i == p - 1 && i != 0) pos[s] = 0;          // swap_remove(0), :783
         }
+        rel_term[s] = mul_rn(one_minus, rel);              // loop invariant, same rounding as :808
+        tri_row[s] = ic * (ic - 1) / 2;
     }
-    uint32_t n_rem = p - 1, n_sel = 1, last = 0;
-    if (lane == 0) {
+    uint32_t n_rem = p - 1, n_sel = 1, last = 0, buf = 0;
+    if (tid == 0) {
         sel_pos[0] = 0;
         if (result != nullptr) result[0] = cands[0];
     }
-    const float one_minus = sub_rn(1.0f, lambda);          // (1.0 - diversity_factor), :808
-    const uint32_t i_max = p - 1;
 
+    // Written with selects, not short-circuit logic: a branch per slot would serialise the
+    // independent per-candidate chains of an in-order warp.
     while (n_sel < top_k && n_rem > 0) {                   // :788
-        float sim[CPL];
-        const uint32_t tl = last * (last - 1) / 2;         // row offset of `last` in the triangle (last > i)
+        float sim[CPT];
+        const uint32_t tl = last * (last - 1) / 2;         // row of `last` in the triangle (for i < last)
 #pragma unroll
-        for (int s = 0; s < CPL; ++s) {
-            uint32_t i = lane + 32u * s;
-            i = i > i_max ? i_max : i;                     // clamp: masked out below
-            const uint32_t idx = i < last ? tl + i : (i == last ? 0u : i * (i - 1) / 2 + last);
+        for (int s = 0; s < CPT; ++s) {
+            uint32_t i = tid + kLoopThreads * s;
+            i = i > i_max ? i_max : i;
+            const uint32_t idx = i < last ? tl + i : (i == last ? 0u : tri_row[s] + last);
             sim[s] = tri[idx];
         }
-        uint32_t best_hi = 0, best_lo = 0, best_i = 0;
-        const uint32_t live = alive & rel_ok;
+        uint64_t best = 0;
+        uint32_t best_i = 0;
+        const uint32_t live = alive & rel_ok;              // :794-797
 #pragma unroll
-        for (int s = 0; s < CPL; ++s) {
-            // dead slots keep updating a max_sim nobody reads; alive slots follow :803-804
-            if (is_finite_f32(sim[s]) && (alive & (1u << s))) max_sim[s] = fmaxf(max_sim[s], sim[s]);
-            const float mmr = sub_rn(mul_rn(one_minus, rel[s]), mul_rn(lambda, max_sim[s])); // :808-809
-            const bool ok = ((live >> s) & 1u) && is_finite_f32(mmr);                        // :794, :812
-            const uint32_t hi = ok ? ord_f32(mmr) : 0u;
-            const uint32_t lo = 0xffffffffu - pos[s];
-            const bool better = (hi > best_hi) || (hi == best_hi && hi != 0u && lo > best_lo);
-            if (better) { best_hi = hi; best_lo = lo; best_i = lane + 32u * s; }
+        for (int s = 0; s < CPT; ++s) {
+            const bool upd = is_finite_f32(sim[s]) & (((alive >> s) & 1u) != 0);      // :803
+            const float ms = fmaxf(max_sim[s], sim[s]);                               // :804
+            max_sim[s] = upd ? ms : max_sim[s];
+            const float mmr = sub_rn(rel_term[s], mul_rn(lambda, max_sim[s]));        // :808-809
+            const bool ok = (((live >> s) & 1u) != 0) & is_finite_f32(mmr);           // :812
+            const uint64_t key = (static_cast<uint64_t>(ord_f32(mmr)) << 32) | (0xffffffffu - pos[s]);
+            const uint64_t k = ok ? key : 0ull;
+            const bool better = k > best;                  // strict '>' on (score, lowest current position)
+            best = better ? k : best;
+            best_i = better ? tid + kLoopThreads * s : best_i;
         }
-        const uint32_t mh = __reduce_max_sync(0xffffffffu, best_hi);
-        if (mh == 0) break;                                // :819-822 (no finite candidate left)
-        const uint32_t ml = __reduce_max_sync(0xffffffffu, best_hi == mh ? best_lo : 0u);
-        const uint32_t owner = __ffs(__ballot_sync(0xffffffffu, best_hi == mh && best_lo == ml)) - 1;
-        best_i = __shfl_sync(0xffffffffu, best_i, owner);
-        const uint32_t b_pos = 0xffffffffu - ml;
+        const uint64_t wk = warp_max_u64(best);
+        const uint32_t owner = __ffs(__ballot_sync(0xffffffffu, best == wk)) - 1;
+        const uint32_t wi = __shfl_sync(0xffffffffu, best_i, owner);
+        if (lane == 0) { s_best[buf][warp] = wk; s_besti[buf][warp] = wi; }
+        named_bar_sync(2, kLoopThreads);
+        uint64_t gk = 0;
+        uint32_t gi = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint64_t k = s_best[buf][w];
+            const uint32_t ii = s_besti[buf][w];
+            const bool better = k > gk;
+            gk = better ? k : gk;
+            gi = better ? ii : gi;
+        }
+        buf ^= 1u;
+        if (gk == 0ull) break;                             // :819-822 (no finite candidate left)
+        const uint32_t b_pos = 0xffffffffu - static_cast<uint32_t>(gk);
         // swap_remove(best_idx), :825: winner leaves, the last element moves into its slot
 #pragma unroll
-        for (int s = 0; s < CPL; ++s) {
-            const uint32_t i = lane + 32u * s;
-            const bool is_alive = (alive >> s) & 1u;
-            if (is_alive && i != best_i && pos[s] == n_rem - 1) pos[s] = b_pos;
-            if (i == best_i) alive &= ~(1u << s);
+        for (int s = 0; s < CPT; ++s) {
+            const uint32_t i = tid + kLoopThreads * s;
+            const bool mv = (((alive >> s) & 1u) != 0) & (i != gi) & (pos[s] == n_rem - 1);
+            pos[s] = mv ? b_pos : pos[s];
+            alive &= ~((i == gi ? 1u : 0u) << s);
         }
-        if (lane == 0) {
-            sel_pos[n_sel] = best_i;
-            if (result != nullptr) result[n_sel] = cands[best_i];
+        if (tid == 0) {
+            sel_pos[n_sel] = gi;
+            if (result != nullptr) result[n_sel] = cands[gi];
         }
-        ++n_sel; --n_rem; last = best_i;
+        ++n_sel; --n_rem; last = gi;
     }
-    if (lane == 0) *sel_n = n_sel;
+    if (tid == 0) *sel_n = n_sel;
 }
 
-template <int CPL>
+template <int CPT>
 __global__ void __launch_bounds__(kGreedyThreads, 1)
 mmr_greedy_kernel(const float *__restrict__ tri_g, const rlr_cand *__restrict__ cands,
                   const float *__restrict__ rel_opt, const uint32_t *__restrict__ d_n, uint32_t top_k,
                   float lambda, int tri_in_smem, uint32_t *__restrict__ sel_pos, uint32_t *__restrict__ sel_n,
                   rlr_cand *__restrict__ result)
 {
-    extern __shared__ __align__(16) float tri_s[];
+    extern __shared__ __align__(128) float tri_s[];
+    __shared__ uint64_t s_best[2][4];
+    __shared__ uint32_t s_besti[2][4];
+    __shared__ __align__(8) uint64_t s_mbar;
     const uint32_t p = *d_n;
     const uint32_t tid = threadIdx.x;
     if (p == 0) {
@@ -196,18 +220,32 @@ mmr_greedy_kernel(const float *__restrict__ tri_g, const rlr_cand *__restrict__ 
         return;
     }
     if (tri_in_smem) {
+        // stage the triangle with bulk async copies (UBLKCP): one thread, a handful of instructions
         const uint32_t n_tri = p * (p - 1) / 2;
-        const uint32_t n4 = n_tri >> 2;
-        const float4 *g4 = reinterpret_cast<const float4 *>(tri_g);
-        float4 *s4 = reinterpret_cast<float4 *>(tri_s);
-        for (uint32_t x = tid; x < n4; x += kGreedyThreads) s4[x] = g4[x];
-        for (uint32_t x = (n4 << 2) + tid; x < n_tri; x += kGreedyThreads) tri_s[x] = tri_g[x];
+        const uint32_t bytes16 = (n_tri * 4u) & ~15u;
+        const uint32_t bar = smem_u32(&s_mbar);
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+        }
         __syncthreads();
-        if (tid >= 32) return;
-        greedy_loop<CPL>(tri_s, cands, rel_opt, p, top_k, lambda, sel_pos, sel_n, result, tid);
+        if (tid == 0) {
+            mbar_arrive_expect_tx(bar, bytes16);
+            for (uint32_t off = 0; off < bytes16; off += 32768u) {
+                const uint32_t n = bytes16 - off < 32768u ? bytes16 - off : 32768u;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(tri_s) + off), "l"(reinterpret_cast<const uint8_t *>(tri_g) + off), "r"(n), "r"(bar)
+                             : "memory");
+            }
+        }
+        for (uint32_t x = (bytes16 >> 2) + tid; x < n_tri; x += kGreedyThreads) tri_s[x] = tri_g[x];   // < 4 floats
+        if (bytes16) mbar_wait(bar, 0);
+        __syncthreads();
+        if (tid >= kLoopThreads) return;
+        greedy_loop<CPT>(tri_s, cands, rel_opt, p, top_k, lambda, sel_pos, sel_n, result, tid, s_best, s_besti);
     } else {
-        if (tid >= 32) return;
-        greedy_loop<CPL>(tri_g, cands, rel_opt, p, top_k, lambda, sel_pos, sel_n, result, tid);
+        if (tid >= kLoopThreads) return;
+        greedy_loop<CPT>(tri_g, cands, rel_opt, p, top_k, lambda, sel_pos, sel_n, result, tid, s_best, s_besti);
     }
 }
 
@@ -249,11 +287,11 @@ cudaError_t mmr_configure()
     e = cudaFuncSetAttribute(mmr_pairwise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              2 * T * PADW * static_cast<int>(sizeof(float)));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(mmr_greedy_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 4 * 1024);
+    e = cudaFuncSetAttribute(mmr_greedy_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 4 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(mmr_greedy_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 4 * 1024);
+    e = cudaFuncSetAttribute(mmr_greedy_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 4 * 1024);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(mmr_greedy_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 4 * 1024);
+    return cudaFuncSetAttribute(mmr_greedy_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 4 * 1024);
 }
 
 cudaError_t mmr_launch(const MmrArgs &a, cudaStream_t stream, uint32_t *launches)
@@ -270,13 +308,13 @@ cudaError_t mmr_launch(const MmrArgs &a, cudaStream_t stream, uint32_t *launches
     const size_t tri_bytes = static_cast<size_t>(a.p_cap) * (a.p_cap - 1) / 2 * sizeof(float);
     const size_t smem_cap = static_cast<size_t>(a.max_smem_optin) - 4 * 1024;
     const int in_smem = tri_bytes <= smem_cap;
-    const size_t smem = in_smem ? tri_bytes + 16 : 0;
+    const size_t smem = in_smem ? tri_bytes + 128 : 0;
 #define RLR_GREEDY(CPL)                                                                                               \
     mmr_greedy_kernel<CPL><<<1, kGreedyThreads, smem, stream>>>(a.d_tri, a.d_cands, a.d_rel, a.d_n, a.top_k, a.lambda, \
                                                                 in_smem, a.d_sel_pos, a.d_sel_n, a.d_result)
-    if (a.p_cap <= 320) RLR_GREEDY(10);
-    else if (a.p_cap <= 512) RLR_GREEDY(16);
-    else RLR_GREEDY(32);
+    if (a.p_cap <= 384) RLR_GREEDY(3);
+    else if (a.p_cap <= 512) RLR_GREEDY(4);
+    else RLR_GREEDY(8);
 #undef RLR_GREEDY
     if (launches) ++*launches;
     return cudaGetLastError();
