@@ -103,12 +103,19 @@ typedef struct rlr_timings {
 } rlr_timings;
 
 /* store flags */
-#define RLR_STORE_KEEP_F16      0x1u  /* also keep an f16 copy of the rows (config 5)      */
+#define RLR_STORE_KEEP_F16      0x1u  /* keep the f32 rows AND a binary16 copy of them      */
 #define RLR_STORE_CHECK_FINITE  0x2u  /* scan uploaded rows for NaN/Inf on the device      */
+#define RLR_STORE_F16_ONLY      0x4u  /* keep only the binary16 copy (half the HBM, config 5) */
 
 /* search flags */
 #define RLR_QUERY_PRENORMALIZED 0x1u  /* skip the normalize(&mut q) of :494                */
 #define RLR_WANT_TIMINGS        0x2u  /* record CUDA events; read with rlr_last_timings    */
+#define RLR_SEARCH_F16          0x4u  /* scan + MMR on the binary16 copy (implied for F16_ONLY
+                                         stores).  Rows are rounded to binary16 once (round to
+                                         nearest even) and widened exactly; all arithmetic stays
+                                         the reference's sequential f32, so results are bit-identical
+                                         to the reference run on the rounded rows.  Measured
+                                         deviation from the f32 store: DESIGN.md "f16 store".   */
 
 /* synthetic fill kinds (bench / parity inputs) */
 #define RLR_SYNTH_IID           0
@@ -282,6 +289,9 @@ int rlr_mmr_store_async(rlr_ctx *c, const void *d_cands, const void *d_n, uint32
 int rlr_search_mmr_async(rlr_ctx *c, const void *d_query, uint32_t top_k, float diversity_factor,
                          float w_embed, float w_lex,
                          void *d_result, void *d_result_n, void *stream);
+
+/* search flags (RLR_SEARCH_F16) used by the device-level entry points of this ctx */
+int rlr_ctx_set_flags(rlr_ctx *c, uint32_t search_flags);
 
 /* launches enqueued by this ctx since creation (bench `gpu_launches`) */
 int rlr_ctx_launch_count(const rlr_ctx *c, uint64_t *out);

@@ -20,8 +20,10 @@ RLR_MAX_M = 1024
 RLR_MAX_DIM = 4096
 RLR_STORE_KEEP_F16 = 0x1
 RLR_STORE_CHECK_FINITE = 0x2
+RLR_STORE_F16_ONLY = 0x4
 RLR_QUERY_PRENORMALIZED = 0x1
 RLR_WANT_TIMINGS = 0x2
+RLR_SEARCH_F16 = 0x4
 RLR_SYNTH_IID = 0
 RLR_SYNTH_CLUSTERED = 1
 
@@ -93,6 +95,7 @@ PROTOTYPES = {
     "rlr_mmr_async": (_int, [_vp, _vp, _u32, _u32, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp, _vp]),
     "rlr_mmr_store_async": (_int, [_vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp, _vp]),
     "rlr_search_mmr_async": (_int, [_vp, _vp, _u32, _f32, _f32, _f32, _vp, _vp, _vp]),
+    "rlr_ctx_set_flags": (_int, [_vp, _u32]),
     "rlr_ctx_launch_count": (_int, [_vp, C.POINTER(_u64)]),
     "rlr_time_scan": (_int, [_vp, _vp, _u32, _u32, _vp, _pf]),
 }

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -125,9 +126,12 @@ struct rlr_store {
     int device = 0;
     uint32_t dim = 0, pitch = 0, flags = 0;
     uint64_t n_rows = 0, row_base = 0;
-    float *d_rows = nullptr;
-    CUtensorMap tmap;
+    float *d_rows = nullptr;        // f32 matrix (absent for RLR_STORE_F16_ONLY)
+    void *d_rows16 = nullptr;       // binary16 copy (RLR_STORE_KEEP_F16 / RLR_STORE_F16_ONLY)
+    uint32_t pitch16 = 0;           // elements per binary16 row (dim rounded up to 64)
+    CUtensorMap tmap, tmap16;
     int sm_count = 0, smem_optin = 0;
+    bool use_half(uint32_t flags) const { return d_rows == nullptr || ((flags & RLR_SEARCH_F16) && d_rows16 != nullptr); }
     std::mutex mu;
     std::vector<rlr_ctx *> free_ctx;
 };
@@ -162,6 +166,7 @@ struct rlr_ctx {
     float *h_rel = nullptr;
     uint64_t launches = 0;
     uint32_t n_lists_cap = 0;
+    uint32_t search_flags = 0;      // RLR_SEARCH_F16 for the device-level entry points
 };
 
 namespace {
@@ -274,7 +279,7 @@ int stage_query(rlr_ctx *c, const float *query, uint32_t dim, uint32_t flags, cu
     for (uint32_t i = 0; i < dim; ++i)
         if (!std::isfinite(c->h_query[i])) return fail(RLR_ERR_NONFINITE, "query[%u] is not finite", i);
     if (!(flags & RLR_QUERY_PRENORMALIZED)) host_normalize(c->h_query, dim);
-    const size_t n = s->pitch + rlr::kChunkFloats * rlr::kScanChunks;
+    const size_t n = ((s->dim + 63u) & ~63u) + 128;   // covers the last (zero) stage of either store copy
     CU_TRY(cudaMemcpyAsync(c->d_query, c->h_query, n * sizeof(float), cudaMemcpyHostToDevice, st));
     return RLR_OK;
 }
@@ -318,17 +323,17 @@ int stage_lex(rlr_ctx *c, const uint32_t *lex_rows, const float *lex_scores, uin
 // scan + merge on `st`: best m records of this store -> d_out / d_out_n
 int enqueue_topm(rlr_ctx *c, const float *d_query, float w_e, float w_l, const uint32_t *d_lex_rows,
                  const float *d_lex_norm, uint32_t n_lex, uint32_t m, rlr_cand *d_out, uint32_t *d_out_n,
-                 cudaStream_t st, cudaEvent_t ev_after_scan)
+                 cudaStream_t st, cudaEvent_t ev_after_scan, bool half)
 {
     rlr_store *s = c->s;
     rlr::ScanArgs a;
     memset(&a, 0, sizeof a);
-    rlr::scan_plan(s->sm_count, s->smem_optin, static_cast<uint32_t>(s->n_rows), s->pitch, &a);
-    a.tmap = &s->tmap;
+    rlr::scan_plan(s->sm_count, s->smem_optin, static_cast<uint32_t>(s->n_rows), half ? s->pitch16 : s->pitch, half, &a);
+    a.tmap = half ? &s->tmap16 : &s->tmap;
     a.d_query = d_query;
     a.n_rows = static_cast<uint32_t>(s->n_rows);
     a.row_base = static_cast<uint32_t>(s->row_base);
-    a.pitch = s->pitch;
+    a.pitch = half ? s->pitch16 : s->pitch;
     a.w_embed = w_e; a.w_lex = w_l;
     a.d_lex_rows = d_lex_rows; a.d_lex_norm = d_lex_norm; a.n_lex = n_lex;
     a.m = m;
@@ -452,6 +457,26 @@ RLR_EXPORT int rlr_resolve_weights(const rlr_query_weights *o, rlr_resolved_weig
 // ---------------------------------------------------------------------------------
 // store
 // ---------------------------------------------------------------------------------
+namespace {
+
+int make_tmap(CUtensorMap *map, void *base, bool half, uint32_t pitch_elems, uint64_t n_rows)
+{
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return fail(RLR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    const uint32_t esz = half ? 2 : 4;
+    const cuuint64_t gdim[2] = {pitch_elems, n_rows};
+    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(pitch_elems) * esz};
+    const cuuint32_t box[2] = {128u / esz, rlr::kScanRows};   // 128-byte box rows: the SWIZZLE_128B span
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RLR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    return RLR_OK;
+}
+
+} // namespace
+
 RLR_EXPORT int rlr_store_create(int device, uint32_t dim, uint64_t n_rows, const float *rows, uint64_t host_pitch,
                                 uint64_t row_base, uint32_t flags, rlr_store **out)
 {
@@ -460,7 +485,8 @@ RLR_EXPORT int rlr_store_create(int device, uint32_t dim, uint64_t n_rows, const
     if (dim == 0 || dim > RLR_MAX_DIM) return fail(RLR_ERR_INVALID_ARG, "dim %u not in 1..%d", dim, RLR_MAX_DIM);
     if (n_rows >= (1ull << 31)) return fail(RLR_ERR_UNSUPPORTED, "n_rows %llu >= 2^31 per store", (unsigned long long)n_rows);
     if (row_base + n_rows >= (1ull << 32)) return fail(RLR_ERR_UNSUPPORTED, "global rows must fit 32 bits");
-    if (flags & RLR_STORE_KEEP_F16) return fail(RLR_ERR_UNSUPPORTED, "f16 store copy is not built yet");
+    if ((flags & RLR_STORE_KEEP_F16) && (flags & RLR_STORE_F16_ONLY))
+        return fail(RLR_ERR_INVALID_ARG, "RLR_STORE_KEEP_F16 and RLR_STORE_F16_ONLY are exclusive");
     if (host_pitch == 0) host_pitch = dim;
     if (host_pitch < dim) return fail(RLR_ERR_INVALID_ARG, "host_pitch %llu < dim %u", (unsigned long long)host_pitch, dim);
     int rc = ensure_device(device);
@@ -470,6 +496,7 @@ RLR_EXPORT int rlr_store_create(int device, uint32_t dim, uint64_t n_rows, const
     s->device = device;
     s->dim = dim;
     s->pitch = (dim + 31u) & ~31u;
+    s->pitch16 = (dim + 63u) & ~63u;
     s->n_rows = n_rows;
     s->row_base = row_base;
     s->flags = flags;
@@ -479,28 +506,24 @@ RLR_EXPORT int rlr_store_create(int device, uint32_t dim, uint64_t n_rows, const
         s->smem_optin = g_dev[device].smem_optin;
     }
     memset(&s->tmap, 0, sizeof s->tmap);
+    memset(&s->tmap16, 0, sizeof s->tmap16);
+    const bool want32 = !(flags & RLR_STORE_F16_ONLY);
+    const bool want16 = flags & (RLR_STORE_F16_ONLY | RLR_STORE_KEEP_F16);
     if (n_rows) {
-        const size_t bytes = static_cast<size_t>(n_rows) * s->pitch * sizeof(float);
-        cudaError_t e = cudaMalloc(&s->d_rows, bytes);
+        cudaError_t e = cudaSuccess;
+        size_t bytes = 0;
+        if (want32) { bytes = static_cast<size_t>(n_rows) * s->pitch * sizeof(float); e = cudaMalloc(&s->d_rows, bytes); }
+        if (e == cudaSuccess && want16) { bytes = static_cast<size_t>(n_rows) * s->pitch16 * 2; e = cudaMalloc(&s->d_rows16, bytes); }
         if (e != cudaSuccess) {
             cudaGetLastError();
+            cudaFree(s->d_rows); cudaFree(s->d_rows16);
             delete s;
             return fail(RLR_ERR_OOM, "cudaMalloc of %zu bytes for the store failed: %s", bytes, cudaGetErrorString(e));
         }
-        PFN_encodeTiled enc = get_encode();
-        if (!enc) { cudaFree(s->d_rows); delete s; return fail(RLR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found"); }
-        const cuuint64_t gdim[2] = {s->pitch, n_rows};
-        const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(s->pitch) * sizeof(float)};
-        const cuuint32_t box[2] = {rlr::kChunkFloats, rlr::kScanRows};
-        const cuuint32_t estr[2] = {1, 1};
-        CUresult r = enc(&s->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, s->d_rows, gdim, gstride, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            cudaFree(s->d_rows);
-            delete s;
-            return fail(RLR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
-        }
+        rc = RLR_OK;
+        if (want32) rc = make_tmap(&s->tmap, s->d_rows, false, s->pitch, n_rows);
+        if (rc == RLR_OK && want16) rc = make_tmap(&s->tmap16, s->d_rows16, true, s->pitch16, n_rows);
+        if (rc != RLR_OK) { cudaFree(s->d_rows); cudaFree(s->d_rows16); delete s; return rc; }
     }
     *out = s;
     if (rows && n_rows) {
@@ -516,6 +539,7 @@ RLR_EXPORT int rlr_store_destroy(rlr_store *s)
     cudaSetDevice(s->device);
     for (rlr_ctx *c : s->free_ctx) ctx_free(c);
     cudaFree(s->d_rows);
+    cudaFree(s->d_rows16);
     cudaGetLastError();
     delete s;
     return RLR_OK;
@@ -527,7 +551,7 @@ RLR_EXPORT int rlr_store_info_get(const rlr_store *s, rlr_store_info *out)
     if (!out) return fail(RLR_ERR_INVALID_ARG, "out is NULL");
     out->n_rows = s->n_rows; out->row_base = s->row_base; out->dim = s->dim; out->pitch = s->pitch;
     out->device = s->device; out->flags = s->flags;
-    out->bytes_device = s->n_rows * s->pitch * sizeof(float);
+    out->bytes_device = (s->d_rows ? s->n_rows * s->pitch * sizeof(float) : 0) + (s->d_rows16 ? s->n_rows * s->pitch16 * 2 : 0);
     return RLR_OK;
 }
 
@@ -540,26 +564,40 @@ RLR_EXPORT int rlr_store_upload(rlr_store *s, uint64_t row0, uint64_t n, const f
     if (host_pitch < s->dim) return fail(RLR_ERR_INVALID_ARG, "host_pitch < dim");
     if (n == 0) return RLR_OK;
     CU_TRY(cudaSetDevice(s->device));
-    float *dst = s->d_rows + row0 * s->pitch;
-    if (s->pitch != s->dim) CU_TRY(cudaMemset(dst, 0, n * s->pitch * sizeof(float)));
-    // cudaMemcpy2D is limited to 2^31-ish heights on some drivers: go in slabs
-    const uint64_t slab = 1u << 20;
-    for (uint64_t r = 0; r < n; r += slab) {
+    // slabs: cudaMemcpy2D heights stay small, and an f16-only store needs only a slab of f32 staging
+    const uint64_t slab = 1u << 18;
+    float *d_stage = nullptr;
+    if (!s->d_rows) CU_TRY(cudaMalloc(&d_stage, std::min(slab, n) * s->pitch * sizeof(float)));
+    int rc = RLR_OK;
+    for (uint64_t r = 0; r < n && rc == RLR_OK; r += slab) {
         const uint64_t cnt = std::min(slab, n - r);
-        CU_TRY(cudaMemcpy2D(dst + r * s->pitch, s->pitch * sizeof(float), rows + r * host_pitch, host_pitch * sizeof(float),
-                            s->dim * sizeof(float), cnt, cudaMemcpyHostToDevice));
+        float *dst32 = s->d_rows ? s->d_rows + (row0 + r) * s->pitch : d_stage;
+        cudaError_t e = cudaSuccess;
+        if (s->pitch != s->dim) e = cudaMemset(dst32, 0, cnt * s->pitch * sizeof(float));
+        if (e == cudaSuccess)
+            e = cudaMemcpy2D(dst32, s->pitch * sizeof(float), rows + r * host_pitch, host_pitch * sizeof(float),
+                             s->dim * sizeof(float), cnt, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && (s->flags & RLR_STORE_CHECK_FINITE)) {
+            uint32_t *d_flag = nullptr, h_flag = 0;
+            e = cudaMalloc(&d_flag, sizeof(uint32_t));
+            if (e == cudaSuccess) e = cudaMemset(d_flag, 0, sizeof(uint32_t));
+            if (e == cudaSuccess) e = rlr::finite_check_launch(dst32, cnt * s->pitch, d_flag, 0);
+            if (e == cudaSuccess) e = cudaMemcpy(&h_flag, d_flag, sizeof h_flag, cudaMemcpyDeviceToHost);
+            cudaFree(d_flag);
+            if (e == cudaSuccess && h_flag) rc = fail(RLR_ERR_NONFINITE, "uploaded rows contain NaN/Inf");
+        }
+        if (e == cudaSuccess && rc == RLR_OK && s->d_rows16) {
+            e = rlr::to_half_launch(dst32, s->pitch, static_cast<__half *>(s->d_rows16) + (row0 + r) * s->pitch16, s->pitch16,
+                                    s->dim, cnt, 0);
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            rc = fail(e == cudaErrorMemoryAllocation ? RLR_ERR_OOM : RLR_ERR_CUDA, "store upload failed: %s", cudaGetErrorString(e));
+        }
     }
-    if (s->flags & RLR_STORE_CHECK_FINITE) {
-        uint32_t *d_flag = nullptr, h_flag = 0;
-        CU_TRY(cudaMalloc(&d_flag, sizeof(uint32_t)));
-        cudaMemset(d_flag, 0, sizeof(uint32_t));
-        cudaError_t e = rlr::finite_check_launch(dst, n * s->pitch, d_flag, 0);
-        if (e == cudaSuccess) e = cudaMemcpy(&h_flag, d_flag, sizeof h_flag, cudaMemcpyDeviceToHost);
-        cudaFree(d_flag);
-        CU_TRY(e);
-        if (h_flag) return fail(RLR_ERR_NONFINITE, "uploaded rows contain NaN/Inf");
-    }
-    return RLR_OK;
+    cudaFree(d_stage);
+    return rc;
 }
 
 RLR_EXPORT int rlr_store_read_rows(const rlr_store *s, const uint32_t *rows, uint64_t n, float *out)
@@ -567,10 +605,16 @@ RLR_EXPORT int rlr_store_read_rows(const rlr_store *s, const uint32_t *rows, uin
     if (int rc = check_store(s)) return rc;
     if ((!rows || !out) && n) return fail(RLR_ERR_INVALID_ARG, "rows/out is NULL");
     CU_TRY(cudaSetDevice(s->device));
+    std::vector<__half> tmp(s->d_rows ? 0 : s->dim);
     for (uint64_t i = 0; i < n; ++i) {
         const uint64_t g = rows[i];
         if (g < s->row_base || g - s->row_base >= s->n_rows) return fail(RLR_ERR_INVALID_ARG, "row %llu not in this store", (unsigned long long)g);
-        CU_TRY(cudaMemcpy(out + i * s->dim, s->d_rows + (g - s->row_base) * s->pitch, s->dim * sizeof(float), cudaMemcpyDeviceToHost));
+        if (s->d_rows) {
+            CU_TRY(cudaMemcpy(out + i * s->dim, s->d_rows + (g - s->row_base) * s->pitch, s->dim * sizeof(float), cudaMemcpyDeviceToHost));
+        } else {   // f16-only store: widen on the host (exact)
+            CU_TRY(cudaMemcpy(tmp.data(), static_cast<const __half *>(s->d_rows16) + (g - s->row_base) * s->pitch16, s->dim * 2, cudaMemcpyDeviceToHost));
+            for (uint32_t c = 0; c < s->dim; ++c) out[i * s->dim + c] = __half2float(tmp[c]);
+        }
     }
     return RLR_OK;
 }
@@ -582,8 +626,8 @@ RLR_EXPORT int rlr_store_fill_synthetic(rlr_store *s, int kind, uint64_t seed, u
     if (kind != RLR_SYNTH_IID && kind != RLR_SYNTH_CLUSTERED) return fail(RLR_ERR_INVALID_ARG, "unknown synthetic kind %d", kind);
     if (kind == RLR_SYNTH_CLUSTERED && n_clusters == 0) return fail(RLR_ERR_INVALID_ARG, "n_clusters must be > 0");
     CU_TRY(cudaSetDevice(s->device));
-    CU_TRY(rlr::synth_launch(s->d_rows, s->pitch, s->dim, s->row_base, static_cast<uint32_t>(s->n_rows), kind, seed,
-                             centroid_seed, n_clusters, sigma, 0));
+    CU_TRY(rlr::synth_launch(s->d_rows, s->pitch, s->d_rows16, s->pitch16, s->dim, s->row_base,
+                             static_cast<uint32_t>(s->n_rows), kind, seed, centroid_seed, n_clusters, sigma, 0));
     CU_TRY(cudaDeviceSynchronize());
     return RLR_OK;
 }
@@ -616,6 +660,8 @@ RLR_EXPORT int rlr_search_topm(rlr_store *s, const float *query, uint32_t dim, u
     if (!w) return fail(RLR_ERR_INVALID_ARG, "weights is NULL");
     if (m == 0 || m > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "m %u not in 1..%d", m, RLR_MAX_M);
     *out_n = 0;
+    if ((flags & RLR_SEARCH_F16) && s->d_rows16 == nullptr && s->n_rows)
+        return fail(RLR_ERR_INVALID_ARG, "RLR_SEARCH_F16 but the store holds no f16 copy");
     if (int rc = ensure_device(s->device)) return rc;
     if (s->n_rows == 0) return RLR_OK; // :476-478
     CtxLease lease(s);
@@ -630,7 +676,7 @@ RLR_EXPORT int rlr_search_topm(rlr_store *s, const float *query, uint32_t dim, u
     const bool timed = flags & RLR_WANT_TIMINGS;
     if (timed) CU_TRY(cudaEventRecord(c->ev[0], st));
     if (int rc = enqueue_topm(c, c->d_query, w->embedding, w->lexical, c->d_lex_rows, c->d_lex_norm, nl, m_eff,
-                              c->d_pool, c->d_pool_n, st, timed ? c->ev[1] : nullptr))
+                              c->d_pool, c->d_pool_n, st, timed ? c->ev[1] : nullptr, s->use_half(flags)))
         return rc;
     if (timed) CU_TRY(cudaEventRecord(c->ev[2], st));
     CU_TRY(cudaMemcpyAsync(c->h_result, c->d_pool, m_eff * sizeof(rlr_cand), cudaMemcpyDeviceToHost, st));
@@ -683,7 +729,8 @@ RLR_EXPORT int rlr_mmr(rlr_store *s, const uint32_t *cand_rows, const float *rel
     if (timed) CU_TRY(cudaEventRecord(c->ev[2], st));
     rlr::MmrArgs a;
     memset(&a, 0, sizeof a);
-    a.d_emb = s->d_rows; a.pitch = s->pitch; a.dim = s->dim;
+    a.half = s->use_half(flags);
+    a.d_emb = a.half ? s->d_rows16 : static_cast<const void *>(s->d_rows); a.pitch = a.half ? s->pitch16 : s->pitch; a.dim = s->dim;
     a.d_cands = nullptr; a.d_n = c->d_p_in; a.d_rows = c->d_rows_in; a.d_rel = c->d_rel_in;
     a.row_base = static_cast<uint32_t>(s->row_base); a.use_rows = 1;
     a.p_cap = p; a.top_k = top_k; a.lambda = lambda;
@@ -743,13 +790,15 @@ RLR_EXPORT int rlr_search_mmr(rlr_store *s, const float *query, uint32_t dim, ui
     const uint32_t p = static_cast<uint32_t>(std::min<uint64_t>(pool, s->n_rows));
     const bool timed = flags & RLR_WANT_TIMINGS;
     if (timed) CU_TRY(cudaEventRecord(c->ev[0], st));
+    const bool half = s->use_half(flags);
     if (int rc = enqueue_topm(c, c->d_query, w->embedding, w->lexical, c->d_lex_rows, c->d_lex_norm, nl, p, c->d_pool,
-                              c->d_pool_n, st, timed ? c->ev[1] : nullptr))
+                              c->d_pool_n, st, timed ? c->ev[1] : nullptr, half))
         return rc;
     if (timed) CU_TRY(cudaEventRecord(c->ev[2], st));
     rlr::MmrArgs a;
     memset(&a, 0, sizeof a);
-    a.d_emb = s->d_rows; a.pitch = s->pitch; a.dim = s->dim;
+    a.half = half;
+    a.d_emb = half ? s->d_rows16 : static_cast<const void *>(s->d_rows); a.pitch = half ? s->pitch16 : s->pitch; a.dim = s->dim;
     a.d_cands = c->d_pool; a.d_n = c->d_pool_n; a.d_rows = nullptr; a.d_rel = nullptr;
     a.row_base = static_cast<uint32_t>(s->row_base); a.use_rows = 1;
     a.p_cap = p; a.top_k = top_k; a.lambda = lambda;
@@ -796,6 +845,15 @@ RLR_EXPORT int rlr_ctx_destroy(rlr_ctx *c)
     return RLR_OK;
 }
 
+RLR_EXPORT int rlr_ctx_set_flags(rlr_ctx *c, uint32_t search_flags)
+{
+    if (!c) return fail(RLR_ERR_INVALID_ARG, "ctx is NULL");
+    if ((search_flags & RLR_SEARCH_F16) && c->s->d_rows16 == nullptr)
+        return fail(RLR_ERR_INVALID_ARG, "RLR_SEARCH_F16 but the store holds no f16 copy");
+    c->search_flags = search_flags;
+    return RLR_OK;
+}
+
 RLR_EXPORT int rlr_ctx_launch_count(const rlr_ctx *c, uint64_t *out)
 {
     if (!c || !out) return fail(RLR_ERR_INVALID_ARG, "ctx/out is NULL");
@@ -821,7 +879,7 @@ RLR_EXPORT int rlr_topm_async(rlr_ctx *c, const void *d_query, float w_embed, fl
     const uint32_t m_eff = m;
     return enqueue_topm(c, static_cast<const float *>(d_query), w_embed, w_lex, static_cast<const uint32_t *>(d_lex_rows),
                         static_cast<const float *>(d_lex_norm), n_lex, m_eff, static_cast<rlr_cand *>(d_out),
-                        static_cast<uint32_t *>(d_out_n), st, nullptr);
+                        static_cast<uint32_t *>(d_out_n), st, nullptr, s->use_half(c->search_flags));
 }
 
 RLR_EXPORT int rlr_merge_async(rlr_ctx *c, const void *d_lists, uint32_t n_lists, uint32_t m, void *d_out,
@@ -843,9 +901,11 @@ RLR_EXPORT int rlr_gather_async(rlr_ctx *c, const void *d_cands, const void *d_n
     if (!c || !d_cands || !d_n || !d_out) return fail(RLR_ERR_INVALID_ARG, "NULL argument");
     rlr_store *s = c->s;
     CU_TRY(cudaSetDevice(s->device));
-    CU_TRY(rlr::gather_launch(s->d_rows, s->pitch, static_cast<uint32_t>(s->n_rows), static_cast<uint32_t>(s->row_base),
+    const bool half = s->use_half(c->search_flags);
+    CU_TRY(rlr::gather_launch(half ? s->d_rows16 : static_cast<const void *>(s->d_rows), half, half ? s->pitch16 : s->pitch,
+                              static_cast<uint32_t>(s->n_rows), static_cast<uint32_t>(s->row_base),
                               static_cast<const rlr_cand *>(d_cands), static_cast<const uint32_t *>(d_n), m,
-                              static_cast<float *>(d_out), static_cast<cudaStream_t>(stream)));
+                              static_cast<float *>(d_out), s->pitch, static_cast<cudaStream_t>(stream)));
     ++c->launches;
     return RLR_OK;
 }
@@ -860,7 +920,7 @@ RLR_EXPORT int rlr_mmr_async(rlr_ctx *c, const void *d_emb, uint32_t pitch, uint
     CU_TRY(cudaSetDevice(c->s->device));
     rlr::MmrArgs a;
     memset(&a, 0, sizeof a);
-    a.d_emb = static_cast<const float *>(d_emb); a.pitch = pitch; a.dim = dim;
+    a.d_emb = d_emb; a.half = 0; a.pitch = pitch; a.dim = dim;   // a gathered matrix is always f32
     a.d_cands = static_cast<const rlr_cand *>(d_cands); a.d_n = static_cast<const uint32_t *>(d_n);
     a.use_rows = 0; a.p_cap = p_cap; a.top_k = top_k; a.lambda = lambda;
     a.d_tri = c->d_tri; a.d_sel_pos = static_cast<uint32_t *>(d_sel_pos); a.d_sel_n = static_cast<uint32_t *>(d_sel_n);
@@ -881,7 +941,8 @@ RLR_EXPORT int rlr_mmr_store_async(rlr_ctx *c, const void *d_cands, const void *
     CU_TRY(cudaSetDevice(s->device));
     rlr::MmrArgs a;
     memset(&a, 0, sizeof a);
-    a.d_emb = s->d_rows; a.pitch = s->pitch; a.dim = s->dim;
+    a.half = s->use_half(c->search_flags);
+    a.d_emb = a.half ? s->d_rows16 : static_cast<const void *>(s->d_rows); a.pitch = a.half ? s->pitch16 : s->pitch; a.dim = s->dim;
     a.d_cands = static_cast<const rlr_cand *>(d_cands); a.d_n = static_cast<const uint32_t *>(d_n);
     a.row_base = static_cast<uint32_t>(s->row_base); a.use_rows = 1;
     a.p_cap = p_cap; a.top_k = top_k; a.lambda = lambda;
@@ -909,17 +970,20 @@ RLR_EXPORT int rlr_search_mmr_async(rlr_ctx *c, const void *d_query, uint32_t to
         const uint32_t m = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint32_t>(top_k, 1), s->n_rows));
         if (m > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "top_k too large");
         return enqueue_topm(c, static_cast<const float *>(d_query), w_embed, w_lex, nullptr, nullptr, 0, m,
-                            static_cast<rlr_cand *>(d_result), static_cast<uint32_t *>(d_result_n), st, nullptr);
+                            static_cast<rlr_cand *>(d_result), static_cast<uint32_t *>(d_result_n), st, nullptr,
+                            s->use_half(c->search_flags));
     }
     const uint64_t pool = std::max<uint64_t>(3ull * top_k, static_cast<uint64_t>(top_k) + 10);
     if (pool > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "candidate pool %llu exceeds %d", (unsigned long long)pool, RLR_MAX_M);
     const uint32_t p = static_cast<uint32_t>(std::min<uint64_t>(pool, s->n_rows));
+    const bool half = s->use_half(c->search_flags);
     if (int rc = enqueue_topm(c, static_cast<const float *>(d_query), w_embed, w_lex, nullptr, nullptr, 0, p, c->d_pool,
-                              c->d_pool_n, st, nullptr))
+                              c->d_pool_n, st, nullptr, half))
         return rc;
     rlr::MmrArgs a;
     memset(&a, 0, sizeof a);
-    a.d_emb = s->d_rows; a.pitch = s->pitch; a.dim = s->dim;
+    a.half = half;
+    a.d_emb = half ? s->d_rows16 : static_cast<const void *>(s->d_rows); a.pitch = half ? s->pitch16 : s->pitch; a.dim = s->dim;
     a.d_cands = c->d_pool; a.d_n = c->d_pool_n;
     a.row_base = static_cast<uint32_t>(s->row_base); a.use_rows = 1;
     a.p_cap = p; a.top_k = top_k; a.lambda = lambda;
@@ -943,9 +1007,11 @@ RLR_EXPORT int rlr_time_scan(rlr_ctx *c, const void *d_query, uint32_t m, uint32
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     rlr::ScanArgs a;
     memset(&a, 0, sizeof a);
-    rlr::scan_plan(s->sm_count, s->smem_optin, static_cast<uint32_t>(s->n_rows), s->pitch, &a);
-    a.tmap = &s->tmap; a.d_query = static_cast<const float *>(d_query);
-    a.n_rows = static_cast<uint32_t>(s->n_rows); a.row_base = static_cast<uint32_t>(s->row_base); a.pitch = s->pitch;
+    const bool half = s->use_half(c->search_flags);
+    rlr::scan_plan(s->sm_count, s->smem_optin, static_cast<uint32_t>(s->n_rows), half ? s->pitch16 : s->pitch, half, &a);
+    a.tmap = half ? &s->tmap16 : &s->tmap; a.d_query = static_cast<const float *>(d_query);
+    a.n_rows = static_cast<uint32_t>(s->n_rows); a.row_base = static_cast<uint32_t>(s->row_base);
+    a.pitch = half ? s->pitch16 : s->pitch;
     a.w_embed = 0.7f; a.w_lex = 0.3f; a.m = m; a.d_lists = c->d_lists; a.d_counts = c->d_counts;
     a.d_ticket = c->d_ticket; a.d_pub = c->d_pub; a.d_out = c->d_pool; a.d_out_n = c->d_pool_n;
     CU_TRY(rlr::scan_launch(a, st)); // warm

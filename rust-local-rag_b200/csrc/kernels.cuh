@@ -13,14 +13,15 @@ constexpr int kScanChunks = 2;        // 128-byte column chunks per pipeline sta
 constexpr int kScanThreads = kScanRows + 64;   // 4 consumer warps + TMA producer warp + threshold warp
 constexpr int kTopBuf = 2048;         // per-CTA candidate buffer (entries)
 constexpr int kChunkFloats = 32;      // 128 B : the TMA SWIZZLE_128B span
-constexpr int kQueryCap = RLR_MAX_DIM + kChunkFloats * kScanChunks; // floats, zero padded
+constexpr int kQueryCap = RLR_MAX_DIM + 128; // floats, zero padded (a stage spans <= 128 elements)
 
 struct ScanArgs {
-    const CUtensorMap *tmap;   // host pointer; copied into the kernel's param space
+    const CUtensorMap *tmap;   // host pointer; copied into the kernel's param space (f32 or f16 map)
+    int half;                  // 1: the map describes the binary16 copy of the store
     const float *d_query;      // kQueryCap floats, zero beyond dim
     uint32_t n_rows;
     uint32_t row_base;
-    uint32_t pitch;            // floats, multiple of 32
+    uint32_t pitch;            // elements per stored row: multiple of 32 (f32) / 64 (f16)
     float w_embed, w_lex;
     const uint32_t *d_lex_rows; // sorted ascending, local rows (may be null)
     const float *d_lex_norm;    // lexical_score per entry (already / max_lexical)
@@ -41,7 +42,7 @@ struct ScanArgs {
 };
 
 // Pick grid / stages / smem for a store on a device.
-void scan_plan(int sm_count, int max_smem_optin, uint32_t n_rows, uint32_t pitch, ScanArgs *a);
+void scan_plan(int sm_count, int max_smem_optin, uint32_t n_rows, uint32_t pitch, int half, ScanArgs *a);
 cudaError_t scan_configure(); // one-time cudaFuncSetAttribute
 cudaError_t scan_launch(const ScanArgs &a, cudaStream_t stream);
 
@@ -57,8 +58,9 @@ cudaError_t merge_launch(const rlr_cand *d_lists, uint32_t n_lists, uint32_t m, 
 //                 (key_row(cand.key) - row_base) when use_rows != 0, else i
 //   d_rel       : optional explicit relevance (else decoded from the keys)
 struct MmrArgs {
-    const float *d_emb;
-    uint32_t pitch, dim;
+    const void *d_emb;         // f32 rows, or binary16 rows when half != 0
+    int half;
+    uint32_t pitch, dim;       // pitch in elements
     const rlr_cand *d_cands;
     const uint32_t *d_n;       // number of valid candidates (device)
     const uint32_t *d_rows;    // optional explicit local rows (overrides keys)
@@ -78,17 +80,19 @@ cudaError_t mmr_configure();
 cudaError_t mmr_launch(const MmrArgs &a, cudaStream_t stream, uint32_t *launches);
 
 // gather rows owned by this shard into a dense p x pitch matrix (zeros otherwise)
-cudaError_t gather_launch(const float *d_store, uint32_t pitch, uint32_t n_rows, uint32_t row_base,
+cudaError_t gather_launch(const void *d_store, int half, uint32_t pitch, uint32_t n_rows, uint32_t row_base,
                           const rlr_cand *d_cands, const uint32_t *d_n, uint32_t p_cap, float *d_out,
-                          cudaStream_t stream);
-cudaError_t gather_rows_launch(const float *d_store, uint32_t pitch, const uint32_t *d_rows, uint32_t n,
+                          uint32_t out_pitch, cudaStream_t stream);
+cudaError_t gather_rows_launch(const void *d_store, int half, uint32_t pitch, const uint32_t *d_rows, uint32_t n,
                                float *d_out, uint32_t out_pitch, cudaStream_t stream);
 
-// synthetic rows + finite check
-cudaError_t synth_launch(float *d_rows, uint32_t pitch, uint32_t dim, uint64_t row_base, uint32_t n_rows,
+// synthetic rows (f32 and/or binary16 output; either pointer may be null) + finite check + f32->f16
+cudaError_t synth_launch(float *d_rows, uint32_t pitch, void *d_rows16, uint32_t pitch16, uint32_t dim, uint64_t row_base, uint32_t n_rows,
                          int kind, uint64_t seed, uint64_t centroid_seed, uint32_t n_clusters, float sigma,
                          cudaStream_t stream);
 cudaError_t finite_check_launch(const float *d_rows, uint64_t n_floats, uint32_t *d_flag, cudaStream_t stream);
+cudaError_t to_half_launch(const float *d_src, uint32_t src_pitch, void *d_dst, uint32_t dst_pitch, uint32_t dim,
+                           uint64_t n_rows, cudaStream_t stream);
 
 // copy a selected subset of records into SoA output arrays (host-facing results)
 cudaError_t unpack_launch(const rlr_cand *d_cands, const uint32_t *d_n, uint32_t cap, uint32_t *d_rows,

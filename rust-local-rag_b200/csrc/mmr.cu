@@ -14,6 +14,8 @@
 // swap_remove bookkeeping (:783,:825) is reproduced with a per-candidate "position in
 // `remaining`" so that exact MMR-score ties resolve to the lowest CURRENT position,
 // exactly what the strict '>' scan at :812 does.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -23,7 +25,6 @@ namespace {
 
 constexpr int T = 16;             // pair tile edge
 constexpr int KC = 768;           // floats of every row staged per pass (whole row for dim <= 768)
-constexpr int PADW = KC + 4;      // +16 B: conflict-free LDS.128 across 8 rows
 
 __device__ __forceinline__ uint32_t cand_row(const rlr_cand *cands, const uint32_t *rows, uint32_t row_base,
                                              int use_rows, uint32_t i)
@@ -38,56 +39,75 @@ __device__ __forceinline__ uint32_t cand_row(const rlr_cand *cands, const uint32
 // single DRAM round trip instead of one per column chunk; then every thread runs its own
 // strictly sequential mul/add chain over the row pair.  Row stride +16 B keeps the LDS.128
 // of eight different rows on eight different bank groups.
+template <bool kHalf>
 __global__ void __launch_bounds__(T * T)
-mmr_pairwise_kernel(const float *__restrict__ emb, uint32_t pitch, const rlr_cand *__restrict__ cands,
+mmr_pairwise_kernel(const void *__restrict__ emb, uint32_t pitch, const rlr_cand *__restrict__ cands,
                     const uint32_t *__restrict__ rows, const uint32_t *__restrict__ d_n, uint32_t row_base,
                     int use_rows, float *__restrict__ tri)
 {
+    constexpr uint32_t ESZ = kHalf ? 2u : 4u;             // bytes per stored element
+    constexpr uint32_t EPV = 16u / ESZ;                   // elements per 16-byte vector
+    constexpr uint32_t ROWB = KC * ESZ + 16u;             // staged row stride in bytes (+16: bank spread)
     const uint32_t bi = blockIdx.x, bj = blockIdx.y;
     if (bi > bj) return;
     const uint32_t p = *d_n;
     if (bi * T >= p || bj * T >= p) return;
 
-    extern __shared__ __align__(16) float pw_smem[];     // [2*T][KC + 4]
-    __shared__ const float *rowptr[2 * T];
+    extern __shared__ __align__(16) uint8_t pw_smem[];    // [2*T][ROWB]
+    __shared__ const uint8_t *rowptr[2 * T];
 
     const uint32_t tid = threadIdx.x;
     if (tid < 2 * T) {
         const uint32_t ci = (tid < T) ? bi * T + tid : bj * T + (tid - T);
-        rowptr[tid] = ci < p ? emb + static_cast<size_t>(cand_row(cands, rows, row_base, use_rows, ci)) * pitch
+        rowptr[tid] = ci < p ? static_cast<const uint8_t *>(emb) +
+                                   static_cast<size_t>(cand_row(cands, rows, row_base, use_rows, ci)) * pitch * ESZ
                              : nullptr;
     }
     __syncthreads();
 
     const uint32_t ti = tid >> 4, tj = tid & 15;
-    const float *a_row = pw_smem + ti * PADW;
-    const float *b_row = pw_smem + (T + tj) * PADW;
+    const uint8_t *a_row = pw_smem + ti * ROWB;
+    const uint8_t *b_row = pw_smem + (T + tj) * ROWB;
     float acc = 0.0f;
     for (uint32_t base = 0; base < pitch; base += KC) {
-        const uint32_t ncols = (pitch - base) < KC ? (pitch - base) : KC;   // multiple of 32
-        const uint32_t n4 = ncols >> 2;
-        for (uint32_t idx = tid; idx < 2 * T * n4; idx += T * T) {
-            const uint32_t r = idx / n4, c4 = idx - r * n4;
-            float *dst = pw_smem + r * PADW + c4 * 4;
-            const float *src = rowptr[r];
+        const uint32_t ncols = (pitch - base) < KC ? (pitch - base) : KC;   // multiple of 32 (f32) / 64 (f16)
+        const uint32_t nv = ncols / EPV;
+        for (uint32_t idx = tid; idx < 2 * T * nv; idx += T * T) {
+            const uint32_t r = idx / nv, cv = idx - r * nv;
+            uint8_t *dst = pw_smem + r * ROWB + cv * 16;
+            const uint8_t *src = rowptr[r];
             if (src != nullptr) {
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src + base + c4 * 4)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)),
+                             "l"(src + static_cast<size_t>(base) * ESZ + cv * 16)
                              : "memory");
             } else {
-                *reinterpret_cast<float4 *>(dst) = make_float4(0, 0, 0, 0);
+                *reinterpret_cast<uint4 *>(dst) = make_uint4(0, 0, 0, 0);
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
 #pragma unroll 8
-        for (uint32_t d = 0; d < ncols; d += 4) {
-            const float4 a = *reinterpret_cast<const float4 *>(a_row + d);
-            const float4 b = *reinterpret_cast<const float4 *>(b_row + d);
-            acc = add_rn(acc, mul_rn(a.x, b.x));
-            acc = add_rn(acc, mul_rn(a.y, b.y));
-            acc = add_rn(acc, mul_rn(a.z, b.z));
-            acc = add_rn(acc, mul_rn(a.w, b.w));
+        for (uint32_t v = 0; v < nv; ++v) {
+            if constexpr (kHalf) {
+                const uint4 ra = *reinterpret_cast<const uint4 *>(a_row + v * 16);
+                const uint4 rb = *reinterpret_cast<const uint4 *>(b_row + v * 16);
+                const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w}, wb[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&wa[h]));
+                    const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&wb[h]));
+                    acc = add_rn(acc, mul_rn(a.x, b.x));
+                    acc = add_rn(acc, mul_rn(a.y, b.y));
+                }
+            } else {
+                const float4 a = *reinterpret_cast<const float4 *>(a_row + v * 16);
+                const float4 b = *reinterpret_cast<const float4 *>(b_row + v * 16);
+                acc = add_rn(acc, mul_rn(a.x, b.x));
+                acc = add_rn(acc, mul_rn(a.y, b.y));
+                acc = add_rn(acc, mul_rn(a.z, b.z));
+                acc = add_rn(acc, mul_rn(a.w, b.w));
+            }
         }
         __syncthreads();
     }
@@ -249,30 +269,45 @@ mmr_greedy_kernel(const float *__restrict__ tri_g, const rlr_cand *__restrict__ 
     }
 }
 
-__global__ void gather_kernel(const float *__restrict__ store, uint32_t pitch, uint32_t n_rows, uint32_t row_base,
+template <bool kHalf>
+__global__ void gather_kernel(const void *__restrict__ store, uint32_t pitch, uint32_t n_rows, uint32_t row_base,
                               const rlr_cand *__restrict__ cands, const uint32_t *__restrict__ d_n,
-                              float *__restrict__ out)
+                              float *__restrict__ out, uint32_t out_pitch)
 {
     const uint32_t i = blockIdx.x;
     const uint32_t p = *d_n;
-    float4 *o = reinterpret_cast<float4 *>(out + static_cast<size_t>(i) * pitch);
-    const float4 *src = nullptr;
+    float *o = out + static_cast<size_t>(i) * out_pitch;
+    const void *src = nullptr;
     if (i < p && cands[i].key != 0ull) {
         const uint32_t g = key_row(cands[i].key);
         if (g >= row_base && g - row_base < n_rows)
-            src = reinterpret_cast<const float4 *>(store + static_cast<size_t>(g - row_base) * pitch);
+            src = static_cast<const uint8_t *>(store) + static_cast<size_t>(g - row_base) * pitch * (kHalf ? 2 : 4);
     }
-    for (uint32_t c = threadIdx.x; c < pitch / 4; c += blockDim.x)
-        o[c] = src != nullptr ? __ldg(src + c) : make_float4(0, 0, 0, 0);
+    for (uint32_t c = threadIdx.x; c < out_pitch; c += blockDim.x) {
+        float v = 0.0f;
+        if (src != nullptr && c < pitch) {
+            if constexpr (kHalf) v = __half2float(static_cast<const __half *>(src)[c]);
+            else v = static_cast<const float *>(src)[c];
+        }
+        o[c] = v;
+    }
 }
 
-__global__ void gather_rows_kernel(const float *__restrict__ store, uint32_t pitch, const uint32_t *__restrict__ rows,
+template <bool kHalf>
+__global__ void gather_rows_kernel(const void *__restrict__ store, uint32_t pitch, const uint32_t *__restrict__ rows,
                                    float *__restrict__ out, uint32_t out_pitch)
 {
     const uint32_t i = blockIdx.x;
-    const float *src = store + static_cast<size_t>(rows[i]) * pitch;
+    const uint8_t *src = static_cast<const uint8_t *>(store) + static_cast<size_t>(rows[i]) * pitch * (kHalf ? 2 : 4);
     float *o = out + static_cast<size_t>(i) * out_pitch;
-    for (uint32_t c = threadIdx.x; c < out_pitch; c += blockDim.x) o[c] = c < pitch ? src[c] : 0.0f;
+    for (uint32_t c = threadIdx.x; c < out_pitch; c += blockDim.x) {
+        float v = 0.0f;
+        if (c < pitch) {
+            if constexpr (kHalf) v = __half2float(reinterpret_cast<const __half *>(src)[c]);
+            else v = reinterpret_cast<const float *>(src)[c];
+        }
+        o[c] = v;
+    }
 }
 
 } // namespace
@@ -284,8 +319,9 @@ cudaError_t mmr_configure()
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(mmr_pairwise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             2 * T * PADW * static_cast<int>(sizeof(float)));
+    e = cudaFuncSetAttribute(mmr_pairwise_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * T * (KC * 4 + 16));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(mmr_pairwise_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * T * (KC * 2 + 16));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(mmr_greedy_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 4 * 1024);
     if (e != cudaSuccess) return e;
@@ -299,8 +335,12 @@ cudaError_t mmr_launch(const MmrArgs &a, cudaStream_t stream, uint32_t *launches
     if (a.p_cap == 0) return cudaErrorInvalidValue;
     const uint32_t nb = (a.p_cap + T - 1) / T;
     if (a.p_cap > 1) {
-        mmr_pairwise_kernel<<<dim3(nb, nb), T * T, 2 * T * PADW * sizeof(float), stream>>>(
-            a.d_emb, a.pitch, a.d_cands, a.d_rows, a.d_n, a.row_base, a.use_rows, a.d_tri);
+        if (a.half)
+            mmr_pairwise_kernel<true><<<dim3(nb, nb), T * T, 2 * T * (KC * 2 + 16), stream>>>(
+                a.d_emb, a.pitch, a.d_cands, a.d_rows, a.d_n, a.row_base, a.use_rows, a.d_tri);
+        else
+            mmr_pairwise_kernel<false><<<dim3(nb, nb), T * T, 2 * T * (KC * 4 + 16), stream>>>(
+                a.d_emb, a.pitch, a.d_cands, a.d_rows, a.d_n, a.row_base, a.use_rows, a.d_tri);
         if (launches) ++*launches;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -320,20 +360,22 @@ cudaError_t mmr_launch(const MmrArgs &a, cudaStream_t stream, uint32_t *launches
     return cudaGetLastError();
 }
 
-cudaError_t gather_launch(const float *d_store, uint32_t pitch, uint32_t n_rows, uint32_t row_base,
-                          const rlr_cand *d_cands, const uint32_t *d_n, uint32_t p_cap, float *d_out,
+cudaError_t gather_launch(const void *d_store, int half, uint32_t pitch, uint32_t n_rows, uint32_t row_base,
+                          const rlr_cand *d_cands, const uint32_t *d_n, uint32_t p_cap, float *d_out, uint32_t out_pitch,
                           cudaStream_t stream)
 {
     if (p_cap == 0) return cudaSuccess;
-    gather_kernel<<<p_cap, 128, 0, stream>>>(d_store, pitch, n_rows, row_base, d_cands, d_n, d_out);
+    if (half) gather_kernel<true><<<p_cap, 128, 0, stream>>>(d_store, pitch, n_rows, row_base, d_cands, d_n, d_out, out_pitch);
+    else gather_kernel<false><<<p_cap, 128, 0, stream>>>(d_store, pitch, n_rows, row_base, d_cands, d_n, d_out, out_pitch);
     return cudaGetLastError();
 }
 
-cudaError_t gather_rows_launch(const float *d_store, uint32_t pitch, const uint32_t *d_rows, uint32_t n,
+cudaError_t gather_rows_launch(const void *d_store, int half, uint32_t pitch, const uint32_t *d_rows, uint32_t n,
                                float *d_out, uint32_t out_pitch, cudaStream_t stream)
 {
     if (n == 0) return cudaSuccess;
-    gather_rows_kernel<<<n, 128, 0, stream>>>(d_store, pitch, d_rows, d_out, out_pitch);
+    if (half) gather_rows_kernel<true><<<n, 128, 0, stream>>>(d_store, pitch, d_rows, d_out, out_pitch);
+    else gather_rows_kernel<false><<<n, 128, 0, stream>>>(d_store, pitch, d_rows, d_out, out_pitch);
     return cudaGetLastError();
 }
 

@@ -23,6 +23,8 @@
 //     the <=148 lists in place (final_merge), so one launch yields the global top-M.
 #include <cstdlib>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "sort_regs.cuh"
@@ -290,6 +292,10 @@ __device__ __forceinline__ void top_r_update_warp(const uint64_t *keys, uint32_t
     }
 }
 
+// kHalf: the store holds IEEE binary16 rows (64 elements per 128-byte box row).  Elements are
+// widened to f32 (exact) and accumulated in f32 in index order, i.e. the reference arithmetic
+// applied to the f16-rounded store.
+template <bool kHalf>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ g_query,
                  uint32_t n_rows, uint32_t row_base, uint32_t n_chunks, float w_embed, float w_lex,
@@ -304,8 +310,9 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
     const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
     uint8_t *smem = smem_raw + pad;
 
+    constexpr uint32_t EPB = kHalf ? 64u : 32u;        // elements per 128-byte box row
     const uint32_t KB = (n_chunks + CH - 1) / CH;      // pipeline stages consumed per tile
-    const uint32_t q_floats = KB * CH * kChunkFloats;
+    const uint32_t q_floats = KB * CH * EPB;
     const SmemLayout L = smem_layout(n_stages, q_floats);
 
     float *q_s = reinterpret_cast<float *>(smem + L.q_off);
@@ -369,7 +376,7 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
 #pragma unroll
                     for (int c = 0; c < CH; ++c)
                         tma_load_2d(stages_addr + stage * kStageBytes + c * kBoxBytes, &tmap,
-                                    static_cast<int32_t>((kb * CH + c) * kChunkFloats),
+                                    static_cast<int32_t>((kb * CH + c) * EPB),
                                     static_cast<int32_t>(tile * R), full_bar + stage * 8, pol);
                     if (++stage == static_cast<uint32_t>(n_stages)) { stage = 0; phase ^= 1; }
                 }
@@ -414,17 +421,35 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
         for (uint32_t kb = 0; kb < KB; ++kb) {
             if (kb != 0) mbar_wait(full_bar + stage * 8, phase);
             const uint8_t *sp = stage0 + stage * kStageBytes;
-            const float4 *qp = q4 + kb * (CH * 8);
+            const float4 *qp = q4 + kb * (CH * (EPB / 4));
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 v = *reinterpret_cast<const float4 *>(sp + c * kBoxBytes + ((j << 4) ^ xr));
-                    const float4 w = qp[c * 8 + j];
-                    acc = add_rn(acc, mul_rn(w.x, v.x));
-                    acc = add_rn(acc, mul_rn(w.y, v.y));
-                    acc = add_rn(acc, mul_rn(w.z, v.z));
-                    acc = add_rn(acc, mul_rn(w.w, v.w));
+                    const uint8_t *src = sp + c * kBoxBytes + ((j << 4) ^ xr);
+                    if constexpr (kHalf) {
+                        const uint4 raw = *reinterpret_cast<const uint4 *>(src);      // 8 halves
+                        const float4 w0 = qp[c * 16 + j * 2], w1 = qp[c * 16 + j * 2 + 1];
+                        const float2 v0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+                        const float2 v1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+                        const float2 v2 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.z));
+                        const float2 v3 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.w));
+                        acc = add_rn(acc, mul_rn(w0.x, v0.x));
+                        acc = add_rn(acc, mul_rn(w0.y, v0.y));
+                        acc = add_rn(acc, mul_rn(w0.z, v1.x));
+                        acc = add_rn(acc, mul_rn(w0.w, v1.y));
+                        acc = add_rn(acc, mul_rn(w1.x, v2.x));
+                        acc = add_rn(acc, mul_rn(w1.y, v2.y));
+                        acc = add_rn(acc, mul_rn(w1.z, v3.x));
+                        acc = add_rn(acc, mul_rn(w1.w, v3.y));
+                    } else {
+                        const float4 v = *reinterpret_cast<const float4 *>(src);
+                        const float4 w = qp[c * 8 + j];
+                        acc = add_rn(acc, mul_rn(w.x, v.x));
+                        acc = add_rn(acc, mul_rn(w.y, v.y));
+                        acc = add_rn(acc, mul_rn(w.z, v.z));
+                        acc = add_rn(acc, mul_rn(w.w, v.w));
+                    }
                 }
             }
             __syncwarp();
@@ -563,11 +588,13 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
 
 } // namespace
 
-void scan_plan(int sm_count, int max_smem_optin, uint32_t n_rows, uint32_t pitch, ScanArgs *a)
+void scan_plan(int sm_count, int max_smem_optin, uint32_t n_rows, uint32_t pitch, int half, ScanArgs *a)
 {
-    const uint32_t n_chunks = pitch / kChunkFloats;
+    const uint32_t epb = half ? 64u : 32u;
+    const uint32_t n_chunks = pitch / epb;
     const uint32_t KB = (n_chunks + CH - 1) / CH;
-    const uint32_t q_floats = KB * CH * kChunkFloats;
+    const uint32_t q_floats = KB * CH * epb;
+    a->half = half;
     const uint32_t n_tiles = (n_rows + R - 1) / R;
     int grid = sm_count;
     if (static_cast<uint32_t>(grid) > n_tiles) grid = static_cast<int>(n_tiles);
@@ -588,7 +615,9 @@ cudaError_t scan_configure()
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(scan_topm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    e = cudaFuncSetAttribute(scan_topm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(scan_topm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
 }
 
 // candidate-buffer capacity for a given m: room for m kept + a few tiles of new entries
@@ -611,10 +640,17 @@ cudaError_t scan_launch(const ScanArgs &a, cudaStream_t stream)
     const bool no_merge = getenv("RLR_DEBUG_NOMERGE") != nullptr;   // tuning knob: time the scan without final_merge
     uint32_t r_pub = (a.m + a.grid - 1) / a.grid;                    // r-th best published per CTA (0 = off)
     if (r_pub > static_cast<uint32_t>(kTopR) || a.d_pub == nullptr || getenv("RLR_DEBUG_NOGLOBALTAU")) r_pub = 0;
-    scan_topm_kernel<<<a.grid, kScanThreads, a.smem_bytes, stream>>>(
-        *a.tmap, a.d_query, a.n_rows, a.row_base, a.pitch / kChunkFloats, a.w_embed, a.w_lex, a.d_lex_rows,
-        a.d_lex_norm, a.n_lex, a.m, buf_cap, r_pub, a.n_stages, a.d_lists, a.d_counts, a.d_pub, a.d_ticket,
-        a.d_ticket + 1, no_merge ? nullptr : a.d_out, a.d_out_n, a.d_trace);
+    const uint32_t n_chunks = a.pitch / (a.half ? 64u : 32u);
+    if (a.half)
+        scan_topm_kernel<true><<<a.grid, kScanThreads, a.smem_bytes, stream>>>(
+            *a.tmap, a.d_query, a.n_rows, a.row_base, n_chunks, a.w_embed, a.w_lex, a.d_lex_rows, a.d_lex_norm, a.n_lex,
+            a.m, buf_cap, r_pub, a.n_stages, a.d_lists, a.d_counts, a.d_pub, a.d_ticket, a.d_ticket + 1,
+            no_merge ? nullptr : a.d_out, a.d_out_n, a.d_trace);
+    else
+        scan_topm_kernel<false><<<a.grid, kScanThreads, a.smem_bytes, stream>>>(
+            *a.tmap, a.d_query, a.n_rows, a.row_base, n_chunks, a.w_embed, a.w_lex, a.d_lex_rows, a.d_lex_norm, a.n_lex,
+            a.m, buf_cap, r_pub, a.n_stages, a.d_lists, a.d_counts, a.d_pub, a.d_ticket, a.d_ticket + 1,
+            no_merge ? nullptr : a.d_out, a.d_out_n, a.d_trace);
     return cudaGetLastError();
 }
 

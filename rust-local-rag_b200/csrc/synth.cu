@@ -7,6 +7,8 @@
 // /root/reference/src/rag_engine.rs:1763-1771 (sequential sum of squares, sqrt, true
 // division per element), so a device-generated store is bit-identical to one the host
 // would have normalised and uploaded.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -31,8 +33,9 @@ __device__ __forceinline__ float synth_value(int kind, uint64_t seed, uint64_t c
 // One thread per row (sequential arithmetic), 32-column tiles transposed through shared
 // memory so that the global stores are 128-byte coalesced.
 __global__ void __launch_bounds__(kRowsPerBlock)
-synth_kernel(float *__restrict__ out, uint32_t pitch, uint32_t dim, uint64_t row_base, uint32_t n_rows, int kind,
-             uint64_t seed, uint64_t centroid_seed, uint32_t n_clusters, float sigma)
+synth_kernel(float *__restrict__ out, uint32_t pitch, __half *__restrict__ out16, uint32_t pitch16, uint32_t dim,
+             uint64_t row_base, uint32_t n_rows, int kind, uint64_t seed, uint64_t centroid_seed, uint32_t n_clusters,
+             float sigma)
 {
     __shared__ float tile[kRowsPerBlock][33];
     const uint32_t t = threadIdx.x;
@@ -50,7 +53,8 @@ synth_kernel(float *__restrict__ out, uint32_t pitch, uint32_t dim, uint64_t row
     const float norm = __fsqrt_rn(norm_sq); // IEEE round-to-nearest
 
     const uint32_t warp = t >> 5, lane = t & 31;
-    for (uint32_t c0 = 0; c0 < pitch; c0 += 32) {
+    const uint32_t pmax = pitch > pitch16 ? pitch : pitch16;
+    for (uint32_t c0 = 0; c0 < pmax; c0 += 32) {
         if (valid)
             for (uint32_t j = 0; j < 32; ++j) {
                 const uint32_t c = c0 + j;
@@ -65,7 +69,12 @@ synth_kernel(float *__restrict__ out, uint32_t pitch, uint32_t dim, uint64_t row
         // warp w writes its own 32 rows: lane = column
         for (uint32_t r = 0; r < 32; ++r) {
             const uint32_t rl = blockIdx.x * kRowsPerBlock + warp * 32 + r;
-            if (rl < n_rows) out[static_cast<size_t>(rl) * pitch + c0 + lane] = tile[warp * 32 + r][lane];
+            if (rl < n_rows) {
+                const float x = tile[warp * 32 + r][lane];
+                if (out != nullptr && c0 < pitch) out[static_cast<size_t>(rl) * pitch + c0 + lane] = x;
+                if (out16 != nullptr && c0 < pitch16)   // binary16 copy: round to nearest even
+                    out16[static_cast<size_t>(rl) * pitch16 + c0 + lane] = __float2half_rn(x);
+            }
         }
         __syncwarp();
     }
@@ -84,13 +93,35 @@ __global__ void finite_check_kernel(const float4 *__restrict__ v, uint64_t n4, u
 
 } // namespace
 
-cudaError_t synth_launch(float *d_rows, uint32_t pitch, uint32_t dim, uint64_t row_base, uint32_t n_rows, int kind,
-                         uint64_t seed, uint64_t centroid_seed, uint32_t n_clusters, float sigma, cudaStream_t stream)
+cudaError_t synth_launch(float *d_rows, uint32_t pitch, void *d_rows16, uint32_t pitch16, uint32_t dim, uint64_t row_base,
+                         uint32_t n_rows, int kind, uint64_t seed, uint64_t centroid_seed, uint32_t n_clusters,
+                         float sigma, cudaStream_t stream)
 {
     if (n_rows == 0) return cudaSuccess;
     const uint32_t blocks = (n_rows + kRowsPerBlock - 1) / kRowsPerBlock;
-    synth_kernel<<<blocks, kRowsPerBlock, 0, stream>>>(d_rows, pitch, dim, row_base, n_rows, kind, seed, centroid_seed,
-                                                       n_clusters ? n_clusters : 1, sigma);
+    synth_kernel<<<blocks, kRowsPerBlock, 0, stream>>>(d_rows, d_rows ? pitch : 0, static_cast<__half *>(d_rows16),
+                                                       d_rows16 ? pitch16 : 0, dim, row_base, n_rows, kind, seed,
+                                                       centroid_seed, n_clusters ? n_clusters : 1, sigma);
+    return cudaGetLastError();
+}
+
+namespace {
+// f32 rows -> zero-padded binary16 rows (round to nearest even), one warp per row segment
+__global__ void to_half_kernel(const float *__restrict__ src, uint32_t src_pitch, __half *__restrict__ dst,
+                               uint32_t dst_pitch, uint32_t dim, uint64_t n_rows)
+{
+    for (uint64_t r = blockIdx.x; r < n_rows; r += gridDim.x)
+        for (uint32_t c = threadIdx.x; c < dst_pitch; c += blockDim.x)
+            dst[r * dst_pitch + c] = c < dim ? __float2half_rn(src[r * src_pitch + c]) : __float2half_rn(0.0f);
+}
+} // namespace
+
+cudaError_t to_half_launch(const float *d_src, uint32_t src_pitch, void *d_dst, uint32_t dst_pitch, uint32_t dim,
+                           uint64_t n_rows, cudaStream_t stream)
+{
+    if (n_rows == 0) return cudaSuccess;
+    const uint32_t blocks = static_cast<uint32_t>(n_rows < 148 * 32 ? n_rows : 148 * 32);
+    to_half_kernel<<<blocks, 256, 0, stream>>>(d_src, src_pitch, static_cast<__half *>(d_dst), dst_pitch, dim, n_rows);
     return cudaGetLastError();
 }
 

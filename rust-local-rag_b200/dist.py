@@ -134,7 +134,7 @@ class CudaBackend:
     """The product backend: every step is a kernel launch from librlr_b200.so on the
     current torch CUDA stream.  No fallback."""
 
-    def __init__(self, store, device: Optional[torch.device] = None):
+    def __init__(self, store, device: Optional[torch.device] = None, search_flags: int = 0):
         from . import binding as B
         self.B = B
         self.lib = B.load()
@@ -144,6 +144,8 @@ class CudaBackend:
         self.device = device if device is not None else torch.device("cuda", info.device)
         self.ctx = C.c_void_p()
         B.check(self.lib.rlr_ctx_create(store.handle, C.byref(self.ctx)))
+        if search_flags:
+            B.check(self.lib.rlr_ctx_set_flags(self.ctx, search_flags))
 
     def close(self):
         if self.ctx:

@@ -147,8 +147,8 @@ class DeviceStore:
     @classmethod
     def synthetic(cls, n_rows: int, dim: int, kind: int = B.RLR_SYNTH_IID, seed: int = 0x5EED0001,
                   centroid_seed: int = 0x5EED00C0, n_clusters: int = 4096, sigma: float = 0.65,
-                  device: int = 0, row_base: int = 0) -> "DeviceStore":
-        s = cls.empty(n_rows, dim, device=device, row_base=row_base)
+                  device: int = 0, row_base: int = 0, flags: int = 0) -> "DeviceStore":
+        s = cls.empty(n_rows, dim, device=device, row_base=row_base, flags=flags)
         B.check(s._lib.rlr_store_fill_synthetic(s._h, kind, seed, centroid_seed, n_clusters, sigma))
         return s
 

@@ -13,6 +13,9 @@ pub const RLR_ERR_NONFINITE: c_int = 7;
 pub const RLR_MAX_M: u32 = 1024;
 pub const RLR_QUERY_PRENORMALIZED: u32 = 0x1;
 pub const RLR_WANT_TIMINGS: u32 = 0x2;
+pub const RLR_SEARCH_F16: u32 = 0x4;
+pub const RLR_STORE_KEEP_F16: u32 = 0x1;
+pub const RLR_STORE_F16_ONLY: u32 = 0x4;
 
 #[repr(C)] pub struct rlr_store { _p: [u8; 0] }
 #[repr(C)] pub struct rlr_ctx { _p: [u8; 0] }
@@ -56,6 +59,7 @@ extern "C" {
     pub fn rlr_mmr_async(c: *mut rlr_ctx, d_emb: *const c_void, pitch: u32, dim: u32, d_cands: *const c_void, d_n: *const c_void, p_cap: u32, top_k: u32, lambda: f32, d_sel_pos: *mut c_void, d_sel_n: *mut c_void, d_result: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn rlr_mmr_store_async(c: *mut rlr_ctx, d_cands: *const c_void, d_n: *const c_void, p_cap: u32, top_k: u32, lambda: f32, d_sel_pos: *mut c_void, d_sel_n: *mut c_void, d_result: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn rlr_search_mmr_async(c: *mut rlr_ctx, d_query: *const c_void, top_k: u32, diversity_factor: f32, w_embed: f32, w_lex: f32, d_result: *mut c_void, d_result_n: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn rlr_ctx_set_flags(c: *mut rlr_ctx, search_flags: u32) -> c_int;
     pub fn rlr_ctx_launch_count(c: *const rlr_ctx, out: *mut u64) -> c_int;
     pub fn rlr_time_scan(c: *mut rlr_ctx, d_query: *const c_void, m: u32, iters: u32, stream: *mut c_void, out_ms_per_launch: *mut f32) -> c_int;
 }

@@ -379,3 +379,66 @@ def test_merge_async_matches_numpy(eng, rlr, n_lists, m, fill):
     assert (got["key"][len(ref):] == 0).all()
     lib.rlr_ctx_destroy(ctx)
     s.close()
+
+
+# ------------------------------------------------------------------ binary16 store copy (BASELINE config 5)
+def _round16(rows):
+    return rows.astype(np.float16).astype(F32)
+
+
+@pytest.mark.parametrize("n,dim,m", [(5000, 768, 300), (20000, 100, 45), (3000, 64, 900), (129, 3, 10), (40000, 1024, 300)])
+def test_f16_only_store_is_exact_on_rounded_rows(eng, rlr, orc, n, dim, m):
+    """An f16 store is 'the reference run on the binary16-rounded embeddings': rows are rounded once
+    (RN-even), widened exactly, and every sum is still the sequential f32 one -> bit-identical."""
+    rng = np.random.default_rng(n + dim)
+    rows = orc.normalize_rows(rng.standard_normal((n, dim)).astype(F32))
+    r16 = _round16(rows)
+    q = rng.standard_normal(dim).astype(F32)
+    s = eng.DeviceStore.from_rows(rows, flags=rlr.RLR_STORE_F16_ONLY)
+    assert same(s.read_rows(np.arange(min(n, 50))), r16[:50])
+    for a, b in zip(s.search_topm(q, m, W()), orc.search(r16, q, m, full_sort=n <= 5000, threads=4)):
+        assert same(a, b)
+    for (k, lam) in ((5, 0.3), (100, 0.7)):
+        for a, b in zip(s.search_mmr(q, k, lam, W()), orc.search_with_diversity(r16, q, k, lam, threads=4)):
+            assert same(a, b)
+    s.close()
+
+
+def test_keep_f16_store_serves_both_precisions_and_states_tolerance(eng, rlr, orc):
+    n, dim = 200_000, 768
+    rows = orc.synth_rows(n, dim, kind=1, n_clusters=256)
+    r16 = _round16(rows)
+    s = eng.DeviceStore.from_rows(rows, flags=rlr.RLR_STORE_KEEP_F16)
+    q = orc.synth_rows(1, dim, kind=1, seed=0x5EED0002, n_clusters=256)[0]
+    f32 = s.search_topm(q, 300, W())
+    f16 = s.search_topm(q, 300, W(), flags=rlr.RLR_SEARCH_F16)
+    for a, b in zip(f32, orc.search(rows, q, 300, threads=4)):
+        assert same(a, b)
+    for a, b in zip(f16, orc.search(r16, q, 300, threads=4)):
+        assert same(a, b)
+    mm16 = s.search_mmr(q, 100, 0.7, W(), flags=rlr.RLR_SEARCH_F16)
+    for a, b in zip(mm16, orc.search_with_diversity(r16, q, 100, 0.7, threads=4)):
+        assert same(a, b)
+    # STATED f16 tolerance vs the f32 store (unit vectors, dim 768): every score of a common row within
+    # 2e-4 absolute (binary16 has 11 significant bits: |dx| <= 2^-11 |x| per element, errors average out
+    # over 768 terms), and the top-300 sets overlap >= 95 %.
+    common = set(f32[0].tolist()) & set(f16[0].tolist())
+    assert len(common) >= 285
+    e32 = dict(zip(f32[0].tolist(), f32[2].tolist())); e16 = dict(zip(f16[0].tolist(), f16[2].tolist()))
+    dev = max(abs(e32[r] - e16[r]) for r in common)
+    assert dev < 2e-4, dev
+    s.close()
+    with pytest.raises(rlr.RlrError):
+        s2 = eng.DeviceStore.from_rows(rows[:100])
+        try:
+            s2.search_topm(q, 5, W(), flags=rlr.RLR_SEARCH_F16)      # no f16 copy in this store
+        finally:
+            s2.close()
+
+
+def test_f16_synthetic_store_matches_rounded_cpu_rows(eng, rlr, orc):
+    n, dim = 3000, 768
+    s = eng.DeviceStore.synthetic(n, dim, kind=1, n_clusters=64, flags=rlr.RLR_STORE_F16_ONLY, row_base=500)
+    ref = _round16(orc.synth_rows(n, dim, kind=1, n_clusters=64, row0=500))
+    assert same(s.read_rows(np.arange(500, 500 + n)), ref)
+    s.close()
