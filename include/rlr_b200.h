@@ -229,6 +229,28 @@ int rlr_embedding_candidates(rlr_store *s, const float *query, uint32_t dim, uin
                              uint32_t count, uint32_t *out_rows, float *out_score,
                              uint32_t *out_n);
 
+/*
+ * rlr_search_batch -- many queries at once (not in the reference, which answers one query
+ * per call; BASELINE config 4 / north_star kernel (3)).  For each of n_queries embeddings:
+ * the top m rows by embedding score (the ordering of get_embedding_candidates, :445), computed
+ * as ONE dense contraction on the tensor cores: tcgen05.mma over the binary16 copy of the
+ * store (needs RLR_STORE_KEEP_F16 or RLR_STORE_F16_ONLY), f32 accumulation in TMEM, a
+ * per-query threshold filter fused into the epilogue.
+ *   queries     n_queries x dim f32, row stride dim; normalised here (:494) unless
+ *               RLR_QUERY_PRENORMALIZED; rounded to binary16 for the contraction
+ *   m           1..RLR_MAX_M
+ *   flags       RLR_BATCH_EXACT_RESCORE: re-score the m shortlisted rows of every query with the
+ *               reference's sequential f32 arithmetic (on the f32 rows when the store has them)
+ *               and order by that; out_scores are then bit-identical to the single-query path.
+ *               Without it out_scores are the tensor-core values (<= ~2e-4 absolute from exact
+ *               on unit vectors) and the order is by those.
+ * Outputs: out_rows / out_scores are n_queries x m (row stride m), out_n[q] = min(m, n_rows).
+ */
+#define RLR_BATCH_EXACT_RESCORE 0x8u
+int rlr_search_batch(rlr_store *s, const float *queries, uint32_t n_queries, uint32_t dim,
+                     uint32_t flags, uint32_t m,
+                     uint32_t *out_rows, float *out_scores, uint32_t *out_n);
+
 /* stage timings of the calling thread's most recent call made with RLR_WANT_TIMINGS */
 int rlr_last_timings(rlr_timings *out);
 

@@ -24,6 +24,7 @@ RLR_STORE_F16_ONLY = 0x4
 RLR_QUERY_PRENORMALIZED = 0x1
 RLR_WANT_TIMINGS = 0x2
 RLR_SEARCH_F16 = 0x4
+RLR_BATCH_EXACT_RESCORE = 0x8
 RLR_SYNTH_IID = 0
 RLR_SYNTH_CLUSTERED = 1
 
@@ -86,6 +87,7 @@ PROTOTYPES = {
     "rlr_search_mmr": (_int, [_vp, _vp, _u32, _u32, _u32, _f32, C.POINTER(ResolvedWeightsC), _vp, _vp, _u32,
                               _vp, _vp, _vp, _vp, _pu32]),
     "rlr_embedding_candidates": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _pu32]),
+    "rlr_search_batch": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp]),
     "rlr_last_timings": (_int, [C.POINTER(TimingsC)]),
     "rlr_ctx_create": (_int, [_vp, C.POINTER(_vp)]),
     "rlr_ctx_destroy": (_int, [_vp]),

@@ -819,6 +819,173 @@ RLR_EXPORT int rlr_search_mmr(rlr_store *s, const float *query, uint32_t dim, ui
     return RLR_OK;
 }
 
+// ---------------------------------------------------------------------------------
+// batched queries on the tensor cores
+// ---------------------------------------------------------------------------------
+namespace {
+
+struct BatchBufs {
+    float *d_q32 = nullptr;
+    void *d_q16 = nullptr;
+    float *d_tau = nullptr;
+    unsigned long long *d_state = nullptr, *d_app = nullptr;
+    uint32_t *d_state_cnt = nullptr, *d_app_cnt = nullptr, *d_overflow = nullptr;
+    ~BatchBufs()
+    {
+        cudaFree(d_q32); cudaFree(d_q16); cudaFree(d_tau); cudaFree(d_state); cudaFree(d_app);
+        cudaFree(d_state_cnt); cudaFree(d_app_cnt); cudaFree(d_overflow);
+        cudaGetLastError();
+    }
+};
+
+constexpr uint32_t kBatchCap = 1024;      // appended candidates per query per phase
+constexpr uint32_t kBatchQTile = 256;     // queries per MMA tile (UMMA N)
+constexpr uint32_t kBatchRTile = 128;     // store rows per MMA tile (UMMA M)
+
+// GEMM + prune over row tiles [t0, t1); on candidate-list overflow the phase is split and retried
+// (the running top-m is only modified by the prune, so a failed GEMM pass leaves it intact).
+int batch_phase(rlr_store *s, const CUtensorMap *tmapQ, BatchBufs &b, uint32_t nq, uint32_t nq_pad, uint32_t m,
+                uint32_t t0, uint32_t t1, cudaStream_t st, uint32_t *launches)
+{
+    CU_TRY(rlr::batch_gemm_launch(&s->tmap16, tmapQ, s->sm_count, static_cast<uint32_t>(s->n_rows),
+                                  static_cast<uint32_t>(s->row_base), t0, t1, nq_pad, s->pitch16, b.d_tau, b.d_app,
+                                  b.d_app_cnt, kBatchCap, b.d_overflow, st));
+    ++*launches;
+    uint32_t h_over = 0;
+    CU_TRY(cudaMemcpyAsync(&h_over, b.d_overflow, sizeof h_over, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (h_over) {
+        if (t1 - t0 <= 1) return fail(RLR_ERR_CUDA, "batch candidate list overflow on a single tile (internal error)");
+        CU_TRY(cudaMemsetAsync(b.d_app_cnt, 0, nq_pad * sizeof(uint32_t), st));
+        CU_TRY(cudaMemsetAsync(b.d_overflow, 0, sizeof(uint32_t), st));
+        const uint32_t mid = t0 + (t1 - t0) / 2;
+        if (int rc = batch_phase(s, tmapQ, b, nq, nq_pad, m, t0, mid, st, launches)) return rc;
+        return batch_phase(s, tmapQ, b, nq, nq_pad, m, mid, t1, st, launches);
+    }
+    CU_TRY(rlr::batch_prune_launch(b.d_state, b.d_state_cnt, m, b.d_app, b.d_app_cnt, kBatchCap, b.d_tau, nq, st));
+    ++*launches;
+    return RLR_OK;
+}
+
+} // namespace
+
+RLR_EXPORT int rlr_search_batch(rlr_store *s, const float *queries, uint32_t n_queries, uint32_t dim, uint32_t flags,
+                                uint32_t m, uint32_t *out_rows, float *out_scores, uint32_t *out_n)
+{
+    if (int rc = check_store(s)) return rc;
+    if (!out_rows || !out_n) return fail(RLR_ERR_INVALID_ARG, "out_rows/out_n is NULL");
+    if (n_queries == 0) return RLR_OK;
+    if (!queries) return fail(RLR_ERR_INVALID_ARG, "queries is NULL");
+    if (m == 0 || m > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "m %u not in 1..%d", m, RLR_MAX_M);
+    if (dim != s->dim) return fail(RLR_ERR_DIM_MISMATCH, "queries have %u dims, store has %u", dim, s->dim);
+    if (n_queries > 4096) return fail(RLR_ERR_UNSUPPORTED, "n_queries %u exceeds 4096 per call", n_queries);
+    for (uint32_t q = 0; q < n_queries; ++q) out_n[q] = 0;
+    if (int rc = ensure_device(s->device)) return rc;
+    if (s->n_rows == 0) return RLR_OK;
+    if (s->d_rows16 == nullptr)
+        return fail(RLR_ERR_INVALID_ARG, "rlr_search_batch needs the binary16 store copy (RLR_STORE_KEEP_F16 / RLR_STORE_F16_ONLY)");
+    {
+        static std::once_flag once[64];
+        cudaError_t ce = cudaSuccess;
+        const int optin = s->smem_optin;
+        std::call_once(once[s->device], [&] { ce = rlr::batch_configure(optin); });
+        CU_TRY(ce);
+    }
+    CtxLease lease(s);
+    if (int rc = lease.acquire()) return rc;
+    rlr_ctx *c = lease.c;
+    cudaStream_t st = c->stream;
+    const uint32_t nq = n_queries, nq_pad = (nq + kBatchQTile - 1) / kBatchQTile * kBatchQTile;
+    const uint32_t m_eff = static_cast<uint32_t>(std::min<uint64_t>(m, s->n_rows));
+
+    // host: normalise (:494) and validate the queries
+    std::vector<float> hq(static_cast<size_t>(nq) * dim);
+    memcpy(hq.data(), queries, hq.size() * sizeof(float));
+    for (uint32_t q = 0; q < nq; ++q) {
+        float *v = hq.data() + static_cast<size_t>(q) * dim;
+        for (uint32_t i = 0; i < dim; ++i)
+            if (!std::isfinite(v[i])) return fail(RLR_ERR_NONFINITE, "queries[%u][%u] is not finite", q, i);
+        if (!(flags & RLR_QUERY_PRENORMALIZED)) host_normalize(v, dim);
+    }
+    BatchBufs b;
+    CU_TRY(cudaMalloc(&b.d_q32, hq.size() * sizeof(float)));
+    CU_TRY(cudaMalloc(&b.d_q16, static_cast<size_t>(nq_pad) * s->pitch16 * 2));
+    CU_TRY(cudaMalloc(&b.d_tau, nq_pad * sizeof(float)));
+    CU_TRY(cudaMalloc(&b.d_state, static_cast<size_t>(nq_pad) * m_eff * 8));
+    CU_TRY(cudaMalloc(&b.d_app, static_cast<size_t>(nq_pad) * kBatchCap * 8));
+    CU_TRY(cudaMalloc(&b.d_state_cnt, nq_pad * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&b.d_app_cnt, nq_pad * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&b.d_overflow, sizeof(uint32_t)));
+    CUtensorMap tmapQ;
+    {
+        PFN_encodeTiled enc = get_encode();
+        if (!enc) return fail(RLR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+        const cuuint64_t gdim[2] = {s->pitch16, nq_pad};
+        const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(s->pitch16) * 2};
+        const cuuint32_t box[2] = {64, kBatchQTile};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tmapQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b.d_q16, gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(RLR_ERR_CUDA, "cuTensorMapEncodeTiled (queries) failed with CUresult %d", static_cast<int>(r));
+    }
+    const bool timed = flags & RLR_WANT_TIMINGS;
+    uint32_t launches = 0;
+    CU_TRY(cudaMemcpyAsync(b.d_q32, hq.data(), hq.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (timed) CU_TRY(cudaEventRecord(c->ev[0], st));
+    CU_TRY(rlr::batch_queries_to_half_launch(b.d_q32, dim, b.d_q16, s->pitch16, nq, nq_pad, st));
+    CU_TRY(rlr::batch_init_launch(b.d_tau, b.d_state_cnt, b.d_app_cnt, nq, nq_pad, b.d_overflow, st));
+    launches += 2;
+    // geometrically growing phases: a phase over rows [a, 4a) appends ~3m candidates per query
+    const uint32_t n_tiles = static_cast<uint32_t>((s->n_rows + kBatchRTile - 1) / kBatchRTile);
+    uint32_t t0 = 0, span = std::max<uint32_t>(1, (2 * m_eff + kBatchRTile - 1) / kBatchRTile);
+    if (span * kBatchRTile > kBatchCap) span = kBatchCap / kBatchRTile;
+    while (t0 < n_tiles) {
+        const uint32_t t1 = std::min(n_tiles, t0 + span);
+        if (int rc = batch_phase(s, &tmapQ, b, nq, nq_pad, m_eff, t0, t1, st, &launches)) return rc;
+        t0 = t1;
+        span = std::max(span, 3 * t0);        // next phase: rows [t0, 4*t0)
+    }
+    if (timed) CU_TRY(cudaEventRecord(c->ev[1], st));
+    if (flags & RLR_BATCH_EXACT_RESCORE) {
+        const bool half = s->d_rows == nullptr;
+        CU_TRY(rlr::batch_rescore_launch(half ? s->d_rows16 : static_cast<const void *>(s->d_rows), half,
+                                         half ? s->pitch16 : s->pitch, s->dim, static_cast<uint32_t>(s->row_base), b.d_q32,
+                                         b.d_state, b.d_state_cnt, m_eff, nq, st));
+        CU_TRY(rlr::batch_prune_launch(b.d_state, b.d_state_cnt, m_eff, b.d_app, b.d_app_cnt, kBatchCap, b.d_tau, nq, st));
+        launches += 2;
+    }
+    if (timed) CU_TRY(cudaEventRecord(c->ev[2], st));
+    std::vector<unsigned long long> h_state(static_cast<size_t>(nq) * m_eff);
+    std::vector<uint32_t> h_cnt(nq);
+    CU_TRY(cudaMemcpyAsync(h_state.data(), b.d_state, h_state.size() * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(h_cnt.data(), b.d_state_cnt, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    for (uint32_t q = 0; q < nq; ++q) {
+        const uint32_t n = std::min(h_cnt[q], m_eff);
+        out_n[q] = n;
+        for (uint32_t i = 0; i < n; ++i) {
+            const unsigned long long k = h_state[static_cast<size_t>(q) * m_eff + i];
+            out_rows[static_cast<size_t>(q) * m + i] = rlr::key_row(k);
+            if (out_scores) {
+                const uint32_t bits = rlr::bits_from_ord(static_cast<uint32_t>(k >> 32));
+                memcpy(&out_scores[static_cast<size_t>(q) * m + i], &bits, 4);
+            }
+        }
+    }
+    c->launches += launches;
+    if (timed) {
+        rlr_timings t = {0, 0, 0, 0, 0};
+        cudaEventElapsedTime(&t.scan_ms, c->ev[0], c->ev[1]);      // contraction + per-phase prunes
+        cudaEventElapsedTime(&t.merge_ms, c->ev[1], c->ev[2]);     // exact re-score (if requested)
+        cudaEventElapsedTime(&t.total_ms, c->ev[0], c->ev[2]);
+        cudaGetLastError();
+        t.launches = launches;
+        g_timings = t;
+    }
+    return RLR_OK;
+}
+
 RLR_EXPORT int rlr_last_timings(rlr_timings *out)
 {
     if (!out) return fail(RLR_ERR_INVALID_ARG, "out is NULL");

@@ -94,6 +94,23 @@ cudaError_t finite_check_launch(const float *d_rows, uint64_t n_floats, uint32_t
 cudaError_t to_half_launch(const float *d_src, uint32_t src_pitch, void *d_dst, uint32_t dst_pitch, uint32_t dim,
                            uint64_t n_rows, cudaStream_t stream);
 
+// batched-query path (tcgen05 GEMM + per-query threshold filter), batch_gemm.cu
+size_t batch_smem_bytes(uint32_t nq_pad);
+cudaError_t batch_configure(int smem_optin);
+cudaError_t batch_init_launch(float *tau, uint32_t *state_cnt, uint32_t *app_cnt, uint32_t nq, uint32_t nq_pad,
+                              uint32_t *overflow, cudaStream_t st);
+cudaError_t batch_queries_to_half_launch(const float *d_q, uint32_t dim, void *d_q16, uint32_t pitch16, uint32_t nq,
+                                         uint32_t nq_pad, cudaStream_t st);
+cudaError_t batch_gemm_launch(const CUtensorMap *tmapA, const CUtensorMap *tmapQ, int grid, uint32_t n_rows,
+                              uint32_t row_base, uint32_t tile0, uint32_t tile1, uint32_t nq_pad, uint32_t pitch16,
+                              const float *tau, unsigned long long *app_keys, uint32_t *app_cnt, uint32_t cap,
+                              uint32_t *overflow, cudaStream_t st);
+cudaError_t batch_prune_launch(unsigned long long *state_keys, uint32_t *state_cnt, uint32_t m, unsigned long long *app_keys,
+                               uint32_t *app_cnt, uint32_t cap, float *tau, uint32_t nq, cudaStream_t st);
+cudaError_t batch_rescore_launch(const void *d_rows, int half, uint32_t pitch, uint32_t dim, uint32_t row_base,
+                                 const float *d_q32, unsigned long long *state_keys, const uint32_t *state_cnt, uint32_t m,
+                                 uint32_t nq, cudaStream_t st);
+
 // copy a selected subset of records into SoA output arrays (host-facing results)
 cudaError_t unpack_launch(const rlr_cand *d_cands, const uint32_t *d_n, uint32_t cap, uint32_t *d_rows,
                           float *d_score, float *d_emb, float *d_lex, cudaStream_t stream);

@@ -231,6 +231,14 @@ class DeviceStore:
                                                    B.ptr(score), C.byref(n)))
         return rows[:n.value], score[:n.value]
 
+    def search_batch(self, queries: np.ndarray, m: int, flags: int = 0):
+        """rlr_search_batch: (rows [nq, m], scores [nq, m], n [nq]) for a batch of query embeddings."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq, dim = q.shape
+        rows = np.zeros((nq, m), np.uint32); scores = np.zeros((nq, m), np.float32); n = np.zeros(nq, np.uint32)
+        B.check(self._lib.rlr_search_batch(self._h, B.ptr(q), nq, dim, flags, m, B.ptr(rows), B.ptr(scores), B.ptr(n)))
+        return rows, scores, n
+
     def last_timings(self) -> B.TimingsC:
         t = B.TimingsC()
         B.check(self._lib.rlr_last_timings(C.byref(t)))

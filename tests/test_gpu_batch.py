@@ -1,0 +1,80 @@
+"""Batched-query path (tcgen05 GEMM + fused per-query threshold filter), BASELINE config 4.
+
+Floating-point kernel: compared against a plain fp32/fp64 reference of the same contraction on
+the same binary16-rounded inputs.  Stated tolerance: |score - ref| <= 2e-6 absolute (f16 x f16
+products are exact in f32; only the f32 accumulation order differs), top-m sets identical except
+for rows whose reference score is within that tolerance of the cut.  With
+RLR_BATCH_EXACT_RESCORE the returned scores are bit-identical to the sequential-f32 oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+TOL = 2e-6
+
+
+def _ref_topm(rows16, q16, m):
+    s = q16.astype(np.float64) @ rows16.astype(np.float64).T            # [nq, n]
+    order = np.argsort(-s, axis=1, kind="stable")[:, :m]
+    return s, order
+
+
+@pytest.mark.parametrize("n,dim,nq,m", [(4096, 768, 256, 100), (20000, 768, 300, 100), (10000, 1024, 1024, 100),
+                                         (5000, 64, 17, 10), (70000, 384, 512, 300), (3000, 768, 5, 900)])
+def test_batch_matches_fp_reference(n, dim, nq, m):
+    import rust_local_rag_b200  # noqa: F401
+    from rust_local_rag_b200 import binding as B, engine
+    from oracle import orc
+    rng = np.random.default_rng(n + nq)
+    rows = orc.normalize_rows(rng.standard_normal((n, dim)).astype(F32))
+    qs = rng.standard_normal((nq, dim)).astype(F32)
+    s = engine.DeviceStore.from_rows(rows, flags=B.RLR_STORE_KEEP_F16)
+    got_rows, got_scores, got_n = s.search_batch(qs, m)
+    rows16 = rows.astype(np.float16).astype(F32)
+    q16 = np.stack([orc.normalize(q) for q in qs]).astype(np.float16).astype(F32)
+    ref, order = _ref_topm(rows16, q16, m)
+    m_eff = min(m, n)
+    assert (got_n == m_eff).all()
+    for q in range(nq):
+        r = got_rows[q, :m_eff]
+        assert len(set(r.tolist())) == m_eff
+        # scores are the contraction of the rounded inputs
+        assert np.abs(got_scores[q, :m_eff].astype(np.float64) - ref[q, r]).max() <= TOL, q
+        assert (np.diff(got_scores[q, :m_eff].astype(np.float64)) <= 0).all()
+        # the set is the reference top-m up to ties at the cut
+        cut = ref[q, order[q, m_eff - 1]]
+        missing = set(order[q].tolist()) - set(r.tolist())
+        assert all(ref[q, x] <= cut + 2 * TOL for x in missing), q
+        assert all(ref[q, x] >= cut - 2 * TOL for x in r.tolist()), q
+    s.close()
+
+
+def test_batch_exact_rescore_is_bit_identical_to_single_query_path():
+    import rust_local_rag_b200  # noqa: F401
+    from rust_local_rag_b200 import binding as B, engine
+    from oracle import orc
+    n, dim, nq, m = 50000, 768, 64, 100
+    rows = orc.synth_rows(n, dim, kind=1, n_clusters=128)
+    qs = orc.synth_rows(nq, dim, kind=1, seed=0x5EED0002, n_clusters=128)
+    s = engine.DeviceStore.from_rows(rows, flags=B.RLR_STORE_KEEP_F16)
+    got_rows, got_scores, _ = s.search_batch(qs, m, flags=B.RLR_BATCH_EXACT_RESCORE)
+    exact_hits = 0
+    for q in range(nq):
+        r, sc = s.embedding_candidates(qs[q], m)                       # exact single-query path (f32 store)
+        # every returned score is the exact sequential dot of that row
+        qn = orc.normalize(qs[q])
+        back = rows[got_rows[q]]
+        assert got_scores[q].tobytes() == np.array([orc.dot(qn, b) for b in back], F32).tobytes()
+        exact_hits += len(set(r.tolist()) & set(got_rows[q].tolist()))
+    # shortlist came from f16 scores: recall of the exact top-100 must be essentially complete
+    assert exact_hits >= 0.99 * nq * m
+    s.close()
+
+
+def test_batch_needs_f16_copy():
+    import rust_local_rag_b200  # noqa: F401
+    from rust_local_rag_b200 import binding as B, engine
+    s = engine.DeviceStore.from_rows(np.eye(64, dtype=F32))
+    with pytest.raises(B.RlrError):
+        s.search_batch(np.ones((2, 64), F32), 3)
+    s.close()
