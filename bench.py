@@ -55,6 +55,9 @@ def workload_config(a, world):
         "queries": N_QUERIES,
         "l2": "inputs larger than L2 (store shard >= 3.8 GB vs 126 MB L2)",
         "parallelism": f"rows/{world}",
+        "exchange": "NCCL all-gather of per-GPU top-300 lists; MMR on rank 0 reads pool rows from peer HBM (CUDA IPC / NVLink)"
+                    if world > 1 and os.environ.get("RLR_DIST_PEERS", "1") == "1" else
+                    ("NCCL all-gather + int32 reduce of pool rows" if world > 1 else "none (single GPU)"),
     }
 
 
@@ -224,6 +227,8 @@ def run_b200(a):
     q_dev = q_pinned.to(dev)
 
     backend = rdist.CudaBackend(store, dev)
+    if world > 1 and os.environ.get("RLR_DIST_PEERS", "1") == "1":
+        backend.open_peers(group, plan)      # rank 0 maps the peer shards (CUDA IPC over NVLink)
     p_cap = max(3 * a.top_k, a.top_k + 10, 1)
     bufs = rdist.Buffers(world, p_cap, pitch, dev)
     w_e, w_l = float(np.float32(0.7)), float(np.float32(0.3))

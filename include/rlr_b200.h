@@ -306,6 +306,24 @@ int rlr_mmr_store_async(rlr_ctx *c, const void *d_cands, const void *d_n, uint32
                         uint32_t top_k, float lambda, void *d_sel_pos, void *d_sel_n,
                         void *d_result /* nullable */, void *stream);
 
+/* ---- peer memory: MMR on rank 0 reads pool rows straight from the owning GPUs' HBM ------------
+ *
+ * Row shards of one corpus on the GPUs of one NVSwitch box.  Each process exports its shard
+ * (CUDA IPC), rank 0 opens all of them, and rlr_mmr_peers_async runs MMR over GLOBAL candidate
+ * rows: the pairwise-similarity kernel dereferences peer pointers (NVLink loads), so no gather
+ * collective and no staging copy are needed.  Shards must agree on dim and precision. */
+#define RLR_IPC_HANDLE_BYTES 64
+typedef struct rlr_peer_set rlr_peer_set;
+
+int rlr_store_ipc_export(const rlr_store *s, uint32_t search_flags, void *handle_out /* 64 bytes */);
+int rlr_peer_set_open(rlr_store *local, uint32_t my_index, uint32_t n_shards,
+                      const void *handles /* n_shards x 64 bytes */, const uint64_t *row_base,
+                      const uint64_t *n_rows, uint32_t search_flags, rlr_peer_set **out);
+int rlr_peer_set_close(rlr_peer_set *p);
+int rlr_mmr_peers_async(rlr_ctx *c, rlr_peer_set *p, const void *d_cands, const void *d_n, uint32_t p_cap,
+                        uint32_t top_k, float lambda, void *d_sel_pos, void *d_sel_n,
+                        void *d_result /* nullable */, void *stream);
+
 /* fused single-GPU search_with_diversity on the device: results stay in HBM.
  * d_result: rlr_cand[max(top_k,1)] in selection order, d_result_n: u32. */
 int rlr_search_mmr_async(rlr_ctx *c, const void *d_query, uint32_t top_k, float diversity_factor,

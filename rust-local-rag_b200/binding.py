@@ -96,6 +96,10 @@ PROTOTYPES = {
     "rlr_gather_async": (_int, [_vp, _vp, _vp, _u32, _vp, _vp]),
     "rlr_mmr_async": (_int, [_vp, _vp, _u32, _u32, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp, _vp]),
     "rlr_mmr_store_async": (_int, [_vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp, _vp]),
+    "rlr_store_ipc_export": (_int, [_vp, _u32, _vp]),
+    "rlr_peer_set_open": (_int, [_vp, _u32, _u32, _vp, _vp, _vp, _u32, C.POINTER(_vp)]),
+    "rlr_peer_set_close": (_int, [_vp]),
+    "rlr_mmr_peers_async": (_int, [_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp, _vp]),
     "rlr_search_mmr_async": (_int, [_vp, _vp, _u32, _f32, _f32, _f32, _vp, _vp, _vp]),
     "rlr_ctx_set_flags": (_int, [_vp, _u32]),
     "rlr_ctx_launch_count": (_int, [_vp, C.POINTER(_u64)]),

@@ -1122,6 +1122,100 @@ RLR_EXPORT int rlr_mmr_store_async(rlr_ctx *c, const void *d_cands, const void *
     return RLR_OK;
 }
 
+struct rlr_peer_set {
+    rlr_store *local = nullptr;
+    rlr::PeerTable table;
+    void *opened[rlr::kMaxPeers];
+    bool half = false;
+};
+
+RLR_EXPORT int rlr_store_ipc_export(const rlr_store *s, uint32_t search_flags, void *handle_out)
+{
+    if (int rc = check_store(s)) return rc;
+    if (!handle_out) return fail(RLR_ERR_INVALID_ARG, "handle_out is NULL");
+    static_assert(sizeof(cudaIpcMemHandle_t) == RLR_IPC_HANDLE_BYTES, "IPC handle size");
+    memset(handle_out, 0, RLR_IPC_HANDLE_BYTES);
+    if (s->n_rows == 0) return RLR_OK;
+    CU_TRY(cudaSetDevice(s->device));
+    const bool half = s->use_half(search_flags);
+    if (half && !s->d_rows16) return fail(RLR_ERR_INVALID_ARG, "store holds no f16 copy");
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, half ? s->d_rows16 : static_cast<void *>(s->d_rows)));
+    memcpy(handle_out, &h, sizeof h);
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_peer_set_open(rlr_store *local, uint32_t my_index, uint32_t n_shards, const void *handles,
+                                 const uint64_t *row_base, const uint64_t *n_rows, uint32_t search_flags,
+                                 rlr_peer_set **out)
+{
+    if (int rc = check_store(local)) return rc;
+    if (!handles || !row_base || !n_rows || !out) return fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    if (n_shards == 0 || n_shards > rlr::kMaxPeers || my_index >= n_shards)
+        return fail(RLR_ERR_INVALID_ARG, "n_shards %u / my_index %u out of range (max %d)", n_shards, my_index, rlr::kMaxPeers);
+    CU_TRY(cudaSetDevice(local->device));
+    rlr_peer_set *p = new rlr_peer_set();
+    p->local = local;
+    p->half = local->use_half(search_flags);
+    memset(&p->table, 0, sizeof p->table);
+    memset(p->opened, 0, sizeof p->opened);
+    for (uint32_t i = 0; i < n_shards; ++i) {
+        p->table.row_base[i] = static_cast<uint32_t>(row_base[i]);
+        p->table.n_rows[i] = static_cast<uint32_t>(n_rows[i]);
+        if (i == my_index) {
+            p->table.base[i] = p->half ? local->d_rows16 : static_cast<void *>(local->d_rows);
+        } else if (n_rows[i] != 0) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, static_cast<const uint8_t *>(handles) + static_cast<size_t>(i) * RLR_IPC_HANDLE_BYTES, sizeof h);
+            cudaError_t e = cudaIpcOpenMemHandle(&p->opened[i], h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                for (uint32_t j = 0; j < i; ++j) if (p->opened[j]) cudaIpcCloseMemHandle(p->opened[j]);
+                delete p;
+                return fail(RLR_ERR_CUDA, "cudaIpcOpenMemHandle for shard %u failed: %s", i, cudaGetErrorString(e));
+            }
+            p->table.base[i] = p->opened[i];
+        }
+    }
+    p->table.n = n_shards;
+    *out = p;
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_peer_set_close(rlr_peer_set *p)
+{
+    if (!p) return RLR_OK;
+    cudaSetDevice(p->local->device);
+    for (int i = 0; i < rlr::kMaxPeers; ++i) if (p->opened[i]) cudaIpcCloseMemHandle(p->opened[i]);
+    cudaGetLastError();
+    delete p;
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_mmr_peers_async(rlr_ctx *c, rlr_peer_set *p, const void *d_cands, const void *d_n, uint32_t p_cap,
+                                   uint32_t top_k, float lambda, void *d_sel_pos, void *d_sel_n, void *d_result,
+                                   void *stream)
+{
+    if (!c || !p || !d_cands || !d_n || !d_sel_pos || !d_sel_n) return fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    if (p_cap == 0 || p_cap > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "p_cap %u not in 1..%d", p_cap, RLR_MAX_M);
+    rlr_store *s = c->s;
+    CU_TRY(cudaSetDevice(s->device));
+    rlr::MmrArgs a;
+    memset(&a, 0, sizeof a);
+    a.half = p->half;
+    a.d_emb = nullptr; a.pitch = p->half ? s->pitch16 : s->pitch; a.dim = s->dim;
+    a.d_cands = static_cast<const rlr_cand *>(d_cands); a.d_n = static_cast<const uint32_t *>(d_n);
+    a.use_rows = 1; a.p_cap = p_cap; a.top_k = top_k; a.lambda = lambda;
+    a.d_tri = c->d_tri; a.d_sel_pos = static_cast<uint32_t *>(d_sel_pos); a.d_sel_n = static_cast<uint32_t *>(d_sel_n);
+    a.d_result = static_cast<rlr_cand *>(d_result);
+    a.max_smem_optin = s->smem_optin;
+    a.peers = &p->table;
+    uint32_t l = 0;
+    CU_TRY(rlr::mmr_launch(a, static_cast<cudaStream_t>(stream), &l));
+    c->launches += l;
+    return RLR_OK;
+}
+
 RLR_EXPORT int rlr_search_mmr_async(rlr_ctx *c, const void *d_query, uint32_t top_k, float diversity_factor,
                                     float w_embed, float w_lex, void *d_result, void *d_result_n, void *stream)
 {

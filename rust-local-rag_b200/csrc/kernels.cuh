@@ -57,6 +57,17 @@ cudaError_t merge_launch(const rlr_cand *d_lists, uint32_t n_lists, uint32_t m, 
 //   d_cands     : p_cap candidate records (rank order); row index of candidate i is
 //                 (key_row(cand.key) - row_base) when use_rows != 0, else i
 //   d_rel       : optional explicit relevance (else decoded from the keys)
+// Row shards of one corpus living on several GPUs of an NVSwitch box, reachable from this GPU
+// through peer mappings (CUDA IPC): the MMR pairwise kernel loads candidate rows straight
+// from the owning GPU's HBM over NVLink.
+constexpr int kMaxPeers = 16;
+struct PeerTable {
+    const void *base[kMaxPeers];
+    uint32_t row_base[kMaxPeers];
+    uint32_t n_rows[kMaxPeers];
+    uint32_t n;                // 0: no peers, rows come from d_emb
+};
+
 struct MmrArgs {
     const void *d_emb;         // f32 rows, or binary16 rows when half != 0
     int half;
@@ -75,6 +86,7 @@ struct MmrArgs {
     uint32_t *d_sel_n;
     rlr_cand *d_result;        // optional: selected records in selection order
     int max_smem_optin;
+    const PeerTable *peers;    // optional (host pointer): candidate rows are global and live on these shards
 };
 cudaError_t mmr_configure();
 cudaError_t mmr_launch(const MmrArgs &a, cudaStream_t stream, uint32_t *launches);

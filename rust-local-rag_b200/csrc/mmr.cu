@@ -14,6 +14,8 @@
 // swap_remove bookkeeping (:783,:825) is reproduced with a per-candidate "position in
 // `remaining`" so that exact MMR-score ties resolve to the lowest CURRENT position,
 // exactly what the strict '>' scan at :812 does.
+#include <cstring>
+
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -43,7 +45,7 @@ template <bool kHalf>
 __global__ void __launch_bounds__(T * T)
 mmr_pairwise_kernel(const void *__restrict__ emb, uint32_t pitch, const rlr_cand *__restrict__ cands,
                     const uint32_t *__restrict__ rows, const uint32_t *__restrict__ d_n, uint32_t row_base,
-                    int use_rows, float *__restrict__ tri)
+                    int use_rows, float *__restrict__ tri, const __grid_constant__ PeerTable peers)
 {
     constexpr uint32_t ESZ = kHalf ? 2u : 4u;             // bytes per stored element
     constexpr uint32_t EPV = 16u / ESZ;                   // elements per 16-byte vector
@@ -59,9 +61,19 @@ mmr_pairwise_kernel(const void *__restrict__ emb, uint32_t pitch, const rlr_cand
     const uint32_t tid = threadIdx.x;
     if (tid < 2 * T) {
         const uint32_t ci = (tid < T) ? bi * T + tid : bj * T + (tid - T);
-        rowptr[tid] = ci < p ? static_cast<const uint8_t *>(emb) +
-                                   static_cast<size_t>(cand_row(cands, rows, row_base, use_rows, ci)) * pitch * ESZ
-                             : nullptr;
+        const uint8_t *ptr = nullptr;
+        if (ci < p) {
+            if (peers.n != 0) {
+                // global row -> owning shard -> peer-mapped pointer (a load over NVLink if not local)
+                const uint32_t g = key_row(cands[ci].key);
+                for (uint32_t s = 0; s < peers.n; ++s)
+                    if (g >= peers.row_base[s] && g - peers.row_base[s] < peers.n_rows[s])
+                        ptr = static_cast<const uint8_t *>(peers.base[s]) + static_cast<size_t>(g - peers.row_base[s]) * pitch * ESZ;
+            } else {
+                ptr = static_cast<const uint8_t *>(emb) + static_cast<size_t>(cand_row(cands, rows, row_base, use_rows, ci)) * pitch * ESZ;
+            }
+        }
+        rowptr[tid] = ptr;
     }
     __syncthreads();
 
@@ -335,12 +347,15 @@ cudaError_t mmr_launch(const MmrArgs &a, cudaStream_t stream, uint32_t *launches
     if (a.p_cap == 0) return cudaErrorInvalidValue;
     const uint32_t nb = (a.p_cap + T - 1) / T;
     if (a.p_cap > 1) {
+        PeerTable pt;
+        memset(&pt, 0, sizeof pt);
+        if (a.peers != nullptr) pt = *a.peers;
         if (a.half)
             mmr_pairwise_kernel<true><<<dim3(nb, nb), T * T, 2 * T * (KC * 2 + 16), stream>>>(
-                a.d_emb, a.pitch, a.d_cands, a.d_rows, a.d_n, a.row_base, a.use_rows, a.d_tri);
+                a.d_emb, a.pitch, a.d_cands, a.d_rows, a.d_n, a.row_base, a.use_rows, a.d_tri, pt);
         else
             mmr_pairwise_kernel<false><<<dim3(nb, nb), T * T, 2 * T * (KC * 4 + 16), stream>>>(
-                a.d_emb, a.pitch, a.d_cands, a.d_rows, a.d_n, a.row_base, a.use_rows, a.d_tri);
+                a.d_emb, a.pitch, a.d_cands, a.d_rows, a.d_n, a.row_base, a.use_rows, a.d_tri, pt);
         if (launches) ++*launches;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;

@@ -5,10 +5,13 @@ Per query, on every rank g of G:
   1. local fused scan + top-P over the rank's contiguous row block   (rlr_topm_async)
   2. ONE all-gather of the fixed-size per-rank lists (P x 16 B)      (NCCL)
   3. merge of the G lists to the global pool of P                    (rlr_merge_async)
-  4. gather of the pool rows this rank owns into a P x pitch matrix  (rlr_gather_async)
-  5. reduce-to-rank-0 of that matrix as int32 bit patterns: every row is non-zero on
-     exactly one rank, and integer x + 0 == x, so the transport is bit-exact (NCCL)
-  6. MMR on rank 0                                                   (rlr_mmr_async)
+  4. MMR on rank 0, whose pairwise-similarity kernel loads the pool rows straight from the
+     owning GPUs' HBM through CUDA-IPC peer mappings (NVLink loads)  (rlr_mmr_peers_async)
+  Fallback when peer mappings are not set up (and what the gloo tests drive):
+  4'. gather of the pool rows this rank owns into a P x pitch matrix (rlr_gather_async)
+  5'. reduce-to-rank-0 of that matrix as int32 bit patterns: every row is non-zero on
+      exactly one rank, and integer x + 0 == x, so the transport is bit-exact (NCCL)
+  6'. MMR on rank 0 over the gathered matrix                         (rlr_mmr_async)
 Nothing here computes on the host; the steps are enqueued on the current CUDA stream.
 
 The choreography takes a `backend` object so that tests/test_dist_gloo.py can drive the
@@ -118,6 +121,13 @@ def sharded_search(backend, group, bufs: Buffers, query, top_k: int, diversity_f
     if lam == 0.0:
         return pool, pool_n
     emb = bufs.emb[:m]
+    if world > 1 and getattr(backend, "peers_ready", False):
+        # peer-memory path: rank 0's MMR kernels load the pool rows straight from the owning
+        # GPUs' HBM over NVLink (CUDA IPC mappings) -- no gather kernel, no second collective
+        if rank != 0:
+            return bufs.result, bufs.sel_n
+        backend.mmr_peers(pool, pool_n, m, top_k, lam, bufs.sel_pos, bufs.sel_n, bufs.result)
+        return bufs.result, bufs.sel_n
     if world > 1:
         backend.gather(pool, pool_n, m, emb)
         dist.reduce(emb.view(torch.int32), dst=dist.get_global_rank(group, 0) if group is not None else 0,
@@ -146,8 +156,40 @@ class CudaBackend:
         B.check(self.lib.rlr_ctx_create(store.handle, C.byref(self.ctx)))
         if search_flags:
             B.check(self.lib.rlr_ctx_set_flags(self.ctx, search_flags))
+        self.search_flags = search_flags
+        self.peer_set = None
+        self.peers_ready = False
+
+    def open_peers(self, group, plan: "ShardPlan"):
+        """Exchange CUDA-IPC handles of the shards; rank 0 maps every peer shard.  Collective."""
+        import numpy as np
+        B = self.B
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        handle = np.zeros(64, np.uint8)
+        B.check(self.lib.rlr_store_ipc_export(self.store.handle, self.search_flags, B.ptr(handle)))
+        info = self.store.info()
+        mine = (handle.tobytes(), int(info.row_base), int(info.n_rows))
+        allv = [None] * world
+        dist.all_gather_object(allv, mine, group=group)
+        if rank == 0:
+            handles = np.frombuffer(b"".join(v[0] for v in allv), np.uint8).copy()
+            row_base = np.array([v[1] for v in allv], np.uint64)
+            n_rows = np.array([v[2] for v in allv], np.uint64)
+            ps = C.c_void_p()
+            B.check(self.lib.rlr_peer_set_open(self.store.handle, 0, world, B.ptr(handles), B.ptr(row_base),
+                                               B.ptr(n_rows), self.search_flags, C.byref(ps)))
+            self.peer_set = ps
+        self.peers_ready = True
+        dist.barrier(group=group)
+
+    def mmr_peers(self, pool, pool_n, p_cap, top_k, lam, sel_pos, sel_n, result):
+        self.B.check(self.lib.rlr_mmr_peers_async(self.ctx, self.peer_set, self._p(pool), self._p(pool_n), p_cap, top_k,
+                                                  lam, self._p(sel_pos), self._p(sel_n), self._p(result), self._stream()))
 
     def close(self):
+        if self.peer_set:
+            self.lib.rlr_peer_set_close(self.peer_set)
+            self.peer_set = None
         if self.ctx:
             self.lib.rlr_ctx_destroy(self.ctx)
             self.ctx = None

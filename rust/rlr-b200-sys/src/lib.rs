@@ -19,6 +19,7 @@ pub const RLR_STORE_F16_ONLY: u32 = 0x4;
 
 #[repr(C)] pub struct rlr_store { _p: [u8; 0] }
 #[repr(C)] pub struct rlr_ctx { _p: [u8; 0] }
+#[repr(C)] pub struct rlr_peer_set { _p: [u8; 0] }
 
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct rlr_query_weights { pub embedding: f32, pub lexical: f32, pub reranker: f32, pub initial: f32, pub has: u32 }
@@ -59,6 +60,10 @@ extern "C" {
     pub fn rlr_gather_async(c: *mut rlr_ctx, d_cands: *const c_void, d_n: *const c_void, m: u32, d_out: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn rlr_mmr_async(c: *mut rlr_ctx, d_emb: *const c_void, pitch: u32, dim: u32, d_cands: *const c_void, d_n: *const c_void, p_cap: u32, top_k: u32, lambda: f32, d_sel_pos: *mut c_void, d_sel_n: *mut c_void, d_result: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn rlr_mmr_store_async(c: *mut rlr_ctx, d_cands: *const c_void, d_n: *const c_void, p_cap: u32, top_k: u32, lambda: f32, d_sel_pos: *mut c_void, d_sel_n: *mut c_void, d_result: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn rlr_store_ipc_export(s: *const rlr_store, search_flags: u32, handle_out: *mut c_void) -> c_int;
+    pub fn rlr_peer_set_open(local: *mut rlr_store, my_index: u32, n_shards: u32, handles: *const c_void, row_base: *const u64, n_rows: *const u64, search_flags: u32, out: *mut *mut rlr_peer_set) -> c_int;
+    pub fn rlr_peer_set_close(p: *mut rlr_peer_set) -> c_int;
+    pub fn rlr_mmr_peers_async(c: *mut rlr_ctx, p: *mut rlr_peer_set, d_cands: *const c_void, d_n: *const c_void, p_cap: u32, top_k: u32, lambda: f32, d_sel_pos: *mut c_void, d_sel_n: *mut c_void, d_result: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn rlr_search_mmr_async(c: *mut rlr_ctx, d_query: *const c_void, top_k: u32, diversity_factor: f32, w_embed: f32, w_lex: f32, d_result: *mut c_void, d_result_n: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn rlr_ctx_set_flags(c: *mut rlr_ctx, search_flags: u32) -> c_int;
     pub fn rlr_ctx_launch_count(c: *const rlr_ctx, out: *mut u64) -> c_int;

@@ -24,6 +24,9 @@ def main():
     kw = dict(kind=B.RLR_SYNTH_CLUSTERED, seed=11, centroid_seed=12, n_clusters=64, sigma=0.65)
     shard = engine.DeviceStore.synthetic(plan.n_local, dim, device=lr, row_base=plan.row0, **kw)
     backend = rdist.CudaBackend(shard, dev)
+    use_peers = os.environ.get("RLR_DIST_PEERS", "1") == "1"
+    if use_peers:
+        backend.open_peers(dist.group.WORLD, plan)
     pitch = shard.info().pitch
     qs = engine.DeviceStore.synthetic(8, dim, device=lr, **{**kw, "seed": 13})
     q_host = qs.read_rows(np.arange(8))
@@ -52,7 +55,7 @@ def main():
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     if rank == 0:
-        print("DIST_PARITY_OK" if ok else "DIST_PARITY_FAIL", f"world={world} n={n} dim={dim}")
+        print("DIST_PARITY_OK" if ok else "DIST_PARITY_FAIL", f"world={world} n={n} dim={dim} peers={use_peers}")
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1 else 1)
