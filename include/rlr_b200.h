@@ -159,6 +159,23 @@ int rlr_store_info_get(const rlr_store *s, rlr_store_info *out);
 int rlr_store_upload(rlr_store *s, uint64_t row0, uint64_t n, const float *rows,
                      uint64_t host_pitch);
 
+/*
+ * Store mutation for `add_document` (src/rag_engine.rs:347-386: `chunks.retain(..)` drops the
+ * document's old chunks, then the new normalised chunks are inserted), called under the
+ * reference's write lock -- exclusivity required.
+ *   rlr_store_reserve      pre-size the device allocations (amortises appends).
+ *   rlr_store_append       append n normalised rows; *out_first_row = global row of the first.
+ *   rlr_store_remove_rows  delete the listed global rows.  The store stays dense: each hole is
+ *                          filled with a surviving row from the tail.  The moves are reported as
+ *                          (out_moved_from[i] -> out_moved_to[i]), i < *out_n_moved <= n, so that
+ *                          the caller can patch its `row -> chunk_id` table; out arrays have capacity n.
+ */
+int rlr_store_reserve(rlr_store *s, uint64_t capacity_rows);
+int rlr_store_append(rlr_store *s, uint64_t n, const float *rows, uint64_t host_pitch,
+                     uint64_t *out_first_row);
+int rlr_store_remove_rows(rlr_store *s, const uint32_t *rows, uint64_t n,
+                          uint32_t *out_moved_from, uint32_t *out_moved_to, uint64_t *out_n_moved);
+
 /* copy rows[i] (local indices) back to host: out is n x dim, stride dim. */
 int rlr_store_read_rows(const rlr_store *s, const uint32_t *rows, uint64_t n, float *out);
 

@@ -79,6 +79,9 @@ PROTOTYPES = {
     "rlr_store_destroy": (_int, [_vp]),
     "rlr_store_info_get": (_int, [_vp, C.POINTER(StoreInfoC)]),
     "rlr_store_upload": (_int, [_vp, _u64, _u64, _vp, _u64]),
+    "rlr_store_reserve": (_int, [_vp, _u64]),
+    "rlr_store_append": (_int, [_vp, _u64, _vp, _u64, C.POINTER(_u64)]),
+    "rlr_store_remove_rows": (_int, [_vp, _vp, _u64, _vp, _vp, C.POINTER(_u64)]),
     "rlr_store_read_rows": (_int, [_vp, _vp, _u64, _vp]),
     "rlr_store_fill_synthetic": (_int, [_vp, _int, _u64, _u64, _u32, _f32]),
     "rlr_search_topm": (_int, [_vp, _vp, _u32, _u32, C.POINTER(ResolvedWeightsC), _vp, _vp, _u32, _u32,

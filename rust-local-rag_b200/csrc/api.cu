@@ -126,6 +126,7 @@ struct rlr_store {
     int device = 0;
     uint32_t dim = 0, pitch = 0, flags = 0;
     uint64_t n_rows = 0, row_base = 0;
+    uint64_t capacity = 0;          // rows the device allocations can hold (>= n_rows)
     float *d_rows = nullptr;        // f32 matrix (absent for RLR_STORE_F16_ONLY)
     void *d_rows16 = nullptr;       // binary16 copy (RLR_STORE_KEEP_F16 / RLR_STORE_F16_ONLY)
     uint32_t pitch16 = 0;           // elements per binary16 row (dim rounded up to 64)
@@ -498,6 +499,7 @@ RLR_EXPORT int rlr_store_create(int device, uint32_t dim, uint64_t n_rows, const
     s->pitch = (dim + 31u) & ~31u;
     s->pitch16 = (dim + 63u) & ~63u;
     s->n_rows = n_rows;
+    s->capacity = n_rows;
     s->row_base = row_base;
     s->flags = flags;
     {
@@ -617,6 +619,120 @@ RLR_EXPORT int rlr_store_read_rows(const rlr_store *s, const uint32_t *rows, uin
         }
     }
     return RLR_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// store mutation (add_document, src/rag_engine.rs:347-386, under the write lock): drop a
+// document's rows, append its new rows.  Mutators require exclusivity (header, "threading").
+// ---------------------------------------------------------------------------------
+namespace {
+
+int store_remap(rlr_store *s)
+{
+    if (s->n_rows == 0) return RLR_OK;
+    if (s->d_rows) if (int rc = make_tmap(&s->tmap, s->d_rows, false, s->pitch, s->n_rows)) return rc;
+    if (s->d_rows16) if (int rc = make_tmap(&s->tmap16, s->d_rows16, true, s->pitch16, s->n_rows)) return rc;
+    return RLR_OK;
+}
+
+int store_grow(rlr_store *s, uint64_t want)
+{
+    if (want <= s->capacity) return RLR_OK;
+    uint64_t cap = std::max<uint64_t>(want, s->capacity + s->capacity / 2 + 1024);
+    if (cap >= (1ull << 31)) cap = (1ull << 31) - 1;
+    if (cap < want) return fail(RLR_ERR_UNSUPPORTED, "store would exceed 2^31 rows");
+    const bool want32 = !(s->flags & RLR_STORE_F16_ONLY);
+    const bool want16 = s->flags & (RLR_STORE_F16_ONLY | RLR_STORE_KEEP_F16);
+    float *n32 = nullptr;
+    void *n16 = nullptr;
+    if (want32) CU_TRY(cudaMalloc(&n32, cap * s->pitch * sizeof(float)));
+    if (want16) {
+        cudaError_t e = cudaMalloc(&n16, cap * s->pitch16 * 2);
+        if (e != cudaSuccess) { cudaGetLastError(); cudaFree(n32); return fail(RLR_ERR_OOM, "cudaMalloc failed growing the store: %s", cudaGetErrorString(e)); }
+    }
+    if (s->n_rows) {
+        if (want32) CU_TRY(cudaMemcpy(n32, s->d_rows, s->n_rows * s->pitch * sizeof(float), cudaMemcpyDeviceToDevice));
+        if (want16) CU_TRY(cudaMemcpy(n16, s->d_rows16, s->n_rows * s->pitch16 * 2, cudaMemcpyDeviceToDevice));
+    }
+    cudaFree(s->d_rows); cudaFree(s->d_rows16);
+    s->d_rows = n32; s->d_rows16 = n16; s->capacity = cap;
+    return RLR_OK;
+}
+
+} // namespace
+
+RLR_EXPORT int rlr_store_reserve(rlr_store *s, uint64_t capacity_rows)
+{
+    if (int rc = check_store(s)) return rc;
+    if (int rc = ensure_device(s->device)) return rc;
+    if (int rc = store_grow(s, capacity_rows)) return rc;
+    return store_remap(s);
+}
+
+RLR_EXPORT int rlr_store_append(rlr_store *s, uint64_t n, const float *rows, uint64_t host_pitch, uint64_t *out_first_row)
+{
+    if (int rc = check_store(s)) return rc;
+    if (!rows && n) return fail(RLR_ERR_INVALID_ARG, "rows is NULL");
+    if (int rc = ensure_device(s->device)) return rc;
+    if (s->row_base + s->n_rows + n >= (1ull << 32)) return fail(RLR_ERR_UNSUPPORTED, "global rows must fit 32 bits");
+    if (out_first_row) *out_first_row = s->row_base + s->n_rows;
+    if (n == 0) return RLR_OK;
+    if (int rc = store_grow(s, s->n_rows + n)) return rc;
+    const uint64_t first = s->n_rows;
+    s->n_rows += n;
+    if (int rc = rlr_store_upload(s, first, n, rows, host_pitch)) { s->n_rows = first; return rc; }
+    return store_remap(s);
+}
+
+RLR_EXPORT int rlr_store_remove_rows(rlr_store *s, const uint32_t *rows, uint64_t n, uint32_t *out_moved_from,
+                                     uint32_t *out_moved_to, uint64_t *out_n_moved)
+{
+    if (int rc = check_store(s)) return rc;
+    if (out_n_moved) *out_n_moved = 0;
+    if (n == 0) return RLR_OK;
+    if (!rows) return fail(RLR_ERR_INVALID_ARG, "rows is NULL");
+    if (int rc = ensure_device(s->device)) return rc;
+    // local, sorted, unique
+    std::vector<uint32_t> rm;
+    rm.reserve(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t g = rows[i];
+        if (g < s->row_base || g - s->row_base >= s->n_rows) return fail(RLR_ERR_INVALID_ARG, "row %llu not in this store", (unsigned long long)g);
+        rm.push_back(static_cast<uint32_t>(g - s->row_base));
+    }
+    std::sort(rm.begin(), rm.end());
+    rm.erase(std::unique(rm.begin(), rm.end()), rm.end());
+    const uint64_t new_n = s->n_rows - rm.size();
+    // holes below new_n are filled, in order, by the surviving rows of the tail [new_n, n_rows)
+    std::vector<uint32_t> from, to;
+    size_t hi = rm.size();                       // rm[lo_end..) are removals inside the tail
+    while (hi > 0 && rm[hi - 1] >= new_n) --hi;
+    size_t tail_rm = hi;
+    uint64_t src = new_n;
+    for (size_t h = 0; h < hi; ++h) {
+        while (tail_rm < rm.size() && rm[tail_rm] == src) { ++src; ++tail_rm; }
+        from.push_back(static_cast<uint32_t>(src++));
+        to.push_back(rm[h]);
+    }
+    if (!from.empty()) {
+        uint32_t *d_from = nullptr, *d_to = nullptr;
+        CU_TRY(cudaMalloc(&d_from, from.size() * 4));
+        cudaError_t e = cudaMalloc(&d_to, to.size() * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(d_from, from.data(), from.size() * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_to, to.data(), to.size() * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && s->d_rows) e = rlr::move_rows_launch(s->d_rows, s->pitch * 4, d_from, d_to, static_cast<uint32_t>(from.size()), 0);
+        if (e == cudaSuccess && s->d_rows16) e = rlr::move_rows_launch(s->d_rows16, s->pitch16 * 2, d_from, d_to, static_cast<uint32_t>(from.size()), 0);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        cudaFree(d_from); cudaFree(d_to);
+        CU_TRY(e);
+    }
+    for (size_t i = 0; i < from.size(); ++i) {
+        if (out_moved_from) out_moved_from[i] = static_cast<uint32_t>(s->row_base + from[i]);
+        if (out_moved_to) out_moved_to[i] = static_cast<uint32_t>(s->row_base + to[i]);
+    }
+    if (out_n_moved) *out_n_moved = from.size();
+    s->n_rows = new_n;
+    return store_remap(s);
 }
 
 RLR_EXPORT int rlr_store_fill_synthetic(rlr_store *s, int kind, uint64_t seed, uint64_t centroid_seed,

@@ -103,6 +103,9 @@ cudaError_t synth_launch(float *d_rows, uint32_t pitch, void *d_rows16, uint32_t
                          int kind, uint64_t seed, uint64_t centroid_seed, uint32_t n_clusters, float sigma,
                          cudaStream_t stream);
 cudaError_t finite_check_launch(const float *d_rows, uint64_t n_floats, uint32_t *d_flag, cudaStream_t stream);
+// rows[to[i]] = rows[from[i]] (disjoint sources and destinations), row_bytes a multiple of 16
+cudaError_t move_rows_launch(void *d_rows, uint32_t row_bytes, const uint32_t *d_from, const uint32_t *d_to, uint32_t n,
+                             cudaStream_t stream);
 cudaError_t to_half_launch(const float *d_src, uint32_t src_pitch, void *d_dst, uint32_t dst_pitch, uint32_t dim,
                            uint64_t n_rows, cudaStream_t stream);
 

@@ -116,6 +116,26 @@ __global__ void to_half_kernel(const float *__restrict__ src, uint32_t src_pitch
 }
 } // namespace
 
+namespace {
+__global__ void move_rows_kernel(uint8_t *rows, uint32_t row_bytes, const uint32_t *__restrict__ from,
+                                 const uint32_t *__restrict__ to, uint32_t n)
+{
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(rows + static_cast<size_t>(from[i]) * row_bytes);
+        uint4 *dst = reinterpret_cast<uint4 *>(rows + static_cast<size_t>(to[i]) * row_bytes);
+        for (uint32_t c = threadIdx.x; c < row_bytes / 16; c += blockDim.x) dst[c] = src[c];
+    }
+}
+} // namespace
+
+cudaError_t move_rows_launch(void *d_rows, uint32_t row_bytes, const uint32_t *d_from, const uint32_t *d_to, uint32_t n,
+                             cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    move_rows_kernel<<<n < 4096 ? n : 4096, 128, 0, stream>>>(static_cast<uint8_t *>(d_rows), row_bytes, d_from, d_to, n);
+    return cudaGetLastError();
+}
+
 cudaError_t to_half_launch(const float *d_src, uint32_t src_pitch, void *d_dst, uint32_t dst_pitch, uint32_t dim,
                            uint64_t n_rows, cudaStream_t stream)
 {

@@ -171,6 +171,22 @@ class DeviceStore:
         rows = np.ascontiguousarray(rows, dtype=np.float32)
         B.check(self._lib.rlr_store_upload(self._h, row0, rows.shape[0], B.ptr(rows), rows.shape[1]))
 
+    def append(self, rows: np.ndarray) -> int:
+        """rlr_store_append: returns the global row of the first appended row."""
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        first = C.c_uint64(0)
+        B.check(self._lib.rlr_store_append(self._h, rows.shape[0], B.ptr(rows) if rows.shape[0] else None,
+                                           rows.shape[1] if rows.ndim == 2 else 0, C.byref(first)))
+        return first.value
+
+    def remove_rows(self, rows: Sequence[int]):
+        """rlr_store_remove_rows: returns the (from, to) row moves that keep the store dense."""
+        r = np.ascontiguousarray(rows, dtype=np.uint32)
+        mf = np.zeros(max(len(r), 1), np.uint32); mt = np.zeros(max(len(r), 1), np.uint32)
+        n = C.c_uint64(0)
+        B.check(self._lib.rlr_store_remove_rows(self._h, B.ptr(r) if len(r) else None, len(r), B.ptr(mf), B.ptr(mt), C.byref(n)))
+        return mf[:n.value], mt[:n.value]
+
     def close(self) -> None:
         if self._h:
             self._lib.rlr_store_destroy(self._h)
@@ -319,6 +335,26 @@ class RagEngine:
         ids = list(chunk_ids) if chunk_ids is not None else [f"chunk-{i}" for i in range(rows.shape[0])]
         metas = [DocumentChunk(id=i) for i in ids]
         return cls(metas, DeviceStore.from_rows(rows, device=device), **kw)
+
+    # ---- mutation: add_document, src/rag_engine.rs:219-402 (the store half: :347-386) ----
+    def replace_document(self, document_name: str, chunks: List[DocumentChunk], embeddings: np.ndarray) -> None:
+        """Drop every chunk of `document_name` (`chunks.retain`, :347-348) and insert the new ones with
+        their embeddings normalised (:359).  Keeps the device store dense and `row -> chunk` in sync."""
+        old = [i for i, c in enumerate(self.chunks) if c.document_name == document_name]
+        if old:
+            mf, mt = self.store.remove_rows(old)
+            for f, t in zip(mf.tolist(), mt.tolist()):
+                self.chunks[t] = self.chunks[f]
+            del self.chunks[len(self.chunks) - len(old):]
+        emb = np.array(embeddings, dtype=np.float32, order="C")
+        lib = B.load()
+        for i in range(emb.shape[0]):
+            B.check(lib.rlr_normalize(emb[i].ctypes.data_as(C.POINTER(C.c_float)), emb.shape[1]))
+        if len(chunks):
+            first = self.store.append(emb)
+            assert first == len(self.chunks)
+            self.chunks.extend(chunks)
+        self.row_of = {c.id: i for i, c in enumerate(self.chunks)}
 
     # ---- helpers ----
     def _embed(self, query: Query) -> np.ndarray:

@@ -45,6 +45,9 @@ extern "C" {
     pub fn rlr_store_destroy(s: *mut rlr_store) -> c_int;
     pub fn rlr_store_info_get(s: *const rlr_store, out: *mut rlr_store_info) -> c_int;
     pub fn rlr_store_upload(s: *mut rlr_store, row0: u64, n: u64, rows: *const f32, host_pitch: u64) -> c_int;
+    pub fn rlr_store_reserve(s: *mut rlr_store, capacity_rows: u64) -> c_int;
+    pub fn rlr_store_append(s: *mut rlr_store, n: u64, rows: *const f32, host_pitch: u64, out_first_row: *mut u64) -> c_int;
+    pub fn rlr_store_remove_rows(s: *mut rlr_store, rows: *const u32, n: u64, out_moved_from: *mut u32, out_moved_to: *mut u32, out_n_moved: *mut u64) -> c_int;
     pub fn rlr_store_read_rows(s: *const rlr_store, rows: *const u32, n: u64, out: *mut f32) -> c_int;
     pub fn rlr_store_fill_synthetic(s: *mut rlr_store, kind: c_int, seed: u64, centroid_seed: u64, n_clusters: u32, sigma: f32) -> c_int;
     pub fn rlr_search_topm(s: *mut rlr_store, query: *const f32, dim: u32, flags: u32, w: *const rlr_resolved_weights, lex_rows: *const u32, lex_scores: *const f32, n_lex: u32, m: u32, out_rows: *mut u32, out_combined: *mut f32, out_emb: *mut f32, out_lex: *mut f32, out_n: *mut u32) -> c_int;

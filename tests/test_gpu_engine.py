@@ -1,0 +1,130 @@
+"""Host mirror of RagEngine over the CUDA path: chunks_{model}.json loading (N1), store mutation
+for add_document (N2), and the reranker-in-the-middle flow (N3) -- SURVEY.md section 8(f)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+def _write_index(path, n, dim, version=2, hashes=True, seed=0):
+    rng = np.random.default_rng(seed)
+    chunks = {}
+    for i in range(n):
+        cid = f"{i:08x}-aaaa-bbbb-cccc-{i:012x}"
+        chunks[cid] = {"id": cid, "document_name": f"doc{i % 7}.pdf", "text": "",
+                       "embedding": [float(x) for x in (rng.standard_normal(dim) * 2.5).astype(F32)],  # NOT normalised
+                       "chunk_index": i, "page_number": 1 + i % 9, "section": None,
+                       "metadata": {"page_range": [1, 2], "sentence_range": [0, 3], "section_title": None,
+                                    "token_count": 180, "overlap_with_previous": 2}}
+    state = {"version": version, "model": "nomic-embed-text", "chunks": chunks, "needs_reindex": False}
+    if hashes:
+        state["document_hashes"] = {f"doc{j}.pdf": "ab" * 32 for j in range(7)}
+    with open(path, "w") as f:
+        json.dump(state, f, indent=2)
+    return chunks
+
+
+def test_load_chunks_json_and_search_documents(tmp_path, orc):
+    """BASELINE config 1 in miniature: chunks_{model}.json -> re-normalise at load (:1678) -> search_documents."""
+    import rust_local_rag_b200  # noqa: F401
+    from rust_local_rag_b200 import engine
+    n, dim = 600, 96
+    path = engine.get_index_path(str(tmp_path), "nomic-embed-text")
+    assert os.path.basename(path) == "chunks_nomic-embed-text.json"
+    chunks = _write_index(path, n, dim)
+    eng = engine.RagEngine.load_from_disk(str(tmp_path), model="nomic-embed-text")
+    assert len(eng.chunks) == n and not eng.needs_reindex
+    rows = orc.normalize_rows(np.array([c["embedding"] for c in chunks.values()], F32))
+    ids = list(chunks.keys())
+    q = np.random.default_rng(5).standard_normal(dim).astype(F32)
+    hits = engine.search_documents(eng, q)                                   # defaults: top_k=5, diversity 0.3
+    ref = orc.search_with_diversity(rows, q, 5, 0.3, full_sort=True)
+    assert [h.chunk_id for h in hits] == [ids[r] for r in ref[0]]
+    assert np.array([h.score for h in hits], F32).tobytes() == ref[1].tobytes()
+    assert all(h.embedding_score is not None and h.reranker_score is None and h.initial_score == h.score for h in hits)
+    assert hits[0].document == chunks[ids[ref[0][0]]]["document_name"] and hits[0].page_number == 1 + ref[0][0] % 9
+    hits = engine.search_documents(eng, q, top_k=500, diversity_factor=7.0)  # clamps: top_k <= 100, lambda <= 1
+    assert len(hits) == 100
+    ref = orc.search_with_diversity(rows, q, 100, 1.0, full_sort=True)
+    assert [h.row for h in hits] == ref[0].tolist()
+    cands = eng.get_embedding_candidates(q, 12)
+    rr, ss = orc.embedding_candidates(rows, q, 12)
+    assert [c["chunk_id"] for c in cands] == [ids[r] for r in rr]
+    assert np.array([c["initial_score"] for c in cands], F32).tobytes() == ss.tobytes()
+
+
+def test_outdated_or_unfingerprinted_index(tmp_path):
+    import rust_local_rag_b200  # noqa: F401
+    from rust_local_rag_b200 import engine
+    p = os.path.join(tmp_path, "chunks_m.json")
+    _write_index(p, 10, 8, version=1)
+    e = engine.RagEngine.from_chunks_json(p)                                 # :1664-1673 wipe + needs_reindex
+    assert e.chunks == [] and e.needs_reindex and e.search(np.ones(8, F32), 5) == []
+    _write_index(p, 10, 8, version=2, hashes=False)
+    e = engine.RagEngine.from_chunks_json(p)                                 # :1686-1691
+    assert len(e.chunks) == 10 and e.needs_reindex
+
+
+def test_replace_document_keeps_store_and_table_in_sync(orc):
+    """add_document (:347-386): drop the document's rows, append the new ones; results must equal the
+    oracle run on the host-side picture of the store after every mutation."""
+    import rust_local_rag_b200  # noqa: F401
+    from rust_local_rag_b200 import engine
+    rng = np.random.default_rng(17)
+    dim = 128
+    docs = {}
+
+    def make_doc(name, n):
+        emb = (rng.standard_normal((n, dim)) * 3).astype(F32)
+        return [engine.DocumentChunk(id=f"{name}-{i}-{rng.integers(1 << 30)}", document_name=name, chunk_index=i)
+                for i in range(n)], emb
+
+    eng = engine.RagEngine.from_rows(np.zeros((0, dim), F32))
+    q = rng.standard_normal(dim).astype(F32)
+    for step, (name, n) in enumerate([("a.pdf", 300), ("b.pdf", 1), ("c.pdf", 700), ("a.pdf", 50), ("d.pdf", 2000),
+                                      ("c.pdf", 0), ("b.pdf", 129), ("a.pdf", 400)]):
+        chunks, emb = make_doc(name, n)
+        eng.replace_document(name, chunks, emb)
+        docs[name] = (chunks, orc.normalize_rows(emb))
+        # host-side picture: whatever order the engine says
+        host = {c.id: e for cs, es in docs.values() for c, e in zip(cs, es)}
+        assert sorted(c.id for c in eng.chunks) == sorted(host)
+        rows = np.array([host[c.id] for c in eng.chunks], F32).reshape(len(eng.chunks), dim)
+        assert eng.store.info().n_rows == len(eng.chunks)
+        got = eng.search_with_diversity(q, 10, 0.4)
+        ref = orc.search_with_diversity(rows, q, 10, 0.4, full_sort=True)
+        assert [g.row for g in got] == ref[0].tolist(), step
+        assert np.array([g.score for g in got], F32).tobytes() == ref[1].tobytes()
+        assert [g.chunk_id for g in got] == [eng.chunks[r].id for r in ref[0]]
+
+
+def test_reranker_in_the_middle_flow(orc):
+    """With a reranker, search() cuts at initial_k = 3*top_k (:544), the host blends reranker and initial
+    scores (:602-665), and MMR runs on the blended relevance (:794): rlr_search_topm -> host -> rlr_mmr."""
+    import rust_local_rag_b200  # noqa: F401
+    from rust_local_rag_b200 import engine
+    rng = np.random.default_rng(23)
+    n, dim, top_k, lam = 30000, 384, 20, 0.6
+    rows = orc.synth_rows(n, dim, kind=1, n_clusters=32)
+    q = orc.synth_rows(1, dim, kind=1, seed=77, n_clusters=32)[0]
+    s = engine.DeviceStore.from_rows(rows)
+    w = engine.resolve_weights(None)
+    pool = max(3 * top_k, top_k + 10)
+    initial_k = 3 * pool
+    r, comb, emb, lex = s.search_topm(q, initial_k, w)
+    R, Cc, E, L = orc.search(rows, q, initial_k, threads=4)
+    assert r.tobytes() == R.tobytes() and comb.tobytes() == Cc.tobytes()
+    # fake LLM relevance in [0,1] per candidate, blended exactly as :618-627
+    relev = rng.random(initial_k).astype(F32)
+    max_r = max(F32(relev.max()), np.finfo(F32).eps); max_i = max(F32(comb.max()), np.finfo(F32).eps)
+    blended = (F32(w.reranker) * (relev / max_r)).astype(F32) + (F32(w.initial) * (comb / max_i)).astype(F32)
+    order = np.argsort(-blended.astype(np.float64), kind="stable")[:pool]   # re-sort, truncate(top_k = pool)
+    cand_rows, cand_rel = r[order], blended[order].astype(F32)
+    sel = s.mmr(cand_rows, cand_rel, top_k, lam)
+    ref = orc.mmr(rows[cand_rows], cand_rel, top_k, lam, threads=4)
+    assert sel.tobytes() == ref.tobytes()
+    s.close()
