@@ -1,0 +1,100 @@
+"""The C++ host mirror (include/rlr_engine.hpp) above the C ABI: it must compile as plain C++17 with
+g++, fail loudly without a GPU, and on a B200 return the oracle's results from a chunks_{model}.json."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "rust-local-rag_b200")
+F32 = np.float32
+
+
+def _build_cli(tmp_path):
+    import rust_local_rag_b200  # noqa: F401
+    from rust_local_rag_b200 import _build
+    _build.build()
+    exe = os.path.join(tmp_path, "engine_cli")
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "cpp", "engine_cli.cpp"),
+           "-L" + PKG, "-l:librlr_b200.so", "-Wl,-rpath," + PKG]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+def _write_index(path, n, dim, seed=3):
+    rng = np.random.default_rng(seed)
+    chunks = {}
+    for i in range(n):
+        cid = f"chunk-{i:05d}"
+        chunks[cid] = {"id": cid, "document_name": f"doc{i % 5}.pdf", "text": "téxt \"quoted\"\n",
+                       "embedding": [float(x) for x in (rng.standard_normal(dim) * 1.7).astype(F32)],
+                       "chunk_index": i, "page_number": 1 + i % 4, "section": None if i % 2 else "Intro",
+                       "metadata": {"page_range": None, "sentence_range": None, "section_title": None, "token_count": 1,
+                                    "overlap_with_previous": 0}}
+    with open(path, "w") as f:
+        json.dump({"version": 2, "model": "m", "chunks": chunks, "needs_reindex": False,
+                   "document_hashes": {"doc0.pdf": "00"}}, f, indent=2)
+    return chunks
+
+
+def _gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_gpu(), reason="checks the no-device failure mode")
+def test_cpp_host_compiles_and_fails_loudly_without_gpu(tmp_path):
+    exe = _build_cli(str(tmp_path))
+    idx = os.path.join(tmp_path, "chunks_m.json")
+    _write_index(idx, 8, 16)
+    q = os.path.join(tmp_path, "q.f32")
+    np.ones(16, F32).tofile(q)
+    res = subprocess.run([exe, idx, q, "5", "0.3"], capture_output=True, text=True)
+    assert res.returncode == 12, (res.returncode, res.stderr)            # 10 + RLR_ERR_NO_DEVICE
+    assert "no CPU fallback" in res.stderr or "CUDA" in res.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_host_matches_oracle(tmp_path, orc):
+    exe = _build_cli(str(tmp_path))
+    n, dim = 900, 64
+    idx = os.path.join(tmp_path, "chunks_m.json")
+    chunks = _write_index(idx, n, dim)
+    ids = list(chunks)
+    rows = orc.normalize_rows(np.array([c["embedding"] for c in chunks.values()], F32))
+    qv = np.random.default_rng(9).standard_normal(dim).astype(F32)
+    qp = os.path.join(tmp_path, "q.f32")
+    qv.tofile(qp)
+    out = json.loads(subprocess.run([exe, idx, qp, "8", "0.5"], capture_output=True, text=True, check=True).stdout)
+    ref = orc.search_with_diversity(rows, qv, 8, 0.5, full_sort=True)
+    assert out["n"] == n and not out["needs_reindex"]
+    assert [r["chunk_id"] for r in out["results"]] == [ids[r] for r in ref[0]]
+    assert [r["score_bits"] for r in out["results"]] == ref[1].view(np.uint32).tolist()
+    assert [r["emb_bits"] for r in out["results"]] == ref[2].view(np.uint32).tolist()
+    assert [r["page"] for r in out["results"]] == [1 + int(r) % 4 for r in ref[0]]
+    cr, cs = orc.embedding_candidates(rows, qv, 7)
+    assert [c["chunk_id"] for c in out["candidates"]] == [ids[r] for r in cr]
+    assert [c["score_bits"] for c in out["candidates"]] == cs.view(np.uint32).tolist()
+    # replace_document("doc2.pdf", 37 new chunks): same SimpleRng stream regenerated here
+    out = json.loads(subprocess.run([exe, idx, qp, "8", "0.5", "replace", "doc2.pdf", "37", "42"], capture_output=True,
+                                    text=True, check=True).stdout)
+    st, vals = 42, []
+    for _ in range(37 * dim):
+        st = (st * 6364136223846793005 + 1) % (1 << 64)
+        vals.append(F32(F32(st >> 32) / F32(0xFFFFFFFF) * F32(2.0) - F32(1.0)))
+    new_rows = orc.normalize_rows(np.array(vals, F32).reshape(37, dim))
+    keep = [i for i in range(n) if chunks[ids[i]]["document_name"] != "doc2.pdf"]
+    host = {ids[i]: rows[i] for i in keep}
+    host.update({f"doc2.pdf#new{i}": new_rows[i] for i in range(37)})
+    assert out["n"] == len(host)
+    # row order after swap-removal is the engine's business: compare by chunk id through the oracle on any order
+    order = list(host)
+    ref = orc.search_with_diversity(np.array([host[k] for k in order], F32), qv, 8, 0.5, full_sort=True)
+    assert [r["score_bits"] for r in out["results"]] == ref[1].view(np.uint32).tolist()
+    assert sorted(r["chunk_id"] for r in out["results"]) == sorted(order[r] for r in ref[0])
