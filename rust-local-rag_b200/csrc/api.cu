@@ -168,6 +168,13 @@ struct rlr_ctx {
     uint64_t launches = 0;
     uint32_t n_lists_cap = 0;
     uint32_t search_flags = 0;      // RLR_SEARCH_F16 for the device-level entry points
+    // batched path workspace (allocated on first use, grown on demand)
+    void *batch_mem = nullptr;
+    size_t batch_bytes = 0;
+    float *h_batch_q = nullptr;     // pinned staging for the query batch
+    size_t h_batch_q_bytes = 0;
+    unsigned long long *h_batch_state = nullptr;
+    size_t h_batch_state_bytes = 0;
 };
 
 namespace {
@@ -181,6 +188,7 @@ void ctx_free(rlr_ctx *c)
     cudaFree(c->d_rel_in); cudaFree(c->d_p_in);
     cudaFreeHost(c->h_query); cudaFreeHost(c->h_lex_rows); cudaFreeHost(c->h_lex_norm);
     cudaFreeHost(c->h_result); cudaFreeHost(c->h_u32); cudaFreeHost(c->h_rel);
+    cudaFree(c->batch_mem); cudaFreeHost(c->h_batch_q); cudaFreeHost(c->h_batch_state);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     cudaGetLastError();
@@ -940,18 +948,12 @@ RLR_EXPORT int rlr_search_mmr(rlr_store *s, const float *query, uint32_t dim, ui
 // ---------------------------------------------------------------------------------
 namespace {
 
-struct BatchBufs {
+struct BatchBufs {                 // views into the ctx's batch workspace
     float *d_q32 = nullptr;
     void *d_q16 = nullptr;
     float *d_tau = nullptr;
     unsigned long long *d_state = nullptr, *d_app = nullptr;
     uint32_t *d_state_cnt = nullptr, *d_app_cnt = nullptr, *d_overflow = nullptr;
-    ~BatchBufs()
-    {
-        cudaFree(d_q32); cudaFree(d_q16); cudaFree(d_tau); cudaFree(d_state); cudaFree(d_app);
-        cudaFree(d_state_cnt); cudaFree(d_app_cnt); cudaFree(d_overflow);
-        cudaGetLastError();
-    }
 };
 
 constexpr uint32_t kBatchCap = 1024;      // appended candidates per query per phase
@@ -961,22 +963,21 @@ constexpr uint32_t kBatchRTile = 128;     // store rows per MMA tile (UMMA M)
 // GEMM + prune over row tiles [t0, t1); on candidate-list overflow the phase is split and retried
 // (the running top-m is only modified by the prune, so a failed GEMM pass leaves it intact).
 int batch_phase(rlr_store *s, const CUtensorMap *tmapQ, BatchBufs &b, uint32_t nq, uint32_t nq_pad, uint32_t m,
-                uint32_t t0, uint32_t t1, cudaStream_t st, uint32_t *launches)
+                uint32_t t0, uint32_t t1, cudaStream_t st, uint32_t *launches, uint32_t *h_flag /* pinned */)
 {
     CU_TRY(rlr::batch_gemm_launch(&s->tmap16, tmapQ, s->sm_count, static_cast<uint32_t>(s->n_rows),
                                   static_cast<uint32_t>(s->row_base), t0, t1, nq_pad, s->pitch16, b.d_tau, b.d_app,
                                   b.d_app_cnt, kBatchCap, b.d_overflow, st));
     ++*launches;
-    uint32_t h_over = 0;
-    CU_TRY(cudaMemcpyAsync(&h_over, b.d_overflow, sizeof h_over, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(h_flag, b.d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
-    if (h_over) {
+    if (*h_flag) {
         if (t1 - t0 <= 1) return fail(RLR_ERR_CUDA, "batch candidate list overflow on a single tile (internal error)");
         CU_TRY(cudaMemsetAsync(b.d_app_cnt, 0, nq_pad * sizeof(uint32_t), st));
         CU_TRY(cudaMemsetAsync(b.d_overflow, 0, sizeof(uint32_t), st));
         const uint32_t mid = t0 + (t1 - t0) / 2;
-        if (int rc = batch_phase(s, tmapQ, b, nq, nq_pad, m, t0, mid, st, launches)) return rc;
-        return batch_phase(s, tmapQ, b, nq, nq_pad, m, mid, t1, st, launches);
+        if (int rc = batch_phase(s, tmapQ, b, nq, nq_pad, m, t0, mid, st, launches, h_flag)) return rc;
+        return batch_phase(s, tmapQ, b, nq, nq_pad, m, mid, t1, st, launches, h_flag);
     }
     CU_TRY(rlr::batch_prune_launch(b.d_state, b.d_state_cnt, m, b.d_app, b.d_app_cnt, kBatchCap, b.d_tau, nq, st));
     ++*launches;
@@ -1024,14 +1025,40 @@ RLR_EXPORT int rlr_search_batch(rlr_store *s, const float *queries, uint32_t n_q
         if (!(flags & RLR_QUERY_PRENORMALIZED)) host_normalize(v, dim);
     }
     BatchBufs b;
-    CU_TRY(cudaMalloc(&b.d_q32, hq.size() * sizeof(float)));
-    CU_TRY(cudaMalloc(&b.d_q16, static_cast<size_t>(nq_pad) * s->pitch16 * 2));
-    CU_TRY(cudaMalloc(&b.d_tau, nq_pad * sizeof(float)));
-    CU_TRY(cudaMalloc(&b.d_state, static_cast<size_t>(nq_pad) * m_eff * 8));
-    CU_TRY(cudaMalloc(&b.d_app, static_cast<size_t>(nq_pad) * kBatchCap * 8));
-    CU_TRY(cudaMalloc(&b.d_state_cnt, nq_pad * sizeof(uint32_t)));
-    CU_TRY(cudaMalloc(&b.d_app_cnt, nq_pad * sizeof(uint32_t)));
-    CU_TRY(cudaMalloc(&b.d_overflow, sizeof(uint32_t)));
+    {
+        // one workspace allocation per ctx, grown on demand (a batch call is a few ms: no per-call cudaMalloc)
+        auto up = [](size_t x) { return (x + 255) & ~static_cast<size_t>(255); };
+        const size_t sz_q32 = up(hq.size() * sizeof(float)), sz_q16 = up(static_cast<size_t>(nq_pad) * s->pitch16 * 2);
+        const size_t sz_tau = up(nq_pad * sizeof(float)), sz_state = up(static_cast<size_t>(nq_pad) * m_eff * 8);
+        const size_t sz_app = up(static_cast<size_t>(nq_pad) * kBatchCap * 8), sz_cnt = up(nq_pad * sizeof(uint32_t));
+        const size_t total = sz_q32 + sz_q16 + sz_tau + sz_state + sz_app + 2 * sz_cnt + 256;
+        if (total > c->batch_bytes) {
+            cudaFree(c->batch_mem); c->batch_mem = nullptr; c->batch_bytes = 0;
+            CU_TRY(cudaMalloc(&c->batch_mem, total));
+            c->batch_bytes = total;
+        }
+        uint8_t *p = static_cast<uint8_t *>(c->batch_mem);
+        b.d_q32 = reinterpret_cast<float *>(p); p += sz_q32;
+        b.d_q16 = p; p += sz_q16;
+        b.d_tau = reinterpret_cast<float *>(p); p += sz_tau;
+        b.d_state = reinterpret_cast<unsigned long long *>(p); p += sz_state;
+        b.d_app = reinterpret_cast<unsigned long long *>(p); p += sz_app;
+        b.d_state_cnt = reinterpret_cast<uint32_t *>(p); p += sz_cnt;
+        b.d_app_cnt = reinterpret_cast<uint32_t *>(p); p += sz_cnt;
+        b.d_overflow = reinterpret_cast<uint32_t *>(p);
+        if (hq.size() * sizeof(float) > c->h_batch_q_bytes) {
+            cudaFreeHost(c->h_batch_q); c->h_batch_q = nullptr; c->h_batch_q_bytes = 0;
+            CU_TRY(cudaMallocHost(&c->h_batch_q, hq.size() * sizeof(float)));
+            c->h_batch_q_bytes = hq.size() * sizeof(float);
+        }
+        const size_t st_bytes = static_cast<size_t>(nq) * m_eff * 8 + nq * sizeof(uint32_t);
+        if (st_bytes > c->h_batch_state_bytes) {
+            cudaFreeHost(c->h_batch_state); c->h_batch_state = nullptr; c->h_batch_state_bytes = 0;
+            CU_TRY(cudaMallocHost(&c->h_batch_state, st_bytes));
+            c->h_batch_state_bytes = st_bytes;
+        }
+        memcpy(c->h_batch_q, hq.data(), hq.size() * sizeof(float));
+    }
     CUtensorMap tmapQ;
     {
         PFN_encodeTiled enc = get_encode();
@@ -1047,7 +1074,7 @@ RLR_EXPORT int rlr_search_batch(rlr_store *s, const float *queries, uint32_t n_q
     }
     const bool timed = flags & RLR_WANT_TIMINGS;
     uint32_t launches = 0;
-    CU_TRY(cudaMemcpyAsync(b.d_q32, hq.data(), hq.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(b.d_q32, c->h_batch_q, hq.size() * sizeof(float), cudaMemcpyHostToDevice, st));
     if (timed) CU_TRY(cudaEventRecord(c->ev[0], st));
     CU_TRY(rlr::batch_queries_to_half_launch(b.d_q32, dim, b.d_q16, s->pitch16, nq, nq_pad, st));
     CU_TRY(rlr::batch_init_launch(b.d_tau, b.d_state_cnt, b.d_app_cnt, nq, nq_pad, b.d_overflow, st));
@@ -1058,7 +1085,7 @@ RLR_EXPORT int rlr_search_batch(rlr_store *s, const float *queries, uint32_t n_q
     if (span * kBatchRTile > kBatchCap) span = kBatchCap / kBatchRTile;
     while (t0 < n_tiles) {
         const uint32_t t1 = std::min(n_tiles, t0 + span);
-        if (int rc = batch_phase(s, &tmapQ, b, nq, nq_pad, m_eff, t0, t1, st, &launches)) return rc;
+        if (int rc = batch_phase(s, &tmapQ, b, nq, nq_pad, m_eff, t0, t1, st, &launches, c->h_u32)) return rc;
         t0 = t1;
         span = std::max(span, 3 * t0);        // next phase: rows [t0, 4*t0)
     }
@@ -1072,10 +1099,10 @@ RLR_EXPORT int rlr_search_batch(rlr_store *s, const float *queries, uint32_t n_q
         launches += 2;
     }
     if (timed) CU_TRY(cudaEventRecord(c->ev[2], st));
-    std::vector<unsigned long long> h_state(static_cast<size_t>(nq) * m_eff);
-    std::vector<uint32_t> h_cnt(nq);
-    CU_TRY(cudaMemcpyAsync(h_state.data(), b.d_state, h_state.size() * 8, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(h_cnt.data(), b.d_state_cnt, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    unsigned long long *h_state = c->h_batch_state;
+    uint32_t *h_cnt = reinterpret_cast<uint32_t *>(h_state + static_cast<size_t>(nq) * m_eff);
+    CU_TRY(cudaMemcpyAsync(h_state, b.d_state, static_cast<size_t>(nq) * m_eff * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(h_cnt, b.d_state_cnt, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     for (uint32_t q = 0; q < nq; ++q) {
         const uint32_t n = std::min(h_cnt[q], m_eff);
