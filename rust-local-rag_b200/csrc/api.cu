@@ -963,21 +963,33 @@ constexpr uint32_t kBatchRTile = 128;     // store rows per MMA tile (UMMA M)
 // GEMM + prune over row tiles [t0, t1); on candidate-list overflow the phase is split and retried
 // (the running top-m is only modified by the prune, so a failed GEMM pass leaves it intact).
 int batch_phase(rlr_store *s, const CUtensorMap *tmapQ, BatchBufs &b, uint32_t nq, uint32_t nq_pad, uint32_t m,
-                uint32_t t0, uint32_t t1, cudaStream_t st, uint32_t *launches, uint32_t *h_flag /* pinned */)
+                uint32_t t0, uint32_t t1, cudaStream_t st, uint32_t *launches, uint32_t *h_flag /* pinned */,
+                bool checked)
 {
+    // tmapQ[0]: box {64, 256} for the 1-CTA kernel; tmapQ[1]: box {64, 128} for the cta_group::2 kernel,
+    // which needs an even first tile (tiles are handed out in 256-row pairs)
+    static const bool two_cta = getenv("RLR_BATCH_1CTA") == nullptr;
+    const uint32_t n_tiles_all = static_cast<uint32_t>((s->n_rows + kBatchRTile - 1) / kBatchRTile);
+    if (two_cta && (t0 % 2 == 0) && (t1 % 2 == 0 || t1 == n_tiles_all) && (t1 - t0) >= 2)
+        CU_TRY(rlr::batch_gemm2_launch(&s->tmap16, tmapQ + 1, s->sm_count, static_cast<uint32_t>(s->n_rows),
+                                       static_cast<uint32_t>(s->row_base), t0, t1, nq_pad, s->pitch16, b.d_tau, b.d_app,
+                                       b.d_app_cnt, kBatchCap, b.d_overflow, st));
+    else
     CU_TRY(rlr::batch_gemm_launch(&s->tmap16, tmapQ, s->sm_count, static_cast<uint32_t>(s->n_rows),
                                   static_cast<uint32_t>(s->row_base), t0, t1, nq_pad, s->pitch16, b.d_tau, b.d_app,
                                   b.d_app_cnt, kBatchCap, b.d_overflow, st));
     ++*launches;
-    CU_TRY(cudaMemcpyAsync(h_flag, b.d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
-    if (*h_flag) {
+    if (checked) {      // safe mode: look at the overflow flag after every phase (a host round trip each)
+        CU_TRY(cudaMemcpyAsync(h_flag, b.d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+    }
+    if (checked && *h_flag) {
         if (t1 - t0 <= 1) return fail(RLR_ERR_CUDA, "batch candidate list overflow on a single tile (internal error)");
-        CU_TRY(cudaMemsetAsync(b.d_app_cnt, 0, nq_pad * sizeof(uint32_t), st));
+        CU_TRY(cudaMemsetAsync(b.d_app_cnt, 0, static_cast<size_t>(nq_pad) * 32 * sizeof(uint32_t), st));
         CU_TRY(cudaMemsetAsync(b.d_overflow, 0, sizeof(uint32_t), st));
         const uint32_t mid = t0 + (t1 - t0) / 2;
-        if (int rc = batch_phase(s, tmapQ, b, nq, nq_pad, m, t0, mid, st, launches, h_flag)) return rc;
-        return batch_phase(s, tmapQ, b, nq, nq_pad, m, mid, t1, st, launches, h_flag);
+        if (int rc = batch_phase(s, tmapQ, b, nq, nq_pad, m, t0, mid, st, launches, h_flag, true)) return rc;
+        return batch_phase(s, tmapQ, b, nq, nq_pad, m, mid, t1, st, launches, h_flag, true);
     }
     CU_TRY(rlr::batch_prune_launch(b.d_state, b.d_state_cnt, m, b.d_app, b.d_app_cnt, kBatchCap, b.d_tau, nq, st));
     ++*launches;
@@ -1031,7 +1043,8 @@ RLR_EXPORT int rlr_search_batch(rlr_store *s, const float *queries, uint32_t n_q
         const size_t sz_q32 = up(hq.size() * sizeof(float)), sz_q16 = up(static_cast<size_t>(nq_pad) * s->pitch16 * 2);
         const size_t sz_tau = up(nq_pad * sizeof(float)), sz_state = up(static_cast<size_t>(nq_pad) * m_eff * 8);
         const size_t sz_app = up(static_cast<size_t>(nq_pad) * kBatchCap * 8), sz_cnt = up(nq_pad * sizeof(uint32_t));
-        const size_t total = sz_q32 + sz_q16 + sz_tau + sz_state + sz_app + 2 * sz_cnt + 256;
+        const size_t sz_acnt = up(static_cast<size_t>(nq_pad) * 32 * sizeof(uint32_t));   // one 128-byte line per counter
+        const size_t total = sz_q32 + sz_q16 + sz_tau + sz_state + sz_app + sz_cnt + sz_acnt + 256;
         if (total > c->batch_bytes) {
             cudaFree(c->batch_mem); c->batch_mem = nullptr; c->batch_bytes = 0;
             CU_TRY(cudaMalloc(&c->batch_mem, total));
@@ -1044,7 +1057,7 @@ RLR_EXPORT int rlr_search_batch(rlr_store *s, const float *queries, uint32_t n_q
         b.d_state = reinterpret_cast<unsigned long long *>(p); p += sz_state;
         b.d_app = reinterpret_cast<unsigned long long *>(p); p += sz_app;
         b.d_state_cnt = reinterpret_cast<uint32_t *>(p); p += sz_cnt;
-        b.d_app_cnt = reinterpret_cast<uint32_t *>(p); p += sz_cnt;
+        b.d_app_cnt = reinterpret_cast<uint32_t *>(p); p += sz_acnt;
         b.d_overflow = reinterpret_cast<uint32_t *>(p);
         if (hq.size() * sizeof(float) > c->h_batch_q_bytes) {
             cudaFreeHost(c->h_batch_q); c->h_batch_q = nullptr; c->h_batch_q_bytes = 0;
@@ -1059,18 +1072,20 @@ RLR_EXPORT int rlr_search_batch(rlr_store *s, const float *queries, uint32_t n_q
         }
         memcpy(c->h_batch_q, hq.data(), hq.size() * sizeof(float));
     }
-    CUtensorMap tmapQ;
+    CUtensorMap tmapQ[2];   // [0] box {64, 256} (1-CTA kernel), [1] box {64, 128} (cta_group::2 kernel)
     {
         PFN_encodeTiled enc = get_encode();
         if (!enc) return fail(RLR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
         const cuuint64_t gdim[2] = {s->pitch16, nq_pad};
         const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(s->pitch16) * 2};
-        const cuuint32_t box[2] = {64, kBatchQTile};
         const cuuint32_t estr[2] = {1, 1};
-        CUresult r = enc(&tmapQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b.d_q16, gdim, gstride, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(RLR_ERR_CUDA, "cuTensorMapEncodeTiled (queries) failed with CUresult %d", static_cast<int>(r));
+        for (int v = 0; v < 2; ++v) {
+            const cuuint32_t box[2] = {64, v == 0 ? kBatchQTile : kBatchQTile / 2};
+            CUresult r = enc(&tmapQ[v], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b.d_q16, gdim, gstride, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(RLR_ERR_CUDA, "cuTensorMapEncodeTiled (queries) failed with CUresult %d", static_cast<int>(r));
+        }
     }
     const bool timed = flags & RLR_WANT_TIMINGS;
     uint32_t launches = 0;
@@ -1079,15 +1094,29 @@ RLR_EXPORT int rlr_search_batch(rlr_store *s, const float *queries, uint32_t n_q
     CU_TRY(rlr::batch_queries_to_half_launch(b.d_q32, dim, b.d_q16, s->pitch16, nq, nq_pad, st));
     CU_TRY(rlr::batch_init_launch(b.d_tau, b.d_state_cnt, b.d_app_cnt, nq, nq_pad, b.d_overflow, st));
     launches += 2;
-    // geometrically growing phases: a phase over rows [a, 4a) appends ~3m candidates per query
+    // Geometrically growing phases.  tau is frozen during a phase, so a phase over rows [a, g*a)
+    // lets ~m*(g-1) rows per query through; g is chosen to keep that near 70 % of the list capacity.
+    // Attempt 0 enqueues all phases back to back and looks at the overflow flag once at the end;
+    // if any list overflowed (skewed data), attempt 1 redoes the batch checking (and splitting) per phase.
     const uint32_t n_tiles = static_cast<uint32_t>((s->n_rows + kBatchRTile - 1) / kBatchRTile);
-    uint32_t t0 = 0, span = std::max<uint32_t>(1, (2 * m_eff + kBatchRTile - 1) / kBatchRTile);
-    if (span * kBatchRTile > kBatchCap) span = kBatchCap / kBatchRTile;
-    while (t0 < n_tiles) {
-        const uint32_t t1 = std::min(n_tiles, t0 + span);
-        if (int rc = batch_phase(s, &tmapQ, b, nq, nq_pad, m_eff, t0, t1, st, &launches, c->h_u32)) return rc;
-        t0 = t1;
-        span = std::max(span, 3 * t0);        // next phase: rows [t0, 4*t0)
+    const uint32_t growth = std::min<uint32_t>(16, std::max<uint32_t>(2, 1 + (7 * kBatchCap) / (10 * m_eff)));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (attempt == 1) {
+            CU_TRY(rlr::batch_init_launch(b.d_tau, b.d_state_cnt, b.d_app_cnt, nq, nq_pad, b.d_overflow, st));
+            ++launches;
+        }
+        uint32_t t0 = 0, span = kBatchCap / kBatchRTile;          // first phase: cap rows, every row is kept
+        while (t0 < n_tiles) {
+            const uint32_t t1 = std::min(n_tiles, t0 + span);
+            if (int rc = batch_phase(s, tmapQ, b, nq, nq_pad, m_eff, t0, t1, st, &launches, c->h_u32, attempt == 1)) return rc;
+            t0 = t1;
+            span = ((attempt == 0 ? growth - 1 : 1) * t0 + 1) & ~1u;   // rows [t0, g*t0); even tile counts
+        }
+        if (attempt == 0) {
+            CU_TRY(cudaMemcpyAsync(c->h_u32, b.d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            if (c->h_u32[0] == 0) break;
+        }
     }
     if (timed) CU_TRY(cudaEventRecord(c->ev[1], st));
     if (flags & RLR_BATCH_EXACT_RESCORE) {

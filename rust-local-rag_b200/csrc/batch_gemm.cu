@@ -21,6 +21,9 @@
 // A second tiny kernel (batch_prune_kernel) merges the appended candidates into each query's
 // running top-M and raises tau[q]; the host runs the corpus in geometrically growing phases
 // so that the expected number of survivors per phase stays below the list capacity.
+#include <cstdio>
+#include <cstdlib>
+
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -40,6 +43,7 @@ constexpr uint32_t kBBytes = kBN * 128;   // 32 KB
 constexpr uint32_t kStageB = kABytes + kBBytes;
 constexpr int kBatchThreads = 256;
 constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kCntStride = 32;     // one 128-byte line per query counter: same-line L2 atomics serialise
 
 // ---- tcgen05 wrappers ----
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -100,11 +104,61 @@ __device__ __forceinline__ void tma_load_2d_nohint(uint32_t dst, const void *tma
                  : "memory");
 }
 
+// Epilogue filter for 32 accumulator columns of one store row: a branch-free pass mask first
+// (the tensor pipe is only ahead of the epilogue if the common "nothing survives" case costs a
+// few dozen instructions), then the rare survivors are appended to their queries' lists.
+__device__ __forceinline__ void epilogue_filter(const uint32_t (&v)[32], const float *tau32, uint32_t q0, bool row_ok,
+                                                uint32_t inv_row, unsigned long long *__restrict__ app_keys,
+                                                uint32_t *__restrict__ app_cnt, uint32_t cap, uint32_t *__restrict__ overflow)
+{
+    uint32_t mask = 0;
+#pragma unroll
+    for (int i4 = 0; i4 < 8; ++i4) {
+        const float4 t = *reinterpret_cast<const float4 *>(tau32 + i4 * 4);       // broadcast LDS.128
+        mask |= (__uint_as_float(v[i4 * 4 + 0]) >= t.x ? 1u : 0u) << (i4 * 4 + 0);
+        mask |= (__uint_as_float(v[i4 * 4 + 1]) >= t.y ? 1u : 0u) << (i4 * 4 + 1);
+        mask |= (__uint_as_float(v[i4 * 4 + 2]) >= t.z ? 1u : 0u) << (i4 * 4 + 2);
+        mask |= (__uint_as_float(v[i4 * 4 + 3]) >= t.w ? 1u : 0u) << (i4 * 4 + 3);
+    }
+    if (!row_ok) mask = 0;
+    const uint32_t colmask = __reduce_or_sync(0xffffffffu, mask);   // columns with a survivor in ANY lane
+    if (colmask == 0) return;
+    // Survivors: the 32 lanes of the warp hold 32 different rows of the SAME query column, so the
+    // appends of one column are aggregated into one atomicAdd per warp and land in consecutive slots.
+    const uint32_t lane = threadIdx.x & 31u;
+    // pass 1: one atomicAdd per (warp, column with survivors); the up-to-32 atomics are independent,
+    // so they are all in flight together (in the early, dense phases a serial chain of atomic round
+    // trips per thread was the whole cost)
+    uint32_t ballots[32], bases[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        ballots[i] = 0;
+        bases[i] = 0;
+        if (((colmask >> i) & 1u) == 0) continue;              // warp-uniform: most columns have no survivor
+        ballots[i] = __ballot_sync(0xffffffffu, (mask >> i) & 1u);
+        if (lane == static_cast<uint32_t>(__ffs(ballots[i]) - 1))
+            bases[i] = atomicAdd(app_cnt + static_cast<size_t>(q0 + i) * kCntStride, static_cast<uint32_t>(__popc(ballots[i])));
+    }
+    // pass 2: consecutive slots per column
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const uint32_t b = ballots[i];
+        if (b == 0) continue;                                   // warp-uniform
+        const uint32_t base = __shfl_sync(0xffffffffu, bases[i], __ffs(b) - 1);
+        if ((mask >> i) & 1u) {
+            const uint32_t slot = base + __popc(b & ((1u << lane) - 1u));
+            if (slot < cap) app_keys[static_cast<size_t>(q0 + i) * cap + slot] = (static_cast<unsigned long long>(ord_f32(__uint_as_float(v[i]))) << 32) | inv_row;
+            else *overflow = 1u;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kBatchThreads, 1)
 batch_gemm_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapQ,
                        uint32_t n_rows, uint32_t row_base, uint32_t tile0, uint32_t tile1, uint32_t nq_tiles,
                        uint32_t n_k, const float *__restrict__ tau, unsigned long long *__restrict__ app_keys,
-                       uint32_t *__restrict__ app_cnt, uint32_t cap, uint32_t *__restrict__ overflow)
+                       uint32_t *__restrict__ app_cnt, uint32_t cap, uint32_t *__restrict__ overflow,
+                       unsigned long long *dbg /* dev-only cycle counters, may be null */)
 {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -112,6 +166,7 @@ batch_gemm_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_c
     uint8_t *smem = smem_raw + pad;
     const uint32_t stages_addr = smem_u32(smem);
     uint8_t *ctrl = smem + kStagesB * kStageB;
+    long long dbg_wait_a = 0, dbg_wait_b = 0, dbg_work = 0, dbg_t0 = clock64();
     const uint32_t full_bar = smem_u32(ctrl);                 // [kStagesB]
     const uint32_t empty_bar = full_bar + kStagesB * 8;       // [kStagesB]
     const uint32_t tfull_bar = empty_bar + kStagesB * 8;      // [2]
@@ -162,11 +217,15 @@ batch_gemm_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_c
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (uint32_t rt = tile0 + blockIdx.x; rt < tile1; rt += gridDim.x)
                 for (uint32_t qt = 0; qt < nq_tiles; ++qt) {
+                    long long c0 = clock64();
                     mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1);      // epilogue has drained this accumulator
+                    dbg_wait_a += clock64() - c0;
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * kBN;
                     for (uint32_t kc = 0; kc < n_k; ++kc) {
+                        long long c1 = clock64();
                         mbar_wait(full_bar + stage * 8, phase);
+                        dbg_wait_b += clock64() - c1;
                         tc_fence_after();
                         const uint32_t a_addr = stages_addr + stage * kStageB;
                         const uint64_t da = make_desc(a_addr), db = make_desc(a_addr + kABytes);
@@ -180,6 +239,7 @@ batch_gemm_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_c
                     acc ^= 1;
                     if (acc == 0) acc_phase ^= 1;
                 }
+            if (dbg != nullptr && blockIdx.x == 0) { dbg[0] = dbg_wait_a; dbg[1] = dbg_wait_b; dbg[2] = clock64() - dbg_t0; }
         }
     } else if (warp >= 4) {
         // ------------------------------ epilogue ------------------------------
@@ -190,24 +250,19 @@ batch_gemm_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_c
             const bool row_ok = row_local < n_rows;
             const uint32_t inv_row = ~(row_base + row_local);
             for (uint32_t qt = 0; qt < nq_tiles; ++qt) {
+                long long c0 = clock64();
                 mbar_wait(tfull_bar + acc * 8, acc_phase);
+                long long c1 = clock64();
+                dbg_wait_a += c1 - c0;
                 tc_fence_after();
 #pragma unroll 1
                 for (uint32_t c = 0; c < kBN / 32; ++c) {
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((w * 32u) << 16) + acc * kBN + c * 32, v);
                     const uint32_t q0 = qt * kBN + c * 32;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float s = __uint_as_float(v[i]);
-                        if (row_ok && s >= tau_s[q0 + i]) {              // rare after the first phases
-                            const uint32_t q = q0 + i;
-                            const uint32_t slot = atomicAdd(app_cnt + q, 1u);
-                            if (slot < cap) app_keys[static_cast<size_t>(q) * cap + slot] = (static_cast<unsigned long long>(ord_f32(s)) << 32) | inv_row;
-                            else *overflow = 1u;
-                        }
-                    }
+                    epilogue_filter(v, tau_s + q0, q0, row_ok, inv_row, app_keys, app_cnt, cap, overflow);
                 }
+                dbg_work += clock64() - c1;
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar + acc * 8);
@@ -216,11 +271,187 @@ batch_gemm_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_c
             }
         }
     }
+    if (dbg != nullptr && blockIdx.x == 0 && tid == 128) { dbg[3] = dbg_wait_a; dbg[4] = dbg_work; }
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256-row x 256-query
+// tile.  Each CTA stages only ITS 128 store rows (A half) and ITS 128 queries (B half) -- the
+// pair's tensor cores read both halves -- so the L2->SM operand traffic per flop drops by a
+// third against the 1-CTA kernel (32 KB instead of 48 KB per k-chunk per CTA for the same
+// 128 x 256 x 64 of math per CTA).  The leader CTA (rank 0) issues the MMAs; every TMA load of
+// either CTA completes on the leader's `full` barrier; tcgen05.commit multicasts to both CTAs'
+// `empty` / `tmem_full` barriers; the peer's epilogue warps arrive remotely on the leader's
+// `tmem_empty` barrier.
+// ------------------------------------------------------------------------------------------
+constexpr int kStages2 = 6;
+constexpr uint32_t kHalfBBytes = 128 * 128;            // 128 queries x 128 B
+constexpr uint32_t kStage2 = kABytes + kHalfBBytes;    // 32 KB per CTA per k-chunk
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;            // clears the CTA-rank bit of a shared::cluster address
+constexpr uint32_t kIdesc2 = (1u << 4) | (static_cast<uint32_t>(kBN >> 3) << 17) | (static_cast<uint32_t>(256 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const void *tmap, int32_t x, int32_t y, uint32_t leader_bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(leader_bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar)   // arrives on the barrier at this offset in BOTH CTAs
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(static_cast<uint16_t>(3))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)
+batch_gemm2_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapQ,
+                        uint32_t n_rows, uint32_t row_base, uint32_t pair0, uint32_t pair1, uint32_t nq_tiles,
+                        uint32_t n_k, const float *__restrict__ tau, unsigned long long *__restrict__ app_keys,
+                        uint32_t *__restrict__ app_cnt, uint32_t cap, uint32_t *__restrict__ overflow)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+    uint8_t *smem = smem_raw + pad;
+    const uint32_t stages_addr = smem_u32(smem);
+    uint8_t *ctrl = smem + kStages2 * kStage2;
+    const uint32_t full_bar = smem_u32(ctrl);                 // [kStages2] (used in the leader)
+    const uint32_t empty_bar = full_bar + kStages2 * 8;       // [kStages2] (one per CTA)
+    const uint32_t tfull_bar = empty_bar + kStages2 * 8;      // [2]        (one per CTA)
+    const uint32_t tempty_bar = tfull_bar + 16;               // [2]        (used in the leader)
+    volatile uint32_t *s_tmem = reinterpret_cast<volatile uint32_t *>(ctrl + 160);
+    float *tau_s = reinterpret_cast<float *>(ctrl + 256);
+
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t pair = blockIdx.x >> 1, n_pairs_grid = gridDim.x >> 1;
+    const uint32_t nq_pad = nq_tiles * kBN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmapA);
+        tma_prefetch_desc(&tmapQ);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages2; ++s) { mbar_init(full_bar + s * 8, 1); mbar_init(empty_bar + s * 8, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + a * 8, 1); mbar_init(tempty_bar + a * 8, 8); }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(const_cast<uint32_t *>(s_tmem))), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    for (uint32_t i = tid; i < nq_pad; i += kBatchThreads) tau_s[i] = tau[i];
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                        // both CTAs' barriers + TMEM exist
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // ---------------- TMA producer (both CTAs; completion on the LEADER's full barrier) ----------------
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t rp = pair0 + pair; rp < pair1; rp += n_pairs_grid)
+                for (uint32_t qt = 0; qt < nq_tiles; ++qt)
+                    for (uint32_t kc = 0; kc < n_k; ++kc) {
+                        mbar_wait(empty_bar + stage * 8, phase ^ 1);
+                        const uint32_t lead_full = (full_bar + stage * 8) & kPeerMask;
+                        if (rank == 0) mbar_arrive_expect_tx(full_bar + stage * 8, 2 * kStage2);   // both CTAs' bytes
+                        const uint32_t a_dst = stages_addr + stage * kStage2;
+                        tma_load_2d_2sm(a_dst, &tmapA, static_cast<int32_t>(kc * kBK), static_cast<int32_t>((rp * 2 + rank) * kBM), lead_full);
+                        tma_load_2d_2sm(a_dst + kABytes, &tmapQ, static_cast<int32_t>(kc * kBK), static_cast<int32_t>(qt * kBN + rank * 128), lead_full);
+                        if (++stage == kStages2) { stage = 0; phase ^= 1; }
+                    }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer (leader CTA only) ----------------
+        if (rank == 0 && lane == 0) {
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (uint32_t rp = pair0 + pair; rp < pair1; rp += n_pairs_grid)
+                for (uint32_t qt = 0; qt < nq_tiles; ++qt) {
+                    mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1);       // both CTAs' epilogues drained it
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * kBN;
+                    for (uint32_t kc = 0; kc < n_k; ++kc) {
+                        mbar_wait(full_bar + stage * 8, phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = stages_addr + stage * kStage2;
+                        const uint64_t da = make_desc(a_addr), db = make_desc(a_addr + kABytes);
+#pragma unroll
+                        for (uint32_t k = 0; k < kBK / 16; ++k)
+                            tc_mma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, kIdesc2, (kc | k) != 0 ? 1u : 0u);
+                        tc_commit_2sm(empty_bar + stage * 8);             // frees this stage in BOTH CTAs
+                        if (++stage == kStages2) { stage = 0; phase ^= 1; }
+                    }
+                    tc_commit_2sm(tfull_bar + acc * 8);                   // accumulator ready in BOTH CTAs
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1;
+                }
+        }
+    } else if (warp >= 4) {
+        // ---------------- epilogue (each CTA: its own 128 rows) ----------------
+        const uint32_t w = warp - 4;
+        uint32_t acc = 0, acc_phase = 0;
+        for (uint32_t rp = pair0 + pair; rp < pair1; rp += n_pairs_grid) {
+            const uint32_t row_local = (rp * 2 + rank) * kBM + w * 32 + lane;
+            const bool row_ok = row_local < n_rows;
+            const uint32_t inv_row = ~(row_base + row_local);
+            for (uint32_t qt = 0; qt < nq_tiles; ++qt) {
+                mbar_wait(tfull_bar + acc * 8, acc_phase);
+                tc_fence_after();
+#pragma unroll 1
+                for (uint32_t c = 0; c < kBN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((w * 32u) << 16) + acc * kBN + c * 32, v);
+                    const uint32_t q0 = qt * kBN + c * 32;
+                    epilogue_filter(v, tau_s + q0, q0, row_ok, inv_row, app_keys, app_cnt, cap, overflow);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster((tempty_bar + acc * 8) & kPeerMask);   // leader's barrier
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                        // nobody touches the peer after this
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
@@ -237,7 +468,7 @@ batch_prune_kernel(unsigned long long *__restrict__ state_keys, uint32_t *__rest
     const uint32_t q = blockIdx.x, t = threadIdx.x;
     if (q >= nq) return;
     const uint32_t ns = state_cnt[q];
-    uint32_t na = app_cnt[q];
+    uint32_t na = app_cnt[static_cast<size_t>(q) * kCntStride];
     if (na > cap) na = cap;
     const uint32_t n = ns + na;
     uint32_t n2 = 1;
@@ -256,7 +487,7 @@ batch_prune_kernel(unsigned long long *__restrict__ state_keys, uint32_t *__rest
     for (uint32_t i = t; i < keep; i += 128) state_keys[static_cast<size_t>(q) * m + i] = keys[i];
     if (t == 0) {
         state_cnt[q] = keep;
-        app_cnt[q] = 0;
+        app_cnt[static_cast<size_t>(q) * kCntStride] = 0;
         if (keep >= m) tau[q] = key_score(keys[m - 1]);
     }
 }
@@ -299,7 +530,7 @@ __global__ void batch_init_kernel(float *tau, uint32_t *state_cnt, uint32_t *app
     if (i < nq_pad) {
         tau[i] = i < nq ? -INFINITY : INFINITY;     // padded queries never pass
         state_cnt[i] = 0;
-        app_cnt[i] = 0;
+        app_cnt[static_cast<size_t>(i) * kCntStride] = 0;
     }
     if (i == 0) *overflow = 0;
 }
@@ -310,7 +541,25 @@ size_t batch_smem_bytes(uint32_t nq_pad) { return kStagesB * kStageB + 256 + nq_
 
 cudaError_t batch_configure(int smem_optin)
 {
-    return cudaFuncSetAttribute(batch_gemm_topm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+    cudaError_t e = cudaFuncSetAttribute(batch_gemm_topm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(batch_gemm2_topm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+}
+
+// 2-CTA variant: tiles are handed out in PAIRS of 128-row tiles; tile0 must be even
+cudaError_t batch_gemm2_launch(const CUtensorMap *tmapA, const CUtensorMap *tmapQ128, int sm_count, uint32_t n_rows,
+                               uint32_t row_base, uint32_t tile0, uint32_t tile1, uint32_t nq_pad, uint32_t pitch16,
+                               const float *tau, unsigned long long *app_keys, uint32_t *app_cnt, uint32_t cap,
+                               uint32_t *overflow, cudaStream_t st)
+{
+    if (tile1 <= tile0) return cudaSuccess;
+    const uint32_t pair0 = tile0 / 2, pair1 = (tile1 + 1) / 2;
+    uint32_t clusters = static_cast<uint32_t>(sm_count / 2);
+    if (clusters > pair1 - pair0) clusters = pair1 - pair0;
+    const size_t smem = kStages2 * kStage2 + 256 + nq_pad * sizeof(float) + 1024;
+    batch_gemm2_topm_kernel<<<clusters * 2, kBatchThreads, smem, st>>>(
+        *tmapA, *tmapQ128, n_rows, row_base, pair0, pair1, nq_pad / kBN, pitch16 / kBK, tau, app_keys, app_cnt, cap, overflow);
+    return cudaGetLastError();
 }
 
 cudaError_t batch_init_launch(float *tau, uint32_t *state_cnt, uint32_t *app_cnt, uint32_t nq, uint32_t nq_pad,
@@ -335,8 +584,18 @@ cudaError_t batch_gemm_launch(const CUtensorMap *tmapA, const CUtensorMap *tmapQ
     if (tile1 <= tile0) return cudaSuccess;
     const uint32_t tiles = tile1 - tile0;
     if (static_cast<uint32_t>(grid) > tiles) grid = static_cast<int>(tiles);
+    unsigned long long *dbg = nullptr;
+    if (getenv("RLR_DEBUG_BATCH_TRACE") && tiles > 2000) { cudaMalloc(&dbg, 64); cudaMemset(dbg, 0, 64); }
     batch_gemm_topm_kernel<<<grid, kBatchThreads, batch_smem_bytes(nq_pad), st>>>(
-        *tmapA, *tmapQ, n_rows, row_base, tile0, tile1, nq_pad / kBN, pitch16 / kBK, tau, app_keys, app_cnt, cap, overflow);
+        *tmapA, *tmapQ, n_rows, row_base, tile0, tile1, nq_pad / kBN, pitch16 / kBK, tau, app_keys, app_cnt, cap, overflow, dbg);
+    if (dbg) {
+        unsigned long long h[8];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, dbg, 64, cudaMemcpyDeviceToHost);
+        cudaFree(dbg);
+        fprintf(stderr, "[batch trace tiles=%u] CTA0 MMA thread: wait tmem_empty %llu, wait smem_full %llu, total %llu cycles; "
+                        "epilogue warp: wait tmem_full %llu, work %llu cycles\n", tiles, h[0], h[1], h[2], h[3], h[4]);
+    }
     return cudaGetLastError();
 }
 

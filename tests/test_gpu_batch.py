@@ -78,3 +78,31 @@ def test_batch_needs_f16_copy():
     with pytest.raises(B.RlrError):
         s.search_batch(np.ones((2, 64), F32), 3)
     s.close()
+
+
+def test_batch_on_skewed_rows_takes_the_checked_path():
+    """Scores that grow with the row index make every later row beat the frozen thresholds: the
+    unchecked fast pass overflows its candidate lists and the batch is redone phase by phase."""
+    import rust_local_rag_b200  # noqa: F401
+    from rust_local_rag_b200 import binding as B, engine
+    from oracle import orc
+    n, dim, nq, m = 30000, 64, 40, 100
+    rng = np.random.default_rng(1)
+    q = orc.normalize(rng.standard_normal(dim).astype(F32))
+    noise = rng.standard_normal((n, dim)).astype(F32)
+    scale = (np.arange(n, dtype=F32)[::-1] / F32(n))[:, None]            # last rows are the most similar to q
+    rows = orc.normalize_rows(q[None, :] + scale * noise)
+    qs = np.tile(q, (nq, 1)) + 0.01 * rng.standard_normal((nq, dim)).astype(F32)
+    s = engine.DeviceStore.from_rows(rows, flags=B.RLR_STORE_KEEP_F16)
+    got_rows, got_scores, got_n = s.search_batch(qs, m)
+    rows16 = rows.astype(np.float16).astype(F32)
+    q16 = np.stack([orc.normalize(x) for x in qs]).astype(np.float16).astype(F32)
+    ref, order = _ref_topm(rows16, q16, m)
+    assert (got_n == m).all()
+    for qi in range(nq):
+        r = got_rows[qi]
+        assert np.abs(got_scores[qi].astype(np.float64) - ref[qi, r]).max() <= TOL
+        cut = ref[qi, order[qi, m - 1]]
+        assert all(ref[qi, x] >= cut - 2 * TOL for x in r.tolist())
+        assert all(ref[qi, x] <= cut + 2 * TOL for x in set(order[qi].tolist()) - set(r.tolist()))
+    s.close()
