@@ -12,9 +12,10 @@ from rust_local_rag_b200 import binding as B, engine
 lib = B.load()
 sizes = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [1_000_000]
 dim = int(sys.argv[2]) if len(sys.argv) > 2 else 768
+f16 = len(sys.argv) > 3 and sys.argv[3] == "f16"
 import torch
 for n in sizes:
-    s = engine.DeviceStore.synthetic(n, dim, kind=1)
+    s = engine.DeviceStore.synthetic(n, dim, kind=1, flags=B.RLR_STORE_F16_ONLY if f16 else 0)
     ctx = C.c_void_p()
     B.check(lib.rlr_ctx_create(s.handle, C.byref(ctx)))
     q = torch.zeros(4096 + 64, device="cuda")
@@ -23,8 +24,8 @@ for n in sizes:
     for m in (300, 900):
         ms = C.c_float()
         B.check(lib.rlr_time_scan(ctx, C.c_void_p(q.data_ptr()), m, 20, None, C.byref(ms)))
-        gb = n * dim * 4 / 1e9
-        print(f"n={n} dim={dim} m={m}: scan {ms.value:.4f} ms  {gb / ms.value * 1e3:.1f} GB/s")
+        gb = n * dim * (2 if f16 else 4) / 1e9
+        print(f"n={n} dim={dim} {'f16' if f16 else 'f32'} m={m}: scan {ms.value:.4f} ms  {gb / ms.value * 1e3:.1f} GB/s")
     w = engine.ResolvedWeights(np.float32(0.7), np.float32(0.3), np.float32(0.7), np.float32(0.3))
     qh = q[:dim].cpu().numpy()
     for _ in range(3):
