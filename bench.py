@@ -55,10 +55,20 @@ def workload_config(a, world):
         "queries": N_QUERIES,
         "l2": "inputs larger than L2 (store shard >= 3.8 GB vs 126 MB L2)",
         "parallelism": f"rows/{world}",
-        "exchange": "NCCL all-gather of per-GPU top-300 lists; MMR on rank 0 reads pool rows from peer HBM (CUDA IPC / NVLink)"
-                    if world > 1 and os.environ.get("RLR_DIST_PEERS", "1") == "1" else
-                    ("NCCL all-gather + int32 reduce of pool rows" if world > 1 else "none (single GPU)"),
+        "exchange": {"fused": "fused: each GPU's scan kernel stores its top-300 list into rank 0's HBM mailbox (NVLink peer "
+                              "stores + release flag, no collective call); rank 0 merges in a waiting kernel and its MMR reads "
+                              "pool rows from peer HBM (CUDA IPC); rank 0 owns fewer rows so that its scan + merge/MMR tail "
+                              "equals the other ranks' scan (tail-balanced sharding)",
+                     "peers": "NCCL all-gather of per-GPU top-300 lists; MMR on rank 0 reads pool rows from peer HBM (CUDA IPC / NVLink)",
+                     "reduce": "NCCL all-gather + int32 reduce of pool rows"}[dist_mode()] if world > 1 else "none (single GPU)",
     }
+
+
+def dist_mode():
+    m = os.environ.get("RLR_DIST_MODE", "fused")
+    if m not in ("fused", "peers", "reduce"):
+        raise SystemExit(f"RLR_DIST_MODE={m!r}: expected fused | peers | reduce")
+    return m
 
 
 # ----------------------------------------------------------------------------------------
@@ -209,10 +219,23 @@ def run_b200(a):
         group = dist.group.WORLD
     lib = B.load()
 
+    mode = dist_mode() if world > 1 else "single"
+    p_cap = max(3 * a.top_k, a.top_k + 10, 1)
+    w_e, w_l = float(np.float32(0.7)), float(np.float32(0.3))
+
+    def build_shard(plan):
+        st = engine.DeviceStore.synthetic(plan.n_local, a.dim, kind=B.RLR_SYNTH_CLUSTERED, seed=SEED_STORE,
+                                          centroid_seed=SEED_CENTROID, n_clusters=N_CLUSTERS, sigma=SIGMA,
+                                          device=local_rank, row_base=plan.row0)
+        be = rdist.CudaBackend(st, dev)
+        if mode in ("fused", "peers"):
+            be.open_peers(group, plan)       # rank 0 maps the peer shards (CUDA IPC over NVLink)
+        if mode == "fused":
+            be.open_mailbox(group, m_cap=p_cap, ring=4)
+        return st, be, rdist.Buffers(world, p_cap, st.info().pitch, dev)
+
     plan = rdist.ShardPlan(a.rows, world, rank)
-    store = engine.DeviceStore.synthetic(plan.n_local, a.dim, kind=B.RLR_SYNTH_CLUSTERED, seed=SEED_STORE,
-                                         centroid_seed=SEED_CENTROID, n_clusters=N_CLUSTERS, sigma=SIGMA,
-                                         device=local_rank, row_base=plan.row0)
+    store, backend, bufs = build_shard(plan)
     info = store.info()
     pitch = info.pitch
     # queries: same generator, different noise seed (clustered around the same centroids)
@@ -226,12 +249,45 @@ def run_b200(a):
     q_pinned[:, :a.dim] = torch.from_numpy(q_host)
     q_dev = q_pinned.to(dev)
 
-    backend = rdist.CudaBackend(store, dev)
-    if world > 1 and os.environ.get("RLR_DIST_PEERS", "1") == "1":
-        backend.open_peers(group, plan)      # rank 0 maps the peer shards (CUDA IPC over NVLink)
-    p_cap = max(3 * a.top_k, a.top_k + 10, 1)
-    bufs = rdist.Buffers(world, p_cap, pitch, dev)
-    w_e, w_l = float(np.float32(0.7)), float(np.float32(0.3))
+    balance = None
+    if mode == "fused" and os.environ.get("RLR_DIST_BALANCE", "1") == "1":
+        # tail-balanced sharding: measure rank 0's merge + MMR tail (flags of a finished query are
+        # already set, so re-running the two steps times the tail alone) and the local scan rate,
+        # then give rank 0 that many fewer rows and rebuild the shards.
+        res0 = rdist.sharded_search(backend, group, bufs, q_dev[0], a.top_k, a.diversity, w_e, w_l)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)
+        cal = torch.zeros(2, dtype=torch.float64, device=dev)
+        if rank == 0:
+            lam = rdist.clamp_lambda(a.diversity)
+            m = rdist.pool_size(a.top_k, lam)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
+            for it in range(reps + 3):
+                if it == 3:
+                    e0.record()
+                backend.mailbox_merge(backend._seq, m, bufs.pool[:m], bufs.pool_n)
+                if lam != 0.0:
+                    backend.mmr_peers(bufs.pool[:m], bufs.pool_n, m, a.top_k, lam, bufs.sel_pos, bufs.sel_n, bufs.result)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            tail_ms = e0.elapsed_time(e1) / reps
+            iso = C.c_float(0)
+            B.check(lib.rlr_time_scan(backend.ctx, C.c_void_p(q_dev[0].data_ptr()), p_cap, 10,
+                                      C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), C.byref(iso)))
+            cal[0], cal[1] = tail_ms, plan.n_local / iso.value
+        dist.broadcast(cal, 0, group=group)
+        tail_ms, rows_per_ms = float(cal[0].item()), float(cal[1].item())
+        head = rdist.ShardPlan.balanced_head_rows(a.rows, world, tail_ms * rows_per_ms)
+        balance = {"tail_ms": tail_ms, "scan_rows_per_ms": rows_per_ms, "rank0_rows": head,
+                   "other_rank_rows": (a.rows - head) // (world - 1)}
+        backend.close(group)
+        dist.barrier(group=group)
+        store.close()
+        del bufs
+        dist.barrier(group=group)
+        plan = rdist.ShardPlan(a.rows, world, rank, head_rows=head)
+        store, backend, bufs = build_shard(plan)
     result_host = torch.zeros((p_cap, 2), dtype=torch.int64).pin_memory()
     n_host = torch.zeros(1, dtype=torch.int32).pin_memory()
     q_stage = torch.zeros(qcap, dtype=torch.float32, device=dev)
@@ -355,15 +411,22 @@ def run_b200(a):
             "cpu_baseline": cpu,
             "clocks": clocks.summary(),
         }
+        if balance is not None:
+            line["config"]["tail_balance"] = balance
         if stage_samples:
             m = [statistics.mean(x[j] for x in stage_samples) for j in range(4)]
             line["stage_ms"] = {"scan": m[0], "merge": m[1], "mmr": m[2], "device_total": m[3]}
         print(json.dumps(line), flush=True)
-    backend.close()
+    timeouts = backend.mailbox_status() if mode == "fused" else 0
+    backend.close(group)
+    if world > 1:
+        dist.barrier(group=group)
     store.close()
     if world > 1:
         dist.barrier(group=group)
         dist.destroy_process_group()
+    if timeouts:
+        raise SystemExit(f"rank {rank}: a mailbox wait timed out (status {timeouts}); the numbers above are invalid")
 
 
 if __name__ == "__main__":

@@ -341,6 +341,31 @@ int rlr_mmr_peers_async(rlr_ctx *c, rlr_peer_set *p, const void *d_cands, const 
                         uint32_t top_k, float lambda, void *d_sel_pos, void *d_sel_n,
                         void *d_result /* nullable */, void *stream);
 
+/* ---- fused exchange: the scan kernel delivers its list into the root GPU's HBM ------------
+ * Replaces the all-gather of SURVEY.md 8(e): the root rank owns a mailbox (a ring of slots,
+ * one list of m_cap records per rank and slot); every other rank maps it through CUDA IPC.
+ * rlr_topm_post_async runs the same scan + top-m as rlr_topm_async, but the kernel's last CTA
+ * stores the merged list straight into slot (seq % ring) of the mailbox -- NVLink peer stores
+ * issued by the compute kernel itself -- and then publishes `seq` with a system-scope release.
+ * rlr_mailbox_merge_async (root only) waits inside its kernel for the n_ranks flags of `seq`,
+ * merges the lists to the global best m and frees the slot.  No collective call, no host
+ * round trip; ranks other than the root are done as soon as their scan is.
+ * Sequence numbers start at 1, increase by 1 per query and must agree across ranks; a slot is
+ * reused after `ring` queries, and a posting kernel waits (bounded, 4 s) for the root to have
+ * consumed it.  rlr_mailbox_status reads a sticky word: non-zero once any wait timed out. */
+typedef struct rlr_mailbox rlr_mailbox;
+int rlr_mailbox_create(int device, uint32_t n_ranks, uint32_t m_cap, uint32_t ring, rlr_mailbox **out);
+int rlr_mailbox_ipc_export(const rlr_mailbox *mb, void *handle_out /* 64 bytes */);
+int rlr_mailbox_open(int device, const void *handle /* 64 bytes */, uint32_t n_ranks, uint32_t m_cap,
+                     uint32_t ring, rlr_mailbox **out);
+int rlr_mailbox_close(rlr_mailbox *mb);
+int rlr_mailbox_status(rlr_mailbox *mb, uint32_t *out);
+int rlr_topm_post_async(rlr_ctx *c, rlr_mailbox *mb, uint32_t my_rank, uint64_t seq, const void *d_query,
+                        float w_embed, float w_lex, const void *d_lex_rows, const void *d_lex_norm,
+                        uint32_t n_lex, uint32_t m, void *stream);
+int rlr_mailbox_merge_async(rlr_ctx *c, rlr_mailbox *mb, uint64_t seq, uint32_t m, void *d_out,
+                            void *d_out_n, void *stream);
+
 /* fused single-GPU search_with_diversity on the device: results stay in HBM.
  * d_result: rlr_cand[max(top_k,1)] in selection order, d_result_n: u32. */
 int rlr_search_mmr_async(rlr_ctx *c, const void *d_query, uint32_t top_k, float diversity_factor,

@@ -25,6 +25,7 @@ RLR_QUERY_PRENORMALIZED = 0x1
 RLR_WANT_TIMINGS = 0x2
 RLR_SEARCH_F16 = 0x4
 RLR_BATCH_EXACT_RESCORE = 0x8
+RLR_IPC_HANDLE_BYTES = 64
 RLR_SYNTH_IID = 0
 RLR_SYNTH_CLUSTERED = 1
 
@@ -103,6 +104,13 @@ PROTOTYPES = {
     "rlr_peer_set_open": (_int, [_vp, _u32, _u32, _vp, _vp, _vp, _u32, C.POINTER(_vp)]),
     "rlr_peer_set_close": (_int, [_vp]),
     "rlr_mmr_peers_async": (_int, [_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp, _vp]),
+    "rlr_mailbox_create": (_int, [_int, _u32, _u32, _u32, C.POINTER(_vp)]),
+    "rlr_mailbox_ipc_export": (_int, [_vp, _vp]),
+    "rlr_mailbox_open": (_int, [_int, _vp, _u32, _u32, _u32, C.POINTER(_vp)]),
+    "rlr_mailbox_close": (_int, [_vp]),
+    "rlr_mailbox_status": (_int, [_vp, _pu32]),
+    "rlr_topm_post_async": (_int, [_vp, _vp, _u32, _u64, _vp, _f32, _f32, _vp, _vp, _u32, _u32, _vp]),
+    "rlr_mailbox_merge_async": (_int, [_vp, _vp, _u64, _u32, _vp, _vp, _vp]),
     "rlr_search_mmr_async": (_int, [_vp, _vp, _u32, _f32, _f32, _f32, _vp, _vp, _vp]),
     "rlr_ctx_set_flags": (_int, [_vp, _u32]),
     "rlr_ctx_launch_count": (_int, [_vp, C.POINTER(_u64)]),

@@ -1388,6 +1388,170 @@ RLR_EXPORT int rlr_mmr_peers_async(rlr_ctx *c, rlr_peer_set *p, const void *d_ca
     return RLR_OK;
 }
 
+// ---------------------------------------------------------------------------------
+// fused exchange: scan kernels post their lists straight into the root GPU's mailbox
+// ---------------------------------------------------------------------------------
+struct rlr_mailbox {
+    int device = 0;
+    bool owner = false;
+    uint32_t n_ranks = 0, m_cap = 0, ring = 0;
+    uint8_t *base = nullptr;          // root's allocation (local on the root, an IPC mapping elsewhere)
+    uint32_t *d_status = nullptr;     // local
+    size_t bytes = 0;
+    // layout: [0] consumed u64 | [128] flags[ring][n_ranks] u64 | counts[ring][n_ranks] u32 | (4 KB aligned) lists
+    size_t flags_off() const { return 128; }
+    size_t counts_off() const { return flags_off() + static_cast<size_t>(ring) * n_ranks * 8; }
+    size_t lists_off() const { return (counts_off() + static_cast<size_t>(ring) * n_ranks * 4 + 4095) & ~static_cast<size_t>(4095); }
+    size_t total() const { return lists_off() + static_cast<size_t>(ring) * n_ranks * m_cap * sizeof(rlr_cand); }
+    unsigned long long *consumed() const { return reinterpret_cast<unsigned long long *>(base); }
+    unsigned long long *flag(uint32_t slot, uint32_t r) const { return reinterpret_cast<unsigned long long *>(base + flags_off()) + static_cast<size_t>(slot) * n_ranks + r; }
+    uint32_t *count(uint32_t slot, uint32_t r) const { return reinterpret_cast<uint32_t *>(base + counts_off()) + static_cast<size_t>(slot) * n_ranks + r; }
+    rlr_cand *list(uint32_t slot, uint32_t r) const { return reinterpret_cast<rlr_cand *>(base + lists_off()) + (static_cast<size_t>(slot) * n_ranks + r) * m_cap; }
+};
+
+namespace {
+int mailbox_check_shape(uint32_t n_ranks, uint32_t m_cap, uint32_t ring)
+{
+    if (n_ranks == 0 || n_ranks > rlr::kMaxPeers) return fail(RLR_ERR_INVALID_ARG, "n_ranks %u not in 1..%d", n_ranks, rlr::kMaxPeers);
+    if (m_cap == 0 || m_cap > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "m_cap %u not in 1..%d", m_cap, RLR_MAX_M);
+    if (ring < 2 || ring > 64) return fail(RLR_ERR_INVALID_ARG, "ring %u not in 2..64", ring);
+    return RLR_OK;
+}
+} // namespace
+
+RLR_EXPORT int rlr_mailbox_create(int device, uint32_t n_ranks, uint32_t m_cap, uint32_t ring, rlr_mailbox **out)
+{
+    if (!out) return fail(RLR_ERR_INVALID_ARG, "out is NULL");
+    if (int rc = mailbox_check_shape(n_ranks, m_cap, ring)) return rc;
+    if (int rc = ensure_device(device)) return rc;
+    rlr_mailbox *mb = new rlr_mailbox();
+    mb->device = device; mb->owner = true; mb->n_ranks = n_ranks; mb->m_cap = m_cap; mb->ring = ring;
+    mb->bytes = mb->total();
+    cudaError_t e = cudaMalloc(&mb->base, mb->bytes);
+    if (e == cudaSuccess) e = cudaMemset(mb->base, 0, mb->bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&mb->d_status, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(mb->d_status, 0, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(mb->base); cudaFree(mb->d_status);
+        delete mb;
+        return fail(e == cudaErrorMemoryAllocation ? RLR_ERR_OOM : RLR_ERR_CUDA, "mailbox allocation failed: %s", cudaGetErrorString(e));
+    }
+    *out = mb;
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_mailbox_ipc_export(const rlr_mailbox *mb, void *handle_out)
+{
+    if (!mb || !handle_out) return fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    if (!mb->owner) return fail(RLR_ERR_INVALID_ARG, "only the creating (root) rank can export a mailbox");
+    CU_TRY(cudaSetDevice(mb->device));
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, mb->base));
+    memcpy(handle_out, &h, sizeof h);
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_mailbox_open(int device, const void *handle, uint32_t n_ranks, uint32_t m_cap, uint32_t ring,
+                                rlr_mailbox **out)
+{
+    if (!handle || !out) return fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    if (int rc = mailbox_check_shape(n_ranks, m_cap, ring)) return rc;
+    if (int rc = ensure_device(device)) return rc;
+    rlr_mailbox *mb = new rlr_mailbox();
+    mb->device = device; mb->owner = false; mb->n_ranks = n_ranks; mb->m_cap = m_cap; mb->ring = ring;
+    mb->bytes = mb->total();
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e == cudaSuccess) { mb->base = static_cast<uint8_t *>(p); e = cudaMalloc(&mb->d_status, sizeof(uint32_t)); }
+    if (e == cudaSuccess) e = cudaMemset(mb->d_status, 0, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (mb->base) cudaIpcCloseMemHandle(mb->base);
+        cudaFree(mb->d_status);
+        delete mb;
+        return fail(RLR_ERR_CUDA, "opening the root's mailbox failed: %s", cudaGetErrorString(e));
+    }
+    *out = mb;
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_mailbox_close(rlr_mailbox *mb)
+{
+    if (!mb) return RLR_OK;
+    cudaSetDevice(mb->device);
+    if (mb->owner) cudaFree(mb->base);
+    else if (mb->base) cudaIpcCloseMemHandle(mb->base);
+    cudaFree(mb->d_status);
+    cudaGetLastError();
+    delete mb;
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_mailbox_status(rlr_mailbox *mb, uint32_t *out)
+{
+    if (!mb || !out) return fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    CU_TRY(cudaSetDevice(mb->device));
+    CU_TRY(cudaMemcpy(out, mb->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_topm_post_async(rlr_ctx *c, rlr_mailbox *mb, uint32_t my_rank, uint64_t seq, const void *d_query,
+                                   float w_embed, float w_lex, const void *d_lex_rows, const void *d_lex_norm,
+                                   uint32_t n_lex, uint32_t m, void *stream)
+{
+    if (!c || !mb || !d_query) return fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    if (m == 0 || m > mb->m_cap) return fail(RLR_ERR_UNSUPPORTED, "m %u not in 1..%u (mailbox capacity)", m, mb->m_cap);
+    if (my_rank >= mb->n_ranks) return fail(RLR_ERR_INVALID_ARG, "my_rank %u >= n_ranks %u", my_rank, mb->n_ranks);
+    if (seq == 0) return fail(RLR_ERR_INVALID_ARG, "sequence numbers start at 1");
+    rlr_store *s = c->s;
+    if (s->n_rows == 0) return fail(RLR_ERR_UNSUPPORTED, "a rank with an empty shard cannot post (give every rank rows)");
+    if (s->device != mb->device) return fail(RLR_ERR_INVALID_ARG, "mailbox opened on device %d, store on %d", mb->device, s->device);
+    CU_TRY(cudaSetDevice(s->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool half = s->use_half(c->search_flags);
+    const uint32_t slot = static_cast<uint32_t>(seq % mb->ring);
+    rlr::ScanArgs a;
+    memset(&a, 0, sizeof a);
+    rlr::scan_plan(s->sm_count, s->smem_optin, static_cast<uint32_t>(s->n_rows), half ? s->pitch16 : s->pitch, half, &a);
+    a.tmap = half ? &s->tmap16 : &s->tmap;
+    a.d_query = static_cast<const float *>(d_query);
+    a.n_rows = static_cast<uint32_t>(s->n_rows);
+    a.row_base = static_cast<uint32_t>(s->row_base);
+    a.pitch = half ? s->pitch16 : s->pitch;
+    a.w_embed = w_embed; a.w_lex = w_lex;
+    a.d_lex_rows = static_cast<const uint32_t *>(d_lex_rows); a.d_lex_norm = static_cast<const float *>(d_lex_norm); a.n_lex = n_lex;
+    a.m = m;
+    a.d_lists = c->d_lists; a.d_counts = c->d_counts; a.d_ticket = c->d_ticket; a.d_pub = c->d_pub;
+    a.d_out = mb->list(slot, my_rank); a.d_out_n = mb->count(slot, my_rank);
+    a.post.flag = mb->flag(slot, my_rank);
+    a.post.consumed = mb->consumed();
+    a.post.seq = seq; a.post.ring = mb->ring; a.post.status = mb->d_status;
+    CU_TRY(rlr::scan_launch(a, st));
+    ++c->launches;
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_mailbox_merge_async(rlr_ctx *c, rlr_mailbox *mb, uint64_t seq, uint32_t m, void *d_out, void *d_out_n,
+                                       void *stream)
+{
+    if (!c || !mb || !d_out || !d_out_n) return fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    if (!mb->owner) return fail(RLR_ERR_INVALID_ARG, "only the root rank merges its mailbox");
+    if (m == 0 || m > mb->m_cap) return fail(RLR_ERR_UNSUPPORTED, "m %u not in 1..%u (mailbox capacity)", m, mb->m_cap);
+    if (seq == 0) return fail(RLR_ERR_INVALID_ARG, "sequence numbers start at 1");
+    CU_TRY(cudaSetDevice(mb->device));
+    const uint32_t slot = static_cast<uint32_t>(seq % mb->ring);
+    CU_TRY(rlr::mailbox_merge_launch(mb->list(slot, 0), mb->m_cap, mb->flag(slot, 0), seq, mb->consumed(), mb->n_ranks, m,
+                                     static_cast<rlr_cand *>(d_out), static_cast<uint32_t *>(d_out_n), mb->d_status,
+                                     static_cast<cudaStream_t>(stream)));
+    ++c->launches;
+    return RLR_OK;
+}
+
 RLR_EXPORT int rlr_search_mmr_async(rlr_ctx *c, const void *d_query, uint32_t top_k, float diversity_factor,
                                     float w_embed, float w_lex, void *d_result, void *d_result_n, void *stream)
 {

@@ -138,6 +138,24 @@ __device__ __forceinline__ float4 lds128(uint32_t addr)
     return v;
 }
 
+// system-scope flag traffic for the cross-GPU mailbox (peer HBM over NVLink)
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns_common()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 // warp-wide max of a u64 with two redux.sync (keys compare as unsigned integers)
 __device__ __forceinline__ uint64_t warp_max_u64(uint64_t key)
 {

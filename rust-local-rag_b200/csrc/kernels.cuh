@@ -15,6 +15,18 @@ constexpr int kTopBuf = 2048;         // per-CTA candidate buffer (entries)
 constexpr int kChunkFloats = 32;      // 128 B : the TMA SWIZZLE_128B span
 constexpr int kQueryCap = RLR_MAX_DIM + 128; // floats, zero padded (a stage spans <= 128 elements)
 
+// Optional delivery of the scan's merged list into a mailbox slot that may live in another
+// GPU's HBM (peer mapping over NVLink): the last CTA waits until the slot is free, writes the
+// list through `d_out`/`d_out_n` (peer pointers), then publishes `seq` with a system-scope
+// release store.  See mailbox_merge_launch.
+struct ScanPost {
+    unsigned long long *flag;            // null: no post (plain local scan)
+    const unsigned long long *consumed;  // slot free once *consumed + ring >= seq
+    unsigned long long seq;
+    uint32_t ring;
+    uint32_t *status;                    // local word, set non-zero if the wait timed out
+};
+
 struct ScanArgs {
     const CUtensorMap *tmap;   // host pointer; copied into the kernel's param space (f32 or f16 map)
     int half;                  // 1: the map describes the binary16 copy of the store
@@ -39,6 +51,7 @@ struct ScanArgs {
     int n_stages;
     uint32_t buf_cap;          // 0: derive from m
     unsigned long long *d_trace; // dev-only: phase timestamps (5*grid + 16 words) or null
+    ScanPost post;             // zeroed: off
 };
 
 // Pick grid / stages / smem for a store on a device.
@@ -51,6 +64,14 @@ cudaError_t scan_launch(const ScanArgs &a, cudaStream_t stream);
 size_t merge_tmp_records(uint32_t n_lists, uint32_t m);
 cudaError_t merge_launch(const rlr_cand *d_lists, uint32_t n_lists, uint32_t m, rlr_cand *d_tmp,
                          rlr_cand *d_out, uint32_t *d_out_n, cudaStream_t stream, uint32_t *launches);
+
+// Root side of the fused exchange: wait (acquire, system scope) until every rank's list for
+// `seq` has landed in the mailbox slot, merge the n_lists lists (each `m` of `list_stride`
+// records) by rank counting, then release the slot (`*consumed = seq`).
+cudaError_t mailbox_merge_launch(const rlr_cand *d_slot, uint32_t list_stride, const unsigned long long *d_flags,
+                                 unsigned long long seq, unsigned long long *d_consumed, uint32_t n_lists, uint32_t m,
+                                 rlr_cand *d_out, uint32_t *d_out_n, uint32_t *d_status, cudaStream_t stream);
+constexpr unsigned long long kMailboxTimeoutNs = 4000000000ull;   // a dead peer must not hang the GPU
 
 // MMR: pairwise similarities (upper triangle) + greedy selection.
 //   d_emb/pitch : matrix the candidate embeddings live in

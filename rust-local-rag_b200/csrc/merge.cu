@@ -122,6 +122,70 @@ merge_rank_kernel(const rlr_cand *__restrict__ in, uint32_t n_lists, uint32_t m,
     if (t == 0 && out_n != nullptr) *out_n = total;
 }
 
+// Root side of the fused exchange: the per-GPU lists are not all-gathered by
+// a collective; every rank's scan kernel stores its list straight into this GPU's mailbox slot
+// (NVLink peer stores) and then publishes the query's sequence number.  This kernel waits for
+// the n_lists flags (acquire, system scope), merges by rank counting exactly as
+// merge_rank_kernel does, and hands the slot back (`*consumed = seq`).
+__global__ void __launch_bounds__(kMergeThreads, 1)
+mailbox_merge_kernel(const rlr_cand *slot, uint32_t list_stride, const unsigned long long *flags,
+                     unsigned long long seq, unsigned long long *consumed, uint32_t n_lists, uint32_t m,
+                     rlr_cand *__restrict__ out, uint32_t *__restrict__ out_n, uint32_t *status)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw);
+    __shared__ uint32_t s_total;
+    const uint32_t t = threadIdx.x;
+    const uint32_t n = n_lists * m;
+    if (t == 0) s_total = 0;
+    if (t < n_lists) {
+        const unsigned long long t_start = globaltimer_ns_common();
+        while (ld_acquire_sys_u64(flags + t) < seq) {
+            if (globaltimer_ns_common() - t_start > kMailboxTimeoutNs) { *status = 2u; break; }
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    // the records were written by other GPUs: read them at L2 (never from a stale L1 line)
+    for (uint32_t i = t; i < n; i += kMergeThreads) {
+        const uint32_t j = i / m;
+        keys[i] = __ldcg(reinterpret_cast<const unsigned long long *>(&slot[static_cast<size_t>(j) * list_stride + (i - j * m)].key));
+    }
+    __syncthreads();
+    if (t < n_lists) {
+        const uint64_t *l = keys + t * m;
+        uint32_t lo = 0, hi = m;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (l[mid] != 0ull) lo = mid + 1; else hi = mid; }
+        atomicAdd(&s_total, lo);
+    }
+    for (uint32_t e = t; e < n; e += kMergeThreads) {
+        const uint64_t x = keys[e];
+        if (x == 0ull) continue;
+        const uint32_t j = e / m;
+        uint32_t rank = e - j * m;
+        for (uint32_t i = 0; i < n_lists && rank < m; ++i) {
+            if (i == j) continue;
+            const uint64_t *l = keys + i * m;
+            uint32_t lo = 0, hi = m;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (l[mid] > x) lo = mid + 1; else hi = mid; }
+            rank += lo;
+        }
+        if (rank < m) {
+            const float2 el = __ldcg(reinterpret_cast<const float2 *>(&slot[static_cast<size_t>(j) * list_stride + (e - j * m)].emb));
+            rlr_cand r;
+            r.key = x; r.emb = el.x; r.lex = el.y;
+            out[rank] = r;
+        }
+    }
+    __syncthreads();
+    const uint32_t total = s_total < m ? s_total : m;
+    for (uint32_t i = total + t; i < m; i += kMergeThreads) { rlr_cand z; z.key = 0; z.emb = 0.0f; z.lex = 0.0f; out[i] = z; }
+    if (t == 0) {
+        if (out_n != nullptr) *out_n = total;
+        st_release_sys_u64(consumed, seq);        // every read of the slot happened before the barrier above
+    }
+}
+
 inline uint32_t lists_per_block(uint32_t m)
 {
     uint32_t l = kMergeCap / m;
@@ -135,6 +199,18 @@ size_t merge_tmp_records(uint32_t n_lists, uint32_t m)
     const uint32_t lpb = lists_per_block(m);
     const size_t nb = (n_lists + lpb - 1) / lpb;
     return 2 * nb * m + m;
+}
+
+cudaError_t mailbox_merge_launch(const rlr_cand *d_slot, uint32_t list_stride, const unsigned long long *d_flags,
+                                 unsigned long long seq, unsigned long long *d_consumed, uint32_t n_lists, uint32_t m,
+                                 rlr_cand *d_out, uint32_t *d_out_n, uint32_t *d_status, cudaStream_t stream)
+{
+    if (static_cast<uint64_t>(n_lists) * m > kRankCap || n_lists > kMergeThreads) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(mailbox_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRankCap * 8);
+    if (e != cudaSuccess) return e;
+    mailbox_merge_kernel<<<1, kMergeThreads, n_lists * m * 8, stream>>>(d_slot, list_stride, d_flags, seq, d_consumed,
+                                                                        n_lists, m, d_out, d_out_n, d_status);
+    return cudaGetLastError();
 }
 
 cudaError_t merge_launch(const rlr_cand *d_lists, uint32_t n_lists, uint32_t m, rlr_cand *d_tmp, rlr_cand *d_out,

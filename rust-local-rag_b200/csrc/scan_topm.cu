@@ -302,7 +302,7 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
                  const uint32_t *__restrict__ lex_rows, const float *__restrict__ lex_norm, uint32_t n_lex,
                  uint32_t m, uint32_t buf_cap, uint32_t r_pub, int n_stages, rlr_cand *g_lists, uint32_t *g_counts,
                  uint32_t *g_pub, uint32_t *g_ticket, uint32_t *g_tile_ctr, rlr_cand *g_out, uint32_t *g_out_n,
-                 unsigned long long *g_trace /* dev-only phase timestamps, may be null */)
+                 unsigned long long *g_trace /* dev-only phase timestamps, may be null */, const ScanPost post)
 {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B atoms are 1024 B: align the carve-up by hand.
@@ -581,8 +581,22 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
     if (g_out == nullptr) return;
     unsigned long long *tr = g_trace != nullptr ? g_trace + 4 * gridDim.x : nullptr;
     if (tr != nullptr && t == 0) tr[0] = globaltimer_ns();
+    if (post.flag != nullptr && post.consumed != nullptr && t == 0 && post.seq > post.ring) {
+        // fused exchange: g_out is a mailbox slot (possibly in a peer GPU's HBM); it is free once
+        // the root has merged the query that used it `ring` sequence numbers ago
+        const unsigned long long t_start = globaltimer_ns();
+        while (ld_acquire_sys_u64(post.consumed) + post.ring < post.seq) {
+            if (globaltimer_ns() - t_start > kMailboxTimeoutNs) { *post.status = 1u; break; }
+            __nanosleep(200);
+        }
+    }
     final_merge(keys, embs, reinterpret_cast<uint32_t *>(smem + L.stages_off + kTopBuf * 12), s_count, s_flag, g_lists,
                 g_counts, gridDim.x, m, row_base, lex_rows, lex_norm, n_lex, g_out, g_out_n, t, tr);
+    if (post.flag != nullptr) {
+        __threadfence_system();               // every writer: the records are visible system-wide ...
+        named_bar_sync(1, R);
+        if (t == 0) st_release_sys_u64(post.flag, post.seq);   // ... before the flag says so
+    }
     if (tr != nullptr && t == 0) tr[7] = globaltimer_ns();
 }
 
@@ -645,12 +659,12 @@ cudaError_t scan_launch(const ScanArgs &a, cudaStream_t stream)
         scan_topm_kernel<true><<<a.grid, kScanThreads, a.smem_bytes, stream>>>(
             *a.tmap, a.d_query, a.n_rows, a.row_base, n_chunks, a.w_embed, a.w_lex, a.d_lex_rows, a.d_lex_norm, a.n_lex,
             a.m, buf_cap, r_pub, a.n_stages, a.d_lists, a.d_counts, a.d_pub, a.d_ticket, a.d_ticket + 1,
-            no_merge ? nullptr : a.d_out, a.d_out_n, a.d_trace);
+            no_merge ? nullptr : a.d_out, a.d_out_n, a.d_trace, a.post);
     else
         scan_topm_kernel<false><<<a.grid, kScanThreads, a.smem_bytes, stream>>>(
             *a.tmap, a.d_query, a.n_rows, a.row_base, n_chunks, a.w_embed, a.w_lex, a.d_lex_rows, a.d_lex_norm, a.n_lex,
             a.m, buf_cap, r_pub, a.n_stages, a.d_lists, a.d_counts, a.d_pub, a.d_ticket, a.d_ticket + 1,
-            no_merge ? nullptr : a.d_out, a.d_out_n, a.d_trace);
+            no_merge ? nullptr : a.d_out, a.d_out_n, a.d_trace, a.post);
     return cudaGetLastError();
 }
 

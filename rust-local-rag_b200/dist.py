@@ -1,7 +1,18 @@
 """Row-sharded search across the GPUs of one NVSwitch box: one process per GPU,
 `torch.distributed` (NCCL over NVLink) for the plumbing.  SURVEY.md 8(e).
 
-Per query, on every rank g of G:
+Per query, on every rank g of G -- FUSED EXCHANGE (the product path on an NVSwitch box):
+  1. local fused scan + top-P; the scan kernel's last CTA stores the rank's list straight into
+     rank 0's mailbox in rank 0's HBM (NVLink peer stores from inside the compute kernel) and
+     publishes the query's sequence number                           (rlr_topm_post_async)
+     -- ranks != 0 are done here and move on to the next query;
+  2. rank 0: one kernel waits for the G flags, merges the lists, frees the slot
+                                                                     (rlr_mailbox_merge_async)
+  3. rank 0: MMR whose pairwise kernel loads the pool rows from the owning GPUs' HBM
+                                                                     (rlr_mmr_peers_async)
+  Rank 0 carries the merge + MMR tail, so `ShardPlan(head_rows=...)` gives it a smaller row
+  block (tail-balanced sharding): all ranks then finish a query at the same time.
+COLLECTIVE path (NCCL; what the gloo tests drive with a stand-in backend):
   1. local fused scan + top-P over the rank's contiguous row block   (rlr_topm_async)
   2. ONE all-gather of the fixed-size per-rank lists (P x 16 B)      (NCCL)
   3. merge of the G lists to the global pool of P                    (rlr_merge_async)
@@ -32,29 +43,50 @@ CAND_WORDS = 2  # one rlr_cand == two int64 words: key, (emb f32 | lex f32 << 32
 
 @dataclass(frozen=True)
 class ShardPlan:
-    """Contiguous row blocks [g*N/G, (g+1)*N/G) (global row = row0 + local)."""
+    """Contiguous row blocks (global row = row0 + local).  Even split [g*N/G, (g+1)*N/G) by
+    default; with `head_rows` rank 0 owns exactly that many rows and ranks 1..G-1 split the
+    rest evenly (tail-balanced sharding: rank 0 also runs the merge + MMR of every query)."""
     n_total: int
     world: int
     rank: int
+    head_rows: Optional[int] = None
 
     @staticmethod
-    def bounds(n_total: int, world: int, rank: int):
-        lo = (n_total * rank) // world
-        hi = (n_total * (rank + 1)) // world
-        return lo, hi
+    def bounds(n_total: int, world: int, rank: int, head_rows: Optional[int] = None):
+        if head_rows is None or world == 1:
+            lo = (n_total * rank) // world
+            hi = (n_total * (rank + 1)) // world
+            return lo, hi
+        head = min(max(int(head_rows), 0), n_total)
+        if rank == 0:
+            return 0, head
+        rest, g = n_total - head, world - 1
+        return head + (rest * (rank - 1)) // g, head + (rest * rank) // g
+
+    @staticmethod
+    def balanced_head_rows(n_total: int, world: int, tail_rows: float) -> int:
+        """Rows for rank 0 such that scan(rank 0) + tail == scan(other ranks), the tail being
+        expressed in rows-scanned-per-second units: n0 = N/G - tail_rows*(G-1)/G."""
+        if world == 1:
+            return n_total
+        n0 = n_total / world - tail_rows * (world - 1) / world
+        return int(min(max(n0, min(n_total, 1024)), n_total))
+
+    def _b(self, rank: int):
+        return self.bounds(self.n_total, self.world, rank, self.head_rows)
 
     @property
     def row0(self) -> int:
-        return self.bounds(self.n_total, self.world, self.rank)[0]
+        return self._b(self.rank)[0]
 
     @property
     def n_local(self) -> int:
-        lo, hi = self.bounds(self.n_total, self.world, self.rank)
+        lo, hi = self._b(self.rank)
         return hi - lo
 
     def owner(self, row: int) -> int:
         for g in range(self.world):
-            lo, hi = self.bounds(self.n_total, self.world, g)
+            lo, hi = self._b(g)
             if lo <= row < hi:
                 return g
         raise ValueError(row)
@@ -102,6 +134,19 @@ def sharded_search(backend, group, bufs: Buffers, query, top_k: int, diversity_f
     m = pool_size(top_k, lam)
     if m > bufs.p_cap:
         raise ValueError(f"pool {m} exceeds buffer capacity {bufs.p_cap}")
+    if world > 1 and getattr(backend, "mailbox_ready", False):
+        # fused exchange: no collective call.  The scan kernel posts this rank's list into rank
+        # 0's HBM; rank 0 merges inside a kernel that waits for the flags, then runs MMR with
+        # peer loads.  Other ranks are done after their scan.
+        seq = backend.next_seq()
+        backend.topm_post(query, w_embed, w_lex, m, seq)
+        if rank != 0:
+            return bufs.result, bufs.sel_n
+        backend.mailbox_merge(seq, m, bufs.pool[:m], bufs.pool_n)
+        if lam == 0.0:
+            return bufs.pool[:m], bufs.pool_n
+        backend.mmr_peers(bufs.pool[:m], bufs.pool_n, m, top_k, lam, bufs.sel_pos, bufs.sel_n, bufs.result)
+        return bufs.result, bufs.sel_n
     local = bufs.local[:m]
     gathered = bufs.gathered[:, :m]
     backend.topm(query, w_embed, w_lex, m, local, bufs.local_n)
@@ -159,6 +204,48 @@ class CudaBackend:
         self.search_flags = search_flags
         self.peer_set = None
         self.peers_ready = False
+        self.mailbox = None
+        self.mailbox_ready = False
+        self._seq = 0
+        self._rank = 0
+
+    def open_mailbox(self, group, m_cap: int = 1024, ring: int = 4):
+        """Rank 0 allocates the mailbox, every other rank maps it (CUDA IPC).  Collective.
+        Needs open_peers() as well (rank 0's MMR reads the pool rows from peer HBM)."""
+        import numpy as np
+        B = self.B
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        self._rank = rank
+        mb = C.c_void_p()
+        handle = np.zeros(B.RLR_IPC_HANDLE_BYTES, np.uint8)
+        if rank == 0:
+            B.check(self.lib.rlr_mailbox_create(self.device.index, world, m_cap, ring, C.byref(mb)))
+            B.check(self.lib.rlr_mailbox_ipc_export(mb, B.ptr(handle)))
+        box = [handle.tobytes() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        if rank != 0:
+            h = np.frombuffer(box[0], np.uint8).copy()
+            B.check(self.lib.rlr_mailbox_open(self.device.index, B.ptr(h), world, m_cap, ring, C.byref(mb)))
+        self.mailbox = mb
+        self.mailbox_ready = True
+        dist.barrier(group=group)
+
+    def next_seq(self) -> int:
+        self._seq += 1
+        return self._seq
+
+    def topm_post(self, query, w_embed, w_lex, m, seq):
+        self.B.check(self.lib.rlr_topm_post_async(self.ctx, self.mailbox, self._rank, seq, self._p(query), w_embed, w_lex,
+                                                  None, None, 0, m, self._stream()))
+
+    def mailbox_merge(self, seq, m, out, out_n):
+        self.B.check(self.lib.rlr_mailbox_merge_async(self.ctx, self.mailbox, seq, m, self._p(out), self._p(out_n),
+                                                      self._stream()))
+
+    def mailbox_status(self) -> int:
+        v = C.c_uint32(0)
+        self.B.check(self.lib.rlr_mailbox_status(self.mailbox, C.byref(v)))
+        return v.value
 
     def open_peers(self, group, plan: "ShardPlan"):
         """Exchange CUDA-IPC handles of the shards; rank 0 maps every peer shard.  Collective."""
@@ -186,7 +273,24 @@ class CudaBackend:
         self.B.check(self.lib.rlr_mmr_peers_async(self.ctx, self.peer_set, self._p(pool), self._p(pool_n), p_cap, top_k,
                                                   lam, self._p(sel_pos), self._p(sel_n), self._p(result), self._stream()))
 
-    def close(self):
+    def close(self, group=None):
+        """With `group` (collective): mappings of other ranks' memory are closed before the
+        owners free it."""
+        if group is not None and dist.get_world_size(group) > 1:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=group)
+            if self.mailbox and self._rank != 0:
+                self.lib.rlr_mailbox_close(self.mailbox)
+                self.mailbox = None
+            if self.peer_set:
+                self.lib.rlr_peer_set_close(self.peer_set)
+                self.peer_set = None
+            dist.barrier(group=group)
+        if self.mailbox:
+            self.lib.rlr_mailbox_close(self.mailbox)
+            self.mailbox = None
+        self.mailbox_ready = False
+        self.peers_ready = False
         if self.peer_set:
             self.lib.rlr_peer_set_close(self.peer_set)
             self.peer_set = None

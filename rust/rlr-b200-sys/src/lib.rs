@@ -20,6 +20,7 @@ pub const RLR_STORE_F16_ONLY: u32 = 0x4;
 #[repr(C)] pub struct rlr_store { _p: [u8; 0] }
 #[repr(C)] pub struct rlr_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct rlr_peer_set { _p: [u8; 0] }
+#[repr(C)] pub struct rlr_mailbox { _p: [u8; 0] }
 
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct rlr_query_weights { pub embedding: f32, pub lexical: f32, pub reranker: f32, pub initial: f32, pub has: u32 }
@@ -67,6 +68,13 @@ extern "C" {
     pub fn rlr_peer_set_open(local: *mut rlr_store, my_index: u32, n_shards: u32, handles: *const c_void, row_base: *const u64, n_rows: *const u64, search_flags: u32, out: *mut *mut rlr_peer_set) -> c_int;
     pub fn rlr_peer_set_close(p: *mut rlr_peer_set) -> c_int;
     pub fn rlr_mmr_peers_async(c: *mut rlr_ctx, p: *mut rlr_peer_set, d_cands: *const c_void, d_n: *const c_void, p_cap: u32, top_k: u32, lambda: f32, d_sel_pos: *mut c_void, d_sel_n: *mut c_void, d_result: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn rlr_mailbox_create(device: c_int, n_ranks: u32, m_cap: u32, ring: u32, out: *mut *mut rlr_mailbox) -> c_int;
+    pub fn rlr_mailbox_ipc_export(mb: *const rlr_mailbox, handle_out: *mut c_void) -> c_int;
+    pub fn rlr_mailbox_open(device: c_int, handle: *const c_void, n_ranks: u32, m_cap: u32, ring: u32, out: *mut *mut rlr_mailbox) -> c_int;
+    pub fn rlr_mailbox_close(mb: *mut rlr_mailbox) -> c_int;
+    pub fn rlr_mailbox_status(mb: *mut rlr_mailbox, out: *mut u32) -> c_int;
+    pub fn rlr_topm_post_async(c: *mut rlr_ctx, mb: *mut rlr_mailbox, my_rank: u32, seq: u64, d_query: *const c_void, w_embed: f32, w_lex: f32, d_lex_rows: *const c_void, d_lex_norm: *const c_void, n_lex: u32, m: u32, stream: *mut c_void) -> c_int;
+    pub fn rlr_mailbox_merge_async(c: *mut rlr_ctx, mb: *mut rlr_mailbox, seq: u64, m: u32, d_out: *mut c_void, d_out_n: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn rlr_search_mmr_async(c: *mut rlr_ctx, d_query: *const c_void, top_k: u32, diversity_factor: f32, w_embed: f32, w_lex: f32, d_result: *mut c_void, d_result_n: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn rlr_ctx_set_flags(c: *mut rlr_ctx, search_flags: u32) -> c_int;
     pub fn rlr_ctx_launch_count(c: *const rlr_ctx, out: *mut u64) -> c_int;

@@ -20,13 +20,17 @@ def main():
     torch.cuda.set_device(lr)
     dev = torch.device("cuda", lr)
     dist.init_process_group("nccl", device_id=dev)
-    plan = rdist.ShardPlan(n, world, rank)
+    mode = os.environ.get("RLR_DIST_MODE", "fused")      # fused | peers | reduce
+    # the fused mode is tested with an uneven (tail-balanced style) split
+    plan = rdist.ShardPlan(n, world, rank, head_rows=(n // world) // 3 if mode == "fused" else None)
     kw = dict(kind=B.RLR_SYNTH_CLUSTERED, seed=11, centroid_seed=12, n_clusters=64, sigma=0.65)
     shard = engine.DeviceStore.synthetic(plan.n_local, dim, device=lr, row_base=plan.row0, **kw)
     backend = rdist.CudaBackend(shard, dev)
-    use_peers = os.environ.get("RLR_DIST_PEERS", "1") == "1"
+    use_peers = mode in ("fused", "peers")
     if use_peers:
         backend.open_peers(dist.group.WORLD, plan)
+    if mode == "fused":
+        backend.open_mailbox(dist.group.WORLD, m_cap=320, ring=2)
     pitch = shard.info().pitch
     qs = engine.DeviceStore.synthetic(8, dim, device=lr, **{**kw, "seed": 13})
     q_host = qs.read_rows(np.arange(8))
@@ -52,10 +56,17 @@ def main():
                     if a.tobytes() != b.tobytes() or a.tobytes() != c.tobytes():
                         ok = False
                         print(f"MISMATCH q={qi} k={k} lam={lam}\n sharded={a[:8]}\n single ={b[:8]}\n oracle ={c[:8]}")
+    if mode == "fused" and backend.mailbox_status() != 0:
+        ok = False
+        print(f"rank {rank}: a mailbox wait timed out")
     flag = torch.tensor([1 if ok else 0], device=dev)
+    if mode == "fused":
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.broadcast(flag, 0)
     if rank == 0:
-        print("DIST_PARITY_OK" if ok else "DIST_PARITY_FAIL", f"world={world} n={n} dim={dim} peers={use_peers}")
+        print("DIST_PARITY_OK" if ok else "DIST_PARITY_FAIL", f"world={world} n={n} dim={dim} mode={mode}")
+    dist.barrier()
+    backend.close(dist.group.WORLD)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1 else 1)
