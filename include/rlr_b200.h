@@ -268,6 +268,18 @@ int rlr_search_batch(rlr_store *s, const float *queries, uint32_t n_queries, uin
                      uint32_t flags, uint32_t m,
                      uint32_t *out_rows, float *out_scores, uint32_t *out_n);
 
+/* Multi-GPU composition of the batched path (BASELINE config 4: rows sharded over the GPUs of
+ * one box).  rlr_search_batch_device is rlr_search_batch with the result left in HBM: d_keys is
+ * n_queries x m u64 rank keys ((ordered(score) << 32) | ~global_row, 0 = empty) in rank order,
+ * d_cnt (nullable) n_queries u32; both are valid on `stream` when the call returns.  After an
+ * all-gather of every rank's d_keys into [n_lists][n_queries][m], rlr_batch_merge_async merges
+ * them per query (one CTA per query) into the global best m. */
+int rlr_search_batch_device(rlr_store *s, const float *queries, uint32_t n_queries, uint32_t dim,
+                            uint32_t flags, uint32_t m, void *d_keys, void *d_cnt /* nullable */,
+                            void *stream);
+int rlr_batch_merge_async(rlr_store *s, const void *d_lists, uint32_t n_lists, uint32_t n_queries,
+                          uint32_t m, void *d_out_keys, void *d_out_cnt /* nullable */, void *stream);
+
 /* stage timings of the calling thread's most recent call made with RLR_WANT_TIMINGS */
 int rlr_last_timings(rlr_timings *out);
 

@@ -92,6 +92,8 @@ PROTOTYPES = {
                               _vp, _vp, _vp, _vp, _pu32]),
     "rlr_embedding_candidates": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _pu32]),
     "rlr_search_batch": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp]),
+    "rlr_search_batch_device": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp]),
+    "rlr_batch_merge_async": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
     "rlr_last_timings": (_int, [C.POINTER(TimingsC)]),
     "rlr_ctx_create": (_int, [_vp, C.POINTER(_vp)]),
     "rlr_ctx_destroy": (_int, [_vp]),

@@ -998,19 +998,30 @@ int batch_phase(rlr_store *s, const CUtensorMap *tmapQ, BatchBufs &b, uint32_t n
 
 } // namespace
 
-RLR_EXPORT int rlr_search_batch(rlr_store *s, const float *queries, uint32_t n_queries, uint32_t dim, uint32_t flags,
-                                uint32_t m, uint32_t *out_rows, float *out_scores, uint32_t *out_n)
+namespace {
+// Shared body of rlr_search_batch (host outputs) and rlr_search_batch_device (d_keys/d_cnt: the
+// per-query rank-ordered key lists stay in HBM, padded with key 0, for the multi-GPU merge).
+int search_batch_core(rlr_store *s, const float *queries, uint32_t n_queries, uint32_t dim, uint32_t flags,
+                      uint32_t m, uint32_t *out_rows, float *out_scores, uint32_t *out_n,
+                      unsigned long long *d_keys, uint32_t *d_cnt, cudaStream_t user_stream)
 {
+    const bool to_device = d_keys != nullptr;
     if (int rc = check_store(s)) return rc;
-    if (!out_rows || !out_n) return fail(RLR_ERR_INVALID_ARG, "out_rows/out_n is NULL");
+    if (!to_device && (!out_rows || !out_n)) return fail(RLR_ERR_INVALID_ARG, "out_rows/out_n is NULL");
     if (n_queries == 0) return RLR_OK;
     if (!queries) return fail(RLR_ERR_INVALID_ARG, "queries is NULL");
     if (m == 0 || m > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "m %u not in 1..%d", m, RLR_MAX_M);
     if (dim != s->dim) return fail(RLR_ERR_DIM_MISMATCH, "queries have %u dims, store has %u", dim, s->dim);
     if (n_queries > 4096) return fail(RLR_ERR_UNSUPPORTED, "n_queries %u exceeds 4096 per call", n_queries);
-    for (uint32_t q = 0; q < n_queries; ++q) out_n[q] = 0;
+    if (out_n) for (uint32_t q = 0; q < n_queries; ++q) out_n[q] = 0;
     if (int rc = ensure_device(s->device)) return rc;
-    if (s->n_rows == 0) return RLR_OK;
+    if (s->n_rows == 0) {
+        if (to_device) {
+            CU_TRY(cudaMemsetAsync(d_keys, 0, static_cast<size_t>(n_queries) * m * 8, user_stream));
+            if (d_cnt) CU_TRY(cudaMemsetAsync(d_cnt, 0, n_queries * sizeof(uint32_t), user_stream));
+        }
+        return RLR_OK;
+    }
     if (s->d_rows16 == nullptr)
         return fail(RLR_ERR_INVALID_ARG, "rlr_search_batch needs the binary16 store copy (RLR_STORE_KEEP_F16 / RLR_STORE_F16_ONLY)");
     {
@@ -1128,6 +1139,27 @@ RLR_EXPORT int rlr_search_batch(rlr_store *s, const float *queries, uint32_t n_q
         launches += 2;
     }
     if (timed) CU_TRY(cudaEventRecord(c->ev[2], st));
+    if (to_device) {
+        // rank-ordered keys stay on the device: [n_queries][m], rows beyond min(m, n_rows) are key 0
+        if (m_eff != m) CU_TRY(cudaMemsetAsync(d_keys, 0, static_cast<size_t>(nq) * m * 8, st));
+        CU_TRY(cudaMemcpy2DAsync(d_keys, static_cast<size_t>(m) * 8, b.d_state, static_cast<size_t>(m_eff) * 8,
+                                 static_cast<size_t>(m_eff) * 8, nq, cudaMemcpyDeviceToDevice, st));
+        if (d_cnt) CU_TRY(cudaMemcpyAsync(d_cnt, b.d_state_cnt, nq * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        CU_TRY(cudaEventRecord(c->ev[3], st));
+        CU_TRY(cudaStreamWaitEvent(user_stream, c->ev[3], 0));   // the caller's stream sees the lists
+        CU_TRY(cudaStreamSynchronize(st));                        // the ctx goes back to the pool idle
+        c->launches += launches;
+        if (timed) {
+            rlr_timings t = {0, 0, 0, 0, 0};
+            cudaEventElapsedTime(&t.scan_ms, c->ev[0], c->ev[1]);
+            cudaEventElapsedTime(&t.merge_ms, c->ev[1], c->ev[2]);
+            cudaEventElapsedTime(&t.total_ms, c->ev[0], c->ev[2]);
+            cudaGetLastError();
+            t.launches = launches;
+            g_timings = t;
+        }
+        return RLR_OK;
+    }
     unsigned long long *h_state = c->h_batch_state;
     uint32_t *h_cnt = reinterpret_cast<uint32_t *>(h_state + static_cast<size_t>(nq) * m_eff);
     CU_TRY(cudaMemcpyAsync(h_state, b.d_state, static_cast<size_t>(nq) * m_eff * 8, cudaMemcpyDeviceToHost, st));
@@ -1155,6 +1187,37 @@ RLR_EXPORT int rlr_search_batch(rlr_store *s, const float *queries, uint32_t n_q
         t.launches = launches;
         g_timings = t;
     }
+    return RLR_OK;
+}
+} // namespace
+
+RLR_EXPORT int rlr_search_batch(rlr_store *s, const float *queries, uint32_t n_queries, uint32_t dim, uint32_t flags,
+                                uint32_t m, uint32_t *out_rows, float *out_scores, uint32_t *out_n)
+{
+    return search_batch_core(s, queries, n_queries, dim, flags, m, out_rows, out_scores, out_n, nullptr, nullptr, nullptr);
+}
+
+RLR_EXPORT int rlr_search_batch_device(rlr_store *s, const float *queries, uint32_t n_queries, uint32_t dim,
+                                       uint32_t flags, uint32_t m, void *d_keys, void *d_cnt, void *stream)
+{
+    if (!d_keys) return fail(RLR_ERR_INVALID_ARG, "d_keys is NULL");
+    return search_batch_core(s, queries, n_queries, dim, flags, m, nullptr, nullptr, nullptr,
+                             static_cast<unsigned long long *>(d_keys), static_cast<uint32_t *>(d_cnt),
+                             static_cast<cudaStream_t>(stream));
+}
+
+RLR_EXPORT int rlr_batch_merge_async(rlr_store *s, const void *d_lists, uint32_t n_lists, uint32_t n_queries, uint32_t m,
+                                     void *d_out_keys, void *d_out_cnt, void *stream)
+{
+    if (int rc = check_store(s)) return rc;
+    if (!d_lists || !d_out_keys) return fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    if (m == 0 || m > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "m %u not in 1..%d", m, RLR_MAX_M);
+    if (n_lists == 0 || n_lists > rlr::kMaxPeers) return fail(RLR_ERR_UNSUPPORTED, "n_lists %u not in 1..%d", n_lists, rlr::kMaxPeers);
+    if (n_queries == 0) return RLR_OK;
+    if (int rc = ensure_device(s->device)) return rc;
+    CU_TRY(rlr::batch_merge_launch(static_cast<const unsigned long long *>(d_lists), n_lists, n_queries, m,
+                                   static_cast<unsigned long long *>(d_out_keys), static_cast<uint32_t *>(d_out_cnt),
+                                   static_cast<cudaStream_t>(stream)));
     return RLR_OK;
 }
 

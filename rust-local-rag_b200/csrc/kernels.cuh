@@ -73,6 +73,11 @@ cudaError_t mailbox_merge_launch(const rlr_cand *d_slot, uint32_t list_stride, c
                                  rlr_cand *d_out, uint32_t *d_out_n, uint32_t *d_status, cudaStream_t stream);
 constexpr unsigned long long kMailboxTimeoutNs = 4000000000ull;   // a dead peer must not hang the GPU
 
+// Batched path, multi-GPU: per query, merge n_lists rank-ordered key lists (d_lists is
+// [n_lists][n_queries][m] u64 keys, zero padded) into the best m (rank counting, one CTA per query).
+cudaError_t batch_merge_launch(const unsigned long long *d_lists, uint32_t n_lists, uint32_t n_queries, uint32_t m,
+                               unsigned long long *d_out, uint32_t *d_out_cnt, cudaStream_t stream);
+
 // MMR: pairwise similarities (upper triangle) + greedy selection.
 //   d_emb/pitch : matrix the candidate embeddings live in
 //   d_cands     : p_cap candidate records (rank order); row index of candidate i is

@@ -186,6 +186,51 @@ mailbox_merge_kernel(const rlr_cand *slot, uint32_t list_stride, const unsigned 
     }
 }
 
+// Batched path across GPUs: query q's lists are in[(j * n_queries + q) * m ...], j < n_lists, each
+// sorted descending with unique keys (they embed the global row) and zero padded.
+constexpr int kBatchMergeThreads = 256;
+__global__ void __launch_bounds__(kBatchMergeThreads)
+batch_merge_kernel(const unsigned long long *__restrict__ in, uint32_t n_lists, uint32_t n_queries, uint32_t m,
+                   unsigned long long *__restrict__ out, uint32_t *__restrict__ out_cnt)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw);
+    __shared__ uint32_t s_total;
+    const uint32_t t = threadIdx.x, q = blockIdx.x;
+    const uint32_t n = n_lists * m;
+    if (t == 0) s_total = 0;
+    for (uint32_t i = t; i < n; i += kBatchMergeThreads) {
+        const uint32_t j = i / m;
+        keys[i] = in[(static_cast<size_t>(j) * n_queries + q) * m + (i - j * m)];
+    }
+    __syncthreads();
+    if (t < n_lists) {
+        const uint64_t *l = keys + t * m;
+        uint32_t lo = 0, hi = m;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (l[mid] != 0ull) lo = mid + 1; else hi = mid; }
+        atomicAdd(&s_total, lo);
+    }
+    unsigned long long *o = out + static_cast<size_t>(q) * m;
+    for (uint32_t e = t; e < n; e += kBatchMergeThreads) {
+        const uint64_t x = keys[e];
+        if (x == 0ull) continue;
+        const uint32_t j = e / m;
+        uint32_t rank = e - j * m;
+        for (uint32_t i = 0; i < n_lists && rank < m; ++i) {
+            if (i == j) continue;
+            const uint64_t *l = keys + i * m;
+            uint32_t lo = 0, hi = m;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (l[mid] > x) lo = mid + 1; else hi = mid; }
+            rank += lo;
+        }
+        if (rank < m) o[rank] = x;
+    }
+    __syncthreads();
+    const uint32_t total = s_total < m ? s_total : m;
+    for (uint32_t i = total + t; i < m; i += kBatchMergeThreads) o[i] = 0ull;
+    if (t == 0 && out_cnt != nullptr) out_cnt[q] = total;
+}
+
 inline uint32_t lists_per_block(uint32_t m)
 {
     uint32_t l = kMergeCap / m;
@@ -199,6 +244,16 @@ size_t merge_tmp_records(uint32_t n_lists, uint32_t m)
     const uint32_t lpb = lists_per_block(m);
     const size_t nb = (n_lists + lpb - 1) / lpb;
     return 2 * nb * m + m;
+}
+
+cudaError_t batch_merge_launch(const unsigned long long *d_lists, uint32_t n_lists, uint32_t n_queries, uint32_t m,
+                               unsigned long long *d_out, uint32_t *d_out_cnt, cudaStream_t stream)
+{
+    if (static_cast<uint64_t>(n_lists) * m > kRankCap) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(batch_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRankCap * 8);
+    if (e != cudaSuccess) return e;
+    batch_merge_kernel<<<n_queries, kBatchMergeThreads, n_lists * m * 8, stream>>>(d_lists, n_lists, n_queries, m, d_out, d_out_cnt);
+    return cudaGetLastError();
 }
 
 cudaError_t mailbox_merge_launch(const rlr_cand *d_slot, uint32_t list_stride, const unsigned long long *d_flags,

@@ -185,6 +185,36 @@ def sharded_search(backend, group, bufs: Buffers, query, top_k: int, diversity_f
     return bufs.result, bufs.sel_n
 
 
+def sharded_search_batch(store, group, queries, m: int, flags: int = 0, device=None):
+    """Batched-query path over a row-sharded corpus (BASELINE config 4).  Every rank runs the
+    tcgen05 contraction over its shard for the same query batch (rlr_search_batch_device), the
+    per-rank [nq, m] key lists are exchanged with ONE all-gather (nq*m*8 B per rank: 0.8 MB for
+    1024 x 100) and merged per query on the device (rlr_batch_merge_async).  Returns
+    (rows [nq, m] uint32 global, scores [nq, m] f32, n [nq]) as numpy arrays, valid on every
+    rank.  `store` is this rank's engine.DeviceStore (needs a binary16 copy)."""
+    import numpy as np
+    from . import binding as B
+    world = dist.get_world_size(group) if group is not None else 1
+    q = np.ascontiguousarray(queries, dtype=np.float32)
+    nq = q.shape[0]
+    dev = device if device is not None else torch.device("cuda", store.info().device)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    local = torch.empty((nq, m), dtype=torch.int64, device=dev)
+    store.search_batch_device(q, m, local, None, stream, flags)
+    if world > 1:
+        gathered = torch.empty((world, nq, m), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gathered.view(world * nq, m), local, group=group)
+        merged = torch.empty((nq, m), dtype=torch.int64, device=dev)
+        cnt = torch.empty(nq, dtype=torch.int32, device=dev)
+        store.batch_merge(gathered, world, nq, m, merged, cnt, stream)
+    else:
+        merged = local
+        cnt = (local != 0).sum(dim=1).to(torch.int32)
+    keys = merged.cpu().numpy().view(np.uint64)
+    n = cnt.cpu().numpy().astype(np.uint32)
+    return B.key_row(keys), B.key_score(keys), n
+
+
 class CudaBackend:
     """The product backend: every step is a kernel launch from librlr_b200.so on the
     current torch CUDA stream.  No fallback."""

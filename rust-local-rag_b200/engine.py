@@ -255,6 +255,21 @@ class DeviceStore:
         B.check(self._lib.rlr_search_batch(self._h, B.ptr(q), nq, dim, flags, m, B.ptr(rows), B.ptr(scores), B.ptr(n)))
         return rows, scores, n
 
+    def search_batch_device(self, queries: np.ndarray, m: int, d_keys, d_cnt=None, stream=None, flags: int = 0) -> None:
+        """rlr_search_batch_device: per-query rank keys stay in HBM (d_keys: [nq, m] int64 torch tensor)."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq, dim = q.shape
+        B.check(self._lib.rlr_search_batch_device(self._h, B.ptr(q), nq, dim, flags, m, C.c_void_p(d_keys.data_ptr()),
+                                                  C.c_void_p(d_cnt.data_ptr()) if d_cnt is not None else None,
+                                                  C.c_void_p(stream) if stream else None))
+
+    def batch_merge(self, d_lists, n_lists: int, nq: int, m: int, d_out, d_out_cnt=None, stream=None) -> None:
+        """rlr_batch_merge_async over all-gathered key lists [n_lists, nq, m]."""
+        B.check(self._lib.rlr_batch_merge_async(self._h, C.c_void_p(d_lists.data_ptr()), n_lists, nq, m,
+                                                C.c_void_p(d_out.data_ptr()),
+                                                C.c_void_p(d_out_cnt.data_ptr()) if d_out_cnt is not None else None,
+                                                C.c_void_p(stream) if stream else None))
+
     def last_timings(self) -> B.TimingsC:
         t = B.TimingsC()
         B.check(self._lib.rlr_last_timings(C.byref(t)))

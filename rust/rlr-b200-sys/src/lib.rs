@@ -56,6 +56,8 @@ extern "C" {
     pub fn rlr_search_mmr(s: *mut rlr_store, query: *const f32, dim: u32, flags: u32, top_k: u32, diversity_factor: f32, w: *const rlr_resolved_weights, lex_rows: *const u32, lex_scores: *const f32, n_lex: u32, out_rows: *mut u32, out_score: *mut f32, out_emb: *mut f32, out_lex: *mut f32, out_n: *mut u32) -> c_int;
     pub fn rlr_embedding_candidates(s: *mut rlr_store, query: *const f32, dim: u32, flags: u32, count: u32, out_rows: *mut u32, out_score: *mut f32, out_n: *mut u32) -> c_int;
     pub fn rlr_search_batch(s: *mut rlr_store, queries: *const f32, n_queries: u32, dim: u32, flags: u32, m: u32, out_rows: *mut u32, out_scores: *mut f32, out_n: *mut u32) -> c_int;
+    pub fn rlr_search_batch_device(s: *mut rlr_store, queries: *const f32, n_queries: u32, dim: u32, flags: u32, m: u32, d_keys: *mut c_void, d_cnt: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn rlr_batch_merge_async(s: *mut rlr_store, d_lists: *const c_void, n_lists: u32, n_queries: u32, m: u32, d_out_keys: *mut c_void, d_out_cnt: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn rlr_last_timings(out: *mut rlr_timings) -> c_int;
     pub fn rlr_ctx_create(s: *mut rlr_store, out: *mut *mut rlr_ctx) -> c_int;
     pub fn rlr_ctx_destroy(c: *mut rlr_ctx) -> c_int;
