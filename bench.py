@@ -194,7 +194,7 @@ def run_reference(a):
 # ----------------------------------------------------------------------------------------
 # own arm
 # ----------------------------------------------------------------------------------------
-def run_b200(a):
+def run_b200(a, guard=None):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -416,7 +416,11 @@ def run_b200(a):
         if stage_samples:
             m = [statistics.mean(x[j] for x in stage_samples) for j in range(4)]
             line["stage_ms"] = {"scan": m[0], "merge": m[1], "mmr": m[2], "device_total": m[3]}
+        if guard is not None:
+            guard.restore()
         print(json.dumps(line), flush=True)
+        if guard is not None:
+            guard.__enter__()
     timeouts = backend.mailbox_status() if mode == "fused" else 0
     backend.close(group)
     if world > 1:
@@ -429,9 +433,32 @@ def run_b200(a):
         raise SystemExit(f"rank {rank}: a mailbox wait timed out (status {timeouts}); the numbers above are invalid")
 
 
+class StdoutToStderr:
+    """Libraries (NCCL's version banner, for one) print to fd 1; the contract is ONE JSON line on
+    stdout.  Everything written to fd 1 while this is active goes to stderr instead."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def restore(self):
+        if self.saved is not None:
+            sys.stdout.flush()
+            os.dup2(self.saved, 1)
+            os.close(self.saved)
+            self.saved = None
+
+    def __exit__(self, *exc):
+        self.restore()
+        return False
+
+
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_b200(args)
+        with StdoutToStderr() as guard:
+            run_b200(args, guard)

@@ -194,7 +194,57 @@ inline std::string get_index_path(const std::string &data_dir, const std::string
     return data_dir + "/chunks_" + sanitize_model_name(model) + ".json";
 }
 
+// LexicalIndex (src/rag_engine.rs:2083-2231) over the library's host-side BM25 index: chunk ids get
+// u64 keys in insertion order (also the tie order of equal scores).
+class LexicalIndex {
+    rlr_lexical *lx_ = nullptr;
+    std::unordered_map<std::string, uint64_t> key_of_;
+    std::unordered_map<uint64_t, std::string> id_of_;
+    uint64_t next_ = 0;
+
+public:
+    LexicalIndex() { check(rlr_lexical_create(&lx_)); }
+    LexicalIndex(const LexicalIndex &) = delete;
+    LexicalIndex &operator=(const LexicalIndex &) = delete;
+    ~LexicalIndex() { rlr_lexical_destroy(lx_); }
+    void add_chunk(const std::string &id, const std::string &text)
+    {
+        auto it = key_of_.find(id);
+        uint64_t key;
+        if (it == key_of_.end()) { key = next_++; key_of_[id] = key; id_of_[key] = id; } else key = it->second;
+        check(rlr_lexical_add_chunk(lx_, key, text.data(), text.size()));
+    }
+    void remove_chunk(const std::string &id)
+    {
+        auto it = key_of_.find(id);
+        if (it == key_of_.end()) return;
+        check(rlr_lexical_remove_chunk(lx_, it->second));
+        id_of_.erase(it->second);
+        key_of_.erase(it);
+    }
+    bool contains(const std::string &id) const
+    {
+        auto it = key_of_.find(id);
+        if (it == key_of_.end()) return false;
+        int out = 0;
+        check(rlr_lexical_contains(lx_, it->second, &out));
+        return out != 0;
+    }
+    std::vector<std::pair<std::string, float>> score(const std::string &query, size_t limit) const
+    {
+        const uint32_t cap = static_cast<uint32_t>(limit > 0 ? limit : std::max<size_t>(key_of_.size(), 1));
+        std::vector<uint64_t> keys(cap);
+        std::vector<float> sc(cap);
+        uint32_t n = 0;
+        check(rlr_lexical_score(lx_, query.data(), query.size(), static_cast<uint32_t>(limit), keys.data(), sc.data(), cap, &n));
+        std::vector<std::pair<std::string, float>> out;
+        for (uint32_t i = 0; i < n; ++i) out.emplace_back(id_of_.at(keys[i]), sc[i]);
+        return out;
+    }
+};
+
 class RagEngine {
+    std::unique_ptr<LexicalIndex> lexical_;          // built by enable_lexical(): validate_index_sync, :1375-1389
     rlr_store *store_ = nullptr;
     std::vector<DocumentChunk> chunks_;              // row -> chunk
     std::unordered_map<std::string, uint32_t> row_of_;
@@ -227,6 +277,33 @@ public:
 
     size_t len() const { return chunks_.size(); }
     bool needs_reindex() const { return needs_reindex_; }
+
+    // Index every chunk's text (what validate_index_sync does after a load, :1382-1389).
+    void enable_lexical()
+    {
+        lexical_.reset(new LexicalIndex());
+        for (auto &c : chunks_) lexical_->add_chunk(c.id, c.text);
+    }
+    const LexicalIndex *lexical() const { return lexical_.get(); }
+
+    // search / search_with_diversity for a TEXT query whose embedding the caller already has
+    // (EmbeddingService is host HTTP, out of scope): runs lexical_index.score(query, 5 * top_k) (:505).
+    std::vector<SearchResult> search_text(const std::string &query, const std::vector<float> &query_embedding, size_t top_k,
+                                          const QueryWeights *weights = nullptr) const
+    {
+        const size_t k = std::max<size_t>(top_k, 1);
+        return search(query_embedding, top_k, weights, lexical_ ? lexical_->score(query, 5 * k) : std::vector<std::pair<std::string, float>>{});
+    }
+    std::vector<SearchResult> search_text_with_diversity(const std::string &query, const std::vector<float> &query_embedding,
+                                                         size_t top_k, float diversity_factor, const QueryWeights *weights = nullptr) const
+    {
+        float lam = diversity_factor;
+        if (lam < 0.0f) lam = 0.0f;
+        if (lam > 1.0f) lam = 1.0f;
+        const size_t pool = lam == 0.0f ? std::max<size_t>(top_k, 1) : std::max<size_t>(3 * top_k, top_k + 10);   // :728-734
+        return search_with_diversity(query_embedding, top_k, diversity_factor, weights,
+                                     lexical_ ? lexical_->score(query, 5 * pool) : std::vector<std::pair<std::string, float>>{});
+    }
     const std::vector<DocumentChunk> &chunks() const { return chunks_; }
 
     // load_from_disk + apply_loaded_state (:1520-1696) for the model-specific file.
@@ -342,6 +419,10 @@ public:
     {
         std::vector<uint32_t> old;
         for (uint32_t i = 0; i < chunks_.size(); ++i) if (chunks_[i].document_name == document_name) old.push_back(i);
+        if (lexical_) {                              // drop_stale + add_chunk, :1379, :382
+            for (uint32_t i : old) lexical_->remove_chunk(chunks_[i].id);
+            for (auto &c : chunks) lexical_->add_chunk(c.id, c.text);
+        }
         if (!old.empty()) {
             std::vector<uint32_t> mf(old.size()), mt(old.size());
             uint64_t nm = 0;

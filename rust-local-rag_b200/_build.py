@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librlr_b200.so")
-SOURCES = ["api.cu", "scan_topm.cu", "merge.cu", "mmr.cu", "synth.cu", "batch_gemm.cu"]
+SOURCES = ["api.cu", "scan_topm.cu", "merge.cu", "mmr.cu", "synth.cu", "batch_gemm.cu", "lexical.cpp"]
 HEADERS = ["common.cuh", "kernels.cuh", "sort_regs.cuh", os.path.join("..", "..", "include", "rlr_b200.h")]
 
 NVCC_FLAGS = [

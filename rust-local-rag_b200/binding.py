@@ -94,6 +94,14 @@ PROTOTYPES = {
     "rlr_search_batch": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp]),
     "rlr_search_batch_device": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp]),
     "rlr_batch_merge_async": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
+    "rlr_lexical_create": (_int, [C.POINTER(_vp)]),
+    "rlr_lexical_destroy": (_int, [_vp]),
+    "rlr_lexical_add_chunk": (_int, [_vp, _u64, C.c_char_p, C.c_size_t]),
+    "rlr_lexical_remove_chunk": (_int, [_vp, _u64]),
+    "rlr_lexical_contains": (_int, [_vp, _u64, C.POINTER(C.c_int)]),
+    "rlr_lexical_stats": (_int, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
+    "rlr_lexical_score": (_int, [_vp, C.c_char_p, C.c_size_t, _u32, _vp, _vp, _u32, _pu32]),
+    "rlr_tokenize": (_int, [C.c_char_p, C.c_size_t, _vp, C.c_size_t, C.POINTER(C.c_size_t), _pu32]),
     "rlr_last_timings": (_int, [C.POINTER(TimingsC)]),
     "rlr_ctx_create": (_int, [_vp, C.POINTER(_vp)]),
     "rlr_ctx_destroy": (_int, [_vp]),

@@ -339,9 +339,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)
 batch_gemm2_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapQ,
                         uint32_t n_rows, uint32_t row_base, uint32_t pair0, uint32_t pair1, uint32_t nq_tiles,
                         uint32_t n_k, const float *__restrict__ tau, unsigned long long *__restrict__ app_keys,
-                        uint32_t *__restrict__ app_cnt, uint32_t cap, uint32_t *__restrict__ overflow)
+                        uint32_t *__restrict__ app_cnt, uint32_t cap, uint32_t *__restrict__ overflow,
+                        unsigned long long *dbg /* dev-only cycle counters of cluster 0, may be null */)
 {
     extern __shared__ uint8_t smem_raw[];
+    const bool trace = dbg != nullptr && blockIdx.x < 2;
+    long long dbg_a = 0, dbg_b = 0, dbg_w = 0;
+    const long long dbg_t0 = clock64();
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
     uint8_t *smem = smem_raw + pad;
@@ -386,7 +390,9 @@ batch_gemm2_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_
             for (uint32_t rp = pair0 + pair; rp < pair1; rp += n_pairs_grid)
                 for (uint32_t qt = 0; qt < nq_tiles; ++qt)
                     for (uint32_t kc = 0; kc < n_k; ++kc) {
+                        const long long c0 = trace ? clock64() : 0;
                         mbar_wait(empty_bar + stage * 8, phase ^ 1);
+                        if (trace) dbg_a += clock64() - c0;
                         const uint32_t lead_full = (full_bar + stage * 8) & kPeerMask;
                         if (rank == 0) mbar_arrive_expect_tx(full_bar + stage * 8, 2 * kStage2);   // both CTAs' bytes
                         const uint32_t a_dst = stages_addr + stage * kStage2;
@@ -394,6 +400,7 @@ batch_gemm2_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_
                         tma_load_2d_2sm(a_dst + kABytes, &tmapQ, static_cast<int32_t>(kc * kBK), static_cast<int32_t>(qt * kBN + rank * 128), lead_full);
                         if (++stage == kStages2) { stage = 0; phase ^= 1; }
                     }
+            if (trace) { dbg[8 * rank + 5] = dbg_a; }
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer (leader CTA only) ----------------
@@ -401,11 +408,15 @@ batch_gemm2_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (uint32_t rp = pair0 + pair; rp < pair1; rp += n_pairs_grid)
                 for (uint32_t qt = 0; qt < nq_tiles; ++qt) {
+                    const long long c0 = trace ? clock64() : 0;
                     mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1);       // both CTAs' epilogues drained it
+                    if (trace) dbg_a += clock64() - c0;
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * kBN;
                     for (uint32_t kc = 0; kc < n_k; ++kc) {
+                        const long long c1 = trace ? clock64() : 0;
                         mbar_wait(full_bar + stage * 8, phase);
+                        if (trace) dbg_b += clock64() - c1;
                         tc_fence_after();
                         const uint32_t a_addr = stages_addr + stage * kStage2;
                         const uint64_t da = make_desc(a_addr), db = make_desc(a_addr + kABytes);
@@ -419,6 +430,7 @@ batch_gemm2_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_
                     acc ^= 1;
                     if (acc == 0) acc_phase ^= 1;
                 }
+            if (trace) { dbg[0] = dbg_a; dbg[1] = dbg_b; dbg[2] = clock64() - dbg_t0; }
         }
     } else if (warp >= 4) {
         // ---------------- epilogue (each CTA: its own 128 rows) ----------------
@@ -429,7 +441,10 @@ batch_gemm2_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_
             const bool row_ok = row_local < n_rows;
             const uint32_t inv_row = ~(row_base + row_local);
             for (uint32_t qt = 0; qt < nq_tiles; ++qt) {
+                const long long c0 = trace ? clock64() : 0;
                 mbar_wait(tfull_bar + acc * 8, acc_phase);
+                const long long c1 = trace ? clock64() : 0;
+                dbg_a += c1 - c0;
                 tc_fence_after();
 #pragma unroll 1
                 for (uint32_t c = 0; c < kBN / 32; ++c) {
@@ -440,12 +455,14 @@ batch_gemm2_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_
                 }
                 tc_fence_before();
                 __syncwarp();
+                if (trace) dbg_w += clock64() - c1;
                 if (lane == 0) mbar_arrive_cluster((tempty_bar + acc * 8) & kPeerMask);   // leader's barrier
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
         }
     }
+    if (trace && tid == 128) { dbg[8 * rank + 3] = dbg_a; dbg[8 * rank + 4] = dbg_w; }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                                        // nobody touches the peer after this
@@ -557,8 +574,19 @@ cudaError_t batch_gemm2_launch(const CUtensorMap *tmapA, const CUtensorMap *tmap
     uint32_t clusters = static_cast<uint32_t>(sm_count / 2);
     if (clusters > pair1 - pair0) clusters = pair1 - pair0;
     const size_t smem = kStages2 * kStage2 + 256 + nq_pad * sizeof(float) + 1024;
+    unsigned long long *dbg = nullptr;
+    if (getenv("RLR_DEBUG_BATCH_TRACE") && pair1 - pair0 > 1000) { cudaMalloc(&dbg, 128); cudaMemset(dbg, 0, 128); }
     batch_gemm2_topm_kernel<<<clusters * 2, kBatchThreads, smem, st>>>(
-        *tmapA, *tmapQ128, n_rows, row_base, pair0, pair1, nq_pad / kBN, pitch16 / kBK, tau, app_keys, app_cnt, cap, overflow);
+        *tmapA, *tmapQ128, n_rows, row_base, pair0, pair1, nq_pad / kBN, pitch16 / kBK, tau, app_keys, app_cnt, cap, overflow, dbg);
+    if (dbg) {
+        unsigned long long h[16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, dbg, 128, cudaMemcpyDeviceToHost);
+        cudaFree(dbg);
+        fprintf(stderr, "[batch2 trace pairs=%u clusters=%u] leader MMA thread: wait tmem_empty %llu, wait smem_full %llu, total %llu cycles; "
+                        "epilogue warp 4 (leader/peer): wait tmem_full %llu/%llu, work %llu/%llu; producer wait smem_empty (leader/peer) %llu/%llu\n",
+                pair1 - pair0, clusters, h[0], h[1], h[2], h[3], h[11], h[4], h[12], h[5], h[13]);
+    }
     return cudaGetLastError();
 }
 

@@ -280,19 +280,80 @@ Query = Union[str, Sequence[float], np.ndarray]
 LexicalFn = Callable[[str, int], List[Tuple[str, float]]]
 
 
+class LexicalIndex:
+    """LexicalIndex (src/rag_engine.rs:2083-2231) over the library's host-side BM25 index
+    (rlr_lexical_*): chunk ids are mapped to u64 keys in insertion order, which is also the
+    tie order of equal scores."""
+
+    def __init__(self):
+        self._lib = B.load()
+        self._h = C.c_void_p()
+        B.check(self._lib.rlr_lexical_create(C.byref(self._h)))
+        self._key_of, self._id_of, self._next = {}, {}, 0
+
+    def add_chunk(self, chunk_id: str, text: str) -> None:
+        key = self._key_of.get(chunk_id)
+        if key is None:
+            key = self._next
+            self._next += 1
+            self._key_of[chunk_id] = key
+            self._id_of[key] = chunk_id
+        b = text.encode("utf-8")
+        B.check(self._lib.rlr_lexical_add_chunk(self._h, key, b, len(b)))
+
+    def remove_chunk(self, chunk_id: str) -> None:
+        key = self._key_of.pop(chunk_id, None)
+        if key is not None:
+            self._id_of.pop(key, None)
+            B.check(self._lib.rlr_lexical_remove_chunk(self._h, key))
+
+    def contains(self, chunk_id: str) -> bool:
+        key = self._key_of.get(chunk_id)
+        if key is None:
+            return False
+        out = C.c_int(0)
+        B.check(self._lib.rlr_lexical_contains(self._h, key, C.byref(out)))
+        return bool(out.value)
+
+    def score(self, query: str, limit: int) -> List[Tuple[str, float]]:
+        b = query.encode("utf-8")
+        cap = max(int(limit), 1) if limit > 0 else max(len(self._key_of), 1)
+        keys, scores, n = np.zeros(cap, np.uint64), np.zeros(cap, np.float32), C.c_uint32(0)
+        B.check(self._lib.rlr_lexical_score(self._h, b, len(b), int(limit), B.ptr(keys), B.ptr(scores), cap, C.byref(n)))
+        return [(self._id_of[int(k)], float(s)) for k, s in zip(keys[:n.value], scores[:n.value])]
+
+    def __call__(self, query: str, limit: int) -> List[Tuple[str, float]]:
+        return self.score(query, limit)
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.rlr_lexical_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class RagEngine:
     """The retrieval half of the reference's RagEngine (src/rag_engine.rs:104-113): chunk
     metadata on the host, embeddings on the device."""
 
     def __init__(self, chunks: List[DocumentChunk], store: DeviceStore, model: str = "nomic-embed-text",
                  embedder: Optional[Callable[[str], Sequence[float]]] = None,
-                 lexical: Optional[LexicalFn] = None):
+                 lexical: Union[None, str, LexicalFn, "LexicalIndex"] = None):
         self.chunks = chunks                     # row -> chunk (the `row -> chunk_id` table)
         self.row_of = {c.id: i for i, c in enumerate(chunks)}
         self.store = store
         self.model = model
         self.embedder = embedder
-        self.lexical = lexical                   # LexicalIndex::score stand-in (host, out of scope)
+        if lexical == "bm25":                    # validate_index_sync, :1375-1389: index every chunk's text
+            lexical = LexicalIndex()
+            for c in chunks:
+                lexical.add_chunk(c.id, c.text)
+        self.lexical = lexical                   # LexicalIndex (host BM25) or any callable (query, limit) -> [(id, score)]
         self.needs_reindex = False
         self.document_hashes = {}
 
@@ -356,6 +417,11 @@ class RagEngine:
         """Drop every chunk of `document_name` (`chunks.retain`, :347-348) and insert the new ones with
         their embeddings normalised (:359).  Keeps the device store dense and `row -> chunk` in sync."""
         old = [i for i, c in enumerate(self.chunks) if c.document_name == document_name]
+        if isinstance(self.lexical, LexicalIndex):
+            for i in old:                        # validate_index_sync -> drop_stale, :1379
+                self.lexical.remove_chunk(self.chunks[i].id)
+            for c in chunks:                     # :382
+                self.lexical.add_chunk(c.id, c.text)
         if old:
             mf, mt = self.store.remove_rows(old)
             for f, t in zip(mf.tolist(), mt.tolist()):

@@ -1,5 +1,5 @@
 // engine_cli -- drives include/rlr_engine.hpp (the C++ host mirror of RagEngine) for the pytest suite.
-//   engine_cli <chunks_{model}.json> <query.f32> <top_k> <diversity>   [replace <doc> <n_new> <seed>]
+//   engine_cli <chunks_{model}.json> <query.f32> <top_k> <diversity>   [replace <doc> <n_new> <seed> | text <query string>]
 // Prints one JSON object: {"n":..,"needs_reindex":..,"results":[{"chunk_id":..,"row":..,"score_bits":..,"emb_bits":..}],
 //                          "candidates":[{"chunk_id":..,"score_bits":..}]}
 #include <cstdio>
@@ -37,12 +37,14 @@ int main(int argc, char **argv)
             }
             eng.replace_document(doc, std::move(cs), std::move(emb));
         }
-        auto res = eng.search_with_diversity(q, top_k, lam);
+        const bool text_mode = argc >= 7 && std::string(argv[5]) == "text";
+        if (text_mode) eng.enable_lexical();         // BM25 over the chunk texts (validate_index_sync)
+        auto res = text_mode ? eng.search_text_with_diversity(argv[6], q, top_k, lam) : eng.search_with_diversity(q, top_k, lam);
         auto cand = eng.get_embedding_candidates(q, 7);
         printf("{\"n\":%zu,\"needs_reindex\":%s,\"results\":[", eng.len(), eng.needs_reindex() ? "true" : "false");
         for (size_t i = 0; i < res.size(); ++i)
-            printf("%s{\"chunk_id\":\"%s\",\"row\":%u,\"score_bits\":%u,\"emb_bits\":%u,\"page\":%zu}", i ? "," : "", res[i].chunk_id.c_str(),
-                   res[i].row, bits(res[i].score), bits(*res[i].embedding_score), res[i].page_number);
+            printf("%s{\"chunk_id\":\"%s\",\"row\":%u,\"score_bits\":%u,\"emb_bits\":%u,\"lex_bits\":%u,\"page\":%zu}", i ? "," : "", res[i].chunk_id.c_str(),
+                   res[i].row, bits(res[i].score), bits(*res[i].embedding_score), bits(*res[i].lexical_score), res[i].page_number);
         printf("],\"candidates\":[");
         for (size_t i = 0; i < cand.size(); ++i)
             printf("%s{\"chunk_id\":\"%s\",\"score_bits\":%u}", i ? "," : "", cand[i].chunk_id.c_str(), bits(cand[i].initial_score));

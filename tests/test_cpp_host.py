@@ -24,12 +24,12 @@ def _build_cli(tmp_path):
     return exe
 
 
-def _write_index(path, n, dim, seed=3):
+def _write_index(path, n, dim, seed=3, texts=None):
     rng = np.random.default_rng(seed)
     chunks = {}
     for i in range(n):
         cid = f"chunk-{i:05d}"
-        chunks[cid] = {"id": cid, "document_name": f"doc{i % 5}.pdf", "text": "téxt \"quoted\"\n",
+        chunks[cid] = {"id": cid, "document_name": f"doc{i % 5}.pdf", "text": texts[i] if texts else "téxt \"quoted\"\n",
                        "embedding": [float(x) for x in (rng.standard_normal(dim) * 1.7).astype(F32)],
                        "chunk_index": i, "page_number": 1 + i % 4, "section": None if i % 2 else "Intro",
                        "metadata": {"page_range": None, "sentence_range": None, "section_title": None, "token_count": 1,
@@ -98,3 +98,36 @@ def test_cpp_host_matches_oracle(tmp_path, orc):
     ref = orc.search_with_diversity(np.array([host[k] for k in order], F32), qv, 8, 0.5, full_sort=True)
     assert [r["score_bits"] for r in out["results"]] == ref[1].view(np.uint32).tolist()
     assert sorted(r["chunk_id"] for r in out["results"]) == sorted(order[r] for r in ref[0])
+
+
+@pytest.mark.gpu
+def test_cpp_host_hybrid_text_query(tmp_path, orc):
+    """rlr::RagEngine::search_text_with_diversity: BM25 over the chunk texts (rlr::LexicalIndex) blended in the
+    scan kernel, against the Python restatement of LexicalIndex + the C search oracle."""
+    import random
+    from oracle import lexical as olex
+    exe = _build_cli(str(tmp_path))
+    vocab = "retrieval embedding vector cosine rust tokio server chunk sentence index search query rerank lexical Memory café".split()
+    rng = random.Random(5)
+    n, dim = 700, 64
+    texts = [" ".join(rng.choice(vocab) for _ in range(rng.randint(4, 30))) + ".\n" for _ in range(n)]
+    idx = os.path.join(tmp_path, "chunks_m.json")
+    chunks = _write_index(idx, n, dim, texts=texts)
+    ids = list(chunks)
+    rows = orc.normalize_rows(np.array([c["embedding"] for c in chunks.values()], F32))
+    qv = np.random.default_rng(11).standard_normal(dim).astype(F32)
+    qp = os.path.join(tmp_path, "q.f32")
+    qv.tofile(qp)
+    ref_idx = olex.LexicalIndex()
+    for i, t in enumerate(texts):
+        ref_idx.add_chunk(i, t)
+    for query, k, lam in (("memory of the café server", 6, 0.4), ("rust tokio", 10, 0.0)):
+        out = json.loads(subprocess.run([exe, idx, qp, str(k), str(lam), "text", query], capture_output=True, text=True,
+                                        check=True).stdout)
+        pool = max(k, 1) if lam == 0.0 else max(3 * k, k + 10)
+        pairs = ref_idx.score(query, 5 * pool)
+        lr, ls = np.array([p[0] for p in pairs], np.uint32), np.array([p[1] for p in pairs], F32)
+        ref = orc.search_with_diversity(rows, qv, k, lam, lex_rows=lr, lex_scores=ls, full_sort=True)
+        assert [r["chunk_id"] for r in out["results"]] == [ids[r] for r in ref[0]], query
+        assert [r["score_bits"] for r in out["results"]] == ref[1].view(np.uint32).tolist()
+        assert [r["lex_bits"] for r in out["results"]] == ref[3].view(np.uint32).tolist()

@@ -128,3 +128,46 @@ def test_reranker_in_the_middle_flow(orc):
     ref = orc.mmr(rows[cand_rows], cand_rel, top_k, lam, threads=4)
     assert sel.tobytes() == ref.tobytes()
     s.close()
+
+
+def test_hybrid_search_with_bm25_index_on_chunk_text(orc):
+    """N4: a string query goes through the host BM25 index (limit 5*top_k, :505), its (row, score) pairs
+    are normalised by the max (:519-530) and blended in the scan kernel (:531-532).  Oracle side: the
+    pure-Python LexicalIndex restatement feeding the C search oracle."""
+    import random
+    import rust_local_rag_b200  # noqa: F401
+    from rust_local_rag_b200 import engine
+    from oracle import lexical as olex
+    vocab = ("retrieval augmented generation embedding vector cosine similarity rust tokio server pdf chunk sentence "
+             "overlap index search query rerank lexical memory bandwidth tensor kernel").split()
+    rng, nrng = random.Random(3), np.random.default_rng(3)
+    n, dim = 3000, 128
+    rows = orc.normalize_rows(nrng.standard_normal((n, dim)).astype(F32))
+    chunks = [engine.DocumentChunk(id=f"c{i}", document_name=f"d{i % 11}.pdf",
+                                   text=" ".join(rng.choice(vocab) for _ in range(rng.randint(5, 40))), chunk_index=i)
+              for i in range(n)]
+    store = engine.DeviceStore.from_rows(rows)
+    qvec = nrng.standard_normal(dim).astype(F32)
+    eng = engine.RagEngine(chunks, store, embedder=lambda s: qvec, lexical="bm25")
+    ref_idx = olex.LexicalIndex()
+    for i, c in enumerate(chunks):
+        ref_idx.add_chunk(i, c.text)
+    for query, k, lam in (("memory bandwidth of the tensor kernel", 5, 0.3), ("rust tokio server", 20, 0.0),
+                          ("zzz nothing matches", 5, 0.5), ("lexical rerank query", 100, 0.7)):
+        pool = max(k, 1) if lam == 0.0 else max(3 * k, k + 10)
+        pairs = ref_idx.score(query, 5 * pool)
+        lr = np.array([p[0] for p in pairs], np.uint32)
+        ls = np.array([p[1] for p in pairs], F32)
+        hits = eng.search_with_diversity(query, k, lam)
+        R, S, E, L = orc.search_with_diversity(rows, qvec, k, lam, lex_rows=lr if len(lr) else None,
+                                               lex_scores=ls if len(ls) else None, full_sort=True)
+        assert [h.row for h in hits] == R.tolist(), query
+        assert np.array([h.score for h in hits], F32).tobytes() == S.tobytes()
+        assert np.array([h.lexical_score for h in hits], F32).tobytes() == L.tobytes()
+    # replace_document keeps the lexical index in sync (validate_index_sync, :1375-1389)
+    new_chunks = [engine.DocumentChunk(id=f"n{i}", document_name="d3.pdf", text="quantum entanglement " * 3, chunk_index=i)
+                  for i in range(4)]
+    eng.replace_document("d3.pdf", new_chunks, nrng.standard_normal((4, dim)).astype(F32))
+    assert not eng.lexical.contains("c3") and eng.lexical.contains("n0")
+    hits = eng.search("quantum entanglement", 4, engine.QueryWeights(embedding=0.0, lexical=1.0))
+    assert sorted(h.chunk_id for h in hits) == ["n0", "n1", "n2", "n3"] and all(h.lexical_score == 1.0 for h in hits)

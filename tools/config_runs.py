@@ -95,7 +95,8 @@ def run4(a, rank, world, lr, dev, group):
     if rank == 0:
         sub = min(plan.n_local, 200_000)
         rows_host = store.read_rows(np.arange(plan.row0, plan.row0 + sub)).astype(np.float64)   # rounded rows, widened
-        q16 = qs[:8].astype(np.float16).astype(np.float64)
+        # the contraction rounds the queries to binary16; the exact re-score uses the f32 queries
+        q16 = (qs[:8] if a.exact else qs[:8].astype(np.float16)).astype(np.float64)
         ref = q16 @ rows_host.T
         tol = 1e-5      # f32 accumulation of 1024 f16 x f16 products with |score| ~ 0.7 (clustered data)
         for q in range(8):
@@ -173,25 +174,43 @@ def run5(a, rank, world, lr, dev, group):
     # Every selected row that falls in the subsample must carry the oracle's exact score for that row.
     res, res_n = step(0)
     torch.cuda.synchronize(dev)
-    ok, worst = True, 0.0
+    got = rdist.decode_result(res, int(res_n.item())) if rank == 0 else None
+    # second probe: plain top-100 (lambda = 0) of the same query, checked against a CPU-scanned slice
+    res2, res2_n = rdist.sharded_search(backend, group, bufs, q_dev[0], k, 0.0, w_e, w_l) if world > 1 else (None, None)
+    torch.cuda.synchronize(dev)
+    ok, worst, slice_ok, slice_rows = True, 0.0, None, 0
     if rank == 0:
         from oracle import orc
-        got_rows, got_score, got_emb, _ = rdist.decode_result(res, int(res_n.item()))
-        sub = min(plan.n_local, 300_000)
-        rows16 = store.read_rows(np.arange(plan.row0, plan.row0 + sub))          # f16-rounded rows, widened to f32
-        f32rows = orc.synth_rows(sub, dim, kind=1, seed=SEED_STORE, centroid_seed=SEED_CENTROID, n_clusters=4096, sigma=0.65,
-                                 row0=plan.row0)
+        synth = dict(kind=1, seed=SEED_STORE, centroid_seed=SEED_CENTROID, n_clusters=4096, sigma=0.65)
+        got_rows, got_score, got_emb, _ = got
+        # (1) every selected row, wherever it lives: regenerate it on the CPU, round to binary16, and
+        #     the oracle's sequential f32 dot must give the bits the GPUs returned
         for r, e in zip(got_rows, got_emb):
-            if plan.row0 <= r < plan.row0 + sub:
-                exact16 = orc.dot(q_host[0], rows16[r - plan.row0])
-                if np.float32(exact16).tobytes() != np.float32(e).tobytes():
-                    ok = False
-                worst = max(worst, abs(float(orc.dot(q_host[0], f32rows[r - plan.row0])) - float(e)))
+            row32 = orc.synth_rows(1, dim, row0=int(r), **synth)[0]
+            row16 = row32.astype(np.float16).astype(np.float32)
+            if np.float32(orc.dot(q_host[0], row16)).tobytes() != np.float32(e).tobytes():
+                ok = False
+            worst = max(worst, abs(float(orc.dot(q_host[0], row32)) - float(e)))
+        # (2) top-100 by score: inside a CPU-scanned slice that straddles the rank 0 / rank 1 boundary, the
+        #     rows beating the 100th score must be exactly the result rows that fall in the slice
+        if res2 is not None:
+            r2, s2, e2, _ = rdist.decode_result(res2, int(res2_n.item()))
+            slice_rows = min(1_000_000, n)
+            lo = max(0, plan.n_local - slice_rows // 2)
+            rows16 = orc.synth_rows(slice_rows, dim, row0=lo, threads=orc.max_threads(), **synth).astype(np.float16).astype(np.float32)
+            R, S, E, _ = orc.search(rows16, q_host[0], min(k, slice_rows), normalize_query=False, threads=orc.max_threads())
+            cut = s2[-1]
+            want = {int(x) + lo: sc for x, sc in zip(R, S) if sc > cut}
+            have = {int(x): sc for x, sc in zip(r2, s2) if lo <= x < lo + slice_rows and sc > cut}
+            slice_ok = want.keys() == have.keys() and all(np.float32(want[x]).tobytes() == np.float32(have[x]).tobytes() for x in want)
+            ok = ok and bool(slice_ok)
         line = {"config": 5, "workload": f"single-query top_k={k} diversity={lam} MMR over {n}x{dim} binary16 chunks ({n * dim * 2 / 1e9:.1f} GB), "
                                          f"rows sharded over {world} GPU(s), fused exchange, tail-balanced",
                 "n_gpus": world, "queries_per_s": 1e3 / ms, "ms_per_query": ms, "rank0_rows": plan.n_local,
                 "scan_ms_rank0": iso.value, "scan_GBps_rank0": plan.n_local * dim * 2 / (iso.value * 1e-3) / 1e9,
                 "f16_scores_bit_equal_to_oracle_on_rounded_rows": ok,
+                "parity_checks": f"all {len(got_rows)} selected rows regenerated on the CPU and re-scored by the oracle (bit-equal); "
+                                 f"top-100 (lambda=0) vs the oracle over a {slice_rows}-row slice across the rank 0/1 boundary: {slice_ok}",
                 "max_abs_deviation_from_f32_scores_in_result": worst,
                 "stated_f16_tolerance": "2e-4 absolute on unit vectors (tests/test_gpu_parity.py)",
                 "mailbox_timeouts": backend.mailbox_status() if world > 1 else 0, "steps": a.steps}
