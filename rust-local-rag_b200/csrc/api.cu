@@ -972,10 +972,24 @@ int batch_phase(rlr_store *s, const CUtensorMap *tmapQ, BatchBufs &b, uint32_t n
     // which needs an even first tile (tiles are handed out in 256-row pairs)
     static const bool two_cta = getenv("RLR_BATCH_1CTA") == nullptr;
     const uint32_t n_tiles_all = static_cast<uint32_t>((s->n_rows + kBatchRTile - 1) / kBatchRTile);
+    // first phase of a batch: tau is -inf everywhere and the phase holds <= cap rows, so every row is kept:
+    // the kernel writes row r to slot r of every list (no filter, no atomics) and the counts are set here
+    const bool dense = two_cta && t0 == 0 && (t1 - t0) * kBatchRTile <= kBatchCap && (t1 % 2 == 0 || t1 == n_tiles_all);
+    if (dense) {
+        CU_TRY(rlr::batch_gemm2_launch(&s->tmap16, tmapQ + 1, s->sm_count, static_cast<uint32_t>(s->n_rows),
+                                       static_cast<uint32_t>(s->row_base), t0, t1, nq_pad, s->pitch16, b.d_tau, b.d_app,
+                                       b.d_app_cnt, kBatchCap, b.d_overflow, 1, st));
+        const uint32_t rows_in_phase = static_cast<uint32_t>(std::min<uint64_t>(s->n_rows, static_cast<uint64_t>(t1) * kBatchRTile));
+        CU_TRY(rlr::batch_set_cnt_launch(b.d_app_cnt, nq, rows_in_phase, st));
+        *launches += 2;
+        CU_TRY(rlr::batch_prune_launch(b.d_state, b.d_state_cnt, m, b.d_app, b.d_app_cnt, kBatchCap, b.d_tau, nq, st));
+        ++*launches;
+        return RLR_OK;
+    }
     if (two_cta && (t0 % 2 == 0) && (t1 % 2 == 0 || t1 == n_tiles_all) && (t1 - t0) >= 2)
         CU_TRY(rlr::batch_gemm2_launch(&s->tmap16, tmapQ + 1, s->sm_count, static_cast<uint32_t>(s->n_rows),
                                        static_cast<uint32_t>(s->row_base), t0, t1, nq_pad, s->pitch16, b.d_tau, b.d_app,
-                                       b.d_app_cnt, kBatchCap, b.d_overflow, st));
+                                       b.d_app_cnt, kBatchCap, b.d_overflow, 0, st));
     else
     CU_TRY(rlr::batch_gemm_launch(&s->tmap16, tmapQ, s->sm_count, static_cast<uint32_t>(s->n_rows),
                                   static_cast<uint32_t>(s->row_base), t0, t1, nq_pad, s->pitch16, b.d_tau, b.d_app,

@@ -280,6 +280,142 @@ batch_gemm_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_c
     }
 }
 
+
+// ---- staged epilogue (2-CTA kernel) ----
+// TMEM loads split from their wait so that the next 32 columns are in flight while the current
+// ones are filtered.
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+constexpr uint32_t kStageCap = 128;      // staged survivors per epilogue warp (keys 1 KB + queries 512 B)
+constexpr uint32_t kStageBytesPerWarp = kStageCap * 12 + 16;   // + the warp's record counter
+
+// Survivors are first parked in a warp-private shared-memory buffer (no global traffic while the
+// accumulator is being drained) and appended to their queries' global lists in batches: one
+// atomicAdd per record, 32 of them in flight per warp, so a batch costs ONE L2 atomic round trip.
+// (Appending per 32-column chunk cost a round trip per chunk and made the epilogue, not the tensor
+// pipe, the bound of the early phases: 25.7k cycles per tile against 8.2k of MMA.)
+__device__ __forceinline__ void sts_u64(uint32_t addr, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t addr) { unsigned long long v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+
+// Append the `cnt` staged records (keys at keys_s, their queries at qs_s: shared-space addresses) to
+// the per-query global lists.  Records of one query sit next to each other, so one atomicAdd per
+// (batch of 32, query); the up-to-32 atomics of a batch are in flight together.  Everything is
+// passed by value: state that lives in a struct handed to a non-inlined function ends up in local
+// memory, and the per-column bookkeeping then runs at local-memory latency (measured: 4.8k cycles
+// per chunk with a survivor).
+__device__ __noinline__ void flush_staged(uint32_t keys_s, uint32_t qs_s, uint32_t cnt, unsigned long long *__restrict__ app_keys,
+                                          uint32_t *__restrict__ app_cnt, uint32_t cap, uint32_t *__restrict__ overflow)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    __syncwarp();
+    for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        const bool live = j < cnt;
+        const uint32_t q = live ? lds_u32(qs_s + j * 4) : 0xffffffffu;
+        const uint32_t same = __match_any_sync(0xffffffffu, q);
+        const uint32_t leader = __ffs(same) - 1;
+        uint32_t base = 0;
+        if (live && lane == leader) base = atomicAdd(app_cnt + static_cast<size_t>(q) * kCntStride, static_cast<uint32_t>(__popc(same)));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (live) {
+            const uint32_t slot = base + __popc(same & ((1u << lane) - 1u));
+            if (slot < cap) app_keys[static_cast<size_t>(q) * cap + slot] = lds_u64(keys_s + j * 8);
+            else *overflow = 1u;
+        }
+    }
+    __syncwarp();
+}
+
+// v[i] for a run-time i without spilling the array to local memory: a 5-level select tree (31 SELs)
+__device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], uint32_t i)
+{
+    uint32_t a[16], b[8], c[4];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = (i & 16u) ? v[16 + j] : v[j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = (i & 8u) ? a[8 + j] : a[j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[j] = (i & 4u) ? b[4 + j] : b[j];
+    const uint32_t d0 = (i & 2u) ? c[2] : c[0], d1 = (i & 2u) ? c[3] : c[1];
+    return (i & 1u) ? d1 : d0;
+}
+
+// 32 accumulator columns (queries q0 .. q0+31) of this lane's store row.  The number of staged
+// records of the warp lives in shared memory at cnt_s (lanes with survivors claim their slots with
+// one shared atomicAdd each).
+__device__ __forceinline__ void filter_stage(const uint32_t (&v)[32], const float *tau32, uint32_t q0, bool row_ok, uint32_t inv_row,
+                                             uint32_t lane, uint32_t keys_s, uint32_t qs_s, uint32_t cnt_s,
+                                             unsigned long long *__restrict__ app_keys, uint32_t *__restrict__ app_cnt, uint32_t cap,
+                                             uint32_t *__restrict__ overflow, bool trace, long long &t_slow, uint32_t &n_slow)
+{
+    // fast path: d = v - tau >= +0  <=>  v >= tau; AND the sign bits of the 32 differences
+    uint32_t sgn = 0xffffffffu;
+#pragma unroll
+    for (int i4 = 0; i4 < 8; ++i4) {
+        const float4 t = *reinterpret_cast<const float4 *>(tau32 + i4 * 4);       // broadcast LDS.128
+        sgn &= __float_as_uint(sub_rn(__uint_as_float(v[i4 * 4 + 0]), t.x)) & __float_as_uint(sub_rn(__uint_as_float(v[i4 * 4 + 1]), t.y));
+        sgn &= __float_as_uint(sub_rn(__uint_as_float(v[i4 * 4 + 2]), t.z)) & __float_as_uint(sub_rn(__uint_as_float(v[i4 * 4 + 3]), t.w));
+    }
+    const bool mine = row_ok && static_cast<int32_t>(sgn) >= 0;
+    if (!__any_sync(0xffffffffu, mine)) return;
+    // slow path (some lane has a survivor).  Kept short and branch-light: a first version walked the 32
+    // columns with a warp-uniform branch + ballot each and cost ~4k cycles per call (instruction-cache
+    // misses on rarely executed, jumpy code); a prefix-sum version with 32 predicated blocks still ~1.9k.
+    const long long s0 = trace ? clock64() : 0;
+    uint32_t mask = 0;
+    if (mine) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(v[i]) >= tau32[i] ? 1u : 0u) << i;
+    }
+    const uint32_t total = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(__popc(mask)));
+    uint32_t n_groups = 1;
+    if (lds_u32(cnt_s) + total > kStageCap) {
+        flush_staged(keys_s, qs_s, lds_u32(cnt_s), app_keys, app_cnt, cap, overflow);
+        if (lane == 0) sts_u32(cnt_s, 0);
+        __syncwarp();
+        if (total > kStageCap) n_groups = 8;      // dense: 4 lanes (<= 128 records) at a time
+    }
+#pragma unroll 1
+    for (uint32_t g = 0; g < n_groups; ++g) {
+        uint32_t m = (n_groups == 1 || (lane >> 2) == g) ? mask : 0u;
+        if (m) {
+            uint32_t pos;
+            const uint32_t n = __popc(m);
+            asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(pos) : "r"(cnt_s), "r"(n) : "memory");
+            while (m) {
+                const uint32_t i = __ffs(m) - 1;
+                m &= m - 1;
+                sts_u64(keys_s + pos * 8, (static_cast<unsigned long long>(ord_f32(__uint_as_float(pick32(v, i)))) << 32) | inv_row);
+                sts_u32(qs_s + pos * 4, q0 + i);
+                ++pos;
+            }
+        }
+        if (n_groups != 1) {
+            __syncwarp();
+            flush_staged(keys_s, qs_s, lds_u32(cnt_s), app_keys, app_cnt, cap, overflow);
+            if (lane == 0) sts_u32(cnt_s, 0);
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    if (trace) { t_slow += clock64() - s0; ++n_slow; }
+}
+
 // ------------------------------------------------------------------------------------------
 // 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256-row x 256-query
 // tile.  Each CTA stages only ITS 128 store rows (A half) and ITS 128 queries (B half) -- the
@@ -335,13 +471,20 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)
+constexpr int kBatch2Threads = 384;     // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue (two per TMEM lane quadrant)
+constexpr uint32_t kEpiWarps2 = 8;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatch2Threads, 1)
 batch_gemm2_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapQ,
                         uint32_t n_rows, uint32_t row_base, uint32_t pair0, uint32_t pair1, uint32_t nq_tiles,
                         uint32_t n_k, const float *__restrict__ tau, unsigned long long *__restrict__ app_keys,
-                        uint32_t *__restrict__ app_cnt, uint32_t cap, uint32_t *__restrict__ overflow,
+                        uint32_t *__restrict__ app_cnt, uint32_t cap, uint32_t *__restrict__ overflow, uint32_t dense,
                         unsigned long long *dbg /* dev-only cycle counters of cluster 0, may be null */)
 {
+    // Work items are (row pair, query tile) flattened, handed out round-robin to the clusters, so
+    // that the early, short phases (4 / 28 row pairs) still spread over all 74 clusters.
+    // dense != 0: the very first phase (tau = -inf, every row is kept, <= cap rows): no filter and no
+    // atomics at all -- row r of the phase goes to slot r of every query's list.
     extern __shared__ uint8_t smem_raw[];
     const bool trace = dbg != nullptr && blockIdx.x < 2;
     long long dbg_a = 0, dbg_b = 0, dbg_w = 0;
@@ -360,7 +503,8 @@ batch_gemm2_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
-    const uint32_t pair = blockIdx.x >> 1, n_pairs_grid = gridDim.x >> 1;
+    const uint32_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const uint32_t n_items = (pair1 - pair0) * nq_tiles;
     const uint32_t nq_pad = nq_tiles * kBN;
 
     if (warp == 0 && lane == 0) {
@@ -369,14 +513,14 @@ batch_gemm2_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages2; ++s) { mbar_init(full_bar + s * 8, 1); mbar_init(empty_bar + s * 8, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + a * 8, 1); mbar_init(tempty_bar + a * 8, 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + a * 8, 1); mbar_init(tempty_bar + a * 8, 2 * kEpiWarps2); }
         fence_mbar_init();
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(const_cast<uint32_t *>(s_tmem))), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
-    for (uint32_t i = tid; i < nq_pad; i += kBatchThreads) tau_s[i] = tau[i];
+    for (uint32_t i = tid; i < nq_pad; i += kBatch2Threads) tau_s[i] = tau[i];
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                                        // both CTAs' barriers + TMEM exist
@@ -387,8 +531,8 @@ batch_gemm2_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_
         // ---------------- TMA producer (both CTAs; completion on the LEADER's full barrier) ----------------
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (uint32_t rp = pair0 + pair; rp < pair1; rp += n_pairs_grid)
-                for (uint32_t qt = 0; qt < nq_tiles; ++qt)
+            for (uint32_t it = cluster_id; it < n_items; it += n_clusters) {
+                const uint32_t rp = pair0 + it / nq_tiles, qt = it % nq_tiles;
                     for (uint32_t kc = 0; kc < n_k; ++kc) {
                         const long long c0 = trace ? clock64() : 0;
                         mbar_wait(empty_bar + stage * 8, phase ^ 1);
@@ -400,14 +544,14 @@ batch_gemm2_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_
                         tma_load_2d_2sm(a_dst + kABytes, &tmapQ, static_cast<int32_t>(kc * kBK), static_cast<int32_t>(qt * kBN + rank * 128), lead_full);
                         if (++stage == kStages2) { stage = 0; phase ^= 1; }
                     }
+            }
             if (trace) { dbg[8 * rank + 5] = dbg_a; }
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer (leader CTA only) ----------------
         if (rank == 0 && lane == 0) {
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (uint32_t rp = pair0 + pair; rp < pair1; rp += n_pairs_grid)
-                for (uint32_t qt = 0; qt < nq_tiles; ++qt) {
+                for (uint32_t it = cluster_id; it < n_items; it += n_clusters) {
                     const long long c0 = trace ? clock64() : 0;
                     mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1);       // both CTAs' epilogues drained it
                     if (trace) dbg_a += clock64() - c0;
@@ -433,34 +577,78 @@ batch_gemm2_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_
             if (trace) { dbg[0] = dbg_a; dbg[1] = dbg_b; dbg[2] = clock64() - dbg_t0; }
         }
     } else if (warp >= 4) {
-        // ---------------- epilogue (each CTA: its own 128 rows) ----------------
-        const uint32_t w = warp - 4;
+        // ---------------- epilogue (each CTA: its own 128 rows; 2 warps per TMEM lane quadrant) ----------------
+        const uint32_t w = warp - 4, quad = w & 3u, half = w >> 2;       // columns [half * 128, half * 128 + 128)
+        const uint32_t keys_s = smem_u32(reinterpret_cast<uint8_t *>(tau_s + nq_pad) + w * kStageBytesPerWarp);
+        const uint32_t qs_s = keys_s + kStageCap * 8;
+        const uint32_t cnt_s = qs_s + kStageCap * 4;
+        if (lane == 0) sts_u32(cnt_s, 0);
+        __syncwarp();
+        uint32_t n_slow = 0;
+        long long t_slow = 0;
+        const bool tr = trace && w == 0;
         uint32_t acc = 0, acc_phase = 0;
-        for (uint32_t rp = pair0 + pair; rp < pair1; rp += n_pairs_grid) {
-            const uint32_t row_local = (rp * 2 + rank) * kBM + w * 32 + lane;
+        for (uint32_t it = cluster_id; it < n_items; it += n_clusters) {
+            const uint32_t rp = pair0 + it / nq_tiles, qt = it % nq_tiles;
+            const uint32_t row_local = (rp * 2 + rank) * kBM + quad * 32 + lane;
             const bool row_ok = row_local < n_rows;
             const uint32_t inv_row = ~(row_base + row_local);
-            for (uint32_t qt = 0; qt < nq_tiles; ++qt) {
+            {
                 const long long c0 = trace ? clock64() : 0;
                 mbar_wait(tfull_bar + acc * 8, acc_phase);
                 const long long c1 = trace ? clock64() : 0;
                 dbg_a += c1 - c0;
                 tc_fence_after();
+                const uint32_t t_base = tmem_base + ((quad * 32u) << 16) + acc * kBN + half * 128;
+                const uint32_t q_base = qt * kBN + half * 128;
+                uint32_t va[32], vb[32];
+                if (dense) {
+                    const uint32_t slot = row_local - pair0 * 2 * kBM;            // < cap by construction of phase 0
 #pragma unroll 1
-                for (uint32_t c = 0; c < kBN / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + ((w * 32u) << 16) + acc * kBN + c * 32, v);
-                    const uint32_t q0 = qt * kBN + c * 32;
-                    epilogue_filter(v, tau_s + q0, q0, row_ok, inv_row, app_keys, app_cnt, cap, overflow);
+                    for (uint32_t c = 0; c < 4; ++c) {
+                        tmem_ld32_nowait(t_base + c * 32, va);
+                        tmem_wait_ld();
+                        if (row_ok) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)                          // a warp writes 32 consecutive slots of one query
+                                app_keys[static_cast<size_t>(q_base + c * 32 + i) * cap + slot] =
+                                    (static_cast<unsigned long long>(ord_f32(__uint_as_float(va[i]))) << 32) | inv_row;
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster((tempty_bar + acc * 8) & kPeerMask);
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1;
+                    continue;
                 }
-                tc_fence_before();
-                __syncwarp();
+                tmem_ld32_nowait(t_base, va);
+                tmem_wait_ld();
+#pragma unroll 1
+                for (uint32_t cc = 0; cc < 2; ++cc) {       // two copies of the filter code, not four
+                    const uint32_t qa = q_base + cc * 64;
+                    tmem_ld32_nowait(t_base + cc * 64 + 32, vb);
+                    filter_stage(va, tau_s + qa, qa, row_ok, inv_row, lane, keys_s, qs_s, cnt_s, app_keys, app_cnt, cap, overflow, tr, t_slow, n_slow);
+                    tmem_wait_ld();
+                    if (cc == 0) {
+                        tmem_ld32_nowait(t_base + 64, va);
+                    } else {
+                        // every column of this warp's half is in registers: hand the accumulator back first
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster((tempty_bar + acc * 8) & kPeerMask);   // leader's barrier
+                    }
+                    filter_stage(vb, tau_s + qa + 32, qa + 32, row_ok, inv_row, lane, keys_s, qs_s, cnt_s, app_keys, app_cnt, cap, overflow, tr, t_slow, n_slow);
+                    if (cc == 0) tmem_wait_ld();
+                }
                 if (trace) dbg_w += clock64() - c1;
-                if (lane == 0) mbar_arrive_cluster((tempty_bar + acc * 8) & kPeerMask);   // leader's barrier
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
         }
+        __syncwarp();
+        flush_staged(keys_s, qs_s, lds_u32(cnt_s), app_keys, app_cnt, cap, overflow);
+        if (tr && lane == 0) { dbg[8 * rank + 6] = 0; dbg[8 * rank + 7] = t_slow; dbg[16 + 2 * rank] = n_slow; dbg[17 + 2 * rank] = 0; }
     }
     if (trace && tid == 128) { dbg[8 * rank + 3] = dbg_a; dbg[8 * rank + 4] = dbg_w; }
     tc_fence_before();
@@ -541,6 +729,12 @@ __global__ void batch_rescore_kernel(const void *__restrict__ rows, uint32_t pit
     state_keys[static_cast<size_t>(q) * m + i] = make_key(acc, row);
 }
 
+__global__ void batch_set_cnt_kernel(uint32_t *app_cnt, uint32_t nq, uint32_t value)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) app_cnt[static_cast<size_t>(i) * kCntStride] = value;
+}
+
 __global__ void batch_init_kernel(float *tau, uint32_t *state_cnt, uint32_t *app_cnt, uint32_t nq, uint32_t nq_pad, uint32_t *overflow)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -567,26 +761,34 @@ cudaError_t batch_configure(int smem_optin)
 cudaError_t batch_gemm2_launch(const CUtensorMap *tmapA, const CUtensorMap *tmapQ128, int sm_count, uint32_t n_rows,
                                uint32_t row_base, uint32_t tile0, uint32_t tile1, uint32_t nq_pad, uint32_t pitch16,
                                const float *tau, unsigned long long *app_keys, uint32_t *app_cnt, uint32_t cap,
-                               uint32_t *overflow, cudaStream_t st)
+                               uint32_t *overflow, int dense, cudaStream_t st)
 {
     if (tile1 <= tile0) return cudaSuccess;
     const uint32_t pair0 = tile0 / 2, pair1 = (tile1 + 1) / 2;
     uint32_t clusters = static_cast<uint32_t>(sm_count / 2);
-    if (clusters > pair1 - pair0) clusters = pair1 - pair0;
-    const size_t smem = kStages2 * kStage2 + 256 + nq_pad * sizeof(float) + 1024;
+    const uint32_t n_items = (pair1 - pair0) * (nq_pad / kBN);
+    if (clusters > n_items) clusters = n_items;
+    const size_t smem = kStages2 * kStage2 + 256 + nq_pad * sizeof(float) + kEpiWarps2 * kStageBytesPerWarp + 1024;
     unsigned long long *dbg = nullptr;
-    if (getenv("RLR_DEBUG_BATCH_TRACE") && pair1 - pair0 > 1000) { cudaMalloc(&dbg, 128); cudaMemset(dbg, 0, 128); }
-    batch_gemm2_topm_kernel<<<clusters * 2, kBatchThreads, smem, st>>>(
-        *tmapA, *tmapQ128, n_rows, row_base, pair0, pair1, nq_pad / kBN, pitch16 / kBK, tau, app_keys, app_cnt, cap, overflow, dbg);
+    if (getenv("RLR_DEBUG_BATCH_TRACE") && pair1 - pair0 > 1000) { cudaMalloc(&dbg, 256); cudaMemset(dbg, 0, 256); }
+    batch_gemm2_topm_kernel<<<clusters * 2, kBatch2Threads, smem, st>>>(
+        *tmapA, *tmapQ128, n_rows, row_base, pair0, pair1, nq_pad / kBN, pitch16 / kBK, tau, app_keys, app_cnt, cap, overflow, dense ? 1u : 0u, dbg);
     if (dbg) {
-        unsigned long long h[16];
+        unsigned long long h[32];
         cudaStreamSynchronize(st);
-        cudaMemcpy(h, dbg, 128, cudaMemcpyDeviceToHost);
+        cudaMemcpy(h, dbg, 256, cudaMemcpyDeviceToHost);
         cudaFree(dbg);
+        fprintf(stderr, "[batch2 trace] leader warp 4: flush %llu cycles, slow path %llu cycles over %llu chunks, %llu records\n", h[6], h[7], h[16], h[17]);
         fprintf(stderr, "[batch2 trace pairs=%u clusters=%u] leader MMA thread: wait tmem_empty %llu, wait smem_full %llu, total %llu cycles; "
                         "epilogue warp 4 (leader/peer): wait tmem_full %llu/%llu, work %llu/%llu; producer wait smem_empty (leader/peer) %llu/%llu\n",
                 pair1 - pair0, clusters, h[0], h[1], h[2], h[3], h[11], h[4], h[12], h[5], h[13]);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t batch_set_cnt_launch(uint32_t *app_cnt, uint32_t nq, uint32_t value, cudaStream_t st)
+{
+    batch_set_cnt_kernel<<<(nq + 255) / 256, 256, 0, st>>>(app_cnt, nq, value);
     return cudaGetLastError();
 }
 

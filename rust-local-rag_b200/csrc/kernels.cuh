@@ -149,7 +149,8 @@ cudaError_t batch_gemm_launch(const CUtensorMap *tmapA, const CUtensorMap *tmapQ
 cudaError_t batch_gemm2_launch(const CUtensorMap *tmapA, const CUtensorMap *tmapQ128, int sm_count, uint32_t n_rows,
                                uint32_t row_base, uint32_t tile0, uint32_t tile1, uint32_t nq_pad, uint32_t pitch16,
                                const float *tau, unsigned long long *app_keys, uint32_t *app_cnt, uint32_t cap,
-                               uint32_t *overflow, cudaStream_t st);
+                               uint32_t *overflow, int dense, cudaStream_t st);
+cudaError_t batch_set_cnt_launch(uint32_t *app_cnt, uint32_t nq, uint32_t value, cudaStream_t st);
 cudaError_t batch_prune_launch(unsigned long long *state_keys, uint32_t *state_cnt, uint32_t m, unsigned long long *app_keys,
                                uint32_t *app_cnt, uint32_t cap, float *tau, uint32_t nq, cudaStream_t st);
 cudaError_t batch_rescore_launch(const void *d_rows, int half, uint32_t pitch, uint32_t dim, uint32_t row_base,
