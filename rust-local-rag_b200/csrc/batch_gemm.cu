@@ -660,9 +660,13 @@ batch_gemm2_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_
     }
 }
 
-// One CTA (128 threads) per query: merge the appended candidates into the running top-M (both
-// as rank keys), write the new top-M (sorted), raise tau[q] to the M-th score, clear the
-// append list.  state/app sizes <= 1024 each -> at most 2048 keys, sorted in registers.
+// One CTA (128 threads) per query: fold the appended candidates into the running top-M (both as
+// rank keys), write the new top-M (sorted), raise tau[q] to the M-th score, clear the append list.
+// Sorting all n = M + appended keys (55 bitonic stages for 1024) made the five prunes of a batch
+// cost 13 % of it.  Only the best M are needed, so: (1) radix-select the M-th largest key T exactly
+// -- 64 rounds of "how many keys are >= T | bit", keys in registers, one barrier per round --
+// (2) compact the keys >= T (keys are unique: exactly min(M, n) of them), (3) sort just those.
+constexpr int kPruneKeysPerThread = kTopBuf / 128;     // 16
 __global__ void __launch_bounds__(128, 4)
 batch_prune_kernel(unsigned long long *__restrict__ state_keys, uint32_t *__restrict__ state_cnt, uint32_t m,
                    unsigned long long *__restrict__ app_keys, uint32_t *__restrict__ app_cnt, uint32_t cap,
@@ -670,30 +674,159 @@ batch_prune_kernel(unsigned long long *__restrict__ state_keys, uint32_t *__rest
 {
     __shared__ uint64_t keys[kTopBuf];
     __shared__ float dummy[kTopBuf];
-    const uint32_t q = blockIdx.x, t = threadIdx.x;
+    __shared__ uint32_t s_part[2][4];
+    __shared__ uint32_t s_sel;
+    const uint32_t q = blockIdx.x, t = threadIdx.x, lane = t & 31u, warp = t >> 5;
     if (q >= nq) return;
     const uint32_t ns = state_cnt[q];
     uint32_t na = app_cnt[static_cast<size_t>(q) * kCntStride];
     if (na > cap) na = cap;
     const uint32_t n = ns + na;
-    uint32_t n2 = 1;
-    while (n2 < n) n2 <<= 1;
-    if (n2 < 128) n2 = 128;
-    for (uint32_t i = t; i < n2; i += 128) {
+    const uint32_t keep = n < m ? n : m;
+    // this thread's keys: positions t, t + 128, ...
+    uint64_t mine[kPruneKeysPerThread];
+#pragma unroll
+    for (int j = 0; j < kPruneKeysPerThread; ++j) {
+        const uint32_t i = t + j * 128;
         uint64_t k = 0;
         if (i < ns) k = state_keys[static_cast<size_t>(q) * m + i];
         else if (i < n) k = app_keys[static_cast<size_t>(q) * cap + (i - ns)];
-        keys[i] = k;
-        dummy[i] = 0.0f;
+        mine[j] = k;
     }
+    if (t == 0) s_sel = 0;
+    // (1) T = the largest value with count(keys >= T) >= keep  ==  the keep-th largest key (keys are unique)
+    uint64_t T = 0;
+    if (n > m) {
+#pragma unroll 1
+        for (int bit = 63; bit >= 0; --bit) {
+            const uint64_t cand = T | (1ull << bit);
+            uint32_t c = 0;
+#pragma unroll
+            for (int j = 0; j < kPruneKeysPerThread; ++j) c += mine[j] >= cand ? 1u : 0u;
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (lane == 0) s_part[bit & 1][warp] = c;
+            named_bar_sync(1, 128);
+            const uint32_t tot = s_part[bit & 1][0] + s_part[bit & 1][1] + s_part[bit & 1][2] + s_part[bit & 1][3];
+            if (tot >= m) T = cand;
+        }
+    } else {
+        T = 1;                                        // keep every (non-zero) key
+        named_bar_sync(1, 128);
+    }
+    // (2) compact the selected keys (order is irrelevant: they are sorted next)
+    uint32_t n2 = 128;
+    while (n2 < keep) n2 <<= 1;
+    for (uint32_t i = t; i < n2; i += 128) { keys[i] = 0; dummy[i] = 0.0f; }
     named_bar_sync(1, 128);
+#pragma unroll
+    for (int j = 0; j < kPruneKeysPerThread; ++j)
+        if (mine[j] >= T) keys[atomicAdd(&s_sel, 1u)] = mine[j];
+    named_bar_sync(1, 128);
+    // (3) sort the <= M survivors
     bitonic_desc(keys, dummy, n2, t);
-    const uint32_t keep = n < m ? n : m;
     for (uint32_t i = t; i < keep; i += 128) state_keys[static_cast<size_t>(q) * m + i] = keys[i];
     if (t == 0) {
         state_cnt[q] = keep;
         app_cnt[static_cast<size_t>(q) * kCntStride] = 0;
         if (keep >= m) tau[q] = key_score(keys[m - 1]);
+    }
+}
+
+// Warp-per-query variant of the prune for the common shapes (M <= 128, M + cap <= 32 * KPL): the
+// keys of one query live in one warp's registers, so the 64 select rounds need no block barrier
+// (the CTA version spends most of its time in them), and 4 queries share a CTA.
+template <int KPL>
+__global__ void __launch_bounds__(128)
+batch_prune_warp_kernel(unsigned long long *__restrict__ state_keys, uint32_t *__restrict__ state_cnt, uint32_t m,
+                        unsigned long long *__restrict__ app_keys, uint32_t *__restrict__ app_cnt, uint32_t cap,
+                        float *__restrict__ tau, uint32_t nq)
+{
+    __shared__ uint64_t s_keys[4][128];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x * 4 + warp;
+    if (q >= nq) return;
+    const uint32_t ns = state_cnt[q];
+    uint32_t na = app_cnt[static_cast<size_t>(q) * kCntStride];
+    if (na > cap) na = cap;
+    const uint32_t n = ns + na;
+    const uint32_t keep = n < m ? n : m;
+    uint64_t mine[KPL];
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+        const uint32_t i = lane + j * 32;
+        uint64_t k = 0;
+        if (i < ns) k = state_keys[static_cast<size_t>(q) * m + i];
+        else if (i < n) k = app_keys[static_cast<size_t>(q) * cap + (i - ns)];
+        mine[j] = k;
+    }
+    uint64_t T = 1;                                   // n <= m: keep every (non-zero) key
+    if (n > m) {
+        // Select on the score half of the keys first (32-bit compares: the kernel is instruction bound,
+        // 1.7 warps per scheduler); the row half only matters when equal scores straddle the cut.
+        uint32_t mxh = 0;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) { const uint32_t h = static_cast<uint32_t>(mine[j] >> 32); mxh = h > mxh ? h : mxh; }
+        mxh = __reduce_max_sync(0xffffffffu, mxh);
+        uint32_t Th = 0;
+#pragma unroll 1
+        for (int bit = 31 - __clz(static_cast<int>(mxh | 1u)); bit >= 0; --bit) {   // bits above the top set bit are zero everywhere
+            const uint32_t cand = Th | (1u << bit);
+            uint32_t c = 0;
+#pragma unroll
+            for (int j = 0; j < KPL; ++j) c += static_cast<uint32_t>(mine[j] >> 32) >= cand ? 1u : 0u;
+            if (__reduce_add_sync(0xffffffffu, c) >= m) Th = cand;
+        }
+        uint32_t c_ge = 0;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) c_ge += static_cast<uint32_t>(mine[j] >> 32) >= Th ? 1u : 0u;
+        c_ge = __reduce_add_sync(0xffffffffu, c_ge);
+        T = static_cast<uint64_t>(Th) << 32;
+        if (c_ge != m) {                               // equal scores at the cut: order by the row half
+#pragma unroll 1
+            for (int bit = 31; bit >= 0; --bit) {
+                const uint64_t cand = T | (1ull << bit);
+                uint32_t c = 0;
+#pragma unroll
+                for (int j = 0; j < KPL; ++j) c += mine[j] >= cand ? 1u : 0u;
+                if (__reduce_add_sync(0xffffffffu, c) >= m) T = cand;
+            }
+        }
+    }
+    // compact the selected keys into this warp's 128 slots, then sort them (4 keys per lane)
+    uint64_t *sk = s_keys[warp];
+    for (uint32_t i = lane; i < 128; i += 32) sk[i] = 0;
+    __syncwarp();
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) cnt += mine[j] >= T ? 1u : 0u;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= static_cast<uint32_t>(d)) incl += x;
+    }
+    uint32_t pos = incl - cnt;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j)
+        if (mine[j] >= T) sk[pos++] = mine[j];
+    __syncwarp();
+    for (uint32_t k = 2; k <= 128; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (uint32_t e = 0; e < 2; ++e) {
+                const uint32_t i = lane + e * 32;                         // 64 compare-exchanges per stage
+                const uint32_t lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
+                const uint64_t a = sk[lo], b = sk[hi];
+                const bool desc = (lo & k) == 0;
+                if ((a < b) == desc) { sk[lo] = b; sk[hi] = a; }
+            }
+            __syncwarp();
+        }
+    for (uint32_t i = lane; i < keep; i += 32) state_keys[static_cast<size_t>(q) * m + i] = sk[i];
+    if (lane == 0) {
+        state_cnt[q] = keep;
+        app_cnt[static_cast<size_t>(q) * kCntStride] = 0;
+        if (keep >= m) tau[q] = key_score(sk[m - 1]);
     }
 }
 
@@ -843,7 +976,11 @@ cudaError_t batch_rescore_launch(const void *d_rows, int half, uint32_t pitch, u
 cudaError_t batch_prune_launch(unsigned long long *state_keys, uint32_t *state_cnt, uint32_t m, unsigned long long *app_keys,
                                uint32_t *app_cnt, uint32_t cap, float *tau, uint32_t nq, cudaStream_t st)
 {
-    batch_prune_kernel<<<nq, 128, 0, st>>>(state_keys, state_cnt, m, app_keys, app_cnt, cap, tau, nq);
+    constexpr int kKPL = 40;                       // warp version holds up to 1280 keys per query in registers
+    if (m <= 128 && m + cap <= 32 * kKPL && getenv("RLR_BATCH_PRUNE_CTA") == nullptr)
+        batch_prune_warp_kernel<kKPL><<<(nq + 3) / 4, 128, 0, st>>>(state_keys, state_cnt, m, app_keys, app_cnt, cap, tau, nq);
+    else
+        batch_prune_kernel<<<nq, 128, 0, st>>>(state_keys, state_cnt, m, app_keys, app_cnt, cap, tau, nq);
     return cudaGetLastError();
 }
 

@@ -157,3 +157,27 @@ def test_sharded_batch_merge_equals_single_store(flags_name):
     for sh in shards:
         sh.close()
     full.close()
+
+
+def test_batch_equal_scores_at_the_cut_are_ordered_by_row():
+    """Every row appears 20 times, so equal tensor-core scores straddle the top-m cut of every query: the
+    prune's select must fall back to the row half of the keys (lower row first), exactly like the full sort."""
+    import rust_local_rag_b200  # noqa: F401
+    from rust_local_rag_b200 import binding as B, engine
+    from oracle import orc
+    rng = np.random.default_rng(77)
+    base = orc.normalize_rows(rng.standard_normal((50, 256)).astype(F32))
+    rows = np.tile(base, (20, 1))                                   # 1000 rows
+    qs = rng.standard_normal((40, 256)).astype(F32)
+    s = engine.DeviceStore.from_rows(rows, flags=B.RLR_STORE_KEEP_F16)
+    full_rows, full_scores, full_n = s.search_batch(qs, 1000)      # complete ranking (CTA prune: m > 128)
+    assert (full_n == 1000).all()
+    for q in range(40):
+        order = np.lexsort((full_rows[q], -full_scores[q].astype(np.float64)))
+        assert (order == np.arange(1000)).all()                     # (score desc, row asc)
+    for m in (100, 7, 128):
+        r, sc, n = s.search_batch(qs, m)                            # warp prune
+        assert (n == m).all()
+        assert r.tobytes() == np.ascontiguousarray(full_rows[:, :m]).tobytes()
+        assert sc.tobytes() == np.ascontiguousarray(full_scores[:, :m]).tobytes()
+    s.close()
