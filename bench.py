@@ -385,8 +385,17 @@ def run_b200(a, guard=None):
         scan_ms = iso_ms.value
         how = "20 back-to-back launches after the timed region, CUDA events on the launch stream"
     achieved = algo_bytes / (scan_ms * 1e-3) / 1e9
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel from the committed
+    # `ncu --set full` capture; used only when that capture is of exactly this launch shape (else null)
+    traffic, traffic_src = None, None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["scan_topm_kernel"]
+        if t["rows"] == plan.n_local and t["dim"] == a.dim and t["elem_bytes"] == 4:
+            traffic, traffic_src = t["dram_bytes_read"] + t["dram_bytes_write"], t["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "scan_topm_kernel", "bytes_per_launch": algo_bytes,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "scan_topm_kernel", "bytes_per_launch": algo_bytes,
                 "ms_per_launch": scan_ms, "isolated_ms_per_launch": iso_ms.value,
                 "isolated_GBps": algo_bytes / (iso_ms.value * 1e-3) / 1e9, "peak_source": peak_src, "how": how,
                 "frac_of_nominal_8TBps": achieved / 8000.0}

@@ -105,6 +105,9 @@ typedef struct rlr_timings {
 /* store flags */
 #define RLR_STORE_KEEP_F16      0x1u  /* keep the f32 rows AND a binary16 copy of them      */
 #define RLR_STORE_CHECK_FINITE  0x2u  /* scan uploaded rows for NaN/Inf on the device      */
+#define RLR_STORE_NORMALIZE_ON_UPLOAD 0x8u /* run normalize (:1763-1771) on every uploaded/appended row on the
+                                            * device (same sequential arithmetic, same bits): bulk loads need not
+                                            * normalise 10M rows on one host core (apply_loaded_state, :1678-1680) */
 #define RLR_STORE_F16_ONLY      0x4u  /* keep only the binary16 copy (half the HBM, config 5) */
 
 /* search flags */

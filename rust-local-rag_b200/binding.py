@@ -21,6 +21,7 @@ RLR_MAX_DIM = 4096
 RLR_STORE_KEEP_F16 = 0x1
 RLR_STORE_CHECK_FINITE = 0x2
 RLR_STORE_F16_ONLY = 0x4
+RLR_STORE_NORMALIZE_ON_UPLOAD = 0x8
 RLR_QUERY_PRENORMALIZED = 0x1
 RLR_WANT_TIMINGS = 0x2
 RLR_SEARCH_F16 = 0x4

@@ -589,6 +589,8 @@ RLR_EXPORT int rlr_store_upload(rlr_store *s, uint64_t row0, uint64_t n, const f
         if (e == cudaSuccess)
             e = cudaMemcpy2D(dst32, s->pitch * sizeof(float), rows + r * host_pitch, host_pitch * sizeof(float),
                              s->dim * sizeof(float), cnt, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && (s->flags & RLR_STORE_NORMALIZE_ON_UPLOAD))      // :1678-1680 on the device, same bits
+            e = rlr::normalize_rows_launch(dst32, s->pitch, s->dim, cnt, 0);
         if (e == cudaSuccess && (s->flags & RLR_STORE_CHECK_FINITE)) {
             uint32_t *d_flag = nullptr, h_flag = 0;
             e = cudaMalloc(&d_flag, sizeof(uint32_t));

@@ -128,6 +128,8 @@ cudaError_t gather_rows_launch(const void *d_store, int half, uint32_t pitch, co
 cudaError_t synth_launch(float *d_rows, uint32_t pitch, void *d_rows16, uint32_t pitch16, uint32_t dim, uint64_t row_base, uint32_t n_rows,
                          int kind, uint64_t seed, uint64_t centroid_seed, uint32_t n_clusters, float sigma,
                          cudaStream_t stream);
+// in-place reference normalize of n_rows stored f32 rows (sequential arithmetic per row)
+cudaError_t normalize_rows_launch(float *d_rows, uint32_t pitch, uint32_t dim, uint64_t n_rows, cudaStream_t stream);
 cudaError_t finite_check_launch(const float *d_rows, uint64_t n_floats, uint32_t *d_flag, cudaStream_t stream);
 // rows[to[i]] = rows[from[i]] (disjoint sources and destinations), row_bytes a multiple of 16
 cudaError_t move_rows_launch(void *d_rows, uint32_t row_bytes, const uint32_t *d_from, const uint32_t *d_to, uint32_t n,

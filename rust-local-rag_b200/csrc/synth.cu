@@ -80,6 +80,45 @@ synth_kernel(float *__restrict__ out, uint32_t pitch, __half *__restrict__ out16
     }
 }
 
+// normalize (/root/reference/src/rag_engine.rs:1763-1771) of stored rows, in place: one thread owns
+// one row and sums x*x strictly left to right (mul and add rounded separately), then divides every
+// element by sqrt(sum) when sum > 1e-20 -- the bits the reference's load path produces (:1678-1680).
+// 32-column tiles go through shared memory so that global traffic is 128-byte coalesced.
+__global__ void __launch_bounds__(kRowsPerBlock)
+normalize_rows_kernel(float *__restrict__ rows, uint32_t pitch, uint32_t dim, uint64_t n_rows)
+{
+    __shared__ float tile[kRowsPerBlock][33];
+    const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const uint64_t r0 = static_cast<uint64_t>(blockIdx.x) * kRowsPerBlock;
+    float norm_sq = 0.0f;
+    for (uint32_t c0 = 0; c0 < dim; c0 += 32) {
+        for (uint32_t r = 0; r < 32; ++r) {
+            const uint64_t row = r0 + warp * 32 + r;
+            tile[warp * 32 + r][lane] = (row < n_rows && c0 + lane < dim) ? rows[row * pitch + c0 + lane] : 0.0f;
+        }
+        __syncwarp();
+        const uint32_t w = dim - c0 < 32 ? dim - c0 : 32;
+        for (uint32_t j = 0; j < w; ++j) { const float x = tile[t][j]; norm_sq = add_rn(norm_sq, mul_rn(x, x)); }
+        __syncwarp();
+    }
+    const bool scale = norm_sq > 1e-20f;
+    const float norm = __fsqrt_rn(norm_sq);
+    for (uint32_t c0 = 0; c0 < dim; c0 += 32) {
+        for (uint32_t r = 0; r < 32; ++r) {
+            const uint64_t row = r0 + warp * 32 + r;
+            tile[warp * 32 + r][lane] = (row < n_rows && c0 + lane < dim) ? rows[row * pitch + c0 + lane] : 0.0f;
+        }
+        __syncwarp();
+        for (uint32_t j = 0; j < 32; ++j) if (scale) tile[t][j] = __fdiv_rn(tile[t][j], norm);
+        __syncwarp();
+        for (uint32_t r = 0; r < 32; ++r) {
+            const uint64_t row = r0 + warp * 32 + r;
+            if (row < n_rows && c0 + lane < dim) rows[row * pitch + c0 + lane] = tile[warp * 32 + r][lane];
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void finite_check_kernel(const float4 *__restrict__ v, uint64_t n4, uint32_t *flag)
 {
     bool bad = false;
@@ -142,6 +181,14 @@ cudaError_t to_half_launch(const float *d_src, uint32_t src_pitch, void *d_dst, 
     if (n_rows == 0) return cudaSuccess;
     const uint32_t blocks = static_cast<uint32_t>(n_rows < 148 * 32 ? n_rows : 148 * 32);
     to_half_kernel<<<blocks, 256, 0, stream>>>(d_src, src_pitch, static_cast<__half *>(d_dst), dst_pitch, dim, n_rows);
+    return cudaGetLastError();
+}
+
+cudaError_t normalize_rows_launch(float *d_rows, uint32_t pitch, uint32_t dim, uint64_t n_rows, cudaStream_t stream)
+{
+    if (n_rows == 0) return cudaSuccess;
+    const uint64_t blocks = (n_rows + kRowsPerBlock - 1) / kRowsPerBlock;
+    normalize_rows_kernel<<<static_cast<unsigned>(blocks), kRowsPerBlock, 0, stream>>>(d_rows, pitch, dim, n_rows);
     return cudaGetLastError();
 }
 

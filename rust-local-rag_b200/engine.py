@@ -119,6 +119,16 @@ def get_index_path(data_dir: str, model_name: str) -> str:
     return os.path.join(data_dir, f"chunks_{sanitize_model_name(model_name)}.json")
 
 
+def get_sidecar_path(data_dir: str, model_name: str) -> str:
+    """Binary twin of chunks_{model}.json (same sanitised model name, :1465-1468): `.rlrbin`."""
+    return get_index_path(data_dir, model_name)[:-len(".json")] + ".rlrbin"
+
+
+SIDECAR_MAGIC = b"RLRB200\x00"
+# header: magic[8] | u32 index version (the reference's, 2) | u32 dim | u64 n_rows | u64 meta_bytes | u64 reserved
+SIDECAR_HEADER = 40
+
+
 class DeviceStore:
     """Owns one rlr_store handle."""
 
@@ -400,6 +410,73 @@ class RagEngine:
             eng.needs_reindex = True
         return eng
 
+    # ---- binary sidecar: the same PersistedState without ~10 bytes of JSON per float ----
+    def save_sidecar(self, path: str, block_rows: int = 1 << 17) -> None:
+        """Atomic tmp + rename like save_to_disk (:1600-1640).  Layout: 40-byte header, n_rows x dim f32
+        rows (little endian, as stored = as the reference would serialise them), then a UTF-8 JSON blob
+        with everything else of PersistedState (:1479-1486) and the chunks in ROW order."""
+        import struct
+        info = self.store.info()
+        n, dim = int(info.n_rows), int(info.dim)
+        meta = json.dumps({"model": self.model, "needs_reindex": bool(self.needs_reindex),
+                           "document_hashes": self.document_hashes,
+                           "chunks": [{"id": c.id, "document_name": c.document_name, "text": c.text,
+                                       "chunk_index": c.chunk_index, "page_number": c.page_number, "section": c.section,
+                                       "metadata": c.metadata} for c in self.chunks]}, ensure_ascii=False).encode("utf-8")
+        tmp = path + ".tmp"
+        with open(tmp, "wb") as f:
+            f.write(SIDECAR_MAGIC + struct.pack("<IIQQQ", 2, dim, n, len(meta), 0))
+            base = int(info.row_base)
+            for r0 in range(0, n, block_rows):
+                r1 = min(n, r0 + block_rows)
+                f.write(np.ascontiguousarray(self.store.read_rows(np.arange(base + r0, base + r1)), np.float32).tobytes())
+            f.write(meta)
+            f.flush()
+            os.fsync(f.fileno())
+        os.replace(tmp, path)
+
+    @classmethod
+    def from_sidecar(cls, path: str, model: str = "nomic-embed-text", device: int = 0, store_flags: int = 0,
+                     block_rows: int = 1 << 18, **kw) -> "RagEngine":
+        """apply_loaded_state (:1655-1696) for the binary sidecar: version gate, re-normalise EVERY row at load
+        (:1678-1680) -- on the device, same sequential arithmetic, same bits (RLR_STORE_NORMALIZE_ON_UPLOAD) --
+        and the unfingerprinted-index rule (:1686-1691).  Rows stream from a memory map in blocks."""
+        import struct
+        with open(path, "rb") as f:
+            head = f.read(SIDECAR_HEADER)
+        if len(head) != SIDECAR_HEADER or head[:8] != SIDECAR_MAGIC:
+            raise ValueError(f"{path}: not an rlr_b200 sidecar")
+        version, dim, n, meta_bytes, _ = struct.unpack("<IIQQQ", head[8:])
+        if version < 2:                          # :1664-1673 outdated index: wipe, mark for reindex
+            eng = cls([], DeviceStore.from_rows(np.zeros((0, 1), np.float32), device=device), model=model, **kw)
+            eng.needs_reindex = True
+            return eng
+        rows_bytes = n * dim * 4
+        if os.path.getsize(path) != SIDECAR_HEADER + rows_bytes + meta_bytes:
+            raise ValueError(f"{path}: truncated or corrupt sidecar")
+        with open(path, "rb") as f:
+            f.seek(SIDECAR_HEADER + rows_bytes)
+            meta = json.loads(f.read(meta_bytes).decode("utf-8"))
+        if len(meta["chunks"]) != n:
+            raise ValueError(f"{path}: {len(meta['chunks'])} chunk records for {n} rows")
+        metas = [DocumentChunk(id=ch["id"], document_name=ch.get("document_name", ""), text=ch.get("text", ""),
+                               chunk_index=int(ch.get("chunk_index", 0)), page_number=int(ch.get("page_number", 0)),
+                               section=ch.get("section"), metadata=ch.get("metadata") or {}) for ch in meta["chunks"]]
+        if n == 0:
+            store = DeviceStore.from_rows(np.zeros((0, max(dim, 1)), np.float32), device=device)
+        else:
+            rows = np.memmap(path, dtype="<f4", mode="r", offset=SIDECAR_HEADER, shape=(n, dim))
+            store = DeviceStore.empty(n, dim, device=device, flags=store_flags | B.RLR_STORE_NORMALIZE_ON_UPLOAD)
+            for r0 in range(0, n, block_rows):
+                store.upload(r0, np.ascontiguousarray(rows[r0:min(n, r0 + block_rows)]))
+            del rows
+        eng = cls(metas, store, model=model, **kw)
+        eng.needs_reindex = bool(meta.get("needs_reindex", False))
+        eng.document_hashes = dict(meta.get("document_hashes", {}))
+        if not eng.document_hashes and metas:    # :1686-1691
+            eng.needs_reindex = True
+        return eng
+
     @classmethod
     def from_rows(cls, rows: np.ndarray, chunk_ids: Optional[Sequence[str]] = None, normalize: bool = True,
                   device: int = 0, **kw) -> "RagEngine":
@@ -429,8 +506,9 @@ class RagEngine:
             del self.chunks[len(self.chunks) - len(old):]
         emb = np.array(embeddings, dtype=np.float32, order="C")
         lib = B.load()
-        for i in range(emb.shape[0]):
-            B.check(lib.rlr_normalize(emb[i].ctypes.data_as(C.POINTER(C.c_float)), emb.shape[1]))
+        if not (self.store.info().flags & B.RLR_STORE_NORMALIZE_ON_UPLOAD):     # else the store normalises on append
+            for i in range(emb.shape[0]):
+                B.check(lib.rlr_normalize(emb[i].ctypes.data_as(C.POINTER(C.c_float)), emb.shape[1]))
         if len(chunks):
             first = self.store.append(emb)
             assert first == len(self.chunks)

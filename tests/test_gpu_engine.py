@@ -171,3 +171,40 @@ def test_hybrid_search_with_bm25_index_on_chunk_text(orc):
     assert not eng.lexical.contains("c3") and eng.lexical.contains("n0")
     hits = eng.search("quantum entanglement", 4, engine.QueryWeights(embedding=0.0, lexical=1.0))
     assert sorted(h.chunk_id for h in hits) == ["n0", "n1", "n2", "n3"] and all(h.lexical_score == 1.0 for h in hits)
+
+
+def test_binary_sidecar_round_trip(tmp_path, orc):
+    """N1: chunks_{model}.rlrbin carries the same PersistedState as the JSON file.  Loading it re-normalises
+    every row like apply_loaded_state does (:1678-1680) -- on the device, and the bits must be the oracle's."""
+    import rust_local_rag_b200  # noqa: F401
+    from rust_local_rag_b200 import engine
+    n, dim = 1500, 200                                                       # dim not a multiple of 32: padded pitch
+    path = engine.get_index_path(str(tmp_path), "nomic-embed-text")
+    chunks = _write_index(path, n, dim, seed=4)
+    eng = engine.RagEngine.load_from_disk(str(tmp_path), model="nomic-embed-text")
+    side = engine.get_sidecar_path(str(tmp_path), "nomic-embed-text")
+    assert os.path.basename(side) == "chunks_nomic-embed-text.rlrbin"
+    eng.save_sidecar(side)
+    assert os.path.getsize(side) < os.path.getsize(path) / 3                 # ~4 bytes per float instead of ~20
+    eng2 = engine.RagEngine.from_sidecar(side, model="nomic-embed-text")
+    assert [c.id for c in eng2.chunks] == [c.id for c in eng.chunks]
+    assert eng2.document_hashes == eng.document_hashes and not eng2.needs_reindex
+    assert eng2.chunks[7].page_number == eng.chunks[7].page_number and eng2.chunks[7].metadata == eng.chunks[7].metadata
+    once = orc.normalize_rows(np.array([c["embedding"] for c in chunks.values()], F32))   # what the JSON load stored
+    twice = orc.normalize_rows(once)                                                      # what the next load scans
+    assert eng2.store.read_rows(np.arange(n)).tobytes() == twice.tobytes()
+    q = np.random.default_rng(6).standard_normal(dim).astype(F32)
+    hits = eng2.search_with_diversity(q, 20, 0.6)
+    ref = orc.search_with_diversity(twice, q, 20, 0.6, full_sort=True)
+    assert [h.row for h in hits] == ref[0].tolist()
+    assert np.array([h.score for h in hits], F32).tobytes() == ref[1].tobytes()
+    # replace_document on a normalise-on-upload store: rows are normalised exactly once
+    new = np.random.default_rng(7).standard_normal((3, dim)).astype(F32) * 3
+    eng2.replace_document("doc1.pdf", [engine.DocumentChunk(id=f"x{i}", document_name="doc1.pdf") for i in range(3)], new)
+    m = len(eng2.chunks)
+    assert eng2.store.read_rows(np.arange(m - 3, m)).tobytes() == orc.normalize_rows(new).tobytes()
+    # corrupt / foreign files are refused
+    with open(side, "r+b") as f:
+        f.write(b"NOTMAGIC")
+    with pytest.raises(ValueError):
+        engine.RagEngine.from_sidecar(side)
