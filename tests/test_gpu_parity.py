@@ -442,3 +442,74 @@ def test_f16_synthetic_store_matches_rounded_cpu_rows(eng, rlr, orc):
     ref = _round16(orc.synth_rows(n, dim, kind=1, n_clusters=64, row0=500))
     assert same(s.read_rows(np.arange(500, 500 + n)), ref)
     s.close()
+
+
+def _host_ram_gb():
+    try:
+        import psutil
+        return psutil.virtual_memory().available / 1e9
+    except Exception:
+        return 0.0
+
+
+def test_config3_10m_x_768_full_size(eng, orc):
+    """BASELINE configs[2] / the bench workload at FULL size: 10M x 768 f32 (30.7 GB), top_k=100, diversity 0.7.
+    (a) with enough host RAM the CPU oracle scans the same 10M rows (bit-identical synthetic twin) and every
+        row, score and MMR pick must match bit for bit;
+    (b) always: two row shards posting through a mailbox (the fused multi-GPU exchange, here on one GPU)
+        must reproduce the single-store result exactly, every returned score must be the oracle's sequential
+        dot of the regenerated row, and the size-independent properties hold."""
+    import ctypes as C
+    import torch
+    from rust_local_rag_b200 import binding as B, dist as rdist
+    if torch.cuda.mem_get_info()[0] < 70e9:
+        pytest.skip("needs ~62 GB of free HBM")
+    n, dim, k, lam = 10_000_000, 768, 100, 0.7
+    kw = dict(kind=1, seed=0x5EED0001, centroid_seed=0x5EED00C0, n_clusters=4096, sigma=0.65)
+    s = eng.DeviceStore.synthetic(n, dim, **kw)
+    qs = orc.synth_rows(3, dim, **{**kw, "seed": 0x5EED0002})
+    got = [s.search_mmr(q, k, lam, W(), flags=B.RLR_QUERY_PRENORMALIZED) for q in qs]
+    pools = [s.search_topm(q, 300, W(), flags=B.RLR_QUERY_PRENORMALIZED) for q in qs]
+    for (rows, score, emb, lex), pool, q in zip(got, pools, qs):
+        assert len(rows) == k and len(set(rows.tolist())) == k
+        assert set(rows.tolist()) <= set(pool[0].tolist()) and rows[0] == pool[0][0]      # MMR picks from the pool, best first
+        assert (np.diff(pool[1].astype(np.float64)) <= 0).all()
+        for r, e in list(zip(rows, emb))[::7]:                                           # exact scores of regenerated rows
+            assert np.float32(orc.dot(q, orc.synth_rows(1, dim, row0=int(r), **kw)[0])).tobytes() == np.float32(e).tobytes()
+    # (b) two shards (uneven) + mailbox on the same GPU
+    lib = B.load()
+    bounds = [(0, 4_200_000), (4_200_000, n)]
+    shards = [eng.DeviceStore.synthetic(hi - lo, dim, row_base=lo, **kw) for lo, hi in bounds]
+    ctxs = []
+    for sh in shards:
+        c = C.c_void_p()
+        B.check(lib.rlr_ctx_create(sh.handle, C.byref(c)))
+        ctxs.append(c)
+    mb = C.c_void_p()
+    B.check(lib.rlr_mailbox_create(0, 2, 300, 2, C.byref(mb)))
+    qd = torch.zeros(B.RLR_MAX_DIM + 64, device="cuda")
+    out = torch.zeros((300, 2), dtype=torch.int64, device="cuda")
+    out_n = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for seq, (q, pool) in enumerate(zip(qs, pools), start=1):
+        qd.zero_(); qd[:dim] = torch.from_numpy(q).cuda()
+        for r in range(2):
+            B.check(lib.rlr_topm_post_async(ctxs[r], mb, r, seq, C.c_void_p(qd.data_ptr()), 0.7, 0.3, None, None, 0, 300, st))
+        B.check(lib.rlr_mailbox_merge_async(ctxs[0], mb, seq, 300, C.c_void_p(out.data_ptr()), C.c_void_p(out_n.data_ptr()), st))
+        torch.cuda.synchronize()
+        mr, ms, me, _ = rdist.decode_result(out, int(out_n.item()))
+        assert same(mr, pool[0]) and same(ms, pool[1]) and same(me, pool[2])
+    lib.rlr_mailbox_close(mb)
+    for c in ctxs:
+        lib.rlr_ctx_destroy(c)
+    for sh in shards:
+        sh.close()
+    # (a) the oracle over all 10M rows
+    if _host_ram_gb() > 45 and orc.max_threads() >= 8:
+        host = orc.synth_rows(n, dim, **kw)
+        for q, g in zip(qs[:2], got[:2]):
+            ref = orc.search_with_diversity(host, q, k, lam, normalize_query=False, full_sort=False, threads=orc.max_threads())
+            for a, b in zip(g, ref):
+                assert same(a, b)
+        del host
+    s.close()
