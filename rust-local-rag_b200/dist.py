@@ -198,12 +198,17 @@ def sharded_search_batch(store, group, queries, m: int, flags: int = 0, device=N
     q = np.ascontiguousarray(queries, dtype=np.float32)
     nq = q.shape[0]
     dev = device if device is not None else torch.device("cuda", store.info().device)
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    stream = torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else None   # cpu: the gloo tests' stand-in store
     local = torch.empty((nq, m), dtype=torch.int64, device=dev)
     store.search_batch_device(q, m, local, None, stream, flags)
     if world > 1:
         gathered = torch.empty((world, nq, m), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(gathered.view(world * nq, m), local, group=group)
+        if dist.get_backend(group) == "nccl":
+            dist.all_gather_into_tensor(gathered.view(world * nq, m), local, group=group)
+        else:
+            parts = [torch.empty_like(local) for _ in range(world)]
+            dist.all_gather(parts, local, group=group)
+            gathered = torch.stack(parts)
         merged = torch.empty((nq, m), dtype=torch.int64, device=dev)
         cnt = torch.empty(nq, dtype=torch.int32, device=dev)
         store.batch_merge(gathered, world, nq, m, merged, cnt, stream)

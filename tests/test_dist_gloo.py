@@ -166,3 +166,87 @@ def test_key_codec_roundtrip():
     assert back.tobytes() == (s + F32(0.0)).tobytes()           # -0.0 is folded onto +0.0
     order = np.argsort(keys)[::-1]
     assert (np.diff(s[order].astype(np.float64)) <= 0).all()    # key order == score order
+
+
+class OracleBatchStore:
+    """TEST-ONLY stand-in for engine.DeviceStore on the batched path (CPU tensors): per-query key lists
+    from the oracle's exact scan of this rank's shard, and the per-query merge."""
+
+    def __init__(self, orc, shard_rows, row0):
+        self.orc, self.rows, self.row0 = orc, shard_rows, row0
+
+    def search_batch_device(self, queries, m, d_keys, d_cnt=None, stream=None, flags=0):
+        out = d_keys.numpy().view(np.uint64)
+        out[:] = 0
+        for q in range(queries.shape[0]):
+            r, s = self.orc.embedding_candidates(self.rows, queries[q], m, normalize_query=False)
+            out[q, :len(r)] = (_ord(s).astype(np.uint64) << np.uint64(32)) | (~(r + np.uint32(self.row0))).astype(np.uint32).astype(np.uint64)
+
+    def batch_merge(self, d_lists, n_lists, nq, m, d_out, d_out_cnt=None, stream=None):
+        lists = d_lists.numpy().view(np.uint64)
+        out = d_out.numpy().view(np.uint64)
+        out[:] = 0
+        for q in range(nq):
+            k = lists[:, q, :].reshape(-1)
+            k = np.sort(k[k != 0])[::-1][:m]
+            out[q, :len(k)] = k
+            if d_out_cnt is not None:
+                d_out_cnt[q] = len(k)
+
+
+def _batch_worker(rank, world, port, n, dim, nq, m, ret):
+    sys.path.insert(0, ROOT)
+    import rust_local_rag_b200  # noqa: F401
+    from rust_local_rag_b200 import dist as rdist
+    from oracle import orc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rows = orc.synth_rows(n, dim, kind=1, n_clusters=16, threads=1)
+        plan = rdist.ShardPlan(n, world, rank, head_rows=n // (3 * world))       # uneven shards
+        store = OracleBatchStore(orc, rows[plan.row0:plan.row0 + plan.n_local], plan.row0)
+        qs = orc.synth_rows(nq, dim, kind=1, seed=7, n_clusters=16, threads=1)
+        r, s, cnt = rdist.sharded_search_batch(store, dist.group.WORLD, qs, m, 0, torch.device("cpu"))
+        if rank == world - 1:                                                    # valid on every rank
+            ret.put((r.tolist(), s.view(np.uint32).tolist(), cnt.tolist()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_batch_matches_unsharded_oracle(orc):
+    world, n, dim, nq, m = 2, 1501, 64, 9, 40
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 29500 + os.getpid() % 2000 + 11
+    procs = [ctx.Process(target=_batch_worker, args=(r, world, port, n, dim, nq, m, ret)) for r in range(world)]
+    [p.start() for p in procs]
+    rows_g, scores_g, cnt = ret.get(timeout=180)
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    rows = orc.synth_rows(n, dim, kind=1, n_clusters=16, threads=1)
+    qs = orc.synth_rows(nq, dim, kind=1, seed=7, n_clusters=16, threads=1)
+    for q in range(nq):
+        R, S = orc.embedding_candidates(rows, qs[q], m, normalize_query=False)
+        assert cnt[q] == m and rows_g[q] == R.tolist() and scores_g[q] == S.view(np.uint32).tolist()
+
+
+def test_shard_plan_with_head_rows():
+    from rust_local_rag_b200.dist import ShardPlan
+    for n, g, head in ((10_000_000, 8, 992_666), (1000, 3, 10), (7, 2, 0), (100, 4, None), (100, 1, 5)):
+        plans = [ShardPlan(n, g, r, head_rows=head) for r in range(g)]
+        assert plans[0].row0 == 0 and sum(p.n_local for p in plans) == n
+        for a, b in zip(plans, plans[1:]):
+            assert a.row0 + a.n_local == b.row0
+        if head is not None and g > 1:
+            assert plans[0].n_local == head
+            rest = [p.n_local for p in plans[1:]]
+            assert max(rest) - min(rest) <= 1
+        for row in (0, n // 2, n - 1):
+            o = plans[0].owner(row)
+            assert plans[o].row0 <= row < plans[o].row0 + plans[o].n_local
+    # tail-balanced: scan(rank 0) + tail == scan(others)
+    h = ShardPlan.balanced_head_rows(10_000_000, 8, tail_rows=300_000)
+    other = (10_000_000 - h) / 7
+    assert abs((h + 300_000) - other) < 2
