@@ -252,10 +252,13 @@ class RagEngine {
     int device_ = 0;
     bool needs_reindex_ = false;
 
+    bool normalize_on_upload_ = false;               // sidecar loads: normalize (:1678-1680) runs on the device
+
     void upload(const std::vector<float> &rows)
     {
         if (store_) { rlr_store_destroy(store_); store_ = nullptr; }
-        check(rlr_store_create(device_, dim_ ? dim_ : 1, chunks_.size(), rows.empty() ? nullptr : rows.data(), dim_, 0, 0, &store_));
+        check(rlr_store_create(device_, dim_ ? dim_ : 1, chunks_.size(), rows.empty() ? nullptr : rows.data(), dim_, 0,
+                               normalize_on_upload_ ? RLR_STORE_NORMALIZE_ON_UPLOAD : 0, &store_));
         row_of_.clear();
         for (uint32_t i = 0; i < chunks_.size(); ++i) row_of_[chunks_[i].id] = i;
     }
@@ -350,6 +353,50 @@ public:
         upload(rows);
     }
 
+    // Binary sidecar `chunks_{model}.rlrbin` written by the Python mirror's save_sidecar:
+    // 40-byte header (magic "RLRB200\0", u32 version, u32 dim, u64 n_rows, u64 meta_bytes, u64 reserved), the
+    // n x dim f32 rows as stored, then a JSON blob {model, needs_reindex, document_hashes, chunks:[...] in row order}.
+    // apply_loaded_state semantics: version gate (:1664), re-normalise every row (:1678, on the device), :1686 rule.
+    void load_sidecar(const std::string &path)
+    {
+        std::ifstream f(path, std::ios::binary);
+        if (!f) throw Error(RLR_ERR_INVALID_ARG, "cannot open " + path);
+        char head[40];
+        f.read(head, 40);
+        if (f.gcount() != 40 || std::memcmp(head, "RLRB200\0", 8) != 0) throw Error(RLR_ERR_INVALID_ARG, path + ": not an rlr_b200 sidecar");
+        uint32_t version, dim; uint64_t n, meta_bytes;
+        std::memcpy(&version, head + 8, 4); std::memcpy(&dim, head + 12, 4);
+        std::memcpy(&n, head + 16, 8); std::memcpy(&meta_bytes, head + 24, 8);
+        chunks_.clear();
+        dim_ = 0;
+        std::vector<float> rows;
+        if (version < 2) { needs_reindex_ = true; upload(rows); return; }
+        rows.resize(n * dim);
+        f.read(reinterpret_cast<char *>(rows.data()), static_cast<std::streamsize>(rows.size() * 4));
+        std::string meta(meta_bytes, '\0');
+        f.read(&meta[0], static_cast<std::streamsize>(meta_bytes));
+        if (!f || f.peek() != std::char_traits<char>::eof()) throw Error(RLR_ERR_INVALID_ARG, path + ": truncated or corrupt sidecar");
+        const Json root = JsonParser(meta).value();
+        const Json *ch = root.get("chunks");
+        if (!ch || ch->kind != Json::Arr || ch->arr.size() != n) throw Error(RLR_ERR_INVALID_ARG, path + ": chunk records do not match the row count");
+        for (auto &c : ch->arr) {
+            DocumentChunk d;
+            if (auto *v = c.get("id")) d.id = v->str;
+            if (auto *v = c.get("document_name")) d.document_name = v->str;
+            if (auto *v = c.get("text")) d.text = v->str;
+            if (auto *v = c.get("chunk_index")) d.chunk_index = static_cast<size_t>(v->num);
+            if (auto *v = c.get("page_number")) d.page_number = static_cast<size_t>(v->num);
+            if (auto *v = c.get("section")) if (v->kind == Json::Str) d.section = v->str;
+            chunks_.push_back(std::move(d));
+        }
+        dim_ = dim;
+        const Json *nr = root.get("needs_reindex"), *dh = root.get("document_hashes");
+        needs_reindex_ = nr && nr->kind == Json::Bool && nr->b;
+        if ((!dh || dh->obj.empty()) && !chunks_.empty()) needs_reindex_ = true;
+        normalize_on_upload_ = true;
+        upload(rows);
+    }
+
     // rows already in memory (normalised here like insert does, :359)
     void load_rows(std::vector<DocumentChunk> chunks, std::vector<float> rows, uint32_t dim)
     {
@@ -432,7 +479,8 @@ public:
         }
         if (!chunks.empty()) {
             if (dim_ == 0) dim_ = static_cast<uint32_t>(embeddings.size() / chunks.size());
-            for (size_t i = 0; i < chunks.size(); ++i) check(rlr_normalize(embeddings.data() + i * dim_, dim_));   // :359
+            if (!normalize_on_upload_)                   // else the store normalises what it is given
+                for (size_t i = 0; i < chunks.size(); ++i) check(rlr_normalize(embeddings.data() + i * dim_, dim_));   // :359
             uint64_t first = 0;
             if (!store_ || chunks_.empty()) {
                 chunks_ = std::move(chunks);

@@ -641,7 +641,8 @@ static uint32_t pick_buf_cap(uint32_t m)
     uint32_t cap = 512;
     while (cap < want) cap <<= 1;
     if (cap > static_cast<uint32_t>(kTopBuf)) cap = kTopBuf;
-    if (const char *e = getenv("RLR_DEBUG_BUFCAP")) {       // tuning knob (power of two, >= m + R)
+    static const char *const bufcap_env = getenv("RLR_DEBUG_BUFCAP");
+    if (const char *e = bufcap_env) {                       // tuning knob (power of two, >= m + R)
         const uint32_t v = static_cast<uint32_t>(atoi(e));
         if (v >= m + R && v <= static_cast<uint32_t>(kTopBuf) && (v & (v - 1)) == 0) cap = v;
     }
@@ -651,9 +652,10 @@ static uint32_t pick_buf_cap(uint32_t m)
 cudaError_t scan_launch(const ScanArgs &a, cudaStream_t stream)
 {
     const uint32_t buf_cap = a.buf_cap ? a.buf_cap : pick_buf_cap(a.m);
-    const bool no_merge = getenv("RLR_DEBUG_NOMERGE") != nullptr;   // tuning knob: time the scan without final_merge
+    static const bool no_merge = getenv("RLR_DEBUG_NOMERGE") != nullptr;   // tuning knob: time the scan without final_merge
+    static const bool no_global_tau = getenv("RLR_DEBUG_NOGLOBALTAU") != nullptr;
     uint32_t r_pub = (a.m + a.grid - 1) / a.grid;                    // r-th best published per CTA (0 = off)
-    if (r_pub > static_cast<uint32_t>(kTopR) || a.d_pub == nullptr || getenv("RLR_DEBUG_NOGLOBALTAU")) r_pub = 0;
+    if (r_pub > static_cast<uint32_t>(kTopR) || a.d_pub == nullptr || no_global_tau) r_pub = 0;
     const uint32_t n_chunks = a.pitch / (a.half ? 64u : 32u);
     if (a.half)
         scan_topm_kernel<true><<<a.grid, kScanThreads, a.smem_bytes, stream>>>(

@@ -15,7 +15,9 @@ int main(int argc, char **argv)
     if (argc < 5) { fprintf(stderr, "usage: engine_cli index.json query.f32 top_k diversity\n"); return 2; }
     try {
         rlr::RagEngine eng(0);
-        eng.load_file(argv[1]);
+        const std::string idx = argv[1];
+        if (idx.size() > 7 && idx.substr(idx.size() - 7) == ".rlrbin") eng.load_sidecar(idx);
+        else eng.load_file(idx);
         std::ifstream qf(argv[2], std::ios::binary);
         std::vector<char> raw((std::istreambuf_iterator<char>(qf)), std::istreambuf_iterator<char>());
         std::vector<float> q(raw.size() / 4);

@@ -131,3 +131,28 @@ def test_cpp_host_hybrid_text_query(tmp_path, orc):
         assert [r["chunk_id"] for r in out["results"]] == [ids[r] for r in ref[0]], query
         assert [r["score_bits"] for r in out["results"]] == ref[1].view(np.uint32).tolist()
         assert [r["lex_bits"] for r in out["results"]] == ref[3].view(np.uint32).tolist()
+
+
+@pytest.mark.gpu
+def test_cpp_host_loads_the_binary_sidecar(tmp_path, orc):
+    """rlr::RagEngine::load_sidecar reads what the Python mirror's save_sidecar wrote; rows are re-normalised on the
+    device at load (:1678-1680), so results are the oracle's on the twice-normalised rows."""
+    from rust_local_rag_b200 import engine
+    exe = _build_cli(str(tmp_path))
+    n, dim = 500, 40
+    idx = os.path.join(tmp_path, "chunks_m.json")
+    chunks = _write_index(idx, n, dim, seed=8)
+    ids = list(chunks)
+    eng = engine.RagEngine.from_chunks_json(idx, model="m")
+    side = os.path.join(tmp_path, "chunks_m.rlrbin")
+    eng.save_sidecar(side)
+    twice = orc.normalize_rows(orc.normalize_rows(np.array([c["embedding"] for c in chunks.values()], F32)))
+    qv = np.random.default_rng(12).standard_normal(dim).astype(F32)
+    qp = os.path.join(tmp_path, "q.f32")
+    qv.tofile(qp)
+    out = json.loads(subprocess.run([exe, side, qp, "9", "0.4"], capture_output=True, text=True, check=True).stdout)
+    ref = orc.search_with_diversity(twice, qv, 9, 0.4, full_sort=True)
+    assert out["n"] == n and not out["needs_reindex"]
+    assert [r["chunk_id"] for r in out["results"]] == [ids[r] for r in ref[0]]
+    assert [r["score_bits"] for r in out["results"]] == ref[1].view(np.uint32).tolist()
+    assert [r["page"] for r in out["results"]] == [1 + int(r) % 4 for r in ref[0]]
