@@ -1479,12 +1479,13 @@ struct rlr_mailbox {
     uint8_t *base = nullptr;          // root's allocation (local on the root, an IPC mapping elsewhere)
     uint32_t *d_status = nullptr;     // local
     size_t bytes = 0;
-    // layout: [0] consumed u64 | [128] flags[ring][n_ranks] u64 | counts[ring][n_ranks] u32 | (4 KB aligned) lists
-    size_t flags_off() const { return 128; }
+    // layout: [0] consumed[ring] u64 (one word per slot: the last sequence number merged out of it)
+    //         | [1024] flags[ring][n_ranks] u64 | counts[ring][n_ranks] u32 | (4 KB aligned) lists
+    size_t flags_off() const { return 1024; }
     size_t counts_off() const { return flags_off() + static_cast<size_t>(ring) * n_ranks * 8; }
     size_t lists_off() const { return (counts_off() + static_cast<size_t>(ring) * n_ranks * 4 + 4095) & ~static_cast<size_t>(4095); }
     size_t total() const { return lists_off() + static_cast<size_t>(ring) * n_ranks * m_cap * sizeof(rlr_cand); }
-    unsigned long long *consumed() const { return reinterpret_cast<unsigned long long *>(base); }
+    unsigned long long *consumed(uint32_t slot) const { return reinterpret_cast<unsigned long long *>(base) + slot; }
     unsigned long long *flag(uint32_t slot, uint32_t r) const { return reinterpret_cast<unsigned long long *>(base + flags_off()) + static_cast<size_t>(slot) * n_ranks + r; }
     uint32_t *count(uint32_t slot, uint32_t r) const { return reinterpret_cast<uint32_t *>(base + counts_off()) + static_cast<size_t>(slot) * n_ranks + r; }
     rlr_cand *list(uint32_t slot, uint32_t r) const { return reinterpret_cast<rlr_cand *>(base + lists_off()) + (static_cast<size_t>(slot) * n_ranks + r) * m_cap; }
@@ -1610,7 +1611,7 @@ RLR_EXPORT int rlr_topm_post_async(rlr_ctx *c, rlr_mailbox *mb, uint32_t my_rank
     a.d_lists = c->d_lists; a.d_counts = c->d_counts; a.d_ticket = c->d_ticket; a.d_pub = c->d_pub;
     a.d_out = mb->list(slot, my_rank); a.d_out_n = mb->count(slot, my_rank);
     a.post.flag = mb->flag(slot, my_rank);
-    a.post.consumed = mb->consumed();
+    a.post.consumed = mb->consumed(slot);
     a.post.seq = seq; a.post.ring = mb->ring; a.post.status = mb->d_status;
     CU_TRY(rlr::scan_launch(a, st));
     ++c->launches;
@@ -1626,7 +1627,7 @@ RLR_EXPORT int rlr_mailbox_merge_async(rlr_ctx *c, rlr_mailbox *mb, uint64_t seq
     if (seq == 0) return fail(RLR_ERR_INVALID_ARG, "sequence numbers start at 1");
     CU_TRY(cudaSetDevice(mb->device));
     const uint32_t slot = static_cast<uint32_t>(seq % mb->ring);
-    CU_TRY(rlr::mailbox_merge_launch(mb->list(slot, 0), mb->m_cap, mb->flag(slot, 0), seq, mb->consumed(), mb->n_ranks, m,
+    CU_TRY(rlr::mailbox_merge_launch(mb->list(slot, 0), mb->m_cap, mb->flag(slot, 0), seq, mb->consumed(slot), mb->n_ranks, m,
                                      static_cast<rlr_cand *>(d_out), static_cast<uint32_t *>(d_out_n), mb->d_status,
                                      static_cast<cudaStream_t>(stream)));
     ++c->launches;

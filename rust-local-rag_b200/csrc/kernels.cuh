@@ -21,7 +21,8 @@ constexpr int kQueryCap = RLR_MAX_DIM + 128; // floats, zero padded (a stage spa
 // release store.  See mailbox_merge_launch.
 struct ScanPost {
     unsigned long long *flag;            // null: no post (plain local scan)
-    const unsigned long long *consumed;  // slot free once *consumed + ring >= seq
+    const unsigned long long *consumed;  // this SLOT's word: free once *consumed + ring >= seq (the root has merged
+                                         // the query that used the slot `ring` sequence numbers ago)
     unsigned long long seq;
     uint32_t ring;
     uint32_t *status;                    // local word, set non-zero if the wait timed out

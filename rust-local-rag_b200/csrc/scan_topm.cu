@@ -610,7 +610,11 @@ void scan_plan(int sm_count, int max_smem_optin, uint32_t n_rows, uint32_t pitch
     const uint32_t q_floats = KB * CH * epb;
     a->half = half;
     const uint32_t n_tiles = (n_rows + R - 1) / R;
-    int grid = sm_count;
+    // tuning knob: leave a few SMs to other streams' small kernels (merge / MMR of the previous query)
+    // (default 2: measured on a B200, the scan reads HBM just as fast from 140 SMs as from 148 -- 7.52 TB/s either
+    // way -- and with two queries in flight the freed SMs let the previous query's tail overlap this scan)
+    static const int reserved = getenv("RLR_SCAN_SMS_RESERVED") ? atoi(getenv("RLR_SCAN_SMS_RESERVED")) : 2;
+    int grid = sm_count - (reserved > 0 && reserved < sm_count ? reserved : 0);
     if (static_cast<uint32_t>(grid) > n_tiles) grid = static_cast<int>(n_tiles);
     if (grid < 1) grid = 1;
     // as many stages as fit (1 KB slack for the manual 1024 B alignment)

@@ -265,6 +265,24 @@ class CudaBackend:
         self.mailbox_ready = True
         dist.barrier(group=group)
 
+    # ---- lanes: several queries in flight on one rank (one ctx = one workspace per lane; the caller
+    # runs each lane on its own CUDA stream, e.g. `with torch.cuda.stream(s): sharded_search(...)`).
+    # While the last CTA of one scan merges its per-CTA lists and rank 0 runs merge + MMR, the next
+    # query's scan already streams rows on the other SMs.  The mailbox ring must be a multiple of the
+    # number of lanes (each slot is then always used by the same lane, in order).
+    def add_lane(self) -> int:
+        if not hasattr(self, "ctxs"):
+            self.ctxs = [self.ctx]
+        c = C.c_void_p()
+        self.B.check(self.lib.rlr_ctx_create(self.store.handle, C.byref(c)))
+        if self.search_flags:
+            self.B.check(self.lib.rlr_ctx_set_flags(c, self.search_flags))
+        self.ctxs.append(c)
+        return len(self.ctxs) - 1
+
+    def use_lane(self, i: int) -> None:
+        self.ctx = self.ctxs[i] if hasattr(self, "ctxs") else self.ctx
+
     def next_seq(self) -> int:
         self._seq += 1
         return self._seq
@@ -329,9 +347,11 @@ class CudaBackend:
         if self.peer_set:
             self.lib.rlr_peer_set_close(self.peer_set)
             self.peer_set = None
-        if self.ctx:
-            self.lib.rlr_ctx_destroy(self.ctx)
-            self.ctx = None
+        for c in getattr(self, "ctxs", [self.ctx]):
+            if c:
+                self.lib.rlr_ctx_destroy(c)
+        self.ctxs = []
+        self.ctx = None
 
     @staticmethod
     def _p(t: torch.Tensor):
@@ -341,9 +361,12 @@ class CudaBackend:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def launches(self) -> int:
-        n = C.c_uint64(0)
-        self.B.check(self.lib.rlr_ctx_launch_count(self.ctx, C.byref(n)))
-        return n.value
+        total = 0
+        for c in getattr(self, "ctxs", [self.ctx]):
+            n = C.c_uint64(0)
+            self.B.check(self.lib.rlr_ctx_launch_count(c, C.byref(n)))
+            total += n.value
+        return total
 
     def topm(self, query, w_embed, w_lex, m, out, out_n):
         self.B.check(self.lib.rlr_topm_async(self.ctx, self._p(query), w_embed, w_lex, None, None, 0, m,
