@@ -225,14 +225,24 @@ def run_b200(a, guard=None):
     w_e, w_l = float(np.float32(0.7)), float(np.float32(0.3))
 
     def build_shard(plan):
+        nonlocal mode
         st = engine.DeviceStore.synthetic(plan.n_local, a.dim, kind=B.RLR_SYNTH_CLUSTERED, seed=SEED_STORE,
                                           centroid_seed=SEED_CENTROID, n_clusters=N_CLUSTERS, sigma=SIGMA,
                                           device=local_rank, row_base=plan.row0)
         be = rdist.CudaBackend(st, dev)
-        if mode in ("fused", "peers"):
-            be.open_peers(group, plan)       # rank 0 maps the peer shards (CUDA IPC over NVLink)
-        if mode == "fused":
-            be.open_mailbox(group, m_cap=p_cap, ring=4)
+        try:
+            if mode in ("fused", "peers"):
+                be.open_peers(group, plan)       # rank 0 maps the peer shards (CUDA IPC over NVLink)
+            if mode == "fused":
+                be.open_mailbox(group, m_cap=p_cap, ring=4)
+        except B.RlrError as e:                  # raised on EVERY rank (dist._agree): no peer access on this box
+            if rank == 0:
+                print(f"[bench] peer-memory setup failed ({e}); falling back to the NCCL all-gather + reduce path",
+                      file=sys.stderr, flush=True)
+            be.close()
+            be = rdist.CudaBackend(st, dev)
+            mode = "reduce"
+            os.environ["RLR_DIST_MODE"] = "reduce"   # workload_config reports what actually ran
         return st, be, rdist.Buffers(world, p_cap, st.info().pitch, dev)
 
     plan = rdist.ShardPlan(a.rows, world, rank)

@@ -245,25 +245,32 @@ class CudaBackend:
         self._rank = 0
 
     def open_mailbox(self, group, m_cap: int = 1024, ring: int = 4):
-        """Rank 0 allocates the mailbox, every other rank maps it (CUDA IPC).  Collective.
-        Needs open_peers() as well (rank 0's MMR reads the pool rows from peer HBM)."""
+        """Rank 0 allocates the mailbox, every other rank maps it (CUDA IPC).  Collective; raises on every
+        rank if any rank failed.  Needs open_peers() as well (rank 0's MMR reads the pool rows from peer HBM)."""
         import numpy as np
         B = self.B
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         self._rank = rank
         mb = C.c_void_p()
         handle = np.zeros(B.RLR_IPC_HANDLE_BYTES, np.uint8)
+        err = None
         if rank == 0:
-            B.check(self.lib.rlr_mailbox_create(self.device.index, world, m_cap, ring, C.byref(mb)))
-            B.check(self.lib.rlr_mailbox_ipc_export(mb, B.ptr(handle)))
+            try:
+                B.check(self.lib.rlr_mailbox_create(self.device.index, world, m_cap, ring, C.byref(mb)))
+                B.check(self.lib.rlr_mailbox_ipc_export(mb, B.ptr(handle)))
+            except Exception as e:      # noqa: BLE001 -- reported collectively below
+                err = str(e)
         box = [handle.tobytes() if rank == 0 else None]
         dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         if rank != 0:
-            h = np.frombuffer(box[0], np.uint8).copy()
-            B.check(self.lib.rlr_mailbox_open(self.device.index, B.ptr(h), world, m_cap, ring, C.byref(mb)))
-        self.mailbox = mb
+            try:
+                h = np.frombuffer(box[0], np.uint8).copy()
+                B.check(self.lib.rlr_mailbox_open(self.device.index, B.ptr(h), world, m_cap, ring, C.byref(mb)))
+            except Exception as e:      # noqa: BLE001
+                err = str(e)
+        self.mailbox = mb if mb else None
+        self._agree(group, err)
         self.mailbox_ready = True
-        dist.barrier(group=group)
 
     # ---- lanes: several queries in flight on one rank (one ctx = one workspace per lane; the caller
     # runs each lane on its own CUDA stream, e.g. `with torch.cuda.stream(s): sharded_search(...)`).
@@ -300,27 +307,44 @@ class CudaBackend:
         self.B.check(self.lib.rlr_mailbox_status(self.mailbox, C.byref(v)))
         return v.value
 
+    def _agree(self, group, err: Optional[str]) -> None:
+        """Collective: every rank learns whether ANY rank failed its local step, and all raise together
+        (a rank that raised alone would leave the others waiting in the next collective)."""
+        objs = [None] * dist.get_world_size(group)
+        dist.all_gather_object(objs, err, group=group)
+        bad = [(r, e) for r, e in enumerate(objs) if e]
+        if bad:
+            raise self.B.RlrError(self.B.RLR_ERR_CUDA, "; ".join(f"rank {r}: {e}" for r, e in bad))
+
     def open_peers(self, group, plan: "ShardPlan"):
-        """Exchange CUDA-IPC handles of the shards; rank 0 maps every peer shard.  Collective."""
+        """Exchange CUDA-IPC handles of the shards; rank 0 maps every peer shard.  Collective; raises
+        on every rank if the mapping failed on any."""
         import numpy as np
         B = self.B
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         handle = np.zeros(64, np.uint8)
-        B.check(self.lib.rlr_store_ipc_export(self.store.handle, self.search_flags, B.ptr(handle)))
+        err = None
+        try:
+            B.check(self.lib.rlr_store_ipc_export(self.store.handle, self.search_flags, B.ptr(handle)))
+        except Exception as e:          # noqa: BLE001 -- reported collectively below
+            err = str(e)
         info = self.store.info()
         mine = (handle.tobytes(), int(info.row_base), int(info.n_rows))
         allv = [None] * world
         dist.all_gather_object(allv, mine, group=group)
-        if rank == 0:
-            handles = np.frombuffer(b"".join(v[0] for v in allv), np.uint8).copy()
-            row_base = np.array([v[1] for v in allv], np.uint64)
-            n_rows = np.array([v[2] for v in allv], np.uint64)
-            ps = C.c_void_p()
-            B.check(self.lib.rlr_peer_set_open(self.store.handle, 0, world, B.ptr(handles), B.ptr(row_base),
-                                               B.ptr(n_rows), self.search_flags, C.byref(ps)))
-            self.peer_set = ps
+        if rank == 0 and err is None:
+            try:
+                handles = np.frombuffer(b"".join(v[0] for v in allv), np.uint8).copy()
+                row_base = np.array([v[1] for v in allv], np.uint64)
+                n_rows = np.array([v[2] for v in allv], np.uint64)
+                ps = C.c_void_p()
+                B.check(self.lib.rlr_peer_set_open(self.store.handle, 0, world, B.ptr(handles), B.ptr(row_base),
+                                                   B.ptr(n_rows), self.search_flags, C.byref(ps)))
+                self.peer_set = ps
+            except Exception as e:      # noqa: BLE001
+                err = str(e)
+        self._agree(group, err)
         self.peers_ready = True
-        dist.barrier(group=group)
 
     def mmr_peers(self, pool, pool_n, p_cap, top_k, lam, sel_pos, sel_n, result):
         self.B.check(self.lib.rlr_mmr_peers_async(self.ctx, self.peer_set, self._p(pool), self._p(pool_n), p_cap, top_k,
