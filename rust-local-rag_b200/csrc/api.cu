@@ -1056,20 +1056,15 @@ int search_batch_core(rlr_store *s, const float *queries, uint32_t n_queries, ui
     const uint32_t nq = n_queries, nq_pad = (nq + kBatchQTile - 1) / kBatchQTile * kBatchQTile;
     const uint32_t m_eff = static_cast<uint32_t>(std::min<uint64_t>(m, s->n_rows));
 
-    // host: normalise (:494) and validate the queries
-    std::vector<float> hq(static_cast<size_t>(nq) * dim);
-    memcpy(hq.data(), queries, hq.size() * sizeof(float));
-    for (uint32_t q = 0; q < nq; ++q) {
-        float *v = hq.data() + static_cast<size_t>(q) * dim;
-        for (uint32_t i = 0; i < dim; ++i)
-            if (!std::isfinite(v[i])) return fail(RLR_ERR_NONFINITE, "queries[%u][%u] is not finite", q, i);
-        if (!(flags & RLR_QUERY_PRENORMALIZED)) host_normalize(v, dim);
-    }
+    // The queries go straight from the caller's buffer to pinned memory and to the device; normalize (:494) and the
+    // NaN/Inf check run there (same sequential arithmetic, same bits as the host normalize; a 1024 x 1024 batch
+    // cost ~3 ms of single-threaded host work before the first kernel could start).
+    const size_t q_floats = static_cast<size_t>(nq) * dim;
     BatchBufs b;
     {
         // one workspace allocation per ctx, grown on demand (a batch call is a few ms: no per-call cudaMalloc)
         auto up = [](size_t x) { return (x + 255) & ~static_cast<size_t>(255); };
-        const size_t sz_q32 = up(hq.size() * sizeof(float)), sz_q16 = up(static_cast<size_t>(nq_pad) * s->pitch16 * 2);
+        const size_t sz_q32 = up(q_floats * sizeof(float)), sz_q16 = up(static_cast<size_t>(nq_pad) * s->pitch16 * 2);
         const size_t sz_tau = up(nq_pad * sizeof(float)), sz_state = up(static_cast<size_t>(nq_pad) * m_eff * 8);
         const size_t sz_app = up(static_cast<size_t>(nq_pad) * kBatchCap * 8), sz_cnt = up(nq_pad * sizeof(uint32_t));
         const size_t sz_acnt = up(static_cast<size_t>(nq_pad) * 32 * sizeof(uint32_t));   // one 128-byte line per counter
@@ -1088,10 +1083,10 @@ int search_batch_core(rlr_store *s, const float *queries, uint32_t n_queries, ui
         b.d_state_cnt = reinterpret_cast<uint32_t *>(p); p += sz_cnt;
         b.d_app_cnt = reinterpret_cast<uint32_t *>(p); p += sz_acnt;
         b.d_overflow = reinterpret_cast<uint32_t *>(p);
-        if (hq.size() * sizeof(float) > c->h_batch_q_bytes) {
+        if (q_floats * sizeof(float) > c->h_batch_q_bytes) {
             cudaFreeHost(c->h_batch_q); c->h_batch_q = nullptr; c->h_batch_q_bytes = 0;
-            CU_TRY(cudaMallocHost(&c->h_batch_q, hq.size() * sizeof(float)));
-            c->h_batch_q_bytes = hq.size() * sizeof(float);
+            CU_TRY(cudaMallocHost(&c->h_batch_q, q_floats * sizeof(float)));
+            c->h_batch_q_bytes = q_floats * sizeof(float);
         }
         const size_t st_bytes = static_cast<size_t>(nq) * m_eff * 8 + nq * sizeof(uint32_t);
         if (st_bytes > c->h_batch_state_bytes) {
@@ -1099,7 +1094,7 @@ int search_batch_core(rlr_store *s, const float *queries, uint32_t n_queries, ui
             CU_TRY(cudaMallocHost(&c->h_batch_state, st_bytes));
             c->h_batch_state_bytes = st_bytes;
         }
-        memcpy(c->h_batch_q, hq.data(), hq.size() * sizeof(float));
+        memcpy(c->h_batch_q, queries, q_floats * sizeof(float));
     }
     CUtensorMap tmapQ[2];   // [0] box {64, 256} (1-CTA kernel), [1] box {64, 128} (cta_group::2 kernel)
     {
@@ -1118,11 +1113,13 @@ int search_batch_core(rlr_store *s, const float *queries, uint32_t n_queries, ui
     }
     const bool timed = flags & RLR_WANT_TIMINGS;
     uint32_t launches = 0;
-    CU_TRY(cudaMemcpyAsync(b.d_q32, c->h_batch_q, hq.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(b.d_q32, c->h_batch_q, q_floats * sizeof(float), cudaMemcpyHostToDevice, st));
     if (timed) CU_TRY(cudaEventRecord(c->ev[0], st));
-    CU_TRY(rlr::batch_queries_to_half_launch(b.d_q32, dim, b.d_q16, s->pitch16, nq, nq_pad, st));
     CU_TRY(rlr::batch_init_launch(b.d_tau, b.d_state_cnt, b.d_app_cnt, nq, nq_pad, b.d_overflow, st));
+    if (!(flags & RLR_QUERY_PRENORMALIZED)) { CU_TRY(rlr::normalize_rows_launch(b.d_q32, dim, dim, nq, st)); ++launches; }
+    CU_TRY(rlr::batch_queries_to_half_launch(b.d_q32, dim, b.d_q16, s->pitch16, nq, nq_pad, b.d_overflow + 1, st));
     launches += 2;
+    bool nonfinite = false;
     // Geometrically growing phases.  tau is frozen during a phase, so a phase over rows [a, g*a)
     // lets ~m*(g-1) rows per query through; g is chosen to keep that near 70 % of the list capacity.
     // Attempt 0 enqueues all phases back to back and looks at the overflow flag once at the end;
@@ -1142,11 +1139,13 @@ int search_batch_core(rlr_store *s, const float *queries, uint32_t n_queries, ui
             span = ((attempt == 0 ? growth - 1 : 1) * t0 + 1) & ~1u;   // rows [t0, g*t0); even tile counts
         }
         if (attempt == 0) {
-            CU_TRY(cudaMemcpyAsync(c->h_u32, b.d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaMemcpyAsync(c->h_u32, b.d_overflow, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             CU_TRY(cudaStreamSynchronize(st));
-            if (c->h_u32[0] == 0) break;
+            nonfinite = c->h_u32[1] != 0;
+            if (c->h_u32[0] == 0 || nonfinite) break;
         }
     }
+    if (nonfinite) return fail(RLR_ERR_NONFINITE, "the query batch contains NaN/Inf");
     if (timed) CU_TRY(cudaEventRecord(c->ev[1], st));
     if (flags & RLR_BATCH_EXACT_RESCORE) {
         const bool half = s->d_rows == nullptr;

@@ -830,12 +830,18 @@ batch_prune_warp_kernel(unsigned long long *__restrict__ state_keys, uint32_t *_
     }
 }
 
+// f32 queries -> zero-padded binary16 operand rows; also the NaN/Inf check of the (normalised) queries
 __global__ void to_half_rows_kernel(const float *__restrict__ src, uint32_t dim, __half *__restrict__ dst, uint32_t pitch,
-                                    uint32_t n_valid, uint32_t n_pad)
+                                    uint32_t n_valid, uint32_t n_pad, uint32_t *__restrict__ nonfinite)
 {
+    bool bad = false;
     for (uint32_t r = blockIdx.x; r < n_pad; r += gridDim.x)
-        for (uint32_t c = threadIdx.x; c < pitch; c += blockDim.x)
-            dst[static_cast<size_t>(r) * pitch + c] = (r < n_valid && c < dim) ? __float2half_rn(src[static_cast<size_t>(r) * dim + c]) : __float2half_rn(0.0f);
+        for (uint32_t c = threadIdx.x; c < pitch; c += blockDim.x) {
+            float x = 0.0f;
+            if (r < n_valid && c < dim) { x = src[static_cast<size_t>(r) * dim + c]; bad |= !is_finite_f32(x); }
+            dst[static_cast<size_t>(r) * pitch + c] = __float2half_rn(x);
+        }
+    if (bad && nonfinite != nullptr) atomicOr(nonfinite, 1u);
 }
 
 // Exact re-score of the shortlist: one thread per (query, candidate) runs the reference's
@@ -876,7 +882,7 @@ __global__ void batch_init_kernel(float *tau, uint32_t *state_cnt, uint32_t *app
         state_cnt[i] = 0;
         app_cnt[static_cast<size_t>(i) * kCntStride] = 0;
     }
-    if (i == 0) *overflow = 0;
+    if (i == 0) { overflow[0] = 0; overflow[1] = 0; }     // [0] list overflow, [1] non-finite query seen
 }
 
 } // namespace
@@ -933,9 +939,9 @@ cudaError_t batch_init_launch(float *tau, uint32_t *state_cnt, uint32_t *app_cnt
 }
 
 cudaError_t batch_queries_to_half_launch(const float *d_q, uint32_t dim, void *d_q16, uint32_t pitch16, uint32_t nq,
-                                         uint32_t nq_pad, cudaStream_t st)
+                                         uint32_t nq_pad, uint32_t *d_nonfinite, cudaStream_t st)
 {
-    to_half_rows_kernel<<<nq_pad < 592 ? nq_pad : 592, 256, 0, st>>>(d_q, dim, static_cast<__half *>(d_q16), pitch16, nq, nq_pad);
+    to_half_rows_kernel<<<nq_pad < 592 ? nq_pad : 592, 256, 0, st>>>(d_q, dim, static_cast<__half *>(d_q16), pitch16, nq, nq_pad, d_nonfinite);
     return cudaGetLastError();
 }
 

@@ -144,7 +144,7 @@ cudaError_t batch_configure(int smem_optin);
 cudaError_t batch_init_launch(float *tau, uint32_t *state_cnt, uint32_t *app_cnt, uint32_t nq, uint32_t nq_pad,
                               uint32_t *overflow, cudaStream_t st);
 cudaError_t batch_queries_to_half_launch(const float *d_q, uint32_t dim, void *d_q16, uint32_t pitch16, uint32_t nq,
-                                         uint32_t nq_pad, cudaStream_t st);
+                                         uint32_t nq_pad, uint32_t *d_nonfinite /* nullable */, cudaStream_t st);
 cudaError_t batch_gemm_launch(const CUtensorMap *tmapA, const CUtensorMap *tmapQ, int grid, uint32_t n_rows,
                               uint32_t row_base, uint32_t tile0, uint32_t tile1, uint32_t nq_pad, uint32_t pitch16,
                               const float *tau, unsigned long long *app_keys, uint32_t *app_cnt, uint32_t cap,

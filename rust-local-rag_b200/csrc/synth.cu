@@ -119,6 +119,29 @@ normalize_rows_kernel(float *__restrict__ rows, uint32_t pitch, uint32_t dim, ui
     }
 }
 
+// Same arithmetic for a FEW rows (a batch of queries): one warp per row.  The row is staged in shared
+// memory with coalesced loads, lane 0 runs the sequential sum of squares (the order is what makes the
+// bits the reference's), all lanes divide.
+__global__ void __launch_bounds__(32)
+normalize_row_per_warp_kernel(float *__restrict__ rows, uint32_t pitch, uint32_t dim)
+{
+    extern __shared__ float srow[];
+    float *row = rows + static_cast<size_t>(blockIdx.x) * pitch;
+    const uint32_t lane = threadIdx.x;
+    for (uint32_t c = lane; c < dim; c += 32) srow[c] = row[c];
+    __syncwarp();
+    float norm_sq = 0.0f;
+    if (lane == 0) {
+#pragma unroll 8
+        for (uint32_t c = 0; c < dim; ++c) { const float x = srow[c]; norm_sq = add_rn(norm_sq, mul_rn(x, x)); }
+    }
+    norm_sq = __shfl_sync(0xffffffffu, norm_sq, 0);
+    if (norm_sq > 1e-20f) {
+        const float norm = __fsqrt_rn(norm_sq);
+        for (uint32_t c = lane; c < dim; c += 32) row[c] = __fdiv_rn(srow[c], norm);
+    }
+}
+
 __global__ void finite_check_kernel(const float4 *__restrict__ v, uint64_t n4, uint32_t *flag)
 {
     bool bad = false;
@@ -187,6 +210,10 @@ cudaError_t to_half_launch(const float *d_src, uint32_t src_pitch, void *d_dst, 
 cudaError_t normalize_rows_launch(float *d_rows, uint32_t pitch, uint32_t dim, uint64_t n_rows, cudaStream_t stream)
 {
     if (n_rows == 0) return cudaSuccess;
+    if (n_rows <= 16384 && dim <= 8192) {      // a query batch: one warp per row keeps every SM busy
+        normalize_row_per_warp_kernel<<<static_cast<unsigned>(n_rows), 32, dim * sizeof(float), stream>>>(d_rows, pitch, dim);
+        return cudaGetLastError();
+    }
     const uint64_t blocks = (n_rows + kRowsPerBlock - 1) / kRowsPerBlock;
     normalize_rows_kernel<<<static_cast<unsigned>(blocks), kRowsPerBlock, 0, stream>>>(d_rows, pitch, dim, n_rows);
     return cudaGetLastError();

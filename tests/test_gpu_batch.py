@@ -181,3 +181,38 @@ def test_batch_equal_scores_at_the_cut_are_ordered_by_row():
         assert r.tobytes() == np.ascontiguousarray(full_rows[:, :m]).tobytes()
         assert sc.tobytes() == np.ascontiguousarray(full_scores[:, :m]).tobytes()
     s.close()
+
+
+def test_batch_queries_are_normalised_and_checked_on_the_device():
+    """The batch's normalize (:494) and NaN/Inf check run on the device: un-normalised queries must give the
+    single-query path's exact bits after the exact re-score (that path normalises on the host), and a NaN
+    anywhere in the batch is RLR_ERR_NONFINITE."""
+    import rust_local_rag_b200  # noqa: F401
+    from rust_local_rag_b200 import binding as B, engine
+    from oracle import orc
+    rng = np.random.default_rng(3)
+    n, dim, nq, m = 20000, 384, 33, 50
+    rows = orc.normalize_rows(rng.standard_normal((n, dim)).astype(F32))
+    qs = (rng.standard_normal((nq, dim)) * 7.5).astype(F32)                # far from unit norm
+    s = engine.DeviceStore.from_rows(rows, flags=B.RLR_STORE_KEEP_F16)
+    got_rows, got_scores, _ = s.search_batch(qs, m, flags=B.RLR_BATCH_EXACT_RESCORE)
+    for q in range(nq):
+        R, S = orc.embedding_candidates(rows, qs[q], m)                     # normalises the query like :425
+        exact = {int(r): sc for r, sc in zip(R, S)}
+        for r, sc in zip(got_rows[q], got_scores[q]):
+            want = exact.get(int(r))
+            if want is not None:
+                assert np.float32(sc).tobytes() == np.float32(want).tobytes(), (q, r)
+        assert len(set(got_rows[q].tolist()) & set(R.tolist())) >= m - 3
+    bad = qs.copy()
+    bad[17, 5] = np.nan
+    with pytest.raises(B.RlrError) as ei:
+        s.search_batch(bad, m)
+    assert ei.value.code == B.RLR_ERR_NONFINITE
+    bad[17, 5] = np.inf
+    with pytest.raises(B.RlrError) as ei:
+        s.search_batch(bad, m)
+    assert ei.value.code == B.RLR_ERR_NONFINITE
+    again = s.search_batch(qs, m, flags=B.RLR_BATCH_EXACT_RESCORE)          # the store is still usable
+    assert again[0].tobytes() == got_rows.tobytes()
+    s.close()
