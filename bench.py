@@ -7,9 +7,13 @@
 A step is one query (one pass of the hot path over the whole corpus).  The corpus is the
 BASELINE.json metric's: 10,000,000 x 768 synthetic unit vectors (clustered, seeded), rows
 sharded contiguously over the N ranks (strong scaling: total work fixed).  `value` times the
-path with queries already resident in HBM; `e2e` times the public host-buffer API (C-ABI
-`rlr_search_mmr` at N=1, the sharded searcher at N>1) with the H2D copy of the query and the
-D2H read of the result inside the timed region.  Prints ONE JSON line on rank 0.
+path with queries already resident in HBM (at N=1 with two queries in flight, each on its own
+workspace and stream; at N>1 one in flight, rank 0's merge/MMR tail hidden by giving rank 0 fewer
+rows); `e2e` times the public host-buffer API one query at a time (C-ABI `rlr_search_mmr` at N=1,
+the sharded searcher at N>1) with the H2D copy of the query and the D2H read of the result inside
+the timed region.  At N>1 the per-GPU lists are exchanged by the scan kernels themselves (peer
+stores into rank 0's HBM; RLR_DIST_MODE=peers|reduce selects the NCCL paths).  Prints ONE JSON
+line on rank 0's stdout; everything else goes to stderr.
 """
 import argparse
 import ctypes as C
@@ -138,7 +142,13 @@ def cpu_reference(a, steps, warmup, budget_s):
     """Times oracle.search_with_diversity (bit-faithful restatement of the reference's
     single-process search, all host threads) on the bench workload.  Returns dict."""
     from oracle import orc
-    threads = orc.max_threads()
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1, which would make
+    # omp_get_max_threads() say 1; the oracle takes its thread count explicitly (num_threads clause)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    threads = max(orc.max_threads(), avail)
     rows_n = a.rows
     t0 = time.perf_counter()
     rows = orc.synth_rows(rows_n, a.dim, kind=1, seed=SEED_STORE, centroid_seed=SEED_CENTROID,

@@ -30,3 +30,13 @@ def test_rust_extern_block_matches_header():
     assert set(h) == set(r), (sorted(set(h) - set(r)), sorted(set(r) - set(h)))
     for name in h:
         assert h[name] == r[name], (name, h[name], r[name])
+
+
+def test_build_rs_compiles_the_same_sources_as_the_python_build():
+    import rust_local_rag_b200  # noqa: F401
+    from rust_local_rag_b200 import _build
+    text = open(os.path.join(ROOT, "rust", "rlr-b200-sys", "build.rs")).read()
+    m = re.search(r"let sources = \[([^\]]*)\]", text)
+    assert m, "sources list not found in build.rs"
+    rust_sources = re.findall(r'"([^"]+)"', m.group(1))
+    assert rust_sources == list(_build.SOURCES)
