@@ -30,14 +30,14 @@ if ROOT not in sys.path:
 
 SEED_STORE, SEED_QUERY, SEED_CENTROID = 0x5EED0001, 0x5EED0002, 0x5EED00C0
 N_CLUSTERS, SIGMA = 4096, 0.65
-N_QUERIES = 64
+N_QUERIES = 128
 METRIC = "search_with_diversity queries/sec (top_k=100 MMR, 10Mx768 f32 chunks)"
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=10_000_000)
