@@ -386,7 +386,8 @@ int rlr_mmr_peers_async(rlr_ctx *c, rlr_peer_set *p, const void *d_cands, const 
  * round trip; ranks other than the root are done as soon as their scan is.
  * Sequence numbers start at 1, increase by 1 per query and must agree across ranks; a slot is
  * reused after `ring` queries, and a posting kernel waits (bounded, 4 s) for the root to have
- * consumed it (one `consumed` word per slot, so queries may be in flight on several streams /
+ * consumed it.  Ranks that mapped the mailbox must rlr_mailbox_close it before the root frees it.
+ * (One `consumed` word per slot, so queries may be in flight on several streams /
  * ctxs of a rank at once as long as `ring` is a multiple of the number of such lanes).  rlr_mailbox_status reads a sticky word: non-zero once any wait timed out. */
 typedef struct rlr_mailbox rlr_mailbox;
 int rlr_mailbox_create(int device, uint32_t n_ranks, uint32_t m_cap, uint32_t ring, rlr_mailbox **out);

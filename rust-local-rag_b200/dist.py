@@ -138,6 +138,8 @@ def sharded_search(backend, group, bufs: Buffers, query, top_k: int, diversity_f
         # fused exchange: no collective call.  The scan kernel posts this rank's list into rank
         # 0's HBM; rank 0 merges inside a kernel that waits for the flags, then runs MMR with
         # peer loads.  Other ranks are done after their scan.
+        if m > backend.mailbox_m_cap:        # checked BEFORE taking a sequence number: ranks must stay in step
+            raise ValueError(f"pool {m} exceeds the mailbox capacity {backend.mailbox_m_cap}")
         seq = backend.next_seq()
         backend.topm_post(query, w_embed, w_lex, m, seq)
         if rank != 0:
@@ -241,6 +243,7 @@ class CudaBackend:
         self.peers_ready = False
         self.mailbox = None
         self.mailbox_ready = False
+        self.mailbox_m_cap = 0
         self._seq = 0
         self._rank = 0
 
@@ -269,6 +272,7 @@ class CudaBackend:
             except Exception as e:      # noqa: BLE001
                 err = str(e)
         self.mailbox = mb if mb else None
+        self.mailbox_m_cap = m_cap
         self._agree(group, err)
         self.mailbox_ready = True
 
