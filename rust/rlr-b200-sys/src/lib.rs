@@ -16,6 +16,15 @@ pub const RLR_WANT_TIMINGS: u32 = 0x2;
 pub const RLR_SEARCH_F16: u32 = 0x4;
 pub const RLR_STORE_KEEP_F16: u32 = 0x1;
 pub const RLR_STORE_F16_ONLY: u32 = 0x4;
+pub const RLR_STORE_CHECK_FINITE: u32 = 0x2;
+pub const RLR_STORE_NORMALIZE_ON_UPLOAD: u32 = 0x8;
+pub const RLR_BATCH_EXACT_RESCORE: u32 = 0x8;
+pub const RLR_MAX_TOP_K: u32 = 100;
+pub const RLR_MAX_DIM: u32 = 4096;
+pub const RLR_IPC_HANDLE_BYTES: usize = 64;
+pub const RLR_SYNTH_IID: c_int = 0;
+pub const RLR_SYNTH_CLUSTERED: c_int = 1;
+pub const RLR_ABI_VERSION: c_int = 1;
 
 #[repr(C)] pub struct rlr_store { _p: [u8; 0] }
 #[repr(C)] pub struct rlr_ctx { _p: [u8; 0] }

@@ -40,3 +40,27 @@ def test_build_rs_compiles_the_same_sources_as_the_python_build():
     assert m, "sources list not found in build.rs"
     rust_sources = re.findall(r'"([^"]+)"', m.group(1))
     assert rust_sources == list(_build.SOURCES)
+
+
+def _header_defines():
+    text = open(os.path.join(ROOT, "include", "rlr_b200.h")).read()
+    out = {}
+    for m in re.finditer(r"^#define\s+(RLR_[A-Z0-9_]+)\s+(0x[0-9a-fA-F]+|\d+)u?\b", text, flags=re.M):
+        out[m.group(1)] = int(m.group(2), 0)
+    out.pop("RLR_B200_H", None)
+    return out
+
+
+def test_constants_agree_between_header_rust_and_python():
+    from rust_local_rag_b200 import binding as B
+    h = _header_defines()
+    assert len(h) >= 20
+    text = open(os.path.join(ROOT, "rust", "rlr-b200-sys", "src", "lib.rs")).read()
+    r = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"pub const (RLR_[A-Z0-9_]+): \w+ = (0x[0-9a-fA-F]+|\d+);", text)}
+    assert set(h) == set(r), (sorted(set(h) - set(r)), sorted(set(r) - set(h)))
+    for k, v in h.items():
+        assert r[k] == v, k
+        if hasattr(B, k):
+            assert getattr(B, k) == v, k
+    for k in ("RLR_STORE_NORMALIZE_ON_UPLOAD", "RLR_BATCH_EXACT_RESCORE", "RLR_SEARCH_F16", "RLR_MAX_M", "RLR_IPC_HANDLE_BYTES"):
+        assert hasattr(B, k), k
