@@ -51,7 +51,7 @@ def parse():
 def workload_config(a, world):
     return {
         "workload": f"single-query top_k={a.top_k} diversity={a.diversity} MMR over {a.rows}x{a.dim} f32 chunks "
-                    f"(BASELINE configs[2]), rows sharded contiguously over {world} GPU(s)",
+                    f"(BASELINE configs[{1 if a.rows == 1_000_000 else 2}]), rows sharded contiguously over {world} GPU(s)",
         "rows": a.rows, "dim": a.dim, "top_k": a.top_k, "diversity": a.diversity,
         "pool": max(3 * a.top_k, a.top_k + 10), "weights": [0.7, 0.3],
         "distribution": f"clustered: normalize(centroid[row % {N_CLUSTERS}] + {SIGMA}*U[-1,1)), splitmix64 counter hash, "
