@@ -305,6 +305,78 @@ int rlr_tokenize(const char *text_utf8, size_t len, char *out, size_t out_cap, s
 /* stage timings of the calling thread's most recent call made with RLR_WANT_TIMINGS */
 int rlr_last_timings(rlr_timings *out);
 
+/* ---- one process, every GPU of the box: the same calls over a row-sharded store ---------------
+ *
+ * The reference is ONE process holding ONE `Arc<RwLock<RagEngine>>` (src/main.rs:140-167; callers take
+ * `rag_state.read()`, src/mcp_server.rs:89,377).  An rlr_cluster is that engine's embedding store sharded
+ * by contiguous row blocks over several GPUs of one NVSwitch box, driven from the calling host thread:
+ * no second process, no torchrun, no NCCL.  Every rlr_cluster_* search has exactly the arguments,
+ * semantics and results (bit for bit, rows are GLOBAL positions) of its rlr_* single-store namesake:
+ *   - per query the host thread enqueues one scan kernel per GPU; each kernel's last CTA stores the
+ *     shard's top-m list straight into a mailbox in shard 0's HBM (peer stores over NVLink, enabled with
+ *     cudaDeviceEnablePeerAccess) and publishes a sequence number with a system-scope release;
+ *   - shard 0's GPU merges inside a kernel that waits for the flags, and its MMR kernels load the pool
+ *     rows from the owning GPUs' HBM through peer pointers -- no collective, no host round trip between
+ *     the stages, one stream synchronisation per query;
+ *   - the lexical pairs (LexicalIndex::score output, :505-506) are normalised by their GLOBAL maximum
+ *     (:511-515) and routed to the shard that owns each row.
+ * Re-entrant like the single-store calls (each concurrent caller leases its own per-GPU workspaces,
+ * streams and mailbox).  A cluster is a bulk-loaded snapshot (load_from_disk, :1520-1696): there is no
+ * rlr_cluster_append / remove; mutate a single-GPU store (rlr_store_append / rlr_store_remove_rows) or
+ * rebuild the cluster.
+ *   devices     n_devices CUDA ordinals; entry 0 is the root (mailbox, merge, MMR).  The same ordinal may
+ *               appear more than once (several shards on one GPU: how the path is tested on a 1-GPU box).
+ *   shard_rows  rows per shard (sum == n_rows, every entry > 0) or NULL for the default plan: even blocks,
+ *               except that the root gets fewer rows so that its scan + merge/MMR tail takes as long as the
+ *               other GPUs' scans (tail-balanced sharding).
+ * Fails with RLR_ERR_UNSUPPORTED when the GPUs cannot reach each other's memory (no peer access). */
+#define RLR_MAX_SHARDS 16
+typedef struct rlr_cluster rlr_cluster;
+typedef struct rlr_cluster_info {
+    uint64_t n_rows;
+    uint32_t dim;
+    uint32_t pitch;
+    uint32_t flags;
+    uint32_t n_shards;
+    int32_t  device[RLR_MAX_SHARDS];
+    uint64_t row_base[RLR_MAX_SHARDS];
+    uint64_t shard_rows[RLR_MAX_SHARDS];
+} rlr_cluster_info;
+
+int rlr_cluster_create(const int *devices, uint32_t n_devices, uint32_t dim, uint64_t n_rows,
+                       const float *rows /* nullable */, uint64_t host_pitch, uint32_t flags,
+                       const uint64_t *shard_rows /* nullable */, rlr_cluster **out);
+int rlr_cluster_destroy(rlr_cluster *c);
+int rlr_cluster_info_get(const rlr_cluster *c, rlr_cluster_info *out);
+/* overwrite GLOBAL rows [row0, row0+n) (routed to the owning shards); rows as for rlr_store_upload */
+int rlr_cluster_upload(rlr_cluster *c, uint64_t row0, uint64_t n, const float *rows, uint64_t host_pitch);
+int rlr_cluster_read_rows(const rlr_cluster *c, const uint32_t *rows, uint64_t n, float *out);
+int rlr_cluster_fill_synthetic(rlr_cluster *c, int kind, uint64_t seed, uint64_t centroid_seed,
+                               uint32_t n_clusters, float sigma);
+/* RagEngine::search (:476-565 + :667-698), as rlr_search_topm */
+int rlr_cluster_search_topm(rlr_cluster *c, const float *query, uint32_t dim, uint32_t flags,
+                            const rlr_resolved_weights *w,
+                            const uint32_t *lex_rows, const float *lex_scores, uint32_t n_lex, uint32_t m,
+                            uint32_t *out_rows, float *out_combined, float *out_emb, float *out_lex,
+                            uint32_t *out_n);
+/* RagEngine::mmr_diversify (:767-839) over GLOBAL candidate rows, as rlr_mmr */
+int rlr_cluster_mmr(rlr_cluster *c, const uint32_t *cand_rows, const float *relevance, uint32_t p,
+                    uint32_t top_k, float lambda, uint32_t flags, uint32_t *out_sel_pos, uint32_t *out_n);
+/* RagEngine::search_with_diversity (:717-759), as rlr_search_mmr: the benchmarked multi-GPU entry point */
+int rlr_cluster_search_mmr(rlr_cluster *c, const float *query, uint32_t dim, uint32_t flags,
+                           uint32_t top_k, float diversity_factor, const rlr_resolved_weights *w,
+                           const uint32_t *lex_rows, const float *lex_scores, uint32_t n_lex,
+                           uint32_t *out_rows, float *out_score, float *out_emb, float *out_lex,
+                           uint32_t *out_n);
+/* RagEngine::get_embedding_candidates (:415-461), as rlr_embedding_candidates */
+int rlr_cluster_embedding_candidates(rlr_cluster *c, const float *query, uint32_t dim, uint32_t flags,
+                                     uint32_t count, uint32_t *out_rows, float *out_score, uint32_t *out_n);
+/* per-shard scan-kernel durations (ms) of the calling thread's most recent rlr_cluster_search_* call made
+ * with RLR_WANT_TIMINGS (rlr_last_timings has the maximum as scan_ms and the root's merge / MMR stages) */
+int rlr_cluster_last_scan_ms(float *out_ms, uint32_t cap, uint32_t *out_n);
+/* kernels launched by this cluster's searches since creation (bench `gpu_launches`) */
+int rlr_cluster_launch_count(const rlr_cluster *c, uint64_t *out);
+
 /* ---- device-level building blocks (multi-GPU composition, bench `value`) -------
  *
  * Same kernels, but inputs/outputs stay in device memory and work is enqueued on a

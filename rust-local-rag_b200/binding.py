@@ -29,6 +29,7 @@ RLR_BATCH_EXACT_RESCORE = 0x8
 RLR_IPC_HANDLE_BYTES = 64
 RLR_SYNTH_IID = 0
 RLR_SYNTH_CLUSTERED = 1
+RLR_MAX_SHARDS = 16
 
 
 class RlrError(RuntimeError):
@@ -57,6 +58,12 @@ class StoreInfoC(C.Structure):
 class DeviceInfoC(C.Structure):
     _fields_ = [("device", C.c_int32), ("sm_count", C.c_int32), ("cc_major", C.c_int32), ("cc_minor", C.c_int32),
                 ("total_mem", C.c_uint64), ("name", C.c_char * 128)]
+
+
+class ClusterInfoC(C.Structure):
+    _fields_ = [("n_rows", C.c_uint64), ("dim", C.c_uint32), ("pitch", C.c_uint32), ("flags", C.c_uint32),
+                ("n_shards", C.c_uint32), ("device", C.c_int32 * 16), ("row_base", C.c_uint64 * 16),
+                ("shard_rows", C.c_uint64 * 16)]
 
 
 class TimingsC(C.Structure):
@@ -104,6 +111,20 @@ PROTOTYPES = {
     "rlr_lexical_score": (_int, [_vp, C.c_char_p, C.c_size_t, _u32, _vp, _vp, _u32, _pu32]),
     "rlr_tokenize": (_int, [C.c_char_p, C.c_size_t, _vp, C.c_size_t, C.POINTER(C.c_size_t), _pu32]),
     "rlr_last_timings": (_int, [C.POINTER(TimingsC)]),
+    "rlr_cluster_create": (_int, [_vp, _u32, _u32, _u64, _vp, _u64, _u32, _vp, C.POINTER(_vp)]),
+    "rlr_cluster_destroy": (_int, [_vp]),
+    "rlr_cluster_info_get": (_int, [_vp, C.POINTER(ClusterInfoC)]),
+    "rlr_cluster_upload": (_int, [_vp, _u64, _u64, _vp, _u64]),
+    "rlr_cluster_read_rows": (_int, [_vp, _vp, _u64, _vp]),
+    "rlr_cluster_fill_synthetic": (_int, [_vp, _int, _u64, _u64, _u32, _f32]),
+    "rlr_cluster_search_topm": (_int, [_vp, _vp, _u32, _u32, C.POINTER(ResolvedWeightsC), _vp, _vp, _u32, _u32,
+                                       _vp, _vp, _vp, _vp, _pu32]),
+    "rlr_cluster_mmr": (_int, [_vp, _vp, _vp, _u32, _u32, _f32, _u32, _vp, _pu32]),
+    "rlr_cluster_search_mmr": (_int, [_vp, _vp, _u32, _u32, _u32, _f32, C.POINTER(ResolvedWeightsC), _vp, _vp, _u32,
+                                      _vp, _vp, _vp, _vp, _pu32]),
+    "rlr_cluster_embedding_candidates": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _pu32]),
+    "rlr_cluster_last_scan_ms": (_int, [_vp, _u32, _pu32]),
+    "rlr_cluster_launch_count": (_int, [_vp, C.POINTER(_u64)]),
     "rlr_ctx_create": (_int, [_vp, C.POINTER(_vp)]),
     "rlr_ctx_destroy": (_int, [_vp]),
     "rlr_topm_async": (_int, [_vp, _vp, _f32, _f32, _vp, _vp, _u32, _u32, _vp, _vp, _vp]),

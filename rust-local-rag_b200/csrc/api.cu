@@ -16,12 +16,9 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
-#include "common.cuh"
-#include "kernels.cuh"
+#include "api_internal.hpp"
 
-#define RLR_EXPORT extern "C" __attribute__((visibility("default")))
-
-namespace {
+namespace rlr_api {
 
 thread_local std::string g_err;
 thread_local rlr_timings g_timings = {0, 0, 0, 0, 0};
@@ -37,17 +34,10 @@ int fail(int code, const char *fmt, ...)
     return code;
 }
 
-#define CU_TRY(expr)                                                                             \
-    do {                                                                                         \
-        cudaError_t e__ = (expr);                                                                \
-        if (e__ != cudaSuccess) {                                                                \
-            cudaGetLastError();                                                                  \
-            return fail(e__ == cudaErrorMemoryAllocation ? RLR_ERR_OOM : RLR_ERR_CUDA,           \
-                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
-        }                                                                                        \
-    } while (0)
+} // namespace rlr_api
+using namespace rlr_api;
 
-constexpr uint32_t kLexCap = 8192;
+namespace {
 
 struct DeviceState {
     bool checked = false;
@@ -59,9 +49,11 @@ struct DeviceState {
 std::mutex g_dev_mu;
 DeviceState g_dev[64];
 
+} // namespace
+
 // A device is usable iff it exists and is compute capability 10.x (the fatbin holds
 // sm_100a SASS only).  There is no fallback.
-int ensure_device(int device)
+int rlr_api::ensure_device(int device)
 {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -100,6 +92,14 @@ int ensure_device(int device)
     return RLR_OK;
 }
 
+int rlr_api::device_sm_count(int device)
+{
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    return (device >= 0 && device < 64) ? g_dev[device].sm_count : 0;
+}
+
+namespace {
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -122,64 +122,7 @@ PFN_encodeTiled get_encode()
 
 } // namespace
 
-struct rlr_store {
-    int device = 0;
-    uint32_t dim = 0, pitch = 0, flags = 0;
-    uint64_t n_rows = 0, row_base = 0;
-    uint64_t capacity = 0;          // rows the device allocations can hold (>= n_rows)
-    float *d_rows = nullptr;        // f32 matrix (absent for RLR_STORE_F16_ONLY)
-    void *d_rows16 = nullptr;       // binary16 copy (RLR_STORE_KEEP_F16 / RLR_STORE_F16_ONLY)
-    uint32_t pitch16 = 0;           // elements per binary16 row (dim rounded up to 64)
-    CUtensorMap tmap, tmap16;
-    int sm_count = 0, smem_optin = 0;
-    bool use_half(uint32_t flags) const { return d_rows == nullptr || ((flags & RLR_SEARCH_F16) && d_rows16 != nullptr); }
-    std::mutex mu;
-    std::vector<rlr_ctx *> free_ctx;
-};
-
-struct rlr_ctx {
-    rlr_store *s = nullptr;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    float *d_query = nullptr;
-    uint32_t *d_lex_rows = nullptr;
-    float *d_lex_norm = nullptr;
-    rlr_cand *d_lists = nullptr;
-    uint32_t *d_counts = nullptr;
-    uint32_t *d_ticket = nullptr;
-    uint32_t *d_pub = nullptr;
-    rlr_cand *d_tmp = nullptr;
-    rlr_cand *d_pool = nullptr;
-    uint32_t *d_pool_n = nullptr;
-    float *d_tri = nullptr;
-    uint32_t *d_sel_pos = nullptr;
-    uint32_t *d_sel_n = nullptr;
-    rlr_cand *d_result = nullptr;
-    uint32_t *d_rows_in = nullptr;
-    float *d_rel_in = nullptr;
-    uint32_t *d_p_in = nullptr;
-    // pinned host staging
-    float *h_query = nullptr;
-    uint32_t *h_lex_rows = nullptr;
-    float *h_lex_norm = nullptr;
-    rlr_cand *h_result = nullptr;   // RLR_MAX_M records
-    uint32_t *h_u32 = nullptr;      // RLR_MAX_M + 8 words
-    float *h_rel = nullptr;
-    uint64_t launches = 0;
-    uint32_t n_lists_cap = 0;
-    uint32_t search_flags = 0;      // RLR_SEARCH_F16 for the device-level entry points
-    // batched path workspace (allocated on first use, grown on demand)
-    void *batch_mem = nullptr;
-    size_t batch_bytes = 0;
-    float *h_batch_q = nullptr;     // pinned staging for the query batch
-    size_t h_batch_q_bytes = 0;
-    unsigned long long *h_batch_state = nullptr;
-    size_t h_batch_state_bytes = 0;
-};
-
-namespace {
-
-void ctx_free(rlr_ctx *c)
+void rlr_api::ctx_free(rlr_ctx *c)
 {
     if (!c) return;
     cudaFree(c->d_query); cudaFree(c->d_lex_rows); cudaFree(c->d_lex_norm); cudaFree(c->d_lists);
@@ -195,7 +138,7 @@ void ctx_free(rlr_ctx *c)
     delete c;
 }
 
-int ctx_new(rlr_store *s, rlr_ctx **out)
+int rlr_api::ctx_new(rlr_store *s, rlr_ctx **out)
 {
     rlr_ctx *c = new rlr_ctx();
     c->s = s;
@@ -244,27 +187,7 @@ int ctx_new(rlr_store *s, rlr_ctx **out)
     return RLR_OK;
 }
 
-// RAII lease of a pooled ctx so that concurrent searches on one store are re-entrant.
-struct CtxLease {
-    rlr_store *s;
-    rlr_ctx *c = nullptr;
-    explicit CtxLease(rlr_store *st) : s(st) {}
-    int acquire()
-    {
-        {
-            std::lock_guard<std::mutex> lk(s->mu);
-            if (!s->free_ctx.empty()) { c = s->free_ctx.back(); s->free_ctx.pop_back(); }
-        }
-        if (c) return RLR_OK;
-        return ctx_new(s, &c);
-    }
-    ~CtxLease()
-    {
-        if (c) { std::lock_guard<std::mutex> lk(s->mu); s->free_ctx.push_back(c); }
-    }
-};
-
-void host_normalize(float *v, size_t n)
+void rlr_api::host_normalize(float *v, size_t n)
 {
     // src/rag_engine.rs:1763-1771; volatile keeps gcc/nvcc-host from re-associating
     volatile float norm_sq = 0.0f;
@@ -274,6 +197,8 @@ void host_normalize(float *v, size_t n)
         for (size_t i = 0; i < n; ++i) v[i] = v[i] / norm;
     }
 }
+
+namespace {
 
 // Stage the query in pinned memory, normalise (:494), upload.  Everything beyond dim
 // stays zero so that the kernel's padded chunks contribute exact zeros.
@@ -354,7 +279,9 @@ int enqueue_topm(rlr_ctx *c, const float *d_query, float w_e, float w_l, const u
     return RLR_OK;
 }
 
-void unpack(const rlr_cand *h, uint32_t n, uint32_t *rows, float *score, float *emb, float *lex)
+} // namespace
+
+void rlr_api::unpack(const rlr_cand *h, uint32_t n, uint32_t *rows, float *score, float *emb, float *lex)
 {
     for (uint32_t i = 0; i < n; ++i) {
         if (rows) rows[i] = rlr::key_row(h[i].key);
@@ -366,6 +293,8 @@ void unpack(const rlr_cand *h, uint32_t n, uint32_t *rows, float *score, float *
         if (lex) lex[i] = h[i].lex;
     }
 }
+
+namespace {
 
 int check_store(const rlr_store *s)
 {
@@ -608,6 +537,15 @@ RLR_EXPORT int rlr_store_upload(rlr_store *s, uint64_t row0, uint64_t n, const f
         if (e != cudaSuccess) {
             cudaGetLastError();
             rc = fail(e == cudaErrorMemoryAllocation ? RLR_ERR_OOM : RLR_ERR_CUDA, "store upload failed: %s", cudaGetErrorString(e));
+        }
+    }
+    // The upload ran on the legacy stream; search streams are cudaStreamNonBlocking and do not wait for it.
+    // Return only when every row (memset, copy, normalize, f16 copy) has landed, and report async errors.
+    {
+        cudaError_t e = cudaStreamSynchronize(0);
+        if (e != cudaSuccess && rc == RLR_OK) {
+            cudaGetLastError();
+            rc = fail(RLR_ERR_CUDA, "store upload failed: %s", cudaGetErrorString(e));
         }
     }
     cudaFree(d_stage);
@@ -1043,11 +981,14 @@ int search_batch_core(rlr_store *s, const float *queries, uint32_t n_queries, ui
     if (s->d_rows16 == nullptr)
         return fail(RLR_ERR_INVALID_ARG, "rlr_search_batch needs the binary16 store copy (RLR_STORE_KEEP_F16 / RLR_STORE_F16_ONLY)");
     {
-        static std::once_flag once[64];
-        cudaError_t ce = cudaSuccess;
-        const int optin = s->smem_optin;
-        std::call_once(once[s->device], [&] { ce = rlr::batch_configure(optin); });
-        CU_TRY(ce);
+        // per device, remembered only when it succeeded: a failed configure is retried (and reported) by the next call
+        static std::mutex mu;
+        static bool configured[64] = {false};
+        std::lock_guard<std::mutex> lk(mu);
+        if (!configured[s->device]) {
+            CU_TRY(rlr::batch_configure(s->smem_optin));
+            configured[s->device] = true;
+        }
     }
     CtxLease lease(s);
     if (int rc = lease.acquire()) return rc;
@@ -1157,7 +1098,10 @@ int search_batch_core(rlr_store *s, const float *queries, uint32_t n_queries, ui
     }
     if (timed) CU_TRY(cudaEventRecord(c->ev[2], st));
     if (to_device) {
-        // rank-ordered keys stay on the device: [n_queries][m], rows beyond min(m, n_rows) are key 0
+        // rank-ordered keys stay on the device: [n_queries][m], rows beyond min(m, n_rows) are key 0.
+        // The caller may still have reads of d_keys / d_cnt queued on its stream: order our writes behind them.
+        CU_TRY(cudaEventRecord(c->ev[4], user_stream));
+        CU_TRY(cudaStreamWaitEvent(st, c->ev[4], 0));
         if (m_eff != m) CU_TRY(cudaMemsetAsync(d_keys, 0, static_cast<size_t>(nq) * m * 8, st));
         CU_TRY(cudaMemcpy2DAsync(d_keys, static_cast<size_t>(m) * 8, b.d_state, static_cast<size_t>(m_eff) * 8,
                                  static_cast<size_t>(m_eff) * 8, nq, cudaMemcpyDeviceToDevice, st));
@@ -1471,25 +1415,6 @@ RLR_EXPORT int rlr_mmr_peers_async(rlr_ctx *c, rlr_peer_set *p, const void *d_ca
 // ---------------------------------------------------------------------------------
 // fused exchange: scan kernels post their lists straight into the root GPU's mailbox
 // ---------------------------------------------------------------------------------
-struct rlr_mailbox {
-    int device = 0;
-    bool owner = false;
-    uint32_t n_ranks = 0, m_cap = 0, ring = 0;
-    uint8_t *base = nullptr;          // root's allocation (local on the root, an IPC mapping elsewhere)
-    uint32_t *d_status = nullptr;     // local
-    size_t bytes = 0;
-    // layout: [0] consumed[ring] u64 (one word per slot: the last sequence number merged out of it)
-    //         | [1024] flags[ring][n_ranks] u64 | counts[ring][n_ranks] u32 | (4 KB aligned) lists
-    size_t flags_off() const { return 1024; }
-    size_t counts_off() const { return flags_off() + static_cast<size_t>(ring) * n_ranks * 8; }
-    size_t lists_off() const { return (counts_off() + static_cast<size_t>(ring) * n_ranks * 4 + 4095) & ~static_cast<size_t>(4095); }
-    size_t total() const { return lists_off() + static_cast<size_t>(ring) * n_ranks * m_cap * sizeof(rlr_cand); }
-    unsigned long long *consumed(uint32_t slot) const { return reinterpret_cast<unsigned long long *>(base) + slot; }
-    unsigned long long *flag(uint32_t slot, uint32_t r) const { return reinterpret_cast<unsigned long long *>(base + flags_off()) + static_cast<size_t>(slot) * n_ranks + r; }
-    uint32_t *count(uint32_t slot, uint32_t r) const { return reinterpret_cast<uint32_t *>(base + counts_off()) + static_cast<size_t>(slot) * n_ranks + r; }
-    rlr_cand *list(uint32_t slot, uint32_t r) const { return reinterpret_cast<rlr_cand *>(base + lists_off()) + (static_cast<size_t>(slot) * n_ranks + r) * m_cap; }
-};
-
 namespace {
 int mailbox_check_shape(uint32_t n_ranks, uint32_t m_cap, uint32_t ring)
 {

@@ -1,0 +1,137 @@
+// api_internal.hpp -- definitions shared by the translation units that implement the C ABI
+// (api.cu: single-GPU stores; cluster.cu: one process driving the GPUs of a box).  Internal.
+#pragma once
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+#define RLR_EXPORT extern "C" __attribute__((visibility("default")))
+
+struct rlr_store {
+    int device = 0;
+    uint32_t dim = 0, pitch = 0, flags = 0;
+    uint64_t n_rows = 0, row_base = 0;
+    uint64_t capacity = 0;          // rows the device allocations can hold (>= n_rows)
+    float *d_rows = nullptr;        // f32 matrix (absent for RLR_STORE_F16_ONLY)
+    void *d_rows16 = nullptr;       // binary16 copy (RLR_STORE_KEEP_F16 / RLR_STORE_F16_ONLY)
+    uint32_t pitch16 = 0;           // elements per binary16 row (dim rounded up to 64)
+    CUtensorMap tmap, tmap16;
+    int sm_count = 0, smem_optin = 0;
+    bool use_half(uint32_t flags) const { return d_rows == nullptr || ((flags & RLR_SEARCH_F16) && d_rows16 != nullptr); }
+    std::mutex mu;
+    std::vector<rlr_ctx *> free_ctx;
+};
+
+struct rlr_ctx {
+    rlr_store *s = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float *d_query = nullptr;
+    uint32_t *d_lex_rows = nullptr;
+    float *d_lex_norm = nullptr;
+    rlr_cand *d_lists = nullptr;
+    uint32_t *d_counts = nullptr;
+    uint32_t *d_ticket = nullptr;
+    uint32_t *d_pub = nullptr;
+    rlr_cand *d_tmp = nullptr;
+    rlr_cand *d_pool = nullptr;
+    uint32_t *d_pool_n = nullptr;
+    float *d_tri = nullptr;
+    uint32_t *d_sel_pos = nullptr;
+    uint32_t *d_sel_n = nullptr;
+    rlr_cand *d_result = nullptr;
+    uint32_t *d_rows_in = nullptr;
+    float *d_rel_in = nullptr;
+    uint32_t *d_p_in = nullptr;
+    // pinned host staging
+    float *h_query = nullptr;
+    uint32_t *h_lex_rows = nullptr;
+    float *h_lex_norm = nullptr;
+    rlr_cand *h_result = nullptr;   // RLR_MAX_M records
+    uint32_t *h_u32 = nullptr;      // RLR_MAX_M + 8 words
+    float *h_rel = nullptr;
+    uint64_t launches = 0;
+    uint32_t n_lists_cap = 0;
+    uint32_t search_flags = 0;      // RLR_SEARCH_F16 for the device-level entry points
+    // batched path workspace (allocated on first use, grown on demand)
+    void *batch_mem = nullptr;
+    size_t batch_bytes = 0;
+    float *h_batch_q = nullptr;     // pinned staging for the query batch
+    size_t h_batch_q_bytes = 0;
+    unsigned long long *h_batch_state = nullptr;
+    size_t h_batch_state_bytes = 0;
+};
+
+struct rlr_mailbox {
+    int device = 0;
+    bool owner = false;
+    uint32_t n_ranks = 0, m_cap = 0, ring = 0;
+    uint8_t *base = nullptr;          // root's allocation (local on the root, an IPC mapping elsewhere)
+    uint32_t *d_status = nullptr;     // local
+    size_t bytes = 0;
+    // layout: [0] consumed[ring] u64 (one word per slot: the last sequence number merged out of it)
+    //         | [1024] flags[ring][n_ranks] u64 | counts[ring][n_ranks] u32 | (4 KB aligned) lists
+    size_t flags_off() const { return 1024; }
+    size_t counts_off() const { return flags_off() + static_cast<size_t>(ring) * n_ranks * 8; }
+    size_t lists_off() const { return (counts_off() + static_cast<size_t>(ring) * n_ranks * 4 + 4095) & ~static_cast<size_t>(4095); }
+    size_t total() const { return lists_off() + static_cast<size_t>(ring) * n_ranks * m_cap * sizeof(rlr_cand); }
+    unsigned long long *consumed(uint32_t slot) const { return reinterpret_cast<unsigned long long *>(base) + slot; }
+    unsigned long long *flag(uint32_t slot, uint32_t r) const { return reinterpret_cast<unsigned long long *>(base + flags_off()) + static_cast<size_t>(slot) * n_ranks + r; }
+    uint32_t *count(uint32_t slot, uint32_t r) const { return reinterpret_cast<uint32_t *>(base + counts_off()) + static_cast<size_t>(slot) * n_ranks + r; }
+    rlr_cand *list(uint32_t slot, uint32_t r) const { return reinterpret_cast<rlr_cand *>(base + lists_off()) + (static_cast<size_t>(slot) * n_ranks + r) * m_cap; }
+};
+
+
+namespace rlr_api {
+
+constexpr uint32_t kLexCap = 8192;
+
+extern thread_local std::string g_err;
+extern thread_local rlr_timings g_timings;
+
+int fail(int code, const char *fmt, ...);
+
+#define CU_TRY(expr)                                                                             \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            cudaGetLastError();                                                                  \
+            return ::rlr_api::fail(e__ == cudaErrorMemoryAllocation ? RLR_ERR_OOM : RLR_ERR_CUDA, \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                        \
+    } while (0)
+
+int ensure_device(int device);          // exists, is sm_100, kernels configured; leaves it current
+int device_sm_count(int device);
+int ctx_new(rlr_store *s, rlr_ctx **out);
+void ctx_free(rlr_ctx *c);
+void host_normalize(float *v, size_t n);   // src/rag_engine.rs:1763-1771
+void unpack(const rlr_cand *h, uint32_t n, uint32_t *rows, float *score, float *emb, float *lex);
+
+// RAII lease of a pooled ctx so that concurrent searches on one store are re-entrant.
+struct CtxLease {
+    rlr_store *s;
+    rlr_ctx *c = nullptr;
+    explicit CtxLease(rlr_store *st) : s(st) {}
+    int acquire()
+    {
+        {
+            std::lock_guard<std::mutex> lk(s->mu);
+            if (!s->free_ctx.empty()) { c = s->free_ctx.back(); s->free_ctx.pop_back(); }
+        }
+        if (c) return RLR_OK;
+        return ctx_new(s, &c);
+    }
+    ~CtxLease()
+    {
+        if (c) { std::lock_guard<std::mutex> lk(s->mu); s->free_ctx.push_back(c); }
+    }
+};
+
+} // namespace rlr_api

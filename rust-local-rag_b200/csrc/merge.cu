@@ -134,18 +134,28 @@ mailbox_merge_kernel(const rlr_cand *slot, uint32_t list_stride, const unsigned 
 {
     extern __shared__ uint8_t smem_raw[];
     uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw);
-    __shared__ uint32_t s_total;
+    __shared__ uint32_t s_total, s_bad;
     const uint32_t t = threadIdx.x;
     const uint32_t n = n_lists * m;
-    if (t == 0) s_total = 0;
+    if (t == 0) { s_total = 0; s_bad = 0; }
+    __syncthreads();
     if (t < n_lists) {
         const unsigned long long t_start = globaltimer_ns_common();
         while (ld_acquire_sys_u64(flags + t) < seq) {
-            if (globaltimer_ns_common() - t_start > kMailboxTimeoutNs) { *status = 2u; break; }
+            if (globaltimer_ns_common() - t_start > kMailboxTimeoutNs) { *status = 2u; s_bad = 1; break; }
             __nanosleep(100);
         }
     }
     __syncthreads();
+    if (s_bad != 0) {
+        // a rank never delivered: an EMPTY result plus the sticky status word, never a merge of stale lists
+        for (uint32_t i = t; i < m; i += kMergeThreads) { rlr_cand z; z.key = 0; z.emb = 0.0f; z.lex = 0.0f; out[i] = z; }
+        if (t == 0) {
+            if (out_n != nullptr) *out_n = 0;
+            st_release_sys_u64(consumed, seq);
+        }
+        return;
+    }
     // the records were written by other GPUs: read them at L2 (never from a stale L1 line)
     for (uint32_t i = t; i < n; i += kMergeThreads) {
         const uint32_t j = i / m;

@@ -65,7 +65,7 @@ mmr_pairwise_kernel(const void *__restrict__ emb, uint32_t pitch, const rlr_cand
         if (ci < p) {
             if (peers.n != 0) {
                 // global row -> owning shard -> peer-mapped pointer (a load over NVLink if not local)
-                const uint32_t g = key_row(cands[ci].key);
+                const uint32_t g = rows != nullptr ? rows[ci] : key_row(cands[ci].key);   // explicit rows are GLOBAL here
                 for (uint32_t s = 0; s < peers.n; ++s)
                     if (g >= peers.row_base[s] && g - peers.row_base[s] < peers.n_rows[s])
                         ptr = static_cast<const uint8_t *>(peers.base[s]) + static_cast<size_t>(g - peers.row_base[s]) * pitch * ESZ;

@@ -581,14 +581,24 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
     if (g_out == nullptr) return;
     unsigned long long *tr = g_trace != nullptr ? g_trace + 4 * gridDim.x : nullptr;
     if (tr != nullptr && t == 0) tr[0] = globaltimer_ns();
-    if (post.flag != nullptr && post.consumed != nullptr && t == 0 && post.seq > post.ring) {
+    if (post.flag != nullptr) {
         // fused exchange: g_out is a mailbox slot (possibly in a peer GPU's HBM); it is free once
-        // the root has merged the query that used it `ring` sequence numbers ago
-        const unsigned long long t_start = globaltimer_ns();
-        while (ld_acquire_sys_u64(post.consumed) + post.ring < post.seq) {
-            if (globaltimer_ns() - t_start > kMailboxTimeoutNs) { *post.status = 1u; break; }
-            __nanosleep(200);
+        // the root has merged the query that used it `ring` sequence numbers ago.  On a timeout the
+        // slot is NOT touched and the flag is not published: the root's merge then times out for this
+        // query as well and delivers an empty result with a sticky status, never a stale list.
+        if (t == 0) {
+            uint32_t timed_out = 0;
+            if (post.consumed != nullptr && post.seq > post.ring) {
+                const unsigned long long t_start = globaltimer_ns();
+                while (ld_acquire_sys_u64(post.consumed) + post.ring < post.seq) {
+                    if (globaltimer_ns() - t_start > kMailboxTimeoutNs) { *post.status = 1u; timed_out = 1; break; }
+                    __nanosleep(200);
+                }
+            }
+            s_tile[0] = timed_out;            // the tile mailbox is idle: the producer has exited
         }
+        named_bar_sync(1, R);
+        if (s_tile[0] != 0) return;
     }
     final_merge(keys, embs, reinterpret_cast<uint32_t *>(smem + L.stages_off + kTopBuf * 12), s_count, s_flag, g_lists,
                 g_counts, gridDim.x, m, row_base, lex_rows, lex_norm, n_lex, g_out, g_out_n, t, tr);

@@ -123,11 +123,36 @@ class Buffers:
         self.p_cap = p_cap
 
 
+def stage_lex(lo: int, hi: int, lex_rows, lex_scores, device):
+    """src/rag_engine.rs:505-530 for ONE shard [lo, hi): the lexical map that LexicalIndex::score
+    returned (global rows, raw BM25 scores; every rank passes the SAME lists) becomes this rank's
+    (sorted local rows, score / max_lexical) device tensors.  max_lexical is the GLOBAL maximum
+    (fold(0.0, max).max(EPSILON), :511-515), so a row's lexical_score does not depend on the sharding;
+    later duplicates of a row win (HashMap collect).  Returns (d_rows int32, d_norm f32, n) or None."""
+    import numpy as np
+    if lex_rows is None or len(lex_rows) == 0:
+        return None
+    rows = np.asarray(lex_rows, dtype=np.int64)
+    sc = np.asarray(lex_scores, dtype=np.float32)
+    max_lex = np.float32(max(np.float32(0.0), sc.max()))
+    max_lex = max(max_lex, np.finfo(np.float32).eps)
+    last = {}
+    for i, r in enumerate(rows.tolist()):
+        if lo <= r < hi:
+            last[r - lo] = i
+    if not last:
+        return None
+    loc = np.array(sorted(last), dtype=np.uint32)
+    norm = (sc[[last[int(r)] for r in loc]] / np.float32(max_lex)).astype(np.float32)     # :527-530, one f32 division
+    return (torch.from_numpy(loc.view(np.int32)).to(device), torch.from_numpy(norm).to(device), int(loc.shape[0]))
+
+
 def sharded_search(backend, group, bufs: Buffers, query, top_k: int, diversity_factor: float,
-                   w_embed: float, w_lex: float):
+                   w_embed: float, w_lex: float, lex=None):
     """search_with_diversity (src/rag_engine.rs:717-759, no reranker) over a row-sharded
     corpus.  Returns (result, result_n) device tensors; they are meaningful on rank 0
-    (for diversity_factor == 0 on every rank)."""
+    (for diversity_factor == 0 on every rank).  `lex`: this rank's `stage_lex(...)` triple (the
+    BM25 term of the blend, :505-532) or None for an embedding-only query."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     lam = clamp_lambda(float(diversity_factor))
@@ -141,7 +166,7 @@ def sharded_search(backend, group, bufs: Buffers, query, top_k: int, diversity_f
         if m > backend.mailbox_m_cap:        # checked BEFORE taking a sequence number: ranks must stay in step
             raise ValueError(f"pool {m} exceeds the mailbox capacity {backend.mailbox_m_cap}")
         seq = backend.next_seq()
-        backend.topm_post(query, w_embed, w_lex, m, seq)
+        backend.topm_post(query, w_embed, w_lex, m, seq, lex)
         if rank != 0:
             return bufs.result, bufs.sel_n
         backend.mailbox_merge(seq, m, bufs.pool[:m], bufs.pool_n)
@@ -151,7 +176,7 @@ def sharded_search(backend, group, bufs: Buffers, query, top_k: int, diversity_f
         return bufs.result, bufs.sel_n
     local = bufs.local[:m]
     gathered = bufs.gathered[:, :m]
-    backend.topm(query, w_embed, w_lex, m, local, bufs.local_n)
+    backend.topm(query, w_embed, w_lex, m, local, bufs.local_n, lex)
     if world > 1:
         g_flat = gathered if gathered.is_contiguous() else None
         if g_flat is not None and dist.get_backend(group) == "nccl":
@@ -244,6 +269,7 @@ class CudaBackend:
         self.mailbox = None
         self.mailbox_ready = False
         self.mailbox_m_cap = 0
+        self.mailbox_ring = 0
         self._seq = 0
         self._rank = 0
 
@@ -273,6 +299,7 @@ class CudaBackend:
                 err = str(e)
         self.mailbox = mb if mb else None
         self.mailbox_m_cap = m_cap
+        self.mailbox_ring = ring
         self._agree(group, err)
         self.mailbox_ready = True
 
@@ -284,6 +311,9 @@ class CudaBackend:
     def add_lane(self) -> int:
         if not hasattr(self, "ctxs"):
             self.ctxs = [self.ctx]
+        if self.mailbox_ready and self.mailbox_ring % (len(self.ctxs) + 1) != 0:
+            raise ValueError(f"mailbox ring {self.mailbox_ring} is not a multiple of {len(self.ctxs) + 1} lanes: "
+                             "a slot must always be used by the same lane")
         c = C.c_void_p()
         self.B.check(self.lib.rlr_ctx_create(self.store.handle, C.byref(c)))
         if self.search_flags:
@@ -298,9 +328,10 @@ class CudaBackend:
         self._seq += 1
         return self._seq
 
-    def topm_post(self, query, w_embed, w_lex, m, seq):
+    def topm_post(self, query, w_embed, w_lex, m, seq, lex=None):
+        lr, ln, nl = (self._p(lex[0]), self._p(lex[1]), lex[2]) if lex is not None else (None, None, 0)
         self.B.check(self.lib.rlr_topm_post_async(self.ctx, self.mailbox, self._rank, seq, self._p(query), w_embed, w_lex,
-                                                  None, None, 0, m, self._stream()))
+                                                  lr, ln, nl, m, self._stream()))
 
     def mailbox_merge(self, seq, m, out, out_n):
         self.B.check(self.lib.rlr_mailbox_merge_async(self.ctx, self.mailbox, seq, m, self._p(out), self._p(out_n),
@@ -310,6 +341,15 @@ class CudaBackend:
         v = C.c_uint32(0)
         self.B.check(self.lib.rlr_mailbox_status(self.mailbox, C.byref(v)))
         return v.value
+
+    def check_mailbox(self) -> None:
+        """Raise if any in-kernel mailbox wait of this rank ever timed out (the affected queries returned
+        EMPTY results; see scan_topm.cu / merge.cu).  Synchronises the device: call it when reading results."""
+        if self.mailbox_ready:
+            st = self.mailbox_status()
+            if st:
+                raise self.B.RlrError(self.B.RLR_ERR_CUDA, f"a mailbox wait timed out on this rank (status {st}): "
+                                      "a peer rank is dead or out of step; results since then are empty")
 
     def _agree(self, group, err: Optional[str]) -> None:
         """Collective: every rank learns whether ANY rank failed its local step, and all raise together
@@ -396,8 +436,9 @@ class CudaBackend:
             total += n.value
         return total
 
-    def topm(self, query, w_embed, w_lex, m, out, out_n):
-        self.B.check(self.lib.rlr_topm_async(self.ctx, self._p(query), w_embed, w_lex, None, None, 0, m,
+    def topm(self, query, w_embed, w_lex, m, out, out_n, lex=None):
+        lr, ln, nl = (self._p(lex[0]), self._p(lex[1]), lex[2]) if lex is not None else (None, None, 0)
+        self.B.check(self.lib.rlr_topm_async(self.ctx, self._p(query), w_embed, w_lex, lr, ln, nl, m,
                                              self._p(out), self._p(out_n), self._stream()))
 
     def merge(self, lists, n_lists, m, out, out_n):

@@ -132,9 +132,14 @@ SIDECAR_HEADER = 40
 class DeviceStore:
     """Owns one rlr_store handle."""
 
+    _HOT_PREFIX = "rlr_"          # ClusterStore: "rlr_cluster_" (same arguments, same results)
+
     def __init__(self, handle, lib):
         self._h = handle
         self._lib = lib
+
+    def _hot(self, name: str):
+        return getattr(self._lib, self._HOT_PREFIX + name)
 
     @classmethod
     def from_rows(cls, rows: np.ndarray, device: int = 0, row_base: int = 0, flags: int = 0) -> "DeviceStore":
@@ -218,7 +223,7 @@ class DeviceStore:
         wc = B.ResolvedWeightsC(w.embedding, w.lexical, w.reranker, w.initial)
         lr = np.ascontiguousarray(lex_rows, dtype=np.uint32) if lex_rows is not None and len(lex_rows) else None
         ls = np.ascontiguousarray(lex_scores, dtype=np.float32) if lr is not None else None
-        B.check(self._lib.rlr_search_topm(self._h, B.ptr(q), q.shape[0], flags, C.byref(wc), B.ptr(lr), B.ptr(ls),
+        B.check(self._hot("search_topm")(self._h, B.ptr(q), q.shape[0], flags, C.byref(wc), B.ptr(lr), B.ptr(ls),
                                           0 if lr is None else len(lr), m, B.ptr(rows), B.ptr(comb), B.ptr(emb),
                                           B.ptr(lex), C.byref(n)))
         k = n.value
@@ -229,7 +234,7 @@ class DeviceStore:
         rel = np.ascontiguousarray(relevance, dtype=np.float32)
         out = np.empty(max(len(r), 1), np.uint32)
         n = C.c_uint32(0)
-        B.check(self._lib.rlr_mmr(self._h, B.ptr(r) if len(r) else None, B.ptr(rel) if len(r) else None, len(r),
+        B.check(self._hot("mmr")(self._h, B.ptr(r) if len(r) else None, B.ptr(rel) if len(r) else None, len(r),
                                   top_k, lam, flags, B.ptr(out), C.byref(n)))
         return out[:n.value]
 
@@ -243,7 +248,7 @@ class DeviceStore:
         wc = B.ResolvedWeightsC(w.embedding, w.lexical, w.reranker, w.initial)
         lr = np.ascontiguousarray(lex_rows, dtype=np.uint32) if lex_rows is not None and len(lex_rows) else None
         ls = np.ascontiguousarray(lex_scores, dtype=np.float32) if lr is not None else None
-        B.check(self._lib.rlr_search_mmr(self._h, B.ptr(q), q.shape[0], flags, top_k, diversity, C.byref(wc),
+        B.check(self._hot("search_mmr")(self._h, B.ptr(q), q.shape[0], flags, top_k, diversity, C.byref(wc),
                                          B.ptr(lr), B.ptr(ls), 0 if lr is None else len(lr), B.ptr(rows),
                                          B.ptr(score), B.ptr(emb), B.ptr(lex), C.byref(n)))
         k = n.value
@@ -253,7 +258,7 @@ class DeviceStore:
         q = np.ascontiguousarray(query, dtype=np.float32)
         rows = np.empty(max(count, 1), np.uint32); score = np.empty(max(count, 1), np.float32)
         n = C.c_uint32(0)
-        B.check(self._lib.rlr_embedding_candidates(self._h, B.ptr(q), q.shape[0], flags, count, B.ptr(rows),
+        B.check(self._hot("embedding_candidates")(self._h, B.ptr(q), q.shape[0], flags, count, B.ptr(rows),
                                                    B.ptr(score), C.byref(n)))
         return rows[:n.value], score[:n.value]
 
@@ -284,6 +289,92 @@ class DeviceStore:
         t = B.TimingsC()
         B.check(self._lib.rlr_last_timings(C.byref(t)))
         return t
+
+
+class ClusterStore(DeviceStore):
+    """Owns one rlr_cluster handle: the same store row-sharded over several GPUs of one box and driven from
+    THIS process (the reference is one process, src/main.rs:140-167).  Same raw hot-path calls as DeviceStore
+    (`search_topm`, `mmr`, `search_mmr`, `embedding_candidates`), same results bit for bit; rows are global."""
+
+    _HOT_PREFIX = "rlr_cluster_"
+
+    @staticmethod
+    def _create(lib, devices, dim, n, rows, flags, shard_rows):
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        sr = np.ascontiguousarray(shard_rows, dtype=np.uint64) if shard_rows is not None else None
+        if sr is not None and len(sr) != len(dev):
+            raise ValueError("shard_rows needs one entry per device")
+        h = C.c_void_p()
+        B.check(lib.rlr_cluster_create(B.ptr(dev), len(dev), dim, n, B.ptr(rows) if rows is not None and n else None, dim,
+                                       flags, B.ptr(sr), C.byref(h)))
+        return h
+
+    @classmethod
+    def from_rows(cls, rows: np.ndarray, devices: Sequence[int] = (0,), flags: int = 0, shard_rows=None) -> "ClusterStore":
+        lib = B.load()
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        if rows.ndim != 2:
+            raise ValueError("rows must be (n, dim)")
+        return cls(cls._create(lib, devices, rows.shape[1], rows.shape[0], rows, flags, shard_rows), lib)
+
+    @classmethod
+    def empty(cls, n_rows: int, dim: int, devices: Sequence[int] = (0,), flags: int = 0, shard_rows=None) -> "ClusterStore":
+        lib = B.load()
+        return cls(cls._create(lib, devices, dim, n_rows, None, flags, shard_rows), lib)
+
+    @classmethod
+    def synthetic(cls, n_rows: int, dim: int, kind: int = B.RLR_SYNTH_IID, seed: int = 0x5EED0001,
+                  centroid_seed: int = 0x5EED00C0, n_clusters: int = 4096, sigma: float = 0.65,
+                  devices: Sequence[int] = (0,), flags: int = 0, shard_rows=None) -> "ClusterStore":
+        s = cls.empty(n_rows, dim, devices=devices, flags=flags, shard_rows=shard_rows)
+        B.check(s._lib.rlr_cluster_fill_synthetic(s._h, kind, seed, centroid_seed, n_clusters, sigma))
+        return s
+
+    def cluster_info(self) -> B.ClusterInfoC:
+        out = B.ClusterInfoC()
+        B.check(self._lib.rlr_cluster_info_get(self._h, C.byref(out)))
+        return out
+
+    def info(self) -> B.StoreInfoC:
+        """The cluster seen as one store (row_base 0, device = the root's)."""
+        ci = self.cluster_info()
+        out = B.StoreInfoC()
+        out.n_rows, out.row_base, out.dim, out.pitch, out.device, out.flags = ci.n_rows, 0, ci.dim, ci.pitch, ci.device[0], ci.flags
+        return out
+
+    def read_rows(self, rows: Sequence[int]) -> np.ndarray:
+        r = np.ascontiguousarray(rows, dtype=np.uint32)
+        out = np.empty((len(r), self.cluster_info().dim), dtype=np.float32)
+        B.check(self._lib.rlr_cluster_read_rows(self._h, B.ptr(r), len(r), B.ptr(out)))
+        return out
+
+    def upload(self, row0: int, rows: np.ndarray) -> None:
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        B.check(self._lib.rlr_cluster_upload(self._h, row0, rows.shape[0], B.ptr(rows), rows.shape[1]))
+
+    def append(self, rows):
+        raise B.RlrError(B.RLR_ERR_UNSUPPORTED, "a cluster is a bulk-loaded snapshot: mutate a single-GPU store or rebuild")
+
+    remove_rows = append
+
+    def last_scan_ms(self) -> List[float]:
+        buf = np.zeros(B.RLR_MAX_SHARDS, np.float32)
+        n = C.c_uint32(0)
+        B.check(self._lib.rlr_cluster_last_scan_ms(B.ptr(buf), len(buf), C.byref(n)))
+        return buf[:n.value].tolist()
+
+    def launches(self) -> int:
+        n = C.c_uint64(0)
+        B.check(self._lib.rlr_cluster_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def search_batch(self, *a, **k):
+        raise B.RlrError(B.RLR_ERR_UNSUPPORTED, "batched queries over a cluster: use dist.sharded_search_batch")
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.rlr_cluster_destroy(self._h)
+            self._h = None
 
 
 Query = Union[str, Sequence[float], np.ndarray]
@@ -347,6 +438,13 @@ class LexicalIndex:
             pass
 
 
+def _make_store(rows: np.ndarray, device: int, devices: Optional[Sequence[int]]):
+    """One GPU -> DeviceStore; `devices=[...]` -> the same rows sharded over those GPUs (ClusterStore)."""
+    if devices is not None and len(devices) > 1:
+        return ClusterStore.from_rows(rows, devices=devices)
+    return DeviceStore.from_rows(rows, device=device if devices is None else devices[0])
+
+
 class RagEngine:
     """The retrieval half of the reference's RagEngine (src/rag_engine.rs:104-113): chunk
     metadata on the host, embeddings on the device."""
@@ -369,13 +467,15 @@ class RagEngine:
 
     # ---- construction ----
     @classmethod
-    def load_from_disk(cls, data_dir: str, model: str = "nomic-embed-text", device: int = 0, **kw) -> "RagEngine":
+    def load_from_disk(cls, data_dir: str, model: str = "nomic-embed-text", device: int = 0,
+                       devices: Optional[Sequence[int]] = None, **kw) -> "RagEngine":
         """load_from_disk + apply_loaded_state, src/rag_engine.rs:1520-1696, for the
         model-specific file `chunks_{sanitized}.json` (:1465-1468)."""
-        return cls.from_chunks_json(get_index_path(data_dir, model), model=model, device=device, **kw)
+        return cls.from_chunks_json(get_index_path(data_dir, model), model=model, device=device, devices=devices, **kw)
 
     @classmethod
-    def from_chunks_json(cls, path: str, model: str = "nomic-embed-text", device: int = 0, **kw) -> "RagEngine":
+    def from_chunks_json(cls, path: str, model: str = "nomic-embed-text", device: int = 0,
+                         devices: Optional[Sequence[int]] = None, **kw) -> "RagEngine":
         with open(path, "r", encoding="utf-8") as f:
             state = json.load(f)
         version = int(state["version"])
@@ -403,7 +503,7 @@ class RagEngine:
         lib = B.load()
         for i in range(rows.shape[0]):           # :1678-1680 re-normalise every embedding at load
             B.check(lib.rlr_normalize(rows[i].ctypes.data_as(C.POINTER(C.c_float)), rows.shape[1]))
-        eng = cls(metas, DeviceStore.from_rows(rows, device=device), model=model, **kw)
+        eng = cls(metas, _make_store(rows, device, devices), model=model, **kw)
         eng.needs_reindex = bool(state.get("needs_reindex", False))
         eng.document_hashes = dict(state.get("document_hashes", {}))
         if not eng.document_hashes and metas:    # :1686-1691
@@ -479,7 +579,7 @@ class RagEngine:
 
     @classmethod
     def from_rows(cls, rows: np.ndarray, chunk_ids: Optional[Sequence[str]] = None, normalize: bool = True,
-                  device: int = 0, **kw) -> "RagEngine":
+                  device: int = 0, devices: Optional[Sequence[int]] = None, **kw) -> "RagEngine":
         rows = np.array(rows, dtype=np.float32, order="C")
         if normalize:                            # :359 normalise at insert
             lib = B.load()
@@ -487,7 +587,7 @@ class RagEngine:
                 B.check(lib.rlr_normalize(rows[i].ctypes.data_as(C.POINTER(C.c_float)), rows.shape[1]))
         ids = list(chunk_ids) if chunk_ids is not None else [f"chunk-{i}" for i in range(rows.shape[0])]
         metas = [DocumentChunk(id=i) for i in ids]
-        return cls(metas, DeviceStore.from_rows(rows, device=device), **kw)
+        return cls(metas, _make_store(rows, device, devices), **kw)
 
     # ---- mutation: add_document, src/rag_engine.rs:219-402 (the store half: :347-386) ----
     def replace_document(self, document_name: str, chunks: List[DocumentChunk], embeddings: np.ndarray) -> None:

@@ -25,12 +25,14 @@ pub const RLR_IPC_HANDLE_BYTES: usize = 64;
 pub const RLR_SYNTH_IID: c_int = 0;
 pub const RLR_SYNTH_CLUSTERED: c_int = 1;
 pub const RLR_ABI_VERSION: c_int = 1;
+pub const RLR_MAX_SHARDS: usize = 16;
 
 #[repr(C)] pub struct rlr_store { _p: [u8; 0] }
 #[repr(C)] pub struct rlr_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct rlr_peer_set { _p: [u8; 0] }
 #[repr(C)] pub struct rlr_mailbox { _p: [u8; 0] }
 #[repr(C)] pub struct rlr_lexical { _p: [u8; 0] }
+#[repr(C)] pub struct rlr_cluster { _p: [u8; 0] }
 
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct rlr_query_weights { pub embedding: f32, pub lexical: f32, pub reranker: f32, pub initial: f32, pub has: u32 }
@@ -42,6 +44,8 @@ pub struct rlr_store_info { pub n_rows: u64, pub row_base: u64, pub dim: u32, pu
 pub struct rlr_device_info { pub device: i32, pub sm_count: i32, pub cc_major: i32, pub cc_minor: i32, pub total_mem: u64, pub name: [c_char; 128] }
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct rlr_timings { pub scan_ms: f32, pub merge_ms: f32, pub mmr_ms: f32, pub total_ms: f32, pub launches: u32 }
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct rlr_cluster_info { pub n_rows: u64, pub dim: u32, pub pitch: u32, pub flags: u32, pub n_shards: u32, pub device: [i32; RLR_MAX_SHARDS], pub row_base: [u64; RLR_MAX_SHARDS], pub shard_rows: [u64; RLR_MAX_SHARDS] }
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct rlr_cand { pub key: u64, pub emb: f32, pub lex: f32 }
 
@@ -77,6 +81,18 @@ extern "C" {
     pub fn rlr_lexical_score(lx: *const rlr_lexical, query_utf8: *const c_char, len: usize, limit: u32, out_keys: *mut u64, out_scores: *mut f32, cap: u32, out_n: *mut u32) -> c_int;
     pub fn rlr_tokenize(text_utf8: *const c_char, len: usize, out: *mut c_char, out_cap: usize, out_len: *mut usize, out_tokens: *mut u32) -> c_int;
     pub fn rlr_last_timings(out: *mut rlr_timings) -> c_int;
+    pub fn rlr_cluster_create(devices: *const c_int, n_devices: u32, dim: u32, n_rows: u64, rows: *const f32, host_pitch: u64, flags: u32, shard_rows: *const u64, out: *mut *mut rlr_cluster) -> c_int;
+    pub fn rlr_cluster_destroy(c: *mut rlr_cluster) -> c_int;
+    pub fn rlr_cluster_info_get(c: *const rlr_cluster, out: *mut rlr_cluster_info) -> c_int;
+    pub fn rlr_cluster_upload(c: *mut rlr_cluster, row0: u64, n: u64, rows: *const f32, host_pitch: u64) -> c_int;
+    pub fn rlr_cluster_read_rows(c: *const rlr_cluster, rows: *const u32, n: u64, out: *mut f32) -> c_int;
+    pub fn rlr_cluster_fill_synthetic(c: *mut rlr_cluster, kind: c_int, seed: u64, centroid_seed: u64, n_clusters: u32, sigma: f32) -> c_int;
+    pub fn rlr_cluster_search_topm(c: *mut rlr_cluster, query: *const f32, dim: u32, flags: u32, w: *const rlr_resolved_weights, lex_rows: *const u32, lex_scores: *const f32, n_lex: u32, m: u32, out_rows: *mut u32, out_combined: *mut f32, out_emb: *mut f32, out_lex: *mut f32, out_n: *mut u32) -> c_int;
+    pub fn rlr_cluster_mmr(c: *mut rlr_cluster, cand_rows: *const u32, relevance: *const f32, p: u32, top_k: u32, lambda: f32, flags: u32, out_sel_pos: *mut u32, out_n: *mut u32) -> c_int;
+    pub fn rlr_cluster_search_mmr(c: *mut rlr_cluster, query: *const f32, dim: u32, flags: u32, top_k: u32, diversity_factor: f32, w: *const rlr_resolved_weights, lex_rows: *const u32, lex_scores: *const f32, n_lex: u32, out_rows: *mut u32, out_score: *mut f32, out_emb: *mut f32, out_lex: *mut f32, out_n: *mut u32) -> c_int;
+    pub fn rlr_cluster_embedding_candidates(c: *mut rlr_cluster, query: *const f32, dim: u32, flags: u32, count: u32, out_rows: *mut u32, out_score: *mut f32, out_n: *mut u32) -> c_int;
+    pub fn rlr_cluster_last_scan_ms(out_ms: *mut f32, cap: u32, out_n: *mut u32) -> c_int;
+    pub fn rlr_cluster_launch_count(c: *const rlr_cluster, out: *mut u64) -> c_int;
     pub fn rlr_ctx_create(s: *mut rlr_store, out: *mut *mut rlr_ctx) -> c_int;
     pub fn rlr_ctx_destroy(c: *mut rlr_ctx) -> c_int;
     pub fn rlr_topm_async(c: *mut rlr_ctx, d_query: *const c_void, w_embed: f32, w_lex: f32, d_lex_rows: *const c_void, d_lex_norm: *const c_void, n_lex: u32, m: u32, d_out: *mut c_void, d_out_n: *mut c_void, stream: *mut c_void) -> c_int;

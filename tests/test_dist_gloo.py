@@ -45,10 +45,17 @@ class OracleBackend:
         from rust_local_rag_b200 import binding as B
         return t.numpy().reshape(-1).view(B.CAND_DTYPE)
 
-    def topm(self, query, w_embed, w_lex, m, out, out_n):
+    def topm(self, query, w_embed, w_lex, m, out, out_n, lex=None):
         q = query.numpy()[:self.dim]
-        r, s, e, l = self.orc.search(self.rows, q, m, w_embed=w_embed, w_lex=w_lex, normalize_query=False,
-                                     full_sort=True)
+        lr = ls = None
+        if lex is not None:
+            # `lex` is dist.stage_lex's triple: local rows + scores ALREADY divided by the global max.  The
+            # oracle divides by the max of what it is given, so a sentinel (row outside the shard, 1.0) makes
+            # that division exact and a no-op.
+            lr = np.concatenate([lex[0].numpy().view(np.uint32)[:lex[2]], np.array([0xFFFFFFFF], np.uint32)])
+            ls = np.concatenate([lex[1].numpy()[:lex[2]], np.array([1.0], F32)])
+        r, s, e, l = self.orc.search(self.rows, q, m, w_embed=w_embed, w_lex=w_lex, lex_rows=lr, lex_scores=ls,
+                                     normalize_query=False, full_sort=True)
         self._view(out)[:] = _records(r + np.uint32(self.row0), s, e, l, m)
         out_n[0] = len(r)
 
@@ -83,7 +90,7 @@ class OracleBackend:
         raise AssertionError("world > 1 must not take the single-GPU path")
 
 
-def _worker(rank, world, port, n, dim, cases, ret):
+def _worker(rank, world, port, n, dim, cases, ret, lex_pairs=None):
     sys.path.insert(0, ROOT)
     import rust_local_rag_b200  # noqa: F401
     from rust_local_rag_b200 import dist as rdist
@@ -103,10 +110,13 @@ def _worker(rank, world, port, n, dim, cases, ret):
             bufs = rdist.Buffers(world, p_cap, pitch, torch.device("cpu"))
             q = torch.zeros(pitch + 64)
             q[:dim] = torch.from_numpy(orc.normalize(orc.synth_rows(1, dim, kind=1, seed=99, n_clusters=16)[0]))
-            res, res_n = rdist.sharded_search(backend, dist.group.WORLD, bufs, q, k, lam, 0.7, 0.3)
+            lex = None
+            if lex_pairs is not None:       # the same global BM25 pairs on every rank; each stages its own slice
+                lex = rdist.stage_lex(plan.row0, plan.row0 + plan.n_local, lex_pairs[0], lex_pairs[1], torch.device("cpu"))
+            res, res_n = rdist.sharded_search(backend, dist.group.WORLD, bufs, q, k, lam, 0.7, 0.3, lex=lex)
             if rank == 0:
                 r, s, e, l = rdist.decode_result(res, int(res_n[0]))
-                out.append((r.tolist(), s.view(np.uint32).tolist(), e.view(np.uint32).tolist()))
+                out.append((r.tolist(), s.view(np.uint32).tolist(), e.view(np.uint32).tolist(), l.view(np.uint32).tolist()))
         if rank == 0:
             ret.put(out)
         dist.barrier()
@@ -128,10 +138,42 @@ def test_sharded_search_matches_unsharded_oracle(world, orc):
     assert all(p.exitcode == 0 for p in procs)
     rows = orc.synth_rows(n, dim, kind=1, n_clusters=16, threads=1)
     q = orc.normalize(orc.synth_rows(1, dim, kind=1, seed=99, n_clusters=16)[0])
-    for (k, lam), (r, s, e) in zip(cases, got):
+    for (k, lam), (r, s, e, _l) in zip(cases, got):
         R, S, E, _ = orc.search_with_diversity(rows, q, k, lam, normalize_query=False, full_sort=True)
         assert r == R.tolist(), (k, lam)
         assert s == S.view(np.uint32).tolist() and e == E.view(np.uint32).tolist()
+
+
+def test_sharded_search_blends_lexical_scores(orc):
+    """The BM25 term of the blend (src/rag_engine.rs:505-532) on the sharded path: every rank stages its slice of
+    the same global (row, score) pairs, normalised by the GLOBAL maximum; rank 0's result must equal the
+    unsharded oracle's, lexical_score included (the sharded path used to drop the term)."""
+    world, n, dim = 2, 2003, 96
+    cases = [(5, 0.3), (100, 0.7), (7, 0.0)]
+    rng = np.random.default_rng(5)
+    lex_rows = rng.choice(n, 60, replace=False).astype(np.uint32)
+    lex_rows[7] = lex_rows[3]                                    # a duplicate row: the later entry wins
+    lex_scores = (rng.random(60) * 9 + 0.1).astype(F32)
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 29500 + os.getpid() % 2000 + 17
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, dim, cases, ret, (lex_rows, lex_scores))) for r in range(world)]
+    [p.start() for p in procs]
+    got = ret.get(timeout=180)
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    rows = orc.synth_rows(n, dim, kind=1, n_clusters=16, threads=1)
+    q = orc.normalize(orc.synth_rows(1, dim, kind=1, seed=99, n_clusters=16)[0])
+    # oracle input without the duplicate (HashMap collect keeps the last value of a key)
+    keep = [i for i in range(60) if i != 3]
+    blended = False
+    for (k, lam), (r, s, e, l) in zip(cases, got):
+        R, S, E, L = orc.search_with_diversity(rows, q, k, lam, lex_rows=lex_rows[keep], lex_scores=lex_scores[keep],
+                                               normalize_query=False, full_sort=True)
+        assert r == R.tolist(), (k, lam)
+        assert s == S.view(np.uint32).tolist() and e == E.view(np.uint32).tolist() and l == L.view(np.uint32).tolist()
+        blended |= bool((L != 0).any())
+    assert blended, "the lexical term never reached a result: the test does not exercise the blend"
 
 
 def test_shard_plan_covers_rows_exactly():
