@@ -520,17 +520,49 @@ def run_b200(a, guard=None):
 
         for i in range(a.warmup):
             step_e2e(i, False)
+        # (1) ONE caller, one query at a time: the latency of a call (and the stage timings for the roofline)
         lat = []
         t_start = time.perf_counter()
         for i in range(a.steps):
             t0 = time.perf_counter()
             step_e2e(a.warmup + i, True)
             lat.append(time.perf_counter() - t0)
+        single_s = time.perf_counter() - t_start
+        # (2) CALLERS host threads calling concurrently, as concurrent searches under the reference's read lock do
+        #     (src/mcp_server.rs:89,377): every call still carries its own H2D query copy and D2H result read.  While
+        #     one query's merge + MMR tail runs, the next query's scan already streams rows.
+        callers = max(1, int(os.environ.get("RLR_BENCH_CALLERS", "2")))
+        errs, lat_multi = [], []
+        start = threading.Barrier(callers + 1)
+
+        def caller(t):
+            try:
+                start.wait()
+                for i in range(t, a.steps, callers):
+                    t0 = time.perf_counter()
+                    step_e2e(a.warmup + i, False)
+                    lat_multi.append(time.perf_counter() - t0)
+            except Exception as e:      # noqa: BLE001
+                errs.append(repr(e))
+
+        for t in range(callers):        # every caller's lane (workspaces, streams, mailbox) exists before the clock starts
+            step_e2e(t, False)
+        th = [threading.Thread(target=caller, args=(t,)) for t in range(callers)]
+        [t.start() for t in th]
+        start.wait()
+        t_start = time.perf_counter()
+        [t.join() for t in th]
         e2e_s = time.perf_counter() - t_start
+        if errs:
+            raise SystemExit(f"concurrent e2e callers failed: {errs[:2]}")
         q_bytes = (((a.dim + 63) & ~63) + 128) * 4
-        e2e = {"value": a.steps / e2e_s, "unit": "queries/s",
-               "h2d_bytes_per_step": q_bytes * world, "d2h_bytes_per_step": max(a.top_k, 1) * 16 + 4 + (4 if world > 1 else 0),
+        e2e = {"value": a.steps / e2e_s, "unit": "queries/s", "callers": callers,
+               "h2d_bytes_per_step": q_bytes * world, "d2h_bytes_per_step": max(a.top_k, 1) * 16 + 16,
                "p50_latency_ms": 1e3 * statistics.median(lat), "p99_latency_ms": 1e3 * sorted(lat)[int(0.99 * (len(lat) - 1))],
+               "single_caller": {"value": a.steps / single_s, "unit": "queries/s", "p50_latency_ms": 1e3 * statistics.median(lat)},
+               "p50_latency_ms_with_concurrent_callers": 1e3 * statistics.median(lat_multi),
+               "note": f"value: {callers} host threads calling concurrently (each call: query H2D, search, result D2H); p50/p99: ONE "
+                       "caller, one query at a time (the latency of a call from idle GPUs)",
                "api": "rlr_search_mmr (C ABI, host buffers)" if world == 1 else
                       f"rlr_cluster_search_mmr (C ABI, host buffers; ONE process drives {world} GPUs, peer-memory mailbox + peer-pointer MMR)"}
         if cluster_info is not None:

@@ -126,11 +126,11 @@ void rlr_api::ctx_free(rlr_ctx *c)
 {
     if (!c) return;
     cudaFree(c->d_query); cudaFree(c->d_lex_rows); cudaFree(c->d_lex_norm); cudaFree(c->d_lists);
-    cudaFree(c->d_counts); cudaFree(c->d_ticket); cudaFree(c->d_pub); cudaFree(c->d_tmp); cudaFree(c->d_pool); cudaFree(c->d_pool_n); cudaFree(c->d_tri);
-    cudaFree(c->d_sel_pos); cudaFree(c->d_sel_n); cudaFree(c->d_result); cudaFree(c->d_rows_in);
+    cudaFree(c->d_counts); cudaFree(c->d_ticket); cudaFree(c->d_pub); cudaFree(c->d_tmp); cudaFree(c->d_pool_blk); cudaFree(c->d_tri);
+    cudaFree(c->d_sel_pos); cudaFree(c->d_result_blk); cudaFree(c->d_rows_in);
     cudaFree(c->d_rel_in); cudaFree(c->d_p_in);
     cudaFreeHost(c->h_query); cudaFreeHost(c->h_lex_rows); cudaFreeHost(c->h_lex_norm);
-    cudaFreeHost(c->h_result); cudaFreeHost(c->h_u32); cudaFreeHost(c->h_rel);
+    cudaFreeHost(c->h_result_blk); cudaFreeHost(c->h_u32); cudaFreeHost(c->h_rel);
     cudaFree(c->batch_mem); cudaFreeHost(c->h_batch_q); cudaFreeHost(c->h_batch_state);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -166,12 +166,16 @@ int rlr_api::ctx_new(rlr_store *s, rlr_ctx **out)
     CTX_TRY(cudaMalloc(&c->d_pub, c->n_lists_cap * sizeof(uint32_t)));
     CTX_TRY(cudaMemset(c->d_pub, 0, c->n_lists_cap * sizeof(uint32_t)));
     CTX_TRY(cudaMalloc(&c->d_tmp, (static_cast<size_t>(c->n_lists_cap) + 3) * RLR_MAX_M * sizeof(rlr_cand)));
-    CTX_TRY(cudaMalloc(&c->d_pool, RLR_MAX_M * sizeof(rlr_cand)));
-    CTX_TRY(cudaMalloc(&c->d_pool_n, sizeof(uint32_t)));
+    // (count, records) pairs live in one block each -- [u32 n | pad to 16 B | records] -- so that ONE D2H
+    // copy brings back a result and its length
+    CTX_TRY(cudaMalloc(&c->d_pool_blk, 16 + RLR_MAX_M * sizeof(rlr_cand)));
+    c->d_pool_n = reinterpret_cast<uint32_t *>(c->d_pool_blk);
+    c->d_pool = reinterpret_cast<rlr_cand *>(c->d_pool_blk + 16);
     CTX_TRY(cudaMalloc(&c->d_tri, static_cast<size_t>(RLR_MAX_M) * (RLR_MAX_M - 1) / 2 * sizeof(float)));
     CTX_TRY(cudaMalloc(&c->d_sel_pos, RLR_MAX_M * sizeof(uint32_t)));
-    CTX_TRY(cudaMalloc(&c->d_sel_n, sizeof(uint32_t)));
-    CTX_TRY(cudaMalloc(&c->d_result, RLR_MAX_M * sizeof(rlr_cand)));
+    CTX_TRY(cudaMalloc(&c->d_result_blk, 16 + RLR_MAX_M * sizeof(rlr_cand)));
+    c->d_sel_n = reinterpret_cast<uint32_t *>(c->d_result_blk);
+    c->d_result = reinterpret_cast<rlr_cand *>(c->d_result_blk + 16);
     CTX_TRY(cudaMalloc(&c->d_rows_in, RLR_MAX_M * sizeof(uint32_t)));
     CTX_TRY(cudaMalloc(&c->d_rel_in, RLR_MAX_M * sizeof(float)));
     CTX_TRY(cudaMalloc(&c->d_p_in, sizeof(uint32_t)));
@@ -179,7 +183,9 @@ int rlr_api::ctx_new(rlr_store *s, rlr_ctx **out)
     memset(c->h_query, 0, rlr::kQueryCap * sizeof(float));
     CTX_TRY(cudaMallocHost(&c->h_lex_rows, kLexCap * sizeof(uint32_t)));
     CTX_TRY(cudaMallocHost(&c->h_lex_norm, kLexCap * sizeof(float)));
-    CTX_TRY(cudaMallocHost(&c->h_result, RLR_MAX_M * sizeof(rlr_cand)));
+    CTX_TRY(cudaMallocHost(&c->h_result_blk, 16 + RLR_MAX_M * sizeof(rlr_cand)));
+    c->h_result_n = reinterpret_cast<uint32_t *>(c->h_result_blk);
+    c->h_result = reinterpret_cast<rlr_cand *>(c->h_result_blk + 16);
     CTX_TRY(cudaMallocHost(&c->h_u32, (RLR_MAX_M + 8) * sizeof(uint32_t)));
     CTX_TRY(cudaMallocHost(&c->h_rel, RLR_MAX_M * sizeof(float)));
 #undef CTX_TRY
@@ -745,10 +751,9 @@ RLR_EXPORT int rlr_search_topm(rlr_store *s, const float *query, uint32_t dim, u
                               c->d_pool, c->d_pool_n, st, timed ? c->ev[1] : nullptr, s->use_half(flags)))
         return rc;
     if (timed) CU_TRY(cudaEventRecord(c->ev[2], st));
-    CU_TRY(cudaMemcpyAsync(c->h_result, c->d_pool, m_eff * sizeof(rlr_cand), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(c->h_u32, c->d_pool_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(c->h_result_blk, c->d_pool_blk, 16 + m_eff * sizeof(rlr_cand), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
-    const uint32_t n = std::min(c->h_u32[0], m_eff);
+    const uint32_t n = std::min(c->h_result_n[0], m_eff);
     unpack(c->h_result, n, out_rows, out_combined, out_emb, out_lex);
     *out_n = n;
     if (timed) { timings_from_events(c, false); g_timings.launches = static_cast<uint32_t>(c->launches - launches0); }
@@ -875,10 +880,9 @@ RLR_EXPORT int rlr_search_mmr(rlr_store *s, const float *query, uint32_t dim, ui
     c->launches += l;
     if (timed) CU_TRY(cudaEventRecord(c->ev[3], st));
     const uint32_t cap = std::min<uint32_t>(p, std::max<uint32_t>(top_k, 1));
-    CU_TRY(cudaMemcpyAsync(c->h_result, c->d_result, cap * sizeof(rlr_cand), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(c->h_u32, c->d_sel_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(c->h_result_blk, c->d_result_blk, 16 + cap * sizeof(rlr_cand), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
-    const uint32_t n = std::min(c->h_u32[0], cap);
+    const uint32_t n = std::min(c->h_result_n[0], cap);
     unpack(c->h_result, n, out_rows, out_score, out_emb, out_lex);
     *out_n = n;
     if (timed) { timings_from_events(c, true); g_timings.launches = static_cast<uint32_t>(c->launches - launches0); }

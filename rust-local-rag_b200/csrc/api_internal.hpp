@@ -40,10 +40,12 @@ struct rlr_ctx {
     uint32_t *d_ticket = nullptr;
     uint32_t *d_pub = nullptr;
     rlr_cand *d_tmp = nullptr;
+    uint8_t *d_pool_blk = nullptr;  // [u32 n | pad to 16 B | RLR_MAX_M records]: d_pool_n / d_pool point into it
     rlr_cand *d_pool = nullptr;
     uint32_t *d_pool_n = nullptr;
     float *d_tri = nullptr;
     uint32_t *d_sel_pos = nullptr;
+    uint8_t *d_result_blk = nullptr; // same layout: d_sel_n / d_result point into it
     uint32_t *d_sel_n = nullptr;
     rlr_cand *d_result = nullptr;
     uint32_t *d_rows_in = nullptr;
@@ -53,6 +55,8 @@ struct rlr_ctx {
     float *h_query = nullptr;
     uint32_t *h_lex_rows = nullptr;
     float *h_lex_norm = nullptr;
+    uint8_t *h_result_blk = nullptr; // pinned mirror of a (count, records) block
+    uint32_t *h_result_n = nullptr;
     rlr_cand *h_result = nullptr;   // RLR_MAX_M records
     uint32_t *h_u32 = nullptr;      // RLR_MAX_M + 8 words
     float *h_rel = nullptr;

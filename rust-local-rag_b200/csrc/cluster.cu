@@ -262,8 +262,7 @@ int cluster_search(rlr_cluster *cl, const float *query, uint32_t dim, uint32_t f
                                      cl->n, pl.m, r0->d_pool, r0->d_pool_n, cc->mb->d_status, st0));
     ++launches;
     if (timed) CU_TRY(cudaEventRecord(r0->ev[2], st0));
-    const rlr_cand *d_res = r0->d_pool;
-    const uint32_t *d_res_n = r0->d_pool_n;
+    const uint8_t *d_res_blk = r0->d_pool_blk;          // [n | records]: one D2H for both
     uint32_t cap = pl.m;
     if (pl.do_mmr) {
         const bool half = s0->use_half(flags);
@@ -279,18 +278,20 @@ int cluster_search(rlr_cluster *cl, const float *query, uint32_t dim, uint32_t f
         uint32_t l = 0;
         CU_TRY(rlr::mmr_launch(a, st0, &l));
         launches += l;
-        d_res = r0->d_result; d_res_n = r0->d_sel_n;
+        d_res_blk = r0->d_result_blk;
         cap = std::min<uint32_t>(pl.m, std::max<uint32_t>(pl.top_k, 1));
     }
     if (timed) CU_TRY(cudaEventRecord(r0->ev[3], st0));
-    CU_TRY(cudaMemcpyAsync(r0->h_result, d_res, cap * sizeof(rlr_cand), cudaMemcpyDeviceToHost, st0));
-    CU_TRY(cudaMemcpyAsync(r0->h_u32, d_res_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, st0));
-    CU_TRY(cudaMemcpyAsync(cc->h_status, cc->mb->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, st0));
+    CU_TRY(cudaMemcpyAsync(r0->h_result_blk, d_res_blk, 16 + cap * sizeof(rlr_cand), cudaMemcpyDeviceToHost, st0));
     CU_TRY(cudaStreamSynchronize(st0));
     cl->launches += launches;
-    if (cc->h_status[0] != 0)
-        return fail(RLR_ERR_CUDA, "a mailbox wait timed out (status %u): a GPU of the cluster did not deliver its list", cc->h_status[0]);
-    const uint32_t n = std::min(r0->h_u32[0], cap);
+    const uint32_t n = std::min(r0->h_result_n[0], cap);
+    if (n == 0) {
+        // every shard owns rows, so an empty result can only mean that a mailbox wait timed out (the kernels then
+        // deliver an EMPTY list and set the sticky status word, scan_topm.cu / merge.cu): read it on this rare path only
+        CU_TRY(cudaMemcpy(cc->h_status, cc->mb->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        return fail(RLR_ERR_CUDA, "the cluster delivered no result (mailbox status %u): a GPU did not deliver its list in time", cc->h_status[0]);
+    }
     unpack(r0->h_result, n, out_rows, out_score, out_emb, out_lex);
     *out_n = n;
     if (timed) {
