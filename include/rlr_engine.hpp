@@ -245,7 +245,9 @@ public:
 
 class RagEngine {
     std::unique_ptr<LexicalIndex> lexical_;          // built by enable_lexical(): validate_index_sync, :1375-1389
-    rlr_store *store_ = nullptr;
+    rlr_store *store_ = nullptr;                     // one GPU ...
+    rlr_cluster *cluster_ = nullptr;                 // ... or the same rows sharded over several GPUs, driven from this process
+    std::vector<int> devices_;                       // > 1 entry: cluster
     std::vector<DocumentChunk> chunks_;              // row -> chunk
     std::unordered_map<std::string, uint32_t> row_of_;
     uint32_t dim_ = 0;
@@ -257,8 +259,13 @@ class RagEngine {
     void upload(const std::vector<float> &rows)
     {
         if (store_) { rlr_store_destroy(store_); store_ = nullptr; }
-        check(rlr_store_create(device_, dim_ ? dim_ : 1, chunks_.size(), rows.empty() ? nullptr : rows.data(), dim_, 0,
-                               normalize_on_upload_ ? RLR_STORE_NORMALIZE_ON_UPLOAD : 0, &store_));
+        if (cluster_) { rlr_cluster_destroy(cluster_); cluster_ = nullptr; }
+        const uint32_t flags = normalize_on_upload_ ? RLR_STORE_NORMALIZE_ON_UPLOAD : 0;
+        if (devices_.size() > 1)
+            check(rlr_cluster_create(devices_.data(), static_cast<uint32_t>(devices_.size()), dim_ ? dim_ : 1, chunks_.size(),
+                                     rows.empty() ? nullptr : rows.data(), dim_, flags, nullptr, &cluster_));
+        else
+            check(rlr_store_create(device_, dim_ ? dim_ : 1, chunks_.size(), rows.empty() ? nullptr : rows.data(), dim_, 0, flags, &store_));
         row_of_.clear();
         for (uint32_t i = 0; i < chunks_.size(); ++i) row_of_[chunks_[i].id] = i;
     }
@@ -274,9 +281,12 @@ class RagEngine {
 
 public:
     explicit RagEngine(int device = 0) : device_(device) {}
+    // the store sharded over `devices` (entry 0 = root), all driven from this process (rlr_cluster_*)
+    explicit RagEngine(std::vector<int> devices) : devices_(std::move(devices)), device_(devices_.empty() ? 0 : devices_[0]) {}
     RagEngine(const RagEngine &) = delete;
     RagEngine &operator=(const RagEngine &) = delete;
-    ~RagEngine() { if (store_) rlr_store_destroy(store_); }
+    ~RagEngine() { if (store_) rlr_store_destroy(store_); if (cluster_) rlr_cluster_destroy(cluster_); }
+    bool sharded() const { return cluster_ != nullptr; }
 
     size_t len() const { return chunks_.size(); }
     bool needs_reindex() const { return needs_reindex_; }
@@ -418,8 +428,9 @@ public:
         for (auto &kv : lexical) { auto it = row_of_.find(kv.first); if (it != row_of_.end()) { lr.push_back(it->second); ls.push_back(kv.second); } }
         std::vector<uint32_t> rows(top_k); std::vector<float> comb(top_k), emb(top_k), lex(top_k);
         uint32_t n = 0;
-        check(rlr_search_topm(store_, query_embedding.data(), static_cast<uint32_t>(query_embedding.size()), 0, &w, lr.data(), ls.data(),
-                              static_cast<uint32_t>(lr.size()), static_cast<uint32_t>(top_k), rows.data(), comb.data(), emb.data(), lex.data(), &n));
+        const uint32_t qd = static_cast<uint32_t>(query_embedding.size()), nl = static_cast<uint32_t>(lr.size()), m = static_cast<uint32_t>(top_k);
+        check(cluster_ ? rlr_cluster_search_topm(cluster_, query_embedding.data(), qd, 0, &w, lr.data(), ls.data(), nl, m, rows.data(), comb.data(), emb.data(), lex.data(), &n)
+                       : rlr_search_topm(store_, query_embedding.data(), qd, 0, &w, lr.data(), ls.data(), nl, m, rows.data(), comb.data(), emb.data(), lex.data(), &n));
         std::vector<SearchResult> out;
         for (uint32_t i = 0; i < n; ++i) out.push_back(result(rows[i], comb[i], emb[i], lex[i]));
         return out;
@@ -437,9 +448,11 @@ public:
         const size_t cap = std::max<size_t>(top_k, 1);
         std::vector<uint32_t> rows(cap); std::vector<float> score(cap), emb(cap), lex(cap);
         uint32_t n = 0;
-        check(rlr_search_mmr(store_, query_embedding.data(), static_cast<uint32_t>(query_embedding.size()), 0, static_cast<uint32_t>(top_k),
-                             diversity_factor, &w, lr.data(), ls.data(), static_cast<uint32_t>(lr.size()), rows.data(), score.data(),
-                             emb.data(), lex.data(), &n));
+        const uint32_t qd = static_cast<uint32_t>(query_embedding.size()), nl = static_cast<uint32_t>(lr.size()), k = static_cast<uint32_t>(top_k);
+        check(cluster_ ? rlr_cluster_search_mmr(cluster_, query_embedding.data(), qd, 0, k, diversity_factor, &w, lr.data(), ls.data(), nl,
+                                                rows.data(), score.data(), emb.data(), lex.data(), &n)
+                       : rlr_search_mmr(store_, query_embedding.data(), qd, 0, k, diversity_factor, &w, lr.data(), ls.data(), nl,
+                                        rows.data(), score.data(), emb.data(), lex.data(), &n));
         std::vector<SearchResult> out;
         for (uint32_t i = 0; i < n; ++i) out.push_back(result(rows[i], score[i], emb[i], lex[i]));
         return out;
@@ -451,8 +464,9 @@ public:
         if (chunks_.empty() || count == 0) return {};
         std::vector<uint32_t> rows(count); std::vector<float> sc(count);
         uint32_t n = 0;
-        check(rlr_embedding_candidates(store_, query_embedding.data(), static_cast<uint32_t>(query_embedding.size()), 0,
-                                       static_cast<uint32_t>(count), rows.data(), sc.data(), &n));
+        const uint32_t qd = static_cast<uint32_t>(query_embedding.size());
+        check(cluster_ ? rlr_cluster_embedding_candidates(cluster_, query_embedding.data(), qd, 0, static_cast<uint32_t>(count), rows.data(), sc.data(), &n)
+                       : rlr_embedding_candidates(store_, query_embedding.data(), qd, 0, static_cast<uint32_t>(count), rows.data(), sc.data(), &n));
         std::vector<RerankerCandidate> out;
         for (uint32_t i = 0; i < n; ++i) {
             const DocumentChunk &c = chunks_.at(rows[i]);
@@ -464,6 +478,7 @@ public:
     // add_document's store update, :347-386: drop the document's chunks, insert the new ones
     void replace_document(const std::string &document_name, std::vector<DocumentChunk> chunks, std::vector<float> embeddings)
     {
+        if (cluster_) throw Error(RLR_ERR_UNSUPPORTED, "a sharded store is a bulk-loaded snapshot: reload it, or keep a live index on one GPU");
         std::vector<uint32_t> old;
         for (uint32_t i = 0; i < chunks_.size(); ++i) if (chunks_[i].document_name == document_name) old.push_back(i);
         if (lexical_) {                              // drop_stale + add_chunk, :1379, :382

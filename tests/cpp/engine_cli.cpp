@@ -14,7 +14,11 @@ int main(int argc, char **argv)
 {
     if (argc < 5) { fprintf(stderr, "usage: engine_cli index.json query.f32 top_k diversity\n"); return 2; }
     try {
-        rlr::RagEngine eng(0);
+        // RLR_CLI_DEVICES="0,1" (or "0,0,0": several shards on one GPU): the store sharded over those GPUs, one process
+        std::vector<int> devs;
+        if (const char *e = getenv("RLR_CLI_DEVICES"))
+            for (const char *p = e; *p;) { devs.push_back(static_cast<int>(strtol(p, const_cast<char **>(&p), 10))); if (*p == ',') ++p; }
+        rlr::RagEngine eng(devs.size() > 1 ? devs : std::vector<int>{devs.empty() ? 0 : devs[0]});
         const std::string idx = argv[1];
         if (idx.size() > 7 && idx.substr(idx.size() - 7) == ".rlrbin") eng.load_sidecar(idx);
         else eng.load_file(idx);

@@ -156,3 +156,44 @@ def test_cpp_host_loads_the_binary_sidecar(tmp_path, orc):
     assert [r["chunk_id"] for r in out["results"]] == [ids[r] for r in ref[0]]
     assert [r["score_bits"] for r in out["results"]] == ref[1].view(np.uint32).tolist()
     assert [r["page"] for r in out["results"]] == [1 + int(r) % 4 for r in ref[0]]
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("devices", ["0,0,0", "0,1"])
+def test_cpp_host_drives_a_sharded_store_from_one_process(tmp_path, orc, devices):
+    """The reference is ONE process (src/main.rs:140-167).  The compiled C++ host mirror with
+    RLR_CLI_DEVICES drives a row-sharded store through rlr_cluster_* -- no torchrun, no NCCL, no Python --
+    and must print the oracle's unsharded answer, BM25 blend included ("0,1": two GPUs, real peer memory)."""
+    if devices == "0,1" and _ngpu() < 2:
+        pytest.skip(f"needs 2 GPUs on the box (has {_ngpu()})")
+    exe = _build_cli(str(tmp_path))
+    n, dim = 2500, 96
+    idx = os.path.join(tmp_path, "chunks_m.json")
+    chunks = _write_index(idx, n, dim, seed=21)
+    ids = list(chunks)
+    rows = orc.normalize_rows(np.array([c["embedding"] for c in chunks.values()], F32))
+    qv = np.random.default_rng(4).standard_normal(dim).astype(F32)
+    qp = os.path.join(tmp_path, "q.f32")
+    qv.tofile(qp)
+    env = dict(os.environ, RLR_CLI_DEVICES=devices)
+    for k, lam in ((8, 0.5), (100, 0.7), (5, 0.0)):
+        out = json.loads(subprocess.run([exe, idx, qp, str(k), str(lam)], capture_output=True, text=True, check=True, env=env).stdout)
+        ref = orc.search_with_diversity(rows, qv, k, lam, full_sort=True)
+        assert out["n"] == n
+        assert [r["chunk_id"] for r in out["results"]] == [ids[r] for r in ref[0]], (devices, k, lam)
+        assert [r["score_bits"] for r in out["results"]] == ref[1].view(np.uint32).tolist()
+        assert [r["emb_bits"] for r in out["results"]] == ref[2].view(np.uint32).tolist()
+        R, S = orc.embedding_candidates(rows, qv, 7)
+        assert [c["chunk_id"] for c in out["candidates"]] == [ids[r] for r in R]
+        assert [c["score_bits"] for c in out["candidates"]] == S.view(np.uint32).tolist()
+    # replace_document on a sharded store is refused loudly (a cluster is a bulk-loaded snapshot)
+    res = subprocess.run([exe, idx, qp, "5", "0.3", "replace", "doc1.pdf", "3", "7"], capture_output=True, text=True, env=env)
+    assert res.returncode == 10 + 6, (res.returncode, res.stderr)       # RLR_ERR_UNSUPPORTED
