@@ -76,7 +76,7 @@ def workload_config(a, world):
         "queries": N_QUERIES,
         "l2": "inputs larger than L2 (store shard >= 3.8 GB vs 126 MB L2)",
         "parallelism": f"rows/{world}",
-        "queries_in_flight": max(1, int(os.environ.get("RLR_BENCH_LANES", "2" if world == 1 else "1"))),
+        "queries_in_flight": max(1, int(os.environ.get("RLR_BENCH_LANES", "2"))),
         "exchange": {"fused": "fused: each GPU's scan kernel stores its top-300 list into rank 0's HBM mailbox (NVLink peer "
                               "stores + release flag, no collective call); rank 0 merges in a waiting kernel and its MMR reads "
                               "pool rows from peer HBM; rank 0 owns fewer rows so that its scan + merge/MMR tail "
@@ -382,7 +382,7 @@ def run_b200(a, guard=None):
     # stream), as a server with concurrent searches does: while the last CTA of one scan merges the per-CTA lists
     # and the MMR kernels run, the next query's scan already streams rows on the other SMs.  Latency (e2e, p50)
     # is measured one query at a time further down.
-    lanes = max(1, int(os.environ.get("RLR_BENCH_LANES", "2" if world == 1 else "1")))
+    lanes = max(1, int(os.environ.get("RLR_BENCH_LANES", "2")))
     for _ in range(lanes - 1):
         backend.add_lane()
     lane_bufs = [bufs] + [rdist.Buffers(world, p_cap, pitch, dev) for _ in range(lanes - 1)]
@@ -792,62 +792,87 @@ def run_extras(a, rank, world, local_rank, dev, group, peaks):
         out["config2_1m_k100"] = rec
         all_ok &= ok
 
-    # ---- config 4: batched queries on the tensor cores ----
+    # ---- config 4: batched queries on the tensor cores, three operand precisions ----
     if world in (1, 8):
-        clk = ClockSampler(local_rank)
         n4 = 1_250_000 * world
         dim4, nq, m4 = 1024, 1024, 100
         plan = rdist.ShardPlan(n4, world, rank)
-        st = engine.DeviceStore.synthetic(plan.n_local, dim4, device=local_rank, row_base=plan.row0, flags=B.RLR_STORE_F16_ONLY, **kw)
+        st = engine.DeviceStore.synthetic(plan.n_local, dim4, device=local_rank, row_base=plan.row0,
+                                          flags=B.RLR_STORE_KEEP_F16 | B.RLR_STORE_KEEP_BF16, **kw)
         qh = queries(nq, dim4)
-        flags = B.RLR_QUERY_PRENORMALIZED | B.RLR_WANT_TIMINGS
-        for _ in range(3):
-            res = rdist.sharded_search_batch(st, group, qh, m4, flags, dev)
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier(group=group)
-        clk.start()
-        wall, dev_ms = [], []
-        for _ in range(10):
+        burst, sustained = peaks.get("bf16_tflops", 1636.3), peaks.get("bf16_tflops_sustained", 1371.9)
+        sub = min(plan.n_local, 100_000)
+        rows_f32 = st.read_rows(np.arange(plan.row0, plan.row0 + sub)) if rank == 0 else None
+
+        def rounded(x, prec):
+            if prec == "f16":
+                return x.astype(np.float16).astype(np.float64)
+            if prec == "bf16":
+                return torch.from_numpy(np.ascontiguousarray(x)).to(torch.bfloat16).double().numpy()
+            return (np.ascontiguousarray(x, np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32).astype(np.float64)
+
+        recs = {}
+        for prec, pflag in (("f16", B.RLR_BATCH_F16), ("bf16", B.RLR_BATCH_BF16), ("tf32", B.RLR_BATCH_TF32)):
+            clk = ClockSampler(local_rank)
+            flags = B.RLR_QUERY_PRENORMALIZED | B.RLR_WANT_TIMINGS | pflag
+            for _ in range(3):
+                res = rdist.sharded_search_batch(st, group, qh, m4, flags, dev)
+            torch.cuda.synchronize(dev)
             if world > 1:
                 dist.barrier(group=group)
-            t0 = time.perf_counter()
-            res = rdist.sharded_search_batch(st, group, qh, m4, flags, dev)
-            wall.append(time.perf_counter() - t0)
-            dev_ms.append(st.last_timings().scan_ms)
-        clk.stop()
-        wall_s = max_over_ranks(statistics.median(wall))
-        gemm_ms = max_over_ranks(statistics.median(dev_ms))
-        flop_gpu = 2.0 * nq * plan.n_local * dim4
-        tf = flop_gpu / (gemm_ms * 1e-3) / 1e12
-        rows_g, scores_g, n_g = res
-        worst, ok4 = 0.0, True
+            clk.start()
+            wall, dev_ms = [], []
+            for _ in range(10):
+                if world > 1:
+                    dist.barrier(group=group)
+                t0 = time.perf_counter()
+                res = rdist.sharded_search_batch(st, group, qh, m4, flags, dev)
+                wall.append(time.perf_counter() - t0)
+                dev_ms.append(st.last_timings().scan_ms)
+            clk.stop()
+            wall_s = max_over_ranks(statistics.median(wall))
+            gemm_ms = max_over_ranks(statistics.median(dev_ms))
+            flop_gpu = 2.0 * nq * plan.n_local * dim4
+            tf = flop_gpu / (gemm_ms * 1e-3) / 1e12
+            rows_g, scores_g, n_g = res
+            if rank == 0:
+                worst, ok4 = 0.0, True
+                ref = rounded(qh[:8], prec) @ rounded(rows_f32, prec).T
+                exact = qh[:8].astype(np.float64) @ rows_f32.astype(np.float64).T
+                worst_exact = 0.0
+                for q in range(8):
+                    inside = (rows_g[q] >= plan.row0) & (rows_g[q] < plan.row0 + sub)
+                    sel, got = rows_g[q][inside], scores_g[q][inside]
+                    if len(sel):
+                        worst = max(worst, float(np.abs(ref[q, sel - plan.row0] - got.astype(np.float64)).max()))
+                        worst_exact = max(worst_exact, float(np.abs(exact[q, sel - plan.row0] - got.astype(np.float64)).max()))
+                    ok4 &= bool((np.diff(scores_g[q][:n_g[q]].astype(np.float64)) <= 0).all()) and int(n_g[q]) == m4
+                ok4 &= worst <= 1e-5
+                # the tensor-rate peak of a precision: the measured dense bf16 figures for the 16-bit kinds; tf32 runs at
+                # half that rate on this part (no tf32 figure in MEASURED_PEAKS.json: half of bf16, stated)
+                pk_b, pk_s = (burst, sustained) if prec != "tf32" else (burst / 2, sustained / 2)
+                recs[prec] = {
+                    "queries_per_s_e2e": nq / wall_s, "ms_per_batch_e2e": wall_s * 1e3, "contraction_ms_per_gpu": gemm_ms,
+                    "flop_per_gpu": flop_gpu, "tflops_per_gpu": tf, "tflops_aggregate": tf * world,
+                    "roofline": {"bound": "tensor", "achieved": tf, "peak": pk_b, "unit": "TFLOP/s", "frac": tf / pk_b,
+                                 "peak_sustained": pk_s, "frac_of_sustained": tf / pk_s,
+                                 "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst) / bf16_tflops_sustained"
+                                                + (" halved: tf32 issues at half the bf16 rate" if prec == "tf32" else "")},
+                    "parity": {"ok": bool(ok4), "max_abs_dev_from_fp64_contraction_of_rounded_inputs": worst, "stated_tolerance": 1e-5,
+                               "max_abs_dev_from_exact_scores": worst_exact},
+                    "steps": 10, "clocks": clk.summary()}
+                all_ok &= ok4
         if rank == 0:
-            sub = min(plan.n_local, 100_000)
-            rows_host = st.read_rows(np.arange(plan.row0, plan.row0 + sub)).astype(np.float64)   # binary16-rounded rows, widened
-            ref = qh[:8].astype(np.float16).astype(np.float64) @ rows_host.T
-            for q in range(8):
-                inside = (rows_g[q] >= plan.row0) & (rows_g[q] < plan.row0 + sub)
-                sel, got = rows_g[q][inside], scores_g[q][inside]
-                if len(sel):
-                    worst = max(worst, float(np.abs(ref[q, sel - plan.row0] - got.astype(np.float64)).max()))
-                ok4 &= bool((np.diff(scores_g[q][:n_g[q]].astype(np.float64)) <= 0).all()) and int(n_g[q]) == m4
-            ok4 &= worst <= 1e-5
-            burst, sustained = peaks.get("bf16_tflops", 1636.3), peaks.get("bf16_tflops_sustained", 1371.9)
             out["config4_batched"] = {
-                "workload": f"batched {nq} queries x {n4}x{dim4} chunks (binary16 operands, f32 accumulate in TMEM), top-{m4} per query, "
-                            f"rows sharded over {world} GPU(s)" + (" (the per-GPU shape of BASELINE configs[3])" if world == 1 else " (BASELINE configs[3])"),
-                "queries_per_s_e2e": nq / wall_s, "ms_per_batch_e2e": wall_s * 1e3, "contraction_ms_per_gpu": gemm_ms,
-                "flop_per_gpu": flop_gpu, "tflops_per_gpu": tf, "tflops_aggregate": tf * world,
-                "roofline": {"bound": "tensor", "achieved": tf, "peak": burst, "unit": "TFLOP/s", "frac": tf / burst,
-                             "peak_sustained": sustained, "frac_of_sustained": tf / sustained,
-                             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst) / bf16_tflops_sustained"},
-                "parity": {"ok": bool(ok4), "max_abs_dev_from_fp64_contraction": worst, "stated_tolerance": 1e-5,
-                           "what": "8 queries: every returned row inside a 100k-row slice against the fp64 contraction of the same "
-                                   "binary16-rounded inputs; lists sorted and full"},
+                "workload": f"batched {nq} queries x {n4}x{dim4} chunks, top-{m4} per query, tcgen05 cta_group::2 contraction with f32 "
+                            f"accumulation in TMEM, rows sharded over {world} GPU(s)"
+                            + (" (the per-GPU shape of BASELINE configs[3])" if world == 1 else " (BASELINE configs[3])"),
+                "operands": {"f16": "binary16 copy of the store (kind::f16)", "bf16": "bfloat16 copy (kind::f16)",
+                             "tf32": "the f32 store itself, no copy (kind::tf32)"},
+                "parity_what": "8 queries: every returned row inside a 100k-row slice against the fp64 contraction of the inputs rounded "
+                               "as that precision rounds them; lists sorted and full",
                 "exchange": "one NCCL all-gather of nq x m u64 keys per rank + per-query device merge" if world > 1 else "none",
-                "steps": 10, "clocks": clk.summary()}
-            all_ok &= ok4
+                **recs}
         st.close()
         torch.cuda.empty_cache()
 

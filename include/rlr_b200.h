@@ -109,6 +109,8 @@ typedef struct rlr_timings {
                                             * device (same sequential arithmetic, same bits): bulk loads need not
                                             * normalise 10M rows on one host core (apply_loaded_state, :1678-1680) */
 #define RLR_STORE_F16_ONLY      0x4u  /* keep only the binary16 copy (half the HBM, config 5) */
+#define RLR_STORE_KEEP_BF16     0x10u /* keep the f32 rows AND a bfloat16 copy (operand of rlr_search_batch with
+                                         RLR_BATCH_BF16; the single-query paths never read it)  */
 
 /* search flags */
 #define RLR_QUERY_PRENORMALIZED 0x1u  /* skip the normalize(&mut q) of :494                */
@@ -253,11 +255,11 @@ int rlr_embedding_candidates(rlr_store *s, const float *query, uint32_t dim, uin
  * rlr_search_batch -- many queries at once (not in the reference, which answers one query
  * per call; BASELINE config 4 / north_star kernel (3)).  For each of n_queries embeddings:
  * the top m rows by embedding score (the ordering of get_embedding_candidates, :445), computed
- * as ONE dense contraction on the tensor cores: tcgen05.mma over the binary16 copy of the
- * store (needs RLR_STORE_KEEP_F16 or RLR_STORE_F16_ONLY), f32 accumulation in TMEM, a
- * per-query threshold filter fused into the epilogue.
+ * as ONE dense contraction on the tensor cores: tcgen05.mma over the binary16 / bfloat16 copy of
+ * the store or (tf32) over the f32 rows themselves, f32 accumulation in TMEM, a per-query
+ * threshold filter fused into the epilogue.
  *   queries     n_queries x dim f32, row stride dim; normalised here (:494) unless
- *               RLR_QUERY_PRENORMALIZED; rounded to binary16 for the contraction
+ *               RLR_QUERY_PRENORMALIZED; converted to the operand precision for the contraction
  *   m           1..RLR_MAX_M
  *   flags       RLR_BATCH_EXACT_RESCORE: re-score the m shortlisted rows of every query with the
  *               reference's sequential f32 arithmetic (on the f32 rows when the store has them)
@@ -267,6 +269,18 @@ int rlr_embedding_candidates(rlr_store *s, const float *query, uint32_t dim, uin
  * Outputs: out_rows / out_scores are n_queries x m (row stride m), out_n[q] = min(m, n_rows).
  */
 #define RLR_BATCH_EXACT_RESCORE 0x8u
+/* operand precision of the contraction (at most one; default: binary16 when the store keeps that copy,
+ * else tf32).  All accumulate in f32 in TMEM.
+ *   RLR_BATCH_F16   tcgen05.mma kind::f16 over the binary16 copy: 10-bit mantissas, |score - exact| <= ~2e-4
+ *   RLR_BATCH_BF16  kind::f16 with bfloat16 operands over the RLR_STORE_KEEP_BF16 copy: 7-bit mantissas,
+ *                   same speed as binary16, <= ~2e-3 absolute on unit vectors
+ *   RLR_BATCH_TF32  kind::tf32 straight over the f32 rows (NO second copy of the store): the tensor core reads
+ *                   the upper 19 bits of every f32 (10-bit mantissas, truncated), <= ~1e-3 absolute on unit
+ *                   vectors; half the tensor rate and twice the operand bytes of the 16-bit kinds
+ * Tolerances are asserted in tests/test_gpu_batch.py; RLR_BATCH_EXACT_RESCORE restores exact bits in every mode. */
+#define RLR_BATCH_F16           0x10u
+#define RLR_BATCH_BF16          0x20u
+#define RLR_BATCH_TF32          0x40u
 int rlr_search_batch(rlr_store *s, const float *queries, uint32_t n_queries, uint32_t dim,
                      uint32_t flags, uint32_t m,
                      uint32_t *out_rows, float *out_scores, uint32_t *out_n);

@@ -26,6 +26,10 @@ RLR_QUERY_PRENORMALIZED = 0x1
 RLR_WANT_TIMINGS = 0x2
 RLR_SEARCH_F16 = 0x4
 RLR_BATCH_EXACT_RESCORE = 0x8
+RLR_BATCH_F16 = 0x10
+RLR_BATCH_BF16 = 0x20
+RLR_BATCH_TF32 = 0x40
+RLR_STORE_KEEP_BF16 = 0x10
 RLR_IPC_HANDLE_BYTES = 64
 RLR_SYNTH_IID = 0
 RLR_SYNTH_CLUSTERED = 1

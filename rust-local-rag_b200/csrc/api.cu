@@ -405,16 +405,18 @@ RLR_EXPORT int rlr_resolve_weights(const rlr_query_weights *o, rlr_resolved_weig
 // ---------------------------------------------------------------------------------
 namespace {
 
-int make_tmap(CUtensorMap *map, void *base, bool half, uint32_t pitch_elems, uint64_t n_rows)
+// dtype: 0 f32, 1 binary16, 2 bfloat16
+int make_tmap(CUtensorMap *map, void *base, int dtype, uint32_t pitch_elems, uint64_t n_rows)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return fail(RLR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
-    const uint32_t esz = half ? 2 : 4;
+    const uint32_t esz = dtype ? 2 : 4;
     const cuuint64_t gdim[2] = {pitch_elems, n_rows};
     const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(pitch_elems) * esz};
     const cuuint32_t box[2] = {128u / esz, rlr::kScanRows};   // 128-byte box rows: the SWIZZLE_128B span
     const cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride,
+    const CUtensorMapDataType dt = dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    CUresult r = enc(map, dt, 2, base, gdim, gstride,
                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(RLR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
@@ -433,6 +435,8 @@ RLR_EXPORT int rlr_store_create(int device, uint32_t dim, uint64_t n_rows, const
     if (row_base + n_rows >= (1ull << 32)) return fail(RLR_ERR_UNSUPPORTED, "global rows must fit 32 bits");
     if ((flags & RLR_STORE_KEEP_F16) && (flags & RLR_STORE_F16_ONLY))
         return fail(RLR_ERR_INVALID_ARG, "RLR_STORE_KEEP_F16 and RLR_STORE_F16_ONLY are exclusive");
+    if ((flags & RLR_STORE_KEEP_BF16) && (flags & RLR_STORE_F16_ONLY))
+        return fail(RLR_ERR_INVALID_ARG, "RLR_STORE_KEEP_BF16 needs the f32 rows (exclusive with RLR_STORE_F16_ONLY)");
     if (host_pitch == 0) host_pitch = dim;
     if (host_pitch < dim) return fail(RLR_ERR_INVALID_ARG, "host_pitch %llu < dim %u", (unsigned long long)host_pitch, dim);
     int rc = ensure_device(device);
@@ -454,6 +458,7 @@ RLR_EXPORT int rlr_store_create(int device, uint32_t dim, uint64_t n_rows, const
     }
     memset(&s->tmap, 0, sizeof s->tmap);
     memset(&s->tmap16, 0, sizeof s->tmap16);
+    memset(&s->tmap_bf16, 0, sizeof s->tmap_bf16);
     const bool want32 = !(flags & RLR_STORE_F16_ONLY);
     const bool want16 = flags & (RLR_STORE_F16_ONLY | RLR_STORE_KEEP_F16);
     if (n_rows) {
@@ -461,16 +466,18 @@ RLR_EXPORT int rlr_store_create(int device, uint32_t dim, uint64_t n_rows, const
         size_t bytes = 0;
         if (want32) { bytes = static_cast<size_t>(n_rows) * s->pitch * sizeof(float); e = cudaMalloc(&s->d_rows, bytes); }
         if (e == cudaSuccess && want16) { bytes = static_cast<size_t>(n_rows) * s->pitch16 * 2; e = cudaMalloc(&s->d_rows16, bytes); }
+        if (e == cudaSuccess && (flags & RLR_STORE_KEEP_BF16)) { bytes = static_cast<size_t>(n_rows) * s->pitch16 * 2; e = cudaMalloc(&s->d_rows_bf16, bytes); }
         if (e != cudaSuccess) {
             cudaGetLastError();
-            cudaFree(s->d_rows); cudaFree(s->d_rows16);
+            cudaFree(s->d_rows); cudaFree(s->d_rows16); cudaFree(s->d_rows_bf16);
             delete s;
             return fail(RLR_ERR_OOM, "cudaMalloc of %zu bytes for the store failed: %s", bytes, cudaGetErrorString(e));
         }
         rc = RLR_OK;
-        if (want32) rc = make_tmap(&s->tmap, s->d_rows, false, s->pitch, n_rows);
-        if (rc == RLR_OK && want16) rc = make_tmap(&s->tmap16, s->d_rows16, true, s->pitch16, n_rows);
-        if (rc != RLR_OK) { cudaFree(s->d_rows); cudaFree(s->d_rows16); delete s; return rc; }
+        if (want32) rc = make_tmap(&s->tmap, s->d_rows, 0, s->pitch, n_rows);
+        if (rc == RLR_OK && want16) rc = make_tmap(&s->tmap16, s->d_rows16, 1, s->pitch16, n_rows);
+        if (rc == RLR_OK && s->d_rows_bf16) rc = make_tmap(&s->tmap_bf16, s->d_rows_bf16, 2, s->pitch16, n_rows);
+        if (rc != RLR_OK) { cudaFree(s->d_rows); cudaFree(s->d_rows16); cudaFree(s->d_rows_bf16); delete s; return rc; }
     }
     *out = s;
     if (rows && n_rows) {
@@ -487,6 +494,7 @@ RLR_EXPORT int rlr_store_destroy(rlr_store *s)
     for (rlr_ctx *c : s->free_ctx) ctx_free(c);
     cudaFree(s->d_rows);
     cudaFree(s->d_rows16);
+    cudaFree(s->d_rows_bf16);
     cudaGetLastError();
     delete s;
     return RLR_OK;
@@ -498,7 +506,8 @@ RLR_EXPORT int rlr_store_info_get(const rlr_store *s, rlr_store_info *out)
     if (!out) return fail(RLR_ERR_INVALID_ARG, "out is NULL");
     out->n_rows = s->n_rows; out->row_base = s->row_base; out->dim = s->dim; out->pitch = s->pitch;
     out->device = s->device; out->flags = s->flags;
-    out->bytes_device = (s->d_rows ? s->n_rows * s->pitch * sizeof(float) : 0) + (s->d_rows16 ? s->n_rows * s->pitch16 * 2 : 0);
+    out->bytes_device = (s->d_rows ? s->n_rows * s->pitch * sizeof(float) : 0) + (s->d_rows16 ? s->n_rows * s->pitch16 * 2 : 0) +
+                        (s->d_rows_bf16 ? s->n_rows * s->pitch16 * 2 : 0);
     return RLR_OK;
 }
 
@@ -540,6 +549,8 @@ RLR_EXPORT int rlr_store_upload(rlr_store *s, uint64_t row0, uint64_t n, const f
                                     s->dim, cnt, 0);
             if (e == cudaSuccess) e = cudaDeviceSynchronize();
         }
+        if (e == cudaSuccess && rc == RLR_OK && s->d_rows_bf16)
+            e = rlr::to_bf16_launch(dst32, s->pitch, static_cast<uint8_t *>(s->d_rows_bf16) + (row0 + r) * s->pitch16 * 2, s->pitch16, s->dim, cnt, 0);
         if (e != cudaSuccess) {
             cudaGetLastError();
             rc = fail(e == cudaErrorMemoryAllocation ? RLR_ERR_OOM : RLR_ERR_CUDA, "store upload failed: %s", cudaGetErrorString(e));
@@ -586,8 +597,9 @@ namespace {
 int store_remap(rlr_store *s)
 {
     if (s->n_rows == 0) return RLR_OK;
-    if (s->d_rows) if (int rc = make_tmap(&s->tmap, s->d_rows, false, s->pitch, s->n_rows)) return rc;
-    if (s->d_rows16) if (int rc = make_tmap(&s->tmap16, s->d_rows16, true, s->pitch16, s->n_rows)) return rc;
+    if (s->d_rows) if (int rc = make_tmap(&s->tmap, s->d_rows, 0, s->pitch, s->n_rows)) return rc;
+    if (s->d_rows16) if (int rc = make_tmap(&s->tmap16, s->d_rows16, 1, s->pitch16, s->n_rows)) return rc;
+    if (s->d_rows_bf16) if (int rc = make_tmap(&s->tmap_bf16, s->d_rows_bf16, 2, s->pitch16, s->n_rows)) return rc;
     return RLR_OK;
 }
 
@@ -606,12 +618,18 @@ int store_grow(rlr_store *s, uint64_t want)
         cudaError_t e = cudaMalloc(&n16, cap * s->pitch16 * 2);
         if (e != cudaSuccess) { cudaGetLastError(); cudaFree(n32); return fail(RLR_ERR_OOM, "cudaMalloc failed growing the store: %s", cudaGetErrorString(e)); }
     }
+    void *nbf = nullptr;
+    if (s->flags & RLR_STORE_KEEP_BF16) {
+        cudaError_t e = cudaMalloc(&nbf, cap * s->pitch16 * 2);
+        if (e != cudaSuccess) { cudaGetLastError(); cudaFree(n32); cudaFree(n16); return fail(RLR_ERR_OOM, "cudaMalloc failed growing the store: %s", cudaGetErrorString(e)); }
+    }
     if (s->n_rows) {
         if (want32) CU_TRY(cudaMemcpy(n32, s->d_rows, s->n_rows * s->pitch * sizeof(float), cudaMemcpyDeviceToDevice));
         if (want16) CU_TRY(cudaMemcpy(n16, s->d_rows16, s->n_rows * s->pitch16 * 2, cudaMemcpyDeviceToDevice));
+        if (nbf && s->d_rows_bf16) CU_TRY(cudaMemcpy(nbf, s->d_rows_bf16, s->n_rows * s->pitch16 * 2, cudaMemcpyDeviceToDevice));
     }
-    cudaFree(s->d_rows); cudaFree(s->d_rows16);
-    s->d_rows = n32; s->d_rows16 = n16; s->capacity = cap;
+    cudaFree(s->d_rows); cudaFree(s->d_rows16); cudaFree(s->d_rows_bf16);
+    s->d_rows = n32; s->d_rows16 = n16; s->d_rows_bf16 = nbf; s->capacity = cap;
     return RLR_OK;
 }
 
@@ -678,6 +696,7 @@ RLR_EXPORT int rlr_store_remove_rows(rlr_store *s, const uint32_t *rows, uint64_
         if (e == cudaSuccess) e = cudaMemcpy(d_to, to.data(), to.size() * 4, cudaMemcpyHostToDevice);
         if (e == cudaSuccess && s->d_rows) e = rlr::move_rows_launch(s->d_rows, s->pitch * 4, d_from, d_to, static_cast<uint32_t>(from.size()), 0);
         if (e == cudaSuccess && s->d_rows16) e = rlr::move_rows_launch(s->d_rows16, s->pitch16 * 2, d_from, d_to, static_cast<uint32_t>(from.size()), 0);
+        if (e == cudaSuccess && s->d_rows_bf16) e = rlr::move_rows_launch(s->d_rows_bf16, s->pitch16 * 2, d_from, d_to, static_cast<uint32_t>(from.size()), 0);
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
         cudaFree(d_from); cudaFree(d_to);
         CU_TRY(e);
@@ -700,6 +719,7 @@ RLR_EXPORT int rlr_store_fill_synthetic(rlr_store *s, int kind, uint64_t seed, u
     CU_TRY(cudaSetDevice(s->device));
     CU_TRY(rlr::synth_launch(s->d_rows, s->pitch, s->d_rows16, s->pitch16, s->dim, s->row_base,
                              static_cast<uint32_t>(s->n_rows), kind, seed, centroid_seed, n_clusters, sigma, 0));
+    if (s->d_rows_bf16) CU_TRY(rlr::to_bf16_launch(s->d_rows, s->pitch, s->d_rows_bf16, s->pitch16, s->dim, s->n_rows, 0));
     CU_TRY(cudaDeviceSynchronize());
     return RLR_OK;
 }
@@ -895,6 +915,9 @@ RLR_EXPORT int rlr_search_mmr(rlr_store *s, const float *query, uint32_t dim, ui
 namespace {
 
 struct BatchBufs {                 // views into the ctx's batch workspace
+    int prec = 0;                  // rlr::kPrecF16 / kPrecBF16 / kPrecTF32: what the operand tiles hold
+    const CUtensorMap *tmapA = nullptr;
+    uint32_t pitch_op = 0;         // operand elements per row (store pitch of that precision)
     float *d_q32 = nullptr;
     void *d_q16 = nullptr;
     float *d_tau = nullptr;
@@ -920,8 +943,8 @@ int batch_phase(rlr_store *s, const CUtensorMap *tmapQ, BatchBufs &b, uint32_t n
     // the kernel writes row r to slot r of every list (no filter, no atomics) and the counts are set here
     const bool dense = two_cta && t0 == 0 && (t1 - t0) * kBatchRTile <= kBatchCap && (t1 % 2 == 0 || t1 == n_tiles_all);
     if (dense) {
-        CU_TRY(rlr::batch_gemm2_launch(&s->tmap16, tmapQ + 1, s->sm_count, static_cast<uint32_t>(s->n_rows),
-                                       static_cast<uint32_t>(s->row_base), t0, t1, nq_pad, s->pitch16, b.d_tau, b.d_app,
+        CU_TRY(rlr::batch_gemm2_launch(b.tmapA, tmapQ + 1, s->sm_count, static_cast<uint32_t>(s->n_rows),
+                                       static_cast<uint32_t>(s->row_base), t0, t1, nq_pad, b.pitch_op, b.prec, b.d_tau, b.d_app,
                                        b.d_app_cnt, kBatchCap, b.d_overflow, 1, st));
         const uint32_t rows_in_phase = static_cast<uint32_t>(std::min<uint64_t>(s->n_rows, static_cast<uint64_t>(t1) * kBatchRTile));
         CU_TRY(rlr::batch_set_cnt_launch(b.d_app_cnt, nq, rows_in_phase, st));
@@ -931,12 +954,12 @@ int batch_phase(rlr_store *s, const CUtensorMap *tmapQ, BatchBufs &b, uint32_t n
         return RLR_OK;
     }
     if (two_cta && (t0 % 2 == 0) && (t1 % 2 == 0 || t1 == n_tiles_all) && (t1 - t0) >= 2)
-        CU_TRY(rlr::batch_gemm2_launch(&s->tmap16, tmapQ + 1, s->sm_count, static_cast<uint32_t>(s->n_rows),
-                                       static_cast<uint32_t>(s->row_base), t0, t1, nq_pad, s->pitch16, b.d_tau, b.d_app,
+        CU_TRY(rlr::batch_gemm2_launch(b.tmapA, tmapQ + 1, s->sm_count, static_cast<uint32_t>(s->n_rows),
+                                       static_cast<uint32_t>(s->row_base), t0, t1, nq_pad, b.pitch_op, b.prec, b.d_tau, b.d_app,
                                        b.d_app_cnt, kBatchCap, b.d_overflow, 0, st));
     else
-    CU_TRY(rlr::batch_gemm_launch(&s->tmap16, tmapQ, s->sm_count, static_cast<uint32_t>(s->n_rows),
-                                  static_cast<uint32_t>(s->row_base), t0, t1, nq_pad, s->pitch16, b.d_tau, b.d_app,
+    CU_TRY(rlr::batch_gemm_launch(b.tmapA, tmapQ, s->sm_count, static_cast<uint32_t>(s->n_rows),
+                                  static_cast<uint32_t>(s->row_base), t0, t1, nq_pad, b.pitch_op, b.prec, b.d_tau, b.d_app,
                                   b.d_app_cnt, kBatchCap, b.d_overflow, st));
     ++*launches;
     if (checked) {      // safe mode: look at the overflow flag after every phase (a host round trip each)
@@ -982,8 +1005,19 @@ int search_batch_core(rlr_store *s, const float *queries, uint32_t n_queries, ui
         }
         return RLR_OK;
     }
-    if (s->d_rows16 == nullptr)
-        return fail(RLR_ERR_INVALID_ARG, "rlr_search_batch needs the binary16 store copy (RLR_STORE_KEEP_F16 / RLR_STORE_F16_ONLY)");
+    // operand precision: what the caller asked for, else binary16 when the store keeps that copy, else tf32 straight
+    // over the f32 rows (no second copy of the store needed)
+    int prec;
+    if (flags & RLR_BATCH_TF32) prec = rlr::kPrecTF32;
+    else if (flags & RLR_BATCH_BF16) prec = rlr::kPrecBF16;
+    else if (flags & RLR_BATCH_F16) prec = rlr::kPrecF16;
+    else prec = s->d_rows16 ? rlr::kPrecF16 : rlr::kPrecTF32;
+    if (prec == rlr::kPrecF16 && s->d_rows16 == nullptr)
+        return fail(RLR_ERR_INVALID_ARG, "RLR_BATCH_F16 needs the binary16 store copy (RLR_STORE_KEEP_F16 / RLR_STORE_F16_ONLY)");
+    if (prec == rlr::kPrecBF16 && s->d_rows_bf16 == nullptr)
+        return fail(RLR_ERR_INVALID_ARG, "RLR_BATCH_BF16 needs the bfloat16 store copy (RLR_STORE_KEEP_BF16)");
+    if (prec == rlr::kPrecTF32 && s->d_rows == nullptr)
+        return fail(RLR_ERR_INVALID_ARG, "RLR_BATCH_TF32 needs the f32 rows (the store is RLR_STORE_F16_ONLY)");
     {
         // per device, remembered only when it succeeded: a failed configure is retried (and reported) by the next call
         static std::mutex mu;
@@ -1006,10 +1040,14 @@ int search_batch_core(rlr_store *s, const float *queries, uint32_t n_queries, ui
     // cost ~3 ms of single-threaded host work before the first kernel could start).
     const size_t q_floats = static_cast<size_t>(nq) * dim;
     BatchBufs b;
+    b.prec = prec;
+    b.tmapA = prec == rlr::kPrecTF32 ? &s->tmap : prec == rlr::kPrecBF16 ? &s->tmap_bf16 : &s->tmap16;
+    b.pitch_op = prec == rlr::kPrecTF32 ? s->pitch : s->pitch16;
+    const uint32_t op_esz = prec == rlr::kPrecTF32 ? 4u : 2u;
     {
         // one workspace allocation per ctx, grown on demand (a batch call is a few ms: no per-call cudaMalloc)
         auto up = [](size_t x) { return (x + 255) & ~static_cast<size_t>(255); };
-        const size_t sz_q32 = up(q_floats * sizeof(float)), sz_q16 = up(static_cast<size_t>(nq_pad) * s->pitch16 * 2);
+        const size_t sz_q32 = up(q_floats * sizeof(float)), sz_q16 = up(static_cast<size_t>(nq_pad) * b.pitch_op * op_esz);
         const size_t sz_tau = up(nq_pad * sizeof(float)), sz_state = up(static_cast<size_t>(nq_pad) * m_eff * 8);
         const size_t sz_app = up(static_cast<size_t>(nq_pad) * kBatchCap * 8), sz_cnt = up(nq_pad * sizeof(uint32_t));
         const size_t sz_acnt = up(static_cast<size_t>(nq_pad) * 32 * sizeof(uint32_t));   // one 128-byte line per counter
@@ -1045,12 +1083,14 @@ int search_batch_core(rlr_store *s, const float *queries, uint32_t n_queries, ui
     {
         PFN_encodeTiled enc = get_encode();
         if (!enc) return fail(RLR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
-        const cuuint64_t gdim[2] = {s->pitch16, nq_pad};
-        const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(s->pitch16) * 2};
+        const cuuint64_t gdim[2] = {b.pitch_op, nq_pad};
+        const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(b.pitch_op) * op_esz};
         const cuuint32_t estr[2] = {1, 1};
+        const CUtensorMapDataType qdt = prec == rlr::kPrecTF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                      : prec == rlr::kPrecBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
         for (int v = 0; v < 2; ++v) {
-            const cuuint32_t box[2] = {64, v == 0 ? kBatchQTile : kBatchQTile / 2};
-            CUresult r = enc(&tmapQ[v], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b.d_q16, gdim, gstride, box, estr,
+            const cuuint32_t box[2] = {128u / op_esz, v == 0 ? kBatchQTile : kBatchQTile / 2};
+            CUresult r = enc(&tmapQ[v], qdt, 2, b.d_q16, gdim, gstride, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return fail(RLR_ERR_CUDA, "cuTensorMapEncodeTiled (queries) failed with CUresult %d", static_cast<int>(r));
@@ -1062,7 +1102,7 @@ int search_batch_core(rlr_store *s, const float *queries, uint32_t n_queries, ui
     if (timed) CU_TRY(cudaEventRecord(c->ev[0], st));
     CU_TRY(rlr::batch_init_launch(b.d_tau, b.d_state_cnt, b.d_app_cnt, nq, nq_pad, b.d_overflow, st));
     if (!(flags & RLR_QUERY_PRENORMALIZED)) { CU_TRY(rlr::normalize_rows_launch(b.d_q32, dim, dim, nq, st)); ++launches; }
-    CU_TRY(rlr::batch_queries_to_half_launch(b.d_q32, dim, b.d_q16, s->pitch16, nq, nq_pad, b.d_overflow + 1, st));
+    CU_TRY(rlr::batch_queries_to_operand_launch(b.d_q32, dim, b.d_q16, b.pitch_op, prec, nq, nq_pad, b.d_overflow + 1, st));
     launches += 2;
     bool nonfinite = false;
     // Geometrically growing phases.  tau is frozen during a phase, so a phase over rows [a, g*a)

@@ -21,7 +21,8 @@ struct rlr_store {
     float *d_rows = nullptr;        // f32 matrix (absent for RLR_STORE_F16_ONLY)
     void *d_rows16 = nullptr;       // binary16 copy (RLR_STORE_KEEP_F16 / RLR_STORE_F16_ONLY)
     uint32_t pitch16 = 0;           // elements per binary16 row (dim rounded up to 64)
-    CUtensorMap tmap, tmap16;
+    void *d_rows_bf16 = nullptr;    // bfloat16 copy (RLR_STORE_KEEP_BF16): an operand of the batched contraction only
+    CUtensorMap tmap, tmap16, tmap_bf16;
     int sm_count = 0, smem_optin = 0;
     bool use_half(uint32_t flags) const { return d_rows == nullptr || ((flags & RLR_SEARCH_F16) && d_rows16 != nullptr); }
     std::mutex mu;

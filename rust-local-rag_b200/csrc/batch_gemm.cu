@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -63,6 +64,17 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uin
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // K-major operand tile in shared memory, rows of exactly 128 bytes, SWIZZLE_128B (what a TMA box
 // {64 halves, rows} with CU_TENSOR_MAP_SWIZZLE_128B produces): 8-row atoms of 1024 bytes.
 //   bits [0,14)  start address >> 4          bits [16,30) leading byte offset >> 4 (unused: 0)
@@ -77,10 +89,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
     d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
-// instruction descriptor, kind::f16: D = f32, A = B = f16, both K-major, M = 128, N = 256
-//   bits [4,6) c_format = 1 (F32); [7,10) a_format = 0 (F16); [10,13) b_format = 0 (F16);
-//   bit 15 / 16 a/b major = 0 (K); bits [17,23) N >> 3; bits [24,29) M >> 4
+// instruction descriptor: D = f32, A and B of one input type, both K-major, M = 128 (256 for the CTA pair), N = 256
+//   bits [4,6) c_format = 1 (F32); [7,10) a_format, [10,13) b_format: kind::f16 -> 0 (F16) / 1 (BF16),
+//   kind::tf32 -> 2 (TF32); bit 15 / 16 a/b major = 0 (K); bits [17,23) N >> 3; bits [24,29) M >> 4
 constexpr uint32_t kIdesc = (1u << 4) | (static_cast<uint32_t>(kBN >> 3) << 17) | (static_cast<uint32_t>(kBM >> 4) << 24);
+// operand precision of the contraction (host + kernels): what the 128-byte k-chunks hold
+//   0: binary16 (64 per chunk, kind::f16)   1: bfloat16 (64 per chunk, kind::f16)   2: tf32 = the f32 store itself
+//   (32 per chunk, kind::tf32: the tensor core reads the upper 19 bits of every f32, K = 8 per instruction)
+__host__ __device__ constexpr uint32_t idesc_fmt(int prec) { return (static_cast<uint32_t>(prec) << 7) | (static_cast<uint32_t>(prec) << 10); }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
 {
@@ -153,10 +169,11 @@ __device__ __forceinline__ void epilogue_filter(const uint32_t (&v)[32], const f
     }
 }
 
+template <bool kTf32>
 __global__ void __launch_bounds__(kBatchThreads, 1)
 batch_gemm_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapQ,
                        uint32_t n_rows, uint32_t row_base, uint32_t tile0, uint32_t tile1, uint32_t nq_tiles,
-                       uint32_t n_k, const float *__restrict__ tau, unsigned long long *__restrict__ app_keys,
+                       uint32_t n_k, uint32_t idesc, const float *__restrict__ tau, unsigned long long *__restrict__ app_keys,
                        uint32_t *__restrict__ app_cnt, uint32_t cap, uint32_t *__restrict__ overflow,
                        unsigned long long *dbg /* dev-only cycle counters, may be null */)
 {
@@ -206,8 +223,8 @@ batch_gemm_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_c
                         mbar_wait(empty_bar + stage * 8, phase ^ 1);
                         mbar_arrive_expect_tx(full_bar + stage * 8, kStageB);
                         const uint32_t a_dst = stages_addr + stage * kStageB;
-                        tma_load_2d_nohint(a_dst, &tmapA, static_cast<int32_t>(kc * kBK), static_cast<int32_t>(rt * kBM), full_bar + stage * 8);
-                        tma_load_2d_nohint(a_dst + kABytes, &tmapQ, static_cast<int32_t>(kc * kBK), static_cast<int32_t>(qt * kBN), full_bar + stage * 8);
+                        tma_load_2d_nohint(a_dst, &tmapA, static_cast<int32_t>(kc * (kTf32 ? 32 : kBK)), static_cast<int32_t>(rt * kBM), full_bar + stage * 8);
+                        tma_load_2d_nohint(a_dst + kABytes, &tmapQ, static_cast<int32_t>(kc * (kTf32 ? 32 : kBK)), static_cast<int32_t>(qt * kBN), full_bar + stage * 8);
                         if (++stage == kStagesB) { stage = 0; phase ^= 1; }
                     }
         }
@@ -230,8 +247,10 @@ batch_gemm_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_c
                         const uint32_t a_addr = stages_addr + stage * kStageB;
                         const uint64_t da = make_desc(a_addr), db = make_desc(a_addr + kABytes);
 #pragma unroll
-                        for (uint32_t k = 0; k < kBK / 16; ++k)        // advance 32 bytes (>>4 == 2) inside the swizzle span
-                            tc_mma_f16(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (kc | k) != 0 ? 1u : 0u);
+                        for (uint32_t k = 0; k < 4; ++k) {             // 4 x 32 bytes (>>4 == 2) inside the swizzle span: K = 16 halves / 8 tf32
+                            if constexpr (kTf32) tc_mma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+                            else tc_mma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+                        }
                         tc_commit(empty_bar + stage * 8);                // smem stage free once these MMAs retire
                         if (++stage == kStagesB) { stage = 0; phase ^= 1; }
                     }
@@ -460,6 +479,17 @@ __device__ __forceinline__ void tc_mma_f16_2sm(uint32_t tmem_d, uint64_t desc_a,
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void tc_mma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void tc_commit_2sm(uint32_t bar)   // arrives on the barrier at this offset in BOTH CTAs
 {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -474,10 +504,11 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
 constexpr int kBatch2Threads = 384;     // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue (two per TMEM lane quadrant)
 constexpr uint32_t kEpiWarps2 = 8;
 
+template <bool kTf32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatch2Threads, 1)
 batch_gemm2_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapQ,
                         uint32_t n_rows, uint32_t row_base, uint32_t pair0, uint32_t pair1, uint32_t nq_tiles,
-                        uint32_t n_k, const float *__restrict__ tau, unsigned long long *__restrict__ app_keys,
+                        uint32_t n_k, uint32_t idesc, const float *__restrict__ tau, unsigned long long *__restrict__ app_keys,
                         uint32_t *__restrict__ app_cnt, uint32_t cap, uint32_t *__restrict__ overflow, uint32_t dense,
                         unsigned long long *dbg /* dev-only cycle counters of cluster 0, may be null */)
 {
@@ -540,8 +571,8 @@ batch_gemm2_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_
                         const uint32_t lead_full = (full_bar + stage * 8) & kPeerMask;
                         if (rank == 0) mbar_arrive_expect_tx(full_bar + stage * 8, 2 * kStage2);   // both CTAs' bytes
                         const uint32_t a_dst = stages_addr + stage * kStage2;
-                        tma_load_2d_2sm(a_dst, &tmapA, static_cast<int32_t>(kc * kBK), static_cast<int32_t>((rp * 2 + rank) * kBM), lead_full);
-                        tma_load_2d_2sm(a_dst + kABytes, &tmapQ, static_cast<int32_t>(kc * kBK), static_cast<int32_t>(qt * kBN + rank * 128), lead_full);
+                        tma_load_2d_2sm(a_dst, &tmapA, static_cast<int32_t>(kc * (kTf32 ? 32 : kBK)), static_cast<int32_t>((rp * 2 + rank) * kBM), lead_full);
+                        tma_load_2d_2sm(a_dst + kABytes, &tmapQ, static_cast<int32_t>(kc * (kTf32 ? 32 : kBK)), static_cast<int32_t>(qt * kBN + rank * 128), lead_full);
                         if (++stage == kStages2) { stage = 0; phase ^= 1; }
                     }
             }
@@ -565,8 +596,10 @@ batch_gemm2_topm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_
                         const uint32_t a_addr = stages_addr + stage * kStage2;
                         const uint64_t da = make_desc(a_addr), db = make_desc(a_addr + kABytes);
 #pragma unroll
-                        for (uint32_t k = 0; k < kBK / 16; ++k)
-                            tc_mma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, kIdesc2, (kc | k) != 0 ? 1u : 0u);
+                        for (uint32_t k = 0; k < 4; ++k) {             // 4 x 32 bytes of the swizzle span: K = 16 halves / 8 tf32 each
+                            if constexpr (kTf32) tc_mma_tf32_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+                            else tc_mma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+                        }
                         tc_commit_2sm(empty_bar + stage * 8);             // frees this stage in BOTH CTAs
                         if (++stage == kStages2) { stage = 0; phase ^= 1; }
                     }
@@ -830,16 +863,22 @@ batch_prune_warp_kernel(unsigned long long *__restrict__ state_keys, uint32_t *_
     }
 }
 
-// f32 queries -> zero-padded binary16 operand rows; also the NaN/Inf check of the (normalised) queries
-__global__ void to_half_rows_kernel(const float *__restrict__ src, uint32_t dim, __half *__restrict__ dst, uint32_t pitch,
-                                    uint32_t n_valid, uint32_t n_pad, uint32_t *__restrict__ nonfinite)
+// f32 queries -> zero-padded operand rows of the contraction's input type (prec 0: binary16, 1: bfloat16,
+// both round to nearest even; 2: f32 kept as it is -- kind::tf32 reads the upper 19 bits); also the NaN/Inf
+// check of the (normalised) queries
+template <int kPrec>
+__global__ void to_operand_rows_kernel(const float *__restrict__ src, uint32_t dim, void *__restrict__ dst_v, uint32_t pitch,
+                                       uint32_t n_valid, uint32_t n_pad, uint32_t *__restrict__ nonfinite)
 {
     bool bad = false;
     for (uint32_t r = blockIdx.x; r < n_pad; r += gridDim.x)
         for (uint32_t c = threadIdx.x; c < pitch; c += blockDim.x) {
             float x = 0.0f;
             if (r < n_valid && c < dim) { x = src[static_cast<size_t>(r) * dim + c]; bad |= !is_finite_f32(x); }
-            dst[static_cast<size_t>(r) * pitch + c] = __float2half_rn(x);
+            const size_t o = static_cast<size_t>(r) * pitch + c;
+            if constexpr (kPrec == 0) static_cast<__half *>(dst_v)[o] = __float2half_rn(x);
+            else if constexpr (kPrec == 1) static_cast<__nv_bfloat16 *>(dst_v)[o] = __float2bfloat16_rn(x);
+            else static_cast<float *>(dst_v)[o] = x;
         }
     if (bad && nonfinite != nullptr) atomicOr(nonfinite, 1u);
 }
@@ -891,17 +930,21 @@ size_t batch_smem_bytes(uint32_t nq_pad) { return kStagesB * kStageB + 256 + nq_
 
 cudaError_t batch_configure(int smem_optin)
 {
-    cudaError_t e = cudaFuncSetAttribute(batch_gemm_topm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(batch_gemm2_topm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+    cudaError_t e = cudaFuncSetAttribute(batch_gemm_topm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(batch_gemm_topm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(batch_gemm2_topm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(batch_gemm2_topm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+    return e;
 }
 
 // 2-CTA variant: tiles are handed out in PAIRS of 128-row tiles; tile0 must be even
 cudaError_t batch_gemm2_launch(const CUtensorMap *tmapA, const CUtensorMap *tmapQ128, int sm_count, uint32_t n_rows,
-                               uint32_t row_base, uint32_t tile0, uint32_t tile1, uint32_t nq_pad, uint32_t pitch16,
+                               uint32_t row_base, uint32_t tile0, uint32_t tile1, uint32_t nq_pad, uint32_t pitch_elems, int prec,
                                const float *tau, unsigned long long *app_keys, uint32_t *app_cnt, uint32_t cap,
                                uint32_t *overflow, int dense, cudaStream_t st)
 {
+    const uint32_t n_k = pitch_elems / (prec == 2 ? 32u : static_cast<uint32_t>(kBK));
+    const uint32_t idesc = kIdesc2 | idesc_fmt(prec);
     if (tile1 <= tile0) return cudaSuccess;
     const uint32_t pair0 = tile0 / 2, pair1 = (tile1 + 1) / 2;
     uint32_t clusters = static_cast<uint32_t>(sm_count / 2);
@@ -910,8 +953,12 @@ cudaError_t batch_gemm2_launch(const CUtensorMap *tmapA, const CUtensorMap *tmap
     const size_t smem = kStages2 * kStage2 + 256 + nq_pad * sizeof(float) + kEpiWarps2 * kStageBytesPerWarp + 1024;
     unsigned long long *dbg = nullptr;
     if (getenv("RLR_DEBUG_BATCH_TRACE") && pair1 - pair0 > 1000) { cudaMalloc(&dbg, 256); cudaMemset(dbg, 0, 256); }
-    batch_gemm2_topm_kernel<<<clusters * 2, kBatch2Threads, smem, st>>>(
-        *tmapA, *tmapQ128, n_rows, row_base, pair0, pair1, nq_pad / kBN, pitch16 / kBK, tau, app_keys, app_cnt, cap, overflow, dense ? 1u : 0u, dbg);
+    if (prec == 2)
+        batch_gemm2_topm_kernel<true><<<clusters * 2, kBatch2Threads, smem, st>>>(
+            *tmapA, *tmapQ128, n_rows, row_base, pair0, pair1, nq_pad / kBN, n_k, idesc, tau, app_keys, app_cnt, cap, overflow, dense ? 1u : 0u, dbg);
+    else
+        batch_gemm2_topm_kernel<false><<<clusters * 2, kBatch2Threads, smem, st>>>(
+            *tmapA, *tmapQ128, n_rows, row_base, pair0, pair1, nq_pad / kBN, n_k, idesc, tau, app_keys, app_cnt, cap, overflow, dense ? 1u : 0u, dbg);
     if (dbg) {
         unsigned long long h[32];
         cudaStreamSynchronize(st);
@@ -938,25 +985,34 @@ cudaError_t batch_init_launch(float *tau, uint32_t *state_cnt, uint32_t *app_cnt
     return cudaGetLastError();
 }
 
-cudaError_t batch_queries_to_half_launch(const float *d_q, uint32_t dim, void *d_q16, uint32_t pitch16, uint32_t nq,
-                                         uint32_t nq_pad, uint32_t *d_nonfinite, cudaStream_t st)
+cudaError_t batch_queries_to_operand_launch(const float *d_q, uint32_t dim, void *d_qop, uint32_t pitch_elems, int prec,
+                                            uint32_t nq, uint32_t nq_pad, uint32_t *d_nonfinite, cudaStream_t st)
 {
-    to_half_rows_kernel<<<nq_pad < 592 ? nq_pad : 592, 256, 0, st>>>(d_q, dim, static_cast<__half *>(d_q16), pitch16, nq, nq_pad, d_nonfinite);
+    const uint32_t grid = nq_pad < 592 ? nq_pad : 592;
+    if (prec == 0) to_operand_rows_kernel<0><<<grid, 256, 0, st>>>(d_q, dim, d_qop, pitch_elems, nq, nq_pad, d_nonfinite);
+    else if (prec == 1) to_operand_rows_kernel<1><<<grid, 256, 0, st>>>(d_q, dim, d_qop, pitch_elems, nq, nq_pad, d_nonfinite);
+    else to_operand_rows_kernel<2><<<grid, 256, 0, st>>>(d_q, dim, d_qop, pitch_elems, nq, nq_pad, d_nonfinite);
     return cudaGetLastError();
 }
 
 cudaError_t batch_gemm_launch(const CUtensorMap *tmapA, const CUtensorMap *tmapQ, int grid, uint32_t n_rows,
-                              uint32_t row_base, uint32_t tile0, uint32_t tile1, uint32_t nq_pad, uint32_t pitch16,
+                              uint32_t row_base, uint32_t tile0, uint32_t tile1, uint32_t nq_pad, uint32_t pitch_elems, int prec,
                               const float *tau, unsigned long long *app_keys, uint32_t *app_cnt, uint32_t cap,
                               uint32_t *overflow, cudaStream_t st)
 {
+    const uint32_t n_k = pitch_elems / (prec == 2 ? 32u : static_cast<uint32_t>(kBK));
+    const uint32_t idesc = kIdesc | idesc_fmt(prec);
     if (tile1 <= tile0) return cudaSuccess;
     const uint32_t tiles = tile1 - tile0;
     if (static_cast<uint32_t>(grid) > tiles) grid = static_cast<int>(tiles);
     unsigned long long *dbg = nullptr;
     if (getenv("RLR_DEBUG_BATCH_TRACE") && tiles > 2000) { cudaMalloc(&dbg, 64); cudaMemset(dbg, 0, 64); }
-    batch_gemm_topm_kernel<<<grid, kBatchThreads, batch_smem_bytes(nq_pad), st>>>(
-        *tmapA, *tmapQ, n_rows, row_base, tile0, tile1, nq_pad / kBN, pitch16 / kBK, tau, app_keys, app_cnt, cap, overflow, dbg);
+    if (prec == 2)
+        batch_gemm_topm_kernel<true><<<grid, kBatchThreads, batch_smem_bytes(nq_pad), st>>>(
+            *tmapA, *tmapQ, n_rows, row_base, tile0, tile1, nq_pad / kBN, n_k, idesc, tau, app_keys, app_cnt, cap, overflow, dbg);
+    else
+        batch_gemm_topm_kernel<false><<<grid, kBatchThreads, batch_smem_bytes(nq_pad), st>>>(
+            *tmapA, *tmapQ, n_rows, row_base, tile0, tile1, nq_pad / kBN, n_k, idesc, tau, app_keys, app_cnt, cap, overflow, dbg);
     if (dbg) {
         unsigned long long h[8];
         cudaStreamSynchronize(st);
@@ -965,6 +1021,24 @@ cudaError_t batch_gemm_launch(const CUtensorMap *tmapA, const CUtensorMap *tmapQ
         fprintf(stderr, "[batch trace tiles=%u] CTA0 MMA thread: wait tmem_empty %llu, wait smem_full %llu, total %llu cycles; "
                         "epilogue warp: wait tmem_full %llu, work %llu cycles\n", tiles, h[0], h[1], h[2], h[3], h[4]);
     }
+    return cudaGetLastError();
+}
+
+// f32 store rows -> bfloat16 copy (round to nearest even), zero padded to dst_pitch
+__global__ void rows_to_bf16_kernel(const float *__restrict__ src, uint32_t src_pitch, __nv_bfloat16 *__restrict__ dst,
+                                    uint32_t dst_pitch, uint32_t dim, uint64_t n_rows)
+{
+    for (uint64_t r = blockIdx.x; r < n_rows; r += gridDim.x)
+        for (uint32_t c = threadIdx.x; c < dst_pitch; c += blockDim.x)
+            dst[r * dst_pitch + c] = __float2bfloat16_rn(c < dim ? src[r * src_pitch + c] : 0.0f);
+}
+
+cudaError_t to_bf16_launch(const float *d_src, uint32_t src_pitch, void *d_dst, uint32_t dst_pitch, uint32_t dim,
+                           uint64_t n_rows, cudaStream_t stream)
+{
+    if (n_rows == 0) return cudaSuccess;
+    const uint32_t grid = static_cast<uint32_t>(n_rows < 148 * 16 ? n_rows : 148 * 16);
+    rows_to_bf16_kernel<<<grid, 256, 0, stream>>>(d_src, src_pitch, static_cast<__nv_bfloat16 *>(d_dst), dst_pitch, dim, n_rows);
     return cudaGetLastError();
 }
 

@@ -143,14 +143,18 @@ size_t batch_smem_bytes(uint32_t nq_pad);
 cudaError_t batch_configure(int smem_optin);
 cudaError_t batch_init_launch(float *tau, uint32_t *state_cnt, uint32_t *app_cnt, uint32_t nq, uint32_t nq_pad,
                               uint32_t *overflow, cudaStream_t st);
-cudaError_t batch_queries_to_half_launch(const float *d_q, uint32_t dim, void *d_q16, uint32_t pitch16, uint32_t nq,
-                                         uint32_t nq_pad, uint32_t *d_nonfinite /* nullable */, cudaStream_t st);
+// operand precision of the batched contraction: what a 128-byte k-chunk of the operand tiles holds
+constexpr int kPrecF16 = 0, kPrecBF16 = 1, kPrecTF32 = 2;
+cudaError_t batch_queries_to_operand_launch(const float *d_q, uint32_t dim, void *d_qop, uint32_t pitch_elems, int prec,
+                                            uint32_t nq, uint32_t nq_pad, uint32_t *d_nonfinite /* nullable */, cudaStream_t st);
+cudaError_t to_bf16_launch(const float *d_src, uint32_t src_pitch, void *d_dst, uint32_t dst_pitch, uint32_t dim,
+                           uint64_t n_rows, cudaStream_t stream);
 cudaError_t batch_gemm_launch(const CUtensorMap *tmapA, const CUtensorMap *tmapQ, int grid, uint32_t n_rows,
-                              uint32_t row_base, uint32_t tile0, uint32_t tile1, uint32_t nq_pad, uint32_t pitch16,
+                              uint32_t row_base, uint32_t tile0, uint32_t tile1, uint32_t nq_pad, uint32_t pitch_elems, int prec,
                               const float *tau, unsigned long long *app_keys, uint32_t *app_cnt, uint32_t cap,
                               uint32_t *overflow, cudaStream_t st);
 cudaError_t batch_gemm2_launch(const CUtensorMap *tmapA, const CUtensorMap *tmapQ128, int sm_count, uint32_t n_rows,
-                               uint32_t row_base, uint32_t tile0, uint32_t tile1, uint32_t nq_pad, uint32_t pitch16,
+                               uint32_t row_base, uint32_t tile0, uint32_t tile1, uint32_t nq_pad, uint32_t pitch_elems, int prec,
                                const float *tau, unsigned long long *app_keys, uint32_t *app_cnt, uint32_t cap,
                                uint32_t *overflow, int dense, cudaStream_t st);
 cudaError_t batch_set_cnt_launch(uint32_t *app_cnt, uint32_t nq, uint32_t value, cudaStream_t st);

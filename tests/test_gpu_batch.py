@@ -71,12 +71,101 @@ def test_batch_exact_rescore_is_bit_identical_to_single_query_path():
     s.close()
 
 
-def test_batch_needs_f16_copy():
+def test_batch_operand_copies_are_required_for_the_16_bit_kinds():
     import rust_local_rag_b200  # noqa: F401
     from rust_local_rag_b200 import binding as B, engine
     s = engine.DeviceStore.from_rows(np.eye(64, dtype=F32))
+    for flag in (B.RLR_BATCH_F16, B.RLR_BATCH_BF16):
+        with pytest.raises(B.RlrError) as ei:
+            s.search_batch(np.ones((2, 64), F32), 3, flags=flag)
+        assert ei.value.code == B.RLR_ERR_INVALID_ARG
+    rows, _, n = s.search_batch(np.eye(2, 64, dtype=F32), 3)          # plain f32 store: tf32 over the rows themselves
+    assert (n == 3).all() and rows[0, 0] == 0 and rows[1, 0] == 1
+    s.close()
+    s = engine.DeviceStore.from_rows(np.eye(64, dtype=F32), flags=B.RLR_STORE_F16_ONLY)
     with pytest.raises(B.RlrError):
-        s.search_batch(np.ones((2, 64), F32), 3)
+        s.search_batch(np.ones((2, 64), F32), 3, flags=B.RLR_BATCH_TF32)
+    s.close()
+
+
+def _tf32_trunc(x):
+    return (np.ascontiguousarray(x, F32).view(np.uint32) & np.uint32(0xFFFFE000)).view(F32)
+
+
+def _bf16_rne(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x, F32)).to(torch.bfloat16).float().numpy()
+
+
+# stated tolerances of the operand precisions against the EXACT scores on unit vectors (asserted below):
+#   binary16 2e-4, tf32 1e-3 (10-bit mantissas, truncated), bfloat16 4e-3 (7-bit mantissas)
+TOL_VS_EXACT = {"f16": 2e-4, "tf32": 1e-3, "bf16": 4e-3}
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16", "f16"])
+@pytest.mark.parametrize("n,dim,nq,m", [(4096, 768, 256, 100), (20000, 1024, 300, 100), (5000, 96, 17, 10), (70000, 384, 512, 300)])
+def test_batch_precisions_match_the_contraction_of_their_rounded_inputs(prec, n, dim, nq, m):
+    """north_star kernel (3): "tcgen05/TMEM tiles with tf32/bf16 inputs".  Each precision is the f64 contraction of
+    the inputs rounded the way that precision rounds them (tf32: truncation to 10 mantissa bits by the tensor core,
+    straight over the f32 store -- no copy; bf16 / binary16: round to nearest even into the store's copy), within
+    TOL absolute (the products are exact in f32, only the f32 accumulation order differs), and within the STATED
+    tolerance of the exact scores."""
+    import rust_local_rag_b200  # noqa: F401
+    from rust_local_rag_b200 import binding as B, engine
+    from oracle import orc
+    rng = np.random.default_rng(n + nq + len(prec))
+    rows = orc.normalize_rows(rng.standard_normal((n, dim)).astype(F32))
+    qs = rng.standard_normal((nq, dim)).astype(F32)
+    qn = np.stack([orc.normalize(q) for q in qs])
+    store_flags = {"tf32": 0, "bf16": B.RLR_STORE_KEEP_BF16, "f16": B.RLR_STORE_KEEP_F16}[prec]
+    flag = {"tf32": B.RLR_BATCH_TF32, "bf16": B.RLR_BATCH_BF16, "f16": B.RLR_BATCH_F16}[prec]
+    rnd = {"tf32": _tf32_trunc, "bf16": _bf16_rne, "f16": lambda x: x.astype(np.float16).astype(F32)}[prec]
+    s = engine.DeviceStore.from_rows(rows, flags=store_flags)
+    got_rows, got_scores, got_n = s.search_batch(qs, m, flags=flag)
+    ref, order = _ref_topm(rnd(rows), rnd(qn), m)
+    exact = qn.astype(np.float64) @ rows.astype(np.float64).T
+    m_eff = min(m, n)
+    assert (got_n == m_eff).all()
+    worst_model, worst_exact = 0.0, 0.0
+    for q in range(nq):
+        r = got_rows[q, :m_eff]
+        assert len(set(r.tolist())) == m_eff
+        g = got_scores[q, :m_eff].astype(np.float64)
+        worst_model = max(worst_model, np.abs(g - ref[q, r]).max())
+        worst_exact = max(worst_exact, np.abs(g - exact[q, r]).max())
+        assert (np.diff(g) <= 0).all()
+        cut = ref[q, order[q, m_eff - 1]]
+        missing = set(order[q].tolist()) - set(r.tolist())
+        assert all(ref[q, x] <= cut + 2 * TOL for x in missing), (prec, q)
+        assert all(ref[q, x] >= cut - 2 * TOL for x in r.tolist()), (prec, q)
+    assert worst_model <= TOL, (prec, worst_model)
+    assert worst_exact <= TOL_VS_EXACT[prec], (prec, worst_exact)
+    # exact re-score restores the single-query path's bits in every precision
+    got_rows, got_scores, _ = s.search_batch(qs[:8], m, flags=flag | B.RLR_BATCH_EXACT_RESCORE)
+    for q in range(8):
+        back = rows[got_rows[q, :m_eff]]
+        assert got_scores[q, :m_eff].tobytes() == np.array([orc.dot(qn[q], b) for b in back], F32).tobytes()
+    s.close()
+
+
+def test_bf16_copy_follows_store_mutation():
+    import rust_local_rag_b200  # noqa: F401
+    from rust_local_rag_b200 import binding as B, engine
+    from oracle import orc
+    rng = np.random.default_rng(77)
+    rows = orc.normalize_rows(rng.standard_normal((3000, 128)).astype(F32))
+    extra = orc.normalize_rows(rng.standard_normal((500, 128)).astype(F32))
+    s = engine.DeviceStore.from_rows(rows, flags=B.RLR_STORE_KEEP_BF16)
+    s.remove_rows(np.arange(100, 400))
+    s.append(extra)
+    n = s.info().n_rows
+    now = s.read_rows(np.arange(n))
+    qs = rng.standard_normal((16, 128)).astype(F32)
+    qn = np.stack([orc.normalize(q) for q in qs])
+    got_rows, got_scores, _ = s.search_batch(qs, 50, flags=B.RLR_BATCH_BF16)
+    ref = _bf16_rne(qn).astype(np.float64) @ _bf16_rne(now).astype(np.float64).T
+    for q in range(16):
+        assert np.abs(got_scores[q].astype(np.float64) - ref[q, got_rows[q]]).max() <= TOL
     s.close()
 
 
