@@ -97,7 +97,8 @@ def dist_mode():
 # clocks: sampled with NVML during the timed regions
 # ----------------------------------------------------------------------------------------
 class ClockSampler:
-    def __init__(self, index):
+    def __init__(self, index, interval=0.02):
+        self.interval = interval
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._t = None
@@ -131,7 +132,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(self.interval)
 
     def start(self):
         if self.nv is not None:
@@ -746,7 +747,7 @@ def run_extras(a, rank, world, local_rank, dev, group, peaks):
 
     def single_query_config(name, rows_n, dim, k, lam, steps, oracle_rows):
         """configs 1 and 2 on one GPU through rlr_search_mmr; parity: complete results vs the oracle."""
-        clk = ClockSampler(local_rank)
+        clk = ClockSampler(local_rank, interval=0.005)
         st = engine.DeviceStore.synthetic(rows_n, dim, device=local_rank, **kw)
         qh = queries(64, dim)
         for i in range(5):
@@ -813,7 +814,7 @@ def run_extras(a, rank, world, local_rank, dev, group, peaks):
 
         recs = {}
         for prec, pflag in (("f16", B.RLR_BATCH_F16), ("bf16", B.RLR_BATCH_BF16), ("tf32", B.RLR_BATCH_TF32)):
-            clk = ClockSampler(local_rank)
+            clk = ClockSampler(local_rank, interval=0.005)
             flags = B.RLR_QUERY_PRENORMALIZED | B.RLR_WANT_TIMINGS | pflag
             for _ in range(3):
                 res = rdist.sharded_search_batch(st, group, qh, m4, flags, dev)
@@ -822,7 +823,7 @@ def run_extras(a, rank, world, local_rank, dev, group, peaks):
                 dist.barrier(group=group)
             clk.start()
             wall, dev_ms = [], []
-            for _ in range(10):
+            for _ in range(20):
                 if world > 1:
                     dist.barrier(group=group)
                 t0 = time.perf_counter()
@@ -860,7 +861,7 @@ def run_extras(a, rank, world, local_rank, dev, group, peaks):
                                                 + (" halved: tf32 issues at half the bf16 rate" if prec == "tf32" else "")},
                     "parity": {"ok": bool(ok4), "max_abs_dev_from_fp64_contraction_of_rounded_inputs": worst, "stated_tolerance": 1e-5,
                                "max_abs_dev_from_exact_scores": worst_exact},
-                    "steps": 10, "clocks": clk.summary()}
+                    "steps": 20, "clocks": clk.summary()}
                 all_ok &= ok4
         if rank == 0:
             out["config4_batched"] = {
