@@ -126,7 +126,7 @@ void rlr_api::ctx_free(rlr_ctx *c)
 {
     if (!c) return;
     cudaFree(c->d_query); cudaFree(c->d_lex_rows); cudaFree(c->d_lex_norm); cudaFree(c->d_lists);
-    cudaFree(c->d_counts); cudaFree(c->d_ticket); cudaFree(c->d_pub); cudaFree(c->d_tmp); cudaFree(c->d_pool_blk); cudaFree(c->d_tri);
+    cudaFree(c->d_counts); cudaFree(c->d_ticket); cudaFree(c->d_pub); cudaFree(c->d_tmp); cudaFree(c->d_pool_blk); cudaFree(c->d_tri); cudaFree(c->d_gather);
     cudaFree(c->d_sel_pos); cudaFree(c->d_result_blk); cudaFree(c->d_rows_in);
     cudaFree(c->d_rel_in); cudaFree(c->d_p_in);
     cudaFreeHost(c->h_query); cudaFreeHost(c->h_lex_rows); cudaFreeHost(c->h_lex_norm);
@@ -172,6 +172,7 @@ int rlr_api::ctx_new(rlr_store *s, rlr_ctx **out)
     c->d_pool_n = reinterpret_cast<uint32_t *>(c->d_pool_blk);
     c->d_pool = reinterpret_cast<rlr_cand *>(c->d_pool_blk + 16);
     CTX_TRY(cudaMalloc(&c->d_tri, static_cast<size_t>(RLR_MAX_M) * (RLR_MAX_M - 1) / 2 * sizeof(float)));
+    CTX_TRY(cudaMalloc(&c->d_gather, static_cast<size_t>(RLR_MAX_M) * s->pitch * sizeof(float)));
     CTX_TRY(cudaMalloc(&c->d_sel_pos, RLR_MAX_M * sizeof(uint32_t)));
     CTX_TRY(cudaMalloc(&c->d_result_blk, 16 + RLR_MAX_M * sizeof(rlr_cand)));
     c->d_sel_n = reinterpret_cast<uint32_t *>(c->d_result_blk);
@@ -1450,6 +1451,7 @@ RLR_EXPORT int rlr_mmr_peers_async(rlr_ctx *c, rlr_peer_set *p, const void *d_ca
     a.d_result = static_cast<rlr_cand *>(d_result);
     a.max_smem_optin = s->smem_optin;
     a.peers = &p->table;
+    a.d_gather = c->d_gather;
     uint32_t l = 0;
     CU_TRY(rlr::mmr_launch(a, static_cast<cudaStream_t>(stream), &l));
     c->launches += l;

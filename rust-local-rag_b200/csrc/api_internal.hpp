@@ -45,6 +45,7 @@ struct rlr_ctx {
     rlr_cand *d_pool = nullptr;
     uint32_t *d_pool_n = nullptr;
     float *d_tri = nullptr;
+    void *d_gather = nullptr;       // RLR_MAX_M x pitch f32 of scratch: pool rows gathered from peer GPUs for MMR
     uint32_t *d_sel_pos = nullptr;
     uint8_t *d_result_blk = nullptr; // same layout: d_sel_n / d_result point into it
     uint32_t *d_sel_n = nullptr;

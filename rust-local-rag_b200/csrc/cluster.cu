@@ -275,6 +275,7 @@ int cluster_search(rlr_cluster *cl, const float *query, uint32_t dim, uint32_t f
         a.d_tri = r0->d_tri; a.d_sel_pos = r0->d_sel_pos; a.d_sel_n = r0->d_sel_n; a.d_result = r0->d_result;
         a.max_smem_optin = s0->smem_optin;
         a.peers = half ? &cl->table16 : &cl->table32;
+        a.d_gather = r0->d_gather;
         uint32_t l = 0;
         CU_TRY(rlr::mmr_launch(a, st0, &l));
         launches += l;
@@ -531,6 +532,7 @@ RLR_EXPORT int rlr_cluster_mmr(rlr_cluster *cl, const uint32_t *cand_rows, const
     a.d_tri = c->d_tri; a.d_sel_pos = c->d_sel_pos; a.d_sel_n = c->d_sel_n; a.d_result = nullptr;
     a.max_smem_optin = s0->smem_optin;
     a.peers = half ? &cl->table16 : &cl->table32;
+    a.d_gather = c->d_gather;
     uint32_t l = 0;
     CU_TRY(rlr::mmr_launch(a, st, &l));
     cl->launches += l;

@@ -114,6 +114,8 @@ struct MmrArgs {
     rlr_cand *d_result;        // optional: selected records in selection order
     int max_smem_optin;
     const PeerTable *peers;    // optional (host pointer): candidate rows are global and live on these shards
+    void *d_gather;            // with peers: p_cap x pitch elements of scratch; the rows are gathered into it once (NVLink)
+                               // and the pairwise kernel reads local memory.  null: the pairwise kernel loads from the peers itself
 };
 cudaError_t mmr_configure();
 cudaError_t mmr_launch(const MmrArgs &a, cudaStream_t stream, uint32_t *launches);

@@ -281,6 +281,26 @@ mmr_greedy_kernel(const float *__restrict__ tri_g, const rlr_cand *__restrict__ 
     }
 }
 
+// Peer-memory MMR, step 0: bring every pool row ONCE from its owning GPU's HBM (NVLink loads through the peer
+// table) into a dense local matrix.  The pairwise kernel tiles the P x P triangle 16 x 16, so it reads every row
+// P/16 (= 19 for P = 300) times; over NVLink that was 18.6 MB of re-reads per query (0.06 ms of the root's tail)
+// against 0.9 MB here.  Raw 16-byte copies: the element type does not matter.
+__global__ void __launch_bounds__(256)
+gather_peers_kernel(const __grid_constant__ PeerTable peers, const rlr_cand *__restrict__ cands, const uint32_t *__restrict__ rows,
+                    const uint32_t *__restrict__ d_n, uint32_t row_bytes, uint8_t *__restrict__ out)
+{
+    const uint32_t i = blockIdx.x;
+    if (i >= *d_n) return;
+    const uint32_t g = rows != nullptr ? rows[i] : key_row(cands[i].key);      // GLOBAL row
+    const uint8_t *src = nullptr;
+    for (uint32_t s = 0; s < peers.n; ++s)
+        if (g >= peers.row_base[s] && g - peers.row_base[s] < peers.n_rows[s])
+            src = static_cast<const uint8_t *>(peers.base[s]) + static_cast<size_t>(g - peers.row_base[s]) * row_bytes;
+    uint4 *dst = reinterpret_cast<uint4 *>(out + static_cast<size_t>(i) * row_bytes);
+    for (uint32_t v = threadIdx.x; v < row_bytes / 16; v += blockDim.x)
+        dst[v] = src != nullptr ? __ldcg(reinterpret_cast<const uint4 *>(src) + v) : make_uint4(0, 0, 0, 0);
+}
+
 template <bool kHalf>
 __global__ void gather_kernel(const void *__restrict__ store, uint32_t pitch, uint32_t n_rows, uint32_t row_base,
                               const rlr_cand *__restrict__ cands, const uint32_t *__restrict__ d_n,
@@ -349,13 +369,26 @@ cudaError_t mmr_launch(const MmrArgs &a, cudaStream_t stream, uint32_t *launches
     if (a.p_cap > 1) {
         PeerTable pt;
         memset(&pt, 0, sizeof pt);
-        if (a.peers != nullptr) pt = *a.peers;
+        const void *emb = a.d_emb;
+        const uint32_t *rows = a.d_rows;
+        int use_rows = a.use_rows;
+        if (a.peers != nullptr && a.d_gather != nullptr) {
+            // rows live on several GPUs: one gather pass over NVLink, then the pairwise kernel reads local memory
+            gather_peers_kernel<<<a.p_cap, 256, 0, stream>>>(*a.peers, a.d_cands, a.d_rows, a.d_n, a.pitch * (a.half ? 2u : 4u),
+                                                             static_cast<uint8_t *>(a.d_gather));
+            if (launches) ++*launches;
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+            emb = a.d_gather; rows = nullptr; use_rows = 0;       // candidate i is row i of the gathered matrix
+        } else if (a.peers != nullptr) {
+            pt = *a.peers;
+        }
         if (a.half)
             mmr_pairwise_kernel<true><<<dim3(nb, nb), T * T, 2 * T * (KC * 2 + 16), stream>>>(
-                a.d_emb, a.pitch, a.d_cands, a.d_rows, a.d_n, a.row_base, a.use_rows, a.d_tri, pt);
+                emb, a.pitch, a.d_cands, rows, a.d_n, a.row_base, use_rows, a.d_tri, pt);
         else
             mmr_pairwise_kernel<false><<<dim3(nb, nb), T * T, 2 * T * (KC * 4 + 16), stream>>>(
-                a.d_emb, a.pitch, a.d_cands, a.d_rows, a.d_n, a.row_base, a.use_rows, a.d_tri, pt);
+                emb, a.pitch, a.d_cands, rows, a.d_n, a.row_base, use_rows, a.d_tri, pt);
         if (launches) ++*launches;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;

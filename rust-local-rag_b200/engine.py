@@ -124,6 +124,106 @@ def get_sidecar_path(data_dir: str, model_name: str) -> str:
     return get_index_path(data_dir, model_name)[:-len(".json")] + ".rlrbin"
 
 
+def get_legacy_path(data_dir: str) -> str:
+    """src/rag_engine.rs:1471-1473."""
+    return os.path.join(data_dir, "chunks.json")
+
+
+def _f32_json(v: np.ndarray) -> List[str]:
+    """Shortest decimal strings that round-trip every f32 (what serde_json's ryu writes, :1504; numpy's f32 -> str
+    is the same shortest-repr algorithm): parsing them as f64 and narrowing -- what serde and `json.load` +
+    np.float32 do -- returns the same bits."""
+    return np.asarray(v, dtype=np.float32).astype(str).tolist()
+
+
+def write_chunks_json(path: str, model: str, chunks: Sequence["DocumentChunk"], rows: np.ndarray, needs_reindex: bool,
+                      document_hashes: dict) -> None:
+    """save_to_disk, src/rag_engine.rs:1477-1518: PersistedState {version: 2, model, chunks: {id -> DocumentChunk},
+    needs_reindex, document_hashes (omitted when empty)} as pretty JSON (serde_json::to_string_pretty: 2-space
+    indent, one array element per line), written to `<path minus .json>.json.tmp` and renamed over `path`
+    (:1494,:1506-1511).  `rows[i]` is chunk i's embedding as stored (normalised)."""
+    if len(chunks) != len(rows):
+        raise ValueError("one embedding row per chunk")
+    marker = "@@RLR_EMBEDDING_%d@@"
+    state = {"version": 2, "model": model,
+             "chunks": {c.id: {"id": c.id, "document_name": c.document_name, "text": c.text, "embedding": marker % i,
+                               "chunk_index": c.chunk_index, "page_number": c.page_number, "section": c.section,
+                               "metadata": _metadata_json(c.metadata)} for i, c in enumerate(chunks)},
+             "needs_reindex": bool(needs_reindex)}
+    if document_hashes:                          # skip_serializing_if = "HashMap::is_empty"
+        state["document_hashes"] = dict(document_hashes)
+    text = json.dumps(state, indent=2, ensure_ascii=False)
+    tmp = path[:-len(".json")] + ".json.tmp" if path.endswith(".json") else path + ".tmp"     # with_extension("json.tmp")
+    with open(tmp, "w", encoding="utf-8") as f:
+        pos = 0
+        for i in range(len(chunks)):
+            tag = '"' + (marker % i) + '"'
+            at = text.index(tag, pos)
+            f.write(text[pos:at])
+            vals = _f32_json(rows[i])
+            f.write("[\n        " + ",\n        ".join(vals) + "\n      ]" if vals else "[]")
+            pos = at + len(tag)
+        f.write(text[pos:])
+        f.flush()
+        os.fsync(f.fileno())
+    os.replace(tmp, path)                        # atomic rename (:1509)
+
+
+def _metadata_json(md: dict) -> dict:
+    """ChunkMetadata, :35-42 (all five fields always serialised; Default::default() when absent)."""
+    md = md or {}
+    return {"page_range": md.get("page_range"), "sentence_range": md.get("sentence_range"),
+            "section_title": md.get("section_title"), "token_count": int(md.get("token_count", 0)),
+            "overlap_with_previous": int(md.get("overlap_with_previous", 0))}
+
+
+@dataclass
+class LoadDecision:
+    """What load_from_disk (:1520-1652) decided before any embedding is touched."""
+    state: Optional[dict]            # parsed PersistedState to apply, or None: start fresh
+    source: Optional[str]            # file the state came from
+    migrate: bool = False            # legacy chunks.json of the SAME model: save to the model-specific file after loading
+    needs_reindex: bool = False      # start fresh but rebuild (corrupt model file / pre-model legacy chunks)
+
+
+def _valid_state(d) -> bool:
+    return isinstance(d, dict) and isinstance(d.get("version"), int) and isinstance(d.get("model"), str) \
+        and isinstance(d.get("chunks"), dict)
+
+
+def decide_load(data_dir: str, model: str) -> LoadDecision:
+    """The file-selection half of load_from_disk, src/rag_engine.rs:1520-1652:
+      1. the model-specific `chunks_{sanitized}.json` wins; if it does not parse, start fresh with
+         needs_reindex (the corrupt file is kept, :1570-1582);
+      2. else a legacy `chunks.json` is migrated ONLY when its `model` is the current one (:1592-1617); another
+         model's legacy file is left alone (:1618-1626); a pre-model file (a bare id -> chunk map) with chunks in
+         it asks for a reindex (:1627-1644);
+      3. else start fresh."""
+    specific, legacy = get_index_path(data_dir, model), get_legacy_path(data_dir)
+    if os.path.exists(specific):
+        try:
+            with open(specific, "r", encoding="utf-8") as f:
+                state = json.load(f)
+            if not _valid_state(state):
+                raise ValueError("not a PersistedState")
+            return LoadDecision(state, specific)
+        except (ValueError, OSError, UnicodeDecodeError):
+            return LoadDecision(None, None, needs_reindex=True)
+    if os.path.exists(legacy):
+        try:
+            with open(legacy, "r", encoding="utf-8") as f:
+                data = json.load(f)
+        except (ValueError, OSError, UnicodeDecodeError):
+            return LoadDecision(None, None)
+        if isinstance(data, dict) and isinstance(data.get("model"), str):            # ModelOnly peek, :1589
+            if data["model"] == model and _valid_state(data):
+                return LoadDecision(data, legacy, migrate=True)
+            return LoadDecision(None, None)                                          # other model / unparsable: fresh
+        if isinstance(data, dict) and data and all(isinstance(v, dict) and "embedding" in v for v in data.values()):
+            return LoadDecision(None, None, needs_reindex=True)                      # :1632-1643
+    return LoadDecision(None, None)
+
+
 SIDECAR_MAGIC = b"RLRB200\x00"
 # header: magic[8] | u32 index version (the reference's, 2) | u32 dim | u64 n_rows | u64 meta_bytes | u64 reserved
 SIDECAR_HEADER = 40
@@ -469,15 +569,45 @@ class RagEngine:
     @classmethod
     def load_from_disk(cls, data_dir: str, model: str = "nomic-embed-text", device: int = 0,
                        devices: Optional[Sequence[int]] = None, **kw) -> "RagEngine":
-        """load_from_disk + apply_loaded_state, src/rag_engine.rs:1520-1696, for the
-        model-specific file `chunks_{sanitized}.json` (:1465-1468)."""
-        return cls.from_chunks_json(get_index_path(data_dir, model), model=model, device=device, devices=devices, **kw)
+        """load_from_disk + apply_loaded_state, src/rag_engine.rs:1520-1696: the model-specific file
+        `chunks_{sanitized}.json` (:1465-1468) first, then the legacy `chunks.json` migration; see decide_load."""
+        d = decide_load(data_dir, model)
+        if d.state is None:
+            eng = cls([], DeviceStore.from_rows(np.zeros((0, 1), np.float32), device=device), model=model, **kw)
+            eng.needs_reindex = d.needs_reindex
+            eng.data_dir = data_dir
+            return eng
+        eng = cls._from_state(d.state, model=model, device=device, devices=devices, **kw)
+        eng.data_dir = data_dir
+        if int(d.state["version"]) < 2:          # :1664-1673: wiped, marked, and the wipe is persisted
+            eng.save_to_disk()
+        elif d.migrate:                          # :1699-1706: legacy file preserved, model-specific file written
+            eng.save_to_disk()
+        return eng
+
+    def save_to_disk(self, data_dir: Optional[str] = None) -> str:
+        """save_to_disk, src/rag_engine.rs:1477-1518 (see write_chunks_json).  The embeddings are read back from
+        the device: they are the normalised rows the searches scan."""
+        data_dir = data_dir if data_dir is not None else getattr(self, "data_dir", None)
+        if data_dir is None:
+            raise ValueError("no data_dir: pass one or load the engine with load_from_disk")
+        path = get_index_path(data_dir, self.model)
+        n = len(self.chunks)
+        rows = self.store.read_rows(np.arange(n)) if n else np.zeros((0, 0), np.float32)
+        write_chunks_json(path, self.model, self.chunks, rows, self.needs_reindex, self.document_hashes)
+        return path
 
     @classmethod
     def from_chunks_json(cls, path: str, model: str = "nomic-embed-text", device: int = 0,
                          devices: Optional[Sequence[int]] = None, **kw) -> "RagEngine":
         with open(path, "r", encoding="utf-8") as f:
             state = json.load(f)
+        return cls._from_state(state, model=model, device=device, devices=devices, **kw)
+
+    @classmethod
+    def _from_state(cls, state: dict, model: str = "nomic-embed-text", device: int = 0,
+                    devices: Optional[Sequence[int]] = None, **kw) -> "RagEngine":
+        """apply_loaded_state, src/rag_engine.rs:1655-1709."""
         version = int(state["version"])
         chunks_map = state.get("chunks", {})
         if version < 2:                          # :1664-1673 outdated index: wipe, mark for reindex

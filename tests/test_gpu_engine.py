@@ -208,3 +208,74 @@ def test_binary_sidecar_round_trip(tmp_path, orc):
         f.write(b"NOTMAGIC")
     with pytest.raises(ValueError):
         engine.RagEngine.from_sidecar(side)
+
+
+def test_save_to_disk_round_trip_and_legacy_migration(tmp_path, orc):
+    """N1 saver: save_to_disk (:1477-1518) writes what load_from_disk reads back bit for bit; a legacy `chunks.json`
+    of the current model is migrated to `chunks_{model}.json` and preserved (:1592-1617, :1699-1706); an outdated
+    (version < 2) index is wiped, marked for reindex, and the wipe is persisted (:1664-1673)."""
+    import rust_local_rag_b200  # noqa: F401
+    from rust_local_rag_b200 import engine
+    d = str(tmp_path)
+    model = "nomic-embed-text"
+    legacy = engine.get_legacy_path(d)
+    chunks = _write_index(legacy, 300, 64, seed=4)                   # un-normalised embeddings, model nomic-embed-text
+    legacy_bytes = open(legacy, "rb").read()
+    eng = engine.RagEngine.load_from_disk(d, model=model)
+    specific = engine.get_index_path(d, model)
+    assert os.path.exists(specific) and open(legacy, "rb").read() == legacy_bytes       # migrated, legacy preserved
+    rows = orc.normalize_rows(np.array([c["embedding"] for c in chunks.values()], F32))
+    st = json.load(open(specific))
+    assert st["version"] == 2 and st["model"] == model and list(st["chunks"]) == list(chunks)
+    saved = np.array([c["embedding"] for c in st["chunks"].values()], np.float64).astype(F32)
+    assert saved.tobytes() == rows.tobytes()                         # the file holds the NORMALISED rows the searches scan
+    assert st["chunks"][eng.chunks[7].id]["metadata"]["token_count"] == 180
+    q = np.random.default_rng(2).standard_normal(64).astype(F32)
+    a = eng.search_with_diversity(q, 10, 0.4)
+    eng2 = engine.RagEngine.load_from_disk(d, model=model)           # now from the model-specific file
+    b = eng2.search_with_diversity(q, 10, 0.4)
+    ref = orc.search_with_diversity(rows, q, 10, 0.4, full_sort=True)
+    ids = list(chunks)
+    assert [h.chunk_id for h in a] == [h.chunk_id for h in b] == [ids[r] for r in ref[0]]
+    assert np.array([h.score for h in b], F32).tobytes() == ref[1].tobytes()
+    # a different model never touches these files and starts fresh
+    other = engine.RagEngine.load_from_disk(d, model="all-minilm")
+    assert len(other.chunks) == 0 and not other.needs_reindex and not os.path.exists(engine.get_index_path(d, "all-minilm"))
+    # outdated index: wiped + needs_reindex, persisted
+    d2 = str(tmp_path / "old")
+    os.makedirs(d2)
+    _write_index(engine.get_index_path(d2, model), 20, 16, version=1)
+    e3 = engine.RagEngine.load_from_disk(d2, model=model)
+    assert len(e3.chunks) == 0 and e3.needs_reindex
+    st = json.load(open(engine.get_index_path(d2, model)))
+    assert st["version"] == 2 and st["chunks"] == {} and st["needs_reindex"] is True and "document_hashes" not in st
+
+
+@pytest.mark.parametrize("devices", [None, [0, 0]])
+def test_config1_10k_x_768_through_the_index_file(tmp_path, orc, devices):
+    """BASELINE configs[0] at its stated size, end to end through the file format: a generated
+    10,000 x 768 `chunks_nomic-embed-text.json` -> load_from_disk (re-normalise, :1678) -> search_documents(top_k=5,
+    diversity=0.3) -> the oracle's answer on the same file contents.  `devices=[0, 0]`: the same through a
+    two-shard cluster."""
+    import sys
+    import rust_local_rag_b200  # noqa: F401
+    from rust_local_rag_b200 import engine
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import make_config1_index
+    path, emb = make_config1_index.make(str(tmp_path), rows=10_000, dim=768)
+    assert os.path.basename(path) == "chunks_nomic-embed-text.json" and os.path.getsize(path) > 50_000_000
+    eng = engine.RagEngine.load_from_disk(str(tmp_path), model="nomic-embed-text", devices=devices)
+    assert len(eng.chunks) == 10_000 and not eng.needs_reindex
+    rows = orc.normalize_rows(emb)                                   # what apply_loaded_state leaves in memory
+    qs = orc.synth_rows(16, 768, kind=1, seed=0x5EED0002, n_clusters=256)
+    for q in qs:
+        hits = engine.search_documents(eng, q)                       # top_k = 5, diversity_factor = 0.3
+        ref = orc.search_with_diversity(rows, q, 5, 0.3, full_sort=True)
+        assert [h.row for h in hits] == ref[0].tolist()
+        assert np.array([h.score for h in hits], F32).tobytes() == ref[1].tobytes()
+        assert np.array([h.embedding_score for h in hits], F32).tobytes() == ref[2].tobytes()
+        assert [h.chunk_id for h in hits] == [eng.chunks[r].id for r in ref[0]]
+    hits = engine.search_documents(eng, qs[0], top_k=100, diversity_factor=0.7)
+    ref = orc.search_with_diversity(rows, qs[0], 100, 0.7, full_sort=True)
+    assert [h.row for h in hits] == ref[0].tolist()
+    eng.store.close()
