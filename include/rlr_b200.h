@@ -297,24 +297,8 @@ int rlr_search_batch_device(rlr_store *s, const float *queries, uint32_t n_queri
 int rlr_batch_merge_async(rlr_store *s, const void *d_lists, uint32_t n_lists, uint32_t n_queries,
                           uint32_t m, void *d_out_keys, void *d_out_cnt /* nullable */, void *stream);
 
-/* ---- host-side BM25 index (LexicalIndex, src/rag_engine.rs:2083-2247) -----------------------
- * Pure host code, no device work: the reference keeps its lexical index on the host and a Rust
- * maintainer keeps using it; this twin lets the host mirrors shipped with this library reproduce
- * `search` on real chunk text.  Its output feeds lex_rows / lex_scores of rlr_search_topm /
- * rlr_search_mmr.  Chunks are identified by caller-chosen u64 keys.  Deterministic where the
- * reference is not: query terms are summed in bytewise order, score ties go to the smaller key.
- * rlr_tokenize returns the tokens of `text` joined by '\n' (:2242-2247). */
-typedef struct rlr_lexical rlr_lexical;
-int rlr_lexical_create(rlr_lexical **out);
-int rlr_lexical_destroy(rlr_lexical *lx);
-int rlr_lexical_add_chunk(rlr_lexical *lx, uint64_t chunk_key, const char *text_utf8, size_t len);
-int rlr_lexical_remove_chunk(rlr_lexical *lx, uint64_t chunk_key);
-int rlr_lexical_contains(const rlr_lexical *lx, uint64_t chunk_key, int *out);
-int rlr_lexical_stats(const rlr_lexical *lx, uint64_t *total_docs, uint64_t *total_length, uint64_t *n_terms);
-int rlr_lexical_score(const rlr_lexical *lx, const char *query_utf8, size_t len, uint32_t limit,
-                      uint64_t *out_keys, float *out_scores, uint32_t cap, uint32_t *out_n);
-int rlr_tokenize(const char *text_utf8, size_t len, char *out, size_t out_cap, size_t *out_len,
-                 uint32_t *out_tokens);
+/* (The host-side BM25 twin that the non-Rust host mirrors use for text queries lives in
+ * include/rlr_hostmirror.h / librlr_hostmirror.so: host-mirror support, not part of this boundary.) */
 
 /* stage timings of the calling thread's most recent call made with RLR_WANT_TIMINGS */
 int rlr_last_timings(rlr_timings *out);

@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "rlr_b200.h"
+#include "rlr_hostmirror.h"   // BM25 twin for text queries: librlr_hostmirror.so (host-mirror support, not the boundary)
 
 namespace rlr {
 
@@ -35,6 +36,10 @@ struct Error : std::runtime_error {
     int code;
     Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
 };
+inline void check_hm(int rc)
+{
+    if (rc != RLR_HM_OK) throw Error(rc, std::string("rlr_hostmirror error ") + std::to_string(rc) + ": " + rlr_hostmirror_last_error());
+}
 inline void check(int rc)
 {
     if (rc != RLR_OK) throw Error(rc, std::string("rlr_b200 error ") + std::to_string(rc) + ": " + rlr_last_error());
@@ -203,7 +208,7 @@ class LexicalIndex {
     uint64_t next_ = 0;
 
 public:
-    LexicalIndex() { check(rlr_lexical_create(&lx_)); }
+    LexicalIndex() { check_hm(rlr_lexical_create(&lx_)); }
     LexicalIndex(const LexicalIndex &) = delete;
     LexicalIndex &operator=(const LexicalIndex &) = delete;
     ~LexicalIndex() { rlr_lexical_destroy(lx_); }
@@ -212,13 +217,13 @@ public:
         auto it = key_of_.find(id);
         uint64_t key;
         if (it == key_of_.end()) { key = next_++; key_of_[id] = key; id_of_[key] = id; } else key = it->second;
-        check(rlr_lexical_add_chunk(lx_, key, text.data(), text.size()));
+        check_hm(rlr_lexical_add_chunk(lx_, key, text.data(), text.size()));
     }
     void remove_chunk(const std::string &id)
     {
         auto it = key_of_.find(id);
         if (it == key_of_.end()) return;
-        check(rlr_lexical_remove_chunk(lx_, it->second));
+        check_hm(rlr_lexical_remove_chunk(lx_, it->second));
         id_of_.erase(it->second);
         key_of_.erase(it);
     }
@@ -227,7 +232,7 @@ public:
         auto it = key_of_.find(id);
         if (it == key_of_.end()) return false;
         int out = 0;
-        check(rlr_lexical_contains(lx_, it->second, &out));
+        check_hm(rlr_lexical_contains(lx_, it->second, &out));
         return out != 0;
     }
     std::vector<std::pair<std::string, float>> score(const std::string &query, size_t limit) const
@@ -236,7 +241,7 @@ public:
         std::vector<uint64_t> keys(cap);
         std::vector<float> sc(cap);
         uint32_t n = 0;
-        check(rlr_lexical_score(lx_, query.data(), query.size(), static_cast<uint32_t>(limit), keys.data(), sc.data(), cap, &n));
+        check_hm(rlr_lexical_score(lx_, query.data(), query.size(), static_cast<uint32_t>(limit), keys.data(), sc.data(), cap, &n));
         std::vector<std::pair<std::string, float>> out;
         for (uint32_t i = 0; i < n; ++i) out.emplace_back(id_of_.at(keys[i]), sc[i]);
         return out;

@@ -16,19 +16,12 @@ F = np.float32
 
 
 def tokenize(text: str):
-    """fn tokenize, :2242-2247: split on !char::is_alphanumeric, keep len() >= 3 BYTES, lowercase.
-    str.isalnum() is Python's spelling of Alphabetic || Numeric for the scripts the tests use."""
-    out, cur = [], []
-    for ch in text:
-        if ch.isalnum():
-            cur.append(ch)
-        else:
-            if cur:
-                out.append("".join(cur))
-            cur = []
-    if cur:
-        out.append("".join(cur))
-    return [t.lower() for t in out if len(t.encode("utf-8")) >= 3]
+    """fn tokenize, :2242-2247: split on !char::is_alphanumeric, keep len() >= 3 BYTES, str::to_lowercase.
+    Independent of the product's generated tables: the `regex` module's \\p{Alphabetic} / \\p{N*} classes are
+    Rust's `Alphabetic || Numeric`, and CPython's str.lower() is the full lowercase mapping with Final_Sigma."""
+    import regex
+    toks = regex.split(r"[^\p{Alphabetic}\p{Nd}\p{Nl}\p{No}]", text)
+    return [t.lower() for t in toks if len(t.encode("utf-8")) >= 3]
 
 
 def logf(x):

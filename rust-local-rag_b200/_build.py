@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librlr_b200.so")
-SOURCES = ["api.cu", "cluster.cu", "scan_topm.cu", "merge.cu", "mmr.cu", "synth.cu", "batch_gemm.cu", "lexical.cpp"]
+SOURCES = ["api.cu", "cluster.cu", "scan_topm.cu", "merge.cu", "mmr.cu", "synth.cu", "batch_gemm.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", "sort_regs.cuh", "api_internal.hpp", os.path.join("..", "..", "include", "rlr_b200.h")]
 
 NVCC_FLAGS = [
@@ -40,3 +40,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print(res.stderr)
     return LIB
+
+
+# ---- host-mirror support (NOT the product): the BM25 / tokenizer twin the non-Rust host mirrors use for text queries
+HM_DIR = os.path.join(HERE, "host_mirror")
+HM_LIB = os.path.join(HERE, "librlr_hostmirror.so")
+HM_DEPS = [os.path.join(HM_DIR, "lexical.cpp"), os.path.join(HM_DIR, "unicode_tables.inc"),
+           os.path.join(HERE, "..", "include", "rlr_hostmirror.h")]
+
+
+def build_hostmirror(force: bool = False) -> str:
+    """g++ host_mirror/lexical.cpp -> librlr_hostmirror.so (plain C++17, no CUDA)."""
+    if not force and os.path.exists(HM_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(HM_LIB) for d in HM_DEPS):
+        return HM_LIB
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-fvisibility=hidden", "-ffp-contract=off",
+           "-o", HM_LIB, HM_DEPS[0]]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return HM_LIB

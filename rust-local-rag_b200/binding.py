@@ -106,14 +106,6 @@ PROTOTYPES = {
     "rlr_search_batch": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp]),
     "rlr_search_batch_device": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp]),
     "rlr_batch_merge_async": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
-    "rlr_lexical_create": (_int, [C.POINTER(_vp)]),
-    "rlr_lexical_destroy": (_int, [_vp]),
-    "rlr_lexical_add_chunk": (_int, [_vp, _u64, C.c_char_p, C.c_size_t]),
-    "rlr_lexical_remove_chunk": (_int, [_vp, _u64]),
-    "rlr_lexical_contains": (_int, [_vp, _u64, C.POINTER(C.c_int)]),
-    "rlr_lexical_stats": (_int, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
-    "rlr_lexical_score": (_int, [_vp, C.c_char_p, C.c_size_t, _u32, _vp, _vp, _u32, _pu32]),
-    "rlr_tokenize": (_int, [C.c_char_p, C.c_size_t, _vp, C.c_size_t, C.POINTER(C.c_size_t), _pu32]),
     "rlr_last_timings": (_int, [C.POINTER(TimingsC)]),
     "rlr_cluster_create": (_int, [_vp, _u32, _u32, _u64, _vp, _u64, _u32, _vp, C.POINTER(_vp)]),
     "rlr_cluster_destroy": (_int, [_vp]),
@@ -153,7 +145,43 @@ PROTOTYPES = {
     "rlr_time_scan": (_int, [_vp, _vp, _u32, _u32, _vp, _pf]),
 }
 
+# librlr_hostmirror.so (include/rlr_hostmirror.h): host-mirror support, not the product boundary
+HOSTMIRROR_PROTOTYPES = {
+    "rlr_hostmirror_last_error": (C.c_char_p, []),
+    "rlr_lexical_create": (_int, [C.POINTER(_vp)]),
+    "rlr_lexical_destroy": (_int, [_vp]),
+    "rlr_lexical_add_chunk": (_int, [_vp, _u64, C.c_char_p, C.c_size_t]),
+    "rlr_lexical_remove_chunk": (_int, [_vp, _u64]),
+    "rlr_lexical_contains": (_int, [_vp, _u64, C.POINTER(C.c_int)]),
+    "rlr_lexical_stats": (_int, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
+    "rlr_lexical_score": (_int, [_vp, C.c_char_p, C.c_size_t, _u32, _vp, _vp, _u32, _pu32]),
+    "rlr_tokenize": (_int, [C.c_char_p, C.c_size_t, _vp, C.c_size_t, C.POINTER(C.c_size_t), _pu32]),
+    "rlr_hostmirror_unicode_dump": (_int, [_vp, _vp, _u32]),
+}
+
 _lib = None
+_hm = None
+
+
+def load_hostmirror(build: bool = True) -> C.CDLL:
+    """dlopen librlr_hostmirror.so: the BM25 / tokenizer twin for the host mirrors' text queries (plain C++)."""
+    global _hm
+    if _hm is not None:
+        return _hm
+    path = _build.build_hostmirror() if build else _build.HM_LIB
+    lib = C.CDLL(path)
+    for name, (res, args) in HOSTMIRROR_PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _hm = lib
+    return lib
+
+
+def check_hm(rc: int) -> None:
+    if rc != 0:
+        msg = load_hostmirror().rlr_hostmirror_last_error()
+        raise RlrError(rc, msg.decode("utf-8", "replace") if msg else "")
 
 
 def load(build: bool = True) -> C.CDLL:

@@ -335,8 +335,6 @@ float resolve_one(bool has, float w, float dflt)
 // ---------------------------------------------------------------------------------
 // library
 // ---------------------------------------------------------------------------------
-extern "C" void rlr_internal_set_error(const char *msg) { g_err = msg ? msg : ""; }   // lexical.cpp (hidden visibility)
-
 RLR_EXPORT int rlr_abi_version(void) { return RLR_ABI_VERSION; }
 RLR_EXPORT const char *rlr_last_error(void) { return g_err.c_str(); }
 

@@ -482,14 +482,14 @@ LexicalFn = Callable[[str, int], List[Tuple[str, float]]]
 
 
 class LexicalIndex:
-    """LexicalIndex (src/rag_engine.rs:2083-2231) over the library's host-side BM25 index
-    (rlr_lexical_*): chunk ids are mapped to u64 keys in insertion order, which is also the
+    """LexicalIndex (src/rag_engine.rs:2083-2231) over the host-mirror support library's BM25 twin
+    (librlr_hostmirror.so, rlr_lexical_*; NOT part of the product library): chunk ids are mapped to u64 keys in insertion order, which is also the
     tie order of equal scores."""
 
     def __init__(self):
-        self._lib = B.load()
+        self._lib = B.load_hostmirror()
         self._h = C.c_void_p()
-        B.check(self._lib.rlr_lexical_create(C.byref(self._h)))
+        B.check_hm(self._lib.rlr_lexical_create(C.byref(self._h)))
         self._key_of, self._id_of, self._next = {}, {}, 0
 
     def add_chunk(self, chunk_id: str, text: str) -> None:
@@ -500,27 +500,27 @@ class LexicalIndex:
             self._key_of[chunk_id] = key
             self._id_of[key] = chunk_id
         b = text.encode("utf-8")
-        B.check(self._lib.rlr_lexical_add_chunk(self._h, key, b, len(b)))
+        B.check_hm(self._lib.rlr_lexical_add_chunk(self._h, key, b, len(b)))
 
     def remove_chunk(self, chunk_id: str) -> None:
         key = self._key_of.pop(chunk_id, None)
         if key is not None:
             self._id_of.pop(key, None)
-            B.check(self._lib.rlr_lexical_remove_chunk(self._h, key))
+            B.check_hm(self._lib.rlr_lexical_remove_chunk(self._h, key))
 
     def contains(self, chunk_id: str) -> bool:
         key = self._key_of.get(chunk_id)
         if key is None:
             return False
         out = C.c_int(0)
-        B.check(self._lib.rlr_lexical_contains(self._h, key, C.byref(out)))
+        B.check_hm(self._lib.rlr_lexical_contains(self._h, key, C.byref(out)))
         return bool(out.value)
 
     def score(self, query: str, limit: int) -> List[Tuple[str, float]]:
         b = query.encode("utf-8")
         cap = max(int(limit), 1) if limit > 0 else max(len(self._key_of), 1)
         keys, scores, n = np.zeros(cap, np.uint64), np.zeros(cap, np.float32), C.c_uint32(0)
-        B.check(self._lib.rlr_lexical_score(self._h, b, len(b), int(limit), B.ptr(keys), B.ptr(scores), cap, C.byref(n)))
+        B.check_hm(self._lib.rlr_lexical_score(self._h, b, len(b), int(limit), B.ptr(keys), B.ptr(scores), cap, C.byref(n)))
         return [(self._id_of[int(k)], float(s)) for k, s in zip(keys[:n.value], scores[:n.value])]
 
     def __call__(self, query: str, limit: int) -> List[Tuple[str, float]]:

@@ -1,23 +1,26 @@
-// lexical.cpp -- host-side BM25 index: the LexicalIndex the hot path blends with
-// (/root/reference/src/rag_engine.rs:2083-2247; consumed by RagEngine::search :505-532).
+// lexical.cpp -- HOST-MIRROR SUPPORT, not part of the product library: a C++ twin of the reference's
+// LexicalIndex (BM25) and tokenizer, /root/reference/src/rag_engine.rs:2083-2247, built into its own
+// librlr_hostmirror.so (plain g++, no CUDA).
 //
-// SURVEY.md 8(f) N4.  The reference keeps this index on the host (string/hash work) and so does
-// this build: the scan kernel takes its OUTPUT (<= 5*top_k (row, score) pairs) and blends it
-// in-kernel.  A maintainer's Rust glue keeps using the reference's own LexicalIndex; this C++
-// twin exists so that the host mirrors shipped here (include/rlr_engine.hpp,
-// rust-local-rag_b200/engine.py) reproduce `search` on real chunk text, not only on embeddings.
+// SURVEY.md section 2 row 7 marks LexicalIndex OUT OF SCOPE (host string/hash work) and 8(f) N4 (scoring the
+// postings on the device) is DECLINED -- DESIGN.md section 8 has the measurement behind that decision.  A Rust
+// maintainer keeps using the reference's own LexicalIndex and hands its <= 5*top_k (row, score) pairs to
+// rlr_search_topm / rlr_search_mmr / rlr_cluster_*, which blend them on the device.  This twin exists only so
+// that the NON-Rust host mirrors shipped here (include/rlr_engine.hpp, rust-local-rag_b200/engine.py) can answer
+// text queries in their tests; nothing in librlr_b200.so depends on it.
 //
-// Fidelity notes (all stated in DESIGN.md):
-//  * arithmetic: f32 throughout, the reference's operation order (:2193-2219); ln is the C
-//    library's logf, which is what Rust's f32::ln calls on Linux.
-//  * the reference sums a document's per-term scores in HashSet iteration order (random per
-//    process, :2194) and sorts ties in HashMap order (:2222-2223): its output is only defined up
-//    to f32 summation order and tie order.  This twin is deterministic: terms in bytewise order,
-//    ties by ascending chunk key -- one of the reference's valid outcomes.
-//  * tokenize (:2242-2247): split on !char::is_alphanumeric, keep tokens of >= 3 BYTES, lowercase.
-//    ASCII, Latin-1, Latin Extended-A, Greek and Cyrillic are classified and case-folded like
-//    Rust does; other non-ASCII code points are treated as letters without case mapping, except
-//    the punctuation/symbol blocks listed in is_alnum_cp (an approximation of the Unicode tables).
+// Fidelity notes:
+//  * arithmetic: f32 throughout, the reference's operation order (:2193-2219); ln is the C library's logf,
+//    which is what Rust's f32::ln calls on Linux.
+//  * the reference sums a document's per-term scores in HashSet iteration order (random per process, :2194)
+//    and sorts ties in HashMap order (:2222-2223): its output is only defined up to f32 summation order and
+//    tie order.  This twin is deterministic: terms in bytewise order, ties by ascending chunk key -- one of
+//    the reference's valid outcomes.
+//  * tokenize (:2242-2247): split on !char::is_alphanumeric, keep tokens of >= 3 BYTES, str::to_lowercase.
+//    Classification (Alphabetic | Nd | Nl | No) and the full lowercase mapping, U+0130's two-code-point
+//    mapping and the Final_Sigma rule included, come from GENERATED Unicode tables (unicode_tables.inc,
+//    tools/gen_unicode_tables.py; tests/test_lexical_cpu.py checks every code point up to U+10FFFF against
+//    the generating databases).  The Unicode versions are recorded in the generated file; Rust 1.88 ships 16.0.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -27,68 +30,40 @@
 #include <unordered_map>
 #include <vector>
 
-#include "../../include/rlr_b200.h"
+#include "../../include/rlr_hostmirror.h"
 
 #define RLR_EXPORT extern "C" __attribute__((visibility("default")))
 
 namespace {
 
+#include "unicode_tables.inc"
+
+template <size_t N>
+bool in_ranges(const uint32_t (&t)[N][2], uint32_t c)
+{
+    size_t lo = 0, hi = N;                       // first range whose end is >= c
+    while (lo < hi) { const size_t mid = (lo + hi) / 2; if (t[mid][1] < c) lo = mid + 1; else hi = mid; }
+    return lo < N && t[lo][0] <= c;
+}
+
 bool is_alnum_cp(uint32_t c)
 {
     if (c < 0x80) return (c >= '0' && c <= '9') || (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z');
-    if (c < 0xC0) return c == 0xAA || c == 0xB2 || c == 0xB3 || c == 0xB5 || c == 0xB9 || c == 0xBA || (c >= 0xBC && c <= 0xBE);
-    if (c == 0xD7 || c == 0xF7) return false;
-    if (c >= 0x02C2 && c <= 0x02C5) return false;
-    if (c >= 0x02D2 && c <= 0x02DF) return false;
-    if (c >= 0x0300 && c <= 0x036F) return c == 0x0345;             // combining marks (only ypogegrammeni is Alphabetic)
-    if (c == 0x037E || c == 0x0387 || c == 0x0482) return false;
-    if (c >= 0x2000 && c <= 0x206F) return false;                   // general punctuation
-    if (c >= 0x20A0 && c <= 0x20FF) return false;                   // currency, combining marks for symbols
-    if (c >= 0x2100 && c <= 0x214F)                                  // letterlike symbols: the Alphabetic ones only
-        return c == 0x2102 || c == 0x2107 || (c >= 0x210A && c <= 0x2113) || c == 0x2115 || (c >= 0x2119 && c <= 0x211D) ||
-               c == 0x2124 || c == 0x2126 || c == 0x2128 || (c >= 0x212A && c <= 0x212D) || (c >= 0x212F && c <= 0x2139) ||
-               (c >= 0x213C && c <= 0x213F) || (c >= 0x2145 && c <= 0x2149) || c == 0x214E;
-    if (c >= 0x2190 && c <= 0x245F) return false;                   // arrows, math, technical, control pictures, OCR
-    if (c >= 0x2500 && c <= 0x2BFF) return (c >= 0x2776 && c <= 0x2793);   // box drawing .. misc symbols (dingbat digits are No)
-    if (c >= 0x2E00 && c <= 0x2E7F) return c == 0x2E2F;             // supplemental punctuation
-    if (c >= 0x3000 && c <= 0x303F) return (c >= 0x3005 && c <= 0x3007) || (c >= 0x3021 && c <= 0x3029) || (c >= 0x3031 && c <= 0x3035) || (c >= 0x3038 && c <= 0x303C);
-    if (c >= 0xE000 && c <= 0xF8FF) return false;                   // private use
-    if (c >= 0xFE10 && c <= 0xFE6F) return false;                   // vertical forms, small form variants
-    if (c >= 0xFF01 && c <= 0xFF0F) return false;
-    if (c >= 0xFF1A && c <= 0xFF20) return false;
-    if (c >= 0xFF3B && c <= 0xFF40) return false;
-    if (c >= 0xFF5B && c <= 0xFF65) return false;
-    if (c >= 0xFFE0) return false;
-    return true;
+    return in_ranges(kAlnum, c);
 }
+bool is_cased_cp(uint32_t c) { return in_ranges(kCased, c); }
+bool is_case_ignorable_cp(uint32_t c) { return in_ranges(kCaseIgnorable, c); }
 
-uint32_t lower_cp(uint32_t c)
+// full lowercase mapping of one code point: writes 1..3 code points, returns how many
+uint32_t lower_cp(uint32_t c, uint32_t out[3])
 {
-    if (c < 0x80) return (c >= 'A' && c <= 'Z') ? c + 32 : c;
-    if (c >= 0xC0 && c <= 0xDE && c != 0xD7) return c + 32;
-    if (c >= 0x0100 && c <= 0x017F) {
-        if (c == 0x0130) return c;                                  // I with dot: multi-char mapping in Rust; left as is
-        if (c == 0x0178) return 0xFF;
-        if ((c >= 0x0139 && c <= 0x0148) || (c >= 0x0179 && c <= 0x017E)) return (c & 1) ? c + 1 : c;
-        if (c == 0x0138 || c == 0x0149 || c == 0x017F) return c;
-        return (c & 1) ? c : c + 1;
-    }
-    if (c >= 0x0391 && c <= 0x03A9 && c != 0x03A2) return c + 32;   // (Rust maps a word-final sigma contextually; not reproduced)
-    if (c >= 0x0386 && c <= 0x038F) {
-        if (c == 0x0386) return 0x03AC;
-        if (c >= 0x0388 && c <= 0x038A) return c + 37;
-        if (c == 0x038C) return 0x03CC;
-        if (c == 0x038E || c == 0x038F) return c + 63;
-        return c;
-    }
-    if (c >= 0x0400 && c <= 0x040F) return c + 80;
-    if (c >= 0x0410 && c <= 0x042F) return c + 32;
-    if (c >= 0x0460 && c <= 0x0481) return (c & 1) ? c : c + 1;
-    if (c >= 0x048A && c <= 0x04BF) return (c & 1) ? c : c + 1;
-    if (c >= 0x1E00 && c <= 0x1E95) return (c & 1) ? c : c + 1;     // Latin Extended Additional
-    if (c >= 0x1EA0 && c <= 0x1EFF) return (c & 1) ? c : c + 1;
-    if (c >= 0xFF21 && c <= 0xFF3A) return c + 32;                  // fullwidth Latin
-    return c;
+    if (c < 0x80) { out[0] = (c >= 'A' && c <= 'Z') ? c + 32 : c; return 1; }
+    const size_t n = sizeof(kLower) / sizeof(kLower[0]);
+    size_t lo = 0, hi = n;
+    while (lo < hi) { const size_t mid = (lo + hi) / 2; if (kLower[mid].cp < c) lo = mid + 1; else hi = mid; }
+    if (lo < n && kLower[lo].cp == c) { for (uint32_t i = 0; i < kLower[lo].n; ++i) out[i] = kLower[lo].to[i]; return kLower[lo].n; }
+    out[0] = c;
+    return 1;
 }
 
 void append_utf8(std::string &s, uint32_t c)
@@ -99,14 +74,36 @@ void append_utf8(std::string &s, uint32_t c)
     else { s.push_back(static_cast<char>(0xF0 | (c >> 18))); s.push_back(static_cast<char>(0x80 | ((c >> 12) & 0x3F))); s.push_back(static_cast<char>(0x80 | ((c >> 6) & 0x3F))); s.push_back(static_cast<char>(0x80 | (c & 0x3F))); }
 }
 
+// str::to_lowercase of one token (a run of alphanumeric code points): full mapping per code point, and
+// U+03A3 -> U+03C2 where Final_Sigma holds: preceded by a cased letter (skipping case-ignorable ones) and not
+// followed by one (library/alloc/src/str.rs: map_uppercase_sigma / case_ignorable_then_cased).
+std::string lowercase_token(const std::vector<uint32_t> &cps)
+{
+    std::string out;
+    for (size_t i = 0; i < cps.size(); ++i) {
+        const uint32_t c = cps[i];
+        if (c == 0x03A3) {
+            bool before = false, after = false;
+            for (size_t j = i; j-- > 0;) { if (is_case_ignorable_cp(cps[j])) continue; before = is_cased_cp(cps[j]); break; }
+            for (size_t j = i + 1; j < cps.size(); ++j) { if (is_case_ignorable_cp(cps[j])) continue; after = is_cased_cp(cps[j]); break; }
+            append_utf8(out, before && !after ? 0x03C2 : 0x03C3);
+            continue;
+        }
+        uint32_t lo[3];
+        const uint32_t n = lower_cp(c, lo);
+        for (uint32_t k = 0; k < n; ++k) append_utf8(out, lo[k]);
+    }
+    return out;
+}
+
 // fn tokenize, :2242-2247
 std::vector<std::string> tokenize(const char *text, size_t len)
 {
     std::vector<std::string> out;
-    std::string cur;
+    std::vector<uint32_t> cur;
     size_t cur_bytes = 0;                       // byte length of the ORIGINAL token (the filter runs before to_lowercase)
     auto flush = [&] {
-        if (cur_bytes >= 3) out.push_back(cur);
+        if (cur_bytes >= 3) out.push_back(lowercase_token(cur));
         cur.clear();
         cur_bytes = 0;
     };
@@ -120,7 +117,7 @@ std::vector<std::string> tokenize(const char *text, size_t len)
         else if ((b >> 4) == 14 && i + 2 < len) { c = ((b & 0x0Fu) << 12) | ((static_cast<unsigned char>(text[i + 1]) & 0x3Fu) << 6) | (static_cast<unsigned char>(text[i + 2]) & 0x3Fu); n = 3; }
         else if ((b >> 3) == 30 && i + 3 < len) { c = ((b & 0x07u) << 18) | ((static_cast<unsigned char>(text[i + 1]) & 0x3Fu) << 12) | ((static_cast<unsigned char>(text[i + 2]) & 0x3Fu) << 6) | (static_cast<unsigned char>(text[i + 3]) & 0x3Fu); n = 4; }
         else { c = 0xFFFD; n = 1; }             // invalid byte: a separator (Rust strings cannot hold it)
-        if (c != 0xFFFD && is_alnum_cp(c)) { append_utf8(cur, lower_cp(c)); cur_bytes += n; }
+        if (c != 0xFFFD && is_alnum_cp(c)) { cur.push_back(c); cur_bytes += n; }
         else flush();
         i += n;
     }
@@ -231,85 +228,99 @@ struct rlr_lexical {
     }
 };
 
-extern "C" void rlr_internal_set_error(const char *msg);   // api.cu: the thread-local message behind rlr_last_error()
-
 namespace {
+thread_local std::string g_hm_err;
 int lex_fail(int code, const char *msg)
 {
-    rlr_internal_set_error(msg);
+    g_hm_err = msg;
     return code;
 }
 } // namespace
 
+RLR_EXPORT const char *rlr_hostmirror_last_error(void) { return g_hm_err.c_str(); }
+
+// test hook: bit 0 of out[cp] = is_alphanumeric(cp); lower[3*cp ..] = its full lowercase mapping (0-padded)
+RLR_EXPORT int rlr_hostmirror_unicode_dump(uint8_t *out_alnum, uint32_t *out_lower, uint32_t n_cp)
+{
+    if (!out_alnum || !out_lower) return lex_fail(RLR_HM_ERR_INVALID_ARG, "NULL argument");
+    for (uint32_t c = 0; c < n_cp; ++c) {
+        out_alnum[c] = is_alnum_cp(c) ? 1 : 0;
+        uint32_t lo[3] = {0, 0, 0};
+        lower_cp(c, lo);
+        out_lower[3 * c] = lo[0]; out_lower[3 * c + 1] = lo[1]; out_lower[3 * c + 2] = lo[2];
+    }
+    return RLR_HM_OK;
+}
+
 RLR_EXPORT int rlr_lexical_create(rlr_lexical **out)
 {
-    if (!out) return lex_fail(RLR_ERR_INVALID_ARG, "out is NULL");
+    if (!out) return lex_fail(RLR_HM_ERR_INVALID_ARG, "out is NULL");
     *out = new rlr_lexical();
-    return RLR_OK;
+    return RLR_HM_OK;
 }
 
 RLR_EXPORT int rlr_lexical_destroy(rlr_lexical *lx)
 {
     delete lx;
-    return RLR_OK;
+    return RLR_HM_OK;
 }
 
 RLR_EXPORT int rlr_lexical_add_chunk(rlr_lexical *lx, uint64_t chunk_key, const char *text, size_t len)
 {
-    if (!lx || (!text && len)) return lex_fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    if (!lx || (!text && len)) return lex_fail(RLR_HM_ERR_INVALID_ARG, "NULL argument");
     lx->add_chunk(chunk_key, text ? text : "", len);
-    return RLR_OK;
+    return RLR_HM_OK;
 }
 
 RLR_EXPORT int rlr_lexical_remove_chunk(rlr_lexical *lx, uint64_t chunk_key)
 {
-    if (!lx) return lex_fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    if (!lx) return lex_fail(RLR_HM_ERR_INVALID_ARG, "NULL argument");
     lx->remove_chunk(chunk_key);
-    return RLR_OK;
+    return RLR_HM_OK;
 }
 
 RLR_EXPORT int rlr_lexical_contains(const rlr_lexical *lx, uint64_t chunk_key, int *out)
 {
-    if (!lx || !out) return lex_fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    if (!lx || !out) return lex_fail(RLR_HM_ERR_INVALID_ARG, "NULL argument");
     *out = lx->doc_terms.count(chunk_key) ? 1 : 0;      // :2229-2231
-    return RLR_OK;
+    return RLR_HM_OK;
 }
 
 RLR_EXPORT int rlr_lexical_stats(const rlr_lexical *lx, uint64_t *total_docs, uint64_t *total_length, uint64_t *n_terms)
 {
-    if (!lx) return lex_fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    if (!lx) return lex_fail(RLR_HM_ERR_INVALID_ARG, "NULL argument");
     if (total_docs) *total_docs = lx->total_docs;
     if (total_length) *total_length = lx->total_length;
     if (n_terms) *n_terms = lx->term_postings.size();
-    return RLR_OK;
+    return RLR_HM_OK;
 }
 
 RLR_EXPORT int rlr_lexical_score(const rlr_lexical *lx, const char *query, size_t len, uint32_t limit, uint64_t *out_keys,
                                  float *out_scores, uint32_t cap, uint32_t *out_n)
 {
-    if (!lx || (!query && len) || !out_n) return lex_fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    if (!lx || (!query && len) || !out_n) return lex_fail(RLR_HM_ERR_INVALID_ARG, "NULL argument");
     const auto r = lx->score(query ? query : "", len, limit);
     const uint32_t n = static_cast<uint32_t>(std::min<size_t>(r.size(), cap));
-    if (n && (!out_keys || !out_scores)) return lex_fail(RLR_ERR_INVALID_ARG, "output buffers are NULL");
+    if (n && (!out_keys || !out_scores)) return lex_fail(RLR_HM_ERR_INVALID_ARG, "output buffers are NULL");
     for (uint32_t i = 0; i < n; ++i) { out_keys[i] = r[i].first; out_scores[i] = r[i].second; }
     *out_n = n;
-    if (r.size() > cap) return lex_fail(RLR_ERR_UNSUPPORTED, "output capacity too small for the result (pass cap >= limit)");
-    return RLR_OK;
+    if (r.size() > cap) return lex_fail(RLR_HM_ERR_UNSUPPORTED, "output capacity too small for the result (pass cap >= limit)");
+    return RLR_HM_OK;
 }
 
 RLR_EXPORT int rlr_tokenize(const char *text, size_t len, char *out, size_t out_cap, size_t *out_len, uint32_t *out_tokens)
 {
     // tokens joined by '\n' (a separator no token can contain)
-    if ((!text && len) || !out_len) return lex_fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    if ((!text && len) || !out_len) return lex_fail(RLR_HM_ERR_INVALID_ARG, "NULL argument");
     const auto toks = tokenize(text ? text : "", len);
     std::string joined;
     for (size_t i = 0; i < toks.size(); ++i) { if (i) joined.push_back('\n'); joined += toks[i]; }
     *out_len = joined.size();
     if (out_tokens) *out_tokens = static_cast<uint32_t>(toks.size());
-    if (joined.size() > out_cap) return lex_fail(RLR_ERR_UNSUPPORTED, "output capacity too small");
+    if (joined.size() > out_cap) return lex_fail(RLR_HM_ERR_UNSUPPORTED, "output capacity too small");
     if (!joined.empty()) {
-        if (!out) return lex_fail(RLR_ERR_INVALID_ARG, "out is NULL");
+        if (!out) return lex_fail(RLR_HM_ERR_INVALID_ARG, "out is NULL");
         memcpy(out, joined.data(), joined.size());
     }
-    return RLR_OK;
+    return RLR_HM_OK;
 }

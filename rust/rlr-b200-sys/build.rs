@@ -8,7 +8,7 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let lib = out.join("librlr_b200.so");
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
-    let sources = ["api.cu", "cluster.cu", "scan_topm.cu", "merge.cu", "mmr.cu", "synth.cu", "batch_gemm.cu", "lexical.cpp"];
+    let sources = ["api.cu", "cluster.cu", "scan_topm.cu", "merge.cu", "mmr.cu", "synth.cu", "batch_gemm.cu"];
     let status = Command::new(&nvcc)
         .current_dir(&csrc)
         .args(["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false"])

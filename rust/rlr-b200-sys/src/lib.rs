@@ -35,7 +35,6 @@ pub const RLR_MAX_SHARDS: usize = 16;
 #[repr(C)] pub struct rlr_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct rlr_peer_set { _p: [u8; 0] }
 #[repr(C)] pub struct rlr_mailbox { _p: [u8; 0] }
-#[repr(C)] pub struct rlr_lexical { _p: [u8; 0] }
 #[repr(C)] pub struct rlr_cluster { _p: [u8; 0] }
 
 #[repr(C)] #[derive(Clone, Copy, Default)]
@@ -76,14 +75,6 @@ extern "C" {
     pub fn rlr_search_batch(s: *mut rlr_store, queries: *const f32, n_queries: u32, dim: u32, flags: u32, m: u32, out_rows: *mut u32, out_scores: *mut f32, out_n: *mut u32) -> c_int;
     pub fn rlr_search_batch_device(s: *mut rlr_store, queries: *const f32, n_queries: u32, dim: u32, flags: u32, m: u32, d_keys: *mut c_void, d_cnt: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn rlr_batch_merge_async(s: *mut rlr_store, d_lists: *const c_void, n_lists: u32, n_queries: u32, m: u32, d_out_keys: *mut c_void, d_out_cnt: *mut c_void, stream: *mut c_void) -> c_int;
-    pub fn rlr_lexical_create(out: *mut *mut rlr_lexical) -> c_int;
-    pub fn rlr_lexical_destroy(lx: *mut rlr_lexical) -> c_int;
-    pub fn rlr_lexical_add_chunk(lx: *mut rlr_lexical, chunk_key: u64, text_utf8: *const c_char, len: usize) -> c_int;
-    pub fn rlr_lexical_remove_chunk(lx: *mut rlr_lexical, chunk_key: u64) -> c_int;
-    pub fn rlr_lexical_contains(lx: *const rlr_lexical, chunk_key: u64, out: *mut c_int) -> c_int;
-    pub fn rlr_lexical_stats(lx: *const rlr_lexical, total_docs: *mut u64, total_length: *mut u64, n_terms: *mut u64) -> c_int;
-    pub fn rlr_lexical_score(lx: *const rlr_lexical, query_utf8: *const c_char, len: usize, limit: u32, out_keys: *mut u64, out_scores: *mut f32, cap: u32, out_n: *mut u32) -> c_int;
-    pub fn rlr_tokenize(text_utf8: *const c_char, len: usize, out: *mut c_char, out_cap: usize, out_len: *mut usize, out_tokens: *mut u32) -> c_int;
     pub fn rlr_last_timings(out: *mut rlr_timings) -> c_int;
     pub fn rlr_cluster_create(devices: *const c_int, n_devices: u32, dim: u32, n_rows: u64, rows: *const f32, host_pitch: u64, flags: u32, shard_rows: *const u64, out: *mut *mut rlr_cluster) -> c_int;
     pub fn rlr_cluster_destroy(c: *mut rlr_cluster) -> c_int;

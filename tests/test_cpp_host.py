@@ -16,9 +16,10 @@ def _build_cli(tmp_path):
     import rust_local_rag_b200  # noqa: F401
     from rust_local_rag_b200 import _build
     _build.build()
+    _build.build_hostmirror()
     exe = os.path.join(tmp_path, "engine_cli")
     cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "cpp", "engine_cli.cpp"),
-           "-L" + PKG, "-l:librlr_b200.so", "-Wl,-rpath," + PKG]
+           "-L" + PKG, "-l:librlr_b200.so", "-l:librlr_hostmirror.so", "-Wl,-rpath," + PKG]
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
     return exe
