@@ -109,8 +109,18 @@ typedef struct rlr_timings {
                                             * device (same sequential arithmetic, same bits): bulk loads need not
                                             * normalise 10M rows on one host core (apply_loaded_state, :1678-1680) */
 #define RLR_STORE_F16_ONLY      0x4u  /* keep only the binary16 copy (half the HBM, config 5) */
+#define RLR_STORE_NO_LATENCY_PATH 0x20u /* never take the small-store latency path (below): always the copy + launch
+                                         sequence + stream synchronisation that large stores use */
 #define RLR_STORE_KEEP_BF16     0x10u /* keep the f32 rows AND a bfloat16 copy (operand of rlr_search_batch with
                                          RLR_BATCH_BF16; the single-query paths never read it)  */
+
+/* Small stores (<= 262,144 rows of <= 1024 dims, f32 -- the reference's real operating point, BASELINE configs[0]) are
+ * served on a LATENCY PATH by rlr_search_topm / rlr_search_mmr / rlr_embedding_candidates: the normalised query and
+ * the lexical pairs travel in the kernel's parameter block (no H2D copy), rows are tiled so that every SM gets work,
+ * for pools <= 32 the scan's last CTA runs merge + pairwise + greedy MMR itself (ONE launch per request), and the
+ * result lands in mapped pinned host memory followed by a system-scope flag that the host polls (no D2H copy, no
+ * cudaStreamSynchronize).  Same arithmetic, same bits.  RLR_NO_LATENCY_PATH=1 in the environment or
+ * RLR_STORE_NO_LATENCY_PATH on the store turn it off. */
 
 /* search flags */
 #define RLR_QUERY_PRENORMALIZED 0x1u  /* skip the normalize(&mut q) of :494                */

@@ -30,6 +30,7 @@ RLR_BATCH_F16 = 0x10
 RLR_BATCH_BF16 = 0x20
 RLR_BATCH_TF32 = 0x40
 RLR_STORE_KEEP_BF16 = 0x10
+RLR_STORE_NO_LATENCY_PATH = 0x20
 RLR_IPC_HANDLE_BYTES = 64
 RLR_SYNTH_IID = 0
 RLR_SYNTH_CLUSTERED = 1

@@ -168,13 +168,16 @@ int rlr_api::ctx_new(rlr_store *s, rlr_ctx **out)
     CTX_TRY(cudaMalloc(&c->d_tmp, (static_cast<size_t>(c->n_lists_cap) + 3) * RLR_MAX_M * sizeof(rlr_cand)));
     // (count, records) pairs live in one block each -- [u32 n | pad to 16 B | records] -- so that ONE D2H
     // copy brings back a result and its length
+    memset(&c->lat, 0, sizeof c->lat);
     CTX_TRY(cudaMalloc(&c->d_pool_blk, 16 + RLR_MAX_M * sizeof(rlr_cand)));
+    CTX_TRY(cudaMemset(c->d_pool_blk, 0, 16));
     c->d_pool_n = reinterpret_cast<uint32_t *>(c->d_pool_blk);
     c->d_pool = reinterpret_cast<rlr_cand *>(c->d_pool_blk + 16);
     CTX_TRY(cudaMalloc(&c->d_tri, static_cast<size_t>(RLR_MAX_M) * (RLR_MAX_M - 1) / 2 * sizeof(float)));
     CTX_TRY(cudaMalloc(&c->d_gather, static_cast<size_t>(RLR_MAX_M) * s->pitch * sizeof(float)));
     CTX_TRY(cudaMalloc(&c->d_sel_pos, RLR_MAX_M * sizeof(uint32_t)));
     CTX_TRY(cudaMalloc(&c->d_result_blk, 16 + RLR_MAX_M * sizeof(rlr_cand)));
+    CTX_TRY(cudaMemset(c->d_result_blk, 0, 16));
     c->d_sel_n = reinterpret_cast<uint32_t *>(c->d_result_blk);
     c->d_result = reinterpret_cast<rlr_cand *>(c->d_result_blk + 16);
     CTX_TRY(cudaMalloc(&c->d_rows_in, RLR_MAX_M * sizeof(uint32_t)));
@@ -185,6 +188,7 @@ int rlr_api::ctx_new(rlr_store *s, rlr_ctx **out)
     CTX_TRY(cudaMallocHost(&c->h_lex_rows, kLexCap * sizeof(uint32_t)));
     CTX_TRY(cudaMallocHost(&c->h_lex_norm, kLexCap * sizeof(float)));
     CTX_TRY(cudaMallocHost(&c->h_result_blk, 16 + RLR_MAX_M * sizeof(rlr_cand)));
+    memset(c->h_result_blk, 0, 16);
     c->h_result_n = reinterpret_cast<uint32_t *>(c->h_result_blk);
     c->h_result = reinterpret_cast<rlr_cand *>(c->h_result_blk + 16);
     CTX_TRY(cudaMallocHost(&c->h_u32, (RLR_MAX_M + 8) * sizeof(uint32_t)));
@@ -405,14 +409,14 @@ RLR_EXPORT int rlr_resolve_weights(const rlr_query_weights *o, rlr_resolved_weig
 namespace {
 
 // dtype: 0 f32, 1 binary16, 2 bfloat16
-int make_tmap(CUtensorMap *map, void *base, int dtype, uint32_t pitch_elems, uint64_t n_rows)
+int make_tmap(CUtensorMap *map, void *base, int dtype, uint32_t pitch_elems, uint64_t n_rows, uint32_t box_rows = rlr::kScanRows)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return fail(RLR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     const uint32_t esz = dtype ? 2 : 4;
     const cuuint64_t gdim[2] = {pitch_elems, n_rows};
     const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(pitch_elems) * esz};
-    const cuuint32_t box[2] = {128u / esz, rlr::kScanRows};   // 128-byte box rows: the SWIZZLE_128B span
+    const cuuint32_t box[2] = {128u / esz, box_rows};          // 128-byte box rows: the SWIZZLE_128B span
     const cuuint32_t estr[2] = {1, 1};
     const CUtensorMapDataType dt = dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     CUresult r = enc(map, dt, 2, base, gdim, gstride,
@@ -458,6 +462,7 @@ RLR_EXPORT int rlr_store_create(int device, uint32_t dim, uint64_t n_rows, const
     memset(&s->tmap, 0, sizeof s->tmap);
     memset(&s->tmap16, 0, sizeof s->tmap16);
     memset(&s->tmap_bf16, 0, sizeof s->tmap_bf16);
+    memset(&s->tmap_small, 0, sizeof s->tmap_small);
     const bool want32 = !(flags & RLR_STORE_F16_ONLY);
     const bool want16 = flags & (RLR_STORE_F16_ONLY | RLR_STORE_KEEP_F16);
     if (n_rows) {
@@ -476,6 +481,8 @@ RLR_EXPORT int rlr_store_create(int device, uint32_t dim, uint64_t n_rows, const
         if (want32) rc = make_tmap(&s->tmap, s->d_rows, 0, s->pitch, n_rows);
         if (rc == RLR_OK && want16) rc = make_tmap(&s->tmap16, s->d_rows16, 1, s->pitch16, n_rows);
         if (rc == RLR_OK && s->d_rows_bf16) rc = make_tmap(&s->tmap_bf16, s->d_rows_bf16, 2, s->pitch16, n_rows);
+        s->rpt = rlr::scan_rows_per_tile(s->sm_count, n_rows);
+        if (rc == RLR_OK && want32 && s->rpt != rlr::kScanRows) rc = make_tmap(&s->tmap_small, s->d_rows, 0, s->pitch, n_rows, s->rpt);
         if (rc != RLR_OK) { cudaFree(s->d_rows); cudaFree(s->d_rows16); cudaFree(s->d_rows_bf16); delete s; return rc; }
     }
     *out = s;
@@ -599,6 +606,8 @@ int store_remap(rlr_store *s)
     if (s->d_rows) if (int rc = make_tmap(&s->tmap, s->d_rows, 0, s->pitch, s->n_rows)) return rc;
     if (s->d_rows16) if (int rc = make_tmap(&s->tmap16, s->d_rows16, 1, s->pitch16, s->n_rows)) return rc;
     if (s->d_rows_bf16) if (int rc = make_tmap(&s->tmap_bf16, s->d_rows_bf16, 2, s->pitch16, s->n_rows)) return rc;
+    s->rpt = rlr::scan_rows_per_tile(s->sm_count, s->n_rows);
+    if (s->d_rows && s->rpt != rlr::kScanRows) if (int rc = make_tmap(&s->tmap_small, s->d_rows, 0, s->pitch, s->n_rows, s->rpt)) return rc;
     return RLR_OK;
 }
 
@@ -728,6 +737,164 @@ RLR_EXPORT int rlr_store_fill_synthetic(rlr_store *s, int kind, uint64_t seed, u
 // ---------------------------------------------------------------------------------
 namespace {
 
+// ---- latency path (small stores; LatParams in kernels.cuh) ----
+constexpr uint64_t kLatMaxRows = 262144;     // beyond this the scan itself dominates and the regular path is as good
+
+bool lat_eligible(const rlr_store *s, uint32_t flags)
+{
+    static const bool off = getenv("RLR_NO_LATENCY_PATH") != nullptr;
+    return !off && !(s->flags & RLR_STORE_NO_LATENCY_PATH) && s->d_rows != nullptr && !s->use_half(flags) && s->pitch <= rlr::kLatQFloats && s->n_rows <= kLatMaxRows;
+}
+
+// query -> the parameter block: copy, NaN/Inf check, normalize (:494).  Floats beyond dim stay zero.
+int lat_stage_query(rlr_ctx *c, const float *query, uint32_t dim, uint32_t flags)
+{
+    rlr_store *s = c->s;
+    if (!query) return fail(RLR_ERR_INVALID_ARG, "query is NULL");
+    if (dim != s->dim)
+        return fail(RLR_ERR_DIM_MISMATCH, "query has %u dims, store has %u (the reference would silently truncate, "
+                    "src/rag_engine.rs:1778; this library refuses)", dim, s->dim);
+    memcpy(c->lat.q, query, dim * sizeof(float));
+    for (uint32_t i = 0; i < dim; ++i)
+        if (!std::isfinite(c->lat.q[i])) return fail(RLR_ERR_NONFINITE, "query[%u] is not finite", i);
+    if (!(flags & RLR_QUERY_PRENORMALIZED)) host_normalize(c->lat.q, dim);
+    return RLR_OK;
+}
+
+// :505-530 into the parameter block; *fits = false when there are more local pairs than the block holds
+int lat_stage_lex(rlr_ctx *c, const uint32_t *lex_rows, const float *lex_scores, uint32_t n_lex, uint32_t *out_n, bool *fits)
+{
+    rlr_store *s = c->s;
+    *out_n = 0; *fits = true;
+    if (n_lex == 0) return RLR_OK;
+    if (!lex_rows || !lex_scores) return fail(RLR_ERR_INVALID_ARG, "n_lex > 0 but lex_rows/lex_scores is NULL");
+    if (n_lex > kLexCap) return fail(RLR_ERR_UNSUPPORTED, "n_lex %u exceeds %u", n_lex, kLexCap);
+    float max_lexical = 0.0f;
+    for (uint32_t i = 0; i < n_lex; ++i) max_lexical = fmaxf(max_lexical, lex_scores[i]);
+    max_lexical = fmaxf(max_lexical, 1.1920929e-07f);
+    std::vector<std::pair<uint32_t, uint32_t>> order;
+    order.reserve(n_lex);
+    for (uint32_t i = 0; i < n_lex; ++i) {
+        const uint64_t g = lex_rows[i];
+        if (g < s->row_base || g - s->row_base >= s->n_rows) continue;
+        order.emplace_back(static_cast<uint32_t>(g - s->row_base), i);
+    }
+    std::stable_sort(order.begin(), order.end(),
+                     [](const std::pair<uint32_t, uint32_t> &a, const std::pair<uint32_t, uint32_t> &b) { return a.first < b.first; });
+    uint32_t n = 0;
+    for (size_t i = 0; i < order.size(); ++i) {
+        if (i + 1 < order.size() && order[i + 1].first == order[i].first) continue;
+        if (n == rlr::kLatLex) { *fits = false; return RLR_OK; }
+        c->lat.lex_rows[n] = order[i].first;
+        c->lat.lex_norm[n] = lex_scores[order[i].second] / max_lexical;
+        ++n;
+    }
+    *out_n = n;
+    return RLR_OK;
+}
+
+// Wait for the kernel's completion word in mapped pinned memory.  Polls the stream now and then so that a kernel
+// that died (or a launch that never ran) becomes an error instead of a hang.
+int lat_wait(rlr_ctx *c, cudaStream_t st)
+{
+    volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(c->h_result_blk + 8);
+    const unsigned long long seq = c->lat_seq;
+    for (uint32_t spins = 1;; ++spins) {
+        if (*flag == seq) break;
+        if ((spins & 0x1fffu) == 0) {
+            const cudaError_t e = cudaStreamQuery(st);
+            if (e == cudaSuccess) {
+                if (*flag == seq) break;
+                return fail(RLR_ERR_CUDA, "latency path: the kernels finished without delivering a result");
+            }
+            if (e != cudaErrorNotReady) { cudaGetLastError(); return fail(RLR_ERR_CUDA, "latency path: %s", cudaGetErrorString(e)); }
+        }
+        __builtin_ia32_pause();
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);     // the records were written before the flag (release, system scope)
+    return RLR_OK;
+}
+
+// One request on the latency path.  pool: records the scan delivers; do_mmr: diversify them to top_k.
+int lat_search(rlr_store *s, rlr_ctx *c, uint32_t flags, const rlr_resolved_weights *w, uint32_t n_lex, uint32_t pool, bool do_mmr,
+               uint32_t top_k, float lambda, uint32_t *out_rows, float *out_score, float *out_emb, float *out_lex, uint32_t *out_n)
+{
+    cudaStream_t st = c->stream;
+    const uint64_t launches0 = c->launches;
+    const bool timed = flags & RLR_WANT_TIMINGS;
+    rlr::LatParams &lp = c->lat;
+    rlr::ScanArgs a;
+    memset(&a, 0, sizeof a);
+    rlr::scan_plan_small(s->sm_count, s->smem_optin, static_cast<uint32_t>(s->n_rows), s->pitch, s->rpt, &a);
+    a.tmap = s->rpt == rlr::kScanRows ? &s->tmap : &s->tmap_small;
+    a.n_rows = static_cast<uint32_t>(s->n_rows);
+    a.row_base = static_cast<uint32_t>(s->row_base);
+    a.pitch = s->pitch;
+    a.w_embed = w->embedding; a.w_lex = w->lexical; a.n_lex = n_lex;
+    a.m = pool;
+    a.d_lists = c->d_lists; a.d_counts = c->d_counts; a.d_ticket = c->d_ticket; a.d_pub = c->d_pub;
+    a.lat = &lp;
+    const unsigned long long seq = ++c->lat_seq;
+    *reinterpret_cast<volatile unsigned long long *>(c->h_result_blk + 8) = 0;
+    lp.top_k = top_k; lp.lambda = lambda; lp.pitch = s->pitch; lp.g_rows = s->d_rows; lp.d_sel_pos = c->d_sel_pos;
+    lp.result = c->h_result; lp.result_n = c->h_result_n;          // mapped pinned memory (UVA: same pointers on the device)
+    lp.flag = reinterpret_cast<unsigned long long *>(c->h_result_blk + 8); lp.seq = seq;
+    const size_t ring_bytes = static_cast<size_t>(a.n_stages) * rlr::kScanChunks * rlr::kScanRows * 128;
+    const bool fuse = do_mmr && pool <= rlr::kLatFusePool && 4096 + static_cast<size_t>(pool) * (s->pitch * 4 + 16) <= ring_bytes;
+    uint32_t cap = pool;
+    if (timed) CU_TRY(cudaEventRecord(c->ev[0], st));
+    if (!do_mmr) {              // search(top_k): the merged list goes straight to the host
+        lp.mode = 1;
+        a.d_out = c->h_result; a.d_out_n = c->h_result_n;
+        CU_TRY(rlr::scan_launch(a, st));
+        ++c->launches;
+        if (timed) { CU_TRY(cudaEventRecord(c->ev[1], st)); CU_TRY(cudaEventRecord(c->ev[2], st)); }
+    } else if (fuse) {          // scan + merge + pairwise + greedy + delivery: ONE launch
+        lp.mode = 2;
+        a.d_out = c->d_pool; a.d_out_n = c->d_pool_n;
+        CU_TRY(rlr::scan_launch(a, st));
+        ++c->launches;
+        if (timed) { CU_TRY(cudaEventRecord(c->ev[1], st)); CU_TRY(cudaEventRecord(c->ev[2], st)); CU_TRY(cudaEventRecord(c->ev[3], st)); }
+        cap = std::min<uint32_t>(pool, std::max<uint32_t>(top_k, 1));
+    } else {                    // larger pools: the two MMR kernels follow; the greedy kernel delivers
+        lp.mode = 0;
+        a.d_out = c->d_pool; a.d_out_n = c->d_pool_n;
+        CU_TRY(rlr::scan_launch(a, st));
+        ++c->launches;
+        if (timed) { CU_TRY(cudaEventRecord(c->ev[1], st)); CU_TRY(cudaEventRecord(c->ev[2], st)); }
+        rlr::MmrArgs ma;
+        memset(&ma, 0, sizeof ma);
+        ma.half = 0;
+        ma.d_emb = s->d_rows; ma.pitch = s->pitch; ma.dim = s->dim;
+        ma.d_cands = c->d_pool; ma.d_n = c->d_pool_n;
+        ma.row_base = static_cast<uint32_t>(s->row_base); ma.use_rows = 1;
+        ma.p_cap = pool; ma.top_k = top_k; ma.lambda = lambda;
+        ma.d_tri = c->d_tri; ma.d_sel_pos = c->d_sel_pos; ma.d_sel_n = c->h_result_n; ma.d_result = c->h_result;
+        ma.max_smem_optin = s->smem_optin;
+        ma.done_flag = lp.flag; ma.done_seq = seq;
+        uint32_t l = 0;
+        CU_TRY(rlr::mmr_launch(ma, st, &l));
+        c->launches += l;
+        if (timed) CU_TRY(cudaEventRecord(c->ev[3], st));
+        cap = std::min<uint32_t>(pool, std::max<uint32_t>(top_k, 1));
+    }
+    if (int rc = lat_wait(c, st)) return rc;
+    const uint32_t n = std::min(c->h_result_n[0], cap);
+    unpack(c->h_result, n, out_rows, out_score, out_emb, out_lex);
+    *out_n = n;
+    if (timed) {
+        CU_TRY(cudaEventSynchronize(c->ev[do_mmr ? 3 : 2]));
+        rlr_timings t = {0, 0, 0, 0, 0};
+        cudaEventElapsedTime(&t.scan_ms, c->ev[0], c->ev[1]);
+        if (do_mmr) cudaEventElapsedTime(&t.mmr_ms, c->ev[2], c->ev[3]);
+        cudaEventElapsedTime(&t.total_ms, c->ev[0], c->ev[do_mmr ? 3 : 2]);
+        cudaGetLastError();
+        t.launches = static_cast<uint32_t>(c->launches - launches0);
+        g_timings = t;
+    }
+    return RLR_OK;
+}
+
 void timings_from_events(rlr_ctx *c, bool has_mmr)
 {
     rlr_timings t = {0, 0, 0, 0, 0};
@@ -760,10 +927,19 @@ RLR_EXPORT int rlr_search_topm(rlr_store *s, const float *query, uint32_t dim, u
     rlr_ctx *c = lease.c;
     cudaStream_t st = c->stream;
     const uint64_t launches0 = c->launches;
+    const uint32_t m_eff = static_cast<uint32_t>(std::min<uint64_t>(m, s->n_rows));
+    if (lat_eligible(s, flags)) {         // small store: one launch, no copies, no stream synchronisation
+        uint32_t nl_lat = 0;
+        bool fits = true;
+        if (int rc = lat_stage_lex(c, lex_rows, lex_scores, n_lex, &nl_lat, &fits)) return rc;
+        if (fits) {
+            if (int rc = lat_stage_query(c, query, dim, flags)) return rc;
+            return lat_search(s, c, flags, w, nl_lat, m_eff, false, 0, 0.0f, out_rows, out_combined, out_emb, out_lex, out_n);
+        }
+    }
     if (int rc = stage_query(c, query, dim, flags, st)) return rc;
     uint32_t nl = 0;
     if (int rc = stage_lex(c, lex_rows, lex_scores, n_lex, &nl, st)) return rc;
-    const uint32_t m_eff = static_cast<uint32_t>(std::min<uint64_t>(m, s->n_rows));
     const bool timed = flags & RLR_WANT_TIMINGS;
     if (timed) CU_TRY(cudaEventRecord(c->ev[0], st));
     if (int rc = enqueue_topm(c, c->d_query, w->embedding, w->lexical, c->d_lex_rows, c->d_lex_norm, nl, m_eff,
@@ -874,10 +1050,19 @@ RLR_EXPORT int rlr_search_mmr(rlr_store *s, const float *query, uint32_t dim, ui
     rlr_ctx *c = lease.c;
     cudaStream_t st = c->stream;
     const uint64_t launches0 = c->launches;
+    const uint32_t p = static_cast<uint32_t>(std::min<uint64_t>(pool, s->n_rows));
+    if (lat_eligible(s, flags)) {         // small store: one launch (pool <= 32) or three, no copies, no stream synchronisation
+        uint32_t nl_lat = 0;
+        bool fits = true;
+        if (int rc = lat_stage_lex(c, lex_rows, lex_scores, n_lex, &nl_lat, &fits)) return rc;
+        if (fits) {
+            if (int rc = lat_stage_query(c, query, dim, flags)) return rc;
+            return lat_search(s, c, flags, w, nl_lat, p, true, top_k, lambda, out_rows, out_score, out_emb, out_lex, out_n);
+        }
+    }
     if (int rc = stage_query(c, query, dim, flags, st)) return rc;
     uint32_t nl = 0;
     if (int rc = stage_lex(c, lex_rows, lex_scores, n_lex, &nl, st)) return rc;
-    const uint32_t p = static_cast<uint32_t>(std::min<uint64_t>(pool, s->n_rows));
     const bool timed = flags & RLR_WANT_TIMINGS;
     if (timed) CU_TRY(cudaEventRecord(c->ev[0], st));
     const bool half = s->use_half(flags);

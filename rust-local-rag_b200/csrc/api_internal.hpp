@@ -23,6 +23,8 @@ struct rlr_store {
     uint32_t pitch16 = 0;           // elements per binary16 row (dim rounded up to 64)
     void *d_rows_bf16 = nullptr;    // bfloat16 copy (RLR_STORE_KEEP_BF16): an operand of the batched contraction only
     CUtensorMap tmap, tmap16, tmap_bf16;
+    CUtensorMap tmap_small;         // f32 rows with `rpt`-row boxes: small stores spread their rows over every SM
+    uint32_t rpt = rlr::kScanRows;  // rows per scan tile on the latency path (scan_rows_per_tile)
     int sm_count = 0, smem_optin = 0;
     bool use_half(uint32_t flags) const { return d_rows == nullptr || ((flags & RLR_SEARCH_F16) && d_rows16 != nullptr); }
     std::mutex mu;
@@ -62,6 +64,8 @@ struct rlr_ctx {
     rlr_cand *h_result = nullptr;   // RLR_MAX_M records
     uint32_t *h_u32 = nullptr;      // RLR_MAX_M + 8 words
     float *h_rel = nullptr;
+    rlr::LatParams lat;             // latency path: the kernel's parameter block (query + lexical pairs + delivery)
+    unsigned long long lat_seq = 0; // completion sequence number of this ctx's mapped result block
     uint64_t launches = 0;
     uint32_t n_lists_cap = 0;
     uint32_t search_flags = 0;      // RLR_SEARCH_F16 for the device-level entry points

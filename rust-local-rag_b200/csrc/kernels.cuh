@@ -28,6 +28,30 @@ struct ScanPost {
     uint32_t *status;                    // local word, set non-zero if the wait timed out
 };
 
+// Latency path for small stores (BASELINE configs[0]: 10k chunks, top_k = 5 -- the reference's real operating
+// point): the WHOLE request is one kernel launch with no copy engine involved.  The normalised query (and the few
+// lexical pairs) travel in the kernel's parameter block, the last CTA runs merge + pairwise + greedy MMR itself when
+// the pool is small, and the result is written straight into mapped pinned host memory followed by a system-scope
+// flag that the host polls -- no H2D copy, no D2H copy, no cudaStreamSynchronize.
+constexpr uint32_t kLatQFloats = 1024;     // query floats a parameter block carries (pitch <= 1024)
+constexpr uint32_t kLatLex = 192;          // lexical pairs a parameter block carries (5 * pool for pool <= 32, rounded up)
+constexpr uint32_t kLatFusePool = 32;      // pools up to this size are diversified by the scan's last CTA itself
+struct LatParams {
+    float q[kLatQFloats];                  // normalised query, zero beyond dim
+    uint32_t lex_rows[kLatLex];            // sorted local rows
+    float lex_norm[kLatLex];
+    uint32_t mode;                         // 0: off (plain scan) | 1: deliver the merged top-m | 2: + fused MMR of the pool
+    uint32_t top_k;
+    float lambda;
+    uint32_t pitch;                        // floats per stored f32 row
+    const float *g_rows;                   // the store's f32 rows (pool rows are staged from here for the fused MMR)
+    uint32_t *d_sel_pos;                   // device scratch, >= kLatFusePool words
+    rlr_cand *result;                      // mapped pinned host memory (mode != 0): records ...
+    uint32_t *result_n;                    // ... count ...
+    unsigned long long *flag;              // ... and the completion word, which receives `seq` last (release, system scope)
+    unsigned long long seq;
+};
+
 struct ScanArgs {
     const CUtensorMap *tmap;   // host pointer; copied into the kernel's param space (f32 or f16 map)
     int half;                  // 1: the map describes the binary16 copy of the store
@@ -53,10 +77,18 @@ struct ScanArgs {
     uint32_t buf_cap;          // 0: derive from m
     unsigned long long *d_trace; // dev-only: phase timestamps (5*grid + 16 words) or null
     ScanPost post;             // zeroed: off
+    uint32_t rows_per_tile;    // 0 / kScanRows: 128-row tiles.  Small stores use fewer rows per tile (a multiple of 8, with
+                               // a tensor map whose box has that many rows) so that the rows spread over every SM
+    const LatParams *lat;      // host pointer or null: latency path (f32 stores only); d_query / d_lex_* are then ignored
 };
 
 // Pick grid / stages / smem for a store on a device.
 void scan_plan(int sm_count, int max_smem_optin, uint32_t n_rows, uint32_t pitch, int half, ScanArgs *a);
+// rows per tile for a store of n_rows on sm_count SMs: kScanRows for stores that fill every SM with 128-row tiles,
+// else the least multiple of 8 that gives every SM at most one tile
+uint32_t scan_rows_per_tile(int sm_count, uint64_t n_rows);
+// plan for the latency path: every SM, `rows_per_tile`-row tiles, room for the lexical pairs in shared memory
+void scan_plan_small(int sm_count, int max_smem_optin, uint32_t n_rows, uint32_t pitch, uint32_t rows_per_tile, ScanArgs *a);
 cudaError_t scan_configure(); // one-time cudaFuncSetAttribute
 cudaError_t scan_launch(const ScanArgs &a, cudaStream_t stream);
 
@@ -114,6 +146,8 @@ struct MmrArgs {
     rlr_cand *d_result;        // optional: selected records in selection order
     int max_smem_optin;
     const PeerTable *peers;    // optional (host pointer): candidate rows are global and live on these shards
+    unsigned long long *done_flag;   // optional: (mapped pinned) word that receives done_seq, system scope, after the
+    unsigned long long done_seq;     // result and count have been written -- the host polls it instead of synchronising
     void *d_gather;            // with peers: p_cap x pitch elements of scratch; the rows are gathered into it once (NVLink)
                                // and the pairwise kernel reads local memory.  null: the pairwise kernel loads from the peers itself
 };

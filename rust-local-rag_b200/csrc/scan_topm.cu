@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "sort_regs.cuh"
+#include "mmr_device.cuh"
 
 namespace rlr {
 
@@ -39,9 +40,9 @@ constexpr uint32_t kBoxBytes = R * 128;            // one TMA box: 128 rows x 12
 constexpr uint32_t kStageBytes = CH * kBoxBytes;
 
 struct SmemLayout {
-    uint32_t stages_off, q_off, keys_off, embs_off, bars_off, misc_off, total;
+    uint32_t stages_off, q_off, keys_off, embs_off, bars_off, misc_off, lex_off, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int n_stages, uint32_t q_floats)
+__host__ __device__ inline SmemLayout smem_layout(int n_stages, uint32_t q_floats, bool lat = false)
 {
     SmemLayout L;
     uint32_t o = 0;
@@ -51,21 +52,20 @@ __host__ __device__ inline SmemLayout smem_layout(int n_stages, uint32_t q_float
     L.embs_off = o;   o += kTopBuf * 4;
     L.bars_off = o;   o += n_stages * 16;
     L.misc_off = o;   o += 128;
+    L.lex_off = o;    o += lat ? kLatLex * 8 : 0;      // latency path: the lexical pairs of the parameter block
     L.total = o;
     return L;
 }
 
-__device__ __forceinline__ float lex_lookup(const uint32_t *__restrict__ rows, const float *__restrict__ vals,
-                                            uint32_t n, uint32_t row)
+__device__ __forceinline__ float lex_lookup(const uint32_t *rows, const float *vals, uint32_t n, uint32_t row)
 {
+    // plain loads: the arrays live in global memory, or in shared memory on the latency path
     uint32_t lo = 0, hi = n;
     while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
-        uint32_t r = __ldg(rows + mid);
-        if (r < row) lo = mid + 1; else hi = mid;
+        const uint32_t mid = (lo + hi) >> 1;
+        if (rows[mid] < row) lo = mid + 1; else hi = mid;
     }
-    if (lo < n && __ldg(rows + lo) == row) return __ldg(vals + lo);
-    return 0.0f;
+    return (lo < n && rows[lo] == row) ? vals[lo] : 0.0f;
 }
 
 __device__ __forceinline__ uint32_t next_pow2(uint32_t x)
@@ -132,8 +132,8 @@ __device__ __forceinline__ uint32_t extras_end(const rlr_cand *list, uint32_t c,
 //      value for the global m-th key, then gather exactly m records.
 __device__ void final_merge(uint64_t *keys, float *embs, uint32_t *s_counts, volatile uint32_t *s_cnt,
                             volatile uint32_t *s_aux, const rlr_cand *lists, const uint32_t *counts, uint32_t Ln,
-                            uint32_t m, uint32_t row_base, const uint32_t *__restrict__ lex_rows,
-                            const float *__restrict__ lex_norm, uint32_t n_lex, rlr_cand *__restrict__ out,
+                            uint32_t m, uint32_t row_base, const uint32_t *lex_rows,
+                            const float *lex_norm, uint32_t n_lex, rlr_cand *__restrict__ out,
                             uint32_t *__restrict__ out_n, uint32_t t, unsigned long long *tr)
 {
     // counts -> shared memory (one batched L2 round trip), total valid records
@@ -295,14 +295,22 @@ __device__ __forceinline__ void top_r_update_warp(const uint64_t *keys, uint32_t
 // kHalf: the store holds IEEE binary16 rows (64 elements per 128-byte box row).  Elements are
 // widened to f32 (exact) and accumulated in f32 in index order, i.e. the reference arithmetic
 // applied to the f16-rounded store.
-template <bool kHalf>
+struct NoLat { uint32_t unused; };
+template <bool kLat> struct LatSel { typedef NoLat type; };
+template <> struct LatSel<true> { typedef LatParams type; };
+
+// kLat: latency path for small f32 stores -- the query and the lexical pairs come from the parameter block `lp`
+// (no H2D copy), and the last CTA delivers the result into mapped pinned host memory (lp.mode, see LatParams).
+template <bool kHalf, bool kLat>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ g_query,
                  uint32_t n_rows, uint32_t row_base, uint32_t n_chunks, float w_embed, float w_lex,
-                 const uint32_t *__restrict__ lex_rows, const float *__restrict__ lex_norm, uint32_t n_lex,
+                 const uint32_t *g_lex_rows, const float *g_lex_norm, uint32_t n_lex,
                  uint32_t m, uint32_t buf_cap, uint32_t r_pub, int n_stages, rlr_cand *g_lists, uint32_t *g_counts,
                  uint32_t *g_pub, uint32_t *g_ticket, uint32_t *g_tile_ctr, rlr_cand *g_out, uint32_t *g_out_n,
-                 unsigned long long *g_trace /* dev-only phase timestamps, may be null */, const ScanPost post)
+                 unsigned long long *g_trace /* dev-only phase timestamps, may be null */, const ScanPost post,
+                 uint32_t rpt /* rows per tile: a multiple of 8, <= R; the tensor map's box has this many rows */,
+                 const __grid_constant__ typename LatSel<kLat>::type lp)
 {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B atoms are 1024 B: align the carve-up by hand.
@@ -313,7 +321,7 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
     constexpr uint32_t EPB = kHalf ? 64u : 32u;        // elements per 128-byte box row
     const uint32_t KB = (n_chunks + CH - 1) / CH;      // pipeline stages consumed per tile
     const uint32_t q_floats = KB * CH * EPB;
-    const SmemLayout L = smem_layout(n_stages, q_floats);
+    const SmemLayout L = smem_layout(n_stages, q_floats, kLat);
 
     float *q_s = reinterpret_cast<float *>(smem + L.q_off);
     uint64_t *keys = reinterpret_cast<uint64_t *>(smem + L.keys_off);
@@ -334,7 +342,15 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
 
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = tid >> 5, lane = tid & 31;
-    const uint32_t n_tiles = (n_rows + R - 1) / R;
+    const uint32_t n_tiles = (n_rows + rpt - 1) / rpt;
+    const uint32_t *lex_rows = g_lex_rows;
+    const float *lex_norm = g_lex_norm;
+    if constexpr (kLat) {
+        uint32_t *lr = reinterpret_cast<uint32_t *>(smem + L.lex_off);
+        float *ln = reinterpret_cast<float *>(smem + L.lex_off + kLatLex * 4);
+        for (uint32_t i = tid; i < n_lex; i += kScanThreads) { lr[i] = lp.lex_rows[i]; ln[i] = lp.lex_norm[i]; }
+        lex_rows = lr; lex_norm = ln;
+    }
 
     if (tid == 0) {
         for (int s = 0; s < n_stages; ++s) {
@@ -349,7 +365,8 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
         *s_ntop = 0;
         fence_mbar_init();
     }
-    for (uint32_t i = tid; i < q_floats; i += kScanThreads) q_s[i] = g_query[i];
+    if constexpr (kLat) { for (uint32_t i = tid; i < q_floats; i += kScanThreads) q_s[i] = lp.q[i]; }
+    else { for (uint32_t i = tid; i < q_floats; i += kScanThreads) q_s[i] = g_query[i]; }
     __syncthreads();
     if (g_trace != nullptr && tid == 0) g_trace[blockIdx.x] = globaltimer_ns();
 
@@ -372,12 +389,12 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
                 if (!has) { mbar_arrive(full_bar + stage * 8); break; }
                 for (uint32_t kb = 0; kb < KB; ++kb) {
                     if (kb != 0) mbar_wait(empty_bar + stage * 8, phase ^ 1);
-                    mbar_arrive_expect_tx(full_bar + stage * 8, kStageBytes);
+                    mbar_arrive_expect_tx(full_bar + stage * 8, CH * rpt * 128u);
 #pragma unroll
                     for (int c = 0; c < CH; ++c)
                         tma_load_2d(stages_addr + stage * kStageBytes + c * kBoxBytes, &tmap,
                                     static_cast<int32_t>((kb * CH + c) * EPB),
-                                    static_cast<int32_t>(tile * R), full_bar + stage * 8, pol);
+                                    static_cast<int32_t>(tile * rpt), full_bar + stage * 8, pol);
                     if (++stage == static_cast<uint32_t>(n_stages)) { stage = 0; phase ^= 1; }
                 }
                 tile = next_tile;
@@ -458,13 +475,13 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
         }
 
         // ---- blend (:531-532) and offer to the CTA's top-M ----
-        const uint32_t row_local = tile * R + t;
+        const uint32_t row_local = tile * rpt + t;
         float lexv = 0.0f;
         if (n_lex) lexv = lex_lookup(lex_rows, lex_norm, n_lex, row_local);
         const float combined = add_rn(mul_rn(w_embed, acc), mul_rn(w_lex, lexv));
         const uint64_t key = make_key(combined, row_base + row_local);
         const uint32_t tau_g = *s_tau_g;          // ordered score bits; 0 while unknown
-        const bool pass = (row_local < n_rows) && (key > tau) && (static_cast<uint32_t>(key >> 32) >= tau_g);
+        const bool pass = (t < rpt) && (row_local < n_rows) && (key > tau) && (static_cast<uint32_t>(key >> 32) >= tau_g);
         const uint32_t mask = __ballot_sync(0xffffffffu, pass);
         if (mask) {
             uint32_t base = 0;
@@ -607,6 +624,60 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
         named_bar_sync(1, R);
         if (t == 0) st_release_sys_u64(post.flag, post.seq);   // ... before the flag says so
     }
+    if constexpr (kLat) {
+        if (lp.mode == 2u) {
+            // ---- fused MMR tail (pool <= kLatFusePool): mmr_diversify (:767-839) by this CTA, no further launch ----
+            // final_merge left the pool in g_out (device memory).  Stage the records and their rows in the idle TMA
+            // ring, compute every pairwise dot with the reference's sequential arithmetic, run the greedy loop, and
+            // let thread 0 write the selection straight into the host's mapped result block.
+            named_bar_sync(1, R);                                         // g_out / g_out_n written by this CTA
+            const uint32_t P = *reinterpret_cast<volatile uint32_t *>(g_out_n);
+            uint8_t *ring = smem + L.stages_off;
+            rlr_cand *pool_s = reinterpret_cast<rlr_cand *>(ring);                                  // 32 x 16 B
+            float *tri_s = reinterpret_cast<float *>(ring + 512);                                   // 496 floats -> 2 KB
+            uint64_t (*s_best)[4] = reinterpret_cast<uint64_t (*)[4]>(ring + 512 + 2048);           // 64 B
+            uint32_t (*s_besti)[4] = reinterpret_cast<uint32_t (*)[4]>(ring + 512 + 2048 + 64);     // 32 B
+            uint8_t *rows_s = ring + 4096;
+            const uint32_t row_stride = lp.pitch * 4u + 16u;              // +16 B: LDS.128 of different rows on different bank groups
+            if (t < P) pool_s[t] = g_out[t];
+            named_bar_sync(1, R);
+            const uint32_t vpr = lp.pitch / 4u;                           // 16-byte vectors per row
+            for (uint32_t idx = t; idx < P * vpr; idx += R) {
+                const uint32_t r = idx / vpr, v = idx - r * vpr;
+                const float4 *src = reinterpret_cast<const float4 *>(lp.g_rows + static_cast<size_t>(key_row(pool_s[r].key) - row_base) * lp.pitch);
+                *reinterpret_cast<float4 *>(rows_s + r * row_stride + v * 16u) = __ldcg(src + v);
+            }
+            named_bar_sync(1, R);
+            const uint32_t n_pairs = P * (P - 1u) / 2u;
+            for (uint32_t pr = t; pr < n_pairs; pr += R) {
+                uint32_t j = 1;
+                while (j * (j + 1u) / 2u <= pr) ++j;                      // pair pr = (i, j), i < j, triangle index j(j-1)/2 + i
+                const uint32_t i = pr - j * (j - 1u) / 2u;
+                const uint8_t *a_row = rows_s + i * row_stride, *b_row = rows_s + j * row_stride;
+                float acc = 0.0f;
+#pragma unroll 4
+                for (uint32_t v = 0; v < vpr; ++v) {                      // dot_product (:1776-1779), strict order, no FMA
+                    const float4 a = *reinterpret_cast<const float4 *>(a_row + v * 16u);
+                    const float4 b = *reinterpret_cast<const float4 *>(b_row + v * 16u);
+                    acc = add_rn(acc, mul_rn(a.x, b.x));
+                    acc = add_rn(acc, mul_rn(a.y, b.y));
+                    acc = add_rn(acc, mul_rn(a.z, b.z));
+                    acc = add_rn(acc, mul_rn(a.w, b.w));
+                }
+                tri_s[pr] = acc;
+            }
+            named_bar_sync(1, R);
+            if (P == 0) { if (t == 0) *lp.result_n = 0; }
+            else greedy_loop<1>(tri_s, pool_s, nullptr, P, lp.top_k, lp.lambda, lp.d_sel_pos, lp.result_n, lp.result, t, s_best, s_besti);
+            // thread 0 wrote the records and the count: its fence orders them before the flag
+            if (t == 0) { __threadfence_system(); st_release_sys_u64(lp.flag, lp.seq); }
+        } else if (lp.mode == 1u) {
+            // the merged top-m went straight into the host's mapped block (g_out / g_out_n point there)
+            __threadfence_system();
+            named_bar_sync(1, R);
+            if (t == 0) st_release_sys_u64(lp.flag, lp.seq);
+        }
+    }
     if (tr != nullptr && t == 0) tr[7] = globaltimer_ns();
 }
 
@@ -636,6 +707,34 @@ void scan_plan(int sm_count, int max_smem_optin, uint32_t n_rows, uint32_t pitch
     a->smem_bytes = static_cast<int>(smem_layout(stages, q_floats).total + 1024);
 }
 
+uint32_t scan_rows_per_tile(int sm_count, uint64_t n_rows)
+{
+    if (n_rows >= static_cast<uint64_t>(R) * sm_count) return R;
+    uint64_t per = (n_rows + sm_count - 1) / sm_count;
+    per = (per + 7) & ~7ull;
+    if (per < 8) per = 8;
+    return static_cast<uint32_t>(per > static_cast<uint64_t>(R) ? R : per);
+}
+
+void scan_plan_small(int sm_count, int max_smem_optin, uint32_t n_rows, uint32_t pitch, uint32_t rows_per_tile, ScanArgs *a)
+{
+    const uint32_t n_chunks = pitch / 32u;
+    const uint32_t KB = (n_chunks + CH - 1) / CH;
+    const uint32_t q_floats = KB * CH * 32u;
+    a->half = 0;
+    a->rows_per_tile = rows_per_tile;
+    const uint32_t n_tiles = (n_rows + rows_per_tile - 1) / rows_per_tile;
+    int grid = sm_count;                                   // nothing else runs beside a latency-path query: every SM
+    if (static_cast<uint32_t>(grid) > n_tiles) grid = static_cast<int>(n_tiles);
+    if (grid < 1) grid = 1;
+    int stages = 8;
+    while (stages > 2 && smem_layout(stages, q_floats, true).total + 1024 > static_cast<uint32_t>(max_smem_optin)) --stages;
+    a->grid = grid;
+    a->n_stages = stages;
+    a->buf_cap = 0;
+    a->smem_bytes = static_cast<int>(smem_layout(stages, q_floats, true).total + 1024);
+}
+
 cudaError_t scan_configure()
 {
     int dev = 0, optin = 0;
@@ -643,9 +742,11 @@ cudaError_t scan_configure()
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(scan_topm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    e = cudaFuncSetAttribute(scan_topm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(scan_topm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    e = cudaFuncSetAttribute(scan_topm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(scan_topm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
 }
 
 // candidate-buffer capacity for a given m: room for m kept + a few tiles of new entries
@@ -671,16 +772,23 @@ cudaError_t scan_launch(const ScanArgs &a, cudaStream_t stream)
     uint32_t r_pub = (a.m + a.grid - 1) / a.grid;                    // r-th best published per CTA (0 = off)
     if (r_pub > static_cast<uint32_t>(kTopR) || a.d_pub == nullptr || no_global_tau) r_pub = 0;
     const uint32_t n_chunks = a.pitch / (a.half ? 64u : 32u);
-    if (a.half)
-        scan_topm_kernel<true><<<a.grid, kScanThreads, a.smem_bytes, stream>>>(
+    const uint32_t rpt = a.rows_per_tile ? a.rows_per_tile : static_cast<uint32_t>(R);
+    const NoLat nolat = {0};
+    if (a.lat != nullptr && !a.half)
+        scan_topm_kernel<false, true><<<a.grid, kScanThreads, a.smem_bytes, stream>>>(
+            *a.tmap, nullptr, a.n_rows, a.row_base, n_chunks, a.w_embed, a.w_lex, nullptr, nullptr, a.n_lex,
+            a.m, buf_cap, r_pub, a.n_stages, a.d_lists, a.d_counts, a.d_pub, a.d_ticket, a.d_ticket + 1,
+            a.d_out, a.d_out_n, a.d_trace, a.post, rpt, *a.lat);
+    else if (a.half)
+        scan_topm_kernel<true, false><<<a.grid, kScanThreads, a.smem_bytes, stream>>>(
             *a.tmap, a.d_query, a.n_rows, a.row_base, n_chunks, a.w_embed, a.w_lex, a.d_lex_rows, a.d_lex_norm, a.n_lex,
             a.m, buf_cap, r_pub, a.n_stages, a.d_lists, a.d_counts, a.d_pub, a.d_ticket, a.d_ticket + 1,
-            no_merge ? nullptr : a.d_out, a.d_out_n, a.d_trace, a.post);
+            no_merge ? nullptr : a.d_out, a.d_out_n, a.d_trace, a.post, rpt, nolat);
     else
-        scan_topm_kernel<false><<<a.grid, kScanThreads, a.smem_bytes, stream>>>(
+        scan_topm_kernel<false, false><<<a.grid, kScanThreads, a.smem_bytes, stream>>>(
             *a.tmap, a.d_query, a.n_rows, a.row_base, n_chunks, a.w_embed, a.w_lex, a.d_lex_rows, a.d_lex_norm, a.n_lex,
             a.m, buf_cap, r_pub, a.n_stages, a.d_lists, a.d_counts, a.d_pub, a.d_ticket, a.d_ticket + 1,
-            no_merge ? nullptr : a.d_out, a.d_out_n, a.d_trace, a.post);
+            no_merge ? nullptr : a.d_out, a.d_out_n, a.d_trace, a.post, rpt, nolat);
     return cudaGetLastError();
 }
 

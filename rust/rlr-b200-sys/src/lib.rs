@@ -23,6 +23,7 @@ pub const RLR_BATCH_F16: u32 = 0x10;
 pub const RLR_BATCH_BF16: u32 = 0x20;
 pub const RLR_BATCH_TF32: u32 = 0x40;
 pub const RLR_STORE_KEEP_BF16: u32 = 0x10;
+pub const RLR_STORE_NO_LATENCY_PATH: u32 = 0x20;
 pub const RLR_MAX_TOP_K: u32 = 100;
 pub const RLR_MAX_DIM: u32 = 4096;
 pub const RLR_IPC_HANDLE_BYTES: usize = 64;

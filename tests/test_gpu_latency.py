@@ -1,0 +1,135 @@
+"""The small-store latency path (include/rlr_b200.h, "LATENCY PATH"; BASELINE configs[0], the reference's real
+operating point: ~10k chunks, top_k = 5, /root/reference/src/mcp_server.rs:81-110): the query travels in the kernel's
+parameter block, rows are tiled over every SM, for pools <= 32 the scan's last CTA runs merge + pairwise + greedy MMR
+itself, and the result is written into mapped pinned host memory behind a flag the host polls.  Bar: the oracle's
+bits, and the same bits as the regular path on the same store."""
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+def W(e=0.7, l=0.3):
+    from rust_local_rag_b200.engine import ResolvedWeights
+    return ResolvedWeights(F32(e), F32(l), F32(0.7), F32(0.3))
+
+
+def same(a, b):
+    return np.asarray(a).tobytes() == np.asarray(b).tobytes()
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from rust_local_rag_b200 import engine
+    return engine
+
+
+# n: 1 tile of 8 rows .. one row tile per SM (rows_per_tile 8..128) .. the 128-row regime (>= 18,944 rows on 148 SMs)
+@pytest.mark.parametrize("n,dim", [(1, 768), (5, 64), (100, 768), (1184, 384), (1185, 768), (5000, 1024), (10000, 768),
+                                   (18943, 96), (18944, 768), (18945, 768), (40000, 768), (9999, 1000)])
+def test_latency_path_equals_oracle_and_regular_path(eng, rlr, orc, n, dim):
+    rows = orc.synth_rows(n, dim, kind=1, n_clusters=min(64, max(1, n // 4)), seed=n)
+    qs = orc.synth_rows(3, dim, kind=1, seed=0x5EED0002, n_clusters=min(64, max(1, n // 4)))
+    fast = eng.DeviceStore.from_rows(rows)
+    slow = eng.DeviceStore.from_rows(rows, flags=rlr.RLR_STORE_NO_LATENCY_PATH)
+    rng = np.random.default_rng(n)
+    n_lex = min(n, 60)
+    lex_rows = rng.choice(n, n_lex, replace=False).astype(np.uint32)
+    lex_scores = (rng.random(n_lex) * 7 + 0.01).astype(F32)
+    for q in qs:
+        # pools 10..33: the fused tail up to 32, the three-launch form beyond; k = 100: pool 300
+        for k, lam in ((5, 0.3), (0, 0.5), (1, 1.0), (7, 0.9), (10, 0.3), (11, 0.3), (100, 0.7), (5, 0.0)):
+            for lex in (None, (lex_rows, lex_scores)):
+                kw = {} if lex is None else dict(lex_rows=lex[0], lex_scores=lex[1])
+                a = fast.search_mmr(q, k, lam, W(), *(lex or ()))
+                b = slow.search_mmr(q, k, lam, W(), *(lex or ()))
+                ref = orc.search_with_diversity(rows, q, k, lam, full_sort=n <= 5000, threads=4, **kw)
+                for x, y, z in zip(a, b, ref):
+                    assert same(x, z) and same(y, z), (n, dim, k, lam, lex is not None)
+        for m in (1, 15, 45, 900):
+            a = fast.search_topm(q, m, W(), lex_rows, lex_scores)
+            ref = orc.search(rows, q, m, lex_rows=lex_rows, lex_scores=lex_scores, full_sort=n <= 5000, threads=4)
+            for x, z in zip(a, ref):
+                assert same(x, z), (n, dim, m)
+        r, sc = fast.embedding_candidates(q, 12)
+        R, S = orc.embedding_candidates(rows, q, 12, threads=4)
+        assert same(r, R) and same(sc, S)
+    t = fast.search_mmr(qs[0], 5, 0.3, W(), flags=rlr.RLR_WANT_TIMINGS)
+    tm = fast.last_timings()
+    assert tm.launches == 1 and tm.total_ms > 0            # ONE launch: scan + merge + MMR + delivery
+    t2 = fast.search_mmr(qs[0], 100, 0.7, W(), flags=rlr.RLR_WANT_TIMINGS)
+    assert fast.last_timings().launches == (3 if n > 1 else 2) and same(t[0][:1], t2[0][:1])
+    fast.close(); slow.close()
+
+
+def test_latency_path_mmr_actually_reorders_and_ties_follow_swap_remove(eng, orc):
+    """Clustered pool where diversity changes the order, and exact ties whose order is decided by swap_remove."""
+    rng = np.random.default_rng(3)
+    base = orc.normalize_rows(rng.standard_normal((6, 256)).astype(F32))
+    rows = np.concatenate([np.tile(base[i:i + 1], (40, 1)) for i in range(6)])          # 6 clusters of 40 identical rows
+    rows = orc.normalize_rows(rows + F32(0.02) * rng.standard_normal(rows.shape).astype(F32))
+    rows[200:240] = rows[200]                                                           # exact duplicates: exact ties
+    s = eng.DeviceStore.from_rows(rows)
+    q = orc.normalize(base[0] + F32(0.5) * base[5])
+    plain = s.search_mmr(q, 5, 0.0, W())
+    reordered = False
+    for lam in (0.3, 0.6, 0.9, 1.0):
+        got = s.search_mmr(q, 5, lam, W())
+        ref = orc.search_with_diversity(rows, q, 5, lam, full_sort=True)
+        for x, z in zip(got, ref):
+            assert same(x, z), lam
+        reordered |= not same(got[0], plain[0])
+    assert reordered, "MMR never changed the order: the test does not exercise the fused tail"
+    s.close()
+
+
+def test_latency_path_many_calls_and_concurrent_callers(eng, orc):
+    rows = orc.synth_rows(10000, 768, kind=1, n_clusters=64)
+    qs = orc.synth_rows(16, 768, kind=1, seed=0x5EED0002, n_clusters=64)
+    s = eng.DeviceStore.from_rows(rows)
+    refs = [orc.search_with_diversity(rows, q, 5, 0.3, full_sort=True) for q in qs]
+    for i in range(300):                                     # the completion word counts up; every call must see ITS result
+        got = s.search_mmr(qs[i % 16], 5, 0.3, W())
+        assert same(got[0], refs[i % 16][0]) and same(got[1], refs[i % 16][1]), i
+    errs = []
+
+    def worker(t):
+        try:
+            for i in range(100):
+                j = (t * 5 + i) % 16
+                got = s.search_mmr(qs[j], 5, 0.3, W())
+                if not (same(got[0], refs[j][0]) and same(got[1], refs[j][1])):
+                    errs.append((t, i))
+        except Exception as e:      # noqa: BLE001
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs[:3]
+    s.close()
+
+
+def test_latency_path_follows_store_mutation(eng, orc):
+    """rows_per_tile and the small tensor map are rebuilt when the store grows or shrinks."""
+    rng = np.random.default_rng(5)
+    rows = orc.normalize_rows(rng.standard_normal((3000, 128)).astype(F32))
+    s = eng.DeviceStore.from_rows(rows[:1000])
+    q = rng.standard_normal(128).astype(F32)
+    for upto in (1000, 3000):
+        if upto > 1000:
+            s.append(rows[1000:upto])
+        got = s.search_mmr(q, 5, 0.3, W())
+        ref = orc.search_with_diversity(rows[:upto], q, 5, 0.3, full_sort=True)
+        for x, z in zip(got, ref):
+            assert same(x, z), upto
+    s.remove_rows(np.arange(500, 2900))
+    now = s.read_rows(np.arange(s.info().n_rows))
+    got = s.search_mmr(q, 5, 0.3, W())
+    ref = orc.search_with_diversity(now, q, 5, 0.3, full_sort=True)
+    for x, z in zip(got, ref):
+        assert same(x, z)
+    s.close()
