@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -852,6 +853,30 @@ int lat_search(rlr_store *s, rlr_ctx *c, uint32_t flags, const rlr_resolved_weig
     } else if (fuse) {          // scan + merge + pairwise + greedy + delivery: ONE launch
         lp.mode = 2;
         a.d_out = c->d_pool; a.d_out_n = c->d_pool_n;
+        static const bool trace = getenv("RLR_DEBUG_LAT_TRACE") != nullptr;      // dev-only: phase timestamps of one request
+        if (trace) {
+            const int g = a.grid;
+            unsigned long long *d_tr = nullptr;
+            std::vector<unsigned long long> h(5 * g + 16, 0);
+            CU_TRY(cudaMalloc(&d_tr, h.size() * 8));
+            CU_TRY(cudaMemset(d_tr, 0, h.size() * 8));
+            a.d_trace = d_tr;
+            unsigned long long host_t0 = 0;
+            { timespec ts; clock_gettime(CLOCK_REALTIME, &ts); host_t0 = ts.tv_sec * 1000000000ull + ts.tv_nsec; }
+            CU_TRY(rlr::scan_launch(a, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            CU_TRY(cudaMemcpy(h.data(), d_tr, h.size() * 8, cudaMemcpyDeviceToHost));
+            cudaFree(d_tr);
+            a.d_trace = nullptr;
+            unsigned long long t0 = ~0ull, t0max = 0, loop_max = 0, loop_min = ~0ull, list_max = 0;
+            for (int i = 0; i < g; ++i) { t0 = std::min(t0, h[i]); t0max = std::max(t0max, h[i]); loop_max = std::max(loop_max, h[g + i]); loop_min = std::min(loop_min, h[g + i]); list_max = std::max(list_max, h[2 * g + i]); }
+            const unsigned long long *tr = h.data() + 4 * g;
+            fprintf(stderr, "[lat trace grid=%d rpt=%u] launch->first CTA prologue done %.1f us (globaltimer vs host clock, approximate); prologue done first/last 0/%.1f; "
+                            "scan loop end first/last %.1f/%.1f; lists written %.1f; merge start %.1f, merged %.1f, rows staged %.1f, pairwise %.1f, delivered %.1f us\n",
+                    g, s->rpt, (double)(long long)(t0 - host_t0) / 1e3, (t0max - t0) / 1e3, (loop_min - t0) / 1e3, (loop_max - t0) / 1e3, (list_max - t0) / 1e3,
+                    (tr[0] - t0) / 1e3, (tr[4] - t0) / 1e3, (tr[5] - t0) / 1e3, (tr[6] - t0) / 1e3, (tr[7] - t0) / 1e3);
+            *reinterpret_cast<volatile unsigned long long *>(c->h_result_blk + 8) = 0;
+        }
         CU_TRY(rlr::scan_launch(a, st));
         ++c->launches;
         if (timed) { CU_TRY(cudaEventRecord(c->ev[1], st)); CU_TRY(cudaEventRecord(c->ev[2], st)); CU_TRY(cudaEventRecord(c->ev[3], st)); }
