@@ -254,6 +254,25 @@ int rlr_search_mmr(rlr_store *s, const float *query, uint32_t dim, uint32_t flag
                    uint32_t *out_n);
 
 /*
+ * rlr_search_mmr_multi -- THROUGHPUT MODE: 2..RLR_MAX_MULTI independent search_with_diversity calls (:717-759)
+ * answered by ONE pass over the rows.  What it models: several searches in flight under the reference's read lock
+ * (src/mcp_server.rs:89,377).  The scan kernel runs one group of consumer warps per query over the SAME shared-
+ * memory tiles, so every row crosses HBM once per call instead of once per query; each (row, query) dot is still
+ * its own strict left-to-right f32 chain, and every query's result is bit-identical to its rlr_search_mmr result.
+ *   queries      nq x dim f32 (row stride dim), each normalised here unless RLR_QUERY_PRENORMALIZED
+ *   lex_*        per query q: n_lex[q] pairs at lex_rows[q] / lex_scores[q] (any may be NULL / 0); lex_rows, lex_scores
+ *                and n_lex themselves may be NULL for embedding-only queries
+ * Outputs: out_* are nq x max(top_k,1) (row stride max(top_k,1)), out_n[q] the count of query q.
+ * The latency of one call is that of a single query plus (nq - 1) MMR tails; use it when queries queue up.
+ */
+#define RLR_MAX_MULTI 3
+int rlr_search_mmr_multi(rlr_store *s, const float *queries, uint32_t nq, uint32_t dim, uint32_t flags,
+                         uint32_t top_k, float diversity_factor, const rlr_resolved_weights *w,
+                         const uint32_t *const *lex_rows, const float *const *lex_scores, const uint32_t *n_lex,
+                         uint32_t *out_rows, float *out_score, float *out_emb, float *out_lex,
+                         uint32_t *out_n);
+
+/*
  * rlr_embedding_candidates -- RagEngine::get_embedding_candidates,
  * src/rag_engine.rs:415-461 (ann_index == None): top `count` by raw dot product.
  */
@@ -487,6 +506,13 @@ int rlr_mailbox_merge_async(rlr_ctx *c, rlr_mailbox *mb, uint64_t seq, uint32_t 
 int rlr_search_mmr_async(rlr_ctx *c, const void *d_query, uint32_t top_k, float diversity_factor,
                          float w_embed, float w_lex,
                          void *d_result, void *d_result_n, void *stream);
+
+/* device-level form of rlr_search_mmr_multi: nq ctxs of ONE store (ctx q holds query q's pool / MMR buffers; the scan
+ * uses ctx 0's launch workspace), d_queries[q] normalised on the device, everything enqueued on `stream`.
+ * d_results[q]: rlr_cand[max(top_k,1)], d_result_ns[q]: u32. */
+int rlr_search_mmr_multi_async(rlr_ctx *const *ctxs, uint32_t nq, const void *const *d_queries, uint32_t top_k,
+                               float diversity_factor, float w_embed, float w_lex,
+                               void *const *d_results, void *const *d_result_ns, void *stream);
 
 /* search flags (RLR_SEARCH_F16) used by the device-level entry points of this ctx */
 int rlr_ctx_set_flags(rlr_ctx *c, uint32_t search_flags);

@@ -35,6 +35,7 @@ RLR_IPC_HANDLE_BYTES = 64
 RLR_SYNTH_IID = 0
 RLR_SYNTH_CLUSTERED = 1
 RLR_MAX_SHARDS = 16
+RLR_MAX_MULTI = 3
 
 
 class RlrError(RuntimeError):
@@ -104,6 +105,9 @@ PROTOTYPES = {
     "rlr_search_mmr": (_int, [_vp, _vp, _u32, _u32, _u32, _f32, C.POINTER(ResolvedWeightsC), _vp, _vp, _u32,
                               _vp, _vp, _vp, _vp, _pu32]),
     "rlr_embedding_candidates": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _pu32]),
+    "rlr_search_mmr_multi": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _f32, C.POINTER(ResolvedWeightsC), _vp, _vp, _vp,
+                                    _vp, _vp, _vp, _vp, _vp]),
+    "rlr_search_mmr_multi_async": (_int, [_vp, _u32, _vp, _u32, _f32, _f32, _f32, _vp, _vp, _vp]),
     "rlr_search_batch": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp]),
     "rlr_search_batch_device": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp]),
     "rlr_batch_merge_async": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),

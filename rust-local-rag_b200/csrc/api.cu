@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -160,12 +161,14 @@ int rlr_api::ctx_new(rlr_store *s, rlr_ctx **out)
     CTX_TRY(cudaMemset(c->d_query, 0, rlr::kQueryCap * sizeof(float)));
     CTX_TRY(cudaMalloc(&c->d_lex_rows, kLexCap * sizeof(uint32_t)));
     CTX_TRY(cudaMalloc(&c->d_lex_norm, kLexCap * sizeof(float)));
-    CTX_TRY(cudaMalloc(&c->d_lists, static_cast<size_t>(c->n_lists_cap) * RLR_MAX_M * sizeof(rlr_cand)));
-    CTX_TRY(cudaMalloc(&c->d_counts, c->n_lists_cap * sizeof(uint32_t)));
-    CTX_TRY(cudaMalloc(&c->d_ticket, 2 * sizeof(uint32_t)));
-    CTX_TRY(cudaMemset(c->d_ticket, 0, 2 * sizeof(uint32_t)));
-    CTX_TRY(cudaMalloc(&c->d_pub, c->n_lists_cap * sizeof(uint32_t)));
-    CTX_TRY(cudaMemset(c->d_pub, 0, c->n_lists_cap * sizeof(uint32_t)));
+    // per-launch scan workspace, one slice per query group (kernels.cuh: ScanArgs)
+    constexpr size_t kG = rlr::kMaxQueryGroups;
+    CTX_TRY(cudaMalloc(&c->d_lists, kG * c->n_lists_cap * RLR_MAX_M * sizeof(rlr_cand)));
+    CTX_TRY(cudaMalloc(&c->d_counts, kG * c->n_lists_cap * sizeof(uint32_t)));
+    CTX_TRY(cudaMalloc(&c->d_ticket, 8 * sizeof(uint32_t)));
+    CTX_TRY(cudaMemset(c->d_ticket, 0, 8 * sizeof(uint32_t)));
+    CTX_TRY(cudaMalloc(&c->d_pub, kG * c->n_lists_cap * sizeof(uint32_t)));
+    CTX_TRY(cudaMemset(c->d_pub, 0, kG * c->n_lists_cap * sizeof(uint32_t)));
     CTX_TRY(cudaMalloc(&c->d_tmp, (static_cast<size_t>(c->n_lists_cap) + 3) * RLR_MAX_M * sizeof(rlr_cand)));
     // (count, records) pairs live in one block each -- [u32 n | pad to 16 B | records] -- so that ONE D2H
     // copy brings back a result and its length
@@ -1116,6 +1119,172 @@ RLR_EXPORT int rlr_search_mmr(rlr_store *s, const float *query, uint32_t dim, ui
     *out_n = n;
     if (timed) { timings_from_events(c, true); g_timings.launches = static_cast<uint32_t>(c->launches - launches0); }
     return RLR_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// throughput mode: several queries per pass over the rows (query groups, scan_topm.cu)
+// ---------------------------------------------------------------------------------
+namespace {
+
+// scan for nq queries (one launch) + per-query MMR, all on `st`.  Group q's query / lexical pairs / pool / MMR buffers
+// are ctx q's; the launch workspace is ctx 0's.  d_result[q] / d_result_n[q]: where query q's result goes.
+int enqueue_multi(rlr_store *s, rlr_ctx *const *cs, uint32_t nq, const float *const *d_query, const uint32_t *nl,
+                  float w_e, float w_l, uint32_t top_k, float lambda, uint32_t flags, rlr_cand *const *d_result,
+                  uint32_t *const *d_result_n, cudaStream_t st, cudaEvent_t ev_after_scan)
+{
+    const bool half = s->use_half(flags);
+    const bool do_mmr = lambda != 0.0f;
+    const uint64_t pool = do_mmr ? std::max<uint64_t>(3ull * top_k, static_cast<uint64_t>(top_k) + 10) : std::max<uint32_t>(top_k, 1);
+    if (pool > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "candidate pool %llu exceeds %d (top_k %u)", (unsigned long long)pool, RLR_MAX_M, top_k);
+    const uint32_t p = static_cast<uint32_t>(std::min<uint64_t>(pool, s->n_rows));
+    rlr_ctx *c0 = cs[0];
+    rlr::ScanArgs a;
+    memset(&a, 0, sizeof a);
+    rlr::scan_plan(s->sm_count, s->smem_optin, static_cast<uint32_t>(s->n_rows), half ? s->pitch16 : s->pitch, half, &a, nq);
+    if (a.grid <= 0) return fail(RLR_ERR_UNSUPPORTED, "%u query groups do not fit this store's row size in shared memory", nq);
+    a.tmap = half ? &s->tmap16 : &s->tmap;
+    a.n_rows = static_cast<uint32_t>(s->n_rows);
+    a.row_base = static_cast<uint32_t>(s->row_base);
+    a.pitch = half ? s->pitch16 : s->pitch;
+    a.w_embed = w_e; a.w_lex = w_l;
+    a.m = p;
+    a.d_lists = c0->d_lists; a.d_counts = c0->d_counts; a.d_ticket = c0->d_ticket; a.d_pub = c0->d_pub;
+    for (uint32_t q = 0; q < nq; ++q) {
+        rlr::ScanGroupIO &g = a.groups.g[q];
+        g.query = d_query[q];
+        g.lex_rows = cs[q]->d_lex_rows; g.lex_norm = cs[q]->d_lex_norm; g.n_lex = nl ? nl[q] : 0;
+        g.out = do_mmr ? cs[q]->d_pool : d_result[q];
+        g.out_n = do_mmr ? cs[q]->d_pool_n : d_result_n[q];
+    }
+    if (nq == 1) {          // scan_launch reads the single-query fields
+        a.d_query = a.groups.g[0].query; a.d_lex_rows = a.groups.g[0].lex_rows; a.d_lex_norm = a.groups.g[0].lex_norm;
+        a.n_lex = a.groups.g[0].n_lex; a.d_out = a.groups.g[0].out; a.d_out_n = a.groups.g[0].out_n;
+    }
+    CU_TRY(rlr::scan_launch(a, st));
+    ++c0->launches;
+    if (ev_after_scan) CU_TRY(cudaEventRecord(ev_after_scan, st));
+    if (!do_mmr) return RLR_OK;
+    for (uint32_t q = 0; q < nq; ++q) {
+        rlr_ctx *c = cs[q];
+        rlr::MmrArgs ma;
+        memset(&ma, 0, sizeof ma);
+        ma.half = half;
+        ma.d_emb = half ? s->d_rows16 : static_cast<const void *>(s->d_rows); ma.pitch = half ? s->pitch16 : s->pitch; ma.dim = s->dim;
+        ma.d_cands = c->d_pool; ma.d_n = c->d_pool_n;
+        ma.row_base = static_cast<uint32_t>(s->row_base); ma.use_rows = 1;
+        ma.p_cap = p; ma.top_k = top_k; ma.lambda = lambda;
+        ma.d_tri = c->d_tri; ma.d_sel_pos = c->d_sel_pos; ma.d_sel_n = d_result_n[q]; ma.d_result = d_result[q];
+        ma.max_smem_optin = s->smem_optin;
+        uint32_t l = 0;
+        CU_TRY(rlr::mmr_launch(ma, st, &l));
+        c0->launches += l;
+    }
+    return RLR_OK;
+}
+
+} // namespace
+
+RLR_EXPORT int rlr_search_mmr_multi(rlr_store *s, const float *queries, uint32_t nq, uint32_t dim, uint32_t flags, uint32_t top_k,
+                                    float diversity_factor, const rlr_resolved_weights *w, const uint32_t *const *lex_rows,
+                                    const float *const *lex_scores, const uint32_t *n_lex, uint32_t *out_rows, float *out_score,
+                                    float *out_emb, float *out_lex, uint32_t *out_n)
+{
+    if (int rc = check_store(s)) return rc;
+    if (!out_rows || !out_n) return fail(RLR_ERR_INVALID_ARG, "out_rows/out_n is NULL");
+    if (!w) return fail(RLR_ERR_INVALID_ARG, "weights is NULL");
+    if (nq == 0) return RLR_OK;
+    if (nq > RLR_MAX_MULTI) return fail(RLR_ERR_UNSUPPORTED, "nq %u exceeds RLR_MAX_MULTI (%d)", nq, RLR_MAX_MULTI);
+    if (!queries) return fail(RLR_ERR_INVALID_ARG, "queries is NULL");
+    const uint32_t cap = std::max<uint32_t>(top_k, 1);
+    if (nq == 1)
+        return rlr_search_mmr(s, queries, dim, flags, top_k, diversity_factor, w, lex_rows ? lex_rows[0] : nullptr,
+                              lex_scores ? lex_scores[0] : nullptr, n_lex ? n_lex[0] : 0, out_rows, out_score, out_emb, out_lex, out_n);
+    for (uint32_t q = 0; q < nq; ++q) out_n[q] = 0;
+    float lambda = diversity_factor;                    // :725 f32::clamp (NaN stays NaN)
+    if (lambda < 0.0f) lambda = 0.0f;
+    if (lambda > 1.0f) lambda = 1.0f;
+    if ((flags & RLR_SEARCH_F16) && s->d_rows16 == nullptr && s->n_rows)
+        return fail(RLR_ERR_INVALID_ARG, "RLR_SEARCH_F16 but the store holds no f16 copy");
+    if (int rc = ensure_device(s->device)) return rc;
+    if (s->n_rows == 0) return RLR_OK;
+    // one pooled ctx per query: its query, lexical pairs, pool, MMR buffers and pinned staging
+    std::vector<std::unique_ptr<CtxLease>> leases;
+    rlr_ctx *cs[RLR_MAX_MULTI];
+    for (uint32_t q = 0; q < nq; ++q) {
+        leases.emplace_back(new CtxLease(s));
+        if (int rc = leases.back()->acquire()) return rc;
+        cs[q] = leases.back()->c;
+    }
+    cudaStream_t st = cs[0]->stream;
+    const float *dq[RLR_MAX_MULTI];
+    uint32_t nl[RLR_MAX_MULTI];
+    rlr_cand *dres[RLR_MAX_MULTI];
+    uint32_t *dres_n[RLR_MAX_MULTI];
+    for (uint32_t q = 0; q < nq; ++q) {
+        if (int rc = stage_query(cs[q], queries + static_cast<size_t>(q) * dim, dim, flags, st)) return rc;
+        nl[q] = 0;
+        if (int rc = stage_lex(cs[q], lex_rows ? lex_rows[q] : nullptr, lex_scores ? lex_scores[q] : nullptr, n_lex ? n_lex[q] : 0, &nl[q], st)) return rc;
+        dq[q] = cs[q]->d_query;
+        dres[q] = cs[q]->d_result; dres_n[q] = cs[q]->d_sel_n;
+    }
+    const bool timed = flags & RLR_WANT_TIMINGS;
+    const uint64_t launches0 = cs[0]->launches;
+    if (timed) CU_TRY(cudaEventRecord(cs[0]->ev[0], st));
+    if (int rc = enqueue_multi(s, cs, nq, dq, nl, w->embedding, w->lexical, top_k, lambda, flags, dres, dres_n, st, timed ? cs[0]->ev[1] : nullptr)) return rc;
+    if (timed) CU_TRY(cudaEventRecord(cs[0]->ev[3], st));
+    const uint64_t pool = lambda != 0.0f ? std::max<uint64_t>(3ull * top_k, static_cast<uint64_t>(top_k) + 10) : cap;
+    const uint32_t p = static_cast<uint32_t>(std::min<uint64_t>(pool, s->n_rows));
+    const uint32_t n_cap = std::min<uint32_t>(p, cap);
+    for (uint32_t q = 0; q < nq; ++q)
+        CU_TRY(cudaMemcpyAsync(cs[q]->h_result_blk, cs[q]->d_result_blk, 16 + n_cap * sizeof(rlr_cand), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    for (uint32_t q = 0; q < nq; ++q) {
+        const uint32_t n = std::min(cs[q]->h_result_n[0], n_cap);
+        unpack(cs[q]->h_result, n, out_rows + static_cast<size_t>(q) * cap, out_score ? out_score + static_cast<size_t>(q) * cap : nullptr,
+               out_emb ? out_emb + static_cast<size_t>(q) * cap : nullptr, out_lex ? out_lex + static_cast<size_t>(q) * cap : nullptr);
+        out_n[q] = n;
+    }
+    if (timed) {
+        rlr_timings t = {0, 0, 0, 0, 0};
+        cudaEventElapsedTime(&t.scan_ms, cs[0]->ev[0], cs[0]->ev[1]);
+        cudaEventElapsedTime(&t.mmr_ms, cs[0]->ev[1], cs[0]->ev[3]);
+        cudaEventElapsedTime(&t.total_ms, cs[0]->ev[0], cs[0]->ev[3]);
+        cudaGetLastError();
+        t.launches = static_cast<uint32_t>(cs[0]->launches - launches0);
+        g_timings = t;
+    }
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_search_mmr_multi_async(rlr_ctx *const *ctxs, uint32_t nq, const void *const *d_queries, uint32_t top_k,
+                                          float diversity_factor, float w_embed, float w_lex, void *const *d_results,
+                                          void *const *d_result_ns, void *stream)
+{
+    if (!ctxs || !d_queries || !d_results || !d_result_ns) return fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    if (nq == 0 || nq > RLR_MAX_MULTI) return fail(RLR_ERR_UNSUPPORTED, "nq %u not in 1..%d", nq, RLR_MAX_MULTI);
+    for (uint32_t q = 0; q < nq; ++q) {
+        if (!ctxs[q] || !d_queries[q] || !d_results[q] || !d_result_ns[q]) return fail(RLR_ERR_INVALID_ARG, "NULL argument for query %u", q);
+        if (ctxs[q]->s != ctxs[0]->s) return fail(RLR_ERR_INVALID_ARG, "the ctxs must belong to one store");
+    }
+    rlr_store *s = ctxs[0]->s;
+    CU_TRY(cudaSetDevice(s->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float lambda = diversity_factor;
+    if (lambda < 0.0f) lambda = 0.0f;
+    if (lambda > 1.0f) lambda = 1.0f;
+    if (s->n_rows == 0) {
+        for (uint32_t q = 0; q < nq; ++q) CU_TRY(cudaMemsetAsync(d_result_ns[q], 0, sizeof(uint32_t), st));
+        return RLR_OK;
+    }
+    const float *dq[RLR_MAX_MULTI];
+    rlr_cand *dres[RLR_MAX_MULTI];
+    uint32_t *dres_n[RLR_MAX_MULTI];
+    for (uint32_t q = 0; q < nq; ++q) {
+        dq[q] = static_cast<const float *>(d_queries[q]);
+        dres[q] = static_cast<rlr_cand *>(d_results[q]);
+        dres_n[q] = static_cast<uint32_t *>(d_result_ns[q]);
+    }
+    return enqueue_multi(s, ctxs, nq, dq, nullptr, w_embed, w_lex, top_k, lambda, ctxs[0]->search_flags, dres, dres_n, st, nullptr);
 }
 
 // ---------------------------------------------------------------------------------

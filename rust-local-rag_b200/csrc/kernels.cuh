@@ -10,7 +10,7 @@ namespace rlr {
 
 constexpr int kScanRows = 128;        // rows per tile == consumer threads per CTA
 constexpr int kScanChunks = 2;        // 128-byte column chunks per pipeline stage
-constexpr int kScanThreads = kScanRows + 64;   // 4 consumer warps + TMA producer warp + threshold warp
+constexpr int kScanThreads = kScanRows + 64;   // 4 consumer warps (per query group) + TMA producer warp + threshold warp
 constexpr int kTopBuf = 2048;         // per-CTA candidate buffer (entries)
 constexpr int kChunkFloats = 32;      // 128 B : the TMA SWIZZLE_128B span
 constexpr int kQueryCap = RLR_MAX_DIM + 128; // floats, zero padded (a stage spans <= 128 elements)
@@ -52,6 +52,19 @@ struct LatParams {
     unsigned long long seq;
 };
 
+// Query groups (throughput mode): one launch answers up to kMaxQueryGroups queries in a single pass over the rows.
+constexpr int kMaxQueryGroups = 3;
+struct ScanGroupIO {
+    const float *query;        // kQueryCap floats on the device, zero beyond dim
+    const uint32_t *lex_rows;  // this query's lexical pairs: sorted local rows (may be null) ...
+    const float *lex_norm;     // ... their lexical_score (already / max_lexical)
+    uint32_t n_lex;
+    rlr_cand *out;             // best m records over all CTAs (null: skip the in-kernel merge)
+    uint32_t *out_n;
+    ScanPost post;             // zeroed: off
+};
+struct ScanGroups { ScanGroupIO g[kMaxQueryGroups]; };
+
 struct ScanArgs {
     const CUtensorMap *tmap;   // host pointer; copied into the kernel's param space (f32 or f16 map)
     int half;                  // 1: the map describes the binary16 copy of the store
@@ -64,11 +77,11 @@ struct ScanArgs {
     const float *d_lex_norm;    // lexical_score per entry (already / max_lexical)
     uint32_t n_lex;
     uint32_t m;                // 1..RLR_MAX_M
-    rlr_cand *d_lists;         // grid x m records
-    uint32_t *d_counts;        // grid
-    uint32_t *d_ticket;        // 2 words, zero-initialised: [0] finish ticket, [1] dynamic tile counter;
-                               // the last CTA to finish merges and resets both
-    uint32_t *d_pub;           // grid words, zero-initialised: per-CTA published r-th best score
+    rlr_cand *d_lists;         // n_groups x grid x m records
+    uint32_t *d_counts;        // n_groups x grid
+    uint32_t *d_ticket;        // 8 words, zero-initialised: [g] finish ticket of query group g, [4] dynamic tile
+                               // counter; the last CTA to finish (per group) merges and resets them
+    uint32_t *d_pub;           // n_groups x grid words, zero-initialised: per-CTA published r-th best score
     rlr_cand *d_out;           // best m records over all CTAs (null: skip the in-kernel merge)
     uint32_t *d_out_n;
     int grid;                  // CTAs to launch (<= SM count)
@@ -77,13 +90,15 @@ struct ScanArgs {
     uint32_t buf_cap;          // 0: derive from m
     unsigned long long *d_trace; // dev-only: phase timestamps (5*grid + 16 words) or null
     ScanPost post;             // zeroed: off
+    uint32_t n_groups;         // 0 / 1: one query (d_query, d_out, d_out_n, post above); 2..kMaxQueryGroups: `groups`
+    ScanGroups groups;         // per-group query / outputs / post when n_groups > 1
     uint32_t rows_per_tile;    // 0 / kScanRows: 128-row tiles.  Small stores use fewer rows per tile (a multiple of 8, with
                                // a tensor map whose box has that many rows) so that the rows spread over every SM
     const LatParams *lat;      // host pointer or null: latency path (f32 stores only); d_query / d_lex_* are then ignored
 };
 
 // Pick grid / stages / smem for a store on a device.
-void scan_plan(int sm_count, int max_smem_optin, uint32_t n_rows, uint32_t pitch, int half, ScanArgs *a);
+void scan_plan(int sm_count, int max_smem_optin, uint32_t n_rows, uint32_t pitch, int half, ScanArgs *a, uint32_t n_groups = 1);
 // rows per tile for a store of n_rows on sm_count SMs: kScanRows for stores that fill every SM with 128-row tiles,
 // else the least multiple of 8 that gives every SM at most one tile
 uint32_t scan_rows_per_tile(int sm_count, uint64_t n_rows);

@@ -22,6 +22,7 @@
 //   * each CTA writes its best M records; the LAST CTA to finish (atomic ticket) merges
 //     the <=148 lists in place (final_merge), so one launch yields the global top-M.
 #include <cstdlib>
+#include <cstring>
 
 #include <cuda_fp16.h>
 
@@ -38,20 +39,28 @@ constexpr int R = kScanRows;
 constexpr int CH = kScanChunks;
 constexpr uint32_t kBoxBytes = R * 128;            // one TMA box: 128 rows x 128 B
 constexpr uint32_t kStageBytes = CH * kBoxBytes;
+constexpr uint32_t kGroupScratch = 32 * 1024;      // per query group: a slice of the idle TMA ring used as scratch by the tail
+                                                   // (kTopBuf keys + payloads = 24 KB, then the per-CTA counts)
 
+// Shared memory: the TMA ring, then one block per QUERY GROUP (query, candidate buffer, a line of scalars), then
+// the barriers, the tile-id mailbox and (latency path) the lexical pairs.
 struct SmemLayout {
-    uint32_t stages_off, q_off, keys_off, embs_off, bars_off, misc_off, lex_off, total;
+    uint32_t stages_off, grp_off, grp_stride, q_rel, keys_rel, embs_rel, misc_rel, bars_off, tile_off, lex_off, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int n_stages, uint32_t q_floats, bool lat = false)
+__host__ __device__ inline SmemLayout smem_layout(int n_stages, uint32_t q_floats, bool lat = false, uint32_t nq = 1)
 {
     SmemLayout L;
     uint32_t o = 0;
     L.stages_off = o; o += n_stages * kStageBytes;
-    L.q_off = o;      o += q_floats * 4;
-    L.keys_off = o;   o += kTopBuf * 8;
-    L.embs_off = o;   o += kTopBuf * 4;
+    L.grp_off = o;
+    L.q_rel = 0;
+    L.keys_rel = q_floats * 4;
+    L.embs_rel = L.keys_rel + kTopBuf * 8;
+    L.misc_rel = L.embs_rel + kTopBuf * 4;
+    L.grp_stride = L.misc_rel + 128;
+    o += nq * L.grp_stride;
     L.bars_off = o;   o += n_stages * 16;
-    L.misc_off = o;   o += 128;
+    L.tile_off = o;   o += 64;
     L.lex_off = o;    o += lat ? kLatLex * 8 : 0;      // latency path: the lexical pairs of the parameter block
     L.total = o;
     return L;
@@ -134,20 +143,20 @@ __device__ void final_merge(uint64_t *keys, float *embs, uint32_t *s_counts, vol
                             volatile uint32_t *s_aux, const rlr_cand *lists, const uint32_t *counts, uint32_t Ln,
                             uint32_t m, uint32_t row_base, const uint32_t *lex_rows,
                             const float *lex_norm, uint32_t n_lex, rlr_cand *__restrict__ out,
-                            uint32_t *__restrict__ out_n, uint32_t t, unsigned long long *tr)
+                            uint32_t *__restrict__ out_n, uint32_t t, unsigned long long *tr, uint32_t bar)
 {
     // counts -> shared memory (one batched L2 round trip), total valid records
     if (t == 0) { *s_cnt = 0; *s_aux = 0; }
-    named_bar_sync(1, R);
+    named_bar_sync(bar, R);
     {
         uint32_t local = 0;
         for (uint32_t j = t; j < Ln; j += R) { const uint32_t cj = __ldcg(counts + j); s_counts[j] = cj; local += cj; }
         if (local) atomicAdd(const_cast<uint32_t *>(s_cnt), local);
     }
-    named_bar_sync(1, R);
+    named_bar_sync(bar, R);
     const uint32_t total = *s_cnt;
     const uint32_t m_out = total < m ? total : m;
-    named_bar_sync(1, R);
+    named_bar_sync(bar, R);
 
     // sample depth: the least c whose sample can hold m records, grown while it does not
     // change the padded (power-of-two) sort size
@@ -166,25 +175,25 @@ __device__ void final_merge(uint64_t *keys, float *embs, uint32_t *s_counts, vol
         if (valid) r = ld_cand(lists + static_cast<size_t>(j) * m + p);
         keys[i] = r.key; embs[i] = r.emb;
     }
-    named_bar_sync(1, R);
+    named_bar_sync(bar, R);
     if (tr != nullptr && t == 0) tr[1] = globaltimer_ns();
-    bitonic_desc(keys, embs, n2, t);
+    bitonic_desc(keys, embs, n2, t, bar);
     if (tr != nullptr && t == 0) tr[2] = globaltimer_ns();
 
     uint32_t n_final = n2;                       // sorted entries currently in keys[]
     if (m_out > 0) {
         const uint64_t TA = (m_out <= nA) ? keys[m_out - 1] : 0ull;   // 0 => sample holds < m_out valid records
         const uint32_t base = (TA != 0ull) ? m_out : nA;
-        named_bar_sync(1, R);
+        named_bar_sync(bar, R);
         // count extras: records at positions >= c with key > TA
         if (t == 0) { *s_cnt = 0; *s_aux = 0; }
-        named_bar_sync(1, R);
+        named_bar_sync(bar, R);
         uint32_t my_extra = 0;
         for (uint32_t j = t; j < Ln; j += R) my_extra += extras_end(lists + static_cast<size_t>(j) * m, c, s_counts[j], TA) - c;
         if (my_extra) atomicAdd(const_cast<uint32_t *>(s_cnt), my_extra);
-        named_bar_sync(1, R);
+        named_bar_sync(bar, R);
         const uint32_t n_extra = *s_cnt;
-        named_bar_sync(1, R);
+        named_bar_sync(bar, R);
         if (tr != nullptr && t == 0) { tr[3] = globaltimer_ns(); tr[8] = (static_cast<unsigned long long>(total) << 32) | n_extra; tr[9] = (static_cast<unsigned long long>(c) << 32) | n2; }
         if (n_extra != 0 && base + n_extra <= kTopBuf) {
             // append extras after the kept prefix, re-sort
@@ -199,37 +208,37 @@ __device__ void final_merge(uint64_t *keys, float *embs, uint32_t *s_counts, vol
                 }
             }
             n2 = next_pow2(base + n_extra);
-            named_bar_sync(1, R);
+            named_bar_sync(bar, R);
             for (uint32_t i = base + n_extra + t; i < n2; i += R) keys[i] = 0;
-            named_bar_sync(1, R);
-            bitonic_desc(keys, embs, n2, t);
+            named_bar_sync(bar, R);
+            bitonic_desc(keys, embs, n2, t, bar);
             n_final = n2;
         } else if (n_extra != 0) {
             // exact bisection for T* = the m_out-th largest key overall
             if (t == 0) *s_aux = 0;
-            named_bar_sync(1, R);
+            named_bar_sync(bar, R);
             {
                 uint32_t hmax = 0;
                 for (uint32_t j = t; j < Ln; j += R)
                     if (__ldcg(counts + j)) { const uint32_t h = static_cast<uint32_t>(ld_key(lists + static_cast<size_t>(j) * m) >> 32); hmax = h > hmax ? h : hmax; }
                 atomicMax(const_cast<uint32_t *>(s_aux), hmax);
             }
-            named_bar_sync(1, R);
+            named_bar_sync(bar, R);
             uint64_t lo = 1, hi = (static_cast<uint64_t>(*s_aux) << 32) | 0xffffffffull;
             while (lo < hi) {
                 const uint64_t mid = lo + ((hi - lo + 1) >> 1);
-                named_bar_sync(1, R);
+                named_bar_sync(bar, R);
                 if (t == 0) *s_cnt = 0;
-                named_bar_sync(1, R);
+                named_bar_sync(bar, R);
                 uint32_t cnt = 0;
                 for (uint32_t j = t; j < Ln; j += R) cnt += count_ge(lists + static_cast<size_t>(j) * m, 0, __ldcg(counts + j), mid);
                 if (cnt) atomicAdd(const_cast<uint32_t *>(s_cnt), cnt);
-                named_bar_sync(1, R);
+                named_bar_sync(bar, R);
                 if (*s_cnt >= m_out) lo = mid; else hi = mid - 1;
             }
-            named_bar_sync(1, R);
+            named_bar_sync(bar, R);
             if (t == 0) *s_cnt = 0;
-            named_bar_sync(1, R);
+            named_bar_sync(bar, R);
             for (uint32_t j = t; j < Ln; j += R) {
                 const rlr_cand *lj = lists + static_cast<size_t>(j) * m;
                 const uint32_t e_end = count_ge(lj, 0, __ldcg(counts + j), lo);
@@ -239,10 +248,10 @@ __device__ void final_merge(uint64_t *keys, float *embs, uint32_t *s_counts, vol
                 }
             }
             n2 = next_pow2(m_out);
-            named_bar_sync(1, R);
+            named_bar_sync(bar, R);
             for (uint32_t i = m_out + t; i < n2; i += R) keys[i] = 0;
-            named_bar_sync(1, R);
-            bitonic_desc(keys, embs, n2, t);
+            named_bar_sync(bar, R);
+            bitonic_desc(keys, embs, n2, t, bar);
             n_final = n2;
         }
     }
@@ -301,17 +310,22 @@ template <> struct LatSel<true> { typedef LatParams type; };
 
 // kLat: latency path for small f32 stores -- the query and the lexical pairs come from the parameter block `lp`
 // (no H2D copy), and the last CTA delivers the result into mapped pinned host memory (lp.mode, see LatParams).
-template <bool kHalf, bool kLat>
-__global__ void __launch_bounds__(kScanThreads, 1)
-scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ g_query,
+// NQ: QUERY GROUPS.  NQ > 1 answers NQ queries in ONE pass over the rows: the CTA has NQ groups of four consumer
+// warps; every group owns one query (its own copy of the query, candidate buffer, thresholds, named barrier, per-CTA
+// list and cross-CTA ticket) and all groups consume the SAME shared-memory stages -- each tile crosses HBM once and
+// feeds NQ exact sequential chains per row.  (row, query) arithmetic is untouched, so results are bit-identical to
+// NQ separate scans; HBM bytes per query drop by NQ.  Throughput mode only (rlr_search_mmr_multi).
+template <bool kHalf, bool kLat, int NQ>
+__global__ void __launch_bounds__(R * NQ + 64, 1)
+scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ScanGroups io,
                  uint32_t n_rows, uint32_t row_base, uint32_t n_chunks, float w_embed, float w_lex,
-                 const uint32_t *g_lex_rows, const float *g_lex_norm, uint32_t n_lex,
-                 uint32_t m, uint32_t buf_cap, uint32_t r_pub, int n_stages, rlr_cand *g_lists, uint32_t *g_counts,
-                 uint32_t *g_pub, uint32_t *g_ticket, uint32_t *g_tile_ctr, rlr_cand *g_out, uint32_t *g_out_n,
-                 unsigned long long *g_trace /* dev-only phase timestamps, may be null */, const ScanPost post,
+                 uint32_t m, uint32_t buf_cap, uint32_t r_pub, int n_stages, rlr_cand *g_lists_all, uint32_t *g_counts_all,
+                 uint32_t *g_pub_all, uint32_t *g_tickets, uint32_t *g_tile_ctr,
+                 unsigned long long *g_trace /* dev-only phase timestamps, may be null */,
                  uint32_t rpt /* rows per tile: a multiple of 8, <= R; the tensor map's box has this many rows */,
                  const __grid_constant__ typename LatSel<kLat>::type lp)
 {
+    static_assert(!kLat || NQ == 1, "the latency path answers one query per launch");
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B atoms are 1024 B: align the carve-up by hand.
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -319,58 +333,79 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
     uint8_t *smem = smem_raw + pad;
 
     constexpr uint32_t EPB = kHalf ? 64u : 32u;        // elements per 128-byte box row
+    constexpr uint32_t kThreads = R * NQ + 64;
+    constexpr uint32_t kConsWarps = (R / 32) * NQ;
     const uint32_t KB = (n_chunks + CH - 1) / CH;      // pipeline stages consumed per tile
     const uint32_t q_floats = KB * CH * EPB;
-    const SmemLayout L = smem_layout(n_stages, q_floats, kLat);
+    const SmemLayout L = smem_layout(n_stages, q_floats, kLat, NQ);
 
-    float *q_s = reinterpret_cast<float *>(smem + L.q_off);
-    uint64_t *keys = reinterpret_cast<uint64_t *>(smem + L.keys_off);
-    float *embs = reinterpret_cast<float *>(smem + L.embs_off);
-    volatile uint32_t *s_count = reinterpret_cast<volatile uint32_t *>(smem + L.misc_off);
-    volatile uint64_t *s_tau = reinterpret_cast<volatile uint64_t *>(smem + L.misc_off + 8);
-    volatile uint32_t *s_flag = reinterpret_cast<volatile uint32_t *>(smem + L.misc_off + 16);
-    volatile uint32_t *s_tau_g = reinterpret_cast<volatile uint32_t *>(smem + L.misc_off + 20);
-    volatile uint32_t *s_done = reinterpret_cast<volatile uint32_t *>(smem + L.misc_off + 24);
-    volatile uint32_t *s_ntop = reinterpret_cast<volatile uint32_t *>(smem + L.misc_off + 28);
-    volatile uint64_t *s_top = reinterpret_cast<volatile uint64_t *>(smem + L.misc_off + 32);   // [kTopR]
+    const uint32_t tid = threadIdx.x;
+    const uint32_t warp = tid >> 5, lane = tid & 31;
+    const uint32_t grp = warp < kConsWarps ? warp / (R / 32) : 0;        // query group of a consumer warp
+    const uint32_t bar = 1 + grp;                                        // the group's named barrier (R threads)
+    uint8_t *gs = smem + L.grp_off + grp * L.grp_stride;
+
+    float *q_s = reinterpret_cast<float *>(gs + L.q_rel);
+    uint64_t *keys = reinterpret_cast<uint64_t *>(gs + L.keys_rel);
+    float *embs = reinterpret_cast<float *>(gs + L.embs_rel);
+    volatile uint32_t *s_count = reinterpret_cast<volatile uint32_t *>(gs + L.misc_rel);
+    volatile uint64_t *s_tau = reinterpret_cast<volatile uint64_t *>(gs + L.misc_rel + 8);
+    volatile uint32_t *s_flag = reinterpret_cast<volatile uint32_t *>(gs + L.misc_rel + 16);
+    volatile uint32_t *s_tau_g = reinterpret_cast<volatile uint32_t *>(gs + L.misc_rel + 20);
+    volatile uint32_t *s_done = reinterpret_cast<volatile uint32_t *>(gs + L.misc_rel + 24);
+    volatile uint32_t *s_ntop = reinterpret_cast<volatile uint32_t *>(gs + L.misc_rel + 28);
+    volatile uint64_t *s_top = reinterpret_cast<volatile uint64_t *>(gs + L.misc_rel + 32);   // [kTopR]
     // tile-id mailbox, one slot per pipeline stage (<= 8): the slot belongs to whoever owns the
     // stage, so the producer can run any number of tiles ahead without overwriting an unread id
-    volatile uint32_t *s_tile = reinterpret_cast<volatile uint32_t *>(smem + L.misc_off + 96);
+    volatile uint32_t *s_tile = reinterpret_cast<volatile uint32_t *>(smem + L.tile_off);
     const uint32_t stages_addr = smem_u32(smem + L.stages_off);
     const uint32_t full_bar = smem_u32(smem + L.bars_off);
     const uint32_t empty_bar = full_bar + n_stages * 8;
 
-    const uint32_t tid = threadIdx.x;
-    const uint32_t warp = tid >> 5, lane = tid & 31;
+    // this group's slice of the per-launch global workspace and its outputs
+    rlr_cand *g_lists = g_lists_all + static_cast<size_t>(grp) * gridDim.x * m;
+    uint32_t *g_counts = g_counts_all + grp * gridDim.x;
+    uint32_t *g_pub = g_pub_all + grp * gridDim.x;
+    uint32_t *g_ticket = g_tickets + grp;
+    rlr_cand *g_out = io.g[grp].out;
+    uint32_t *g_out_n = io.g[grp].out_n;
+    const ScanPost post = io.g[grp].post;
+
     const uint32_t n_tiles = (n_rows + rpt - 1) / rpt;
-    const uint32_t *lex_rows = g_lex_rows;
-    const float *lex_norm = g_lex_norm;
+    const uint32_t *lex_rows = io.g[grp].lex_rows;
+    const float *lex_norm = io.g[grp].lex_norm;
+    const uint32_t n_lex = io.g[grp].n_lex;
     if constexpr (kLat) {
         uint32_t *lr = reinterpret_cast<uint32_t *>(smem + L.lex_off);
         float *ln = reinterpret_cast<float *>(smem + L.lex_off + kLatLex * 4);
-        for (uint32_t i = tid; i < n_lex; i += kScanThreads) { lr[i] = lp.lex_rows[i]; ln[i] = lp.lex_norm[i]; }
+        for (uint32_t i = tid; i < n_lex; i += kThreads) { lr[i] = lp.lex_rows[i]; ln[i] = lp.lex_norm[i]; }
         lex_rows = lr; lex_norm = ln;
     }
 
     if (tid == 0) {
         for (int s = 0; s < n_stages; ++s) {
             mbar_init(full_bar + s * 8, 1);
-            mbar_init(empty_bar + s * 8, R / 32);
+            mbar_init(empty_bar + s * 8, kConsWarps);          // every consumer warp of every group arrives
         }
-        *s_count = 0;
-        *s_tau = 0;
-        *s_flag = 0;
-        *s_tau_g = 0;
-        *s_done = 0;
-        *s_ntop = 0;
         fence_mbar_init();
     }
-    if constexpr (kLat) { for (uint32_t i = tid; i < q_floats; i += kScanThreads) q_s[i] = lp.q[i]; }
-    else { for (uint32_t i = tid; i < q_floats; i += kScanThreads) q_s[i] = g_query[i]; }
+    if (warp < kConsWarps) {
+        const uint32_t tg = tid - grp * R;
+        if (tg == 0) {
+            *s_count = 0;
+            *s_tau = 0;
+            *s_flag = 0;
+            *s_tau_g = 0;
+            *s_done = 0;
+            *s_ntop = 0;
+        }
+        if constexpr (kLat) { for (uint32_t i = tg; i < q_floats; i += R) q_s[i] = lp.q[i]; }
+        else { const float *gq = io.g[grp].query; for (uint32_t i = tg; i < q_floats; i += R) q_s[i] = gq[i]; }
+    }
     __syncthreads();
     if (g_trace != nullptr && tid == 0) g_trace[blockIdx.x] = globaltimer_ns();
 
-    if (warp == R / 32) {
+    if (warp == kConsWarps) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
             tma_prefetch_desc(&tmap);
@@ -402,26 +437,36 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
         }
         return;
     }
-    if (warp == R / 32 + 1) {
+    if (warp == kConsWarps + 1) {
         // ---------------- threshold warp: global lower bound of the m-th best score ----------------
         // Every CTA publishes the score of its r-th best row so far, r = ceil(m / grid).  All
         // CTAs then hold >= r rows at or above min_j pub[j], i.e. >= m rows in total, so the
         // global m-th best score is >= that minimum at any moment: rows strictly below it can
         // be dropped without ever entering a buffer.  Stale reads only make the bound looser.
+        // One warp serves every query group.
         if (r_pub == 0) return;
-        const volatile uint32_t *pub = g_pub;
-        while (*s_done == 0) {
-            uint32_t v = 0xffffffffu;
-            for (uint32_t j = lane; j < gridDim.x; j += 32) { const uint32_t u = pub[j]; v = u < v ? u : v; }
-            v = __reduce_min_sync(0xffffffffu, v);
-            if (lane == 0 && v > *s_tau_g) *s_tau_g = v;
+        for (;;) {
+            bool all_done = true;
+#pragma unroll
+            for (int g = 0; g < NQ; ++g) {
+                uint8_t *gg = smem + L.grp_off + g * L.grp_stride + L.misc_rel;
+                volatile uint32_t *tau_g = reinterpret_cast<volatile uint32_t *>(gg + 20);
+                if (*reinterpret_cast<volatile uint32_t *>(gg + 24) != 0) continue;       // this group's consumers left the loop
+                all_done = false;
+                const volatile uint32_t *pub = g_pub_all + g * gridDim.x;
+                uint32_t v = 0xffffffffu;
+                for (uint32_t j = lane; j < gridDim.x; j += 32) { const uint32_t u = pub[j]; v = u < v ? u : v; }
+                v = __reduce_min_sync(0xffffffffu, v);
+                if (lane == 0 && v > *tau_g) *tau_g = v;
+            }
+            if (all_done) break;
             __nanosleep(400);
         }
         return;
     }
 
     // --------------------------------- consumers ---------------------------------
-    const uint32_t t = tid;                       // row of the tile owned by this thread
+    const uint32_t t = tid - grp * R;             // row of the tile owned by this thread (within its query group)
     const uint32_t xr = (t & 7u) << 4;            // SWIZZLE_128B: 16B-chunk index ^= row & 7
     const uint8_t *stage0 = smem + L.stages_off + t * 128;
     const float4 *q4 = reinterpret_cast<const float4 *>(q_s);
@@ -493,17 +538,17 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
                 embs[idx] = acc;
             }
         }
-        named_bar_sync(1, R);
+        named_bar_sync(bar, R);
         uint32_t cnt = *s_count;
         if (warp == 0 && r_pub != 0 && cnt > prev_cnt)
             top_r_update_warp(keys, prev_cnt, cnt, s_top, s_ntop, r_pub, lane, g_pub + blockIdx.x);
-        named_bar_sync(1, R);
+        named_bar_sync(bar, R);
         if (cnt > buf_cap - R) {
             // prune: keep the best m, raise the threshold.  buf_cap (a power of two <= kTopBuf)
             // is sized so that one prune costs about as much HBM time as the TMA ring holds.
             for (uint32_t i = cnt + t; i < buf_cap; i += R) keys[i] = 0;
-            named_bar_sync(1, R);
-            bitonic_desc(keys, embs, buf_cap, t);
+            named_bar_sync(bar, R);
+            bitonic_desc(keys, embs, buf_cap, t, bar);
             if (t == 0) {
                 const uint32_t kept = cnt < m ? cnt : m;
                 *s_count = kept;
@@ -516,18 +561,19 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
                         *reinterpret_cast<volatile uint32_t *>(g_pub + blockIdx.x) = static_cast<uint32_t>(keys[r_pub - 1] >> 32);
                 }
             }
-            named_bar_sync(1, R);
+            named_bar_sync(bar, R);
             tau = *s_tau;
             cnt = *s_count;
-            named_bar_sync(1, R);             // reads done before the next tile's appends bump s_count
+            named_bar_sync(bar, R);             // reads done before the next tile's appends bump s_count
         }
         prev_cnt = cnt;
     }
 
     // ---- final: drop what the freshest global bound excludes, sort the rest, write the list ----
-    if (g_trace != nullptr && t == 0) g_trace[gridDim.x + blockIdx.x] = globaltimer_ns();
+    if constexpr (NQ > 1) named_bar_sync(15, R * NQ);     // every group has consumed its last stage: the ring is idle for all
+    if (g_trace != nullptr && tid == 0) g_trace[gridDim.x + blockIdx.x] = globaltimer_ns();
     if (t == 0) { *s_done = 1; *s_flag = 0xffffffffu; }
-    named_bar_sync(1, R);
+    named_bar_sync(bar, R);
     const uint32_t cnt = *s_count;
     if (r_pub != 0) {
         const volatile uint32_t *pub = g_pub;
@@ -536,14 +582,15 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
         v = __reduce_min_sync(0xffffffffu, v);
         if (lane == 0) atomicMin(const_cast<uint32_t *>(s_flag), v);
     }
-    named_bar_sync(1, R);                     // everyone has read cnt; the atomicMin results are in
+    named_bar_sync(bar, R);                     // everyone has read cnt; the atomicMin results are in
     uint32_t tau_fin = *s_tau_g;
     if (r_pub != 0 && *s_flag > tau_fin) tau_fin = *s_flag;
     if (t == 0) *s_count = 0;
-    named_bar_sync(1, R);
+    named_bar_sync(bar, R);
     // the TMA ring is idle now (every issued load was consumed): reuse it as the compaction target
-    uint64_t *keys2 = reinterpret_cast<uint64_t *>(smem + L.stages_off);
-    float *embs2 = reinterpret_cast<float *>(smem + L.stages_off + kTopBuf * 8);
+    uint8_t *scratch = smem + L.stages_off + grp * kGroupScratch;          // this group's slice of the idle ring
+    uint64_t *keys2 = reinterpret_cast<uint64_t *>(scratch);
+    float *embs2 = reinterpret_cast<float *>(scratch + kTopBuf * 8);
     for (uint32_t i0 = 0; i0 < cnt; i0 += R) {
         const uint32_t i = i0 + t;
         const uint64_t k = i < cnt ? keys[i] : 0ull;
@@ -560,12 +607,12 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
             }
         }
     }
-    named_bar_sync(1, R);
+    named_bar_sync(bar, R);
     const uint32_t cnt2 = *s_count;
     const uint32_t n2 = next_pow2(cnt2);
     for (uint32_t i = cnt2 + t; i < n2; i += R) keys2[i] = 0;
-    named_bar_sync(1, R);
-    bitonic_desc(keys2, embs2, n2, t);
+    named_bar_sync(bar, R);
+    bitonic_desc(keys2, embs2, n2, t, bar);
     const uint32_t keep = cnt2 < m ? cnt2 : m;
     rlr_cand *out = g_lists + static_cast<size_t>(blockIdx.x) * m;
     for (uint32_t i = t; i < keep; i += R) {       // records beyond `keep` are never read
@@ -576,27 +623,29 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
         out[i] = c;
     }
     if (t == 0) g_counts[blockIdx.x] = keep;
-    if (g_trace != nullptr && t == 0) {
+    if (g_trace != nullptr && tid == 0) {
         g_trace[2 * gridDim.x + blockIdx.x] = globaltimer_ns();
         g_trace[3 * gridDim.x + blockIdx.x] = (static_cast<unsigned long long>(n_my_tiles) << 48) | (static_cast<unsigned long long>(cnt) << 24) | cnt2;
     }
 
     // ---- cross-CTA merge, done by whichever CTA finishes last (no second launch) ----
     __threadfence();
-    named_bar_sync(1, R);
+    named_bar_sync(bar, R);
     if (t == 0) {
         const uint32_t ticket = atomicAdd(g_ticket, 1u);
         *s_flag = (ticket == gridDim.x - 1) ? 1u : 0u;
     }
-    named_bar_sync(1, R);
+    named_bar_sync(bar, R);
     const uint32_t is_last = *s_flag;
-    named_bar_sync(1, R);                     // s_flag is reused below: everyone reads it first
+    named_bar_sync(bar, R);                     // s_flag is reused below: everyone reads it first
     if (is_last == 0) return;
     __threadfence();
-    if (t == 0) { *g_ticket = 0; *g_tile_ctr = 0; } // stream-ordered launches reuse the ticket, the tile counter ...
+    // stream-ordered launches reuse the ticket, the tile counter (every producer is done once ANY group's last CTA
+    // gets here: all CTAs' consumers of that group have seen the end marker) ...
+    if (t == 0) { *g_ticket = 0; if (grp == 0) *g_tile_ctr = 0; }
     for (uint32_t j = t; j < gridDim.x; j += R) g_pub[j] = 0;   // ... and the published bounds
     if (g_out == nullptr) return;
-    unsigned long long *tr = g_trace != nullptr ? g_trace + 4 * gridDim.x : nullptr;
+    unsigned long long *tr = (g_trace != nullptr && grp == 0) ? g_trace + 4 * gridDim.x : nullptr;
     if (tr != nullptr && t == 0) tr[0] = globaltimer_ns();
     if (post.flag != nullptr) {
         // fused exchange: g_out is a mailbox slot (possibly in a peer GPU's HBM); it is free once
@@ -614,14 +663,14 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
             }
             s_tile[0] = timed_out;            // the tile mailbox is idle: the producer has exited
         }
-        named_bar_sync(1, R);
+        named_bar_sync(bar, R);
         if (s_tile[0] != 0) return;
     }
-    final_merge(keys, embs, reinterpret_cast<uint32_t *>(smem + L.stages_off + kTopBuf * 12), s_count, s_flag, g_lists,
-                g_counts, gridDim.x, m, row_base, lex_rows, lex_norm, n_lex, g_out, g_out_n, t, tr);
+    final_merge(keys, embs, reinterpret_cast<uint32_t *>(scratch + kTopBuf * 12), s_count, s_flag, g_lists,
+                g_counts, gridDim.x, m, row_base, lex_rows, lex_norm, n_lex, g_out, g_out_n, t, tr, bar);
     if (post.flag != nullptr) {
         __threadfence_system();               // every writer: the records are visible system-wide ...
-        named_bar_sync(1, R);
+        named_bar_sync(bar, R);
         if (t == 0) st_release_sys_u64(post.flag, post.seq);   // ... before the flag says so
     }
     if constexpr (kLat) {
@@ -630,7 +679,7 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
             // final_merge left the pool in g_out (device memory).  Stage the records and their rows in the idle TMA
             // ring, compute every pairwise dot with the reference's sequential arithmetic, run the greedy loop, and
             // let thread 0 write the selection straight into the host's mapped result block.
-            named_bar_sync(1, R);                                         // g_out / g_out_n written by this CTA
+            named_bar_sync(bar, R);                                         // g_out / g_out_n written by this CTA
             const uint32_t P = *reinterpret_cast<volatile uint32_t *>(g_out_n);
             uint8_t *ring = smem + L.stages_off;
             rlr_cand *pool_s = reinterpret_cast<rlr_cand *>(ring);                                  // 32 x 16 B
@@ -640,7 +689,7 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
             uint8_t *rows_s = ring + 4096;
             const uint32_t row_stride = lp.pitch * 4u + 16u;              // +16 B: LDS.128 of different rows on different bank groups
             if (t < P) pool_s[t] = g_out[t];
-            named_bar_sync(1, R);
+            named_bar_sync(bar, R);
             const uint32_t vpr = lp.pitch / 4u;                           // 16-byte vectors per row
             // cp.async (LDGSTS, 16 B each, L2 only): every load of the pool's rows is in flight at once -- one L2 round
             // trip instead of one per loop iteration (6 us -> ~1 us for 15 x 3 KB)
@@ -651,7 +700,7 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
-            named_bar_sync(1, R);
+            named_bar_sync(bar, R);
             if (tr != nullptr && t == 0) tr[5] = globaltimer_ns();
             const uint32_t n_pairs = P * (P - 1u) / 2u;
             for (uint32_t pr = t; pr < n_pairs; pr += R) {
@@ -671,7 +720,7 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
                 }
                 tri_s[pr] = acc;
             }
-            named_bar_sync(1, R);
+            named_bar_sync(bar, R);
             if (tr != nullptr && t == 0) tr[6] = globaltimer_ns();
             if (P == 0) { if (t == 0) *lp.result_n = 0; }
             else greedy_loop<1>(tri_s, pool_s, nullptr, P, lp.top_k, lp.lambda, lp.d_sel_pos, lp.result_n, lp.result, t, s_best, s_besti);
@@ -680,7 +729,7 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
         } else if (lp.mode == 1u) {
             // the merged top-m went straight into the host's mapped block (g_out / g_out_n point there)
             __threadfence_system();
-            named_bar_sync(1, R);
+            named_bar_sync(bar, R);
             if (t == 0) st_release_sys_u64(lp.flag, lp.seq);
         }
     }
@@ -689,13 +738,15 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
 
 } // namespace
 
-void scan_plan(int sm_count, int max_smem_optin, uint32_t n_rows, uint32_t pitch, int half, ScanArgs *a)
+void scan_plan(int sm_count, int max_smem_optin, uint32_t n_rows, uint32_t pitch, int half, ScanArgs *a, uint32_t n_groups)
 {
     const uint32_t epb = half ? 64u : 32u;
     const uint32_t n_chunks = pitch / epb;
     const uint32_t KB = (n_chunks + CH - 1) / CH;
     const uint32_t q_floats = KB * CH * epb;
+    if (n_groups < 1) n_groups = 1;
     a->half = half;
+    a->n_groups = n_groups;
     const uint32_t n_tiles = (n_rows + R - 1) / R;
     // tuning knob: leave a few SMs to other streams' small kernels (merge / MMR of the previous query)
     // (default 2: measured on a B200, the scan reads HBM just as fast from 140 SMs as from 148 -- 7.52 TB/s either
@@ -704,13 +755,15 @@ void scan_plan(int sm_count, int max_smem_optin, uint32_t n_rows, uint32_t pitch
     int grid = sm_count - (reserved > 0 && reserved < sm_count ? reserved : 0);
     if (static_cast<uint32_t>(grid) > n_tiles) grid = static_cast<int>(n_tiles);
     if (grid < 1) grid = 1;
-    // as many stages as fit (1 KB slack for the manual 1024 B alignment)
+    // as many stages as fit (1 KB slack for the manual 1024 B alignment); the tail of every query group uses
+    // kGroupScratch bytes of the idle ring, so the ring must hold n_groups of those
     int stages = 8;
-    while (stages > 2 && smem_layout(stages, q_floats).total + 1024 > static_cast<uint32_t>(max_smem_optin)) --stages;
+    while (stages > 2 && smem_layout(stages, q_floats, false, n_groups).total + 1024 > static_cast<uint32_t>(max_smem_optin)) --stages;
     a->grid = grid;
     a->n_stages = stages;
     a->buf_cap = 0;
-    a->smem_bytes = static_cast<int>(smem_layout(stages, q_floats).total + 1024);
+    a->smem_bytes = static_cast<int>(smem_layout(stages, q_floats, false, n_groups).total + 1024);
+    if (static_cast<uint32_t>(stages) * kStageBytes < n_groups * kGroupScratch) a->grid = 0;     // does not fit: the caller reports it
 }
 
 uint32_t scan_rows_per_tile(int sm_count, uint64_t n_rows)
@@ -748,11 +801,12 @@ cudaError_t scan_configure()
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(scan_topm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(scan_topm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(scan_topm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+#define RLR_CFG(...) if (e == cudaSuccess) e = cudaFuncSetAttribute(scan_topm_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)
+    RLR_CFG(false, false, 1); RLR_CFG(false, false, 2); RLR_CFG(false, false, 3);
+    RLR_CFG(true, false, 1);  RLR_CFG(true, false, 2);  RLR_CFG(true, false, 3);
+    RLR_CFG(false, true, 1);
+#undef RLR_CFG
+    return e;
 }
 
 // candidate-buffer capacity for a given m: room for m kept + a few tiles of new entries
@@ -780,21 +834,34 @@ cudaError_t scan_launch(const ScanArgs &a, cudaStream_t stream)
     const uint32_t n_chunks = a.pitch / (a.half ? 64u : 32u);
     const uint32_t rpt = a.rows_per_tile ? a.rows_per_tile : static_cast<uint32_t>(R);
     const NoLat nolat = {0};
-    if (a.lat != nullptr && !a.half)
-        scan_topm_kernel<false, true><<<a.grid, kScanThreads, a.smem_bytes, stream>>>(
-            *a.tmap, nullptr, a.n_rows, a.row_base, n_chunks, a.w_embed, a.w_lex, nullptr, nullptr, a.n_lex,
-            a.m, buf_cap, r_pub, a.n_stages, a.d_lists, a.d_counts, a.d_pub, a.d_ticket, a.d_ticket + 1,
-            a.d_out, a.d_out_n, a.d_trace, a.post, rpt, *a.lat);
-    else if (a.half)
-        scan_topm_kernel<true, false><<<a.grid, kScanThreads, a.smem_bytes, stream>>>(
-            *a.tmap, a.d_query, a.n_rows, a.row_base, n_chunks, a.w_embed, a.w_lex, a.d_lex_rows, a.d_lex_norm, a.n_lex,
-            a.m, buf_cap, r_pub, a.n_stages, a.d_lists, a.d_counts, a.d_pub, a.d_ticket, a.d_ticket + 1,
-            no_merge ? nullptr : a.d_out, a.d_out_n, a.d_trace, a.post, rpt, nolat);
-    else
-        scan_topm_kernel<false, false><<<a.grid, kScanThreads, a.smem_bytes, stream>>>(
-            *a.tmap, a.d_query, a.n_rows, a.row_base, n_chunks, a.w_embed, a.w_lex, a.d_lex_rows, a.d_lex_norm, a.n_lex,
-            a.m, buf_cap, r_pub, a.n_stages, a.d_lists, a.d_counts, a.d_pub, a.d_ticket, a.d_ticket + 1,
-            no_merge ? nullptr : a.d_out, a.d_out_n, a.d_trace, a.post, rpt, nolat);
+    const uint32_t nq = a.n_groups > 1 ? a.n_groups : 1;
+    if (nq > static_cast<uint32_t>(kMaxQueryGroups) || a.grid <= 0) return cudaErrorInvalidValue;
+    ScanGroups io;
+    memset(&io, 0, sizeof io);
+    if (nq == 1) {
+        io.g[0].query = a.d_query; io.g[0].out = a.d_out; io.g[0].out_n = a.d_out_n; io.g[0].post = a.post;
+        io.g[0].lex_rows = a.d_lex_rows; io.g[0].lex_norm = a.d_lex_norm; io.g[0].n_lex = a.n_lex;
+    }
+    else io = a.groups;
+    if (no_merge) for (uint32_t g = 0; g < nq; ++g) io.g[g].out = nullptr;
+#define RLR_SCAN_ARGS *a.tmap, io, a.n_rows, a.row_base, n_chunks, a.w_embed, a.w_lex, \
+                      a.m, buf_cap, r_pub, a.n_stages, a.d_lists, a.d_counts, a.d_pub, a.d_ticket, a.d_ticket + 4, a.d_trace, rpt
+    const int threads = R * static_cast<int>(nq) + 64;
+    if (a.lat != nullptr && !a.half && nq == 1) {
+        io.g[0].query = nullptr; io.g[0].lex_rows = nullptr; io.g[0].lex_norm = nullptr;     // they ride in the parameter block
+        scan_topm_kernel<false, true, 1><<<a.grid, threads, a.smem_bytes, stream>>>(
+            *a.tmap, io, a.n_rows, a.row_base, n_chunks, a.w_embed, a.w_lex,
+            a.m, buf_cap, r_pub, a.n_stages, a.d_lists, a.d_counts, a.d_pub, a.d_ticket, a.d_ticket + 4, a.d_trace, rpt, *a.lat);
+    } else if (a.half) {
+        if (nq == 1) scan_topm_kernel<true, false, 1><<<a.grid, threads, a.smem_bytes, stream>>>(RLR_SCAN_ARGS, nolat);
+        else if (nq == 2) scan_topm_kernel<true, false, 2><<<a.grid, threads, a.smem_bytes, stream>>>(RLR_SCAN_ARGS, nolat);
+        else scan_topm_kernel<true, false, 3><<<a.grid, threads, a.smem_bytes, stream>>>(RLR_SCAN_ARGS, nolat);
+    } else {
+        if (nq == 1) scan_topm_kernel<false, false, 1><<<a.grid, threads, a.smem_bytes, stream>>>(RLR_SCAN_ARGS, nolat);
+        else if (nq == 2) scan_topm_kernel<false, false, 2><<<a.grid, threads, a.smem_bytes, stream>>>(RLR_SCAN_ARGS, nolat);
+        else scan_topm_kernel<false, false, 3><<<a.grid, threads, a.smem_bytes, stream>>>(RLR_SCAN_ARGS, nolat);
+    }
+#undef RLR_SCAN_ARGS
     return cudaGetLastError();
 }
 

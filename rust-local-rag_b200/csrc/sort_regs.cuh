@@ -7,7 +7,7 @@ namespace rlr {
 
 namespace {
 
-constexpr int kSortThreads = kScanRows;   // the R consumer threads, named barrier 1
+constexpr int kSortThreads = kScanRows;   // the R threads of one consumer group; `bar` = that group's named barrier
 #define R kSortThreads
 
 // ---------------------------------------------------------------------------------
@@ -47,7 +47,7 @@ __device__ __forceinline__ void ce_in_regs(uint64_t (&k)[E], float (&v)[E], uint
 // one sub-stage (compile-time K, J) of the network over the thread's E registers
 template <int E, uint32_t K, uint32_t J>
 __device__ __forceinline__ void substage(uint64_t (&k)[E], float (&v)[E], uint64_t *skeys, float *sembs, uint32_t g0,
-                                         uint32_t lane)
+                                         uint32_t lane, uint32_t bar)
 {
     if constexpr (J < static_cast<uint32_t>(E)) {
         ce_in_regs<E, static_cast<int>(J)>(k, v, g0, K);
@@ -69,12 +69,12 @@ __device__ __forceinline__ void substage(uint64_t (&k)[E], float (&v)[E], uint64
     } else {
 #pragma unroll
         for (int e = 0; e < E; ++e) { skeys[g0 + e] = k[e]; sembs[g0 + e] = v[e]; }
-        named_bar_sync(1, R);
+        named_bar_sync(bar, R);
         uint64_t ok[E];
         float ov[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) { ok[e] = skeys[(g0 + e) ^ J]; ov[e] = sembs[(g0 + e) ^ J]; }
-        named_bar_sync(1, R);
+        named_bar_sync(bar, R);
         const bool is_lower = (g0 & J) == 0;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
@@ -86,22 +86,22 @@ __device__ __forceinline__ void substage(uint64_t (&k)[E], float (&v)[E], uint64
 
 template <int E, uint32_t K, uint32_t J>
 __device__ __forceinline__ void stage_from(uint64_t (&k)[E], float (&v)[E], uint64_t *skeys, float *sembs, uint32_t g0,
-                                           uint32_t lane)
+                                           uint32_t lane, uint32_t bar)
 {
-    substage<E, K, J>(k, v, skeys, sembs, g0, lane);
-    if constexpr (J > 1) stage_from<E, K, J / 2>(k, v, skeys, sembs, g0, lane);
+    substage<E, K, J>(k, v, skeys, sembs, g0, lane, bar);
+    if constexpr (J > 1) stage_from<E, K, J / 2>(k, v, skeys, sembs, g0, lane, bar);
 }
 
 template <int E, uint32_t K>
 __device__ __forceinline__ void network_from(uint64_t (&k)[E], float (&v)[E], uint64_t *skeys, float *sembs, uint32_t g0,
-                                             uint32_t lane)
+                                             uint32_t lane, uint32_t bar)
 {
-    stage_from<E, K, K / 2>(k, v, skeys, sembs, g0, lane);
-    if constexpr (K < static_cast<uint32_t>(E) * R) network_from<E, K * 2>(k, v, skeys, sembs, g0, lane);
+    stage_from<E, K, K / 2>(k, v, skeys, sembs, g0, lane, bar);
+    if constexpr (K < static_cast<uint32_t>(E) * R) network_from<E, K * 2>(k, v, skeys, sembs, g0, lane, bar);
 }
 
 template <int E>
-__device__ __noinline__ void sort_desc_regs(uint64_t *skeys, float *sembs, uint32_t t)
+__device__ __noinline__ void sort_desc_regs(uint64_t *skeys, float *sembs, uint32_t t, uint32_t bar)
 {
     uint64_t k[E];
     float v[E];
@@ -109,27 +109,27 @@ __device__ __noinline__ void sort_desc_regs(uint64_t *skeys, float *sembs, uint3
     const uint32_t lane = t & 31;
 #pragma unroll
     for (int e = 0; e < E; ++e) { k[e] = skeys[g0 + e]; v[e] = sembs[g0 + e]; }
-    named_bar_sync(1, R);                       // everyone has read its block before anyone overwrites
-    network_from<E, 2>(k, v, skeys, sembs, g0, lane);   // the whole network, unrolled at compile time
+    named_bar_sync(bar, R);                       // everyone has read its block before anyone overwrites
+    network_from<E, 2>(k, v, skeys, sembs, g0, lane, bar);   // the whole network, unrolled at compile time
 #pragma unroll
     for (int e = 0; e < E; ++e) { skeys[g0 + e] = k[e]; sembs[g0 + e] = v[e]; }
-    named_bar_sync(1, R);
+    named_bar_sync(bar, R);
 }
 
 // n must be a power of two <= kTopBuf; entries [n, max(n, R)) are zeroed here when n < R
-__device__ __noinline__ void bitonic_desc(uint64_t *keys, float *embs, uint32_t n, uint32_t t)
+__device__ __noinline__ void bitonic_desc(uint64_t *keys, float *embs, uint32_t n, uint32_t t, uint32_t bar = 1)
 {
     if (n < static_cast<uint32_t>(R)) {
         for (uint32_t i = n + t; i < static_cast<uint32_t>(R); i += R) keys[i] = 0;
-        named_bar_sync(1, R);
+        named_bar_sync(bar, R);
         n = R;
     }
     switch (n / R) {
-    case 1: sort_desc_regs<1>(keys, embs, t); break;
-    case 2: sort_desc_regs<2>(keys, embs, t); break;
-    case 4: sort_desc_regs<4>(keys, embs, t); break;
-    case 8: sort_desc_regs<8>(keys, embs, t); break;
-    default: sort_desc_regs<16>(keys, embs, t); break;
+    case 1: sort_desc_regs<1>(keys, embs, t, bar); break;
+    case 2: sort_desc_regs<2>(keys, embs, t, bar); break;
+    case 4: sort_desc_regs<4>(keys, embs, t, bar); break;
+    case 8: sort_desc_regs<8>(keys, embs, t, bar); break;
+    default: sort_desc_regs<16>(keys, embs, t, bar); break;
     }
 }
 

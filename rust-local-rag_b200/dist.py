@@ -415,10 +415,12 @@ class CudaBackend:
         if self.peer_set:
             self.lib.rlr_peer_set_close(self.peer_set)
             self.peer_set = None
-        for c in getattr(self, "ctxs", [self.ctx]):
+        for c in list(getattr(self, "ctxs", [self.ctx])) + list(getattr(self, "_extra_ctxs", [])):
             if c:
                 self.lib.rlr_ctx_destroy(c)
         self.ctxs = []
+        self._extra_ctxs = []
+        self._multi_ctxs = {}
         self.ctx = None
 
     @staticmethod
@@ -458,6 +460,26 @@ class CudaBackend:
         # single GPU: candidates are read straight from the store (no gather)
         self.B.check(self.lib.rlr_mmr_store_async(self.ctx, self._p(pool), self._p(pool_n), p_cap, top_k, lam,
                                                   self._p(sel_pos), self._p(sel_n), self._p(result), self._stream()))
+
+    def search_mmr_multi(self, queries, top_k, diversity_factor, w_embed, w_lex, results, result_ns):
+        """throughput mode (rlr_search_mmr_multi_async): len(queries) <= RLR_MAX_MULTI queries, ONE pass over the rows.
+        Each lane keeps its own set of per-query ctxs (pool / MMR buffers); query 0 uses the lane's ctx."""
+        nq = len(queries)
+        key = id(self.ctx) if not isinstance(self.ctx, C.c_void_p) else self.ctx.value
+        sets = self.__dict__.setdefault("_multi_ctxs", {})
+        cs = sets.setdefault(key, [self.ctx])
+        while len(cs) < nq:
+            c = C.c_void_p()
+            self.B.check(self.lib.rlr_ctx_create(self.store.handle, C.byref(c)))
+            if self.search_flags:
+                self.B.check(self.lib.rlr_ctx_set_flags(c, self.search_flags))
+            cs.append(c)
+            self.__dict__.setdefault("_extra_ctxs", []).append(c)
+        arr = lambda ptrs: (C.c_void_p * nq)(*ptrs)       # noqa: E731
+        self.B.check(self.lib.rlr_search_mmr_multi_async(arr([c.value for c in cs[:nq]]), nq,
+                                                         arr([q.data_ptr() for q in queries]), top_k, diversity_factor,
+                                                         w_embed, w_lex, arr([r.data_ptr() for r in results]),
+                                                         arr([r.data_ptr() for r in result_ns]), self._stream()))
 
     def search_mmr(self, query, top_k, diversity_factor, w_embed, w_lex, result, result_n):
         """fused single-GPU path (rlr_search_mmr_async)."""

@@ -354,6 +354,33 @@ class DeviceStore:
         k = n.value
         return rows[:k], score[:k], emb[:k], lex[:k]
 
+    def search_mmr_multi(self, queries: np.ndarray, top_k: int, diversity: float, w: ResolvedWeights, lex=None,
+                         flags: int = 0):
+        """rlr_search_mmr_multi (throughput mode): up to RLR_MAX_MULTI queries answered by ONE pass over the rows.
+        `lex`: optional list of (lex_rows, lex_scores) per query (None entries allowed).  Returns a list of
+        (rows, score, emb, lex) per query, each identical to search_mmr's result for that query."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq, dim = q.shape
+        cap = max(top_k, 1)
+        rows = np.zeros((nq, cap), np.uint32); score = np.zeros((nq, cap), np.float32)
+        emb = np.zeros((nq, cap), np.float32); lx = np.zeros((nq, cap), np.float32)
+        n = np.zeros(nq, np.uint32)
+        wc = B.ResolvedWeightsC(w.embedding, w.lexical, w.reranker, w.initial)
+        lr_ptrs = ls_ptrs = nl = None
+        keep = []
+        if lex is not None:
+            lr_ptrs = (C.c_void_p * nq)(); ls_ptrs = (C.c_void_p * nq)(); nl = np.zeros(nq, np.uint32)
+            for i, pair in enumerate(lex):
+                if pair is None or pair[0] is None or len(pair[0]) == 0:
+                    continue
+                a = np.ascontiguousarray(pair[0], dtype=np.uint32); b = np.ascontiguousarray(pair[1], dtype=np.float32)
+                keep += [a, b]
+                lr_ptrs[i] = a.ctypes.data; ls_ptrs[i] = b.ctypes.data; nl[i] = len(a)
+        B.check(self._lib.rlr_search_mmr_multi(self._h, B.ptr(q), nq, dim, flags, top_k, diversity, C.byref(wc),
+                                               lr_ptrs, ls_ptrs, B.ptr(nl) if nl is not None else None,
+                                               B.ptr(rows), B.ptr(score), B.ptr(emb), B.ptr(lx), B.ptr(n)))
+        return [(rows[i, :n[i]].copy(), score[i, :n[i]].copy(), emb[i, :n[i]].copy(), lx[i, :n[i]].copy()) for i in range(nq)]
+
     def embedding_candidates(self, query: np.ndarray, count: int, flags: int = 0):
         q = np.ascontiguousarray(query, dtype=np.float32)
         rows = np.empty(max(count, 1), np.uint32); score = np.empty(max(count, 1), np.float32)

@@ -31,6 +31,7 @@ pub const RLR_SYNTH_IID: c_int = 0;
 pub const RLR_SYNTH_CLUSTERED: c_int = 1;
 pub const RLR_ABI_VERSION: c_int = 1;
 pub const RLR_MAX_SHARDS: usize = 16;
+pub const RLR_MAX_MULTI: u32 = 3;
 
 #[repr(C)] pub struct rlr_store { _p: [u8; 0] }
 #[repr(C)] pub struct rlr_ctx { _p: [u8; 0] }
@@ -72,6 +73,8 @@ extern "C" {
     pub fn rlr_search_topm(s: *mut rlr_store, query: *const f32, dim: u32, flags: u32, w: *const rlr_resolved_weights, lex_rows: *const u32, lex_scores: *const f32, n_lex: u32, m: u32, out_rows: *mut u32, out_combined: *mut f32, out_emb: *mut f32, out_lex: *mut f32, out_n: *mut u32) -> c_int;
     pub fn rlr_mmr(s: *mut rlr_store, cand_rows: *const u32, relevance: *const f32, p: u32, top_k: u32, lambda: f32, flags: u32, out_sel_pos: *mut u32, out_n: *mut u32) -> c_int;
     pub fn rlr_search_mmr(s: *mut rlr_store, query: *const f32, dim: u32, flags: u32, top_k: u32, diversity_factor: f32, w: *const rlr_resolved_weights, lex_rows: *const u32, lex_scores: *const f32, n_lex: u32, out_rows: *mut u32, out_score: *mut f32, out_emb: *mut f32, out_lex: *mut f32, out_n: *mut u32) -> c_int;
+    pub fn rlr_search_mmr_multi(s: *mut rlr_store, queries: *const f32, nq: u32, dim: u32, flags: u32, top_k: u32, diversity_factor: f32, w: *const rlr_resolved_weights, lex_rows: *const *const u32, lex_scores: *const *const f32, n_lex: *const u32, out_rows: *mut u32, out_score: *mut f32, out_emb: *mut f32, out_lex: *mut f32, out_n: *mut u32) -> c_int;
+    pub fn rlr_search_mmr_multi_async(ctxs: *const *mut rlr_ctx, nq: u32, d_queries: *const *const c_void, top_k: u32, diversity_factor: f32, w_embed: f32, w_lex: f32, d_results: *const *mut c_void, d_result_ns: *const *mut c_void, stream: *mut c_void) -> c_int;
     pub fn rlr_embedding_candidates(s: *mut rlr_store, query: *const f32, dim: u32, flags: u32, count: u32, out_rows: *mut u32, out_score: *mut f32, out_n: *mut u32) -> c_int;
     pub fn rlr_search_batch(s: *mut rlr_store, queries: *const f32, n_queries: u32, dim: u32, flags: u32, m: u32, out_rows: *mut u32, out_scores: *mut f32, out_n: *mut u32) -> c_int;
     pub fn rlr_search_batch_device(s: *mut rlr_store, queries: *const f32, n_queries: u32, dim: u32, flags: u32, m: u32, d_keys: *mut c_void, d_cnt: *mut c_void, stream: *mut c_void) -> c_int;
