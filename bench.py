@@ -576,6 +576,13 @@ def run_b200(a, guard=None):
                       f"rlr_cluster_search_mmr (C ABI, host buffers; ONE process drives {world} GPUs, peer-memory mailbox + peer-pointer MMR)"}
         if cluster_info is not None:
             e2e["cluster"] = cluster_info
+        if world > 1 and os.environ.get("RLR_BENCH_MULTI", "1") == "1":
+            # throughput mode through the cluster's C-ABI call: Q queries per pass over every GPU's shard
+            try:
+                throughput = api_throughput_mode(a, cluster, q_host, wts, callers, [target.search_mmr(q_host[i], a.top_k, a.diversity, wts) for i in range(3)],
+                                                 f"rlr_cluster_search_mmr_multi (C ABI, host buffers, one process, {world} GPUs)")
+            except B.RlrError as e:
+                throughput = {"error": str(e)}
         # parity, public API path: the call a user makes (it normalises the query, :494)
         for qi in range(N_PARITY):
             r, s, e, _ = target.search_mmr(q_host[qi], a.top_k, a.diversity, wts)
@@ -720,6 +727,57 @@ def run_b200(a, guard=None):
         raise SystemExit(3)
 
 
+def api_throughput_mode(a, target, q_host, wts, callers, singles, api):
+    """Throughput mode through the public host-buffer call: `callers` host threads, each call carries Q queries that are
+    answered by ONE pass over the rows.  Separate from the single-query headline."""
+    out = {"what": "Q independent top_k=%d diversity=%.1f searches per call, answered by ONE scan of the store per GPU; "
+                   "queries/s counts queries" % (a.top_k, a.diversity), "api": api, "callers": callers}
+    ok = True
+    for nq in (2, 3):
+        calls = max(4, a.steps // nq)
+        errs, lat = [], []
+        start = threading.Barrier(callers + 1)
+
+        def caller(t):
+            try:
+                for i in range(3):
+                    target.search_mmr_multi(q_host[[(t + i + j) % N_QUERIES for j in range(nq)]], a.top_k, a.diversity, wts)
+                start.wait()
+                for i in range(t, calls, callers):
+                    idx = [(i * nq + j) % N_QUERIES for j in range(nq)]
+                    t0 = time.perf_counter()
+                    target.search_mmr_multi(q_host[idx], a.top_k, a.diversity, wts)
+                    lat.append(time.perf_counter() - t0)
+            except Exception as e:      # noqa: BLE001
+                errs.append(repr(e))
+                try:
+                    start.abort()
+                except Exception:       # noqa: BLE001
+                    pass
+
+        th = [threading.Thread(target=caller, args=(t,)) for t in range(callers)]
+        [t.start() for t in th]
+        try:
+            start.wait()
+        except threading.BrokenBarrierError:
+            pass
+        t_start = time.perf_counter()
+        [t.join() for t in th]
+        wall = time.perf_counter() - t_start
+        if errs:
+            out[f"q{nq}"] = {"error": errs[0]}
+            ok = False
+            continue
+        got = target.search_mmr_multi(q_host[:nq], a.top_k, a.diversity, wts)
+        same = all(got[j][0].tobytes() == singles[j][0].tobytes() and got[j][1].tobytes() == singles[j][1].tobytes() for j in range(nq))
+        ok &= same
+        out[f"q{nq}"] = {"queries_per_pass": nq, "value": calls * nq / wall, "unit": "queries/s",
+                         "p50_latency_ms_per_call": 1e3 * statistics.median(lat),
+                         "identical_to_single_query_results": bool(same)}
+    out["parity_ok"] = bool(ok)
+    return out
+
+
 def run_throughput_mode(a, backend, store, q_dev, q_host, dev, p_cap, w_e, w_l, lanes):
     """Separate from the single-query headline (never folded into `value`): Q = 2 and 3 queries per pass over the rows.
     Each (row, query) dot is still its own sequential f32 chain, so every answer is bit-identical to the single-query
@@ -762,6 +820,8 @@ def run_throughput_mode(a, backend, store, q_dev, q_host, dev, p_cap, w_e, w_l, 
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1)
         # host-buffer API, one caller: latency of a call that carries nq queries
+        for i in range(3):
+            store.search_mmr_multi(q_host[[j % N_QUERIES for j in range(nq)]], a.top_k, a.diversity, wts)     # leases + warms nq workspaces
         lat = []
         for i in range(calls):
             idx = [(i * nq + j) % N_QUERIES for j in range(nq)]

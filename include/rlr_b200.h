@@ -395,6 +395,12 @@ int rlr_cluster_search_mmr(rlr_cluster *c, const float *query, uint32_t dim, uin
                            const uint32_t *lex_rows, const float *lex_scores, uint32_t n_lex,
                            uint32_t *out_rows, float *out_score, float *out_emb, float *out_lex,
                            uint32_t *out_n);
+/* throughput mode over the cluster, as rlr_search_mmr_multi (embedding-only queries: no lexical pairs): every GPU
+ * scans its shard ONCE for the nq queries and posts nq lists; the root merges and diversifies each */
+int rlr_cluster_search_mmr_multi(rlr_cluster *c, const float *queries, uint32_t nq, uint32_t dim, uint32_t flags,
+                                 uint32_t top_k, float diversity_factor, const rlr_resolved_weights *w,
+                                 uint32_t *out_rows, float *out_score, float *out_emb, float *out_lex,
+                                 uint32_t *out_n);
 /* RagEngine::get_embedding_candidates (:415-461), as rlr_embedding_candidates */
 int rlr_cluster_embedding_candidates(rlr_cluster *c, const float *query, uint32_t dim, uint32_t flags,
                                      uint32_t count, uint32_t *out_rows, float *out_score, uint32_t *out_n);

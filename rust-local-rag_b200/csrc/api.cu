@@ -157,8 +157,9 @@ int rlr_api::ctx_new(rlr_store *s, rlr_ctx **out)
     } while (0)
     CTX_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) CTX_TRY(cudaEventCreate(&e));
-    CTX_TRY(cudaMalloc(&c->d_query, rlr::kQueryCap * sizeof(float)));
-    CTX_TRY(cudaMemset(c->d_query, 0, rlr::kQueryCap * sizeof(float)));
+    // room for one query per query group (throughput mode over a cluster stages them side by side)
+    CTX_TRY(cudaMalloc(&c->d_query, rlr::kMaxQueryGroups * rlr::kQueryCap * sizeof(float)));
+    CTX_TRY(cudaMemset(c->d_query, 0, rlr::kMaxQueryGroups * rlr::kQueryCap * sizeof(float)));
     CTX_TRY(cudaMalloc(&c->d_lex_rows, kLexCap * sizeof(uint32_t)));
     CTX_TRY(cudaMalloc(&c->d_lex_norm, kLexCap * sizeof(float)));
     // per-launch scan workspace, one slice per query group (kernels.cuh: ScanArgs)
@@ -187,8 +188,8 @@ int rlr_api::ctx_new(rlr_store *s, rlr_ctx **out)
     CTX_TRY(cudaMalloc(&c->d_rows_in, RLR_MAX_M * sizeof(uint32_t)));
     CTX_TRY(cudaMalloc(&c->d_rel_in, RLR_MAX_M * sizeof(float)));
     CTX_TRY(cudaMalloc(&c->d_p_in, sizeof(uint32_t)));
-    CTX_TRY(cudaMallocHost(&c->h_query, rlr::kQueryCap * sizeof(float)));
-    memset(c->h_query, 0, rlr::kQueryCap * sizeof(float));
+    CTX_TRY(cudaMallocHost(&c->h_query, rlr::kMaxQueryGroups * rlr::kQueryCap * sizeof(float)));
+    memset(c->h_query, 0, rlr::kMaxQueryGroups * rlr::kQueryCap * sizeof(float));
     CTX_TRY(cudaMallocHost(&c->h_lex_rows, kLexCap * sizeof(uint32_t)));
     CTX_TRY(cudaMallocHost(&c->h_lex_norm, kLexCap * sizeof(float)));
     CTX_TRY(cudaMallocHost(&c->h_result_blk, 16 + RLR_MAX_M * sizeof(rlr_cand)));

@@ -33,6 +33,7 @@ namespace {
 // one lane of a cluster: everything a query in flight needs on every GPU
 struct ClusterCtx {
     std::vector<rlr_ctx *> c;          // one workspace + stream per shard, on that shard's device
+    std::vector<rlr_ctx *> root_extra; // throughput mode: pool / MMR buffers of queries 1.. on the root (created on first use)
     rlr_mailbox *mb = nullptr;         // in the root's HBM, private to this lane
     uint64_t seq = 0;                  // sequence numbers of this lane's mailbox start at 1
     uint32_t *h_status = nullptr;      // pinned: sticky mailbox status read back with every result
@@ -66,6 +67,7 @@ void cctx_free(rlr_cluster *cl, ClusterCtx *cc)
     if (!cc) return;
     for (size_t g = 0; g < cc->c.size(); ++g)
         if (cc->c[g]) { cudaSetDevice(cl->device[g]); ctx_free(cc->c[g]); }
+    for (rlr_ctx *x : cc->root_extra) { cudaSetDevice(cl->device[0]); ctx_free(x); }
     if (cc->mb) rlr_mailbox_close(cc->mb);
     if (cc->h_status) cudaFreeHost(cc->h_status);
     cudaGetLastError();
@@ -314,7 +316,140 @@ int cluster_search(rlr_cluster *cl, const float *query, uint32_t dim, uint32_t f
     return RLR_OK;
 }
 
+// throughput mode over the cluster: nq queries, ONE pass over every shard (query groups), nq posts per shard into
+// consecutive mailbox slots, nq merges + MMRs on the root
+int cluster_search_multi(rlr_cluster *cl, const float *queries, uint32_t nq, uint32_t dim, uint32_t flags, uint32_t pool,
+                         bool do_mmr, uint32_t top_k, float lambda, const rlr_resolved_weights *w, uint32_t *out_rows,
+                         float *out_score, float *out_emb, float *out_lex, uint32_t *out_n)
+{
+    ClusterLease lease(cl);
+    if (int rc = lease.acquire()) return rc;
+    ClusterCtx *cc = lease.cc;
+    rlr_ctx *r0 = cc->c[0];
+    if (dim != cl->dim) return fail(RLR_ERR_DIM_MISMATCH, "queries have %u dims, store has %u", dim, cl->dim);
+    while (cc->root_extra.size() + 1 < nq) {
+        rlr_ctx *x = nullptr;
+        if (int rc = ensure_device(cl->device[0])) return rc;
+        if (int rc = ctx_new(cl->shard[0], &x)) return rc;
+        cc->root_extra.push_back(x);
+    }
+    for (uint32_t q = 0; q < nq; ++q) {
+        float *hq = r0->h_query + static_cast<size_t>(q) * rlr::kQueryCap;
+        memcpy(hq, queries + static_cast<size_t>(q) * dim, dim * sizeof(float));
+        for (uint32_t i = 0; i < dim; ++i)
+            if (!std::isfinite(hq[i])) return fail(RLR_ERR_NONFINITE, "queries[%u][%u] is not finite", q, i);
+        if (!(flags & RLR_QUERY_PRENORMALIZED)) host_normalize(hq, dim);
+    }
+    const uint64_t seq0 = cc->seq + 1;
+    cc->seq += nq;
+    uint64_t launches = 0;
+    for (uint32_t k = 0; k < cl->n; ++k) {
+        const uint32_t g = (k + 1) % cl->n;
+        rlr_store *s = cl->shard[g];
+        rlr_ctx *c = cc->c[g];
+        cudaStream_t st = c->stream;
+        CU_TRY(cudaSetDevice(s->device));
+        CU_TRY(cudaMemcpyAsync(c->d_query, r0->h_query, static_cast<size_t>(nq) * rlr::kQueryCap * sizeof(float), cudaMemcpyHostToDevice, st));
+        const bool half = s->use_half(flags);
+        rlr::ScanArgs a;
+        memset(&a, 0, sizeof a);
+        rlr::scan_plan(s->sm_count, s->smem_optin, static_cast<uint32_t>(s->n_rows), half ? s->pitch16 : s->pitch, half, &a, nq);
+        if (a.grid <= 0) return fail(RLR_ERR_UNSUPPORTED, "%u query groups do not fit this store's row size in shared memory", nq);
+        a.tmap = half ? &s->tmap16 : &s->tmap;
+        a.n_rows = static_cast<uint32_t>(s->n_rows);
+        a.row_base = static_cast<uint32_t>(s->row_base);
+        a.pitch = half ? s->pitch16 : s->pitch;
+        a.w_embed = w->embedding; a.w_lex = w->lexical;
+        a.m = pool;
+        a.d_lists = c->d_lists; a.d_counts = c->d_counts; a.d_ticket = c->d_ticket; a.d_pub = c->d_pub;
+        for (uint32_t q = 0; q < nq; ++q) {
+            const uint32_t slot = static_cast<uint32_t>((seq0 + q) % cc->mb->ring);
+            rlr::ScanGroupIO &io = a.groups.g[q];
+            io.query = c->d_query + static_cast<size_t>(q) * rlr::kQueryCap;
+            io.out = cc->mb->list(slot, g); io.out_n = cc->mb->count(slot, g);
+            io.post.flag = cc->mb->flag(slot, g);
+            io.post.consumed = cc->mb->consumed(slot);
+            io.post.seq = seq0 + q; io.post.ring = cc->mb->ring; io.post.status = cc->mb->d_status;
+        }
+        CU_TRY(rlr::scan_launch(a, st));
+        ++launches;
+    }
+    rlr_store *s0 = cl->shard[0];
+    cudaStream_t st0 = r0->stream;
+    const uint32_t cap = do_mmr ? std::min<uint32_t>(pool, std::max<uint32_t>(top_k, 1)) : pool;
+    for (uint32_t q = 0; q < nq; ++q) {
+        rlr_ctx *rq = q == 0 ? r0 : cc->root_extra[q - 1];
+        const uint32_t slot = static_cast<uint32_t>((seq0 + q) % cc->mb->ring);
+        CU_TRY(rlr::mailbox_merge_launch(cc->mb->list(slot, 0), cc->mb->m_cap, cc->mb->flag(slot, 0), seq0 + q, cc->mb->consumed(slot),
+                                         cl->n, pool, rq->d_pool, rq->d_pool_n, cc->mb->d_status, st0));
+        ++launches;
+        const uint8_t *d_blk = rq->d_pool_blk;
+        if (do_mmr) {
+            const bool half = s0->use_half(flags);
+            rlr::MmrArgs a;
+            memset(&a, 0, sizeof a);
+            a.half = half;
+            a.pitch = half ? cl->pitch16 : cl->pitch; a.dim = cl->dim;
+            a.d_cands = rq->d_pool; a.d_n = rq->d_pool_n;
+            a.use_rows = 1; a.p_cap = pool; a.top_k = top_k; a.lambda = lambda;
+            a.d_tri = rq->d_tri; a.d_sel_pos = rq->d_sel_pos; a.d_sel_n = rq->d_sel_n; a.d_result = rq->d_result;
+            a.max_smem_optin = s0->smem_optin;
+            a.peers = half ? &cl->table16 : &cl->table32;
+            a.d_gather = rq->d_gather;
+            uint32_t l = 0;
+            CU_TRY(rlr::mmr_launch(a, st0, &l));
+            launches += l;
+            d_blk = rq->d_result_blk;
+        }
+        CU_TRY(cudaMemcpyAsync(rq->h_result_blk, d_blk, 16 + cap * sizeof(rlr_cand), cudaMemcpyDeviceToHost, st0));
+    }
+    CU_TRY(cudaStreamSynchronize(st0));
+    cl->launches += launches;
+    const uint32_t stride = std::max<uint32_t>(top_k, 1);
+    for (uint32_t q = 0; q < nq; ++q) {
+        rlr_ctx *rq = q == 0 ? r0 : cc->root_extra[q - 1];
+        const uint32_t n = std::min(rq->h_result_n[0], cap);
+        if (n == 0) {
+            CU_TRY(cudaMemcpy(cc->h_status, cc->mb->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            return fail(RLR_ERR_CUDA, "the cluster delivered no result for query %u (mailbox status %u)", q, cc->h_status[0]);
+        }
+        unpack(rq->h_result, n, out_rows + static_cast<size_t>(q) * stride, out_score ? out_score + static_cast<size_t>(q) * stride : nullptr,
+               out_emb ? out_emb + static_cast<size_t>(q) * stride : nullptr, out_lex ? out_lex + static_cast<size_t>(q) * stride : nullptr);
+        out_n[q] = n;
+    }
+    return RLR_OK;
+}
+
 } // namespace
+
+RLR_EXPORT int rlr_cluster_search_mmr_multi(rlr_cluster *cl, const float *queries, uint32_t nq, uint32_t dim, uint32_t flags,
+                                            uint32_t top_k, float diversity_factor, const rlr_resolved_weights *w,
+                                            uint32_t *out_rows, float *out_score, float *out_emb, float *out_lex, uint32_t *out_n)
+{
+    if (int rc = check_cluster(cl)) return rc;
+    if (!out_rows || !out_n) return fail(RLR_ERR_INVALID_ARG, "out_rows/out_n is NULL");
+    if (!w) return fail(RLR_ERR_INVALID_ARG, "weights is NULL");
+    if (nq == 0) return RLR_OK;
+    if (nq > RLR_MAX_MULTI) return fail(RLR_ERR_UNSUPPORTED, "nq %u exceeds RLR_MAX_MULTI (%d)", nq, RLR_MAX_MULTI);
+    if (!queries) return fail(RLR_ERR_INVALID_ARG, "queries is NULL");
+    if (cl->n == 1)
+        return rlr_search_mmr_multi(cl->shard[0], queries, nq, dim, flags, top_k, diversity_factor, w, nullptr, nullptr, nullptr,
+                                    out_rows, out_score, out_emb, out_lex, out_n);
+    if (nq == 1)
+        return rlr_cluster_search_mmr(cl, queries, dim, flags, top_k, diversity_factor, w, nullptr, nullptr, 0, out_rows, out_score,
+                                      out_emb, out_lex, out_n);
+    for (uint32_t q = 0; q < nq; ++q) out_n[q] = 0;
+    float lambda = diversity_factor;
+    if (lambda < 0.0f) lambda = 0.0f;
+    if (lambda > 1.0f) lambda = 1.0f;
+    const bool do_mmr = lambda != 0.0f;
+    const uint64_t pool = do_mmr ? std::max<uint64_t>(3ull * top_k, static_cast<uint64_t>(top_k) + 10) : std::max<uint32_t>(top_k, 1);
+    if (pool > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "candidate pool %llu exceeds %d (top_k %u)", (unsigned long long)pool, RLR_MAX_M, top_k);
+    if ((flags & RLR_SEARCH_F16) && !(cl->flags & (RLR_STORE_KEEP_F16 | RLR_STORE_F16_ONLY)))
+        return fail(RLR_ERR_INVALID_ARG, "RLR_SEARCH_F16 but the store holds no f16 copy");
+    return cluster_search_multi(cl, queries, nq, dim, flags, static_cast<uint32_t>(std::min<uint64_t>(pool, cl->n_rows)), do_mmr, top_k,
+                                lambda, w, out_rows, out_score, out_emb, out_lex, out_n);
+}
 
 RLR_EXPORT int rlr_cluster_create(const int *devices, uint32_t n_devices, uint32_t dim, uint64_t n_rows, const float *rows,
                                   uint64_t host_pitch, uint32_t flags, const uint64_t *shard_rows, rlr_cluster **out)

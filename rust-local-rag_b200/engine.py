@@ -479,6 +479,22 @@ class ClusterStore(DeviceStore):
         rows = np.ascontiguousarray(rows, dtype=np.float32)
         B.check(self._lib.rlr_cluster_upload(self._h, row0, rows.shape[0], B.ptr(rows), rows.shape[1]))
 
+    def search_mmr_multi(self, queries: np.ndarray, top_k: int, diversity: float, w: ResolvedWeights, lex=None,
+                         flags: int = 0):
+        """rlr_cluster_search_mmr_multi: throughput mode over the cluster (embedding-only queries)."""
+        if lex is not None and any(p is not None for p in lex):
+            raise B.RlrError(B.RLR_ERR_UNSUPPORTED, "throughput mode over a cluster takes embedding-only queries")
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq, dim = q.shape
+        cap = max(top_k, 1)
+        rows = np.zeros((nq, cap), np.uint32); score = np.zeros((nq, cap), np.float32)
+        emb = np.zeros((nq, cap), np.float32); lx = np.zeros((nq, cap), np.float32)
+        n = np.zeros(nq, np.uint32)
+        wc = B.ResolvedWeightsC(w.embedding, w.lexical, w.reranker, w.initial)
+        B.check(self._lib.rlr_cluster_search_mmr_multi(self._h, B.ptr(q), nq, dim, flags, top_k, diversity, C.byref(wc),
+                                                       B.ptr(rows), B.ptr(score), B.ptr(emb), B.ptr(lx), B.ptr(n)))
+        return [(rows[i, :n[i]].copy(), score[i, :n[i]].copy(), emb[i, :n[i]].copy(), lx[i, :n[i]].copy()) for i in range(nq)]
+
     def append(self, rows):
         raise B.RlrError(B.RLR_ERR_UNSUPPORTED, "a cluster is a bulk-loaded snapshot: mutate a single-GPU store or rebuild")
 

@@ -204,3 +204,25 @@ def test_engine_over_a_cluster(eng, orc, corpus, devices):
     ref = orc.search(rows[:20000], qs[1], 30)
     assert same(np.array([r.row for r in res], np.uint32), ref[0])
     e.store.close()
+
+
+@pytest.mark.parametrize("devices", _device_sets())
+def test_cluster_throughput_mode_multi_query(eng, orc, corpus, devices):
+    """rlr_cluster_search_mmr_multi: 2-3 queries, ONE pass over every shard, one mailbox post per (GPU, query)."""
+    rows, qs = corpus
+    cl = eng.ClusterStore.from_rows(rows, devices=devices)
+    refs = [orc.search_with_diversity(rows, q, 100, 0.7, threads=4) for q in qs]
+    for it in range(10):                                  # slots 1..3 of the ring are reused call after call
+        nq = 2 + it % 2
+        idx = [(it + j) % len(qs) for j in range(nq)]
+        got = cl.search_mmr_multi(qs[idx], 100, 0.7, W())
+        for j, i in enumerate(idx):
+            assert same(got[j][0], refs[i][0]) and same(got[j][1], refs[i][1]) and same(got[j][2], refs[i][2]), (it, j)
+        one = cl.search_mmr(qs[it % len(qs)], 100, 0.7, W())           # single-query calls interleave on the same lane
+        assert same(one[0], refs[it % len(qs)][0])
+    for k, lam in ((5, 0.3), (7, 0.0)):
+        got = cl.search_mmr_multi(qs[:3], k, lam, W())
+        for j in range(3):
+            ref = orc.search_with_diversity(rows, qs[j], k, lam, threads=4)
+            assert same(got[j][0], ref[0]) and same(got[j][1], ref[1])
+    cl.close()

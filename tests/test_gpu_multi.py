@@ -37,8 +37,9 @@ def test_multi_equals_single_and_oracle(eng, rlr, orc, n, dim, nq):
         if i == 1:
             lex.append(None)                               # an embedding-only query among text queries
         else:
-            lr = rng.choice(n, 200, replace=False).astype(np.uint32)
-            lex.append((lr, (rng.random(200) * 5 + 0.1).astype(F32)))
+            nl = min(n, 200)
+            lr = rng.choice(n, nl, replace=False).astype(np.uint32)
+            lex.append((lr, (rng.random(nl) * 5 + 0.1).astype(F32)))
     for k, lam in ((100, 0.7), (5, 0.3), (7, 0.0), (0, 0.5)):
         for lx in (None, lex):
             got = s.search_mmr_multi(qs[:nq], k, lam, W(), lex=lx)
