@@ -576,17 +576,31 @@ def run_b200(a, guard=None):
                       f"rlr_cluster_search_mmr (C ABI, host buffers; ONE process drives {world} GPUs, peer-memory mailbox + peer-pointer MMR)"}
         if cluster_info is not None:
             e2e["cluster"] = cluster_info
-        if world > 1 and os.environ.get("RLR_BENCH_MULTI", "1") == "1":
-            # throughput mode through the cluster's C-ABI call: Q queries per pass over every GPU's shard
-            try:
-                throughput = api_throughput_mode(a, cluster, q_host, wts, callers, [target.search_mmr(q_host[i], a.top_k, a.diversity, wts) for i in range(3)],
-                                                 f"rlr_cluster_search_mmr_multi (C ABI, host buffers, one process, {world} GPUs)")
-            except B.RlrError as e:
-                throughput = {"error": str(e)}
         # parity, public API path: the call a user makes (it normalises the query, :494)
         for qi in range(N_PARITY):
             r, s, e, _ = target.search_mmr(q_host[qi], a.top_k, a.diversity, wts)
             api_results.append((r.copy(), s.copy(), e.copy()))
+        if world > 1 and os.environ.get("RLR_BENCH_MULTI", "1") == "1":
+            # throughput mode through the cluster's C-ABI call: Q queries per pass over every GPU's shard.  The root
+            # now carries Q merge + MMR tails per pass, so this mode gets its own tail-balanced plan (Q = 3).
+            try:
+                singles = [target.search_mmr(q_host[i], a.top_k, a.diversity, wts) for i in range(3)]
+                tp_cluster, tp_plan = cluster, cluster_info["shard_rows"]
+                if balance is not None:
+                    head3 = rdist.ShardPlan.balanced_head_rows(a.rows, world, 3 * balance["tail_ms"] * balance["scan_rows_per_ms"])
+                    tp_plan = [rdist.ShardPlan(a.rows, world, r, head_rows=head3).n_local for r in range(world)]
+                    cluster.close()
+                    cluster = None
+                    tp_cluster = engine.ClusterStore.synthetic(a.rows, a.dim, kind=B.RLR_SYNTH_CLUSTERED, seed=SEED_STORE,
+                                                               centroid_seed=SEED_CENTROID, n_clusters=N_CLUSTERS, sigma=SIGMA,
+                                                               devices=list(range(world)), shard_rows=tp_plan)
+                throughput = api_throughput_mode(a, tp_cluster, q_host, wts, callers, singles,
+                                                 f"rlr_cluster_search_mmr_multi (C ABI, host buffers, one process, {world} GPUs)")
+                throughput["shard_rows"] = tp_plan
+                if tp_cluster is not cluster:
+                    tp_cluster.close()
+            except B.RlrError as e:
+                throughput = {"error": str(e)}
     clocks.stop()
 
     # ---- roofline: the scan kernel (dominant) ----
