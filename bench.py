@@ -695,7 +695,7 @@ def run_b200(a, guard=None):
         torch.cuda.empty_cache()
     if want_extras:
         try:
-            extras = run_extras(a, rank, world, local_rank, dev, group, peaks)
+            extras = run_extras(a, rank, world, local_rank, dev, group, peaks, cpu_group)
         except Exception as e:      # noqa: BLE001 -- extras must never take the headline line down with them
             extras = {"error": repr(e)}
             log("extra configs failed:", repr(e))
@@ -865,7 +865,7 @@ def scan_source_sha16():
 # ----------------------------------------------------------------------------------------
 # extra configs
 # ----------------------------------------------------------------------------------------
-def run_extras(a, rank, world, local_rank, dev, group, peaks):
+def run_extras(a, rank, world, local_rank, dev, group, peaks, cpu_group=None):
     """BASELINE configs other than the headline one, measured in the same driver-visible run.  Every record
     carries its own `clocks` sample.  N=1: configs 1, 2 and the per-GPU shape of config 4.  N=8: config 4
     sharded over the 8 GPUs and config 5 (100M x 768 f16)."""
@@ -1024,6 +1024,48 @@ def run_extras(a, rank, world, local_rank, dev, group, peaks):
                 **recs}
         st.close()
         torch.cuda.empty_cache()
+
+    # ---- config 4 again, from ONE process: rlr_cluster_search_batch (rank 0 drives all GPUs; the others wait on the CPU) ----
+    if world == 8:
+        if rank == 0:
+            clk = ClockSampler(local_rank, interval=0.005)
+            n4, dim4, nq, m4 = 10_000_000, 1024, 1024, 100
+            cl = engine.ClusterStore.synthetic(n4, dim4, devices=list(range(world)), flags=B.RLR_STORE_KEEP_F16,
+                                               shard_rows=[rdist.ShardPlan(n4, world, r).n_local for r in range(world)], **kw)
+            qh = queries(nq, dim4)
+            fl = B.RLR_QUERY_PRENORMALIZED | B.RLR_BATCH_F16
+            for _ in range(3):
+                res = cl.search_batch(qh, m4, flags=fl)
+            clk.start()
+            wall = []
+            for _ in range(20):
+                t0 = time.perf_counter()
+                res = cl.search_batch(qh, m4, flags=fl)
+                wall.append(time.perf_counter() - t0)
+            clk.stop()
+            w = statistics.median(wall)
+            rows_g, scores_g, n_g = res
+            sub = 100_000
+            rows_f32 = cl.read_rows(np.arange(sub))
+            ref = qh[:8].astype(np.float16).astype(np.float64) @ rows_f32.astype(np.float16).astype(np.float64).T
+            worst, okc = 0.0, True
+            for q in range(8):
+                inside = rows_g[q] < sub
+                if inside.any():
+                    worst = max(worst, float(np.abs(ref[q, rows_g[q][inside]] - scores_g[q][inside].astype(np.float64)).max()))
+                okc &= bool((np.diff(scores_g[q][:n_g[q]].astype(np.float64)) <= 0).all()) and int(n_g[q]) == m4
+            okc &= worst <= 1e-5
+            out["config4_batched_one_process"] = {
+                "workload": f"batched {nq} queries x {n4}x{dim4} chunks, top-{m4}, binary16 operands, 8 GPUs driven by ONE process",
+                "api": "rlr_cluster_search_batch (C ABI, host buffers): per-GPU contraction, peer copies of the key lists to the root, per-query device merge",
+                "queries_per_s_e2e": nq / w, "ms_per_batch_e2e": w * 1e3, "tflops_aggregate_e2e": 2.0 * nq * n4 * dim4 / w / 1e12,
+                "parity": {"ok": bool(okc), "max_abs_dev_from_fp64_contraction_of_rounded_inputs": worst, "stated_tolerance": 1e-5},
+                "steps": 20, "clocks": clk.summary()}
+            all_ok &= bool(okc)
+            cl.close()
+            torch.cuda.empty_cache()
+        if cpu_group is not None:
+            dist.barrier(group=cpu_group)
 
     # ---- config 5: 100M x 768 binary16 store over 8 GPUs, fused exchange ----
     if world == 8:

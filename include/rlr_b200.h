@@ -401,6 +401,10 @@ int rlr_cluster_search_mmr_multi(rlr_cluster *c, const float *queries, uint32_t 
                                  uint32_t top_k, float diversity_factor, const rlr_resolved_weights *w,
                                  uint32_t *out_rows, float *out_score, float *out_emb, float *out_lex,
                                  uint32_t *out_n);
+/* the batched contraction over the cluster, as rlr_search_batch (flags: operand precision, exact re-score): every GPU
+ * contracts the batch against its shard, the root pulls the per-shard key lists over NVLink and merges them per query */
+int rlr_cluster_search_batch(rlr_cluster *c, const float *queries, uint32_t n_queries, uint32_t dim, uint32_t flags,
+                             uint32_t m, uint32_t *out_rows, float *out_scores, uint32_t *out_n);
 /* RagEngine::get_embedding_candidates (:415-461), as rlr_embedding_candidates */
 int rlr_cluster_embedding_candidates(rlr_cluster *c, const float *query, uint32_t dim, uint32_t flags,
                                      uint32_t count, uint32_t *out_rows, float *out_score, uint32_t *out_n);

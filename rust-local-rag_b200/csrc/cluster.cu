@@ -20,6 +20,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -37,6 +38,11 @@ struct ClusterCtx {
     rlr_mailbox *mb = nullptr;         // in the root's HBM, private to this lane
     uint64_t seq = 0;                  // sequence numbers of this lane's mailbox start at 1
     uint32_t *h_status = nullptr;      // pinned: sticky mailbox status read back with every result
+    // batched path: per-shard key lists (on the shard's GPU), the gathered lists + merged result on the root, pinned mirror
+    std::vector<void *> batch_keys;
+    void *batch_all = nullptr, *batch_out = nullptr, *batch_cnt = nullptr;
+    unsigned long long *h_batch = nullptr;
+    size_t batch_cap = 0;              // n_queries * m the buffers hold
 };
 
 thread_local std::vector<float> g_shard_scan_ms;
@@ -68,6 +74,10 @@ void cctx_free(rlr_cluster *cl, ClusterCtx *cc)
     for (size_t g = 0; g < cc->c.size(); ++g)
         if (cc->c[g]) { cudaSetDevice(cl->device[g]); ctx_free(cc->c[g]); }
     for (rlr_ctx *x : cc->root_extra) { cudaSetDevice(cl->device[0]); ctx_free(x); }
+    for (size_t g = 0; g < cc->batch_keys.size(); ++g) if (cc->batch_keys[g]) { cudaSetDevice(cl->device[g]); cudaFree(cc->batch_keys[g]); }
+    cudaSetDevice(cl->device[0]);
+    cudaFree(cc->batch_all); cudaFree(cc->batch_out); cudaFree(cc->batch_cnt);
+    if (cc->h_batch) cudaFreeHost(cc->h_batch);
     if (cc->mb) rlr_mailbox_close(cc->mb);
     if (cc->h_status) cudaFreeHost(cc->h_status);
     cudaGetLastError();
@@ -421,6 +431,80 @@ int cluster_search_multi(rlr_cluster *cl, const float *queries, uint32_t nq, uin
 }
 
 } // namespace
+
+// rlr_search_batch over the cluster (BASELINE configs[3] from ONE process): every GPU contracts the query batch
+// against its shard (one host thread per GPU for the duration of the call: the per-shard call is host-synchronous),
+// the root pulls the per-shard key lists over NVLink (cudaMemcpyPeerAsync) and merges them per query on the device.
+RLR_EXPORT int rlr_cluster_search_batch(rlr_cluster *cl, const float *queries, uint32_t n_queries, uint32_t dim, uint32_t flags,
+                                        uint32_t m, uint32_t *out_rows, float *out_scores, uint32_t *out_n)
+{
+    if (int rc = check_cluster(cl)) return rc;
+    if (cl->n == 1) return rlr_search_batch(cl->shard[0], queries, n_queries, dim, flags, m, out_rows, out_scores, out_n);
+    if (!out_rows || !out_n) return fail(RLR_ERR_INVALID_ARG, "out_rows/out_n is NULL");
+    if (n_queries == 0) return RLR_OK;
+    if (!queries) return fail(RLR_ERR_INVALID_ARG, "queries is NULL");
+    if (m == 0 || m > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "m %u not in 1..%d", m, RLR_MAX_M);
+    if (dim != cl->dim) return fail(RLR_ERR_DIM_MISMATCH, "queries have %u dims, store has %u", dim, cl->dim);
+    if (static_cast<uint64_t>(cl->n) * m > 16384) return fail(RLR_ERR_UNSUPPORTED, "n_shards * m exceeds the merge capacity");
+    ClusterLease lease(cl);
+    if (int rc = lease.acquire()) return rc;
+    ClusterCtx *cc = lease.cc;
+    const size_t per = static_cast<size_t>(n_queries) * m;
+    if (per > cc->batch_cap || cc->batch_keys.size() != cl->n) {
+        for (size_t g = 0; g < cc->batch_keys.size(); ++g) if (cc->batch_keys[g]) { cudaSetDevice(cl->device[g]); cudaFree(cc->batch_keys[g]); }
+        cc->batch_keys.assign(cl->n, nullptr);
+        CU_TRY(cudaSetDevice(cl->device[0]));
+        cudaFree(cc->batch_all); cudaFree(cc->batch_out); cudaFree(cc->batch_cnt);
+        if (cc->h_batch) cudaFreeHost(cc->h_batch);
+        cc->batch_all = cc->batch_out = cc->batch_cnt = nullptr; cc->h_batch = nullptr; cc->batch_cap = 0;
+        for (uint32_t g = 0; g < cl->n; ++g) {
+            CU_TRY(cudaSetDevice(cl->device[g]));
+            CU_TRY(cudaMalloc(&cc->batch_keys[g], per * 8));
+        }
+        CU_TRY(cudaSetDevice(cl->device[0]));
+        CU_TRY(cudaMalloc(&cc->batch_all, per * 8 * cl->n));
+        CU_TRY(cudaMalloc(&cc->batch_out, per * 8));
+        CU_TRY(cudaMalloc(&cc->batch_cnt, static_cast<size_t>(n_queries) * 4));
+        CU_TRY(cudaMallocHost(&cc->h_batch, per * 8 + static_cast<size_t>(n_queries) * 4));
+        cc->batch_cap = per;
+    }
+    // every shard in parallel: the contraction leaves rank-ordered keys (global rows) on the shard's GPU
+    std::vector<int> rcs(cl->n, RLR_OK);
+    std::vector<std::string> errs(cl->n);
+    std::vector<std::thread> th;
+    for (uint32_t g = 0; g < cl->n; ++g)
+        th.emplace_back([&, g] {
+            cudaSetDevice(cl->device[g]);
+            rcs[g] = rlr_search_batch_device(cl->shard[g], queries, n_queries, dim, flags, m, cc->batch_keys[g], nullptr, cc->c[g]->stream);
+            if (rcs[g] == RLR_OK && cudaStreamSynchronize(cc->c[g]->stream) != cudaSuccess) { cudaGetLastError(); rcs[g] = RLR_ERR_CUDA; }
+            if (rcs[g] != RLR_OK) errs[g] = rlr_last_error();
+        });
+    for (auto &t : th) t.join();
+    for (uint32_t g = 0; g < cl->n; ++g)
+        if (rcs[g] != RLR_OK) return fail(rcs[g], "shard %u: %s", g, errs[g].c_str());
+    CU_TRY(cudaSetDevice(cl->device[0]));
+    cudaStream_t st0 = cc->c[0]->stream;
+    for (uint32_t g = 0; g < cl->n; ++g)
+        CU_TRY(cudaMemcpyPeerAsync(static_cast<uint8_t *>(cc->batch_all) + g * per * 8, cl->device[0], cc->batch_keys[g], cl->device[g], per * 8, st0));
+    if (int rc = rlr_batch_merge_async(cl->shard[0], cc->batch_all, cl->n, n_queries, m, cc->batch_out, cc->batch_cnt, st0)) return rc;
+    uint32_t *h_cnt = reinterpret_cast<uint32_t *>(cc->h_batch + per);
+    CU_TRY(cudaMemcpyAsync(cc->h_batch, cc->batch_out, per * 8, cudaMemcpyDeviceToHost, st0));
+    CU_TRY(cudaMemcpyAsync(h_cnt, cc->batch_cnt, static_cast<size_t>(n_queries) * 4, cudaMemcpyDeviceToHost, st0));
+    CU_TRY(cudaStreamSynchronize(st0));
+    for (uint32_t q = 0; q < n_queries; ++q) {
+        const uint32_t n = std::min(h_cnt[q], m);
+        out_n[q] = n;
+        for (uint32_t i = 0; i < n; ++i) {
+            const unsigned long long k = cc->h_batch[static_cast<size_t>(q) * m + i];
+            out_rows[static_cast<size_t>(q) * m + i] = rlr::key_row(k);
+            if (out_scores) {
+                const uint32_t bits = rlr::bits_from_ord(static_cast<uint32_t>(k >> 32));
+                memcpy(&out_scores[static_cast<size_t>(q) * m + i], &bits, 4);
+            }
+        }
+    }
+    return RLR_OK;
+}
 
 RLR_EXPORT int rlr_cluster_search_mmr_multi(rlr_cluster *cl, const float *queries, uint32_t nq, uint32_t dim, uint32_t flags,
                                             uint32_t top_k, float diversity_factor, const rlr_resolved_weights *w,

@@ -511,8 +511,13 @@ class ClusterStore(DeviceStore):
         B.check(self._lib.rlr_cluster_launch_count(self._h, C.byref(n)))
         return n.value
 
-    def search_batch(self, *a, **k):
-        raise B.RlrError(B.RLR_ERR_UNSUPPORTED, "batched queries over a cluster: use dist.sharded_search_batch")
+    def search_batch(self, queries: np.ndarray, m: int, flags: int = 0):
+        """rlr_cluster_search_batch: the tcgen05 contraction on every GPU's shard, per-query merge on the root."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq, dim = q.shape
+        rows = np.zeros((nq, m), np.uint32); scores = np.zeros((nq, m), np.float32); n = np.zeros(nq, np.uint32)
+        B.check(self._lib.rlr_cluster_search_batch(self._h, B.ptr(q), nq, dim, flags, m, B.ptr(rows), B.ptr(scores), B.ptr(n)))
+        return rows, scores, n
 
     def close(self) -> None:
         if self._h:

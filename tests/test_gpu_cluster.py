@@ -226,3 +226,25 @@ def test_cluster_throughput_mode_multi_query(eng, orc, corpus, devices):
             ref = orc.search_with_diversity(rows, qs[j], k, lam, threads=4)
             assert same(got[j][0], ref[0]) and same(got[j][1], ref[1])
     cl.close()
+
+
+@pytest.mark.parametrize("devices", _device_sets())
+def test_cluster_batched_contraction_equals_single_store(eng, rlr, orc, corpus, devices):
+    """rlr_cluster_search_batch (BASELINE configs[3] from one process): a row's tensor-core score does not depend on
+    the shard it is computed in, so the cluster's answer equals the single store's bit for bit in every precision;
+    with RLR_BATCH_EXACT_RESCORE it carries the oracle's exact scores."""
+    rows, qs = corpus
+    q = np.concatenate([qs] * 10)[:50]
+    flags_store = rlr.RLR_STORE_KEEP_F16 | rlr.RLR_STORE_KEEP_BF16
+    one = eng.DeviceStore.from_rows(rows, flags=flags_store)
+    cl = eng.ClusterStore.from_rows(rows, devices=devices, flags=flags_store)
+    for pf in (rlr.RLR_BATCH_TF32, rlr.RLR_BATCH_BF16, rlr.RLR_BATCH_F16):
+        a = one.search_batch(q, 100, flags=pf)
+        b = cl.search_batch(q, 100, flags=pf)
+        assert (a[2] == 100).all() and same(a[2], b[2])
+        assert same(a[0], b[0]) and same(a[1], b[1]), pf
+    r, sc, n = cl.search_batch(q[:6], 40, flags=rlr.RLR_BATCH_EXACT_RESCORE)
+    for i in range(6):
+        qn = orc.normalize(q[i])
+        assert sc[i].tobytes() == np.array([orc.dot(qn, rows[x]) for x in r[i]], F32).tobytes()
+    one.close(); cl.close()
