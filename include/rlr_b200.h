@@ -326,6 +326,45 @@ int rlr_search_batch_device(rlr_store *s, const float *queries, uint32_t n_queri
 int rlr_batch_merge_async(rlr_store *s, const void *d_lists, uint32_t n_lists, uint32_t n_queries,
                           uint32_t m, void *d_out_keys, void *d_out_cnt /* nullable */, void *stream);
 
+/* ---- BM25 on the device: LexicalIndex (src/rag_engine.rs:2083-2237) for text queries -- SURVEY.md 8(f) N4 ----------
+ *
+ * RagEngine::search blends a BM25 score into every text query (:505-532).  On the host that pass costs 18 ms per query
+ * at 10k chunks and 0.2 s at 100k (tools/bm25_cost.py: hash-map postings like the reference's) -- two to three orders
+ * of magnitude more than the whole GPU search.  An rlr_bm25 index keeps the NUMERIC half of LexicalIndex on the device
+ * and scores it there; strings stay on the host: the caller tokenizes (`tokenize`, :2242-2247) and owns the
+ * term -> id dictionary.
+ *   rlr_bm25_set_doc      add_chunk (:2106-2138) for the chunk at `row` (a global row of the store): its distinct term
+ *                         ids with their counts; replaces what the row held; no terms => the row is not indexed
+ *   rlr_bm25_remove_doc   remove_chunk (:2140-2167)
+ *   rlr_bm25_move_doc     follow rlr_store_remove_rows: `to_row` takes over the document of `from_row`
+ *   rlr_bm25_score        LexicalIndex::score(query, limit) (:2169-2227): the `limit` best (row, score) by score desc.
+ *                         query_terms: the ids of the query's tokens that exist in the dictionary, in BYTEWISE ORDER OF
+ *                         THE TERM STRINGS (that order fixes the f32 summation order per document; the reference's is a
+ *                         random HashSet order); duplicates are ignored.  Exact-score ties go to the lower row.
+ *   rlr_search_text_topm / rlr_search_text_mmr
+ *                         RagEngine::search / search_with_diversity for a TEXT query: BM25 scoring, the top 5*top_k
+ *                         selection, max-normalisation (:511-530), the embedding scan with the blend, top-k and MMR all
+ *                         run on the device on one stream with no host round trip in between.
+ * Scores are bit-identical to the reference's f32 formula evaluated in that term order (idf's ln() is the C library's
+ * logf, computed on the host per query term).  Mutators need exclusivity like the store's; scoring is re-entrant.
+ * Single-GPU stores; a cluster takes host-computed pairs (rlr_cluster_search_*). */
+typedef struct rlr_bm25 rlr_bm25;
+int rlr_bm25_create(rlr_store *s, rlr_bm25 **out);
+int rlr_bm25_destroy(rlr_bm25 *ix);
+int rlr_bm25_set_doc(rlr_bm25 *ix, uint32_t row, const uint32_t *term_ids, const uint32_t *term_freqs, uint32_t n_terms);
+int rlr_bm25_remove_doc(rlr_bm25 *ix, uint32_t row);
+int rlr_bm25_move_doc(rlr_bm25 *ix, uint32_t from_row, uint32_t to_row);
+int rlr_bm25_stats(const rlr_bm25 *ix, uint64_t *total_docs, uint64_t *total_length, uint64_t *n_terms);
+int rlr_bm25_score(rlr_bm25 *ix, const uint32_t *query_terms, uint32_t n_terms, uint32_t limit,
+                   uint32_t *out_rows, float *out_scores, uint32_t cap, uint32_t *out_n);
+int rlr_search_text_topm(rlr_store *s, rlr_bm25 *ix, const float *query, uint32_t dim, uint32_t flags,
+                         const rlr_resolved_weights *w, const uint32_t *query_terms, uint32_t n_terms, uint32_t m,
+                         uint32_t *out_rows, float *out_combined, float *out_emb, float *out_lex, uint32_t *out_n);
+int rlr_search_text_mmr(rlr_store *s, rlr_bm25 *ix, const float *query, uint32_t dim, uint32_t flags,
+                        uint32_t top_k, float diversity_factor, const rlr_resolved_weights *w,
+                        const uint32_t *query_terms, uint32_t n_terms,
+                        uint32_t *out_rows, float *out_score, float *out_emb, float *out_lex, uint32_t *out_n);
+
 /* (The host-side BM25 twin that the non-Rust host mirrors use for text queries lives in
  * include/rlr_hostmirror.h / librlr_hostmirror.so: host-mirror support, not part of this boundary.) */
 

@@ -6,8 +6,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librlr_b200.so")
-SOURCES = ["api.cu", "cluster.cu", "scan_topm.cu", "merge.cu", "mmr.cu", "synth.cu", "batch_gemm.cu"]
-HEADERS = ["common.cuh", "kernels.cuh", "sort_regs.cuh", "api_internal.hpp", os.path.join("..", "..", "include", "rlr_b200.h")]
+SOURCES = ["api.cu", "cluster.cu", "scan_topm.cu", "merge.cu", "mmr.cu", "synth.cu", "batch_gemm.cu", "bm25.cu"]
+HEADERS = ["common.cuh", "kernels.cuh", "sort_regs.cuh", "mmr_device.cuh", "api_internal.hpp", os.path.join("..", "..", "include", "rlr_b200.h")]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3",

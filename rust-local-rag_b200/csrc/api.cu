@@ -937,9 +937,38 @@ void timings_from_events(rlr_ctx *c, bool has_mmr)
 
 } // namespace
 
-RLR_EXPORT int rlr_search_topm(rlr_store *s, const float *query, uint32_t dim, uint32_t flags,
+namespace {
+
+// A text query's lexical stage on the device (bm25.cu): LexicalIndex::score(query, 5 * top_k) (:505) enqueued on the
+// ctx's stream, its (sorted local rows, score / max_lexical) form written into the ctx's lexical arrays.
+struct TextQuery {
+    rlr_bm25 *ix = nullptr;           // null: the caller supplied (row, score) pairs instead
+    const uint32_t *terms = nullptr;
+    uint32_t n_terms = 0;
+};
+struct Bm25WsGuard {
+    rlr_bm25 *ix = nullptr;
+    void *ws = nullptr;
+    ~Bm25WsGuard() { if (ws) rlr_api_bm25_ws_release(ix, ws); }
+};
+int stage_text(rlr_ctx *c, const TextQuery &tq, uint32_t limit, Bm25WsGuard &g, cudaStream_t st, uint32_t *out_nl)
+{
+    *out_nl = 0;
+    if (rlr_api_bm25_store(tq.ix) != c->s) return fail(RLR_ERR_INVALID_ARG, "the BM25 index belongs to another store");
+    if (limit > kLexCap) return fail(RLR_ERR_UNSUPPORTED, "5 * m = %u lexical candidates exceed %u", limit, kLexCap);
+    g.ix = tq.ix;
+    if (int rc = rlr_api_bm25_ws_acquire(tq.ix, &g.ws)) return rc;
+    bool active = false;
+    if (int rc = rlr_api_bm25_enqueue(tq.ix, g.ws, tq.terms, tq.n_terms, limit, c->d_lex_rows, c->d_lex_norm, limit, nullptr, nullptr,
+                                      nullptr, st, &active))
+        return rc;
+    if (active) { *out_nl = limit; c->launches += rlr_api_bm25_launches(); }
+    return RLR_OK;
+}
+
+int search_topm_impl(rlr_store *s, const float *query, uint32_t dim, uint32_t flags,
                                const rlr_resolved_weights *w, const uint32_t *lex_rows, const float *lex_scores,
-                               uint32_t n_lex, uint32_t m, uint32_t *out_rows, float *out_combined, float *out_emb,
+                               uint32_t n_lex, const TextQuery &tq, uint32_t m, uint32_t *out_rows, float *out_combined, float *out_emb,
                                float *out_lex, uint32_t *out_n)
 {
     if (int rc = check_store(s)) return rc;
@@ -957,9 +986,18 @@ RLR_EXPORT int rlr_search_topm(rlr_store *s, const float *query, uint32_t dim, u
     cudaStream_t st = c->stream;
     const uint64_t launches0 = c->launches;
     const uint32_t m_eff = static_cast<uint32_t>(std::min<uint64_t>(m, s->n_rows));
+    Bm25WsGuard bm_guard;
+    const uint32_t lex_limit = 5u * m;       // lexical_index.score(query, top_k * 5), :505 (m is `top_k` here)
     if (lat_eligible(s, flags)) {         // small store: one launch, no copies, no stream synchronisation
         uint32_t nl_lat = 0;
         bool fits = true;
+        c->lat.d_lex_rows = nullptr; c->lat.d_lex_norm = nullptr;
+        if (tq.ix) {
+            if (int rc = lat_stage_query(c, query, dim, flags)) return rc;
+            if (int rc = stage_text(c, tq, lex_limit, bm_guard, st, &nl_lat)) return rc;
+            c->lat.d_lex_rows = c->d_lex_rows; c->lat.d_lex_norm = c->d_lex_norm;
+            return lat_search(s, c, flags, w, nl_lat, m_eff, false, 0, 0.0f, out_rows, out_combined, out_emb, out_lex, out_n);
+        }
         if (int rc = lat_stage_lex(c, lex_rows, lex_scores, n_lex, &nl_lat, &fits)) return rc;
         if (fits) {
             if (int rc = lat_stage_query(c, query, dim, flags)) return rc;
@@ -968,7 +1006,8 @@ RLR_EXPORT int rlr_search_topm(rlr_store *s, const float *query, uint32_t dim, u
     }
     if (int rc = stage_query(c, query, dim, flags, st)) return rc;
     uint32_t nl = 0;
-    if (int rc = stage_lex(c, lex_rows, lex_scores, n_lex, &nl, st)) return rc;
+    if (tq.ix) { if (int rc = stage_text(c, tq, lex_limit, bm_guard, st, &nl)) return rc; }
+    else if (int rc = stage_lex(c, lex_rows, lex_scores, n_lex, &nl, st)) return rc;
     const bool timed = flags & RLR_WANT_TIMINGS;
     if (timed) CU_TRY(cudaEventRecord(c->ev[0], st));
     if (int rc = enqueue_topm(c, c->d_query, w->embedding, w->lexical, c->d_lex_rows, c->d_lex_norm, nl, m_eff,
@@ -982,6 +1021,26 @@ RLR_EXPORT int rlr_search_topm(rlr_store *s, const float *query, uint32_t dim, u
     *out_n = n;
     if (timed) { timings_from_events(c, false); g_timings.launches = static_cast<uint32_t>(c->launches - launches0); }
     return RLR_OK;
+}
+
+} // namespace
+
+RLR_EXPORT int rlr_search_topm(rlr_store *s, const float *query, uint32_t dim, uint32_t flags,
+                               const rlr_resolved_weights *w, const uint32_t *lex_rows, const float *lex_scores,
+                               uint32_t n_lex, uint32_t m, uint32_t *out_rows, float *out_combined, float *out_emb,
+                               float *out_lex, uint32_t *out_n)
+{
+    return search_topm_impl(s, query, dim, flags, w, lex_rows, lex_scores, n_lex, TextQuery(), m, out_rows, out_combined, out_emb, out_lex, out_n);
+}
+
+RLR_EXPORT int rlr_search_text_topm(rlr_store *s, rlr_bm25 *ix, const float *query, uint32_t dim, uint32_t flags,
+                                    const rlr_resolved_weights *w, const uint32_t *query_terms, uint32_t n_terms, uint32_t m,
+                                    uint32_t *out_rows, float *out_combined, float *out_emb, float *out_lex, uint32_t *out_n)
+{
+    if (!ix) return fail(RLR_ERR_INVALID_ARG, "the BM25 index is NULL");
+    TextQuery tq;
+    tq.ix = ix; tq.terms = query_terms; tq.n_terms = n_terms;
+    return search_topm_impl(s, query, dim, flags, w, nullptr, nullptr, 0, tq, m, out_rows, out_combined, out_emb, out_lex, out_n);
 }
 
 RLR_EXPORT int rlr_embedding_candidates(rlr_store *s, const float *query, uint32_t dim, uint32_t flags, uint32_t count,
@@ -1052,9 +1111,10 @@ RLR_EXPORT int rlr_mmr(rlr_store *s, const uint32_t *cand_rows, const float *rel
     return RLR_OK;
 }
 
-RLR_EXPORT int rlr_search_mmr(rlr_store *s, const float *query, uint32_t dim, uint32_t flags, uint32_t top_k,
+namespace {
+int search_mmr_impl(rlr_store *s, const float *query, uint32_t dim, uint32_t flags, uint32_t top_k,
                               float diversity_factor, const rlr_resolved_weights *w, const uint32_t *lex_rows,
-                              const float *lex_scores, uint32_t n_lex, uint32_t *out_rows, float *out_score,
+                              const float *lex_scores, uint32_t n_lex, const TextQuery &tq, uint32_t *out_rows, float *out_score,
                               float *out_emb, float *out_lex, uint32_t *out_n)
 {
     if (int rc = check_store(s)) return rc;
@@ -1066,8 +1126,8 @@ RLR_EXPORT int rlr_search_mmr(rlr_store *s, const float *query, uint32_t dim, ui
     if (lambda > 1.0f) lambda = 1.0f;
     if (lambda == 0.0f) { // :728-730 -> search(top_k), top_k.max(1) at :490
         const uint32_t m = std::max<uint32_t>(top_k, 1);
-        return rlr_search_topm(s, query, dim, flags, w, lex_rows, lex_scores, n_lex, m, out_rows, out_score, out_emb,
-                               out_lex, out_n);
+        return search_topm_impl(s, query, dim, flags, w, lex_rows, lex_scores, n_lex, tq, m, out_rows, out_score, out_emb,
+                                out_lex, out_n);
     }
     *out_n = 0;
     const uint64_t pool = std::max<uint64_t>(3ull * top_k, static_cast<uint64_t>(top_k) + 10); // :734
@@ -1080,9 +1140,18 @@ RLR_EXPORT int rlr_search_mmr(rlr_store *s, const float *query, uint32_t dim, ui
     cudaStream_t st = c->stream;
     const uint64_t launches0 = c->launches;
     const uint32_t p = static_cast<uint32_t>(std::min<uint64_t>(pool, s->n_rows));
+    Bm25WsGuard bm_guard;
+    const uint32_t lex_limit = static_cast<uint32_t>(5u * pool);      // search(pool): lexical_index.score(query, pool * 5), :505
     if (lat_eligible(s, flags)) {         // small store: one launch (pool <= 32) or three, no copies, no stream synchronisation
         uint32_t nl_lat = 0;
         bool fits = true;
+        c->lat.d_lex_rows = nullptr; c->lat.d_lex_norm = nullptr;
+        if (tq.ix) {
+            if (int rc = lat_stage_query(c, query, dim, flags)) return rc;
+            if (int rc = stage_text(c, tq, lex_limit, bm_guard, st, &nl_lat)) return rc;
+            c->lat.d_lex_rows = c->d_lex_rows; c->lat.d_lex_norm = c->d_lex_norm;
+            return lat_search(s, c, flags, w, nl_lat, p, true, top_k, lambda, out_rows, out_score, out_emb, out_lex, out_n);
+        }
         if (int rc = lat_stage_lex(c, lex_rows, lex_scores, n_lex, &nl_lat, &fits)) return rc;
         if (fits) {
             if (int rc = lat_stage_query(c, query, dim, flags)) return rc;
@@ -1091,7 +1160,8 @@ RLR_EXPORT int rlr_search_mmr(rlr_store *s, const float *query, uint32_t dim, ui
     }
     if (int rc = stage_query(c, query, dim, flags, st)) return rc;
     uint32_t nl = 0;
-    if (int rc = stage_lex(c, lex_rows, lex_scores, n_lex, &nl, st)) return rc;
+    if (tq.ix) { if (int rc = stage_text(c, tq, lex_limit, bm_guard, st, &nl)) return rc; }
+    else if (int rc = stage_lex(c, lex_rows, lex_scores, n_lex, &nl, st)) return rc;
     const bool timed = flags & RLR_WANT_TIMINGS;
     if (timed) CU_TRY(cudaEventRecord(c->ev[0], st));
     const bool half = s->use_half(flags);
@@ -1120,6 +1190,27 @@ RLR_EXPORT int rlr_search_mmr(rlr_store *s, const float *query, uint32_t dim, ui
     *out_n = n;
     if (timed) { timings_from_events(c, true); g_timings.launches = static_cast<uint32_t>(c->launches - launches0); }
     return RLR_OK;
+}
+} // namespace
+
+RLR_EXPORT int rlr_search_mmr(rlr_store *s, const float *query, uint32_t dim, uint32_t flags, uint32_t top_k,
+                              float diversity_factor, const rlr_resolved_weights *w, const uint32_t *lex_rows,
+                              const float *lex_scores, uint32_t n_lex, uint32_t *out_rows, float *out_score,
+                              float *out_emb, float *out_lex, uint32_t *out_n)
+{
+    return search_mmr_impl(s, query, dim, flags, top_k, diversity_factor, w, lex_rows, lex_scores, n_lex, TextQuery(), out_rows, out_score,
+                           out_emb, out_lex, out_n);
+}
+
+RLR_EXPORT int rlr_search_text_mmr(rlr_store *s, rlr_bm25 *ix, const float *query, uint32_t dim, uint32_t flags, uint32_t top_k,
+                                   float diversity_factor, const rlr_resolved_weights *w, const uint32_t *query_terms,
+                                   uint32_t n_terms, uint32_t *out_rows, float *out_score, float *out_emb, float *out_lex,
+                                   uint32_t *out_n)
+{
+    if (!ix) return fail(RLR_ERR_INVALID_ARG, "the BM25 index is NULL");
+    TextQuery tq;
+    tq.ix = ix; tq.terms = query_terms; tq.n_terms = n_terms;
+    return search_mmr_impl(s, query, dim, flags, top_k, diversity_factor, w, nullptr, nullptr, 0, tq, out_rows, out_score, out_emb, out_lex, out_n);
 }
 
 // ---------------------------------------------------------------------------------

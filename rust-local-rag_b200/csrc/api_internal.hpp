@@ -145,3 +145,13 @@ struct CtxLease {
 };
 
 } // namespace rlr_api
+
+// bm25.cu: the device BM25 index, used by the text-query entry points of api.cu
+struct rlr_bm25;
+int rlr_api_bm25_ws_acquire(rlr_bm25 *ix, void **out);
+void rlr_api_bm25_ws_release(rlr_bm25 *ix, void *ws);
+int rlr_api_bm25_enqueue(rlr_bm25 *ix, void *ws, const uint32_t *query_terms, uint32_t n_terms, uint32_t limit,
+                         uint32_t *d_lex_rows, float *d_lex_norm, uint32_t lex_pad, uint32_t *d_desc_rows, float *d_desc_scores,
+                         uint32_t *d_n, cudaStream_t st, bool *active);
+uint32_t rlr_api_bm25_launches();
+rlr_store *rlr_api_bm25_store(rlr_bm25 *ix);

@@ -40,6 +40,8 @@ struct LatParams {
     float q[kLatQFloats];                  // normalised query, zero beyond dim
     uint32_t lex_rows[kLatLex];            // sorted local rows
     float lex_norm[kLatLex];
+    const uint32_t *d_lex_rows;            // non-null: the lexical pairs are DEVICE arrays instead (written by the device
+    const float *d_lex_norm;               // BM25 stage right before this launch); the two arrays above are ignored
     uint32_t mode;                         // 0: off (plain scan) | 1: deliver the merged top-m | 2: + fused MMR of the pool
     uint32_t top_k;
     float lambda;

@@ -376,10 +376,14 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     const float *lex_norm = io.g[grp].lex_norm;
     const uint32_t n_lex = io.g[grp].n_lex;
     if constexpr (kLat) {
-        uint32_t *lr = reinterpret_cast<uint32_t *>(smem + L.lex_off);
-        float *ln = reinterpret_cast<float *>(smem + L.lex_off + kLatLex * 4);
-        for (uint32_t i = tid; i < n_lex; i += kThreads) { lr[i] = lp.lex_rows[i]; ln[i] = lp.lex_norm[i]; }
-        lex_rows = lr; lex_norm = ln;
+        if (lp.d_lex_rows != nullptr) {
+            lex_rows = lp.d_lex_rows; lex_norm = lp.d_lex_norm;       // written on the device by the BM25 stage
+        } else {
+            uint32_t *lr = reinterpret_cast<uint32_t *>(smem + L.lex_off);
+            float *ln = reinterpret_cast<float *>(smem + L.lex_off + kLatLex * 4);
+            for (uint32_t i = tid; i < n_lex; i += kThreads) { lr[i] = lp.lex_rows[i]; ln[i] = lp.lex_norm[i]; }
+            lex_rows = lr; lex_norm = ln;
+        }
     }
 
     if (tid == 0) {

@@ -354,6 +354,35 @@ class DeviceStore:
         k = n.value
         return rows[:k], score[:k], emb[:k], lex[:k]
 
+    def search_text_topm(self, query: np.ndarray, m: int, w: ResolvedWeights, bm25, terms, flags: int = 0):
+        """rlr_search_text_topm: RagEngine::search for a TEXT query -- BM25 (`bm25`: an rlr_bm25 handle, `terms`: the
+        query's term ids in bytewise term order), blend, top-m, all on the device."""
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        t = np.ascontiguousarray(terms, dtype=np.uint32)
+        rows = np.empty(m, np.uint32); comb = np.empty(m, np.float32)
+        emb = np.empty(m, np.float32); lex = np.empty(m, np.float32)
+        n = C.c_uint32(0)
+        wc = B.ResolvedWeightsC(w.embedding, w.lexical, w.reranker, w.initial)
+        B.check(self._lib.rlr_search_text_topm(self._h, bm25, B.ptr(q), q.shape[0], flags, C.byref(wc), B.ptr(t) if len(t) else None,
+                                               len(t), m, B.ptr(rows), B.ptr(comb), B.ptr(emb), B.ptr(lex), C.byref(n)))
+        k = n.value
+        return rows[:k], comb[:k], emb[:k], lex[:k]
+
+    def search_text_mmr(self, query: np.ndarray, top_k: int, diversity: float, w: ResolvedWeights, bm25, terms, flags: int = 0):
+        """rlr_search_text_mmr: RagEngine::search_with_diversity for a TEXT query, one device sequence."""
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        t = np.ascontiguousarray(terms, dtype=np.uint32)
+        cap = max(top_k, 1)
+        rows = np.empty(cap, np.uint32); score = np.empty(cap, np.float32)
+        emb = np.empty(cap, np.float32); lex = np.empty(cap, np.float32)
+        n = C.c_uint32(0)
+        wc = B.ResolvedWeightsC(w.embedding, w.lexical, w.reranker, w.initial)
+        B.check(self._lib.rlr_search_text_mmr(self._h, bm25, B.ptr(q), q.shape[0], flags, top_k, diversity, C.byref(wc),
+                                              B.ptr(t) if len(t) else None, len(t), B.ptr(rows), B.ptr(score), B.ptr(emb),
+                                              B.ptr(lex), C.byref(n)))
+        k = n.value
+        return rows[:k], score[:k], emb[:k], lex[:k]
+
     def search_mmr_multi(self, queries: np.ndarray, top_k: int, diversity: float, w: ResolvedWeights, lex=None,
                          flags: int = 0):
         """rlr_search_mmr_multi (throughput mode): up to RLR_MAX_MULTI queries answered by ONE pass over the rows.
@@ -586,6 +615,75 @@ class LexicalIndex:
             pass
 
 
+def tokenize(text: str) -> List[str]:
+    """fn tokenize (src/rag_engine.rs:2242-2247) through the host-mirror support library (strings stay on the host)."""
+    lib = B.load_hostmirror()
+    b = text.encode("utf-8")
+    out = C.create_string_buffer(3 * len(b) + 16)          # lowercase mappings may grow a token
+    n, nt = C.c_size_t(0), C.c_uint32(0)
+    B.check_hm(lib.rlr_tokenize(b, len(b), out, len(out), C.byref(n), C.byref(nt)))
+    return out.raw[:n.value].decode("utf-8").split("\n") if n.value else []
+
+
+class DeviceLexicalIndex:
+    """LexicalIndex (src/rag_engine.rs:2083-2231) with the postings scored ON THE DEVICE (rlr_bm25_*).
+    The host keeps what is string work: the tokenizer and the term -> id dictionary.  Chunks are identified by their
+    row in the store."""
+
+    def __init__(self, store: "DeviceStore"):
+        self._lib = B.load()
+        self._store = store
+        self._h = C.c_void_p()
+        B.check(self._lib.rlr_bm25_create(store.handle, C.byref(self._h)))
+        self.vocab = {}
+
+    @property
+    def handle(self):
+        return self._h
+
+    def add_chunk(self, row: int, text: str) -> None:
+        counts = {}
+        for t in tokenize(text):
+            counts[t] = counts.get(t, 0) + 1
+        ids = np.array([self.vocab.setdefault(t, len(self.vocab)) for t in counts], np.uint32)
+        tfs = np.array(list(counts.values()), np.uint32)
+        B.check(self._lib.rlr_bm25_set_doc(self._h, row, B.ptr(ids) if len(ids) else None, B.ptr(tfs) if len(ids) else None, len(ids)))
+
+    def remove_chunk(self, row: int) -> None:
+        B.check(self._lib.rlr_bm25_remove_doc(self._h, row))
+
+    def move(self, from_row: int, to_row: int) -> None:
+        B.check(self._lib.rlr_bm25_move_doc(self._h, from_row, to_row))
+
+    def query_terms(self, query: str) -> np.ndarray:
+        """The query's known term ids in bytewise order of the term strings (the summation order, see rlr_b200.h)."""
+        terms = sorted(set(tokenize(query)), key=lambda t: t.encode("utf-8"))
+        return np.array([self.vocab[t] for t in terms if t in self.vocab], np.uint32)
+
+    def stats(self):
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        B.check(self._lib.rlr_bm25_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def score(self, query: str, limit: int) -> List[Tuple[int, float]]:
+        """LexicalIndex::score(query, limit) -> [(row, score)], score desc (ties: lower row)."""
+        t = self.query_terms(query)
+        rows, sc, n = np.zeros(limit, np.uint32), np.zeros(limit, np.float32), C.c_uint32(0)
+        B.check(self._lib.rlr_bm25_score(self._h, B.ptr(t) if len(t) else None, len(t), limit, B.ptr(rows), B.ptr(sc), limit, C.byref(n)))
+        return [(int(r), np.float32(x)) for r, x in zip(rows[:n.value], sc[:n.value])]
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.rlr_bm25_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _make_store(rows: np.ndarray, device: int, devices: Optional[Sequence[int]]):
     """One GPU -> DeviceStore; `devices=[...]` -> the same rows sharded over those GPUs (ClusterStore)."""
     if devices is not None and len(devices) > 1:
@@ -605,6 +703,10 @@ class RagEngine:
         self.store = store
         self.model = model
         self.embedder = embedder
+        if lexical == "bm25-device":             # the same index with the postings on the GPU (rlr_bm25_*)
+            lexical = DeviceLexicalIndex(store)
+            for i, c in enumerate(chunks):
+                lexical.add_chunk(i, c.text)
         if lexical == "bm25":                    # validate_index_sync, :1375-1389: index every chunk's text
             lexical = LexicalIndex()
             for c in chunks:
@@ -803,7 +905,7 @@ class RagEngine:
         return np.asarray(query, dtype=np.float32)
 
     def _lex(self, query: Query, top_k: int):
-        if self.lexical is None or not isinstance(query, str):
+        if self.lexical is None or not isinstance(query, str) or isinstance(self.lexical, DeviceLexicalIndex):
             return None, None
         pairs = self.lexical(query, top_k * 5)   # :505 lexical_index.score(query, top_k*5)
         rows, scores = [], []
@@ -829,6 +931,9 @@ class RagEngine:
         w = resolve_weights(weights)             # :481
         top_k = max(int(top_k), 1)               # :490
         q = self._embed(query)
+        if isinstance(self.lexical, DeviceLexicalIndex) and isinstance(query, str):
+            rows, comb, emb, lex = self.store.search_text_topm(q, top_k, w, self.lexical.handle, self.lexical.query_terms(query))
+            return [self._result(r, c, e, l) for r, c, e, l in zip(rows, comb, emb, lex)]
         lr, ls = self._lex(query, top_k)
         rows, comb, emb, lex = self.store.search_topm(q, top_k, w, lr, ls)
         return [self._result(r, c, e, l) for r, c, e, l in zip(rows, comb, emb, lex)]
@@ -840,6 +945,10 @@ class RagEngine:
             return []
         w = resolve_weights(weights)
         q = self._embed(query)
+        if isinstance(self.lexical, DeviceLexicalIndex) and isinstance(query, str):
+            rows, score, emb, lex = self.store.search_text_mmr(q, int(top_k), float(diversity_factor), w, self.lexical.handle,
+                                                                self.lexical.query_terms(query))
+            return [self._result(r, c, e, l) for r, c, e, l in zip(rows, score, emb, lex)]
         lam = min(max(float(diversity_factor), 0.0), 1.0) if diversity_factor == diversity_factor else diversity_factor
         pool = max(int(top_k), 1) if lam == 0.0 else max(3 * int(top_k), int(top_k) + 10)
         lr, ls = self._lex(query, pool)

@@ -8,7 +8,7 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let lib = out.join("librlr_b200.so");
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
-    let sources = ["api.cu", "cluster.cu", "scan_topm.cu", "merge.cu", "mmr.cu", "synth.cu", "batch_gemm.cu"];
+    let sources = ["api.cu", "cluster.cu", "scan_topm.cu", "merge.cu", "mmr.cu", "synth.cu", "batch_gemm.cu", "bm25.cu"];
     let status = Command::new(&nvcc)
         .current_dir(&csrc)
         .args(["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false"])
@@ -18,7 +18,7 @@ fn main() {
         .status()
         .expect("failed to run nvcc");
     assert!(status.success(), "nvcc failed");
-    for s in sources.iter().chain(["common.cuh", "kernels.cuh", "sort_regs.cuh", "api_internal.hpp"].iter()) {
+    for s in sources.iter().chain(["common.cuh", "kernels.cuh", "sort_regs.cuh", "mmr_device.cuh", "api_internal.hpp"].iter()) {
         println!("cargo:rerun-if-changed={}", csrc.join(s).display());
     }
     println!("cargo:rerun-if-changed={}", root.join("include/rlr_b200.h").display());
