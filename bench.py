@@ -947,6 +947,79 @@ def run_extras(a, rank, world, local_rank, dev, group, peaks, cpu_group=None):
         out["config2_1m_k100"] = rec
         all_ok &= ok
 
+    # ---- config 1 as a TEXT query: BM25 (LexicalIndex::score) on the device vs on the host, then the same search ----
+    if world == 1:
+        import random as _random
+        from oracle import lexical as olex
+        clk = ClockSampler(local_rank, interval=0.005)
+        n_t, dim_t, k_t, lam_t = 10_000, 768, 5, 0.3
+        rng = _random.Random(1)
+        vocab = [f"w{rng.randrange(10**6):06d}" for _ in range(30000)]
+        zipf = [1.0 / (i + 1) for i in range(len(vocab))]
+        docs = [" ".join(rng.choices(vocab, zipf, k=200)) for _ in range(n_t)]
+        tq = [" ".join(rng.choices(vocab, zipf, k=8)) for _ in range(32)]
+        st = engine.DeviceStore.synthetic(n_t, dim_t, device=local_rank, **kw)
+        qh = queries(32, dim_t)
+        dev_ix = engine.DeviceLexicalIndex(st)
+        host_ix = engine.LexicalIndex()
+        for i, d in enumerate(docs):
+            dev_ix.add_chunk(i, d)
+            host_ix.add_chunk(str(i), d)
+        limit = 5 * max(3 * k_t, k_t + 10)
+        terms = [dev_ix.query_terms(q) for q in tq]
+
+        def host_query(i):
+            pairs = host_ix.score(tq[i % 32], limit)
+            lr = np.array([int(r) for r, _ in pairs], np.uint32); ls = np.array([s_ for _, s_ in pairs], np.float32)
+            return st.search_mmr(qh[i % 32], k_t, lam_t, wts, lr, ls)
+
+        def p50(f, n):
+            for i in range(5):
+                f(i)
+            lat = []
+            for i in range(n):
+                t0 = time.perf_counter()
+                f(i)
+                lat.append(time.perf_counter() - t0)
+            return 1e3 * statistics.median(lat)
+
+        clk.start()
+        dev_ms = p50(lambda i: st.search_text_mmr(qh[i % 32], k_t, lam_t, wts, dev_ix.handle, terms[i % 32]), 300)
+        clk.stop()
+        host_ms = p50(host_query, 20)
+        bm_dev_ms = p50(lambda i: dev_ix.score(tq[i % 32], limit), 100)
+        bm_host_ms = p50(lambda i: host_ix.score(tq[i % 32], limit), 20)
+        # parity: device BM25 + search == host-twin pairs + search (two product paths), and == the oracle's search fed with
+        # the pure-Python oracle's BM25 pairs for two queries (the restatement is slow on 10k x 200-token chunks)
+        okt = True
+        for i in range(8):
+            a_, b_ = st.search_text_mmr(qh[i], k_t, lam_t, wts, dev_ix.handle, terms[i]), host_query(i)
+            okt &= all(x.tobytes() == y.tobytes() for x, y in zip(a_, b_))
+        ref_ix = olex.LexicalIndex()
+        for i, d in enumerate(docs):
+            ref_ix.add_chunk(i, d)
+        host_rows = orc.synth_rows(n_t, dim_t, threads=max(orc.max_threads(), 1), **SYNTH)
+        for i in range(2):
+            pairs = ref_ix.score(tq[i], limit)
+            lr = np.array([r for r, _ in pairs], np.uint32); ls = np.array([s_ for _, s_ in pairs], np.float32)
+            want = orc.search_with_diversity(host_rows, qh[i], k_t, lam_t, lex_rows=lr, lex_scores=ls, threads=max(orc.max_threads(), 1))
+            got = st.search_text_mmr(qh[i], k_t, lam_t, wts, dev_ix.handle, terms[i])
+            okt &= all(x.tobytes() == y.tobytes() for x, y in zip(got, want))
+        out["config1_text_query_bm25_on_device"] = {
+            "workload": f"search_documents for a TEXT query (8 terms, Zipf vocabulary) over {n_t} chunks of 200 tokens x {dim_t}-d, top_k={k_t} "
+                        f"diversity={lam_t}: LexicalIndex::score(query, {limit}) + blend + top-k + MMR",
+            "device_bm25": {"p50_latency_ms": dev_ms, "api": "rlr_search_text_mmr: BM25 scoring, top-5k selection, normalisation, scan + blend, MMR on one stream",
+                            "lexical_score_only_p50_ms": bm_dev_ms},
+            "host_bm25": {"p50_latency_ms": host_ms, "api": "host-mirror LexicalIndex twin (hash-map postings like the reference's) + rlr_search_mmr",
+                          "lexical_score_only_p50_ms": bm_host_ms},
+            "speedup_whole_query": host_ms / dev_ms,
+            "parity": {"ok": bool(okt), "what": "8 queries: device-BM25 path == host-pairs path bit for bit; 2 queries == the oracle's search fed with "
+                                                "the pure-Python BM25 restatement's pairs"},
+            "clocks": clk.summary()}
+        all_ok &= bool(okt)
+        dev_ix.close(); host_ix.close(); st.close()
+        del host_rows
+
     # ---- config 4: batched queries on the tensor cores, three operand precisions ----
     if world in (1, 8):
         n4 = 1_250_000 * world

@@ -133,28 +133,53 @@ bm25_select_pass_kernel(const unsigned long long *__restrict__ keys, uint32_t n,
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // last CTA: walk the bins from the top until the wanted rank falls inside one
+    // last CTA: find, from the top, the bin that holds the wanted rank.  Parallel: thread t owns the 8 bins
+    // [(255 - t) * 8, (255 - t) * 8 + 8) (thread 0 = the top bins), a block-wide scan of the per-thread sums tells each
+    // thread how many keys sit above its bins, and exactly one thread finds the rank inside its own eight.
     for (uint32_t i = threadIdx.x; i < kBins; i += blockDim.x) h[i] = __ldcg(hist + i);
     __syncthreads();
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_want, s_skip;
     if (threadIdx.x == 0) {
-        uint32_t want = pass == 0 ? limit : sel->remaining;
         const uint32_t n_hits = *reinterpret_cast<volatile uint32_t *>(&sel->n_hits);
+        s_skip = 0;
         if (pass == 0 && n_hits <= limit) {
             sel->kstar = 1ull;                                        // fewer hits than the limit: everything survives
             sel->remaining = 0;
-        } else if (sel->kstar != 1ull) {
-            uint32_t d = (1u << width) - 1u;
-            for (;; --d) {
-                const uint32_t c = h[d];
-                if (c >= want) break;
-                want -= c;
-                if (d == 0) break;
-            }
-            sel->prefix = prefix | (static_cast<unsigned long long>(d) << shift);
-            sel->remaining = want;
-            if (shift == 0) sel->kstar = sel->prefix;                 // every digit decided: the limit-th largest key
+            s_skip = 1;
+        } else if (sel->kstar == 1ull) {
+            s_skip = 1;
         }
+        s_want = pass == 0 ? limit : sel->remaining;
         sel->ticket = 0;
+    }
+    __syncthreads();
+    if (!s_skip) {
+        const uint32_t t = threadIdx.x, lane = t & 31u, wp = t >> 5;
+        const uint32_t base = (255u - t) * 8u;
+        uint32_t c[8], sum = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { c[i] = h[base + 7 - i]; sum += c[i]; }      // c[0] = the highest of my bins
+        uint32_t incl = sum;                                                      // inclusive scan over threads 0..t
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= static_cast<uint32_t>(o)) incl += v; }
+        if (lane == 31) s_warp[wp] = incl;
+        __syncthreads();
+        uint32_t above = incl - sum;
+        for (uint32_t w2 = 0; w2 < wp; ++w2) above += s_warp[w2];
+        const uint32_t want = s_want;
+        if (above < want && want <= above + sum) {                                // the rank falls inside my eight bins
+            uint32_t w3 = want - above, d = base + 7;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (w3 <= c[i]) { d = base + 7 - i; break; }
+                w3 -= c[i];
+            }
+            const unsigned long long np = prefix | (static_cast<unsigned long long>(d) << shift);
+            sel->prefix = np;
+            sel->remaining = w3;
+            if (shift == 0) sel->kstar = np;                                      // every digit decided: the limit-th largest key
+        }
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < kBins; i += blockDim.x) hist[i] = 0;      // ready for the next pass
