@@ -248,8 +248,57 @@ public:
     }
 };
 
+// LexicalIndex with the postings scored ON THE DEVICE (rlr_bm25_*): the host keeps the tokenizer (host-mirror support
+// library) and the term -> id dictionary; chunks are identified by their row in the store.
+class DeviceLexicalIndex {
+    rlr_bm25 *ix_ = nullptr;
+    std::unordered_map<std::string, uint32_t> vocab_;
+
+    static std::vector<std::string> tokenize(const std::string &text)      // fn tokenize, :2242-2247
+    {
+        std::string buf(3 * text.size() + 16, '\0');
+        size_t n = 0;
+        uint32_t nt = 0;
+        check_hm(rlr_tokenize(text.data(), text.size(), &buf[0], buf.size(), &n, &nt));
+        std::vector<std::string> out;
+        size_t a = 0;
+        for (size_t i = 0; i <= n && n; ++i)
+            if (i == n || buf[i] == '\n') { out.emplace_back(buf.substr(a, i - a)); a = i + 1; }
+        return out;
+    }
+
+public:
+    explicit DeviceLexicalIndex(rlr_store *s) { check(rlr_bm25_create(s, &ix_)); }
+    DeviceLexicalIndex(const DeviceLexicalIndex &) = delete;
+    DeviceLexicalIndex &operator=(const DeviceLexicalIndex &) = delete;
+    ~DeviceLexicalIndex() { rlr_bm25_destroy(ix_); }
+    rlr_bm25 *handle() const { return ix_; }
+    void add_chunk(uint32_t row, const std::string &text)
+    {
+        std::map<std::string, uint32_t> counts;
+        for (auto &t : tokenize(text)) ++counts[t];
+        std::vector<uint32_t> ids, tfs;
+        for (auto &kv : counts) {
+            auto it = vocab_.find(kv.first);
+            if (it == vocab_.end()) it = vocab_.emplace(kv.first, static_cast<uint32_t>(vocab_.size())).first;
+            ids.push_back(it->second); tfs.push_back(kv.second);
+        }
+        check(rlr_bm25_set_doc(ix_, row, ids.data(), tfs.data(), static_cast<uint32_t>(ids.size())));
+    }
+    // the query's known term ids in bytewise order of the term strings (std::map<std::string> iterates in that order)
+    std::vector<uint32_t> query_terms(const std::string &query) const
+    {
+        std::map<std::string, int> uniq;
+        for (auto &t : tokenize(query)) uniq[t] = 1;
+        std::vector<uint32_t> out;
+        for (auto &kv : uniq) { auto it = vocab_.find(kv.first); if (it != vocab_.end()) out.push_back(it->second); }
+        return out;
+    }
+};
+
 class RagEngine {
     std::unique_ptr<LexicalIndex> lexical_;          // built by enable_lexical(): validate_index_sync, :1375-1389
+    std::unique_ptr<DeviceLexicalIndex> dev_lexical_; // or by enable_lexical_on_device(): the same index, postings on the GPU
     rlr_store *store_ = nullptr;                     // one GPU ...
     rlr_cluster *cluster_ = nullptr;                 // ... or the same rows sharded over several GPUs, driven from this process
     std::vector<int> devices_;                       // > 1 entry: cluster
@@ -290,7 +339,7 @@ public:
     explicit RagEngine(std::vector<int> devices) : devices_(std::move(devices)), device_(devices_.empty() ? 0 : devices_[0]) {}
     RagEngine(const RagEngine &) = delete;
     RagEngine &operator=(const RagEngine &) = delete;
-    ~RagEngine() { if (store_) rlr_store_destroy(store_); if (cluster_) rlr_cluster_destroy(cluster_); }
+    ~RagEngine() { dev_lexical_.reset(); if (store_) rlr_store_destroy(store_); if (cluster_) rlr_cluster_destroy(cluster_); }
     bool sharded() const { return cluster_ != nullptr; }
 
     size_t len() const { return chunks_.size(); }
@@ -303,6 +352,14 @@ public:
         for (auto &c : chunks_) lexical_->add_chunk(c.id, c.text);
     }
     const LexicalIndex *lexical() const { return lexical_.get(); }
+    // The same, with the postings on the device (single-GPU stores): text queries then run BM25, blend, top-k and MMR
+    // as one device sequence (rlr_search_text_*).
+    void enable_lexical_on_device()
+    {
+        if (!store_) throw Error(RLR_ERR_UNSUPPORTED, "device BM25 needs a single-GPU store");
+        dev_lexical_.reset(new DeviceLexicalIndex(store_));
+        for (uint32_t i = 0; i < chunks_.size(); ++i) dev_lexical_->add_chunk(i, chunks_[i].text);
+    }
 
     // search / search_with_diversity for a TEXT query whose embedding the caller already has
     // (EmbeddingService is host HTTP, out of scope): runs lexical_index.score(query, 5 * top_k) (:505).
@@ -318,6 +375,19 @@ public:
         float lam = diversity_factor;
         if (lam < 0.0f) lam = 0.0f;
         if (lam > 1.0f) lam = 1.0f;
+        if (dev_lexical_ && !chunks_.empty()) {
+            const rlr_resolved_weights w = resolve_weights(weights);
+            const std::vector<uint32_t> terms = dev_lexical_->query_terms(query);
+            const size_t cap = std::max<size_t>(top_k, 1);
+            std::vector<uint32_t> rows(cap); std::vector<float> score(cap), emb(cap), lex(cap);
+            uint32_t n = 0;
+            check(rlr_search_text_mmr(store_, dev_lexical_->handle(), query_embedding.data(), static_cast<uint32_t>(query_embedding.size()), 0,
+                                      static_cast<uint32_t>(top_k), diversity_factor, &w, terms.data(), static_cast<uint32_t>(terms.size()),
+                                      rows.data(), score.data(), emb.data(), lex.data(), &n));
+            std::vector<SearchResult> out;
+            for (uint32_t i = 0; i < n; ++i) out.push_back(result(rows[i], score[i], emb[i], lex[i]));
+            return out;
+        }
         const size_t pool = lam == 0.0f ? std::max<size_t>(top_k, 1) : std::max<size_t>(3 * top_k, top_k + 10);   // :728-734
         return search_with_diversity(query_embedding, top_k, diversity_factor, weights,
                                      lexical_ ? lexical_->score(query, 5 * pool) : std::vector<std::pair<std::string, float>>{});

@@ -44,7 +44,10 @@ int main(int argc, char **argv)
             eng.replace_document(doc, std::move(cs), std::move(emb));
         }
         const bool text_mode = argc >= 7 && std::string(argv[5]) == "text";
-        if (text_mode) eng.enable_lexical();         // BM25 over the chunk texts (validate_index_sync)
+        if (text_mode) {                             // BM25 over the chunk texts (validate_index_sync)
+            if (getenv("RLR_CLI_BM25_DEVICE")) eng.enable_lexical_on_device();   // postings scored on the GPU (rlr_bm25_*)
+            else eng.enable_lexical();
+        }
         auto res = text_mode ? eng.search_text_with_diversity(argv[6], q, top_k, lam) : eng.search_with_diversity(q, top_k, lam);
         auto cand = eng.get_embedding_candidates(q, 7);
         printf("{\"n\":%zu,\"needs_reindex\":%s,\"results\":[", eng.len(), eng.needs_reindex() ? "true" : "false");

@@ -122,9 +122,13 @@ def test_cpp_host_hybrid_text_query(tmp_path, orc):
     ref_idx = olex.LexicalIndex()
     for i, t in enumerate(texts):
         ref_idx.add_chunk(i, t)
-    for query, k, lam in (("memory of the café server", 6, 0.4), ("rust tokio", 10, 0.0)):
+    for query, k, lam, on_device in (("memory of the café server", 6, 0.4, False), ("rust tokio", 10, 0.0, False),
+                                     ("memory of the café server", 6, 0.4, True), ("rust tokio index", 10, 0.0, True),
+                                     ("Memory MEMORY lexical rerank", 100, 0.7, True)):
+        # on_device: rlr::DeviceLexicalIndex -- the postings scored on the GPU, the whole text query one device sequence
+        env = dict(os.environ, RLR_CLI_BM25_DEVICE="1") if on_device else dict(os.environ)
         out = json.loads(subprocess.run([exe, idx, qp, str(k), str(lam), "text", query], capture_output=True, text=True,
-                                        check=True).stdout)
+                                        check=True, env=env).stdout)
         pool = max(k, 1) if lam == 0.0 else max(3 * k, k + 10)
         pairs = ref_idx.score(query, 5 * pool)
         lr, ls = np.array([p[0] for p in pairs], np.uint32), np.array([p[1] for p in pairs], F32)
