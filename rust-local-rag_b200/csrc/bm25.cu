@@ -111,6 +111,7 @@ bm25_select_pass_kernel(const unsigned long long *__restrict__ keys, uint32_t n,
     const uint32_t hi_bit = 64u - pass * kDigitBits;                  // bits [shift, hi_bit) are this pass's digit
     const uint32_t shift = hi_bit > kDigitBits ? hi_bit - kDigitBits : 0u;
     const uint32_t width = hi_bit - shift;
+    if (pass != 0 && sel->kstar != 0ull) return;                      // decided by an earlier pass (written by an earlier launch)
     const unsigned long long prefix = sel->prefix;
     const unsigned long long hi_mask = pass == 0 ? 0ull : ~0ull << hi_bit;
     for (uint32_t i = threadIdx.x; i < kBins; i += blockDim.x) h[i] = 0;
@@ -169,16 +170,19 @@ bm25_select_pass_kernel(const unsigned long long *__restrict__ keys, uint32_t n,
         for (uint32_t w2 = 0; w2 < wp; ++w2) above += s_warp[w2];
         const uint32_t want = s_want;
         if (above < want && want <= above + sum) {                                // the rank falls inside my eight bins
-            uint32_t w3 = want - above, d = base + 7;
+            uint32_t w3 = want - above, d = base + 7, cd = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                if (w3 <= c[i]) { d = base + 7 - i; break; }
+                if (w3 <= c[i]) { d = base + 7 - i; cd = c[i]; break; }
                 w3 -= c[i];
             }
             const unsigned long long np = prefix | (static_cast<unsigned long long>(d) << shift);
             sel->prefix = np;
             sel->remaining = w3;
-            if (shift == 0) sel->kstar = np;                                      // every digit decided: the limit-th largest key
+            // every digit decided -- or EVERY key of the chosen bin is wanted, so the cut falls right below the bin and the
+            // smallest key with this prefix is a valid threshold: the remaining passes have nothing to do (the usual case
+            // once the 32 score bits are decided and the scores at the cut are distinct)
+            if (shift == 0 || cd == w3) sel->kstar = np;
         }
     }
     __syncthreads();
