@@ -138,3 +138,27 @@ def test_mailbox_argument_errors(rlr):
     lib.rlr_ctx_destroy(ctx)
     lib.rlr_mailbox_close(mb)
     s.close()
+
+
+def test_a_rank_that_never_delivers_yields_an_empty_result_and_a_sticky_status(orc):
+    """a mailbox timeout must not degrade into a wrong answer.  Rank 1 never posts query 1: after the 4 s
+    in-kernel timeout the root's merge delivers an EMPTY result (n = 0, zero keys) and sets the status word -- it
+    does not merge whatever the slot happens to hold -- and a later, complete query is answered correctly again."""
+    n, dim, m = 9000, 96, 40
+    rows = orc.synth_rows(n, dim, kind=1, n_clusters=16)
+    q = orc.normalize(orc.synth_rows(1, dim, kind=1, seed=5, n_clusters=16)[0])
+    rig = Rig(rows, [(0, 4000), (4000, n)], m_cap=64, ring=2)
+    rig.set_query(q)
+    rig.post(0, 1, m)                      # rank 0 posts, rank 1 stays silent
+    rig.merge(1, m)
+    r, s, e, l = rig.result()              # returns after the timeout
+    assert len(r) == 0 and rig.status() == 2
+    assert (rig.out[:m, 0] == 0).all().item()
+    for rk in (0, 1):                      # query 2 is complete: the mailbox works again, the status stays set
+        rig.post(rk, 2, m)
+    rig.merge(2, m)
+    r, s, e, l = rig.result()
+    R, S, E, L = orc.search(rows, q, m, normalize_query=False, full_sort=True)
+    assert r.tobytes() == R.tobytes() and s.tobytes() == S.tobytes()
+    assert rig.status() == 2
+    rig.close()
