@@ -347,6 +347,7 @@ int rlr_batch_merge_async(rlr_store *s, const void *d_lists, uint32_t n_lists, u
  *                         run on the device on one stream with no host round trip in between.
  * Scores are bit-identical to the reference's f32 formula evaluated in that term order (idf's ln() is the C library's
  * logf, computed on the host per query term).  Mutators need exclusivity like the store's; scoring is re-entrant.
+ * An index is bound to its store: use it only while the store lives (destroying it afterwards is allowed).
  * Single-GPU stores; a cluster takes host-computed pairs (rlr_cluster_search_*). */
 typedef struct rlr_bm25 rlr_bm25;
 int rlr_bm25_create(rlr_store *s, rlr_bm25 **out);

@@ -295,6 +295,7 @@ void ws_free(Bm25Ws *w)
 
 struct rlr_bm25 {
     rlr_store *s = nullptr;
+    int device = 0;                  // cached: destroy must not touch the store (it may already be gone)
     // numeric forward index on the host (rebuilt into CSR on the device when dirty): per local row, (term, tf) by term
     std::vector<std::vector<std::pair<uint32_t, uint32_t>>> docs;
     std::vector<uint32_t> doc_len;
@@ -457,6 +458,7 @@ RLR_EXPORT int rlr_bm25_create(rlr_store *s, rlr_bm25 **out)
     if (int rc = ensure_device(s->device)) return rc;
     rlr_bm25 *ix = new rlr_bm25();
     ix->s = s;
+    ix->device = s->device;
     *out = ix;
     return RLR_OK;
 }
@@ -464,7 +466,7 @@ RLR_EXPORT int rlr_bm25_create(rlr_store *s, rlr_bm25 **out)
 RLR_EXPORT int rlr_bm25_destroy(rlr_bm25 *ix)
 {
     if (!ix) return RLR_OK;
-    cudaSetDevice(ix->s->device);
+    cudaSetDevice(ix->device);
     for (Bm25Ws *w : ix->free_ws) ws_free(w);
     cudaFree(ix->d_off); cudaFree(ix->d_terms); cudaFree(ix->d_tfs); cudaFree(ix->d_doclen);
     cudaGetLastError();
