@@ -744,6 +744,7 @@ namespace {
 
 // ---- latency path (small stores; LatParams in kernels.cuh) ----
 constexpr uint64_t kLatMaxRows = 262144;     // beyond this the scan itself dominates and the regular path is as good
+constexpr uint64_t kLatL2Bytes = 48ull << 20;  // stores up to this size are kept L2-resident between queries (126 MB L2, two 63 MB halves)
 
 bool lat_eligible(const rlr_store *s, uint32_t flags)
 {
@@ -842,10 +843,11 @@ int lat_search(rlr_store *s, rlr_ctx *c, uint32_t flags, const rlr_resolved_weig
     const unsigned long long seq = ++c->lat_seq;
     *reinterpret_cast<volatile unsigned long long *>(c->h_result_blk + 8) = 0;
     lp.top_k = top_k; lp.lambda = lambda; lp.pitch = s->pitch; lp.g_rows = s->d_rows; lp.d_sel_pos = c->d_sel_pos;
+    lp.keep_l2 = static_cast<uint64_t>(s->n_rows) * s->pitch * 4 <= kLatL2Bytes ? 1u : 0u;
     lp.result = c->h_result; lp.result_n = c->h_result_n;          // mapped pinned memory (UVA: same pointers on the device)
     lp.flag = reinterpret_cast<unsigned long long *>(c->h_result_blk + 8); lp.seq = seq;
     const size_t ring_bytes = static_cast<size_t>(a.n_stages) * rlr::kScanChunks * rlr::kScanRows * 128;
-    const bool fuse = do_mmr && pool <= rlr::kLatFusePool && 4096 + static_cast<size_t>(pool) * (s->pitch * 4 + 16) <= ring_bytes;
+    const bool fuse = do_mmr && pool <= rlr::kLatFusePool && 4096 + static_cast<size_t>(pool) * (s->pitch * 4 + 128) <= ring_bytes;
     uint32_t cap = pool;
     if (timed) CU_TRY(cudaEventRecord(c->ev[0], st));
     if (!do_mmr) {              // search(top_k): the merged list goes straight to the host
@@ -875,10 +877,15 @@ int lat_search(rlr_store *s, rlr_ctx *c, uint32_t flags, const rlr_resolved_weig
             unsigned long long t0 = ~0ull, t0max = 0, loop_max = 0, loop_min = ~0ull, list_max = 0;
             for (int i = 0; i < g; ++i) { t0 = std::min(t0, h[i]); t0max = std::max(t0max, h[i]); loop_max = std::max(loop_max, h[g + i]); loop_min = std::min(loop_min, h[g + i]); list_max = std::max(list_max, h[2 * g + i]); }
             const unsigned long long *tr = h.data() + 4 * g;
-            fprintf(stderr, "[lat trace grid=%d rpt=%u] launch->first CTA prologue done %.1f us (globaltimer vs host clock, approximate); prologue done first/last 0/%.1f; "
-                            "scan loop end first/last %.1f/%.1f; lists written %.1f; merge start %.1f, merged %.1f, rows staged %.1f, pairwise %.1f, delivered %.1f us\n",
-                    g, s->rpt, (double)(long long)(t0 - host_t0) / 1e3, (t0max - t0) / 1e3, (loop_min - t0) / 1e3, (loop_max - t0) / 1e3, (list_max - t0) / 1e3,
-                    (tr[0] - t0) / 1e3, (tr[4] - t0) / 1e3, (tr[5] - t0) / 1e3, (tr[6] - t0) / 1e3, (tr[7] - t0) / 1e3);
+            unsigned long long entry_min = ~0ull, entry_max = 0;
+            for (int i = 0; i < g; ++i) { entry_min = std::min(entry_min, tr[16 + i]); entry_max = std::max(entry_max, tr[16 + i]); }
+            (void)host_t0;
+            fprintf(stderr, "[lat trace grid=%d rpt=%u] times from the first CTA's kernel entry: entry last %.1f; prologue done first/last %.1f/%.1f; "
+                            "scan loop end first/last %.1f/%.1f; lists written %.1f; merge start %.1f, heads sorted %.1f, merged %.1f, rows staged %.1f, "
+                            "pairwise %.1f, greedy %.1f, delivered %.1f us\n",
+                    g, s->rpt, (entry_max - entry_min) / 1e3, (t0 - entry_min) / 1e3, (t0max - entry_min) / 1e3, (loop_min - entry_min) / 1e3,
+                    (loop_max - entry_min) / 1e3, (list_max - entry_min) / 1e3, (tr[0] - entry_min) / 1e3, (tr[2] - entry_min) / 1e3,
+                    (tr[4] - entry_min) / 1e3, (tr[5] - entry_min) / 1e3, (tr[6] - entry_min) / 1e3, (tr[10] - entry_min) / 1e3, (tr[7] - entry_min) / 1e3);
             *reinterpret_cast<volatile unsigned long long *>(c->h_result_blk + 8) = 0;
         }
         CU_TRY(rlr::scan_launch(a, st));

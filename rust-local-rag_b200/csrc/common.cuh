@@ -109,6 +109,13 @@ __device__ __forceinline__ uint64_t policy_evict_first()
     return pol;
 }
 
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
 // 2-D tiled TMA load, global -> this CTA's shared memory, completion on an mbarrier.
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, int32_t x, int32_t y,
                                             uint32_t bar, uint64_t policy)
@@ -127,6 +134,12 @@ __device__ __forceinline__ void tma_prefetch_desc(const void *tmap)
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// non-blocking half of a named barrier: counts this warp's threads as arrived and carries on
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 __device__ __forceinline__ float4 lds128(uint32_t addr)

@@ -37,11 +37,12 @@ constexpr uint32_t kLatQFloats = 1024;     // query floats a parameter block car
 constexpr uint32_t kLatLex = 192;          // lexical pairs a parameter block carries (5 * pool for pool <= 32, rounded up)
 constexpr uint32_t kLatFusePool = 32;      // pools up to this size are diversified by the scan's last CTA itself
 struct LatParams {
-    float q[kLatQFloats];                  // normalised query, zero beyond dim
+    alignas(16) float q[kLatQFloats];      // normalised query, zero beyond dim (read 16 bytes at a time)
     uint32_t lex_rows[kLatLex];            // sorted local rows
     float lex_norm[kLatLex];
     const uint32_t *d_lex_rows;            // non-null: the lexical pairs are DEVICE arrays instead (written by the device
     const float *d_lex_norm;               // BM25 stage right before this launch); the two arrays above are ignored
+    uint32_t keep_l2;                      // 1: the whole store fits L2 -- load it evict_last so that it stays resident between queries
     uint32_t mode;                         // 0: off (plain scan) | 1: deliver the merged top-m | 2: + fused MMR of the pool
     uint32_t top_k;
     float lambda;

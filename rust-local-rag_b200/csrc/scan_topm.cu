@@ -270,6 +270,158 @@ __device__ void final_merge(uint64_t *keys, float *embs, uint32_t *s_counts, vol
     if (t == 0) *out_n = m_out;
 }
 
+// number of keys in keys[0, n) strictly greater than `mine`: the position of `mine` in descending order (keys are
+// unique).  Every thread walks the same addresses (shared-memory broadcast); for n <= R this beats a bitonic sort.
+__device__ __forceinline__ uint32_t rank_desc(const uint64_t *keys, uint32_t n, uint64_t mine)
+{
+    uint32_t r = 0;
+#pragma unroll 4
+    for (uint32_t i = 0; i < n; ++i) r += keys[i] > mine ? 1u : 0u;
+    return r;
+}
+
+// Latency path (m <= kLatFusePool): the exact top-m of the L sorted lists through a bound taken from the list HEADS.
+// T = the m-th largest head is a lower bound of the global m-th key (m distinct records are >= T), and only the
+// <= m lists whose head is >= T can hold records >= T: sort the heads (payload = list id), then look at those m
+// lists only -- m * m <= 1024 records, all loaded at once -- and rank the survivors.  Two L2 round trips and one
+// small register sort instead of final_merge's sample / verify / append sequence.  The pool is left in `out` (global) AND in `pool_s`
+// (shared); *s_pool_n = its size.
+__device__ __forceinline__ void merge_small(uint64_t *keys, float *embs, uint32_t *s_counts, volatile uint32_t *s_cnt,
+                                         const rlr_cand *lists, const uint32_t *counts, uint32_t Ln, uint32_t m, uint32_t row_base,
+                                         const uint32_t *lex_rows, const float *lex_norm, uint32_t n_lex,
+                                         rlr_cand *__restrict__ out, uint32_t *__restrict__ out_n, rlr_cand *pool_s,
+                                         volatile uint32_t *s_pool_n, uint32_t t, unsigned long long *tr, uint32_t bar)
+{
+    if (t == 0) *s_cnt = 0;
+    named_bar_sync(bar, R);
+    {
+        // 256 head slots, two per thread, both loads (and both counts) in flight together: one L2 round trip
+        static_assert(R == 128, "two head slots per thread");
+        const uint32_t ja = t, jb = t + R;
+        const uint32_t ca = ja < Ln ? __ldcg(counts + ja) : 0u, cb = jb < Ln ? __ldcg(counts + jb) : 0u;
+        const uint64_t ka = ja < Ln ? ld_key(lists + static_cast<size_t>(ja) * m) : 0ull;      // independent of the counts
+        const uint64_t kb = jb < Ln ? ld_key(lists + static_cast<size_t>(jb) * m) : 0ull;
+        s_counts[ja] = ca; s_counts[jb] = cb;
+        keys[ja] = ca ? ka : 0ull; keys[jb] = cb ? kb : 0ull;
+        embs[ja] = __uint_as_float(ja); embs[jb] = __uint_as_float(jb);         // payload: the list a head belongs to
+        if (ca + cb) atomicAdd(const_cast<uint32_t *>(s_cnt), ca + cb);
+    }
+    named_bar_sync(bar, R);
+    const uint32_t total = *s_cnt;
+    const uint32_t m_out = total < m ? total : m;
+    named_bar_sync(bar, R);
+    if (t == 0) { *s_cnt = 0; *s_pool_n = m_out; }
+    if (m_out == 0) {
+        for (uint32_t i = t; i < m; i += R) { rlr_cand r; r.key = 0; r.emb = 0.0f; r.lex = 0.0f; out[i] = r; }
+        if (t == 0) *out_n = 0;
+        named_bar_sync(bar, R);
+        return;
+    }
+    if (tr != nullptr && t == 0) tr[1] = globaltimer_ns();
+    bitonic_desc(keys, embs, 256u, t, bar);                       // register sort: faster than ranking 2 x 148 heads
+    if (tr != nullptr && t == 0) tr[2] = globaltimer_ns();
+    const uint64_t T = keys[m_out - 1];                           // 0: fewer than m_out non-empty lists => keep everything
+    constexpr int kPer = (kLatFusePool * kLatFusePool + R - 1) / R;            // records per thread, all in flight at once
+    rlr_cand rec[kPer];
+    const uint32_t n_scan = m_out * m;
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+        const uint32_t idx = t + static_cast<uint32_t>(u) * R;
+        const uint32_t li = idx < n_scan ? idx / m : 0u;
+        const uint32_t p = idx - li * m;
+        const uint32_t j = __float_as_uint(embs[li]);             // < 256
+        const bool valid = idx < n_scan && keys[li] != 0ull && p < s_counts[j];
+        const rlr_cand *src = lists + (valid ? static_cast<size_t>(j) * m + p : 0u);
+        rec[u] = ld_cand(src);                                    // always a valid address; masked below
+        if (!valid) rec[u].key = 0ull;
+    }
+    named_bar_sync(bar, R);                                       // the heads are read before keys[] is overwritten
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+        if (rec[u].key != 0ull && rec[u].key >= T) {
+            const uint32_t slot = atomicAdd(const_cast<uint32_t *>(s_cnt), 1u);
+            keys[slot] = rec[u].key; embs[slot] = rec[u].emb;     // <= m * m <= kTopBuf survivors
+        }
+    }
+    named_bar_sync(bar, R);
+    const uint32_t n = *s_cnt;                                    // >= m_out
+    if (tr != nullptr && t == 0) tr[3] = globaltimer_ns();
+    if (n <= static_cast<uint32_t>(R)) {
+        if (t < n) {
+            const uint64_t k = keys[t];
+            const uint32_t r = rank_desc(keys, n, k);
+            if (r < m_out) {
+                rlr_cand c;
+                c.key = k; c.emb = embs[t];
+                c.lex = n_lex ? lex_lookup(lex_rows, lex_norm, n_lex, key_row(k) - row_base) : 0.0f;
+                pool_s[r] = c;
+                out[r] = c;
+            }
+        }
+    } else {
+        const uint32_t n2 = next_pow2(n);
+        for (uint32_t i = n + t; i < n2; i += R) keys[i] = 0;
+        named_bar_sync(bar, R);
+        bitonic_desc(keys, embs, n2, t, bar);
+        for (uint32_t i = t; i < m_out; i += R) {
+            rlr_cand c;
+            c.key = keys[i]; c.emb = embs[i];
+            c.lex = n_lex ? lex_lookup(lex_rows, lex_norm, n_lex, key_row(c.key) - row_base) : 0.0f;
+            pool_s[i] = c;
+            out[i] = c;
+        }
+    }
+    for (uint32_t i = m_out + t; i < m; i += R) { rlr_cand c; c.key = 0; c.emb = 0.0f; c.lex = 0.0f; out[i] = c; }
+    if (t == 0) *out_n = m_out;
+    if (tr != nullptr && t == 0) tr[4] = globaltimer_ns();
+    named_bar_sync(bar, R);                                       // pool_s / s_pool_n are visible to the CTA
+}
+
+// Fused MMR tail: where pool row r starts in the staging area.  Rows are skewed by 16-byte bank groups so that the
+// LDS.128 of eight consecutive EVEN rows (and of eight consecutive ODD rows) -- what a wavefront of pairwise_small
+// touches -- fall on eight different bank groups: even row 2b -> group b, odd row 2b+1 -> group b+4 (mod 8).
+__device__ __forceinline__ uint32_t lat_row_off(uint32_t r, uint32_t row_stride)
+{
+    return r * row_stride + ((((r >> 1) + 4u * (r & 1u)) & 7u) << 4);
+}
+
+// All pairwise dot products of the P staged pool rows (dot_product, :1776-1779: strict index order, separate multiply
+// and add roundings) into the triangle tri[j(j-1)/2 + i], i < j.  One thread owns the pairs (i0, j), (i0+1, j): two
+// independent accumulation chains keep the FADD pipe busy (the dependent chain, 4 cycles per add, is the bound) for
+// three instead of four row loads per 16-byte step.  Measured: an LDS.128 costs four shared-memory cycles per WARP
+// whatever its active lanes, and this loop is bound by them -- so tiles are packed into as few warps as possible
+// (P = 15: 56 tiles in two warps, 6 LDS.128 per step; one pair per thread needed four warps and 8).
+__device__ __forceinline__ void pairwise_small(const uint8_t *rows_s, uint32_t row_stride, uint32_t vpr, uint32_t P,
+                                            float *tri, uint32_t t)
+{
+    if (P < 2u) return;
+    uint32_t n_tiles2 = 0;
+    for (uint32_t j = 1; j < P; ++j) n_tiles2 += (j + 1u) / 2u;   // ceil(j / 2) tiles in column j
+    for (uint32_t tile = t; tile < n_tiles2; tile += R) {         // packed: as few warps as possible (see above)
+        uint32_t j = 1, c = 0;
+        while (c + (j + 1u) / 2u <= tile) { c += (j + 1u) / 2u; ++j; }
+        const uint32_t i0 = 2u * (tile - c), i1 = i0 + 1u;        // i0 < j always; i1 < j unless j is odd and this is its last tile
+        const bool has_i1 = i1 < j;
+        const uint8_t *a0 = rows_s + lat_row_off(i0, row_stride);
+        const uint8_t *a1 = rows_s + lat_row_off(has_i1 ? i1 : i0, row_stride);
+        const uint8_t *b0 = rows_s + lat_row_off(j, row_stride);
+        float c0 = 0.0f, c1 = 0.0f;
+#pragma unroll 8
+        for (uint32_t v = 0; v < vpr; ++v) {
+            const float4 x0 = *reinterpret_cast<const float4 *>(a0 + v * 16u);
+            const float4 x1 = *reinterpret_cast<const float4 *>(a1 + v * 16u);
+            const float4 y = *reinterpret_cast<const float4 *>(b0 + v * 16u);
+            c0 = add_rn(c0, mul_rn(x0.x, y.x)); c1 = add_rn(c1, mul_rn(x1.x, y.x));
+            c0 = add_rn(c0, mul_rn(x0.y, y.y)); c1 = add_rn(c1, mul_rn(x1.y, y.y));
+            c0 = add_rn(c0, mul_rn(x0.z, y.z)); c1 = add_rn(c1, mul_rn(x1.z, y.z));
+            c0 = add_rn(c0, mul_rn(x0.w, y.w)); c1 = add_rn(c1, mul_rn(x1.w, y.w));
+        }
+        const uint32_t row = j * (j - 1u) / 2u;
+        tri[row + i0] = c0;
+        if (has_i1) tri[row + i1] = c1;
+    }
+}
+
 constexpr int kTopR = 8;   // a CTA publishes its r-th best score, r = ceil(m / grid) <= kTopR
 
 // warp 0: fold the keys appended since the last call (keys[from, to)) into the CTA's sorted
@@ -386,12 +538,19 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         }
     }
 
-    if (tid == 0) {
-        for (int s = 0; s < n_stages; ++s) {
-            mbar_init(full_bar + s * 8, 1);
-            mbar_init(empty_bar + s * 8, kConsWarps);          // every consumer warp of every group arrives
+    if (g_trace != nullptr && tid == 0) g_trace[4 * gridDim.x + 16 + blockIdx.x] = globaltimer_ns();   // kernel entry
+    // The producer warp initialises the pipeline barriers itself, ARRIVES at the prologue barrier and starts
+    // issuing TMA loads at once: the first tile is in flight while the consumers still stage the query.
+    if (warp == kConsWarps) {
+        if (lane == 0) {
+            for (int s = 0; s < n_stages; ++s) {
+                mbar_init(full_bar + s * 8, 1);
+                mbar_init(empty_bar + s * 8, kConsWarps);      // every consumer warp of every group arrives
+            }
+            fence_mbar_init();
         }
-        fence_mbar_init();
+        __syncwarp();
+        named_bar_arrive(14, kThreads);
     }
     if (warp < kConsWarps) {
         const uint32_t tg = tid - grp * R;
@@ -403,17 +562,21 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             *s_done = 0;
             *s_ntop = 0;
         }
-        if constexpr (kLat) { for (uint32_t i = tg; i < q_floats; i += R) q_s[i] = lp.q[i]; }
+        if constexpr (kLat) {       // 16 bytes per constant-bank access: the index differs per lane, so accesses serialise
+            const float4 *pq = reinterpret_cast<const float4 *>(lp.q);
+            for (uint32_t i = tg; i < q_floats / 4u; i += R) reinterpret_cast<float4 *>(q_s)[i] = pq[i];
+        }
         else { const float *gq = io.g[grp].query; for (uint32_t i = tg; i < q_floats; i += R) q_s[i] = gq[i]; }
     }
-    __syncthreads();
+    if (warp != kConsWarps) named_bar_sync(14, kThreads);         // consumers + threshold warp wait; the producer only arrived
     if (g_trace != nullptr && tid == 0) g_trace[blockIdx.x] = globaltimer_ns();
 
     if (warp == kConsWarps) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
             tma_prefetch_desc(&tmap);
-            const uint64_t pol = policy_evict_first();
+            uint64_t pol = policy_evict_first();                  // a streaming pass: do not displace what others keep in L2
+            if constexpr (kLat) { if (lp.keep_l2) pol = policy_evict_last(); }   // a store that fits L2 stays there between queries
             uint32_t stage = 0, phase = 0;
             // Tiles are handed out dynamically (first one static, then a global counter): SMs
             // do not get equal shares of HBM bandwidth, and with a static split the slow ones
@@ -613,18 +776,33 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     }
     named_bar_sync(bar, R);
     const uint32_t cnt2 = *s_count;
-    const uint32_t n2 = next_pow2(cnt2);
-    for (uint32_t i = cnt2 + t; i < n2; i += R) keys2[i] = 0;
-    named_bar_sync(bar, R);
-    bitonic_desc(keys2, embs2, n2, t, bar);
     const uint32_t keep = cnt2 < m ? cnt2 : m;
     rlr_cand *out = g_lists + static_cast<size_t>(blockIdx.x) * m;
-    for (uint32_t i = t; i < keep; i += R) {       // records beyond `keep` are never read
-        rlr_cand c;
-        c.key = keys2[i];
-        c.emb = embs2[i];
-        c.lex = n_lex ? lex_lookup(lex_rows, lex_norm, n_lex, key_row(c.key) - row_base) : 0.0f;
-        out[i] = c;
+    if (cnt2 <= static_cast<uint32_t>(R)) {
+        // one entry per thread (small stores: a single short tile): its rank IS its place in the list, no sort
+        if (t < cnt2) {
+            const uint64_t k = keys2[t];
+            const uint32_t r = rank_desc(keys2, cnt2, k);
+            if (r < keep) {
+                rlr_cand c;
+                c.key = k;
+                c.emb = embs2[t];
+                c.lex = n_lex ? lex_lookup(lex_rows, lex_norm, n_lex, key_row(k) - row_base) : 0.0f;
+                out[r] = c;
+            }
+        }
+    } else {
+        const uint32_t n2 = next_pow2(cnt2);
+        for (uint32_t i = cnt2 + t; i < n2; i += R) keys2[i] = 0;
+        named_bar_sync(bar, R);
+        bitonic_desc(keys2, embs2, n2, t, bar);
+        for (uint32_t i = t; i < keep; i += R) {       // records beyond `keep` are never read
+            rlr_cand c;
+            c.key = keys2[i];
+            c.emb = embs2[i];
+            c.lex = n_lex ? lex_lookup(lex_rows, lex_norm, n_lex, key_row(c.key) - row_base) : 0.0f;
+            out[i] = c;
+        }
     }
     if (t == 0) g_counts[blockIdx.x] = keep;
     if (g_trace != nullptr && tid == 0) {
@@ -670,8 +848,19 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         named_bar_sync(bar, R);
         if (s_tile[0] != 0) return;
     }
-    final_merge(keys, embs, reinterpret_cast<uint32_t *>(scratch + kTopBuf * 12), s_count, s_flag, g_lists,
-                g_counts, gridDim.x, m, row_base, lex_rows, lex_norm, n_lex, g_out, g_out_n, t, tr, bar);
+    bool merged = false;
+    if constexpr (kLat) {
+        if (lp.mode == 2u && m <= kLatFusePool && gridDim.x <= 256u) {
+            // the pool also lands in shared memory (the idle ring's first 512 bytes) for the fused MMR tail below
+            merge_small(keys, embs, reinterpret_cast<uint32_t *>(scratch + kTopBuf * 12), s_count, g_lists, g_counts,
+                        gridDim.x, m, row_base, lex_rows, lex_norm, n_lex, g_out, g_out_n,
+                        reinterpret_cast<rlr_cand *>(smem + L.stages_off), s_flag, t, tr, bar);
+            merged = true;
+        }
+    }
+    if (!merged)
+        final_merge(keys, embs, reinterpret_cast<uint32_t *>(scratch + kTopBuf * 12), s_count, s_flag, g_lists,
+                    g_counts, gridDim.x, m, row_base, lex_rows, lex_norm, n_lex, g_out, g_out_n, t, tr, bar);
     if (post.flag != nullptr) {
         __threadfence_system();               // every writer: the records are visible system-wide ...
         named_bar_sync(bar, R);
@@ -680,56 +869,44 @@ scan_topm_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     if constexpr (kLat) {
         if (lp.mode == 2u) {
             // ---- fused MMR tail (pool <= kLatFusePool): mmr_diversify (:767-839) by this CTA, no further launch ----
-            // final_merge left the pool in g_out (device memory).  Stage the records and their rows in the idle TMA
+            // merge_small left the pool in shared memory (and in g_out).  Stage the pool's rows in the idle TMA
             // ring, compute every pairwise dot with the reference's sequential arithmetic, run the greedy loop, and
             // let thread 0 write the selection straight into the host's mapped result block.
-            named_bar_sync(bar, R);                                         // g_out / g_out_n written by this CTA
-            const uint32_t P = *reinterpret_cast<volatile uint32_t *>(g_out_n);
             uint8_t *ring = smem + L.stages_off;
             rlr_cand *pool_s = reinterpret_cast<rlr_cand *>(ring);                                  // 32 x 16 B
             float *tri_s = reinterpret_cast<float *>(ring + 512);                                   // 496 floats -> 2 KB
             uint64_t (*s_best)[4] = reinterpret_cast<uint64_t (*)[4]>(ring + 512 + 2048);           // 64 B
             uint32_t (*s_besti)[4] = reinterpret_cast<uint32_t (*)[4]>(ring + 512 + 2048 + 64);     // 32 B
             uint8_t *rows_s = ring + 4096;
-            const uint32_t row_stride = lp.pitch * 4u + 16u;              // +16 B: LDS.128 of different rows on different bank groups
-            if (t < P) pool_s[t] = g_out[t];
-            named_bar_sync(bar, R);
+            const uint32_t row_stride = lp.pitch * 4u + 128u;             // + room for the per-row bank-group skew (lat_row_off)
+            uint32_t P;
+            if (merged) P = *s_flag;                                      // merge_small left the pool in pool_s already
+            else {
+                named_bar_sync(bar, R);                                   // g_out / g_out_n written by this CTA
+                P = *reinterpret_cast<volatile uint32_t *>(g_out_n);
+                if (t < P) pool_s[t] = g_out[t];
+                named_bar_sync(bar, R);
+            }
             const uint32_t vpr = lp.pitch / 4u;                           // 16-byte vectors per row
             // cp.async (LDGSTS, 16 B each, L2 only): every load of the pool's rows is in flight at once -- one L2 round
             // trip instead of one per loop iteration (6 us -> ~1 us for 15 x 3 KB)
             for (uint32_t idx = t; idx < P * vpr; idx += R) {
                 const uint32_t r = idx / vpr, v = idx - r * vpr;
                 const float *src = lp.g_rows + static_cast<size_t>(key_row(pool_s[r].key) - row_base) * lp.pitch + v * 4u;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(rows_s + r * row_stride + v * 16u)), "l"(src) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(rows_s + lat_row_off(r, row_stride) + v * 16u)), "l"(src) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             named_bar_sync(bar, R);
             if (tr != nullptr && t == 0) tr[5] = globaltimer_ns();
-            const uint32_t n_pairs = P * (P - 1u) / 2u;
-            for (uint32_t pr = t; pr < n_pairs; pr += R) {
-                uint32_t j = 1;
-                while (j * (j + 1u) / 2u <= pr) ++j;                      // pair pr = (i, j), i < j, triangle index j(j-1)/2 + i
-                const uint32_t i = pr - j * (j - 1u) / 2u;
-                const uint8_t *a_row = rows_s + i * row_stride, *b_row = rows_s + j * row_stride;
-                float acc = 0.0f;
-#pragma unroll 4
-                for (uint32_t v = 0; v < vpr; ++v) {                      // dot_product (:1776-1779), strict order, no FMA
-                    const float4 a = *reinterpret_cast<const float4 *>(a_row + v * 16u);
-                    const float4 b = *reinterpret_cast<const float4 *>(b_row + v * 16u);
-                    acc = add_rn(acc, mul_rn(a.x, b.x));
-                    acc = add_rn(acc, mul_rn(a.y, b.y));
-                    acc = add_rn(acc, mul_rn(a.z, b.z));
-                    acc = add_rn(acc, mul_rn(a.w, b.w));
-                }
-                tri_s[pr] = acc;
-            }
+            pairwise_small(rows_s, row_stride, vpr, P, tri_s, t);
             named_bar_sync(bar, R);
             if (tr != nullptr && t == 0) tr[6] = globaltimer_ns();
             if (P == 0) { if (t == 0) *lp.result_n = 0; }
             else greedy_loop<1>(tri_s, pool_s, nullptr, P, lp.top_k, lp.lambda, lp.d_sel_pos, lp.result_n, lp.result, t, s_best, s_besti);
-            // thread 0 wrote the records and the count: its fence orders them before the flag
-            if (t == 0) { __threadfence_system(); st_release_sys_u64(lp.flag, lp.seq); }
+            if (tr != nullptr && t == 0) tr[10] = globaltimer_ns();
+            // thread 0 alone wrote the records and the count: its release store orders them before the flag
+            if (t == 0) st_release_sys_u64(lp.flag, lp.seq);
         } else if (lp.mode == 1u) {
             // the merged top-m went straight into the host's mapped block (g_out / g_out_n point there)
             __threadfence_system();
@@ -835,6 +1012,10 @@ cudaError_t scan_launch(const ScanArgs &a, cudaStream_t stream)
     static const bool no_global_tau = getenv("RLR_DEBUG_NOGLOBALTAU") != nullptr;
     uint32_t r_pub = (a.m + a.grid - 1) / a.grid;                    // r-th best published per CTA (0 = off)
     if (r_pub > static_cast<uint32_t>(kTopR) || a.d_pub == nullptr || no_global_tau) r_pub = 0;
+    {   // one tile per CTA (latency path): a global bound cannot prune anything, its L2 round trip is pure cost
+        const uint32_t rows_tile = a.rows_per_tile ? a.rows_per_tile : static_cast<uint32_t>(R);
+        if (a.lat != nullptr && (a.n_rows + rows_tile - 1) / rows_tile <= static_cast<uint32_t>(a.grid)) r_pub = 0;
+    }
     const uint32_t n_chunks = a.pitch / (a.half ? 64u : 32u);
     const uint32_t rpt = a.rows_per_tile ? a.rows_per_tile : static_cast<uint32_t>(R);
     const NoLat nolat = {0};
