@@ -348,7 +348,7 @@ int rlr_batch_merge_async(rlr_store *s, const void *d_lists, uint32_t n_lists, u
  * Scores are bit-identical to the reference's f32 formula evaluated in that term order (idf's ln() is the C library's
  * logf, computed on the host per query term).  Mutators need exclusivity like the store's; scoring is re-entrant.
  * An index is bound to its store: use it only while the store lives (destroying it afterwards is allowed).
- * Single-GPU stores; a cluster takes host-computed pairs (rlr_cluster_search_*). */
+ * rlr_bm25 serves one single-GPU store; rlr_cluster_bm25 (below) is the same index over a cluster. */
 typedef struct rlr_bm25 rlr_bm25;
 int rlr_bm25_create(rlr_store *s, rlr_bm25 **out);
 int rlr_bm25_destroy(rlr_bm25 *ix);
@@ -453,6 +453,29 @@ int rlr_cluster_embedding_candidates(rlr_cluster *c, const float *query, uint32_
 int rlr_cluster_last_scan_ms(float *out_ms, uint32_t cap, uint32_t *out_n);
 /* kernels launched by this cluster's searches since creation (bench `gpu_launches`) */
 int rlr_cluster_launch_count(const rlr_cluster *c, uint64_t *out);
+
+/* BM25 over the cluster (LexicalIndex, src/rag_engine.rs:2083-2237, for a corpus sharded over several GPUs): one
+ * device index per shard.  A query is scored on EVERY shard's GPU at once with the statistics of the whole corpus
+ * (N, average length, df -- so a document's score does not depend on the sharding), each shard ranks its own `limit`
+ * best on the device, and the host merges those short lists (<= 16 x limit records) into the global `limit` best:
+ * exactly what one index over all rows returns.  rlr_cluster_search_text_* then run the cluster search with those
+ * pairs -- the results equal rlr_search_text_* on one store holding the same rows, bit for bit.  `row` arguments are
+ * global rows.  With one shard everything is forwarded to the single-GPU entry points. */
+typedef struct rlr_cluster_bm25 rlr_cluster_bm25;
+int rlr_cluster_bm25_create(rlr_cluster *c, rlr_cluster_bm25 **out);
+int rlr_cluster_bm25_destroy(rlr_cluster_bm25 *ix);
+int rlr_cluster_bm25_set_doc(rlr_cluster_bm25 *ix, uint32_t row, const uint32_t *term_ids, const uint32_t *term_freqs, uint32_t n_terms);
+int rlr_cluster_bm25_remove_doc(rlr_cluster_bm25 *ix, uint32_t row);
+int rlr_cluster_bm25_stats(const rlr_cluster_bm25 *ix, uint64_t *total_docs, uint64_t *total_length, uint64_t *n_terms);
+int rlr_cluster_bm25_score(rlr_cluster_bm25 *ix, const uint32_t *query_terms, uint32_t n_terms, uint32_t limit,
+                           uint32_t *out_rows, float *out_scores, uint32_t cap, uint32_t *out_n);
+int rlr_cluster_search_text_topm(rlr_cluster *c, rlr_cluster_bm25 *ix, const float *query, uint32_t dim, uint32_t flags,
+                                 const rlr_resolved_weights *w, const uint32_t *query_terms, uint32_t n_terms, uint32_t m,
+                                 uint32_t *out_rows, float *out_combined, float *out_emb, float *out_lex, uint32_t *out_n);
+int rlr_cluster_search_text_mmr(rlr_cluster *c, rlr_cluster_bm25 *ix, const float *query, uint32_t dim, uint32_t flags,
+                                uint32_t top_k, float diversity_factor, const rlr_resolved_weights *w,
+                                const uint32_t *query_terms, uint32_t n_terms,
+                                uint32_t *out_rows, float *out_score, float *out_emb, float *out_lex, uint32_t *out_n);
 
 /* ---- device-level building blocks (multi-GPU composition, bench `value`) -------
  *

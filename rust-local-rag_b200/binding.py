@@ -120,6 +120,14 @@ PROTOTYPES = {
     "rlr_bm25_score": (_int, [_vp, _vp, _u32, _u32, _vp, _vp, _u32, _pu32]),
     "rlr_search_text_topm": (_int, [_vp, _vp, _vp, _u32, _u32, C.POINTER(ResolvedWeightsC), _vp, _u32, _u32, _vp, _vp, _vp, _vp, _pu32]),
     "rlr_search_text_mmr": (_int, [_vp, _vp, _vp, _u32, _u32, _u32, _f32, C.POINTER(ResolvedWeightsC), _vp, _u32, _vp, _vp, _vp, _vp, _pu32]),
+    "rlr_cluster_bm25_create": (_int, [_vp, C.POINTER(_vp)]),
+    "rlr_cluster_bm25_destroy": (_int, [_vp]),
+    "rlr_cluster_bm25_set_doc": (_int, [_vp, _u32, _vp, _vp, _u32]),
+    "rlr_cluster_bm25_remove_doc": (_int, [_vp, _u32]),
+    "rlr_cluster_bm25_stats": (_int, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
+    "rlr_cluster_bm25_score": (_int, [_vp, _vp, _u32, _u32, _vp, _vp, _u32, _pu32]),
+    "rlr_cluster_search_text_topm": (_int, [_vp, _vp, _vp, _u32, _u32, C.POINTER(ResolvedWeightsC), _vp, _u32, _u32, _vp, _vp, _vp, _vp, _pu32]),
+    "rlr_cluster_search_text_mmr": (_int, [_vp, _vp, _vp, _u32, _u32, _u32, _f32, C.POINTER(ResolvedWeightsC), _vp, _u32, _vp, _vp, _vp, _vp, _pu32]),
     "rlr_last_timings": (_int, [C.POINTER(TimingsC)]),
     "rlr_cluster_create": (_int, [_vp, _u32, _u32, _u64, _vp, _u64, _u32, _vp, C.POINTER(_vp)]),
     "rlr_cluster_destroy": (_int, [_vp]),

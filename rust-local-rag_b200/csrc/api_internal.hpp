@@ -150,8 +150,22 @@ struct CtxLease {
 struct rlr_bm25;
 int rlr_api_bm25_ws_acquire(rlr_bm25 *ix, void **out);
 void rlr_api_bm25_ws_release(rlr_bm25 *ix, void *ws);
+// corpus statistics of a sharded index: every shard scores with the GLOBAL N, avgdl and df (df[j]: query_terms[j])
+struct rlr_api_bm25_global { uint64_t total_docs, total_length; const uint32_t *df; };
 int rlr_api_bm25_enqueue(rlr_bm25 *ix, void *ws, const uint32_t *query_terms, uint32_t n_terms, uint32_t limit,
                          uint32_t *d_lex_rows, float *d_lex_norm, uint32_t lex_pad, uint32_t *d_desc_rows, float *d_desc_scores,
-                         uint32_t *d_n, cudaStream_t st, bool *active);
+                         uint32_t *d_n, cudaStream_t st, bool *active, const rlr_api_bm25_global *gs = nullptr);
 uint32_t rlr_api_bm25_launches();
 rlr_store *rlr_api_bm25_store(rlr_bm25 *ix);
+
+// cluster.cu <-> bm25.cu: a BM25 index over a sharded store (rlr_cluster_bm25_*)
+struct rlr_cluster;
+struct rlr_cluster_bm25;
+uint32_t rlr_api_cluster_n(const rlr_cluster *cl);
+rlr_store *rlr_api_cluster_shard(const rlr_cluster *cl, uint32_t i);
+rlr_cluster *rlr_api_cluster_bm25_cluster(rlr_cluster_bm25 *ix);
+rlr_bm25 *rlr_api_cluster_bm25_part(rlr_cluster_bm25 *ix, uint32_t i);
+// LexicalIndex::score(query, limit) over every shard (device scoring with global statistics, host merge of the
+// per-shard ranked lists): global rows + raw scores, score desc, ties to the lower row
+int rlr_api_cluster_bm25_score(rlr_cluster_bm25 *ix, const uint32_t *query_terms, uint32_t n_terms, uint32_t limit,
+                               std::vector<uint32_t> &rows, std::vector<float> &scores);

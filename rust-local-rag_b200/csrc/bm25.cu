@@ -380,7 +380,7 @@ int bm25_sync(rlr_bm25 *ix)
 // *active = false when the query cannot match anything (no terms / empty index): nothing is enqueued.
 int rlr_api_bm25_enqueue(rlr_bm25 *ix, void *ws_opaque, const uint32_t *query_terms, uint32_t n_terms, uint32_t limit,
                          uint32_t *d_lex_rows, float *d_lex_norm, uint32_t lex_pad, uint32_t *d_desc_rows, float *d_desc_scores,
-                         uint32_t *d_n, cudaStream_t st, bool *active)
+                         uint32_t *d_n, cudaStream_t st, bool *active, const rlr_api_bm25_global *gs)
 {
     Bm25Ws *w = static_cast<Bm25Ws *>(ws_opaque);
     *active = false;
@@ -389,20 +389,23 @@ int rlr_api_bm25_enqueue(rlr_bm25 *ix, void *ws_opaque, const uint32_t *query_te
     if (int rc = bm25_sync(ix)) return rc;
     rlr_store *s = ix->s;
     const uint32_t n = static_cast<uint32_t>(s->n_rows);
-    if (ix->total_docs == 0 || n == 0) return RLR_OK;                                  // :2170-2172
+    if (ix->total_docs == 0 || n == 0) return RLR_OK;                                  // :2170-2172 (a shard without documents has no hits)
+    // one shard of a cluster scores with the statistics of the WHOLE corpus
+    const uint64_t total_docs = gs ? gs->total_docs : ix->total_docs, total_length = gs ? gs->total_length : ix->total_length;
     rlr::Bm25Query q;
     memset(&q, 0, sizeof q);
     // avg_doc_len = total_length as f32 / total_docs as f32 (:2188)
-    q.avg_doc_len = static_cast<float>(ix->total_length) / static_cast<float>(ix->total_docs);
+    q.avg_doc_len = static_cast<float>(total_length) / static_cast<float>(total_docs);
     for (uint32_t j = 0; j < n_terms; ++j) {
         const uint32_t t = query_terms[j];
         bool dup = false;
         for (uint32_t i = 0; i < q.n_terms; ++i) dup |= q.term[i] == t;                // HashSet: unique terms
-        if (dup || t >= ix->df.size() || ix->df[t] == 0) continue;                     // `if let Some(postings)`
+        const uint32_t df_t = gs ? gs->df[j] : (t < ix->df.size() ? ix->df[t] : 0u);
+        if (dup || df_t == 0) continue;                                                // `if let Some(postings)`
         if (q.n_terms == rlr::kBm25MaxTerms) return fail(RLR_ERR_UNSUPPORTED, "more than %u unique query terms", rlr::kBm25MaxTerms);
         // idf = ((N - df + 0.5) / (df + 0.5)).ln().max(0.0), f32 throughout, the C library's logf (:2197-2200)
-        const float df = static_cast<float>(ix->df[t]);
-        volatile float num = static_cast<float>(ix->total_docs) - df;
+        const float df = static_cast<float>(df_t);
+        volatile float num = static_cast<float>(total_docs) - df;
         num = num + 0.5f;
         volatile float den = df + 0.5f;
         volatile float ratio = num / den;
@@ -591,3 +594,158 @@ RLR_EXPORT int rlr_bm25_score(rlr_bm25 *ix, const uint32_t *query_terms, uint32_
     return rc;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// the same index over a sharded store (rlr_cluster): one rlr_bm25 per shard, global statistics at query time
+// ---------------------------------------------------------------------------------------------------------------
+struct rlr_cluster_bm25 {
+    rlr_cluster *cl = nullptr;
+    std::vector<rlr_bm25 *> parts;
+};
+
+rlr_cluster *rlr_api_cluster_bm25_cluster(rlr_cluster_bm25 *ix) { return ix->cl; }
+rlr_bm25 *rlr_api_cluster_bm25_part(rlr_cluster_bm25 *ix, uint32_t i) { return ix->parts[i]; }
+
+namespace {
+// the shard that owns global row `row` (shards are contiguous row ranges)
+rlr_bm25 *part_of(rlr_cluster_bm25 *ix, uint32_t row)
+{
+    for (rlr_bm25 *p : ix->parts)
+        if (row >= p->s->row_base && row - p->s->row_base < p->s->n_rows) return p;
+    return nullptr;
+}
+} // namespace
+
+RLR_EXPORT int rlr_cluster_bm25_create(rlr_cluster *cl, rlr_cluster_bm25 **out)
+{
+    if (!cl || !out) return fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    rlr_cluster_bm25 *ix = new rlr_cluster_bm25();
+    ix->cl = cl;
+    for (uint32_t i = 0; i < rlr_api_cluster_n(cl); ++i) {
+        rlr_bm25 *p = nullptr;
+        if (int rc = rlr_bm25_create(rlr_api_cluster_shard(cl, i), &p)) { rlr_cluster_bm25_destroy(ix); return rc; }
+        ix->parts.push_back(p);
+    }
+    *out = ix;
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_cluster_bm25_destroy(rlr_cluster_bm25 *ix)
+{
+    if (!ix) return RLR_OK;
+    for (rlr_bm25 *p : ix->parts) rlr_bm25_destroy(p);
+    delete ix;
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_cluster_bm25_set_doc(rlr_cluster_bm25 *ix, uint32_t row, const uint32_t *term_ids, const uint32_t *term_freqs, uint32_t n_terms)
+{
+    if (!ix) return fail(RLR_ERR_INVALID_ARG, "index is NULL");
+    rlr_bm25 *p = part_of(ix, row);
+    if (!p) return fail(RLR_ERR_INVALID_ARG, "row %u not in the cluster", row);
+    return rlr_bm25_set_doc(p, row, term_ids, term_freqs, n_terms);
+}
+
+RLR_EXPORT int rlr_cluster_bm25_remove_doc(rlr_cluster_bm25 *ix, uint32_t row)
+{
+    if (!ix) return fail(RLR_ERR_INVALID_ARG, "index is NULL");
+    rlr_bm25 *p = part_of(ix, row);
+    if (!p) return fail(RLR_ERR_INVALID_ARG, "row %u not in the cluster", row);
+    return rlr_bm25_remove_doc(p, row);
+}
+
+RLR_EXPORT int rlr_cluster_bm25_stats(const rlr_cluster_bm25 *ix, uint64_t *total_docs, uint64_t *total_length, uint64_t *n_terms)
+{
+    if (!ix) return fail(RLR_ERR_INVALID_ARG, "index is NULL");
+    uint64_t docs = 0, len = 0, live = 0;
+    size_t vocab = 0;
+    for (const rlr_bm25 *p : ix->parts) { docs += p->total_docs; len += p->total_length; vocab = std::max(vocab, p->df.size()); }
+    if (n_terms) {
+        for (size_t t = 0; t < vocab; ++t) {
+            bool any = false;
+            for (const rlr_bm25 *p : ix->parts) any |= t < p->df.size() && p->df[t] != 0;
+            live += any ? 1 : 0;
+        }
+        *n_terms = live;
+    }
+    if (total_docs) *total_docs = docs;
+    if (total_length) *total_length = len;
+    return RLR_OK;
+}
+
+int rlr_api_cluster_bm25_score(rlr_cluster_bm25 *ix, const uint32_t *query_terms, uint32_t n_terms, uint32_t limit,
+                               std::vector<uint32_t> &rows, std::vector<float> &scores)
+{
+    rows.clear(); scores.clear();
+    if (limit == 0 || limit > rlr::kBm25MaxLimit) return fail(RLR_ERR_UNSUPPORTED, "limit %u not in 1..%u", limit, rlr::kBm25MaxLimit);
+    if (n_terms && !query_terms) return fail(RLR_ERR_INVALID_ARG, "query_terms is NULL");
+    // the statistics of the whole corpus: N, total length, df of every query term (:2188, :2197)
+    rlr_api_bm25_global gs = {0, 0, nullptr};
+    std::vector<uint32_t> df(n_terms, 0);
+    for (const rlr_bm25 *p : ix->parts) {
+        gs.total_docs += p->total_docs; gs.total_length += p->total_length;
+        for (uint32_t j = 0; j < n_terms; ++j) df[j] += query_terms[j] < p->df.size() ? p->df[query_terms[j]] : 0u;
+    }
+    gs.df = df.data();
+    if (gs.total_docs == 0 || n_terms == 0) return RLR_OK;
+    const size_t np = ix->parts.size();
+    std::vector<Bm25Ws *> ws(np, nullptr);
+    std::vector<char> active(np, 0);
+    int rc = RLR_OK;
+    // every shard scores its documents and ranks its own `limit` best (all enqueued before anything is awaited) ...
+    for (size_t i = 0; i < np && rc == RLR_OK; ++i) {
+        rlr_bm25 *p = ix->parts[i];
+        rc = ensure_device(p->s->device);
+        void *wv = nullptr;
+        if (rc == RLR_OK) rc = rlr_api_bm25_ws_acquire(p, &wv);
+        if (rc != RLR_OK) break;
+        Bm25Ws *w = ws[i] = static_cast<Bm25Ws *>(wv);
+        bool act = false;
+        rc = rlr_api_bm25_enqueue(p, w, query_terms, n_terms, limit, nullptr, nullptr, 0, w->d_desc_rows, w->d_desc_scores, w->d_n,
+                                  w->stream, &act, &gs);
+        if (rc == RLR_OK && act) {
+            cudaError_t e = cudaMemcpyAsync(w->h_n, w->d_n, 4, cudaMemcpyDeviceToHost, w->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(w->h_rows, w->d_desc_rows, limit * 4, cudaMemcpyDeviceToHost, w->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(w->h_scores, w->d_desc_scores, limit * 4, cudaMemcpyDeviceToHost, w->stream);
+            if (e != cudaSuccess) { cudaGetLastError(); rc = fail(RLR_ERR_CUDA, "bm25 score failed: %s", cudaGetErrorString(e)); }
+            active[i] = 1;
+        }
+    }
+    // ... then the global `limit` best are the best of the shards' lists
+    struct Hit { float score; uint32_t row; };
+    std::vector<Hit> hits;
+    for (size_t i = 0; i < np; ++i) {
+        if (!ws[i]) continue;
+        if (active[i]) {
+            cudaSetDevice(ix->parts[i]->s->device);
+            const cudaError_t e = cudaStreamSynchronize(ws[i]->stream);
+            if (e != cudaSuccess) { cudaGetLastError(); if (rc == RLR_OK) rc = fail(RLR_ERR_CUDA, "bm25 score failed: %s", cudaGetErrorString(e)); }
+            else if (rc == RLR_OK) {
+                const uint32_t n = std::min(ws[i]->h_n[0], limit);
+                for (uint32_t k = 0; k < n; ++k) hits.push_back({ws[i]->h_scores[k], ws[i]->h_rows[k]});
+            }
+        }
+        rlr_api_bm25_ws_release(ix->parts[i], ws[i]);
+    }
+    if (rc != RLR_OK) return rc;
+    const auto before = [](const Hit &a, const Hit &b) { return a.score > b.score || (a.score == b.score && a.row < b.row); };
+    const size_t keep = std::min<size_t>(limit, hits.size());
+    std::partial_sort(hits.begin(), hits.begin() + keep, hits.end(), before);
+    rows.resize(keep); scores.resize(keep);
+    for (size_t k = 0; k < keep; ++k) { rows[k] = hits[k].row; scores[k] = hits[k].score; }
+    return RLR_OK;
+}
+
+RLR_EXPORT int rlr_cluster_bm25_score(rlr_cluster_bm25 *ix, const uint32_t *query_terms, uint32_t n_terms, uint32_t limit,
+                                      uint32_t *out_rows, float *out_scores, uint32_t cap, uint32_t *out_n)
+{
+    if (!ix || !out_n) return fail(RLR_ERR_INVALID_ARG, "NULL argument");
+    *out_n = 0;
+    std::vector<uint32_t> rows;
+    std::vector<float> scores;
+    if (int rc = rlr_api_cluster_bm25_score(ix, query_terms, n_terms, limit, rows, scores)) return rc;
+    if (rows.size() > cap) return fail(RLR_ERR_INVALID_ARG, "output capacity %u < %zu results", cap, rows.size());
+    if (!rows.empty() && (!out_rows || !out_scores)) return fail(RLR_ERR_INVALID_ARG, "output buffers are NULL");
+    if (!rows.empty()) { memcpy(out_rows, rows.data(), rows.size() * 4); memcpy(out_scores, scores.data(), scores.size() * 4); }
+    *out_n = static_cast<uint32_t>(rows.size());
+    return RLR_OK;
+}

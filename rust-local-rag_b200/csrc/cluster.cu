@@ -715,6 +715,51 @@ RLR_EXPORT int rlr_cluster_search_mmr(rlr_cluster *cl, const float *query, uint3
     return cluster_search(cl, query, dim, flags, pl, w, lex_rows, lex_scores, n_lex, out_rows, out_score, out_emb, out_lex, out_n);
 }
 
+// ---- text queries over the cluster: BM25 scored on every shard's GPU (global statistics), ranked lists merged on the
+// host, then the very same search as with caller-supplied pairs ----
+uint32_t rlr_api_cluster_n(const rlr_cluster *cl) { return cl->n; }
+rlr_store *rlr_api_cluster_shard(const rlr_cluster *cl, uint32_t i) { return cl->shard[i]; }
+
+RLR_EXPORT int rlr_cluster_search_text_topm(rlr_cluster *cl, rlr_cluster_bm25 *ix, const float *query, uint32_t dim, uint32_t flags,
+                                            const rlr_resolved_weights *w, const uint32_t *query_terms, uint32_t n_terms, uint32_t m,
+                                            uint32_t *out_rows, float *out_combined, float *out_emb, float *out_lex, uint32_t *out_n)
+{
+    if (int rc = check_cluster(cl)) return rc;
+    if (!ix || rlr_api_cluster_bm25_cluster(ix) != cl) return fail(RLR_ERR_INVALID_ARG, "the BM25 index is NULL or belongs to another cluster");
+    if (cl->n == 1)        // one shard: the single-GPU path keeps everything on the device
+        return rlr_search_text_topm(cl->shard[0], rlr_api_cluster_bm25_part(ix, 0), query, dim, flags, w, query_terms, n_terms, m,
+                                    out_rows, out_combined, out_emb, out_lex, out_n);
+    if (m == 0 || m > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "m %u not in 1..%d", m, RLR_MAX_M);
+    std::vector<uint32_t> lr;
+    std::vector<float> ls;
+    if (int rc = rlr_api_cluster_bm25_score(ix, query_terms, n_terms, 5u * m, lr, ls)) return rc;      // lexical_index.score(query, top_k * 5), :505
+    return rlr_cluster_search_topm(cl, query, dim, flags, w, lr.data(), ls.data(), static_cast<uint32_t>(lr.size()), m, out_rows,
+                                   out_combined, out_emb, out_lex, out_n);
+}
+
+RLR_EXPORT int rlr_cluster_search_text_mmr(rlr_cluster *cl, rlr_cluster_bm25 *ix, const float *query, uint32_t dim, uint32_t flags,
+                                           uint32_t top_k, float diversity_factor, const rlr_resolved_weights *w,
+                                           const uint32_t *query_terms, uint32_t n_terms, uint32_t *out_rows, float *out_score,
+                                           float *out_emb, float *out_lex, uint32_t *out_n)
+{
+    if (int rc = check_cluster(cl)) return rc;
+    if (!ix || rlr_api_cluster_bm25_cluster(ix) != cl) return fail(RLR_ERR_INVALID_ARG, "the BM25 index is NULL or belongs to another cluster");
+    if (cl->n == 1)
+        return rlr_search_text_mmr(cl->shard[0], rlr_api_cluster_bm25_part(ix, 0), query, dim, flags, top_k, diversity_factor, w,
+                                   query_terms, n_terms, out_rows, out_score, out_emb, out_lex, out_n);
+    float lambda = diversity_factor;                                    // :725 f32::clamp (NaN stays NaN)
+    if (lambda < 0.0f) lambda = 0.0f;
+    if (lambda > 1.0f) lambda = 1.0f;
+    // search(m): m = top_k.max(1) without diversity (:728-730, :490), the candidate pool otherwise (:734)
+    const uint64_t m = lambda == 0.0f ? std::max<uint64_t>(top_k, 1) : std::max<uint64_t>(3ull * top_k, static_cast<uint64_t>(top_k) + 10);
+    if (m > RLR_MAX_M) return fail(RLR_ERR_UNSUPPORTED, "candidate pool %llu exceeds %d (top_k %u)", (unsigned long long)m, RLR_MAX_M, top_k);
+    std::vector<uint32_t> lr;
+    std::vector<float> ls;
+    if (int rc = rlr_api_cluster_bm25_score(ix, query_terms, n_terms, static_cast<uint32_t>(5u * m), lr, ls)) return rc;
+    return rlr_cluster_search_mmr(cl, query, dim, flags, top_k, diversity_factor, w, lr.data(), ls.data(), static_cast<uint32_t>(lr.size()),
+                                  out_rows, out_score, out_emb, out_lex, out_n);
+}
+
 RLR_EXPORT int rlr_cluster_mmr(rlr_cluster *cl, const uint32_t *cand_rows, const float *relevance, uint32_t p, uint32_t top_k,
                                float lambda, uint32_t flags, uint32_t *out_sel_pos, uint32_t *out_n)
 {

@@ -363,7 +363,7 @@ class DeviceStore:
         emb = np.empty(m, np.float32); lex = np.empty(m, np.float32)
         n = C.c_uint32(0)
         wc = B.ResolvedWeightsC(w.embedding, w.lexical, w.reranker, w.initial)
-        B.check(self._lib.rlr_search_text_topm(self._h, bm25, B.ptr(q), q.shape[0], flags, C.byref(wc), B.ptr(t) if len(t) else None,
+        B.check(self._hot("search_text_topm")(self._h, bm25, B.ptr(q), q.shape[0], flags, C.byref(wc), B.ptr(t) if len(t) else None,
                                                len(t), m, B.ptr(rows), B.ptr(comb), B.ptr(emb), B.ptr(lex), C.byref(n)))
         k = n.value
         return rows[:k], comb[:k], emb[:k], lex[:k]
@@ -377,7 +377,7 @@ class DeviceStore:
         emb = np.empty(cap, np.float32); lex = np.empty(cap, np.float32)
         n = C.c_uint32(0)
         wc = B.ResolvedWeightsC(w.embedding, w.lexical, w.reranker, w.initial)
-        B.check(self._lib.rlr_search_text_mmr(self._h, bm25, B.ptr(q), q.shape[0], flags, top_k, diversity, C.byref(wc),
+        B.check(self._hot("search_text_mmr")(self._h, bm25, B.ptr(q), q.shape[0], flags, top_k, diversity, C.byref(wc),
                                               B.ptr(t) if len(t) else None, len(t), B.ptr(rows), B.ptr(score), B.ptr(emb),
                                               B.ptr(lex), C.byref(n)))
         k = n.value
@@ -634,8 +634,13 @@ class DeviceLexicalIndex:
         self._lib = B.load()
         self._store = store
         self._h = C.c_void_p()
-        B.check(self._lib.rlr_bm25_create(store.handle, C.byref(self._h)))
+        # a ClusterStore gets rlr_cluster_bm25_* (one device index per shard, global statistics): same calls, same results
+        self._prefix = store._HOT_PREFIX + "bm25_"
+        B.check(self._fn("create")(store.handle, C.byref(self._h)))
         self.vocab = {}
+
+    def _fn(self, name: str):
+        return getattr(self._lib, self._prefix + name)
 
     @property
     def handle(self):
@@ -647,12 +652,14 @@ class DeviceLexicalIndex:
             counts[t] = counts.get(t, 0) + 1
         ids = np.array([self.vocab.setdefault(t, len(self.vocab)) for t in counts], np.uint32)
         tfs = np.array(list(counts.values()), np.uint32)
-        B.check(self._lib.rlr_bm25_set_doc(self._h, row, B.ptr(ids) if len(ids) else None, B.ptr(tfs) if len(ids) else None, len(ids)))
+        B.check(self._fn("set_doc")(self._h, row, B.ptr(ids) if len(ids) else None, B.ptr(tfs) if len(ids) else None, len(ids)))
 
     def remove_chunk(self, row: int) -> None:
-        B.check(self._lib.rlr_bm25_remove_doc(self._h, row))
+        B.check(self._fn("remove_doc")(self._h, row))
 
     def move(self, from_row: int, to_row: int) -> None:
+        if isinstance(self._store, ClusterStore):
+            raise B.RlrError(B.RLR_ERR_UNSUPPORTED, "a cluster has no row removal to follow")
         B.check(self._lib.rlr_bm25_move_doc(self._h, from_row, to_row))
 
     def query_terms(self, query: str) -> np.ndarray:
@@ -662,19 +669,19 @@ class DeviceLexicalIndex:
 
     def stats(self):
         a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
-        B.check(self._lib.rlr_bm25_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        B.check(self._fn("stats")(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
     def score(self, query: str, limit: int) -> List[Tuple[int, float]]:
         """LexicalIndex::score(query, limit) -> [(row, score)], score desc (ties: lower row)."""
         t = self.query_terms(query)
         rows, sc, n = np.zeros(limit, np.uint32), np.zeros(limit, np.float32), C.c_uint32(0)
-        B.check(self._lib.rlr_bm25_score(self._h, B.ptr(t) if len(t) else None, len(t), limit, B.ptr(rows), B.ptr(sc), limit, C.byref(n)))
+        B.check(self._fn("score")(self._h, B.ptr(t) if len(t) else None, len(t), limit, B.ptr(rows), B.ptr(sc), limit, C.byref(n)))
         return [(int(r), np.float32(x)) for r, x in zip(rows[:n.value], sc[:n.value])]
 
     def close(self) -> None:
         if self._h:
-            self._lib.rlr_bm25_destroy(self._h)
+            self._fn("destroy")(self._h)
             self._h = None
 
     def __del__(self):

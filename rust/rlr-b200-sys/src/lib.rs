@@ -39,6 +39,7 @@ pub const RLR_MAX_MULTI: u32 = 3;
 #[repr(C)] pub struct rlr_mailbox { _p: [u8; 0] }
 #[repr(C)] pub struct rlr_cluster { _p: [u8; 0] }
 #[repr(C)] pub struct rlr_bm25 { _p: [u8; 0] }
+#[repr(C)] pub struct rlr_cluster_bm25 { _p: [u8; 0] }
 
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct rlr_query_weights { pub embedding: f32, pub lexical: f32, pub reranker: f32, pub initial: f32, pub has: u32 }
@@ -89,6 +90,14 @@ extern "C" {
     pub fn rlr_bm25_score(ix: *mut rlr_bm25, query_terms: *const u32, n_terms: u32, limit: u32, out_rows: *mut u32, out_scores: *mut f32, cap: u32, out_n: *mut u32) -> c_int;
     pub fn rlr_search_text_topm(s: *mut rlr_store, ix: *mut rlr_bm25, query: *const f32, dim: u32, flags: u32, w: *const rlr_resolved_weights, query_terms: *const u32, n_terms: u32, m: u32, out_rows: *mut u32, out_combined: *mut f32, out_emb: *mut f32, out_lex: *mut f32, out_n: *mut u32) -> c_int;
     pub fn rlr_search_text_mmr(s: *mut rlr_store, ix: *mut rlr_bm25, query: *const f32, dim: u32, flags: u32, top_k: u32, diversity_factor: f32, w: *const rlr_resolved_weights, query_terms: *const u32, n_terms: u32, out_rows: *mut u32, out_score: *mut f32, out_emb: *mut f32, out_lex: *mut f32, out_n: *mut u32) -> c_int;
+    pub fn rlr_cluster_bm25_create(c: *mut rlr_cluster, out: *mut *mut rlr_cluster_bm25) -> c_int;
+    pub fn rlr_cluster_bm25_destroy(ix: *mut rlr_cluster_bm25) -> c_int;
+    pub fn rlr_cluster_bm25_set_doc(ix: *mut rlr_cluster_bm25, row: u32, term_ids: *const u32, term_freqs: *const u32, n_terms: u32) -> c_int;
+    pub fn rlr_cluster_bm25_remove_doc(ix: *mut rlr_cluster_bm25, row: u32) -> c_int;
+    pub fn rlr_cluster_bm25_stats(ix: *const rlr_cluster_bm25, total_docs: *mut u64, total_length: *mut u64, n_terms: *mut u64) -> c_int;
+    pub fn rlr_cluster_bm25_score(ix: *mut rlr_cluster_bm25, query_terms: *const u32, n_terms: u32, limit: u32, out_rows: *mut u32, out_scores: *mut f32, cap: u32, out_n: *mut u32) -> c_int;
+    pub fn rlr_cluster_search_text_topm(c: *mut rlr_cluster, ix: *mut rlr_cluster_bm25, query: *const f32, dim: u32, flags: u32, w: *const rlr_resolved_weights, query_terms: *const u32, n_terms: u32, m: u32, out_rows: *mut u32, out_combined: *mut f32, out_emb: *mut f32, out_lex: *mut f32, out_n: *mut u32) -> c_int;
+    pub fn rlr_cluster_search_text_mmr(c: *mut rlr_cluster, ix: *mut rlr_cluster_bm25, query: *const f32, dim: u32, flags: u32, top_k: u32, diversity_factor: f32, w: *const rlr_resolved_weights, query_terms: *const u32, n_terms: u32, out_rows: *mut u32, out_score: *mut f32, out_emb: *mut f32, out_lex: *mut f32, out_n: *mut u32) -> c_int;
     pub fn rlr_last_timings(out: *mut rlr_timings) -> c_int;
     pub fn rlr_cluster_create(devices: *const c_int, n_devices: u32, dim: u32, n_rows: u64, rows: *const f32, host_pitch: u64, flags: u32, shard_rows: *const u64, out: *mut *mut rlr_cluster) -> c_int;
     pub fn rlr_cluster_destroy(c: *mut rlr_cluster) -> c_int;

@@ -147,3 +147,91 @@ def test_engine_text_queries_with_device_bm25(eng, orc):
                    [(x.row, F32(x.score).tobytes(), F32(x.lexical_score).tobytes()) for x in rb], (query, k, lam)
         ra, rb = a.search(query, 30), b.search(query, 30)
         assert [(x.row, F32(x.score).tobytes()) for x in ra] == [(x.row, F32(x.score).tobytes()) for x in rb], query
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _cluster_device_sets():
+    sets = [pytest.param([0, 0, 0], id="3-shards-on-gpu0"), pytest.param([0], id="1-shard")]
+    for g in (2, 4, 8):
+        sets.append(pytest.param(list(range(g)), id=f"{g}-gpus",
+                                 marks=pytest.mark.skipif(_ngpu() < g, reason=f"needs {g} GPUs on the box (has {_ngpu()})")))
+    return sets
+
+
+@pytest.mark.parametrize("devices", _cluster_device_sets())
+def test_cluster_bm25_equals_one_index_over_all_rows(eng, orc, devices):
+    """rlr_cluster_bm25_*: one device index per shard, scored with the statistics of the whole corpus, ranked lists merged
+    on the host.  Scores and order must not depend on the sharding: bit-equal to the pure-Python restatement over all
+    documents, and the text search over the cluster bit-equal to the oracle's search fed with those pairs."""
+    n, dim = 9000, 256
+    docs = _corpus(11, n, zipf=True)
+    rows = orc.synth_rows(n, dim, kind=1, n_clusters=64)
+    g = len(devices)
+    plan = None if g == 1 else [n - (g - 1) * (n // g + 7)] + [n // g + 7] * (g - 1)       # uneven shards
+    cl = eng.ClusterStore.from_rows(rows, devices=devices, shard_rows=plan)
+    ix = eng.DeviceLexicalIndex(cl)
+    ref = olex.LexicalIndex()
+    for i, d in enumerate(docs):
+        ix.add_chunk(i, d)
+        ref.add_chunk(i, d)
+    assert ix.stats() == (ref.total_docs, ref.total_length, len(ref.term_postings))
+    for query in QUERIES:
+        for limit in (1, 75, 1500):
+            got, want = ix.score(query, limit), ref.score(query, limit)
+            assert [r for r, _ in got] == [k for k, _ in want], (devices, query, limit)
+            assert all(F32(a).tobytes() == F32(b).tobytes() for (_, a), (_, b) in zip(got, want)), (devices, query, limit)
+    qs = orc.synth_rows(len(QUERIES), dim, kind=1, seed=0x5EED0002, n_clusters=64)
+    blended = False
+    for query, q in zip(QUERIES, qs):
+        terms = ix.query_terms(query)
+        for k, lam in ((5, 0.3), (100, 0.7), (10, 0.0)):
+            pool = max(k, 1) if lam == 0.0 else max(3 * k, k + 10)
+            pairs = ref.score(query, 5 * pool)
+            lr = np.array([r for r, _ in pairs], np.uint32); ls = np.array([s for _, s in pairs], F32)
+            got = cl.search_text_mmr(q, k, lam, W(), ix.handle, terms)
+            want = orc.search_with_diversity(rows, q, k, lam, lex_rows=lr if len(lr) else None, lex_scores=ls if len(lr) else None, full_sort=True)
+            for a, b in zip(got, want):
+                assert same(a, b), (devices, query, k, lam)
+            blended |= bool((want[3] != 0).any())
+        pairs = ref.score(query, 5 * 45)
+        lr = np.array([r for r, _ in pairs], np.uint32); ls = np.array([s for _, s in pairs], F32)
+        got = cl.search_text_topm(q, 45, W(), ix.handle, terms)
+        want = orc.search(rows, q, 45, lex_rows=lr if len(lr) else None, lex_scores=ls if len(lr) else None, full_sort=True)
+        for a, b in zip(got, want):
+            assert same(a, b), (devices, query)
+    assert blended
+    # mutation: documents replaced / removed on two different shards change the GLOBAL statistics for every shard
+    for r in (3, n - 5):
+        ix.add_chunk(r, "bandwidth bandwidth bandwidth HBM kernel")
+        ref.add_chunk(r, "bandwidth bandwidth bandwidth HBM kernel")
+    ix.remove_chunk(n // 2); ref.remove_chunk(n // 2)
+    assert ix.stats() == (ref.total_docs, ref.total_length, len(ref.term_postings))
+    got, want = ix.score("HBM bandwidth kernel", 75), ref.score("HBM bandwidth kernel", 75)
+    assert [r for r, _ in got] == [k for k, _ in want]
+    assert all(F32(a).tobytes() == F32(b).tobytes() for (_, a), (_, b) in zip(got, want))
+    ix.close(); cl.close()
+
+
+def test_engine_text_queries_over_a_cluster_with_device_bm25(eng, orc):
+    """RagEngine(lexical="bm25-device") over a ClusterStore == the same engine over one store."""
+    n, dim = 4000, 128
+    docs = _corpus(5, n, zipf=True)
+    rows = orc.synth_rows(n, dim, kind=1, n_clusters=32)
+    qv = {q: v for q, v in zip(QUERIES, orc.synth_rows(len(QUERIES), dim, kind=1, seed=0x5EED0002, n_clusters=32))}
+    chunks = [eng.DocumentChunk(id=f"c{i}", document_name="d.pdf", text=docs[i], chunk_index=i) for i in range(n)]
+    one = eng.RagEngine(chunks, eng.DeviceStore.from_rows(rows), embedder=lambda s: qv[s], lexical="bm25-device")
+    many = eng.RagEngine(chunks, eng.ClusterStore.from_rows(rows, devices=[0, 0]), embedder=lambda s: qv[s], lexical="bm25-device")
+    for query in QUERIES:
+        for k, lam in ((5, 0.3), (20, 0.0)):
+            ra, rb = one.search_with_diversity(query, k, lam), many.search_with_diversity(query, k, lam)
+            assert [(x.row, F32(x.score).tobytes(), F32(x.lexical_score).tobytes()) for x in ra] == \
+                   [(x.row, F32(x.score).tobytes(), F32(x.lexical_score).tobytes()) for x in rb], (query, k, lam)
+        ra, rb = one.search(query, 30), many.search(query, 30)
+        assert [(x.row, F32(x.score).tobytes()) for x in ra] == [(x.row, F32(x.score).tobytes()) for x in rb], query
