@@ -353,6 +353,10 @@ typedef struct rlr_bm25 rlr_bm25;
 int rlr_bm25_create(rlr_store *s, rlr_bm25 **out);
 int rlr_bm25_destroy(rlr_bm25 *ix);
 int rlr_bm25_set_doc(rlr_bm25 *ix, uint32_t row, const uint32_t *term_ids, const uint32_t *term_freqs, uint32_t n_terms);
+/* bulk rlr_bm25_set_doc for rows [row0, row0 + n_docs): CSR, offsets[n_docs + 1] index term_ids / term_freqs
+ * (what a loader does for every chunk at start-up, validate_index_sync :1375-1389) */
+int rlr_bm25_set_docs(rlr_bm25 *ix, uint32_t row0, uint32_t n_docs, const uint64_t *offsets,
+                      const uint32_t *term_ids, const uint32_t *term_freqs);
 int rlr_bm25_remove_doc(rlr_bm25 *ix, uint32_t row);
 int rlr_bm25_move_doc(rlr_bm25 *ix, uint32_t from_row, uint32_t to_row);
 int rlr_bm25_stats(const rlr_bm25 *ix, uint64_t *total_docs, uint64_t *total_length, uint64_t *n_terms);
@@ -465,6 +469,8 @@ typedef struct rlr_cluster_bm25 rlr_cluster_bm25;
 int rlr_cluster_bm25_create(rlr_cluster *c, rlr_cluster_bm25 **out);
 int rlr_cluster_bm25_destroy(rlr_cluster_bm25 *ix);
 int rlr_cluster_bm25_set_doc(rlr_cluster_bm25 *ix, uint32_t row, const uint32_t *term_ids, const uint32_t *term_freqs, uint32_t n_terms);
+int rlr_cluster_bm25_set_docs(rlr_cluster_bm25 *ix, uint32_t row0, uint32_t n_docs, const uint64_t *offsets,
+                              const uint32_t *term_ids, const uint32_t *term_freqs);
 int rlr_cluster_bm25_remove_doc(rlr_cluster_bm25 *ix, uint32_t row);
 int rlr_cluster_bm25_stats(const rlr_cluster_bm25 *ix, uint64_t *total_docs, uint64_t *total_length, uint64_t *n_terms);
 int rlr_cluster_bm25_score(rlr_cluster_bm25 *ix, const uint32_t *query_terms, uint32_t n_terms, uint32_t limit,

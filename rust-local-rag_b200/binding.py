@@ -114,6 +114,7 @@ PROTOTYPES = {
     "rlr_bm25_create": (_int, [_vp, C.POINTER(_vp)]),
     "rlr_bm25_destroy": (_int, [_vp]),
     "rlr_bm25_set_doc": (_int, [_vp, _u32, _vp, _vp, _u32]),
+    "rlr_bm25_set_docs": (_int, [_vp, _u32, _u32, _vp, _vp, _vp]),
     "rlr_bm25_remove_doc": (_int, [_vp, _u32]),
     "rlr_bm25_move_doc": (_int, [_vp, _u32, _u32]),
     "rlr_bm25_stats": (_int, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
@@ -123,6 +124,7 @@ PROTOTYPES = {
     "rlr_cluster_bm25_create": (_int, [_vp, C.POINTER(_vp)]),
     "rlr_cluster_bm25_destroy": (_int, [_vp]),
     "rlr_cluster_bm25_set_doc": (_int, [_vp, _u32, _vp, _vp, _u32]),
+    "rlr_cluster_bm25_set_docs": (_int, [_vp, _u32, _u32, _vp, _vp, _vp]),
     "rlr_cluster_bm25_remove_doc": (_int, [_vp, _u32]),
     "rlr_cluster_bm25_stats": (_int, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
     "rlr_cluster_bm25_score": (_int, [_vp, _vp, _u32, _u32, _vp, _vp, _u32, _pu32]),

@@ -26,6 +26,8 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -305,6 +307,7 @@ struct rlr_bm25 {
     unsigned long long *d_off = nullptr; uint32_t *d_terms = nullptr, *d_tfs = nullptr, *d_doclen = nullptr;
     uint64_t dev_rows = 0;
     std::mutex mu;
+    std::mutex sync_mu;              // the first queries after a mutation may arrive together: one of them rebuilds the CSR
     std::vector<Bm25Ws *> free_ws;
 };
 
@@ -345,6 +348,7 @@ void ws_release(rlr_bm25 *ix, Bm25Ws *w)
 // (re)build the device CSR from the host forward index; mutators require exclusivity, like the store's
 int bm25_sync(rlr_bm25 *ix)
 {
+    std::lock_guard<std::mutex> lk(ix->sync_mu);
     if (!ix->dirty) return RLR_OK;
     const uint64_t n = ix->s->n_rows;
     if (ix->docs.size() < n) { ix->docs.resize(n); ix->doc_len.resize(n, 0); }
@@ -523,6 +527,19 @@ RLR_EXPORT int rlr_bm25_set_doc(rlr_bm25 *ix, uint32_t row, const uint32_t *term
     return RLR_OK;
 }
 
+RLR_EXPORT int rlr_bm25_set_docs(rlr_bm25 *ix, uint32_t row0, uint32_t n_docs, const uint64_t *offsets, const uint32_t *term_ids,
+                                 const uint32_t *term_freqs)
+{
+    if (!ix) return fail(RLR_ERR_INVALID_ARG, "index is NULL");
+    if (n_docs && !offsets) return fail(RLR_ERR_INVALID_ARG, "offsets is NULL");
+    for (uint32_t i = 0; i < n_docs; ++i) {
+        if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] > 0xffffffffull) return fail(RLR_ERR_INVALID_ARG, "offsets must ascend");
+        const uint32_t nt = static_cast<uint32_t>(offsets[i + 1] - offsets[i]);
+        if (int rc = rlr_bm25_set_doc(ix, row0 + i, nt ? term_ids + offsets[i] : nullptr, nt ? term_freqs + offsets[i] : nullptr, nt)) return rc;
+    }
+    return RLR_OK;
+}
+
 RLR_EXPORT int rlr_bm25_remove_doc(rlr_bm25 *ix, uint32_t row)
 {
     if (!ix) return fail(RLR_ERR_INVALID_ARG, "index is NULL");
@@ -645,6 +662,19 @@ RLR_EXPORT int rlr_cluster_bm25_set_doc(rlr_cluster_bm25 *ix, uint32_t row, cons
     return rlr_bm25_set_doc(p, row, term_ids, term_freqs, n_terms);
 }
 
+RLR_EXPORT int rlr_cluster_bm25_set_docs(rlr_cluster_bm25 *ix, uint32_t row0, uint32_t n_docs, const uint64_t *offsets,
+                                         const uint32_t *term_ids, const uint32_t *term_freqs)
+{
+    if (!ix) return fail(RLR_ERR_INVALID_ARG, "index is NULL");
+    if (n_docs && !offsets) return fail(RLR_ERR_INVALID_ARG, "offsets is NULL");
+    for (uint32_t i = 0; i < n_docs; ++i) {
+        if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] > 0xffffffffull) return fail(RLR_ERR_INVALID_ARG, "offsets must ascend");
+        const uint32_t nt = static_cast<uint32_t>(offsets[i + 1] - offsets[i]);
+        if (int rc = rlr_cluster_bm25_set_doc(ix, row0 + i, nt ? term_ids + offsets[i] : nullptr, nt ? term_freqs + offsets[i] : nullptr, nt)) return rc;
+    }
+    return RLR_OK;
+}
+
 RLR_EXPORT int rlr_cluster_bm25_remove_doc(rlr_cluster_bm25 *ix, uint32_t row)
 {
     if (!ix) return fail(RLR_ERR_INVALID_ARG, "index is NULL");
@@ -688,50 +718,60 @@ int rlr_api_cluster_bm25_score(rlr_cluster_bm25 *ix, const uint32_t *query_terms
     gs.df = df.data();
     if (gs.total_docs == 0 || n_terms == 0) return RLR_OK;
     const size_t np = ix->parts.size();
-    std::vector<Bm25Ws *> ws(np, nullptr);
-    std::vector<char> active(np, 0);
-    int rc = RLR_OK;
-    // every shard scores its documents and ranks its own `limit` best (all enqueued before anything is awaited) ...
-    for (size_t i = 0; i < np && rc == RLR_OK; ++i) {
+    // every shard scores its documents and ranks its own `limit` best, driven by one host thread per shard (a shard's
+    // request is ~13 launches and copies: in sequence they would cost more host time than the GPUs need) ...
+    struct Hit { float score; uint32_t row; };
+    std::vector<std::vector<Hit>> part_hits(np);
+    std::vector<int> rcs(np, RLR_OK);
+    std::vector<std::string> errs(np);
+    const auto run = [&](size_t i) {
         rlr_bm25 *p = ix->parts[i];
-        rc = ensure_device(p->s->device);
+        int rc = ensure_device(p->s->device);
         void *wv = nullptr;
         if (rc == RLR_OK) rc = rlr_api_bm25_ws_acquire(p, &wv);
-        if (rc != RLR_OK) break;
-        Bm25Ws *w = ws[i] = static_cast<Bm25Ws *>(wv);
-        bool act = false;
-        rc = rlr_api_bm25_enqueue(p, w, query_terms, n_terms, limit, nullptr, nullptr, 0, w->d_desc_rows, w->d_desc_scores, w->d_n,
-                                  w->stream, &act, &gs);
-        if (rc == RLR_OK && act) {
-            cudaError_t e = cudaMemcpyAsync(w->h_n, w->d_n, 4, cudaMemcpyDeviceToHost, w->stream);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(w->h_rows, w->d_desc_rows, limit * 4, cudaMemcpyDeviceToHost, w->stream);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(w->h_scores, w->d_desc_scores, limit * 4, cudaMemcpyDeviceToHost, w->stream);
-            if (e != cudaSuccess) { cudaGetLastError(); rc = fail(RLR_ERR_CUDA, "bm25 score failed: %s", cudaGetErrorString(e)); }
-            active[i] = 1;
-        }
-    }
-    // ... then the global `limit` best are the best of the shards' lists
-    struct Hit { float score; uint32_t row; };
-    std::vector<Hit> hits;
-    for (size_t i = 0; i < np; ++i) {
-        if (!ws[i]) continue;
-        if (active[i]) {
-            cudaSetDevice(ix->parts[i]->s->device);
-            const cudaError_t e = cudaStreamSynchronize(ws[i]->stream);
-            if (e != cudaSuccess) { cudaGetLastError(); if (rc == RLR_OK) rc = fail(RLR_ERR_CUDA, "bm25 score failed: %s", cudaGetErrorString(e)); }
-            else if (rc == RLR_OK) {
-                const uint32_t n = std::min(ws[i]->h_n[0], limit);
-                for (uint32_t k = 0; k < n; ++k) hits.push_back({ws[i]->h_scores[k], ws[i]->h_rows[k]});
+        if (rc == RLR_OK) {
+            Bm25Ws *w = static_cast<Bm25Ws *>(wv);
+            bool act = false;
+            rc = rlr_api_bm25_enqueue(p, w, query_terms, n_terms, limit, nullptr, nullptr, 0, w->d_desc_rows, w->d_desc_scores, w->d_n,
+                                      w->stream, &act, &gs);
+            if (rc == RLR_OK && act) {
+                cudaError_t e = cudaMemcpyAsync(w->h_n, w->d_n, 4, cudaMemcpyDeviceToHost, w->stream);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(w->h_rows, w->d_desc_rows, limit * 4, cudaMemcpyDeviceToHost, w->stream);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(w->h_scores, w->d_desc_scores, limit * 4, cudaMemcpyDeviceToHost, w->stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
+                if (e != cudaSuccess) { cudaGetLastError(); rc = fail(RLR_ERR_CUDA, "bm25 score failed: %s", cudaGetErrorString(e)); }
+                else {
+                    const uint32_t n = std::min(w->h_n[0], limit);
+                    part_hits[i].resize(n);
+                    for (uint32_t k = 0; k < n; ++k) part_hits[i][k] = {w->h_scores[k], w->h_rows[k]};
+                }
             }
+            rlr_api_bm25_ws_release(p, w);
         }
-        rlr_api_bm25_ws_release(ix->parts[i], ws[i]);
+        rcs[i] = rc;
+        if (rc != RLR_OK) errs[i] = rlr_last_error();          // the message is thread-local: carry it to the caller
+    };
+    if (np == 1) run(0);
+    else {
+        std::vector<std::thread> th;
+        for (size_t i = 0; i < np; ++i) th.emplace_back(run, i);
+        for (auto &t : th) t.join();
     }
-    if (rc != RLR_OK) return rc;
+    for (size_t i = 0; i < np; ++i)
+        if (rcs[i] != RLR_OK) return fail(rcs[i], "shard %zu: %s", i, errs[i].c_str());
+    // ... then the global `limit` best are the best of the shards' lists: each list is already in rank order (score
+    // descending, ties to the lower row), so a k-way merge of the <= 16 heads yields them in order
     const auto before = [](const Hit &a, const Hit &b) { return a.score > b.score || (a.score == b.score && a.row < b.row); };
-    const size_t keep = std::min<size_t>(limit, hits.size());
-    std::partial_sort(hits.begin(), hits.begin() + keep, hits.end(), before);
-    rows.resize(keep); scores.resize(keep);
-    for (size_t k = 0; k < keep; ++k) { rows[k] = hits[k].row; scores[k] = hits[k].score; }
+    std::vector<size_t> head(np, 0);
+    rows.reserve(limit); scores.reserve(limit);
+    while (rows.size() < limit) {
+        size_t best = np;
+        for (size_t i = 0; i < np; ++i)
+            if (head[i] < part_hits[i].size() && (best == np || before(part_hits[i][head[i]], part_hits[best][head[best]]))) best = i;
+        if (best == np) break;
+        const Hit &h = part_hits[best][head[best]++];
+        rows.push_back(h.row); scores.push_back(h.score);
+    }
     return RLR_OK;
 }
 

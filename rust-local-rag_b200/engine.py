@@ -654,6 +654,12 @@ class DeviceLexicalIndex:
         tfs = np.array(list(counts.values()), np.uint32)
         B.check(self._fn("set_doc")(self._h, row, B.ptr(ids) if len(ids) else None, B.ptr(tfs) if len(ids) else None, len(ids)))
 
+    def add_documents_csr(self, row0: int, offsets: np.ndarray, term_ids: np.ndarray, term_freqs: np.ndarray) -> None:
+        """Bulk add_chunk for rows [row0, row0 + len(offsets) - 1) from numeric term ids (rlr_bm25_set_docs)."""
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ids = np.ascontiguousarray(term_ids, dtype=np.uint32); tfs = np.ascontiguousarray(term_freqs, dtype=np.uint32)
+        B.check(self._fn("set_docs")(self._h, row0, len(off) - 1, B.ptr(off), B.ptr(ids) if len(ids) else None, B.ptr(tfs) if len(ids) else None))
+
     def remove_chunk(self, row: int) -> None:
         B.check(self._fn("remove_doc")(self._h, row))
 

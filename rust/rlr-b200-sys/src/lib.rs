@@ -84,6 +84,7 @@ extern "C" {
     pub fn rlr_bm25_create(s: *mut rlr_store, out: *mut *mut rlr_bm25) -> c_int;
     pub fn rlr_bm25_destroy(ix: *mut rlr_bm25) -> c_int;
     pub fn rlr_bm25_set_doc(ix: *mut rlr_bm25, row: u32, term_ids: *const u32, term_freqs: *const u32, n_terms: u32) -> c_int;
+    pub fn rlr_bm25_set_docs(ix: *mut rlr_bm25, row0: u32, n_docs: u32, offsets: *const u64, term_ids: *const u32, term_freqs: *const u32) -> c_int;
     pub fn rlr_bm25_remove_doc(ix: *mut rlr_bm25, row: u32) -> c_int;
     pub fn rlr_bm25_move_doc(ix: *mut rlr_bm25, from_row: u32, to_row: u32) -> c_int;
     pub fn rlr_bm25_stats(ix: *const rlr_bm25, total_docs: *mut u64, total_length: *mut u64, n_terms: *mut u64) -> c_int;
@@ -93,6 +94,7 @@ extern "C" {
     pub fn rlr_cluster_bm25_create(c: *mut rlr_cluster, out: *mut *mut rlr_cluster_bm25) -> c_int;
     pub fn rlr_cluster_bm25_destroy(ix: *mut rlr_cluster_bm25) -> c_int;
     pub fn rlr_cluster_bm25_set_doc(ix: *mut rlr_cluster_bm25, row: u32, term_ids: *const u32, term_freqs: *const u32, n_terms: u32) -> c_int;
+    pub fn rlr_cluster_bm25_set_docs(ix: *mut rlr_cluster_bm25, row0: u32, n_docs: u32, offsets: *const u64, term_ids: *const u32, term_freqs: *const u32) -> c_int;
     pub fn rlr_cluster_bm25_remove_doc(ix: *mut rlr_cluster_bm25, row: u32) -> c_int;
     pub fn rlr_cluster_bm25_stats(ix: *const rlr_cluster_bm25, total_docs: *mut u64, total_length: *mut u64, n_terms: *mut u64) -> c_int;
     pub fn rlr_cluster_bm25_score(ix: *mut rlr_cluster_bm25, query_terms: *const u32, n_terms: u32, limit: u32, out_rows: *mut u32, out_scores: *mut f32, cap: u32, out_n: *mut u32) -> c_int;
