@@ -251,7 +251,8 @@ public:
 // LexicalIndex with the postings scored ON THE DEVICE (rlr_bm25_*): the host keeps the tokenizer (host-mirror support
 // library) and the term -> id dictionary; chunks are identified by their row in the store.
 class DeviceLexicalIndex {
-    rlr_bm25 *ix_ = nullptr;
+    rlr_bm25 *ix_ = nullptr;                 // over one store ...
+    rlr_cluster_bm25 *cix_ = nullptr;        // ... or over a cluster (one device index per shard, global statistics)
     std::unordered_map<std::string, uint32_t> vocab_;
 
     static std::vector<std::string> tokenize(const std::string &text)      // fn tokenize, :2242-2247
@@ -269,10 +270,12 @@ class DeviceLexicalIndex {
 
 public:
     explicit DeviceLexicalIndex(rlr_store *s) { check(rlr_bm25_create(s, &ix_)); }
+    explicit DeviceLexicalIndex(rlr_cluster *c) { check(rlr_cluster_bm25_create(c, &cix_)); }
     DeviceLexicalIndex(const DeviceLexicalIndex &) = delete;
     DeviceLexicalIndex &operator=(const DeviceLexicalIndex &) = delete;
-    ~DeviceLexicalIndex() { rlr_bm25_destroy(ix_); }
+    ~DeviceLexicalIndex() { rlr_bm25_destroy(ix_); rlr_cluster_bm25_destroy(cix_); }
     rlr_bm25 *handle() const { return ix_; }
+    rlr_cluster_bm25 *cluster_handle() const { return cix_; }
     void add_chunk(uint32_t row, const std::string &text)
     {
         std::map<std::string, uint32_t> counts;
@@ -283,7 +286,8 @@ public:
             if (it == vocab_.end()) it = vocab_.emplace(kv.first, static_cast<uint32_t>(vocab_.size())).first;
             ids.push_back(it->second); tfs.push_back(kv.second);
         }
-        check(rlr_bm25_set_doc(ix_, row, ids.data(), tfs.data(), static_cast<uint32_t>(ids.size())));
+        check(cix_ ? rlr_cluster_bm25_set_doc(cix_, row, ids.data(), tfs.data(), static_cast<uint32_t>(ids.size()))
+                   : rlr_bm25_set_doc(ix_, row, ids.data(), tfs.data(), static_cast<uint32_t>(ids.size())));
     }
     // the query's known term ids in bytewise order of the term strings (std::map<std::string> iterates in that order)
     std::vector<uint32_t> query_terms(const std::string &query) const
@@ -352,12 +356,14 @@ public:
         for (auto &c : chunks_) lexical_->add_chunk(c.id, c.text);
     }
     const LexicalIndex *lexical() const { return lexical_.get(); }
-    // The same, with the postings on the device (single-GPU stores): text queries then run BM25, blend, top-k and MMR
-    // as one device sequence (rlr_search_text_*).
+    // The same, with the postings on the device: text queries then run BM25, blend, top-k and MMR as one device
+    // sequence (rlr_search_text_*); over a cluster every shard scores its documents with the corpus-wide statistics
+    // (rlr_cluster_search_text_*).
     void enable_lexical_on_device()
     {
-        if (!store_) throw Error(RLR_ERR_UNSUPPORTED, "device BM25 needs a single-GPU store");
-        dev_lexical_.reset(new DeviceLexicalIndex(store_));
+        if (!store_ && !cluster_) throw Error(RLR_ERR_UNSUPPORTED, "device BM25 needs a store");
+        if (cluster_) dev_lexical_.reset(new DeviceLexicalIndex(cluster_));
+        else dev_lexical_.reset(new DeviceLexicalIndex(store_));
         for (uint32_t i = 0; i < chunks_.size(); ++i) dev_lexical_->add_chunk(i, chunks_[i].text);
     }
 
@@ -381,9 +387,13 @@ public:
             const size_t cap = std::max<size_t>(top_k, 1);
             std::vector<uint32_t> rows(cap); std::vector<float> score(cap), emb(cap), lex(cap);
             uint32_t n = 0;
-            check(rlr_search_text_mmr(store_, dev_lexical_->handle(), query_embedding.data(), static_cast<uint32_t>(query_embedding.size()), 0,
-                                      static_cast<uint32_t>(top_k), diversity_factor, &w, terms.data(), static_cast<uint32_t>(terms.size()),
-                                      rows.data(), score.data(), emb.data(), lex.data(), &n));
+            check(cluster_ ? rlr_cluster_search_text_mmr(cluster_, dev_lexical_->cluster_handle(), query_embedding.data(),
+                                                         static_cast<uint32_t>(query_embedding.size()), 0, static_cast<uint32_t>(top_k),
+                                                         diversity_factor, &w, terms.data(), static_cast<uint32_t>(terms.size()),
+                                                         rows.data(), score.data(), emb.data(), lex.data(), &n)
+                           : rlr_search_text_mmr(store_, dev_lexical_->handle(), query_embedding.data(), static_cast<uint32_t>(query_embedding.size()), 0,
+                                                 static_cast<uint32_t>(top_k), diversity_factor, &w, terms.data(), static_cast<uint32_t>(terms.size()),
+                                                 rows.data(), score.data(), emb.data(), lex.data(), &n));
             std::vector<SearchResult> out;
             for (uint32_t i = 0; i < n; ++i) out.push_back(result(rows[i], score[i], emb[i], lex[i]));
             return out;

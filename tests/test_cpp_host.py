@@ -124,9 +124,13 @@ def test_cpp_host_hybrid_text_query(tmp_path, orc):
         ref_idx.add_chunk(i, t)
     for query, k, lam, on_device in (("memory of the café server", 6, 0.4, False), ("rust tokio", 10, 0.0, False),
                                      ("memory of the café server", 6, 0.4, True), ("rust tokio index", 10, 0.0, True),
-                                     ("Memory MEMORY lexical rerank", 100, 0.7, True)):
-        # on_device: rlr::DeviceLexicalIndex -- the postings scored on the GPU, the whole text query one device sequence
+                                     ("Memory MEMORY lexical rerank", 100, 0.7, True),
+                                     ("memory of the café server", 6, 0.4, "0,0,0"), ("Memory MEMORY lexical rerank", 100, 0.7, "0,0")):
+        # on_device: rlr::DeviceLexicalIndex -- the postings scored on the GPU, the whole text query one device sequence;
+        # a device list: the same over a sharded store (rlr_cluster_bm25_*, rlr_cluster_search_text_mmr)
         env = dict(os.environ, RLR_CLI_BM25_DEVICE="1") if on_device else dict(os.environ)
+        if isinstance(on_device, str):
+            env["RLR_CLI_DEVICES"] = on_device
         out = json.loads(subprocess.run([exe, idx, qp, str(k), str(lam), "text", query], capture_output=True, text=True,
                                         check=True, env=env).stdout)
         pool = max(k, 1) if lam == 0.0 else max(3 * k, k + 10)
