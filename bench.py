@@ -1221,6 +1221,24 @@ def run_extras(a, rank, world, local_rank, dev, group, peaks, cpu_group=None):
         be.close(group)
         dist.barrier(group=group)
         st.close()
+    # ---- the 10M x 768 store as a TEXT corpus: BM25 scored on the 8 GPUs + the same search, ONE process (rank 0 runs
+    # tools/cluster_text_time.py in a child process; every rank's own stores are closed by now) ----
+    if world == 8:
+        if rank == 0:
+            import subprocess
+            torch.cuda.empty_cache()
+            try:
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "cluster_text_time.py"), "10000000", "8", "768"],
+                                   capture_output=True, text=True, timeout=600, cwd=ROOT)
+                rec = json.loads(r.stdout.strip().splitlines()[-1])
+                rec["exit_code"] = r.returncode
+                out["config3_text_query_bm25_on_8_gpus"] = rec
+                all_ok &= bool(rec.get("parity_ok")) and r.returncode == 0
+            except Exception as e:                     # reported, and it fails the run's parity flag
+                out["config3_text_query_bm25_on_8_gpus"] = {"error": repr(e)[:300]}
+                all_ok = False
+        if cpu_group is not None:
+            dist.barrier(group=cpu_group)
     if rank == 0:
         out["all_parity_ok"] = bool(all_ok)
     return out
