@@ -439,10 +439,11 @@ int rlr_cluster_search_mmr(rlr_cluster *c, const float *query, uint32_t dim, uin
                            const uint32_t *lex_rows, const float *lex_scores, uint32_t n_lex,
                            uint32_t *out_rows, float *out_score, float *out_emb, float *out_lex,
                            uint32_t *out_n);
-/* throughput mode over the cluster, as rlr_search_mmr_multi (embedding-only queries: no lexical pairs): every GPU
- * scans its shard ONCE for the nq queries and posts nq lists; the root merges and diversifies each */
+/* throughput mode over the cluster, as rlr_search_mmr_multi (same arguments, per-query lexical pairs included): every
+ * GPU scans its shard ONCE for the nq queries and posts nq lists; the root merges and diversifies each */
 int rlr_cluster_search_mmr_multi(rlr_cluster *c, const float *queries, uint32_t nq, uint32_t dim, uint32_t flags,
                                  uint32_t top_k, float diversity_factor, const rlr_resolved_weights *w,
+                                 const uint32_t *const *lex_rows, const float *const *lex_scores, const uint32_t *n_lex,
                                  uint32_t *out_rows, float *out_score, float *out_emb, float *out_lex,
                                  uint32_t *out_n);
 /* the batched contraction over the cluster, as rlr_search_batch (flags: operand precision, exact re-score): every GPU

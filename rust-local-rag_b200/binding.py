@@ -142,7 +142,8 @@ PROTOTYPES = {
     "rlr_cluster_mmr": (_int, [_vp, _vp, _vp, _u32, _u32, _f32, _u32, _vp, _pu32]),
     "rlr_cluster_search_mmr": (_int, [_vp, _vp, _u32, _u32, _u32, _f32, C.POINTER(ResolvedWeightsC), _vp, _vp, _u32,
                                       _vp, _vp, _vp, _vp, _pu32]),
-    "rlr_cluster_search_mmr_multi": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _f32, C.POINTER(ResolvedWeightsC), _vp, _vp, _vp, _vp, _vp]),
+    "rlr_cluster_search_mmr_multi": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _f32, C.POINTER(ResolvedWeightsC), _vp, _vp, _vp,
+                                     _vp, _vp, _vp, _vp, _vp]),
     "rlr_cluster_search_batch": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp]),
     "rlr_cluster_embedding_candidates": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _pu32]),
     "rlr_cluster_last_scan_ms": (_int, [_vp, _u32, _pu32]),

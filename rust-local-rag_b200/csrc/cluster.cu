@@ -35,6 +35,8 @@ namespace {
 struct ClusterCtx {
     std::vector<rlr_ctx *> c;          // one workspace + stream per shard, on that shard's device
     std::vector<rlr_ctx *> root_extra; // throughput mode: pool / MMR buffers of queries 1.. on the root (created on first use)
+    struct LexBuf { uint32_t *h_rows = nullptr, *d_rows = nullptr; float *h_norm = nullptr, *d_norm = nullptr; };
+    std::vector<std::vector<LexBuf>> lex_extra;   // throughput mode: [shard][query - 1] lexical pairs of queries 1.. (query 0 uses the ctx's)
     rlr_mailbox *mb = nullptr;         // in the root's HBM, private to this lane
     uint64_t seq = 0;                  // sequence numbers of this lane's mailbox start at 1
     uint32_t *h_status = nullptr;      // pinned: sticky mailbox status read back with every result
@@ -74,6 +76,11 @@ void cctx_free(rlr_cluster *cl, ClusterCtx *cc)
     for (size_t g = 0; g < cc->c.size(); ++g)
         if (cc->c[g]) { cudaSetDevice(cl->device[g]); ctx_free(cc->c[g]); }
     for (rlr_ctx *x : cc->root_extra) { cudaSetDevice(cl->device[0]); ctx_free(x); }
+    for (size_t g = 0; g < cc->lex_extra.size(); ++g)
+        for (auto &b : cc->lex_extra[g]) {
+            cudaSetDevice(cl->device[g]);
+            cudaFree(b.d_rows); cudaFree(b.d_norm); cudaFreeHost(b.h_rows); cudaFreeHost(b.h_norm);
+        }
     for (size_t g = 0; g < cc->batch_keys.size(); ++g) if (cc->batch_keys[g]) { cudaSetDevice(cl->device[g]); cudaFree(cc->batch_keys[g]); }
     cudaSetDevice(cl->device[0]);
     cudaFree(cc->batch_all); cudaFree(cc->batch_out); cudaFree(cc->batch_cnt);
@@ -182,7 +189,7 @@ struct Plan {
 
 // :505-530 for every shard: (sorted local rows, score / GLOBAL max_lexical), later duplicates win
 int stage_lex_shards(rlr_cluster *cl, ClusterCtx *cc, const uint32_t *lex_rows, const float *lex_scores, uint32_t n_lex,
-                     std::vector<uint32_t> *n_out)
+                     std::vector<uint32_t> *n_out, uint32_t q = 0 /* throughput mode: which query's buffers */)
 {
     n_out->assign(cl->n, 0);
     if (n_lex == 0) return RLR_OK;
@@ -201,9 +208,11 @@ int stage_lex_shards(rlr_cluster *cl, ClusterCtx *cc, const uint32_t *lex_rows, 
         if (i + 1 < order.size() && order[i + 1].first == order[i].first) continue;
         const uint32_t g = owner_of(cl, order[i].first);
         rlr_ctx *c = cc->c[g];
+        uint32_t *h_rows = q == 0 ? c->h_lex_rows : cc->lex_extra[g][q - 1].h_rows;
+        float *h_norm = q == 0 ? c->h_lex_norm : cc->lex_extra[g][q - 1].h_norm;
         uint32_t &n = (*n_out)[g];
-        c->h_lex_rows[n] = static_cast<uint32_t>(order[i].first - cl->row_base[g]);
-        c->h_lex_norm[n] = lex_scores[order[i].second] / max_lexical; // :527-530
+        h_rows[n] = static_cast<uint32_t>(order[i].first - cl->row_base[g]);
+        h_norm[n] = lex_scores[order[i].second] / max_lexical; // :527-530
         ++n;
     }
     return RLR_OK;
@@ -329,7 +338,8 @@ int cluster_search(rlr_cluster *cl, const float *query, uint32_t dim, uint32_t f
 // throughput mode over the cluster: nq queries, ONE pass over every shard (query groups), nq posts per shard into
 // consecutive mailbox slots, nq merges + MMRs on the root
 int cluster_search_multi(rlr_cluster *cl, const float *queries, uint32_t nq, uint32_t dim, uint32_t flags, uint32_t pool,
-                         bool do_mmr, uint32_t top_k, float lambda, const rlr_resolved_weights *w, uint32_t *out_rows,
+                         bool do_mmr, uint32_t top_k, float lambda, const rlr_resolved_weights *w,
+                         const uint32_t *const *lex_rows, const float *const *lex_scores, const uint32_t *n_lex, uint32_t *out_rows,
                          float *out_score, float *out_emb, float *out_lex, uint32_t *out_n)
 {
     ClusterLease lease(cl);
@@ -350,6 +360,28 @@ int cluster_search_multi(rlr_cluster *cl, const float *queries, uint32_t nq, uin
             if (!std::isfinite(hq[i])) return fail(RLR_ERR_NONFINITE, "queries[%u][%u] is not finite", q, i);
         if (!(flags & RLR_QUERY_PRENORMALIZED)) host_normalize(hq, dim);
     }
+    // lexical pairs, per query: routed to the owning shards, normalised by that query's global maximum (:505-530)
+    std::vector<std::vector<uint32_t>> nl(nq, std::vector<uint32_t>(cl->n, 0));
+    bool any_lex = false;
+    for (uint32_t q = 0; q < nq; ++q) any_lex |= n_lex != nullptr && n_lex[q] != 0;
+    if (any_lex) {
+        if (!lex_rows || !lex_scores) return fail(RLR_ERR_INVALID_ARG, "n_lex > 0 but lex_rows/lex_scores is NULL");
+        if (cc->lex_extra.size() < cl->n) cc->lex_extra.resize(cl->n);
+        for (uint32_t g = 0; g < cl->n; ++g)
+            while (cc->lex_extra[g].size() + 1 < nq) {
+                if (int rc = ensure_device(cl->device[g])) return rc;
+                ClusterCtx::LexBuf b;
+                cudaError_t e = cudaMallocHost(&b.h_rows, kLexCap * sizeof(uint32_t));
+                if (e == cudaSuccess) e = cudaMallocHost(&b.h_norm, kLexCap * sizeof(float));
+                if (e == cudaSuccess) e = cudaMalloc(&b.d_rows, kLexCap * sizeof(uint32_t));
+                if (e == cudaSuccess) e = cudaMalloc(&b.d_norm, kLexCap * sizeof(float));
+                cc->lex_extra[g].push_back(b);          // owned (and freed) by the lane even when an allocation failed
+                if (e != cudaSuccess) { cudaGetLastError(); return fail(RLR_ERR_OOM, "lexical staging allocation failed: %s", cudaGetErrorString(e)); }
+            }
+        for (uint32_t q = 0; q < nq; ++q)
+            if (n_lex[q])
+                if (int rc = stage_lex_shards(cl, cc, lex_rows[q], lex_scores[q], n_lex[q], &nl[q], q)) return rc;
+    }
     const uint64_t seq0 = cc->seq + 1;
     cc->seq += nq;
     uint64_t launches = 0;
@@ -360,6 +392,15 @@ int cluster_search_multi(rlr_cluster *cl, const float *queries, uint32_t nq, uin
         cudaStream_t st = c->stream;
         CU_TRY(cudaSetDevice(s->device));
         CU_TRY(cudaMemcpyAsync(c->d_query, r0->h_query, static_cast<size_t>(nq) * rlr::kQueryCap * sizeof(float), cudaMemcpyHostToDevice, st));
+        for (uint32_t q = 0; q < nq; ++q) {
+            if (!nl[q][g]) continue;
+            const uint32_t *hr = q == 0 ? c->h_lex_rows : cc->lex_extra[g][q - 1].h_rows;
+            const float *hn = q == 0 ? c->h_lex_norm : cc->lex_extra[g][q - 1].h_norm;
+            uint32_t *dr = q == 0 ? c->d_lex_rows : cc->lex_extra[g][q - 1].d_rows;
+            float *dn = q == 0 ? c->d_lex_norm : cc->lex_extra[g][q - 1].d_norm;
+            CU_TRY(cudaMemcpyAsync(dr, hr, nl[q][g] * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            CU_TRY(cudaMemcpyAsync(dn, hn, nl[q][g] * sizeof(float), cudaMemcpyHostToDevice, st));
+        }
         const bool half = s->use_half(flags);
         rlr::ScanArgs a;
         memset(&a, 0, sizeof a);
@@ -376,6 +417,9 @@ int cluster_search_multi(rlr_cluster *cl, const float *queries, uint32_t nq, uin
             const uint32_t slot = static_cast<uint32_t>((seq0 + q) % cc->mb->ring);
             rlr::ScanGroupIO &io = a.groups.g[q];
             io.query = c->d_query + static_cast<size_t>(q) * rlr::kQueryCap;
+            io.lex_rows = q == 0 ? c->d_lex_rows : (nl[q][g] ? cc->lex_extra[g][q - 1].d_rows : nullptr);
+            io.lex_norm = q == 0 ? c->d_lex_norm : (nl[q][g] ? cc->lex_extra[g][q - 1].d_norm : nullptr);
+            io.n_lex = nl[q][g];
             io.out = cc->mb->list(slot, g); io.out_n = cc->mb->count(slot, g);
             io.post.flag = cc->mb->flag(slot, g);
             io.post.consumed = cc->mb->consumed(slot);
@@ -508,6 +552,7 @@ RLR_EXPORT int rlr_cluster_search_batch(rlr_cluster *cl, const float *queries, u
 
 RLR_EXPORT int rlr_cluster_search_mmr_multi(rlr_cluster *cl, const float *queries, uint32_t nq, uint32_t dim, uint32_t flags,
                                             uint32_t top_k, float diversity_factor, const rlr_resolved_weights *w,
+                                            const uint32_t *const *lex_rows, const float *const *lex_scores, const uint32_t *n_lex,
                                             uint32_t *out_rows, float *out_score, float *out_emb, float *out_lex, uint32_t *out_n)
 {
     if (int rc = check_cluster(cl)) return rc;
@@ -517,11 +562,11 @@ RLR_EXPORT int rlr_cluster_search_mmr_multi(rlr_cluster *cl, const float *querie
     if (nq > RLR_MAX_MULTI) return fail(RLR_ERR_UNSUPPORTED, "nq %u exceeds RLR_MAX_MULTI (%d)", nq, RLR_MAX_MULTI);
     if (!queries) return fail(RLR_ERR_INVALID_ARG, "queries is NULL");
     if (cl->n == 1)
-        return rlr_search_mmr_multi(cl->shard[0], queries, nq, dim, flags, top_k, diversity_factor, w, nullptr, nullptr, nullptr,
+        return rlr_search_mmr_multi(cl->shard[0], queries, nq, dim, flags, top_k, diversity_factor, w, lex_rows, lex_scores, n_lex,
                                     out_rows, out_score, out_emb, out_lex, out_n);
     if (nq == 1)
-        return rlr_cluster_search_mmr(cl, queries, dim, flags, top_k, diversity_factor, w, nullptr, nullptr, 0, out_rows, out_score,
-                                      out_emb, out_lex, out_n);
+        return rlr_cluster_search_mmr(cl, queries, dim, flags, top_k, diversity_factor, w, lex_rows ? lex_rows[0] : nullptr,
+                                      lex_scores ? lex_scores[0] : nullptr, n_lex ? n_lex[0] : 0, out_rows, out_score, out_emb, out_lex, out_n);
     for (uint32_t q = 0; q < nq; ++q) out_n[q] = 0;
     float lambda = diversity_factor;
     if (lambda < 0.0f) lambda = 0.0f;
@@ -532,7 +577,7 @@ RLR_EXPORT int rlr_cluster_search_mmr_multi(rlr_cluster *cl, const float *querie
     if ((flags & RLR_SEARCH_F16) && !(cl->flags & (RLR_STORE_KEEP_F16 | RLR_STORE_F16_ONLY)))
         return fail(RLR_ERR_INVALID_ARG, "RLR_SEARCH_F16 but the store holds no f16 copy");
     return cluster_search_multi(cl, queries, nq, dim, flags, static_cast<uint32_t>(std::min<uint64_t>(pool, cl->n_rows)), do_mmr, top_k,
-                                lambda, w, out_rows, out_score, out_emb, out_lex, out_n);
+                                lambda, w, lex_rows, lex_scores, n_lex, out_rows, out_score, out_emb, out_lex, out_n);
 }
 
 RLR_EXPORT int rlr_cluster_create(const int *devices, uint32_t n_devices, uint32_t dim, uint64_t n_rows, const float *rows,

@@ -385,7 +385,8 @@ class DeviceStore:
 
     def search_mmr_multi(self, queries: np.ndarray, top_k: int, diversity: float, w: ResolvedWeights, lex=None,
                          flags: int = 0):
-        """rlr_search_mmr_multi (throughput mode): up to RLR_MAX_MULTI queries answered by ONE pass over the rows.
+        """rlr_search_mmr_multi / rlr_cluster_search_mmr_multi (throughput mode): up to RLR_MAX_MULTI queries answered by
+        ONE pass over the rows (of every shard).
         `lex`: optional list of (lex_rows, lex_scores) per query (None entries allowed).  Returns a list of
         (rows, score, emb, lex) per query, each identical to search_mmr's result for that query."""
         q = np.ascontiguousarray(queries, dtype=np.float32)
@@ -405,7 +406,7 @@ class DeviceStore:
                 a = np.ascontiguousarray(pair[0], dtype=np.uint32); b = np.ascontiguousarray(pair[1], dtype=np.float32)
                 keep += [a, b]
                 lr_ptrs[i] = a.ctypes.data; ls_ptrs[i] = b.ctypes.data; nl[i] = len(a)
-        B.check(self._lib.rlr_search_mmr_multi(self._h, B.ptr(q), nq, dim, flags, top_k, diversity, C.byref(wc),
+        B.check(self._hot("search_mmr_multi")(self._h, B.ptr(q), nq, dim, flags, top_k, diversity, C.byref(wc),
                                                lr_ptrs, ls_ptrs, B.ptr(nl) if nl is not None else None,
                                                B.ptr(rows), B.ptr(score), B.ptr(emb), B.ptr(lx), B.ptr(n)))
         return [(rows[i, :n[i]].copy(), score[i, :n[i]].copy(), emb[i, :n[i]].copy(), lx[i, :n[i]].copy()) for i in range(nq)]
@@ -507,22 +508,6 @@ class ClusterStore(DeviceStore):
     def upload(self, row0: int, rows: np.ndarray) -> None:
         rows = np.ascontiguousarray(rows, dtype=np.float32)
         B.check(self._lib.rlr_cluster_upload(self._h, row0, rows.shape[0], B.ptr(rows), rows.shape[1]))
-
-    def search_mmr_multi(self, queries: np.ndarray, top_k: int, diversity: float, w: ResolvedWeights, lex=None,
-                         flags: int = 0):
-        """rlr_cluster_search_mmr_multi: throughput mode over the cluster (embedding-only queries)."""
-        if lex is not None and any(p is not None for p in lex):
-            raise B.RlrError(B.RLR_ERR_UNSUPPORTED, "throughput mode over a cluster takes embedding-only queries")
-        q = np.ascontiguousarray(queries, dtype=np.float32)
-        nq, dim = q.shape
-        cap = max(top_k, 1)
-        rows = np.zeros((nq, cap), np.uint32); score = np.zeros((nq, cap), np.float32)
-        emb = np.zeros((nq, cap), np.float32); lx = np.zeros((nq, cap), np.float32)
-        n = np.zeros(nq, np.uint32)
-        wc = B.ResolvedWeightsC(w.embedding, w.lexical, w.reranker, w.initial)
-        B.check(self._lib.rlr_cluster_search_mmr_multi(self._h, B.ptr(q), nq, dim, flags, top_k, diversity, C.byref(wc),
-                                                       B.ptr(rows), B.ptr(score), B.ptr(emb), B.ptr(lx), B.ptr(n)))
-        return [(rows[i, :n[i]].copy(), score[i, :n[i]].copy(), emb[i, :n[i]].copy(), lx[i, :n[i]].copy()) for i in range(nq)]
 
     def append(self, rows):
         raise B.RlrError(B.RLR_ERR_UNSUPPORTED, "a cluster is a bulk-loaded snapshot: mutate a single-GPU store or rebuild")

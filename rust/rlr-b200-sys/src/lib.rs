@@ -110,7 +110,7 @@ extern "C" {
     pub fn rlr_cluster_search_topm(c: *mut rlr_cluster, query: *const f32, dim: u32, flags: u32, w: *const rlr_resolved_weights, lex_rows: *const u32, lex_scores: *const f32, n_lex: u32, m: u32, out_rows: *mut u32, out_combined: *mut f32, out_emb: *mut f32, out_lex: *mut f32, out_n: *mut u32) -> c_int;
     pub fn rlr_cluster_mmr(c: *mut rlr_cluster, cand_rows: *const u32, relevance: *const f32, p: u32, top_k: u32, lambda: f32, flags: u32, out_sel_pos: *mut u32, out_n: *mut u32) -> c_int;
     pub fn rlr_cluster_search_mmr(c: *mut rlr_cluster, query: *const f32, dim: u32, flags: u32, top_k: u32, diversity_factor: f32, w: *const rlr_resolved_weights, lex_rows: *const u32, lex_scores: *const f32, n_lex: u32, out_rows: *mut u32, out_score: *mut f32, out_emb: *mut f32, out_lex: *mut f32, out_n: *mut u32) -> c_int;
-    pub fn rlr_cluster_search_mmr_multi(c: *mut rlr_cluster, queries: *const f32, nq: u32, dim: u32, flags: u32, top_k: u32, diversity_factor: f32, w: *const rlr_resolved_weights, out_rows: *mut u32, out_score: *mut f32, out_emb: *mut f32, out_lex: *mut f32, out_n: *mut u32) -> c_int;
+    pub fn rlr_cluster_search_mmr_multi(c: *mut rlr_cluster, queries: *const f32, nq: u32, dim: u32, flags: u32, top_k: u32, diversity_factor: f32, w: *const rlr_resolved_weights, lex_rows: *const *const u32, lex_scores: *const *const f32, n_lex: *const u32, out_rows: *mut u32, out_score: *mut f32, out_emb: *mut f32, out_lex: *mut f32, out_n: *mut u32) -> c_int;
     pub fn rlr_cluster_search_batch(c: *mut rlr_cluster, queries: *const f32, n_queries: u32, dim: u32, flags: u32, m: u32, out_rows: *mut u32, out_scores: *mut f32, out_n: *mut u32) -> c_int;
     pub fn rlr_cluster_embedding_candidates(c: *mut rlr_cluster, query: *const f32, dim: u32, flags: u32, count: u32, out_rows: *mut u32, out_score: *mut f32, out_n: *mut u32) -> c_int;
     pub fn rlr_cluster_last_scan_ms(out_ms: *mut f32, cap: u32, out_n: *mut u32) -> c_int;

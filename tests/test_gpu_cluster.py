@@ -225,6 +225,31 @@ def test_cluster_throughput_mode_multi_query(eng, orc, corpus, devices):
         for j in range(3):
             ref = orc.search_with_diversity(rows, qs[j], k, lam, threads=4)
             assert same(got[j][0], ref[0]) and same(got[j][1], ref[1])
+    # per-query lexical pairs (a text query each; one query without): routed per shard, each normalised by ITS global max
+    rng = np.random.default_rng(31)
+    n = len(rows)
+    for it in range(4):
+        lex = []
+        for j in range(3):
+            if j == it % 3:
+                lex.append(None)
+                continue
+            cnt = int(rng.integers(41, 1500))
+            top = np.argsort(-(rows @ orc.normalize_rows(qs[j:j + 1])[0]))[:40].astype(np.uint32)       # pairs that matter
+            rest = np.setdiff1d(rng.choice(n, cnt, replace=False).astype(np.uint32), top)[: cnt - 40]
+            lr = np.concatenate([top, rng.permutation(rest)]).astype(np.uint32)                          # unique rows, any order
+            lex.append((lr, (rng.random(len(lr)) * 7).astype(F32)))
+        got = cl.search_mmr_multi(qs[:3], 100, 0.7, W(), lex=lex)
+        blended = False
+        for j in range(3):
+            lr, ls = lex[j] if lex[j] is not None else (None, None)
+            ref = orc.search_with_diversity(rows, qs[j], 100, 0.7, lex_rows=lr, lex_scores=ls, threads=4)
+            for a, b in zip(got[j], ref):
+                assert same(a, b), (devices, it, j)
+            one = cl.search_mmr(qs[j], 100, 0.7, W(), lr, ls)
+            assert all(same(a, b) for a, b in zip(one, ref))
+            blended |= bool((ref[3] != 0).any())
+        assert blended
     cl.close()
 
 
