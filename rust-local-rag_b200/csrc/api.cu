@@ -966,10 +966,11 @@ int stage_text(rlr_ctx *c, const TextQuery &tq, uint32_t limit, Bm25WsGuard &g, 
     g.ix = tq.ix;
     if (int rc = rlr_api_bm25_ws_acquire(tq.ix, &g.ws)) return rc;
     bool active = false;
+    uint32_t launches = 0;
     if (int rc = rlr_api_bm25_enqueue(tq.ix, g.ws, tq.terms, tq.n_terms, limit, c->d_lex_rows, c->d_lex_norm, limit, nullptr, nullptr,
-                                      nullptr, st, &active))
+                                      nullptr, st, &active, nullptr, &launches))
         return rc;
-    if (active) { *out_nl = limit; c->launches += rlr_api_bm25_launches(); }
+    if (active) { *out_nl = limit; c->launches += launches; }
     return RLR_OK;
 }
 

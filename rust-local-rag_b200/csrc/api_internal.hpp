@@ -154,8 +154,8 @@ void rlr_api_bm25_ws_release(rlr_bm25 *ix, void *ws);
 struct rlr_api_bm25_global { uint64_t total_docs, total_length; const uint32_t *df; };
 int rlr_api_bm25_enqueue(rlr_bm25 *ix, void *ws, const uint32_t *query_terms, uint32_t n_terms, uint32_t limit,
                          uint32_t *d_lex_rows, float *d_lex_norm, uint32_t lex_pad, uint32_t *d_desc_rows, float *d_desc_scores,
-                         uint32_t *d_n, cudaStream_t st, bool *active, const rlr_api_bm25_global *gs = nullptr);
-uint32_t rlr_api_bm25_launches();
+                         uint32_t *d_n, cudaStream_t st, bool *active, const rlr_api_bm25_global *gs = nullptr,
+                         uint32_t *launches_out = nullptr);
 rlr_store *rlr_api_bm25_store(rlr_bm25 *ix);
 
 // cluster.cu <-> bm25.cu: a BM25 index over a sharded store (rlr_cluster_bm25_*)

@@ -43,6 +43,7 @@ constexpr uint32_t kBm25MaxLimit = 8192;     // 5 * m: 1500 for top_k = 100 with
 constexpr uint32_t kDigitBits = 11;
 constexpr uint32_t kBins = 1u << kDigitBits;
 constexpr uint32_t kPasses = 6;              // 6 x 11 bits >= 64
+constexpr uint64_t kBm25InvertedMinRows = 262144;   // beyond the latency path's stores the device index is inverted (see below)
 
 struct Bm25Query {
     uint32_t n_terms;
@@ -204,6 +205,40 @@ __global__ void bm25_compact_kernel(const unsigned long long *__restrict__ keys,
     }
 }
 
+// Large stores: the same scores from an INVERTED index (postings by term, rows ascending), touching only the
+// postings of the query's terms instead of every (row, term) pair of the corpus.  `scores[doc] += contribution` must
+// happen in the caller's term order for every document, so the terms are processed by consecutive launches on one
+// stream (a term lists a row once: no two threads of a launch touch the same score, no atomics), each posting doing
+// exactly the arithmetic of bm25_score_kernel.  An untouched score keeps its 0xffffffff fill: the first
+// contribution is added to 0.0 (`entry.or_insert(0.0)`), and "never touched" stays distinguishable from a sum of 0.0.
+__global__ void bm25_term_pass_kernel(const uint32_t *__restrict__ pdocs, const uint32_t *__restrict__ ptfs, unsigned long long p_lo,
+                                      unsigned long long p_hi, const uint32_t *__restrict__ doc_len, float idf, float avg_doc_len,
+                                      float *__restrict__ scores)
+{
+    const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    for (unsigned long long p = p_lo + static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < p_hi; p += stride) {
+        const uint32_t r = pdocs[p];
+        const float dl = static_cast<float>(doc_len[r]);
+        if (dl == 0.0f) continue;                                       // `if doc_length == 0.0 { continue; }`
+        const float k1 = 1.5f, b = 0.75f;
+        const float x = mul_rn(k1, add_rn(sub_rn(1.0f, b), mul_rn(b, __fdiv_rn(dl, avg_doc_len))));
+        const float tf = static_cast<float>(ptfs[p]);
+        const float denom = add_rn(tf, x);
+        if (denom == 0.0f) continue;                                    // `if denom == 0.0 { continue; }`
+        const float sc = __fdiv_rn(mul_rn(idf, mul_rn(tf, add_rn(k1, 1.0f))), denom);
+        const float prev = scores[r];
+        scores[r] = add_rn(__float_as_uint(prev) == 0xffffffffu ? 0.0f : prev, sc);   // *entry.or_insert(0.0) += score
+    }
+}
+
+__global__ void bm25_keys_kernel(const float *__restrict__ scores, uint32_t n_rows, uint32_t row_base, unsigned long long *__restrict__ keys)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const float sc = scores[r];
+    keys[r] = __float_as_uint(sc) == 0xffffffffu ? 0ull : make_key(sc, row_base + r);
+}
+
 __device__ void bitonic_smem_desc(unsigned long long *k, uint32_t n2)
 {
     for (uint32_t size = 2; size <= n2; size <<= 1)
@@ -273,6 +308,7 @@ namespace {
 
 struct Bm25Ws {                      // per-request device workspace
     unsigned long long *d_keys = nullptr; size_t keys_cap = 0;
+    float *d_scores = nullptr; size_t scores_cap = 0;      // inverted-index path: per-row running sums
     uint32_t *d_hist = nullptr;
     rlr::Bm25Sel *d_sel = nullptr;
     unsigned long long *d_out = nullptr;
@@ -285,7 +321,7 @@ struct Bm25Ws {                      // per-request device workspace
 void ws_free(Bm25Ws *w)
 {
     if (!w) return;
-    cudaFree(w->d_keys); cudaFree(w->d_hist); cudaFree(w->d_sel); cudaFree(w->d_out); cudaFree(w->d_desc_rows);
+    cudaFree(w->d_keys); cudaFree(w->d_scores); cudaFree(w->d_hist); cudaFree(w->d_sel); cudaFree(w->d_out); cudaFree(w->d_desc_rows);
     cudaFree(w->d_desc_scores); cudaFree(w->d_n); cudaFree(w->d_lex_rows); cudaFree(w->d_lex_norm);
     cudaFreeHost(w->h_rows); cudaFreeHost(w->h_scores); cudaFreeHost(w->h_n);
     if (w->stream) cudaStreamDestroy(w->stream);
@@ -305,6 +341,11 @@ struct rlr_bm25 {
     uint64_t total_docs = 0, total_length = 0, n_terms_live = 0;
     bool dirty = true;
     unsigned long long *d_off = nullptr; uint32_t *d_terms = nullptr, *d_tfs = nullptr, *d_doclen = nullptr;
+    // stores beyond kBm25InvertedMinRows: the device holds postings BY TERM instead (local rows ascending per term);
+    // poff (host) are the term boundaries, read per query
+    bool inverted = false;
+    std::vector<unsigned long long> poff;
+    uint32_t *d_pdocs = nullptr, *d_ptfs = nullptr;
     uint64_t dev_rows = 0;
     std::mutex mu;
     std::mutex sync_mu;              // the first queries after a mutation may arrive together: one of them rebuilds the CSR
@@ -352,26 +393,47 @@ int bm25_sync(rlr_bm25 *ix)
     if (!ix->dirty) return RLR_OK;
     const uint64_t n = ix->s->n_rows;
     if (ix->docs.size() < n) { ix->docs.resize(n); ix->doc_len.resize(n, 0); }
-    std::vector<unsigned long long> off(n + 1, 0);
-    for (uint64_t r = 0; r < n; ++r) off[r + 1] = off[r] + ix->docs[r].size();
-    const unsigned long long total = off[n];
-    std::vector<uint32_t> terms(total), tfs(total);
-    for (uint64_t r = 0; r < n; ++r) {
-        unsigned long long o = off[r];
-        for (auto &p : ix->docs[r]) { terms[o] = p.first; tfs[o] = p.second; ++o; }
-    }
-    cudaFree(ix->d_off); cudaFree(ix->d_terms); cudaFree(ix->d_tfs); cudaFree(ix->d_doclen);
-    ix->d_off = nullptr; ix->d_terms = ix->d_tfs = ix->d_doclen = nullptr;
-    CU_TRY(cudaMalloc(&ix->d_off, (n + 1) * 8));
-    CU_TRY(cudaMalloc(&ix->d_terms, std::max<unsigned long long>(total, 1) * 4));
-    CU_TRY(cudaMalloc(&ix->d_tfs, std::max<unsigned long long>(total, 1) * 4));
+    cudaFree(ix->d_off); cudaFree(ix->d_terms); cudaFree(ix->d_tfs); cudaFree(ix->d_doclen); cudaFree(ix->d_pdocs); cudaFree(ix->d_ptfs);
+    ix->d_off = nullptr; ix->d_terms = ix->d_tfs = ix->d_doclen = ix->d_pdocs = ix->d_ptfs = nullptr;
+    const char *const force = getenv("RLR_BM25_INDEX");                 // dev / test knob: "forward" | "inverted" whatever the size
+    ix->inverted = force ? strcmp(force, "inverted") == 0 : n > rlr::kBm25InvertedMinRows;
     CU_TRY(cudaMalloc(&ix->d_doclen, std::max<uint64_t>(n, 1) * 4));
-    CU_TRY(cudaMemcpy(ix->d_off, off.data(), (n + 1) * 8, cudaMemcpyHostToDevice));
-    if (total) {
-        CU_TRY(cudaMemcpy(ix->d_terms, terms.data(), total * 4, cudaMemcpyHostToDevice));
-        CU_TRY(cudaMemcpy(ix->d_tfs, tfs.data(), total * 4, cudaMemcpyHostToDevice));
-    }
     if (n) CU_TRY(cudaMemcpy(ix->d_doclen, ix->doc_len.data(), n * 4, cudaMemcpyHostToDevice));
+    if (!ix->inverted) {
+        // forward index (CSR by row): one thread per row looks the query terms up in the row's sorted term list
+        std::vector<unsigned long long> off(n + 1, 0);
+        for (uint64_t r = 0; r < n; ++r) off[r + 1] = off[r] + ix->docs[r].size();
+        const unsigned long long total = off[n];
+        std::vector<uint32_t> terms(total), tfs(total);
+        for (uint64_t r = 0; r < n; ++r) {
+            unsigned long long o = off[r];
+            for (auto &p : ix->docs[r]) { terms[o] = p.first; tfs[o] = p.second; ++o; }
+        }
+        CU_TRY(cudaMalloc(&ix->d_off, (n + 1) * 8));
+        CU_TRY(cudaMalloc(&ix->d_terms, std::max<unsigned long long>(total, 1) * 4));
+        CU_TRY(cudaMalloc(&ix->d_tfs, std::max<unsigned long long>(total, 1) * 4));
+        CU_TRY(cudaMemcpy(ix->d_off, off.data(), (n + 1) * 8, cudaMemcpyHostToDevice));
+        if (total) {
+            CU_TRY(cudaMemcpy(ix->d_terms, terms.data(), total * 4, cudaMemcpyHostToDevice));
+            CU_TRY(cudaMemcpy(ix->d_tfs, tfs.data(), total * 4, cudaMemcpyHostToDevice));
+        }
+    } else {
+        // inverted index (CSR by term): rows are visited in ascending order, so every term's postings ascend by row
+        const size_t vocab = ix->df.size();
+        ix->poff.assign(vocab + 1, 0);
+        for (size_t t = 0; t < vocab; ++t) ix->poff[t + 1] = ix->poff[t] + ix->df[t];
+        const unsigned long long total = ix->poff[vocab];
+        std::vector<uint32_t> pdocs(total), ptfs(total);
+        std::vector<unsigned long long> cur(ix->poff.begin(), ix->poff.end() - 1);
+        for (uint64_t r = 0; r < n; ++r)
+            for (auto &p : ix->docs[r]) { const unsigned long long o = cur[p.first]++; pdocs[o] = static_cast<uint32_t>(r); ptfs[o] = p.second; }
+        CU_TRY(cudaMalloc(&ix->d_pdocs, std::max<unsigned long long>(total, 1) * 4));
+        CU_TRY(cudaMalloc(&ix->d_ptfs, std::max<unsigned long long>(total, 1) * 4));
+        if (total) {
+            CU_TRY(cudaMemcpy(ix->d_pdocs, pdocs.data(), total * 4, cudaMemcpyHostToDevice));
+            CU_TRY(cudaMemcpy(ix->d_ptfs, ptfs.data(), total * 4, cudaMemcpyHostToDevice));
+        }
+    }
     ix->dev_rows = n;
     ix->dirty = false;
     return RLR_OK;
@@ -384,7 +446,7 @@ int bm25_sync(rlr_bm25 *ix)
 // *active = false when the query cannot match anything (no terms / empty index): nothing is enqueued.
 int rlr_api_bm25_enqueue(rlr_bm25 *ix, void *ws_opaque, const uint32_t *query_terms, uint32_t n_terms, uint32_t limit,
                          uint32_t *d_lex_rows, float *d_lex_norm, uint32_t lex_pad, uint32_t *d_desc_rows, float *d_desc_scores,
-                         uint32_t *d_n, cudaStream_t st, bool *active, const rlr_api_bm25_global *gs)
+                         uint32_t *d_n, cudaStream_t st, bool *active, const rlr_api_bm25_global *gs, uint32_t *launches_out)
 {
     Bm25Ws *w = static_cast<Bm25Ws *>(ws_opaque);
     *active = false;
@@ -424,8 +486,31 @@ int rlr_api_bm25_enqueue(rlr_bm25 *ix, void *ws_opaque, const uint32_t *query_te
         w->keys_cap = s->capacity > n ? s->capacity : n;
     }
     CU_TRY(cudaMemsetAsync(w->d_sel, 0, sizeof(rlr::Bm25Sel), st));
-    rlr::bm25_score_kernel<<<(n + 255) / 256, 256, 0, st>>>(ix->d_off, ix->d_terms, ix->d_tfs, ix->d_doclen, n,
-                                                            static_cast<uint32_t>(s->row_base), q, w->d_keys);
+    uint32_t launches = 0;
+    if (!ix->inverted) {
+        rlr::bm25_score_kernel<<<(n + 255) / 256, 256, 0, st>>>(ix->d_off, ix->d_terms, ix->d_tfs, ix->d_doclen, n,
+                                                                static_cast<uint32_t>(s->row_base), q, w->d_keys);
+        launches = 1;
+    } else {
+        if (w->scores_cap < n) {
+            cudaFree(w->d_scores); w->d_scores = nullptr; w->scores_cap = 0;
+            CU_TRY(cudaMalloc(&w->d_scores, static_cast<size_t>(s->capacity > n ? s->capacity : n) * 4));
+            w->scores_cap = s->capacity > n ? s->capacity : n;
+        }
+        CU_TRY(cudaMemsetAsync(w->d_scores, 0xff, static_cast<size_t>(n) * 4, st));
+        for (uint32_t j = 0; j < q.n_terms; ++j) {                      // consecutive launches: the caller's term order per document
+            const uint32_t t = q.term[j];
+            if (t + 1 >= ix->poff.size()) continue;                     // a term no local document holds
+            const unsigned long long p_lo = ix->poff[t], p_hi = ix->poff[t + 1];
+            if (p_hi == p_lo) continue;
+            const unsigned long long blocks = (p_hi - p_lo + 255) / 256;
+            const uint32_t g = static_cast<uint32_t>(std::min<unsigned long long>(blocks, static_cast<unsigned long long>(s->sm_count) * 16ull));
+            rlr::bm25_term_pass_kernel<<<g, 256, 0, st>>>(ix->d_pdocs, ix->d_ptfs, p_lo, p_hi, ix->d_doclen, q.idf[j], q.avg_doc_len, w->d_scores);
+            ++launches;
+        }
+        rlr::bm25_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(w->d_scores, n, static_cast<uint32_t>(s->row_base), w->d_keys);
+        ++launches;
+    }
     const uint32_t grid = std::min<uint32_t>((n + 255) / 256, static_cast<uint32_t>(s->sm_count) * 4u);
     for (uint32_t pass = 0; pass < rlr::kPasses; ++pass)
         rlr::bm25_select_pass_kernel<<<grid, 256, 0, st>>>(w->d_keys, n, pass, limit, w->d_hist, w->d_sel);
@@ -445,6 +530,7 @@ int rlr_api_bm25_enqueue(rlr_bm25 *ix, void *ws_opaque, const uint32_t *query_te
                                                   d_desc_scores, d_n, d_lex_rows, d_lex_norm, lex_pad);
     CU_TRY(cudaGetLastError());
     *active = true;
+    if (launches_out) *launches_out = launches + rlr::kPasses + 2;
     return RLR_OK;
 }
 
@@ -456,7 +542,6 @@ int rlr_api_bm25_ws_acquire(rlr_bm25 *ix, void **out)
     return RLR_OK;
 }
 void rlr_api_bm25_ws_release(rlr_bm25 *ix, void *w) { ws_release(ix, static_cast<Bm25Ws *>(w)); }
-uint32_t rlr_api_bm25_launches() { return 1 + rlr::kPasses + 2; }
 rlr_store *rlr_api_bm25_store(rlr_bm25 *ix) { return ix->s; }
 
 RLR_EXPORT int rlr_bm25_create(rlr_store *s, rlr_bm25 **out)
@@ -475,7 +560,7 @@ RLR_EXPORT int rlr_bm25_destroy(rlr_bm25 *ix)
     if (!ix) return RLR_OK;
     cudaSetDevice(ix->device);
     for (Bm25Ws *w : ix->free_ws) ws_free(w);
-    cudaFree(ix->d_off); cudaFree(ix->d_terms); cudaFree(ix->d_tfs); cudaFree(ix->d_doclen);
+    cudaFree(ix->d_off); cudaFree(ix->d_terms); cudaFree(ix->d_tfs); cudaFree(ix->d_doclen); cudaFree(ix->d_pdocs); cudaFree(ix->d_ptfs);
     cudaGetLastError();
     delete ix;
     return RLR_OK;

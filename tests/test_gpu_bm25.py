@@ -41,6 +41,14 @@ def eng():
     return engine
 
 
+@pytest.fixture(autouse=True, params=["forward", "inverted"])
+def index_kind(request, monkeypatch):
+    """Every test runs over both device layouts: the forward index (CSR by row, small stores) and the inverted index
+    (CSR by term, one launch per query term; stores beyond 262144 rows).  The knob is read at each index (re)build."""
+    monkeypatch.setenv("RLR_BM25_INDEX", request.param)
+    return request.param
+
+
 def _build(eng, rows, docs, flags=0):
     store = eng.DeviceStore.from_rows(rows, flags=flags)
     ix = eng.DeviceLexicalIndex(store)
