@@ -15,6 +15,8 @@
 // thread per row walks the query terms in order and looks each up in the row's sorted (term, tf) list (a forward
 // index in CSR form), so `scores[doc] += contribution` happens in a fixed order per document.  idf needs ln(): it is
 // computed on the host with the C library's logf (what Rust's f32::ln calls), one value per query term.
+// Stores beyond kBm25InvertedMinRows keep the postings BY TERM instead and run one launch per query term, in the
+// caller's order (bm25_term_pass_kernel): only the query's postings are read, and the per-document order is the same.
 //
 // Then `results.sort_by(score desc); truncate(limit)` (:2222-2226) without sorting n keys: an exact radix select of
 // the limit-th largest rank key (score bits | ~row: ties go to the lower row, one of the reference's valid orders)
